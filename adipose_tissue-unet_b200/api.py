@@ -1,0 +1,436 @@
+"""Host-side mirror of the reference's inference seam.
+
+Same class names, method names, argument meaning and return types as
+Segmentation/full_evaluation_enhanced.py (AdiposeUNet :1156-1353,
+TestTimeAugmentation :522-600, GaussianBlender :115-183, LinearBlender :186-204,
+SlidingWindowInference :207-329, binarize_prediction :716-718,
+calculate_pixel_metrics :721-785) so that reconstruct_full_images.py /
+segmentation_inference.py style callers work unchanged — but every array
+operation runs in libadipose_b200.so on the GPU.  NumPy here is plumbing
+(buffers, slicing views, float64 ratios of four integers).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .layers import LAYER_NAMES, weight_shapes
+
+TTA_OPCODES = {"minimal": [0, 4], "basic": [0, 4, 5, 1], "full": [0, 1, 2, 3, 4, 5, 6, 7]}
+
+
+def _f32c(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Engine:
+    """Owner of one adp_engine handle (one GPU, one stream)."""
+
+    def __init__(self, precision: str = "bf16", device: int = 0, init_nb: int = 44, max_forwards: int = 16):
+        self.lib = _lib.load()
+        self.precision = precision
+        h = C.c_void_p()
+        _lib.check(self.lib.adp_create(device, _lib.PRECISIONS[precision], init_nb, max_forwards, C.byref(h)))
+        self.h = h
+        self.device = device
+        self.init_nb = init_nb
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.adp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights
+    def set_weights(self, weights: Dict[str, np.ndarray]):
+        """weights: '<layer>/kernel' (HWIO float32) and '<layer>/bias' per Keras layer name."""
+        for name in LAYER_NAMES:
+            k = _f32c(weights[name + "/kernel"])
+            b = _f32c(weights[name + "/bias"])
+            shp = (C.c_int64 * 4)(*k.shape)
+            _lib.check(self.lib.adp_set_weight(self.h, name.encode(), _lib.ptr(k), shp, _lib.ptr(b), b.size))
+
+    def get_weights(self) -> Dict[str, np.ndarray]:
+        out = {}
+        for name, (ks, bs) in weight_shapes(self.init_nb).items():
+            k = np.empty(ks, np.float32)
+            b = np.empty(bs, np.float32)
+            _lib.check(self.lib.adp_get_weight(self.h, name.encode(), _lib.ptr(k), k.size, _lib.ptr(b), b.size))
+            out[name + "/kernel"] = k
+            out[name + "/bias"] = b
+        return out
+
+    # ---- inference
+    def predict(self, tiles, mean: float, std: float, ops: Optional[Sequence[int]] = None, out=None):
+        """tiles: (n,S,S) float32 / uint8 (n,S,S) or (n,S,S,3); host ndarray or CUDA torch tensor.
+        Returns (n,S,S) float32 probabilities (ndarray, or `out` if given)."""
+        is_np = isinstance(tiles, np.ndarray)
+        shape = tuple(tiles.shape)
+        n, S = shape[0], shape[1]
+        assert shape[2] == S
+        ops = list(ops) if ops else []
+        ops_arr = _lib.int_array(ops) if ops else None
+        if out is None:
+            out = np.empty((n, S, S), np.float32)
+        dt = str(tiles.dtype)
+        if "uint8" in dt:
+            ch = shape[3] if len(shape) == 4 else 1
+            if is_np:
+                tiles = np.ascontiguousarray(tiles)
+            _lib.check(self.lib.adp_predict_u8(self.h, _lib.ptr(tiles), n, S, ch, mean, std, ops_arr, len(ops), _lib.ptr(out)))
+        else:
+            if is_np:
+                tiles = _f32c(tiles)
+            _lib.check(self.lib.adp_predict(self.h, _lib.ptr(tiles), n, S, mean, std, ops_arr, len(ops), _lib.ptr(out)))
+        return out
+
+    def debug_layer(self, name: str, idx: int = 0) -> np.ndarray:
+        shp = (C.c_int64 * 3)()
+        _lib.check(self.lib.adp_debug_layer(self.h, name.encode(), idx, None, 0, shp))
+        out = np.empty(tuple(shp), np.float32)
+        _lib.check(self.lib.adp_debug_layer(self.h, name.encode(), idx, _lib.ptr(out), out.size, shp))
+        return out
+
+    def tta_combine(self, planes: np.ndarray, ops: Sequence[int]) -> np.ndarray:
+        planes = _f32c(planes)
+        k, S, _ = planes.shape
+        out = np.empty((S, S), np.float32)
+        _lib.check(self.lib.adp_tta_combine(self.h, _lib.ptr(planes), S, _lib.int_array(list(ops)), k, _lib.ptr(out)))
+        return out
+
+    def threshold_metrics(self, prob, gt=None, threshold: float = 0.5, want_mask: bool = True):
+        n = int(np.prod(prob.shape))
+        if isinstance(prob, np.ndarray):
+            prob = _f32c(prob)
+        mask = np.empty(prob.shape, np.uint8) if want_mask else None
+        counts = (C.c_int64 * 4)()
+        g = None
+        if gt is not None:
+            g = np.ascontiguousarray((np.asarray(gt) > 0.5).astype(np.uint8)) if isinstance(gt, np.ndarray) else gt
+        _lib.check(self.lib.adp_threshold_metrics(self.h, _lib.ptr(prob), _lib.ptr(g), n, threshold, _lib.ptr(mask), counts))
+        return mask, tuple(int(c) for c in counts)
+
+    def blend(self, mode: int, tiles: Sequence[np.ndarray], positions, output_shape, window: Optional[np.ndarray]):
+        h, w = int(output_shape[0]), int(output_shape[1])
+        out = np.empty((h, w), np.float32)
+        n = len(tiles)
+        if n == 0:
+            out[:] = 0
+            return out
+        th, tw = tiles[0].shape[:2]
+        if any(t.shape[:2] != (th, tw) for t in tiles):
+            raise ValueError("all tiles must have the same shape")
+        arr = _f32c(np.stack(tiles)) if not (isinstance(tiles, np.ndarray) and tiles.ndim == 3) else _f32c(tiles)
+        ys = np.ascontiguousarray([p[0] for p in positions], dtype=np.int32)
+        xs = np.ascontiguousarray([p[1] for p in positions], dtype=np.int32)
+        win = None
+        if window is not None:
+            win = _f32c(window[:th, :tw])
+        _lib.check(self.lib.adp_blend_reconstruct(self.h, mode, _lib.ptr(arr), n, th, tw, _lib.ptr(ys), _lib.ptr(xs),
+                                                  _lib.ptr(win), h, w, _lib.ptr(out)))
+        return out
+
+    def loss_metrics(self, p, y, want_grad: bool = False):
+        p = _f32c(p); y = _f32c(y)
+        out = (C.c_double * 4)()
+        g = np.empty(p.shape, np.float32) if want_grad else None
+        _lib.check(self.lib.adp_loss_metrics(self.h, _lib.ptr(p), _lib.ptr(y), p.size, _lib.ptr(g), out))
+        res = dict(loss=out[0], bce=out[1], dice_loss=out[2], dice_coef=out[3])
+        return (res, g) if want_grad else res
+
+    # ---- whole-slide accumulator
+    def wsi_begin(self, rows, W, y0, tile, mode, window):
+        win = _f32c(window) if window is not None else None
+        _lib.check(self.lib.adp_wsi_begin(self.h, rows, W, y0, tile, mode, _lib.ptr(win)))
+
+    def wsi_push_tiles(self, tiles, ys, xs, mean, std, ops):
+        if isinstance(tiles, np.ndarray):
+            tiles = _f32c(tiles)
+        ys = np.ascontiguousarray(ys, dtype=np.int32); xs = np.ascontiguousarray(xs, dtype=np.int32)
+        ops = list(ops) if ops else []
+        _lib.check(self.lib.adp_wsi_push_tiles(self.h, _lib.ptr(tiles), len(ys), _lib.ptr(ys), _lib.ptr(xs), mean, std,
+                                               _lib.int_array(ops) if ops else None, len(ops)))
+
+    def wsi_push_from_slide(self, slide_dev, region_y0, region_rows, ys, xs, mean, std, ops):
+        ys = np.ascontiguousarray(ys, dtype=np.int32); xs = np.ascontiguousarray(xs, dtype=np.int32)
+        ops = list(ops) if ops else []
+        _lib.check(self.lib.adp_wsi_push_from_slide(self.h, _lib.ptr(slide_dev), region_y0, region_rows, len(ys),
+                                                    _lib.ptr(ys), _lib.ptr(xs), mean, std,
+                                                    _lib.int_array(ops) if ops else None, len(ops)))
+
+    def wsi_push_probs(self, probs, ys, xs):
+        probs = _f32c(probs)
+        ys = np.ascontiguousarray(ys, dtype=np.int32); xs = np.ascontiguousarray(xs, dtype=np.int32)
+        _lib.check(self.lib.adp_wsi_push_probs(self.h, _lib.ptr(probs), len(ys), _lib.ptr(ys), _lib.ptr(xs)))
+
+    def wsi_export(self, y, rows, W):
+        acc = np.empty((rows, W), np.float32); wt = np.empty((rows, W), np.float32)
+        _lib.check(self.lib.adp_wsi_export(self.h, y, rows, _lib.ptr(acc), _lib.ptr(wt)))
+        return acc, wt
+
+    def wsi_import_add(self, y, acc, wt):
+        acc = _f32c(acc); wt = _f32c(wt)
+        _lib.check(self.lib.adp_wsi_import_add(self.h, y, acc.shape[0], _lib.ptr(acc), _lib.ptr(wt)))
+
+    def wsi_finalize(self, y, rows, W, threshold=0.5, gt=None, want_prob=True, want_mask=True):
+        prob = np.empty((rows, W), np.float32) if want_prob else None
+        mask = np.empty((rows, W), np.uint8) if want_mask else None
+        counts = (C.c_int64 * 4)()
+        g = np.ascontiguousarray((np.asarray(gt) > 0.5).astype(np.uint8)) if gt is not None else None
+        _lib.check(self.lib.adp_wsi_finalize(self.h, y, rows, threshold, _lib.ptr(prob), _lib.ptr(mask), _lib.ptr(g), counts))
+        return prob, mask, tuple(int(c) for c in counts)
+
+    def wsi_end(self):
+        _lib.check(self.lib.adp_wsi_end(self.h))
+
+    # ---- profiling
+    def profile(self, on: bool):
+        self.lib.adp_profile_enable(self.h, 1 if on else 0)
+        if on:
+            self.lib.adp_profile_reset(self.h)
+
+    def profile_rows(self) -> List[dict]:
+        rows = (_lib.ProfRow * 64)()
+        n = self.lib.adp_profile_read(self.h, rows, 64)
+        return [dict(name=rows[i].name.decode(), launches=rows[i].launches, ms=rows[i].ms, flops=rows[i].flops,
+                     bytes=rows[i].bytes) for i in range(n)]
+
+    def launch_count(self) -> int:
+        return int(self.lib.adp_launch_count(self.h))
+
+    def synchronize(self):
+        _lib.check(self.lib.adp_synchronize(self.h))
+
+
+_default_engine: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    """Engine used by the stateless reference-style objects (blenders, metrics)."""
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(precision="fp32", max_forwards=8)
+    return _default_engine
+
+
+# =====================================================================================
+# Reference-shaped objects
+# =====================================================================================
+class AdiposeUNet:
+    """Drop-in for full_evaluation_enhanced.AdiposeUNet / segmentation_inference.AdiposeUNet."""
+
+    def __init__(self, precision: str = "bf16", device: int = 0, max_forwards: int = 16):
+        self.net = None
+        self.use_deep_supervision = False
+        self._precision, self._device, self._max_forwards = precision, device, max_forwards
+        self.engine: Optional[Engine] = None
+
+    def build_model(self, init_nb: int = 44, dropout_rate: float = 0.3, use_deep_supervision: bool = False):
+        # Dropout is identity at inference; the deep-supervision heads do not feed main_out
+        # (full_evaluation_enhanced.py:1313-1319 only ever returns 'main_out').
+        self.use_deep_supervision = use_deep_supervision
+        self.engine = Engine(self._precision, self._device, init_nb, self._max_forwards)
+        self.net = self.engine
+        return self.net
+
+    def set_weights(self, weights: Dict[str, np.ndarray]):
+        self.engine.set_weights(weights)
+
+    def load_weights(self, weights_path: str):
+        from .weights_io import load_weights_file
+        self.engine.set_weights(load_weights_file(weights_path, self.engine.init_nb))
+        print(f"✓ Loaded weights from {weights_path}")
+
+    def predict_single(self, image: np.ndarray, mean: float, std: float) -> np.ndarray:
+        return self.engine.predict(np.asarray(image)[None], float(mean), float(std))[0]
+
+    def predict_batch(self, tiles, mean: float, std: float, tta_mode: Optional[str] = None):
+        ops = TTA_OPCODES[tta_mode] if tta_mode else None
+        return self.engine.predict(tiles, float(mean), float(std), ops)
+
+    def predict(self, image: np.ndarray, mean: float, std: float, use_tta: bool = False,
+                tta_mode: str = "basic") -> Tuple[np.ndarray, dict]:
+        start = time.time()
+        if not use_tta:
+            pred = self.predict_single(image, mean, std)
+            return pred, {"num_augmentations": 1, "total_time": time.time() - start, "tta_enabled": False}
+        pred, timing = TestTimeAugmentation(mode=tta_mode).predict_with_tta(self, image, mean, std)
+        timing["tta_enabled"] = True
+        timing["tta_mode"] = tta_mode
+        return pred, timing
+
+
+class TestTimeAugmentation:
+    """full_evaluation_enhanced.TestTimeAugmentation (:522-600).  For the native model the
+    eight forwards, the inverse dihedral ops and the mean run as one device batch; for any other
+    object with predict_single (the reference's ONNX seam) the per-augmentation predictions are
+    de-augmented and averaged by the device kernel."""
+    __test__ = False
+
+    def __init__(self, mode: str = "basic"):
+        mode = (mode or "basic").lower()
+        if mode not in TTA_OPCODES:
+            mode = "basic"
+        self.mode = mode
+        self.ops = TTA_OPCODES[mode]
+        self.transforms = [(_aug_fn(op), _aug_fn(_INV[op])) for op in self.ops]
+
+    def predict_with_tta(self, model_wrapper: Any, image: np.ndarray, mean: float, std: float):
+        start = time.time()
+        if isinstance(model_wrapper, AdiposeUNet):
+            avg = model_wrapper.engine.predict(np.asarray(image)[None], float(mean), float(std), self.ops)[0]
+        else:
+            planes = [np.asarray(model_wrapper.predict_single(aug(image), mean, std), dtype=np.float32)
+                      for aug, _ in self.transforms]
+            avg = default_engine().tta_combine(np.stack(planes), self.ops)
+        return avg, {"num_augmentations": len(self.ops), "total_time": time.time() - start}
+
+
+_INV = [0, 3, 2, 1, 4, 5, 6, 7]
+
+
+def _aug_fn(op: int):
+    """NumPy *view* of the dihedral op (host plumbing for foreign models only)."""
+    fns = {0: lambda x: x, 1: lambda x: np.rot90(x, 1), 2: lambda x: np.rot90(x, 2), 3: lambda x: np.rot90(x, 3),
+           4: lambda x: np.flip(x, axis=1), 5: lambda x: np.flip(x, axis=0),
+           6: lambda x: np.flip(np.rot90(x, 1), axis=1), 7: lambda x: np.flip(np.rot90(x, 1), axis=0)}
+    return fns[op]
+
+
+class GaussianBlender:
+    """full_evaluation_enhanced.GaussianBlender (:115-183)."""
+
+    def __init__(self, tile_size: int = 1024, sigma_factor: float = 0.25, engine: Optional[Engine] = None):
+        self.tile_size = tile_size
+        self.sigma = tile_size * sigma_factor
+        self.weight_map = self._create_gaussian_weight_map()
+        self._engine = engine
+
+    def _create_gaussian_weight_map(self) -> np.ndarray:
+        # float64 -> /max -> float32, centre = tile/2 (:133-147); 4 MB computed once on the host
+        center = self.tile_size / 2
+        y, x = np.ogrid[0:self.tile_size, 0:self.tile_size]
+        w = np.exp(-((x - center) ** 2 + (y - center) ** 2) / (2 * self.sigma ** 2))
+        return (w / w.max()).astype(np.float32)
+
+    def reconstruct(self, tiles, positions, output_shape) -> np.ndarray:
+        eng = self._engine or default_engine()
+        return eng.blend(_lib.BLEND_GAUSSIAN, tiles, positions, output_shape, self.weight_map)
+
+
+class LinearBlender:
+    """full_evaluation_enhanced.LinearBlender (:186-204)."""
+
+    def __init__(self, engine: Optional[Engine] = None):
+        self._engine = engine
+
+    def reconstruct(self, tiles, positions, output_shape) -> np.ndarray:
+        eng = self._engine or default_engine()
+        return eng.blend(_lib.BLEND_LINEAR, tiles, positions, output_shape, None)
+
+
+class SlidingWindowInference:
+    """full_evaluation_enhanced.SlidingWindowInference (:207-329)."""
+
+    def __init__(self, tile_size: int = 1024, overlap: float = 0.5, blend_mode: str = "gaussian", verbose: bool = True):
+        self.tile_size = tile_size
+        self.overlap = max(0.0, min(overlap, 0.75))
+        self.stride = int(tile_size * (1 - self.overlap))
+        self.blend_mode = blend_mode
+        if blend_mode == "gaussian":
+            self.blender = GaussianBlender(tile_size)
+        elif blend_mode == "linear":
+            self.blender = LinearBlender()
+        else:
+            self.blender = None
+        if verbose:
+            print(f"[SlidingWindow] Initialized: tile={tile_size}, stride={self.stride}, "
+                  f"overlap={overlap:.1%}, blend={blend_mode}")
+
+    def extract_tile_positions(self, image_shape) -> List[Tuple[int, int]]:
+        h, w = image_shape[:2]
+        t, s = self.tile_size, self.stride
+        positions = []
+        y_steps = max(1, math.ceil((h - t) / s) + 1)
+        x_steps = max(1, math.ceil((w - t) / s) + 1)
+        for yi in range(y_steps):
+            for xi in range(x_steps):
+                y = min(yi * s, h - t)
+                x = min(xi * s, w - t)
+                if y >= 0 and x >= 0 and y + t <= h and x + t <= w:
+                    positions.append((y, x))
+        return positions
+
+    def extract_tiles(self, image: np.ndarray):
+        positions = self.extract_tile_positions(image.shape)
+        t = self.tile_size
+        return [image[y:y + t, x:x + t] for y, x in positions], positions
+
+    def predict_with_sliding_window(self, image: np.ndarray, model, mean: float, std: float, use_tta: bool = False,
+                                    tta_mode: str = "basic") -> np.ndarray:
+        tiles, positions = self.extract_tiles(image)
+        h, w = image.shape[:2]
+        gaussian = isinstance(self.blender, GaussianBlender)
+        if isinstance(model, AdiposeUNet):
+            eng = model.engine
+            ops = TTA_OPCODES[tta_mode if tta_mode in TTA_OPCODES else "basic"] if use_tta else None
+            eng.wsi_begin(h, w, 0, self.tile_size, _lib.BLEND_GAUSSIAN if gaussian else _lib.BLEND_LINEAR,
+                          self.blender.weight_map if gaussian else None)
+            try:
+                step = 16
+                for i in range(0, len(tiles), step):
+                    chunk = np.stack([np.asarray(t, dtype=np.float32) for t in tiles[i:i + step]])
+                    pos = positions[i:i + step]
+                    eng.wsi_push_tiles(chunk, [p[0] for p in pos], [p[1] for p in pos], float(mean), float(std), ops)
+                prob, _, _ = eng.wsi_finalize(0, h, w, want_mask=False)
+            finally:
+                eng.wsi_end()
+            return prob
+        preds = []
+        for tile in tiles:
+            if use_tta:
+                pred, _ = TestTimeAugmentation(mode=tta_mode).predict_with_tta(model, tile, mean, std)
+            else:
+                pred = model.predict_single(tile, mean, std)
+            preds.append(np.asarray(pred, dtype=np.float32))
+        blender = self.blender if self.blender is not None else LinearBlender()
+        return blender.reconstruct(preds, positions, (h, w))
+
+
+def binarize_prediction(pred: np.ndarray, threshold: float = 0.5, engine: Optional[Engine] = None) -> np.ndarray:
+    """full_evaluation_enhanced.binarize_prediction (:716-718)."""
+    mask, _ = (engine or default_engine()).threshold_metrics(pred, None, threshold)
+    return mask
+
+
+def metrics_from_counts(tp: int, fp: int, fn: int, tn: int) -> Dict[str, float]:
+    """Ratios of full_evaluation_enhanced.calculate_pixel_metrics (:735-785) from the four counts."""
+    if tp == 0 and fp == 0 and fn == 0:
+        return {"dice_score": 1.0, "jaccard_index": 1.0, "sensitivity": 1.0, "specificity": 1.0, "precision": 1.0,
+                "f1_score": 1.0, "accuracy": 1.0, "tp": 0, "fp": 0, "fn": 0, "tn": int(tn)}
+    precision = tp / (tp + fp + 1e-10)
+    sensitivity = tp / (tp + fn + 1e-10)
+    specificity = tn / (tn + fp + 1e-10)
+    accuracy = (tp + tn) / (tp + fp + fn + tn + 1e-10)
+    f1 = 2 * tp / (2 * tp + fp + fn + 1e-10)
+    jaccard = tp / (tp + fp + fn + 1e-10)
+    return {"dice_score": float(f1), "jaccard_index": float(jaccard), "sensitivity": float(sensitivity),
+            "specificity": float(specificity), "precision": float(precision), "f1_score": float(f1),
+            "accuracy": float(accuracy), "tp": int(tp), "fp": int(fp), "fn": int(fn), "tn": int(tn)}
+
+
+def calculate_pixel_metrics(pred: np.ndarray, true: np.ndarray, threshold: float = 0.5,
+                            engine: Optional[Engine] = None) -> Dict[str, float]:
+    """full_evaluation_enhanced.calculate_pixel_metrics (:721-785): counts on the device, ratios here."""
+    _, (tp, fp, fn, tn) = (engine or default_engine()).threshold_metrics(pred, true, threshold, want_mask=False)
+    return metrics_from_counts(tp, fp, fn, tn)

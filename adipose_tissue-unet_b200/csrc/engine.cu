@@ -1,0 +1,1100 @@
+// engine.cu — libadipose_b200.so: engine object, weight packing, forward orchestration and the
+// C ABI of include/adipose_b200.h.  Host code is plain C++17 + CUDA runtime; the only driver API
+// symbol (cuTensorMapEncodeTiled) is resolved at run time so the library loads on a CPU-only box.
+#include "../../include/adipose_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "kernels_post.cuh"
+#include "kernels_simt.cuh"
+
+using namespace adp;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    ADP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) throw Error(ADP_ECUDA, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    release();
+    ADP_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+  }
+  ~DevBuf() { release(); }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+bool is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
+
+struct FwTable {          // per-launch forward table, passed by value
+  int tile[64];
+  int op[64];
+  long long origin[64];
+};
+
+__global__ void fw_table_store(FwTable t, int *tile, int *op, long long *origin, int n) {
+  int i = threadIdx.x;
+  if (i < n) { tile[i] = t.tile[i]; op[i] = t.op[i]; origin[i] = t.origin[i]; }
+}
+
+struct ProfEntry { int64_t launches = 0; double ms = 0, flops = 0, bytes = 0; };
+
+struct HostWeight { std::vector<float> k; int64_t shape[4] = {0, 0, 0, 0}; std::vector<float> b; bool set = false; };
+
+struct ConvLayer {
+  std::string name;
+  int cin, cout, dil;          // real channels
+  bool up = false;             // input is UpSampling2D(2x2) of the source buffer
+  int skip = 0;                // >0: concat-fed; first `skip` real input channels come from the skip path
+  int cin_pad = 0, cout_pad = 0;
+  DevBuf w_simt, bias, w_tc;   // [9][cin_pad][cout_pad] fp32 | [cout_pad] fp32 | packed bf16 blocks
+  ConvTcParams tc{};           // geometry-independent part filled at pack time
+  bool tc_ready = false;
+};
+
+}  // namespace
+
+struct adp_engine {
+  int device = 0, prec = 0, init_nb = 44, max_fw = 16;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  int c[4], cp[4];                 // real / padded channel counts at the four levels
+  std::map<std::string, HostWeight> hw;
+  std::vector<ConvLayer> layers;   // the 20 generic 3x3 convs (all but down1_conv1 and the head)
+  DevBuf w_first, b_first, w_head, b_head;
+  bool packed = false;
+
+  // activation arena for tile size S
+  int S = 0;
+  size_t esz = 4;
+  DevBuf a1, cat1, b1, pl1, a2, cat2, b2, pl2, a3, cat3, b3, pl3, t[6], ts, prob;
+  DevBuf in_stage, out_stage, fwt_tile, fwt_op, fwt_origin;
+  std::map<std::string, CUtensorMap> tmaps;
+  int last_nfw = 0;
+
+  // whole-slide accumulator
+  bool wsi_on = false;
+  int wsi_rows = 0, wsi_W = 0, wsi_y0 = 0, wsi_tile = 0, wsi_mode = 0;
+  DevBuf wsi_acc, wsi_wsum, wsi_window, counts, misc;
+
+  // profiling
+  bool prof = false;
+  std::map<std::string, ProfEntry> prof_rows;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+  int dbg = 0;
+
+  template <typename F> void launch(const char *kind, double flops, double bytes, F &&f) {
+    if (prof) ADP_CUDA(cudaEventRecord(ev0, stream));
+    f();
+    ADP_CUDA(cudaGetLastError());
+    ++launches;
+    if (prof) {
+      ADP_CUDA(cudaEventRecord(ev1, stream));
+      ADP_CUDA(cudaEventSynchronize(ev1));
+      float ms = 0;
+      ADP_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+      auto &r = prof_rows[kind];
+      r.launches++; r.ms += ms; r.flops += flops; r.bytes += bytes;
+    }
+  }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// graph description (train_adipose_unet_v3.py:668-709)
+void build_layers(adp_engine *e) {
+  const int c1 = e->c[0], c2 = e->c[1], c4 = e->c[2], c8 = e->c[3];
+  auto add = [&](const char *n, int ci, int co, int d, bool up, int skip) {
+    ConvLayer L;
+    L.name = n; L.cin = ci; L.cout = co; L.dil = d; L.up = up; L.skip = skip;
+    L.cout_pad = pad16(co);
+    L.cin_pad = skip ? 2 * pad16(skip) : pad16(ci);
+    e->layers.push_back(std::move(L));
+  };
+  add("down1_conv2", c1, c1, 1, false, 0);
+  add("down2_conv1", c1, c2, 1, false, 0);
+  add("down2_conv2", c2, c2, 1, false, 0);
+  add("down3_conv1", c2, c4, 1, false, 0);
+  add("down3_conv2", c4, c4, 1, false, 0);
+  add("dilate1", c4, c8, 1, false, 0);
+  add("dilate2", c8, c8, 2, false, 0);
+  add("dilate3", c8, c8, 4, false, 0);
+  add("dilate4", c8, c8, 8, false, 0);
+  add("dilate5", c8, c8, 16, false, 0);
+  add("dilate6", c8, c8, 32, false, 0);
+  add("up3_conv1", c8, c4, 1, true, 0);
+  add("up3_conv2", c8, c4, 1, false, c4);
+  add("up3_conv3", c4, c4, 1, false, 0);
+  add("up2_conv1", c4, c2, 1, true, 0);
+  add("up2_conv2", c4, c2, 1, false, c2);
+  add("up2_conv3", c2, c2, 1, false, 0);
+  add("up1_conv1", c2, c1, 1, true, 0);
+  add("up1_conv2", c2, c1, 1, false, c1);
+  add("up1_conv3", c1, c1, 1, false, 0);
+}
+
+ConvLayer &layer(adp_engine *e, const std::string &n) {
+  for (auto &L : e->layers)
+    if (L.name == n) return L;
+  throw Error(ADP_EINVAL, "unknown layer " + n);
+}
+
+const char *const kAllNames[22] = {"down1_conv1", "down1_conv2", "down2_conv1", "down2_conv2", "down3_conv1",
+                                   "down3_conv2", "dilate1", "dilate2", "dilate3", "dilate4", "dilate5", "dilate6",
+                                   "up3_conv1", "up3_conv2", "up3_conv3", "up2_conv1", "up2_conv2", "up2_conv3",
+                                   "up1_conv1", "up1_conv2", "up1_conv3", "output_softmax"};
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 plan: everything of ConvTcParams that does not depend on the tile size
+void plan_tc(ConvLayer &L) {
+  ConvTcParams &p = L.tc;
+  memset(&p, 0, sizeof(p));
+  const int N = (L.cout_pad <= 256) ? L.cout_pad : L.cout_pad / 2;
+  const int nsplit = L.cout_pad / N;            // 1, or 2 for the 352-wide bottleneck
+  ADP_REQUIRE(N % 16 == 0 && N <= 256 && nsplit <= 2, "unsupported output channel count for tcgen05 path");
+  p.N = N;
+  int T = (N <= 64) ? 4 : (N <= 128 ? 2 : 1);
+  if (L.dil > 1) T = 1;
+  p.T = T;
+  if (L.up) {
+    // four output parities, 2x2 taps each (see conv_tc.cuh)
+    p.nvar = 4; p.ntaps = 4; p.nbox = 1; p.BR = T + 1; p.PW = 129; p.oscale = 2;
+    for (int v = 0; v < 4; ++v) {
+      const int py = v >> 1, px = v & 1;
+      p.var[v].y0 = py - 1; p.var[v].x0 = px - 1; p.var[v].oy = py; p.var[v].ox = px;
+      p.var[v].bias_off = 0; p.var[v].out_coff = 0;
+    }
+    for (int t = 0; t < 4; ++t) { p.tap_box[t] = 0; p.tap_row[t] = t >> 1; p.tap_xs[t] = t & 1; }
+    p.box_dy[0] = 0;
+  } else {
+    p.nvar = nsplit; p.ntaps = 9; p.oscale = 1;
+    for (int v = 0; v < nsplit; ++v) {
+      p.var[v].y0 = -L.dil; p.var[v].x0 = -L.dil; p.var[v].oy = 0; p.var[v].ox = 0;
+      p.var[v].bias_off = v * N; p.var[v].out_coff = v * N;
+    }
+    p.PW = 128 + 2 * L.dil;
+    if (L.dil == 1) {
+      p.nbox = 1; p.BR = T + 2; p.box_dy[0] = 0;
+      for (int t = 0; t < 9; ++t) { p.tap_box[t] = 0; p.tap_row[t] = t / 3; p.tap_xs[t] = t % 3; }
+    } else {
+      p.nbox = 3; p.BR = T;
+      for (int b = 0; b < 3; ++b) p.box_dy[b] = b * L.dil;
+      for (int t = 0; t < 9; ++t) { p.tap_box[t] = t / 3; p.tap_row[t] = 0; p.tap_xs[t] = (t % 3) * L.dil; }
+    }
+  }
+  // channel chunk: largest divisor (in units of 16) that fits the shared-memory budget
+  const int k16 = L.cin_pad / 16;
+  const size_t budget = 200 * 1024;
+  int best = 1;
+  for (int k = k16; k >= 1; --k) {
+    if (k16 % k) continue;
+    size_t a = (size_t)p.nbox * (((size_t)p.BR * (2 * k) * p.PW * 16 + 127) / 128 * 128);
+    a = (a + 1023) / 1024 * 1024;
+    size_t b = ((size_t)16 * k * N * 2 + 127) / 128 * 128;
+    if (2 * a + 4 * b <= budget && a <= 80 * 1024) { best = k; break; }
+  }
+  const int KC = 16 * best;
+  p.CG = KC / 8; p.nchunks = k16 / best;
+  p.a_box_stride = (uint32_t)(((size_t)p.BR * p.CG * p.PW * 16 + 127) / 128 * 128);
+  p.a_stride = (uint32_t)(((size_t)p.nbox * p.a_box_stride + 1023) / 1024 * 1024);
+  p.a_tx_bytes = (uint32_t)((size_t)p.nbox * p.BR * p.CG * p.PW * 16);
+  p.b_bytes = (uint32_t)((size_t)KC * N * 2);
+  p.b_stride = (p.b_bytes + 127) / 128 * 128;
+  p.SB = (int)std::min<size_t>(8, std::max<size_t>(3, (32 * 1024) / p.b_stride));
+  size_t rest = budget - (size_t)p.SB * p.b_stride;
+  p.SA = (int)std::min<size_t>(4, std::max<size_t>(2, rest / p.a_stride));
+  p.idesc = ptx::make_idesc(128, N, 1);
+  p.relu = 1;
+  for (int v = 0; v < p.nvar; ++v) p.var[v].wbase = v * p.nchunks * p.ntaps;
+}
+
+size_t tc_smem_bytes(const ConvTcParams &p) {
+  return (size_t)p.SA * p.a_stride + (size_t)p.SB * p.b_stride + (2 * p.SA + 2 * p.SB + 4) * 8 + 16;
+}
+
+// Effective padded fp32 weights wp[9][cin_pad][cout_pad] (concat layers: skip channels land in
+// [0, pad16(skip)), upsampled-path channels in [pad16(skip), ...)) — Appendix A of SURVEY.md.
+std::vector<float> padded_weights(const ConvLayer &L, const HostWeight &h, bool round_bf16) {
+  std::vector<float> wp((size_t)9 * L.cin_pad * L.cout_pad, 0.f);
+  const int sp = L.skip ? pad16(L.skip) : 0;
+  for (int t = 0; t < 9; ++t)
+    for (int ci = 0; ci < L.cin; ++ci) {
+      const int cip = (L.skip && ci >= L.skip) ? sp + (ci - L.skip) : ci;
+      for (int co = 0; co < L.cout; ++co) {
+        float v = h.k[((size_t)t * L.cin + ci) * L.cout + co];
+        wp[((size_t)t * L.cin_pad + cip) * L.cout_pad + co] = round_bf16 ? bf16_round(v) : v;
+      }
+    }
+  return wp;
+}
+
+void pack_layer(adp_engine *e, ConvLayer &L) {
+  const HostWeight &h = e->hw.at(L.name);
+  const bool bf = e->prec != ADP_PREC_FP32;
+  // SIMT weights + bias (bias stays fp32 on every path)
+  std::vector<float> wp = padded_weights(L, h, bf);
+  L.w_simt.ensure(wp.size() * 4);
+  ADP_CUDA(cudaMemcpy(L.w_simt.p, wp.data(), wp.size() * 4, cudaMemcpyHostToDevice));
+  std::vector<float> bp(L.cout_pad, 0.f);
+  std::copy(h.b.begin(), h.b.end(), bp.begin());
+  L.bias.ensure(bp.size() * 4);
+  ADP_CUDA(cudaMemcpy(L.bias.p, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
+  if (e->prec != ADP_PREC_BF16) return;
+
+  plan_tc(L);
+  const ConvTcParams &p = L.tc;
+  std::vector<float> w32 = padded_weights(L, h, false);   // sum taps in fp32, round once
+  auto W = [&](int t, int ci, int co) -> float { return w32[((size_t)t * L.cin_pad + ci) * L.cout_pad + co]; };
+  const int KC = p.CG * 8, N = p.N;
+  const size_t blk = (size_t)KC * N;
+  std::vector<__nv_bfloat16> pk((size_t)p.nvar * p.nchunks * p.ntaps * blk);
+  for (int v = 0; v < p.nvar; ++v)
+    for (int c = 0; c < p.nchunks; ++c)
+      for (int t = 0; t < p.ntaps; ++t) {
+        __nv_bfloat16 *dst = pk.data() + ((size_t)p.var[v].wbase + (size_t)c * p.ntaps + t) * blk;
+        for (int g = 0; g < p.CG; ++g)
+          for (int n = 0; n < N; ++n)
+            for (int j = 0; j < 8; ++j) {
+              const int ci = c * KC + g * 8 + j;
+              float val = 0.f;
+              if (ci < L.cin_pad) {
+                if (L.up) {
+                  // parity (py,px), tap (ry,rx) in {0,1}^2: sum of the 3x3 taps that read this source pixel
+                  const int py = v >> 1, px = v & 1, ry = t >> 1, rx = t & 1;
+                  for (int ky = 0; ky < 3; ++ky) {
+                    const int sy = (py + ky - 1) >= 0 ? (py + ky - 1) / 2 : -1;   // floor((py+ky-1)/2)
+                    if (sy - (py - 1) != ry) continue;
+                    for (int kx = 0; kx < 3; ++kx) {
+                      const int sx = (px + kx - 1) >= 0 ? (px + kx - 1) / 2 : -1;
+                      if (sx - (px - 1) != rx) continue;
+                      val += W(ky * 3 + kx, ci, n);
+                    }
+                  }
+                } else {
+                  val = W(t, ci, p.var[v].out_coff + n);
+                }
+              }
+              dst[((size_t)g * N + n) * 8 + j] = __float2bfloat16_rn(val);
+            }
+      }
+  L.w_tc.ensure(pk.size() * 2);
+  ADP_CUDA(cudaMemcpy(L.w_tc.p, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+  L.tc_ready = true;
+}
+
+void pack_all(adp_engine *e) {
+  for (const char *n : kAllNames)
+    if (!e->hw.count(n) || !e->hw[n].set) throw Error(ADP_ESTATE, std::string("weights of layer ") + n + " not set");
+  const bool bf = e->prec != ADP_PREC_FP32;
+  // first conv: [9][cp0]; never rounded (computed in fp32 from the fp32 image on every path)
+  {
+    const HostWeight &h = e->hw["down1_conv1"];
+    std::vector<float> w((size_t)9 * e->cp[0], 0.f), b(e->cp[0], 0.f);
+    for (int t = 0; t < 9; ++t)
+      for (int co = 0; co < e->c[0]; ++co) w[(size_t)t * e->cp[0] + co] = h.k[(size_t)t * e->c[0] + co];
+    std::copy(h.b.begin(), h.b.end(), b.begin());
+    e->w_first.ensure(w.size() * 4); e->b_first.ensure(b.size() * 4);
+    ADP_CUDA(cudaMemcpy(e->w_first.p, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    ADP_CUDA(cudaMemcpy(e->b_first.p, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+  }
+  {
+    const HostWeight &h = e->hw["output_softmax"];   // (1,1,c1,2)
+    std::vector<float> w((size_t)2 * e->cp[0], 0.f);
+    for (int ci = 0; ci < e->c[0]; ++ci)
+      for (int k = 0; k < 2; ++k) w[(size_t)k * e->cp[0] + ci] = h.k[(size_t)ci * 2 + k];
+    e->w_head.ensure(w.size() * 4); e->b_head.ensure(8);
+    ADP_CUDA(cudaMemcpy(e->w_head.p, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    ADP_CUDA(cudaMemcpy(e->b_head.p, h.b.data(), 8, cudaMemcpyHostToDevice));
+  }
+  (void)bf;
+  for (auto &L : e->layers) pack_layer(e, L);
+  e->packed = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// activation arena
+void ensure_arena(adp_engine *e, int S) {
+  if (e->S == S) return;
+  ADP_REQUIRE(S >= 8 && S % 8 == 0 && S <= 8192, "tile size must be a multiple of 8");
+  const size_t es = e->esz, nf = e->max_fw;
+  const size_t s1 = (size_t)S * S, s2 = s1 / 4, s3 = s1 / 16, s4 = s1 / 64;
+  const int *cp = e->cp;
+  e->a1.ensure(nf * s1 * cp[0] * es);   e->b1.ensure(nf * s1 * cp[0] * es);   e->cat1.ensure(nf * s1 * 2 * cp[0] * es);
+  e->pl1.ensure(nf * s2 * cp[0] * es);
+  e->a2.ensure(nf * s2 * cp[1] * es);   e->b2.ensure(nf * s2 * cp[1] * es);   e->cat2.ensure(nf * s2 * 2 * cp[1] * es);
+  e->pl2.ensure(nf * s3 * cp[1] * es);
+  e->a3.ensure(nf * s3 * cp[2] * es);   e->b3.ensure(nf * s3 * cp[2] * es);   e->cat3.ensure(nf * s3 * 2 * cp[2] * es);
+  e->pl3.ensure(nf * s4 * cp[2] * es);
+  for (int i = 0; i < 6; ++i) e->t[i].ensure(nf * s4 * cp[3] * es);
+  e->ts.ensure(nf * s4 * cp[3] * es);
+  e->prob.ensure(nf * s1 * 4);
+  e->fwt_tile.ensure(64 * 4); e->fwt_op.ensure(64 * 4); e->fwt_origin.ensure(64 * 8);
+  e->tmaps.clear();
+  e->S = S;
+}
+
+template <typename T> View<T> view(const DevBuf &b, int H, int W, int pitch, int coff, int C) {
+  View<T> v;
+  v.p = b.as<T>(); v.H = H; v.W = W; v.pitch = pitch; v.coff = coff; v.C = C;
+  return v;
+}
+
+const CUtensorMap &get_tmap(adp_engine *e, const ConvLayer &L, const DevBuf &src, int H, int W, int pitch, int coff,
+                            int C) {
+  auto it = e->tmaps.find(L.name);
+  if (it != e->tmaps.end()) return it->second;
+  const ConvTcParams &p = L.tc;
+  CUtensorMap m;
+  cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)(C / 8), (cuuint64_t)H, (cuuint64_t)e->max_fw};
+  cuuint64_t gstr[4] = {(cuuint64_t)pitch * 2, 16, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
+  cuuint32_t box[5] = {8, (cuuint32_t)p.PW, (cuuint32_t)p.CG, (cuuint32_t)p.BR, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  void *base = (void *)(src.as<__nv_bfloat16>() + coff);
+  CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw Error(ADP_ECUDA, "cuTensorMapEncodeTiled failed for " + L.name + " code " + std::to_string((int)r));
+  return e->tmaps.emplace(L.name, m).first->second;
+}
+
+double conv_flops(const ConvLayer &L, int Hout, int Wout, int nb) {
+  return 2.0 * nb * Hout * Wout * 9.0 * L.cin * L.cout;
+}
+
+// one generic 3x3 conv layer: src view (H,W are the SOURCE buffer dims) -> dst view
+void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs, int Ws, int spitch, int scoff,
+              const DevBuf &dst, int dpitch, int dcoff, int nb) {
+  ConvLayer &L = layer(e, name);
+  const int Ho = L.up ? Hs * 2 : Hs, Wo = L.up ? Ws * 2 : Ws;
+  const double fl = conv_flops(L, Ho, Wo, nb);
+  const double by = (double)nb * ((double)Hs * Ws * L.cin_pad + (double)Ho * Wo * L.cout_pad) * e->esz;
+  if (e->prec == ADP_PREC_BF16) {
+    ConvTcParams p = L.tc;
+    p.nb = nb; p.Hin = Hs; p.Win = Ws;
+    p.ntx = cdiv(Ws, 128); p.nty = cdiv(Hs, p.T);
+    p.wpk = L.w_tc.as<__nv_bfloat16>(); p.bias = L.bias.as<float>();
+    p.out = dst.as<__nv_bfloat16>(); p.out_pitch = dpitch; p.out_coff = dcoff; p.Hout = Ho; p.Wout = Wo;
+    p.dbg = e->dbg;
+    const CUtensorMap &tm = get_tmap(e, L, src, Hs, Ws, spitch, scoff, L.cin_pad);
+    const int nitems = nb * p.nty * p.ntx * p.nvar;
+    const int grid = std::min(nitems, e->num_sms);
+    const size_t smem = tc_smem_bytes(p);
+    e->launch("conv3x3_tcgen05", fl, by, [&] {
+      conv_tc_kernel<<<grid, 256, smem, e->stream>>>(tm, p);
+    });
+    return;
+  }
+  dim3 grid(cdiv(Wo, 16), cdiv(Ho, 16), nb * (L.cout_pad / 16));
+  dim3 block(16, 16);
+  if (e->prec == ADP_PREC_FP32) {
+    auto in = view<float>(src, Hs, Ws, spitch, scoff, L.cin_pad);
+    auto out = view<float>(dst, Ho, Wo, dpitch, dcoff, L.cout_pad);
+    e->launch("conv3x3_simt_fp32", fl, by, [&] {
+      if (L.up) conv3x3_simt_kernel<float, true><<<grid, block, 0, e->stream>>>(in, out, L.w_simt.as<float>(), L.bias.as<float>(), L.dil, 1);
+      else conv3x3_simt_kernel<float, false><<<grid, block, 0, e->stream>>>(in, out, L.w_simt.as<float>(), L.bias.as<float>(), L.dil, 1);
+    });
+  } else {
+    auto in = view<__nv_bfloat16>(src, Hs, Ws, spitch, scoff, L.cin_pad);
+    auto out = view<__nv_bfloat16>(dst, Ho, Wo, dpitch, dcoff, L.cout_pad);
+    e->launch("conv3x3_simt_bf16", fl, by, [&] {
+      if (L.up) conv3x3_simt_kernel<__nv_bfloat16, true><<<grid, block, 0, e->stream>>>(in, out, L.w_simt.as<float>(), L.bias.as<float>(), L.dil, 1);
+      else conv3x3_simt_kernel<__nv_bfloat16, false><<<grid, block, 0, e->stream>>>(in, out, L.w_simt.as<float>(), L.bias.as<float>(), L.dil, 1);
+    });
+  }
+}
+
+template <typename T>
+void run_pool(adp_engine *e, const DevBuf &src, int Hs, int Ws, int spitch, int C, const DevBuf &dst, int nb) {
+  auto in = view<T>(src, Hs, Ws, spitch, 0, C);
+  auto out = view<T>(dst, Hs / 2, Ws / 2, C, 0, C);
+  const size_t total = (size_t)nb * (Hs / 2) * (Ws / 2) * (C / (16 / sizeof(T)));
+  const int grid = (int)std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 16);
+  e->launch("maxpool2x2", 0, (double)nb * Hs * Ws * C * sizeof(T) * 1.25, [&] {
+    maxpool2_kernel<T><<<grid, 256, 0, e->stream>>>(in, out, nb);
+  });
+}
+
+template <typename T> void forward_t(adp_engine *e, const FirstConvSrc &src, const FwTable &fw, int nfw, float mean, float std_) {
+  const int S = e->S, S2 = S / 2, S3 = S / 4, S4 = S / 8;
+  const int *cp = e->cp;
+  // forward table -> device (kernel parameter copy; no host buffer lifetime to worry about)
+  e->launch("fw_table", 0, 0, [&] {
+    fw_table_store<<<1, 64, 0, e->stream>>>(fw, e->fwt_tile.as<int>(), e->fwt_op.as<int>(), e->fwt_origin.as<long long>(), nfw);
+  });
+  FirstConvSrc s = src;
+  s.slide_origin = reinterpret_cast<const int64_t *>(e->fwt_origin.p);
+  const float mean_f = mean;
+  const float sd_f = (float)((double)std_ + 1e-10);
+  {
+    auto out = view<T>(e->a1, S, S, cp[0], 0, cp[0]);
+    dim3 grid(cdiv(S, 16), cdiv(S, 16), nfw), block(16, 16);
+    const size_t smem = (size_t)10 * cp[0] * 4;
+    e->launch("first_conv", 2.0 * nfw * S * S * 9.0 * e->c[0], (double)nfw * S * S * (4 + cp[0] * sizeof(T)), [&] {
+      first_conv_kernel<T><<<grid, block, smem, e->stream>>>(s, e->fwt_tile.as<int>(), e->fwt_op.as<int>(), S, mean_f, sd_f,
+                                                            e->w_first.as<float>(), e->b_first.as<float>(), out);
+    });
+  }
+  run_conv(e, "down1_conv2", e->a1, S, S, cp[0], 0, e->cat1, 2 * cp[0], 0, nfw);
+  run_pool<T>(e, e->cat1, S, S, 2 * cp[0], cp[0], e->pl1, nfw);
+  run_conv(e, "down2_conv1", e->pl1, S2, S2, cp[0], 0, e->a2, cp[1], 0, nfw);
+  run_conv(e, "down2_conv2", e->a2, S2, S2, cp[1], 0, e->cat2, 2 * cp[1], 0, nfw);
+  run_pool<T>(e, e->cat2, S2, S2, 2 * cp[1], cp[1], e->pl2, nfw);
+  run_conv(e, "down3_conv1", e->pl2, S3, S3, cp[1], 0, e->a3, cp[2], 0, nfw);
+  run_conv(e, "down3_conv2", e->a3, S3, S3, cp[2], 0, e->cat3, 2 * cp[2], 0, nfw);
+  run_pool<T>(e, e->cat3, S3, S3, 2 * cp[2], cp[2], e->pl3, nfw);
+  run_conv(e, "dilate1", e->pl3, S4, S4, cp[2], 0, e->t[0], cp[3], 0, nfw);
+  const char *dn[5] = {"dilate2", "dilate3", "dilate4", "dilate5", "dilate6"};
+  for (int i = 0; i < 5; ++i) run_conv(e, dn[i], e->t[i], S4, S4, cp[3], 0, e->t[i + 1], cp[3], 0, nfw);
+  {
+    const size_t nvec = (size_t)nfw * S4 * S4 * cp[3] * sizeof(T) / 16;
+    const int grid = (int)std::min<size_t>(cdiv64(nvec, 256), (size_t)e->num_sms * 16);
+    e->launch("add6", 0, (double)nvec * 16 * 7, [&] {
+      add6_kernel<T><<<grid, 256, 0, e->stream>>>(e->t[0].as<T>(), e->t[1].as<T>(), e->t[2].as<T>(), e->t[3].as<T>(),
+                                                 e->t[4].as<T>(), e->t[5].as<T>(), e->ts.as<T>(), nvec);
+    });
+  }
+  run_conv(e, "up3_conv1", e->ts, S4, S4, cp[3], 0, e->cat3, 2 * cp[2], cp[2], nfw);
+  run_conv(e, "up3_conv2", e->cat3, S3, S3, 2 * cp[2], 0, e->a3, cp[2], 0, nfw);
+  run_conv(e, "up3_conv3", e->a3, S3, S3, cp[2], 0, e->b3, cp[2], 0, nfw);
+  run_conv(e, "up2_conv1", e->b3, S3, S3, cp[2], 0, e->cat2, 2 * cp[1], cp[1], nfw);
+  run_conv(e, "up2_conv2", e->cat2, S2, S2, 2 * cp[1], 0, e->a2, cp[1], 0, nfw);
+  run_conv(e, "up2_conv3", e->a2, S2, S2, cp[1], 0, e->b2, cp[1], 0, nfw);
+  run_conv(e, "up1_conv1", e->b2, S2, S2, cp[1], 0, e->cat1, 2 * cp[0], cp[0], nfw);
+  run_conv(e, "up1_conv2", e->cat1, S, S, 2 * cp[0], 0, e->a1, cp[0], 0, nfw);
+  run_conv(e, "up1_conv3", e->a1, S, S, cp[0], 0, e->b1, cp[0], 0, nfw);
+  {
+    auto in = view<T>(e->b1, S, S, cp[0], 0, cp[0]);
+    const size_t total = (size_t)nfw * S * S;
+    const int grid = (int)std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 16);
+    e->launch("head_softmax", 2.0 * total * e->c[0] * 2, (double)total * (cp[0] * sizeof(T) + 4), [&] {
+      head_kernel<T><<<grid, 256, (size_t)2 * cp[0] * 4, e->stream>>>(in, nfw, e->w_head.as<float>(), e->b_head.as<float>(),
+                                                                      e->prob.as<float>());
+    });
+  }
+  e->last_nfw = nfw;
+}
+
+void forward(adp_engine *e, const FirstConvSrc &src, const FwTable &fw, int nfw, float mean, float std_) {
+  if (e->prec == ADP_PREC_FP32) forward_t<float>(e, src, fw, nfw, mean, std_);
+  else forward_t<__nv_bfloat16>(e, src, fw, nfw, mean, std_);
+}
+
+// Runs n tiles through forward + TTA combine.
+// Source kinds: 0 = packed float32 tiles, 1 = packed uint8 tiles (src.ch channels),
+// 2 = device-resident uint8 slide region (tile origins given).
+// Sink: out (mode 0) or the slide accumulator (ys/xs given).
+void run_tiles(adp_engine *e, int kind, FirstConvSrc src, const void *src_base, int n, int S, float mean, float std_,
+               const int *ops_in, int n_ops_in, float *out, const int32_t *ys, const int32_t *xs,
+               const long long *origins) {
+  if (!e->packed) pack_all(e);
+  ensure_arena(e, S);
+  int ops[8] = {0}; int n_ops = 1;
+  if (ops_in && n_ops_in > 0) {
+    ADP_REQUIRE(n_ops_in <= 8, "at most 8 TTA ops");
+    n_ops = n_ops_in;
+    for (int i = 0; i < n_ops; ++i) { ADP_REQUIRE(ops_in[i] >= 0 && ops_in[i] < 8, "bad dihedral op"); ops[i] = ops_in[i]; }
+  }
+  ADP_REQUIRE(n_ops <= e->max_fw, "max_forwards smaller than the number of TTA ops");
+  const int tpc = std::max(1, e->max_fw / n_ops);      // tiles per chunk
+  const bool out_host = out && !is_device_ptr(out);
+  const size_t tile_px = (size_t)S * S;
+  const size_t src_tile_bytes = kind == 0 ? tile_px * 4 : (kind == 1 ? tile_px * src.ch : 0);
+  const bool src_host = kind != 2 && !is_device_ptr(src_base);
+  TtaOps tops; tops.n = n_ops;
+  for (int i = 0; i < 8; ++i) tops.inv[i] = d4_inverse(ops[i < n_ops ? i : 0]);
+  for (int t0 = 0; t0 < n; t0 += tpc) {
+    const int nt = std::min(tpc, n - t0);
+    FirstConvSrc s = src;
+    if (kind != 2) {
+      const uint8_t *sp = reinterpret_cast<const uint8_t *>(src_base) + (size_t)t0 * src_tile_bytes;
+      const void *dp = sp;
+      if (src_host) {
+        e->in_stage.ensure((size_t)tpc * src_tile_bytes);
+        ADP_CUDA(cudaMemcpyAsync(e->in_stage.p, sp, (size_t)nt * src_tile_bytes, cudaMemcpyHostToDevice, e->stream));
+        dp = e->in_stage.p;
+      }
+      s.f32 = kind == 0 ? reinterpret_cast<const float *>(dp) : nullptr;
+      s.u8 = kind == 1 ? reinterpret_cast<const uint8_t *>(dp) : nullptr;
+    }
+    FwTable fw;
+    memset(&fw, 0, sizeof(fw));
+    for (int t = 0; t < nt; ++t) {
+      fw.origin[t] = origins ? origins[t0 + t] : 0;     // indexed by local tile
+      for (int k = 0; k < n_ops; ++k) { fw.tile[t * n_ops + k] = t; fw.op[t * n_ops + k] = ops[k]; }
+    }
+    forward(e, s, fw, nt * n_ops, mean, std_);
+    dim3 grid(cdiv(S, 32), cdiv(S, 32)), block(32, 8);
+    float *dout = nullptr;
+    if (out) {
+      if (out_host) { e->out_stage.ensure((size_t)tpc * tile_px * 4); dout = e->out_stage.as<float>(); }
+      else dout = out + (size_t)t0 * tile_px;
+    }
+    for (int t = 0; t < nt; ++t) {
+      const float *planes = e->prob.as<float>() + (size_t)t * n_ops * tile_px;
+      const double by = (double)tile_px * 4 * (n_ops + (out ? 1 : (e->wsi_mode == ADP_BLEND_GAUSSIAN ? 5 : 4)));
+      if (out) {
+        e->launch("tta_combine", 0, by, [&] {
+          tta_blend_kernel<<<grid, block, 0, e->stream>>>(planes, tops, S, 0, dout + (size_t)t * tile_px, nullptr, nullptr,
+                                                         nullptr, 0, 0, 0, 0);
+        });
+      } else {
+        const int mode = e->wsi_mode == ADP_BLEND_GAUSSIAN ? 1 : 2;
+        e->launch("tta_blend", 0, by, [&] {
+          tta_blend_kernel<<<grid, block, 0, e->stream>>>(planes, tops, S, mode, nullptr, e->wsi_acc.as<float>(),
+                                                         e->wsi_wsum.as<float>(), e->wsi_window.as<float>(), e->wsi_W,
+                                                         e->wsi_rows, ys[t0 + t] - e->wsi_y0, xs[t0 + t]);
+        });
+      }
+    }
+    if (out && out_host)
+      ADP_CUDA(cudaMemcpyAsync(out + (size_t)t0 * tile_px, dout, (size_t)nt * tile_px * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (src_host || out_host) ADP_CUDA(cudaStreamSynchronize(e->stream));   // staging buffers are reused
+  }
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+}
+
+// device-visible copy of a small/large host or device array
+const void *to_device(adp_engine *e, DevBuf &buf, const void *p, size_t bytes) {
+  if (!p) return nullptr;
+  if (is_device_ptr(p)) return p;
+  buf.ensure(bytes);
+  ADP_CUDA(cudaMemcpyAsync(buf.p, p, bytes, cudaMemcpyHostToDevice, e->stream));
+  return buf.p;
+}
+
+void run_finalize(adp_engine *e, const float *acc, const float *wsum, int linear, size_t n, float thr, float *prob,
+                  uint8_t *mask, const uint8_t *gt, int64_t counts[4]) {
+  DevBuf dprob, dmask, dgt;
+  const bool prob_host = prob && !is_device_ptr(prob), mask_host = mask && !is_device_ptr(mask);
+  float *dp = prob; uint8_t *dm = mask;
+  if (prob_host) { dprob.ensure(n * 4); dp = dprob.as<float>(); }
+  if (mask_host) { dmask.ensure(n); dm = dmask.as<uint8_t>(); }
+  const uint8_t *dg = reinterpret_cast<const uint8_t *>(to_device(e, dgt, gt, n));
+  e->counts.ensure(32);
+  ADP_CUDA(cudaMemsetAsync(e->counts.p, 0, 32, e->stream));
+  const int grid = (int)std::min<size_t>(cdiv64(n, 256 * 4), (size_t)e->num_sms * 8);
+  const double by = (double)n * ((wsum ? 8 : 4) + (dp ? 4 : 0) + (dm ? 1 : 0) + (dg ? 1 : 0));
+  e->launch("finalize_threshold_metrics", 0, by, [&] {
+    finalize_kernel<<<std::max(grid, 1), 256, 0, e->stream>>>(acc, wsum, linear, n, thr, dp, dm, dg,
+                                                             e->counts.as<unsigned long long>());
+  });
+  if (prob_host) ADP_CUDA(cudaMemcpyAsync(prob, dp, n * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (mask_host) ADP_CUDA(cudaMemcpyAsync(mask, dm, n, cudaMemcpyDeviceToHost, e->stream));
+  unsigned long long hc[4];
+  ADP_CUDA(cudaMemcpyAsync(hc, e->counts.p, 32, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  if (counts) for (int i = 0; i < 4; ++i) counts[i] = (int64_t)hc[i];
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+#define ADP_TRY try {
+#define ADP_CATCH                                              \
+  }                                                            \
+  catch (const adp::Error &ex) { g_last_error = ex.what(); return ex.code; } \
+  catch (const std::exception &ex) { g_last_error = ex.what(); return ADP_ECUDA; } \
+  return ADP_OK;
+
+extern "C" {
+
+int adp_abi_version(void) { return ADP_ABI_VERSION; }
+const char *adp_last_error(void) { return g_last_error.c_str(); }
+
+int adp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, i) == cudaSuccess && pr.major == 10) ++ok;
+  }
+  return ok;
+}
+
+int adp_create(int device, int precision, int init_nb, int max_forwards, adp_engine **out) {
+  ADP_TRY
+  ADP_REQUIRE(out, "out is null");
+  ADP_REQUIRE(precision >= 0 && precision <= 2, "precision");
+  if (init_nb <= 0) init_nb = 44;
+  ADP_REQUIRE(init_nb % 4 == 0 && init_nb <= 64, "init_nb must be a multiple of 4, at most 64");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); throw Error(ADP_ENODEV, "no CUDA device (libadipose_b200 has no CPU fallback)"); }
+  ADP_REQUIRE(device >= 0 && device < n, "device index");
+  cudaDeviceProp pr;
+  ADP_CUDA(cudaGetDeviceProperties(&pr, device));
+  if (pr.major != 10) throw Error(ADP_ENODEV, std::string("device is sm_") + std::to_string(pr.major * 10 + pr.minor) + ", this library is sm_100a only");
+  ADP_CUDA(cudaSetDevice(device));
+  std::unique_ptr<adp_engine> e(new adp_engine());
+  e->device = device; e->prec = precision; e->init_nb = init_nb;
+  e->max_fw = max_forwards > 0 ? std::min(max_forwards, 64) : 16;
+  e->num_sms = pr.multiProcessorCount;
+  e->esz = precision == ADP_PREC_FP32 ? 4 : 2;
+  for (int i = 0; i < 4; ++i) { e->c[i] = init_nb << i; e->cp[i] = pad16(e->c[i]); }
+  ADP_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  ADP_CUDA(cudaEventCreate(&e->ev0));
+  ADP_CUDA(cudaEventCreate(&e->ev1));
+  ADP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (const char *d = getenv("ADP_TC_DEBUG")) e->dbg = atoi(d);
+  build_layers(e.get());
+  *out = e.release();
+  ADP_CATCH
+}
+
+int adp_destroy(adp_engine *e) {
+  ADP_TRY
+  if (!e) return ADP_OK;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  ADP_CATCH
+}
+
+int adp_precision(const adp_engine *e) { return e ? e->prec : ADP_EINVAL; }
+
+int adp_synchronize(adp_engine *e) {
+  ADP_TRY
+  ADP_REQUIRE(e, "engine");
+  ADP_CUDA(cudaSetDevice(e->device));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  ADP_CATCH
+}
+
+int adp_set_weight(adp_engine *e, const char *layer_name, const float *kernel, const int64_t kshape[4], const float *bias,
+                   int64_t nbias) {
+  ADP_TRY
+  ADP_REQUIRE(e && layer_name && kernel && kshape && bias, "null argument");
+  ADP_CUDA(cudaSetDevice(e->device));
+  std::string n = layer_name;
+  int64_t want[4];
+  if (n == "down1_conv1") { want[0] = 3; want[1] = 3; want[2] = 1; want[3] = e->c[0]; }
+  else if (n == "output_softmax") { want[0] = 1; want[1] = 1; want[2] = e->c[0]; want[3] = 2; }
+  else { ConvLayer &L = layer(e, n); want[0] = 3; want[1] = 3; want[2] = L.cin; want[3] = L.cout; }
+  for (int i = 0; i < 4; ++i)
+    if (kshape[i] != want[i])
+      throw Error(ADP_EINVAL, "kernel shape mismatch for " + n + ": expected (" + std::to_string(want[0]) + "," + std::to_string(want[1]) +
+                                  "," + std::to_string(want[2]) + "," + std::to_string(want[3]) + ")");
+  ADP_REQUIRE(nbias == want[3], "bias length mismatch");
+  HostWeight &h = e->hw[n];
+  const size_t ne = (size_t)(want[0] * want[1] * want[2] * want[3]);
+  h.k.assign(kernel, kernel + ne);
+  h.b.assign(bias, bias + nbias);
+  for (int i = 0; i < 4; ++i) h.shape[i] = want[i];
+  h.set = true;
+  e->packed = false;
+  ADP_CATCH
+}
+
+int adp_get_weight(adp_engine *e, const char *layer_name, float *kernel, int64_t kernel_elems, float *bias, int64_t nbias) {
+  ADP_TRY
+  ADP_REQUIRE(e && layer_name, "null argument");
+  auto it = e->hw.find(layer_name);
+  if (it == e->hw.end() || !it->second.set) throw Error(ADP_ESTATE, std::string("layer not set: ") + layer_name);
+  const HostWeight &h = it->second;
+  if (kernel) { ADP_REQUIRE(kernel_elems == (int64_t)h.k.size(), "kernel_elems"); memcpy(kernel, h.k.data(), h.k.size() * 4); }
+  if (bias) { ADP_REQUIRE(nbias == (int64_t)h.b.size(), "nbias"); memcpy(bias, h.b.data(), h.b.size() * 4); }
+  ADP_CATCH
+}
+
+int adp_weights_ready(adp_engine *e) {
+  if (!e) return 0;
+  for (const char *n : kAllNames) {
+    auto it = e->hw.find(n);
+    if (it == e->hw.end() || !it->second.set) return 0;
+  }
+  return 1;
+}
+
+int adp_tta_ops(int mode, int ops[8]) {
+  static const int full[8] = {0, 1, 2, 3, 4, 5, 6, 7}, basic[4] = {0, 4, 5, 1}, minimal[2] = {0, 4};
+  if (!ops) return ADP_EINVAL;
+  switch (mode) {
+    case ADP_TTA_NONE: ops[0] = 0; return 1;
+    case ADP_TTA_MINIMAL: memcpy(ops, minimal, sizeof(minimal)); return 2;
+    case ADP_TTA_BASIC: memcpy(ops, basic, sizeof(basic)); return 4;
+    case ADP_TTA_FULL: memcpy(ops, full, sizeof(full)); return 8;
+  }
+  return ADP_EINVAL;
+}
+
+int adp_predict(adp_engine *e, const float *tiles, int n, int size, float mean, float std_, const int *ops, int n_ops,
+                float *out) {
+  ADP_TRY
+  ADP_REQUIRE(e && tiles && out && n > 0, "null/empty argument");
+  ADP_CUDA(cudaSetDevice(e->device));
+  FirstConvSrc s{};
+  run_tiles(e, 0, s, tiles, n, size, mean, std_, ops, n_ops, out, nullptr, nullptr, nullptr);
+  ADP_CATCH
+}
+
+int adp_predict_u8(adp_engine *e, const uint8_t *tiles, int n, int size, int channels, float mean, float std_,
+                   const int *ops, int n_ops, float *out) {
+  ADP_TRY
+  ADP_REQUIRE(e && tiles && out && n > 0, "null/empty argument");
+  ADP_REQUIRE(channels == 1 || channels == 3, "channels must be 1 or 3");
+  ADP_CUDA(cudaSetDevice(e->device));
+  FirstConvSrc s{};
+  s.ch = channels;
+  run_tiles(e, 1, s, tiles, n, size, mean, std_, ops, n_ops, out, nullptr, nullptr, nullptr);
+  ADP_CATCH
+}
+
+int adp_tta_combine(adp_engine *e, const float *planes, int size, const int *ops, int n_ops, float *out) {
+  ADP_TRY
+  ADP_REQUIRE(e && planes && ops && out && size > 0 && n_ops > 0 && n_ops <= 8, "null/empty argument");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const size_t px = (size_t)size * size;
+  DevBuf dpl, dout;
+  const float *pl = reinterpret_cast<const float *>(to_device(e, dpl, planes, px * 4 * n_ops));
+  const bool host = !is_device_ptr(out);
+  float *o = out;
+  if (host) { dout.ensure(px * 4); o = dout.as<float>(); }
+  TtaOps tops; tops.n = n_ops;
+  for (int i = 0; i < 8; ++i) {
+    const int op = ops[i < n_ops ? i : 0];
+    ADP_REQUIRE(op >= 0 && op < 8, "bad dihedral op");
+    tops.inv[i] = d4_inverse(op);
+  }
+  dim3 grid(cdiv(size, 32), cdiv(size, 32)), block(32, 8);
+  e->launch("tta_combine", 0, (double)px * 4 * (n_ops + 1), [&] {
+    tta_blend_kernel<<<grid, block, 0, e->stream>>>(pl, tops, size, 0, o, nullptr, nullptr, nullptr, 0, 0, 0, 0);
+  });
+  if (host) ADP_CUDA(cudaMemcpyAsync(out, o, px * 4, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  ADP_CATCH
+}
+
+int adp_debug_layer(adp_engine *e, const char *name, int idx, float *out, int64_t out_elems, int64_t shape_hwc[3]) {
+  ADP_TRY
+  ADP_REQUIRE(e && name && shape_hwc, "null argument");
+  ADP_CUDA(cudaSetDevice(e->device));
+  ADP_REQUIRE(e->S > 0 && idx >= 0 && idx < e->last_nfw, "no forward to tap / idx out of range");
+  const int S = e->S;
+  const int *cp = e->cp, *c = e->c;
+  struct Tap { const DevBuf *b; int H, pitch, coff, C; };
+  std::map<std::string, Tap> m = {
+      {"down1_conv2", {&e->cat1, S, 2 * cp[0], 0, c[0]}},      {"up1_conv1", {&e->cat1, S, 2 * cp[0], cp[0], c[0]}},
+      {"down2_conv2", {&e->cat2, S / 2, 2 * cp[1], 0, c[1]}},  {"up2_conv1", {&e->cat2, S / 2, 2 * cp[1], cp[1], c[1]}},
+      {"down3_conv2", {&e->cat3, S / 4, 2 * cp[2], 0, c[2]}},  {"up3_conv1", {&e->cat3, S / 4, 2 * cp[2], cp[2], c[2]}},
+      {"dilate1", {&e->t[0], S / 8, cp[3], 0, c[3]}},          {"dilate2", {&e->t[1], S / 8, cp[3], 0, c[3]}},
+      {"dilate3", {&e->t[2], S / 8, cp[3], 0, c[3]}},          {"dilate4", {&e->t[3], S / 8, cp[3], 0, c[3]}},
+      {"dilate5", {&e->t[4], S / 8, cp[3], 0, c[3]}},          {"dilate6", {&e->t[5], S / 8, cp[3], 0, c[3]}},
+      {"dilate_add", {&e->ts, S / 8, cp[3], 0, c[3]}},
+      {"up3_conv2", {&e->a3, S / 4, cp[2], 0, c[2]}},          {"up3_conv3", {&e->b3, S / 4, cp[2], 0, c[2]}},
+      {"up2_conv2", {&e->a2, S / 2, cp[1], 0, c[1]}},          {"up2_conv3", {&e->b2, S / 2, cp[1], 0, c[1]}},
+      {"up1_conv2", {&e->a1, S, cp[0], 0, c[0]}},              {"up1_conv3", {&e->b1, S, cp[0], 0, c[0]}},
+      {"pool1", {&e->pl1, S / 2, cp[0], 0, c[0]}},             {"pool2", {&e->pl2, S / 4, cp[1], 0, c[1]}},
+      {"pool3", {&e->pl3, S / 8, cp[2], 0, c[2]}},
+  };
+  std::string n = name;
+  if (n == "prob") {
+    shape_hwc[0] = S; shape_hwc[1] = S; shape_hwc[2] = 1;
+    if (out) {
+      ADP_REQUIRE(out_elems == (int64_t)S * S, "out_elems");
+      ADP_CUDA(cudaMemcpy(out, e->prob.as<float>() + (size_t)idx * S * S, (size_t)S * S * 4, cudaMemcpyDeviceToHost));
+    }
+    return ADP_OK;
+  }
+  auto it = m.find(n);
+  if (it == m.end()) throw Error(ADP_EINVAL, "layer not tappable (overwritten later in the forward): " + n);
+  const Tap &t = it->second;
+  shape_hwc[0] = t.H; shape_hwc[1] = t.H; shape_hwc[2] = t.C;
+  if (!out) return ADP_OK;
+  ADP_REQUIRE(out_elems == (int64_t)t.H * t.H * t.C, "out_elems");
+  const size_t npx = (size_t)t.H * t.H, img = npx * t.pitch * e->esz;
+  std::vector<uint8_t> host(img);
+  ADP_CUDA(cudaMemcpy(host.data(), (const uint8_t *)t.b->p + (size_t)idx * img, img, cudaMemcpyDeviceToHost));
+  for (size_t px = 0; px < npx; ++px)
+    for (int ch = 0; ch < t.C; ++ch) {
+      const size_t si = px * t.pitch + t.coff + ch;
+      out[px * t.C + ch] = e->esz == 4 ? reinterpret_cast<const float *>(host.data())[si]
+                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(host.data())[si]);
+    }
+  ADP_CATCH
+}
+
+int adp_threshold_metrics(adp_engine *e, const float *prob, const uint8_t *gt, int64_t n_px, float thr, uint8_t *mask,
+                          int64_t counts[4]) {
+  ADP_TRY
+  ADP_REQUIRE(e && prob && n_px > 0, "null/empty argument");
+  ADP_CUDA(cudaSetDevice(e->device));
+  DevBuf dp;
+  const float *p = reinterpret_cast<const float *>(to_device(e, dp, prob, (size_t)n_px * 4));
+  run_finalize(e, p, nullptr, 0, (size_t)n_px, thr, nullptr, mask, gt, counts);
+  ADP_CATCH
+}
+
+int adp_blend_reconstruct(adp_engine *e, int blend_mode, const float *tiles, int n, int th, int tw, const int32_t *ys,
+                          const int32_t *xs, const float *window, int H, int W, float *out) {
+  ADP_TRY
+  ADP_REQUIRE(e && out && H > 0 && W > 0 && n >= 0, "null/empty argument");
+  ADP_REQUIRE(blend_mode == ADP_BLEND_GAUSSIAN || blend_mode == ADP_BLEND_LINEAR, "blend_mode");
+  ADP_REQUIRE(blend_mode == ADP_BLEND_LINEAR || window, "Gaussian blending needs a window");
+  ADP_REQUIRE(n == 0 || (tiles && ys && xs && th > 0 && tw > 0), "tiles/positions");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const size_t npx = (size_t)H * W, tpx = (size_t)th * tw;
+  DevBuf acc, ws, dwin, dtiles;
+  acc.ensure(npx * 4); ws.ensure(npx * 4);
+  ADP_CUDA(cudaMemsetAsync(acc.p, 0, npx * 4, e->stream));
+  ADP_CUDA(cudaMemsetAsync(ws.p, 0, npx * 4, e->stream));
+  const float *dw = reinterpret_cast<const float *>(to_device(e, dwin, window, tpx * 4));
+  const bool th_host = n && !is_device_ptr(tiles);
+  const int chunk = (int)std::max<size_t>(1, (256u << 20) / (tpx * 4));
+  const int mode = blend_mode == ADP_BLEND_GAUSSIAN ? 1 : 2;
+  const int grid = (int)std::min<size_t>(cdiv64(tpx, 256), (size_t)e->num_sms * 8);
+  for (int t0 = 0; t0 < n; t0 += chunk) {
+    const int nt = std::min(chunk, n - t0);
+    const float *dt = tiles + (size_t)t0 * tpx;
+    if (th_host) {
+      dtiles.ensure((size_t)chunk * tpx * 4);
+      ADP_CUDA(cudaMemcpyAsync(dtiles.p, dt, (size_t)nt * tpx * 4, cudaMemcpyHostToDevice, e->stream));
+      dt = dtiles.as<float>();
+    }
+    for (int t = 0; t < nt; ++t)   // stream order == list order: same accumulation order as the NumPy loop
+      e->launch("blend_tile", 0, (double)tpx * 4 * (mode == 1 ? 6 : 5), [&] {
+        blend_tile_kernel<<<grid, 256, 0, e->stream>>>(dt + (size_t)t * tpx, th, tw, mode, acc.as<float>(), ws.as<float>(), dw,
+                                                      tw, W, H, ys[t0 + t], xs[t0 + t]);
+      });
+    if (th_host) ADP_CUDA(cudaStreamSynchronize(e->stream));
+  }
+  run_finalize(e, acc.as<float>(), ws.as<float>(), blend_mode == ADP_BLEND_LINEAR, npx, 0.5f, out, nullptr, nullptr, nullptr);
+  ADP_CATCH
+}
+
+int adp_wsi_begin(adp_engine *e, int rows, int W, int y0, int tile, int blend_mode, const float *window) {
+  ADP_TRY
+  ADP_REQUIRE(e && rows > 0 && W > 0 && tile > 0, "null/empty argument");
+  ADP_REQUIRE(blend_mode == ADP_BLEND_GAUSSIAN || blend_mode == ADP_BLEND_LINEAR, "blend_mode");
+  ADP_REQUIRE(blend_mode == ADP_BLEND_LINEAR || window, "Gaussian blending needs a window");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const size_t npx = (size_t)rows * W;
+  e->wsi_acc.ensure(npx * 4); e->wsi_wsum.ensure(npx * 4);
+  ADP_CUDA(cudaMemsetAsync(e->wsi_acc.p, 0, npx * 4, e->stream));
+  ADP_CUDA(cudaMemsetAsync(e->wsi_wsum.p, 0, npx * 4, e->stream));
+  if (window) {
+    e->wsi_window.ensure((size_t)tile * tile * 4);
+    ADP_CUDA(cudaMemcpyAsync(e->wsi_window.p, window, (size_t)tile * tile * 4, cudaMemcpyDefault, e->stream));
+  }
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  e->wsi_rows = rows; e->wsi_W = W; e->wsi_y0 = y0; e->wsi_tile = tile; e->wsi_mode = blend_mode; e->wsi_on = true;
+  ADP_CATCH
+}
+
+int adp_wsi_push_tiles(adp_engine *e, const float *tiles, int n, const int32_t *ys, const int32_t *xs, float mean,
+                       float std_, const int *ops, int n_ops) {
+  ADP_TRY
+  ADP_REQUIRE(e && tiles && ys && xs && n > 0, "null/empty argument");
+  if (!e->wsi_on) throw Error(ADP_ESTATE, "adp_wsi_begin not called");
+  ADP_CUDA(cudaSetDevice(e->device));
+  FirstConvSrc s{};
+  run_tiles(e, 0, s, tiles, n, e->wsi_tile, mean, std_, ops, n_ops, nullptr, ys, xs, nullptr);
+  ADP_CATCH
+}
+
+int adp_wsi_push_from_slide(adp_engine *e, const uint8_t *slide, int region_y0, int region_rows, int n, const int32_t *ys,
+                            const int32_t *xs, float mean, float std_, const int *ops, int n_ops) {
+  ADP_TRY
+  ADP_REQUIRE(e && slide && ys && xs && n > 0, "null/empty argument");
+  if (!e->wsi_on) throw Error(ADP_ESTATE, "adp_wsi_begin not called");
+  ADP_REQUIRE(is_device_ptr(slide), "slide region must be device-resident (copy it once, then push tile positions)");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const int S = e->wsi_tile;
+  std::vector<long long> org(n);
+  for (int i = 0; i < n; ++i) {
+    ADP_REQUIRE(ys[i] >= region_y0 && ys[i] + S <= region_y0 + region_rows && xs[i] >= 0 && xs[i] + S <= e->wsi_W,
+                "tile outside the resident slide region");
+    org[i] = (long long)(ys[i] - region_y0) * e->wsi_W + xs[i];
+  }
+  FirstConvSrc s{};
+  s.u8 = slide; s.ch = 1; s.slideW = e->wsi_W;
+  run_tiles(e, 2, s, nullptr, n, S, mean, std_, ops, n_ops, nullptr, ys, xs, org.data());
+  ADP_CATCH
+}
+
+int adp_wsi_push_probs(adp_engine *e, const float *probs, int n, const int32_t *ys, const int32_t *xs) {
+  ADP_TRY
+  ADP_REQUIRE(e && probs && ys && xs && n > 0, "null/empty argument");
+  if (!e->wsi_on) throw Error(ADP_ESTATE, "adp_wsi_begin not called");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const int S = e->wsi_tile;
+  const size_t tpx = (size_t)S * S;
+  const bool host = !is_device_ptr(probs);
+  const int mode = e->wsi_mode == ADP_BLEND_GAUSSIAN ? 1 : 2;
+  const int grid = (int)std::min<size_t>(cdiv64(tpx, 256), (size_t)e->num_sms * 8);
+  const int chunk = 16;
+  for (int t0 = 0; t0 < n; t0 += chunk) {
+    const int nt = std::min(chunk, n - t0);
+    const float *dt = probs + (size_t)t0 * tpx;
+    if (host) {
+      e->in_stage.ensure((size_t)chunk * tpx * 4);
+      ADP_CUDA(cudaMemcpyAsync(e->in_stage.p, dt, (size_t)nt * tpx * 4, cudaMemcpyHostToDevice, e->stream));
+      dt = e->in_stage.as<float>();
+    }
+    for (int t = 0; t < nt; ++t)
+      e->launch("blend_tile", 0, (double)tpx * 4 * (mode == 1 ? 6 : 5), [&] {
+        blend_tile_kernel<<<grid, 256, 0, e->stream>>>(dt + (size_t)t * tpx, S, S, mode, e->wsi_acc.as<float>(),
+                                                      e->wsi_wsum.as<float>(), e->wsi_window.as<float>(), S, e->wsi_W,
+                                                      e->wsi_rows, ys[t0 + t] - e->wsi_y0, xs[t0 + t]);
+      });
+    ADP_CUDA(cudaStreamSynchronize(e->stream));
+  }
+  ADP_CATCH
+}
+
+int adp_wsi_export(adp_engine *e, int y, int rows, float *acc, float *weight) {
+  ADP_TRY
+  ADP_REQUIRE(e && acc && weight, "null argument");
+  if (!e->wsi_on) throw Error(ADP_ESTATE, "adp_wsi_begin not called");
+  ADP_REQUIRE(y >= e->wsi_y0 && rows > 0 && y + rows <= e->wsi_y0 + e->wsi_rows, "row range outside the accumulator");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const size_t off = (size_t)(y - e->wsi_y0) * e->wsi_W, nb = (size_t)rows * e->wsi_W * 4;
+  ADP_CUDA(cudaMemcpyAsync(acc, e->wsi_acc.as<float>() + off, nb, cudaMemcpyDefault, e->stream));
+  ADP_CUDA(cudaMemcpyAsync(weight, e->wsi_wsum.as<float>() + off, nb, cudaMemcpyDefault, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  ADP_CATCH
+}
+
+int adp_wsi_import_add(adp_engine *e, int y, int rows, const float *acc, const float *weight) {
+  ADP_TRY
+  ADP_REQUIRE(e && acc && weight, "null argument");
+  if (!e->wsi_on) throw Error(ADP_ESTATE, "adp_wsi_begin not called");
+  ADP_REQUIRE(y >= e->wsi_y0 && rows > 0 && y + rows <= e->wsi_y0 + e->wsi_rows, "row range outside the accumulator");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const size_t off = (size_t)(y - e->wsi_y0) * e->wsi_W, n = (size_t)rows * e->wsi_W;
+  DevBuf da, dw;
+  const float *a = reinterpret_cast<const float *>(to_device(e, da, acc, n * 4));
+  const float *w = reinterpret_cast<const float *>(to_device(e, dw, weight, n * 4));
+  const int grid = (int)std::min<size_t>(cdiv64(n, 256), (size_t)e->num_sms * 8);
+  e->launch("wsi_add_partial", 0, (double)n * 24, [&] {
+    add_partial_kernel<<<grid, 256, 0, e->stream>>>(e->wsi_acc.as<float>() + off, e->wsi_wsum.as<float>() + off, a, w, n);
+  });
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  ADP_CATCH
+}
+
+int adp_wsi_finalize(adp_engine *e, int y, int rows, float thr, float *prob, uint8_t *mask, const uint8_t *gt,
+                     int64_t counts[4]) {
+  ADP_TRY
+  ADP_REQUIRE(e, "engine");
+  if (!e->wsi_on) throw Error(ADP_ESTATE, "adp_wsi_begin not called");
+  ADP_REQUIRE(y >= e->wsi_y0 && rows > 0 && y + rows <= e->wsi_y0 + e->wsi_rows, "row range outside the accumulator");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const size_t off = (size_t)(y - e->wsi_y0) * e->wsi_W, n = (size_t)rows * e->wsi_W;
+  run_finalize(e, e->wsi_acc.as<float>() + off, e->wsi_wsum.as<float>() + off, e->wsi_mode == ADP_BLEND_LINEAR, n, thr,
+               prob, mask, gt, counts);
+  ADP_CATCH
+}
+
+int adp_wsi_end(adp_engine *e) {
+  ADP_TRY
+  ADP_REQUIRE(e, "engine");
+  ADP_CUDA(cudaSetDevice(e->device));
+  e->wsi_acc.release(); e->wsi_wsum.release(); e->wsi_window.release();
+  e->wsi_on = false;
+  ADP_CATCH
+}
+
+int adp_loss_metrics(adp_engine *e, const float *p, const float *y, int64_t n_px, float *dldp, double out[4]) {
+  ADP_TRY
+  ADP_REQUIRE(e && p && y && out && n_px > 0, "null/empty argument");
+  ADP_CUDA(cudaSetDevice(e->device));
+  DevBuf dp, dy, dg;
+  const size_t n = (size_t)n_px;
+  const float *pp = reinterpret_cast<const float *>(to_device(e, dp, p, n * 4));
+  const float *yy = reinterpret_cast<const float *>(to_device(e, dy, y, n * 4));
+  e->misc.ensure(64);
+  ADP_CUDA(cudaMemsetAsync(e->misc.p, 0, 64, e->stream));
+  const int grid = (int)std::min<size_t>(cdiv64(n, 256 * 4), (size_t)e->num_sms * 8);
+  e->launch("loss_reduce", 0, (double)n * 8, [&] {
+    loss_reduce_kernel<<<std::max(grid, 1), 256, 0, e->stream>>>(pp, yy, n, e->misc.as<double>());
+  });
+  double s[6];
+  ADP_CUDA(cudaMemcpyAsync(s, e->misc.p, 48, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  const double bce = s[0] / (double)n;
+  const double denom = s[2] + s[3] + 1.0;
+  const double dice_loss = 1.0 - (2.0 * s[1] + 1.0) / denom;
+  out[0] = bce + dice_loss; out[1] = bce; out[2] = dice_loss;
+  out[3] = (2.0 * s[4] + 1.0) / (s[2] + s[5] + 1.0);
+  if (dldp) {
+    const bool host = !is_device_ptr(dldp);
+    float *g = dldp;
+    if (host) { dg.ensure(n * 4); g = dg.as<float>(); }
+    e->launch("loss_grad", 0, (double)n * 12, [&] {
+      loss_grad_kernel<<<std::max(grid, 1), 256, 0, e->stream>>>(pp, yy, n, (float)(1.0 / (double)n), (float)(2.0 * s[1] + 1.0),
+                                                                (float)denom, g);
+    });
+    if (host) ADP_CUDA(cudaMemcpyAsync(dldp, g, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    ADP_CUDA(cudaStreamSynchronize(e->stream));
+  }
+  ADP_CATCH
+}
+
+int adp_profile_enable(adp_engine *e, int on) { if (!e) return ADP_EINVAL; e->prof = on != 0; return ADP_OK; }
+int adp_profile_reset(adp_engine *e) { if (!e) return ADP_EINVAL; e->prof_rows.clear(); return ADP_OK; }
+int adp_profile_read(adp_engine *e, adp_prof_row *rows, int cap) {
+  if (!e || (!rows && cap > 0)) return ADP_EINVAL;
+  int i = 0;
+  for (auto &kv : e->prof_rows) {
+    if (i >= cap) break;
+    memset(&rows[i], 0, sizeof(rows[i]));
+    strncpy(rows[i].name, kv.first.c_str(), sizeof(rows[i].name) - 1);
+    rows[i].launches = kv.second.launches; rows[i].ms = kv.second.ms; rows[i].flops = kv.second.flops; rows[i].bytes = kv.second.bytes;
+    ++i;
+  }
+  return i;
+}
+int64_t adp_launch_count(adp_engine *e) { return e ? e->launches : 0; }
+
+}  // extern "C"

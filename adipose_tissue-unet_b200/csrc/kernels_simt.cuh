@@ -1,0 +1,265 @@
+// kernels_simt.cuh — CUDA-core kernels of the U-Net path: first conv (Cin=1, fused z-score +
+// dihedral load), generic 3x3 conv (exact-fp32 parity path and bf16 cross-check), max-pool,
+// six-way add, 1x1 softmax head.  All activations are NHWC with the channel count padded to a
+// multiple of 16 (pad channels are exact zeros); `pitch` is the channel pitch of the buffer and
+// `coff` the first channel of the view, so concat buffers are written in place
+// (Concatenate([skip, up]) of train_adipose_unet_v3.py:693,700,707 costs nothing).
+#pragma once
+#include "common.cuh"
+
+namespace adp {
+
+template <typename T> struct View {   // NHWC view into an activation buffer
+  T *p;
+  int H, W;      // spatial size of one image
+  int pitch;     // channels per pixel in the underlying buffer
+  int coff;      // first channel of this view
+  int C;         // channels of the view (padded to 16)
+  __host__ __device__ size_t img_stride() const { return (size_t)H * W * pitch; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// First layer: Reshape + Conv2D(1 -> C, 3x3, same) + ReLU  (train_adipose_unet_v3.py:665-668),
+// fused with predict_single's normalisation x = (img - mean) / (std + 1e-10) in float32
+// (full_evaluation_enhanced.py:1306) and the TTA input transform aug(img)
+// (full_evaluation_enhanced.py:590).  One thread per output pixel.
+// src is float32 or uint8 (1 or 3 interleaved channels -> OpenCV gray).
+struct FirstConvSrc {
+  const float *f32;     // n_tiles * S * S, or null
+  const uint8_t *u8;    // n_tiles * S * S * ch, or null (ch = 1 or 3); or a slide region
+  int ch;
+  // slide mode (u8, ch==1): tile t starts at slide_origin[t] = (y*slideW + x) within u8
+  const int64_t *slide_origin;
+  int slideW;           // row pitch in bytes of the slide region (0 = packed tiles)
+};
+
+ADP_DEVINL float first_conv_fetch(const FirstConvSrc &s, int tile, int S, int si, int sj) {
+  if (s.f32) return s.f32[((size_t)tile * S + si) * S + sj];
+  if (s.slideW) return (float)s.u8[s.slide_origin[tile] + (int64_t)si * s.slideW + sj];
+  if (s.ch == 1) return (float)s.u8[((size_t)tile * S + si) * S + sj];
+  const uint8_t *q = s.u8 + (((size_t)tile * S + si) * S + sj) * 3;
+  int y = (4899 * (int)q[0] + 9617 * (int)q[1] + 1868 * (int)q[2] + 8192) >> 14;
+  return (float)y;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+first_conv_kernel(FirstConvSrc src, const int *__restrict__ fw_tile, const int *__restrict__ fw_op,
+                  int S, float mean_f, float sd_f, const float *__restrict__ w /*[9][C]*/,
+                  const float *__restrict__ bias /*[C]*/, View<T> out) {
+  extern __shared__ float sm[];
+  float *ws = sm;                 // 9*C
+  float *bs = sm + 9 * out.C;     // C
+  for (int i = threadIdx.x + threadIdx.y * 16; i < 9 * out.C; i += 256) ws[i] = w[i];
+  for (int i = threadIdx.x + threadIdx.y * 16; i < out.C; i += 256) bs[i] = bias[i];
+  __syncthreads();
+  const int x = blockIdx.x * 16 + threadIdx.x;
+  const int y = blockIdx.y * 16 + threadIdx.y;
+  const int f = blockIdx.z;
+  if (x >= S || y >= S) return;
+  const int tile = fw_tile[f], op = fw_op[f];
+  float v[9];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      int i = y + ky - 1, j = x + kx - 1;
+      float val = 0.f;    // 'same' zero padding applies to the normalised image
+      if (i >= 0 && i < S && j >= 0 && j < S) {
+        int si, sj;
+        d4_src(op, i, j, S, si, sj);
+        float raw = first_conv_fetch(src, tile, S, si, sj);
+        val = __fdiv_rn(__fsub_rn(raw, mean_f), sd_f);
+      }
+      v[ky * 3 + kx] = val;
+    }
+  T *o = out.p + (size_t)f * out.img_stride() + ((size_t)y * S + x) * out.pitch + out.coff;
+  for (int c0 = 0; c0 < out.C; c0 += 8) {
+    float a[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = bs[c0 + c];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[c] = fmaf(v[t], ws[t * out.C + c0 + c], a[c]);
+    if constexpr (sizeof(T) == 2) {
+      __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) h[c] = __float2bfloat16_rn(fmaxf(a[c], 0.f));
+      *reinterpret_cast<uint4 *>(o + c0) = *reinterpret_cast<uint4 *>(h);
+    } else {
+      float4 lo = make_float4(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f), fmaxf(a[2], 0.f), fmaxf(a[3], 0.f));
+      float4 hi = make_float4(fmaxf(a[4], 0.f), fmaxf(a[5], 0.f), fmaxf(a[6], 0.f), fmaxf(a[7], 0.f));
+      *reinterpret_cast<float4 *>(o + c0) = lo;
+      *reinterpret_cast<float4 *>(o + c0 + 4) = hi;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic Conv2D(3x3, same, dilation d) + bias + ReLU on CUDA cores (fp32 accumulate).
+// UP: the logical input is UpSampling2D((2,2)) nearest of `in` (out[y][x] = in[y//2][x//2],
+// train_adipose_unet_v3.py:691,698,705), folded into the gather.
+// One thread = one output pixel x 16 output channels.  grid = (W/16, H/16, nb * Cout/16).
+// w: [9][Cin][Cout] fp32 (padded, zero in pad rows/cols).
+template <typename T, bool UP>
+__global__ void __launch_bounds__(256)
+conv3x3_simt_kernel(View<T> in, View<T> out, const float *__restrict__ w, const float *__restrict__ bias,
+                    int dil, int relu) {
+  __shared__ float ws[9][16][16];
+  const int H = out.H, W = out.W;
+  const int cgroups = out.C >> 4;
+  const int n = blockIdx.z / cgroups;
+  const int co0 = (blockIdx.z % cgroups) << 4;
+  const int x = blockIdx.x * 16 + threadIdx.x;
+  const int y = blockIdx.y * 16 + threadIdx.y;
+  const int tid = threadIdx.y * 16 + threadIdx.x;
+  const bool live = (x < W) && (y < H);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  const T *ibase = in.p + (size_t)n * in.img_stride() + in.coff;
+  for (int c0 = 0; c0 < in.C; c0 += 16) {
+    __syncthreads();
+    for (int i = tid; i < 9 * 256; i += 256) {
+      int t = i >> 8, c = (i >> 4) & 15, co = i & 15;
+      ws[t][c][co] = w[((size_t)t * in.C + c0 + c) * out.C + co0 + co];
+    }
+    __syncthreads();
+    if (!live) continue;
+#pragma unroll 1
+    for (int t = 0; t < 9; ++t) {
+      const int iy = y + (t / 3 - 1) * dil, ix = x + (t % 3 - 1) * dil;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      const int sy = UP ? (iy >> 1) : iy, sx = UP ? (ix >> 1) : ix;
+      const T *ip = ibase + ((size_t)sy * in.W + sx) * in.pitch + c0;
+      float a[16];
+      if constexpr (sizeof(T) == 2) {
+        __align__(16) __nv_bfloat16 h[16];
+        *reinterpret_cast<uint4 *>(h) = *reinterpret_cast<const uint4 *>(ip);
+        *reinterpret_cast<uint4 *>(h + 8) = *reinterpret_cast<const uint4 *>(ip + 8);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) a[c] = __bfloat162float(h[c]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 f = *reinterpret_cast<const float4 *>(ip + 4 * q);
+          a[4 * q] = f.x; a[4 * q + 1] = f.y; a[4 * q + 2] = f.z; a[4 * q + 3] = f.w;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float4 *wr = reinterpret_cast<const float4 *>(&ws[t][c][0]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 wv = wr[q];
+          acc[4 * q] = fmaf(a[c], wv.x, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(a[c], wv.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(a[c], wv.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(a[c], wv.w, acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  if (!live) return;
+  T *o = out.p + (size_t)n * out.img_stride() + ((size_t)y * W + x) * out.pitch + out.coff + co0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float v = acc[i] + bias[co0 + i];
+    acc[i] = relu ? fmaxf(v, 0.f) : v;
+  }
+  if constexpr (sizeof(T) == 2) {
+    __align__(16) __nv_bfloat16 h[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) h[i] = __float2bfloat16_rn(acc[i]);
+    *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<uint4 *>(h);
+    *reinterpret_cast<uint4 *>(o + 8) = *reinterpret_cast<uint4 *>(h + 8);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4 *>(o + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPooling2D((2,2), strides=(2,2)) — train_adipose_unet_v3.py:670,674,678.  16-byte vectors.
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2_kernel(View<T> in, View<T> out, int nb) {
+  constexpr int V = 16 / sizeof(T);
+  const int vec_per_px = out.C / V;
+  const size_t total = (size_t)nb * out.H * out.W * vec_per_px;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int v = i % vec_per_px;
+    size_t px = i / vec_per_px;
+    int x = px % out.W;
+    size_t r = px / out.W;
+    int y = r % out.H;
+    int n = r / out.H;
+    const T *ip = in.p + (size_t)n * in.img_stride() + ((size_t)(2 * y) * in.W + 2 * x) * in.pitch + in.coff + v * V;
+    __align__(16) T a[V], b[V], c[V], d[V], m[V];
+    *reinterpret_cast<uint4 *>(a) = *reinterpret_cast<const uint4 *>(ip);
+    *reinterpret_cast<uint4 *>(b) = *reinterpret_cast<const uint4 *>(ip + in.pitch);
+    *reinterpret_cast<uint4 *>(c) = *reinterpret_cast<const uint4 *>(ip + (size_t)in.W * in.pitch);
+    *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(ip + (size_t)in.W * in.pitch + in.pitch);
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+      m[k] = from_f<T>(fmaxf(fmaxf(to_f(a[k]), to_f(b[k])), fmaxf(to_f(c[k]), to_f(d[k]))));
+    T *op = out.p + (size_t)n * out.img_stride() + ((size_t)y * out.W + x) * out.pitch + out.coff + v * V;
+    *reinterpret_cast<uint4 *>(op) = *reinterpret_cast<uint4 *>(m);
+  }
+}
+
+// Add([dilate1..6]) — train_adipose_unet_v3.py:688.  Dense buffers of identical shape.
+template <typename T>
+__global__ void __launch_bounds__(256)
+add6_kernel(const T *a0, const T *a1, const T *a2, const T *a3, const T *a4, const T *a5, T *out, size_t nvec) {
+  constexpr int V = 16 / sizeof(T);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    __align__(16) T r[6][V], o[V];
+    *reinterpret_cast<uint4 *>(r[0]) = reinterpret_cast<const uint4 *>(a0)[i];
+    *reinterpret_cast<uint4 *>(r[1]) = reinterpret_cast<const uint4 *>(a1)[i];
+    *reinterpret_cast<uint4 *>(r[2]) = reinterpret_cast<const uint4 *>(a2)[i];
+    *reinterpret_cast<uint4 *>(r[3]) = reinterpret_cast<const uint4 *>(a3)[i];
+    *reinterpret_cast<uint4 *>(r[4]) = reinterpret_cast<const uint4 *>(a4)[i];
+    *reinterpret_cast<uint4 *>(r[5]) = reinterpret_cast<const uint4 *>(a5)[i];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float s = to_f(r[0][k]);
+#pragma unroll
+      for (int j = 1; j < 6; ++j) s += to_f(r[j][k]);
+      o[k] = from_f<T>(s);
+    }
+    reinterpret_cast<uint4 *>(out)[i] = *reinterpret_cast<uint4 *>(o);
+  }
+}
+
+// Conv2D(2, 1x1, softmax) -> channel 1 -> squeeze  (train_adipose_unet_v3.py:748-750).
+// softmax(z)[1] == sigmoid(z1 - z0).  wh: [2][C] (padded with zeros), bh: [2].  One thread per pixel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_kernel(View<T> in, int nb, const float *__restrict__ wh, const float *__restrict__ bh, float *__restrict__ prob) {
+  extern __shared__ float sm[];
+  for (int i = threadIdx.x; i < 2 * in.C; i += blockDim.x) sm[i] = wh[i];
+  __syncthreads();
+  const size_t total = (size_t)nb * in.H * in.W;
+  const float b0 = bh[0], b1 = bh[1];
+  for (size_t px = blockIdx.x * (size_t)blockDim.x + threadIdx.x; px < total; px += (size_t)gridDim.x * blockDim.x) {
+    const T *ip = in.p + px * in.pitch + in.coff;   // images are contiguous: n*H*W + y*W + x
+    float z0 = 0.f, z1 = 0.f;
+    constexpr int V = 16 / sizeof(T);
+    for (int c0 = 0; c0 < in.C; c0 += V) {
+      __align__(16) T a[V];
+      *reinterpret_cast<uint4 *>(a) = *reinterpret_cast<const uint4 *>(ip + c0);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float v = to_f(a[k]);
+        z0 = fmaf(v, sm[c0 + k], z0);
+        z1 = fmaf(v, sm[in.C + c0 + k], z1);
+      }
+    }
+    z0 += b0; z1 += b1;
+    prob[px] = 1.f / (1.f + expf(z0 - z1));
+  }
+}
+
+}  // namespace adp

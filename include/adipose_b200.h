@@ -1,0 +1,187 @@
+/*
+ * adipose_b200.h — C ABI of libadipose_b200.so
+ *
+ * B200-native (sm_100a) replacement for the U-Net segmentation hot path of
+ * MAGIC-SCAN/adipose_tissue-unet.  The reference has no FFI: its seam is a
+ * duck-typed Python object.  Each entry point below names
+ * the reference interface it replaces (paths relative to the reference root);
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions: every function returns 0 on success and a negative ADP_E* code on
+ * failure (adp_last_error() gives the message; no exception crosses the
+ * boundary).  Buffers are caller-owned.  Every data pointer may be a host
+ * pointer (pageable or pinned) or a CUDA device pointer on the engine's device;
+ * the library detects which.  One CUDA stream per engine; an engine must not be
+ * used from two threads at once.  All calls are synchronous on return unless
+ * stated otherwise.  There is NO CPU fallback: adp_create fails without a
+ * compute-capability-10.x device.
+ */
+#ifndef ADIPOSE_B200_H
+#define ADIPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADP_ABI_VERSION 1
+
+/* error codes */
+#define ADP_OK 0
+#define ADP_EINVAL -1   /* bad argument */
+#define ADP_ECUDA -2    /* CUDA runtime / driver error */
+#define ADP_ENODEV -3   /* no sm_100 device */
+#define ADP_ESTATE -4   /* call out of order (e.g. predict before weights are loaded) */
+#define ADP_ENOMEM -5
+
+/* arithmetic of the convolution path */
+#define ADP_PREC_FP32 0       /* fp32 activations, CUDA-core FFMA convs (exact-fp32 parity path) */
+#define ADP_PREC_BF16 1       /* bf16 activations, tcgen05/TMEM implicit-GEMM convs, fp32 accumulate */
+#define ADP_PREC_BF16_SIMT 2  /* bf16 activations, CUDA-core convs (cross-check of the tcgen05 path) */
+
+/* blend modes — GaussianBlender / LinearBlender, Segmentation/full_evaluation_enhanced.py:115-204 */
+#define ADP_BLEND_GAUSSIAN 0
+#define ADP_BLEND_LINEAR 1
+
+/* Dihedral op codes (aug image A[i][j] = img[src(i,j)], N = tile size):
+ *  0 ident (i,j)       1 rot90 (j,N-1-i)    2 rot180 (N-1-i,N-1-j)   3 rot270 (N-1-j,i)
+ *  4 flip_h (i,N-1-j)  5 flip_v (N-1-i,j)   6 flip_h∘rot90 (N-1-j,N-1-i)   7 flip_v∘rot90 (j,i)
+ * TestTimeAugmentation modes (full_evaluation_enhanced.py:545-575, segmentation_inference.py:181-219):
+ *  minimal = {0,4}   basic = {0,4,5,1}   full = {0,1,2,3,4,5,6,7}   (this order) */
+#define ADP_TTA_NONE 0
+#define ADP_TTA_MINIMAL 1
+#define ADP_TTA_BASIC 2
+#define ADP_TTA_FULL 3
+
+typedef struct adp_engine adp_engine;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int adp_abi_version(void);
+const char *adp_last_error(void);           /* thread-local message of the last failing call */
+int adp_device_count(void);                 /* number of sm_100 devices visible, 0 if none */
+
+/* ---- engine lifetime ------------------------------------------------------------------------
+ * Replaces AdiposeUNet.__init__/build_model (full_evaluation_enhanced.py:1156-1264,
+ * segmentation_inference.py:82-146): the graph is fixed (init_nb, 22 convs), so "building"
+ * is allocating the engine.  max_forwards = how many (tile, augmentation) forwards are kept in
+ * flight per launch wave (activation arena is sized for it; 0 = default 16). */
+int adp_create(int device, int precision, int init_nb, int max_forwards, adp_engine **out);
+int adp_destroy(adp_engine *e);
+int adp_precision(const adp_engine *e);
+int adp_synchronize(adp_engine *e);
+
+/* ---- weights ---------------------------------------------------------------------------------
+ * Replaces net.load_weights / load_legacy_weights (full_evaluation_enhanced.py:1266-1301): the
+ * host layer parses the .h5 and hands over one tensor pair per Keras layer name
+ * ("down1_conv1" ... "up1_conv3", "dilate1".."dilate6", "output_softmax"): kernel float32 HWIO
+ * (kh,kw,cin,cout) and bias (cout).  adp_get_weight copies the fp32 master copy back out. */
+int adp_set_weight(adp_engine *e, const char *layer, const float *kernel_hwio, const int64_t kshape[4],
+                   const float *bias, int64_t nbias);
+int adp_get_weight(adp_engine *e, const char *layer, float *kernel_hwio, int64_t kernel_elems,
+                   float *bias, int64_t nbias);
+int adp_weights_ready(adp_engine *e);       /* 1 if all 22 layers are set, else 0 */
+
+/* ---- tile inference ---------------------------------------------------------------------------
+ * Replaces AdiposeUNet.predict_single (full_evaluation_enhanced.py:1303-1321,
+ * segmentation_inference.py:153-158) and TestTimeAugmentation.predict_with_tta
+ * (full_evaluation_enhanced.py:577-600) for a batch of n square tiles of side `size`
+ * (multiple of 8; 1024 in the reference): x = (tile - mean) / (std + 1e-10) in float32,
+ * forward, inverse dihedral op, mean over the n_ops augmentations in list order.
+ * tiles: n*size*size float32 (gray 0..255).  out: n*size*size float32 probabilities.
+ * ops == NULL or n_ops == 0 means a single identity forward. */
+int adp_predict(adp_engine *e, const float *tiles, int n, int size, float mean, float std,
+                const int *ops, int n_ops, float *out);
+/* same, uint8 input; channels = 1 (gray) or 3 (interleaved RGB, converted with OpenCV's
+ * 8-bit formula Y=(4899R+9617G+1868B+8192)>>14, i.e. cv2.imread(..., IMREAD_GRAYSCALE) of
+ * the reference, train_adipose_unet_v3.py:555) */
+int adp_predict_u8(adp_engine *e, const uint8_t *tiles, int n, int size, int channels, float mean,
+                   float std, const int *ops, int n_ops, float *out);
+int adp_tta_ops(int mode, int ops[8]);      /* fills ops, returns their count (1,2,4,8) */
+/* de-augment + average only: planes = n_ops probability maps (size*size each) predicted on the
+ * augmented inputs aug_k(img) by ANY predict_single backend (the reference's ONNX seam,
+ * segmentation_inference.py:161-178); out = mean_k deaug_k(planes[k]) — the tail of
+ * TestTimeAugmentation.predict_with_tta (full_evaluation_enhanced.py:591-594). */
+int adp_tta_combine(adp_engine *e, const float *planes, int size, const int *ops, int n_ops, float *out);
+
+/* per-layer activation tap for parity tests: after adp_predict with n*n_ops <= max_forwards,
+ * copies layer `name` of forward `idx` out as float32 NHWC (h*w*channels, unpadded channels).
+ * Names: the 21 3x3 conv layers, "dilate_add", "prob". */
+int adp_debug_layer(adp_engine *e, const char *name, int idx, float *out, int64_t out_elems,
+                    int64_t shape_hwc[3]);
+
+/* ---- threshold + pixel metrics -----------------------------------------------------------------
+ * Replaces binarize_prediction / calculate_pixel_metrics (full_evaluation_enhanced.py:716-785):
+ * mask = (p > thr) as uint8 (may be NULL), truth = (gt > 0.5) (gt uint8, may be NULL -> counts
+ * only count predicted positives in counts[0] and negatives in counts[3]).
+ * counts = {tp, fp, fn, tn}.  The ratios (+1e-10) are formed by the caller in float64. */
+int adp_threshold_metrics(adp_engine *e, const float *prob, const uint8_t *gt, int64_t n_px, float thr,
+                          uint8_t *mask, int64_t counts[4]);
+
+/* ---- blenders ----------------------------------------------------------------------------------
+ * Replaces GaussianBlender.reconstruct / LinearBlender.reconstruct
+ * (full_evaluation_enhanced.py:149-204).  tiles: n tiles of th*tw float32, positions (y,x) in list
+ * order, window: th*tw float32 weight map slice (Gaussian; NULL for linear), out: H*W float32.
+ * Bit-exact with the NumPy code for identical inputs (same fp32 mul, add, div, same tile order). */
+int adp_blend_reconstruct(adp_engine *e, int blend_mode, const float *tiles, int n, int th, int tw,
+                          const int32_t *ys, const int32_t *xs, const float *window, int H, int W,
+                          float *out);
+
+/* ---- whole-slide sliding window (persistent accumulator) ---------------------------------------
+ * Replaces SlidingWindowInference.predict_with_sliding_window (full_evaluation_enhanced.py:286-329)
+ * and reconstruct_slide (reconstruct_full_images.py:334-417) without ever holding the per-tile
+ * predictions: tiles are predicted (TTA) and blend-accumulated on the device.
+ * The accumulator covers slide rows [y0, y0+rows) x [0, W): a rank that owns a tile-row strip
+ * passes its own row range (multi-GPU sharding).
+ * window: tile*tile float32 (Gaussian) or NULL (linear). */
+int adp_wsi_begin(adp_engine *e, int rows, int W, int y0, int tile, int blend_mode, const float *window);
+/* predict n tiles (float32 gray 0..255) and accumulate them at slide positions (ys[i], xs[i]) */
+int adp_wsi_push_tiles(adp_engine *e, const float *tiles, int n, const int32_t *ys, const int32_t *xs,
+                       float mean, float std, const int *ops, int n_ops);
+/* same, the tiles are cut on the device from a resident uint8 gray slide region
+ * (slide: region_rows x W bytes covering rows [region_y0, ...)) — the sliding-window case */
+int adp_wsi_push_from_slide(adp_engine *e, const uint8_t *slide, int region_y0, int region_rows,
+                            int n, const int32_t *ys, const int32_t *xs, float mean, float std,
+                            const int *ops, int n_ops);
+/* add already-predicted probability tiles (blend only; used for ground-truth re-blending,
+ * reconstruct_full_images.py:404-415) */
+int adp_wsi_push_probs(adp_engine *e, const float *probs, int n, const int32_t *ys, const int32_t *xs);
+/* raw partial sums of rows [y, y+rows) (slide coordinates): acc and weight (float32 each; for
+ * linear blending weight holds the count as float32) — the boundary rows a strip owner ships */
+int adp_wsi_export(adp_engine *e, int y, int rows, float *acc, float *weight);
+/* add another strip's partial sums into this accumulator */
+int adp_wsi_import_add(adp_engine *e, int y, int rows, const float *acc, const float *weight);
+/* normalise rows [y, y+rows): prob = acc / max(weight, 1e-8) (linear: / max(count,1)), threshold,
+ * count.  prob, mask, gt may each be NULL.  counts = {tp, fp, fn, tn}. */
+int adp_wsi_finalize(adp_engine *e, int y, int rows, float thr, float *prob, uint8_t *mask,
+                     const uint8_t *gt, int64_t counts[4]);
+int adp_wsi_end(adp_engine *e);
+
+/* ---- loss / training step ----------------------------------------------------------------------
+ * adp_loss_metrics: combined_loss_standard = mean BCE + (1 - global Dice) and dice_coef
+ * (train_adipose_unet_v3.py:217-241, src/utils/model.py:93-98) of probabilities p against y,
+ * n_px pixels over the whole batch; dldp (may be NULL) receives dL/dp.
+ * out = {loss, bce_mean, dice_loss, dice_coef}. */
+int adp_loss_metrics(adp_engine *e, const float *p, const float *y, int64_t n_px, float *dldp, double out[4]);
+
+/* ---- profiling ---------------------------------------------------------------------------------
+ * When enabled, every kernel launch is bracketed by CUDA events on the engine stream and
+ * accumulated per kernel kind.  adp_profile_read returns up to `cap` rows
+ * (name, launches, total milliseconds, algorithmic flops, algorithmic bytes). */
+typedef struct adp_prof_row {
+  char name[48];
+  int64_t launches;
+  double ms;
+  double flops;
+  double bytes;
+} adp_prof_row;
+int adp_profile_enable(adp_engine *e, int on);
+int adp_profile_reset(adp_engine *e);
+int adp_profile_read(adp_engine *e, adp_prof_row *rows, int cap);
+int64_t adp_launch_count(adp_engine *e);    /* kernels launched by this engine since creation */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADIPOSE_B200_H */

@@ -1,0 +1,142 @@
+"""GPU parity of the U-Net forward against the PyTorch-CPU oracle (parity unpinned upstream:
+oracle/unet.py header).  Tolerances are BASELINE.json's: max-abs probability error <= 1e-4 on the
+fp32 path, <= 1e-2 on the bf16 path; thresholded-mask Dice agreement >= 0.999."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import adipose_unet_b200 as A
+from adipose_unet_b200 import api
+from oracle import geometry as G
+from oracle import unet as U
+
+MEAN, STD = A.synth.DEFAULT_MEAN, A.synth.DEFAULT_STD
+TOL = {"fp32": 1e-4, "bf16": 1e-2, "bf16_simt": 1e-2}
+LAYER_TAPS = ["down1_conv2", "down2_conv2", "down3_conv2", "dilate1", "dilate2", "dilate3", "dilate4", "dilate5",
+              "dilate6", "dilate_add", "up3_conv1", "up3_conv2", "up3_conv3", "up2_conv1", "up2_conv2", "up2_conv3",
+              "up1_conv1", "up1_conv2", "up1_conv3"]
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return A.synth.init_weights()
+
+
+@pytest.fixture(scope="module")
+def params(weights):
+    return U.to_torch_params(weights)
+
+
+_models = {}
+
+
+def model(prec, weights):
+    if prec not in _models:
+        m = api.AdiposeUNet(precision=prec, max_forwards=16)
+        m.build_model()
+        m.set_weights(weights)
+        _models[prec] = m
+    return _models[prec]
+
+
+def mask_dice(a, b):
+    a = a > 0.5; b = b > 0.5
+    return (2.0 * (a & b).sum() + 1e-10) / (a.sum() + b.sum() + 1e-10)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16_simt", "bf16"])
+def test_per_layer_256(prec, weights, params):
+    S = 256
+    tile = A.synth.ecm_tile(S, seed=21).astype(np.float32)
+    taps = {}
+    with torch.no_grad():
+        x = torch.from_numpy((tile - MEAN) / (STD + 1e-10)).float().unsqueeze(0)
+        U.forward(x, params, taps=taps)
+    m = model(prec, weights)
+    out = m.predict_single(tile, MEAN, STD)
+    rel_tol = 1e-4 if prec == "fp32" else 3e-2
+    worst = {}
+    for name in LAYER_TAPS:
+        ref = taps[name][0].permute(1, 2, 0).numpy()
+        got = m.engine.debug_layer(name, 0)
+        assert got.shape == ref.shape, name
+        worst[name] = float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-6))
+    bad = {k: v for k, v in worst.items() if not v <= rel_tol}
+    assert not bad, f"{prec}: per-layer rel-to-max error over {rel_tol}: {bad} (all: {worst})"
+    err = float(np.abs(out - taps["prob"][0].numpy()).max())
+    assert err <= TOL[prec], f"{prec}: prob max-abs err {err}"
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_tta_full_256(prec, weights, params):
+    S = 256
+    tile = A.synth.ecm_tile(S, seed=22).astype(np.float32)
+    ref = U.predict_with_tta(tile, MEAN, STD, params, "full")
+    m = model(prec, weights)
+    out, info = m.predict(tile, MEAN, STD, use_tta=True, tta_mode="full")
+    assert info["num_augmentations"] == 8
+    assert np.abs(out - ref).max() <= TOL[prec]
+    if prec == "fp32":
+        assert mask_dice(out, ref) >= 0.999
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_batch_and_modes_128(prec, weights, params):
+    S = 128
+    tiles = A.synth.ecm_tiles(5, S, seed=30)
+    m = model(prec, weights)
+    for mode in (None, "minimal", "basic"):
+        out = m.predict_batch(tiles, MEAN, STD, mode)
+        for i in range(5):
+            ref = U.predict_single(tiles[i], MEAN, STD, params) if mode is None else \
+                U.predict_with_tta(tiles[i], MEAN, STD, params, mode)
+            assert np.abs(out[i] - ref).max() <= TOL[prec], (mode, i)
+
+
+def test_u8_and_rgb_front_end(weights, params):
+    S = 128
+    m = model("fp32", weights)
+    gray = A.synth.ecm_tile(S, seed=40)
+    rgb = A.synth.rgb_tile(S, seed=41)
+    out_g = m.engine.predict(gray[None], MEAN, STD)[0]
+    assert np.abs(out_g - U.predict_single(gray.astype(np.float32), MEAN, STD, params)).max() <= 1e-4
+    import cv2
+    g_cv = cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY)
+    np.testing.assert_array_equal(A.synth.rgb_to_gray_u8(rgb), g_cv)
+    out_c = m.engine.predict(rgb[None], MEAN, STD)[0]
+    assert np.abs(out_c - U.predict_single(g_cv.astype(np.float32), MEAN, STD, params)).max() <= 1e-4
+
+
+def test_full_size_1024_fp32_and_bf16(weights, params):
+    """BASELINE config 1: one 1024^2 ECM tile, batch 1."""
+    tile = A.synth.ecm_tile(1024).astype(np.float32)
+    ref = U.predict_single(tile, MEAN, STD, params)
+    for prec in ("fp32", "bf16"):
+        out = model(prec, weights).predict_single(tile, MEAN, STD)
+        err = float(np.abs(out - ref).max())
+        assert err <= TOL[prec], (prec, err)
+        d = mask_dice(out, ref)
+        band = float((np.abs(ref - 0.5) < TOL[prec]).mean())
+        print(f"1024^2 {prec}: max|dp|={err:.2e} mask-dice={d:.5f} px within tol of 0.5: {band:.4%}")
+        if prec == "fp32":
+            assert d >= 0.999
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_sliding_window_native(prec, weights, params):
+    S = 128
+    img = A.synth.synthetic_slide(300, 420, block=128).astype(np.float32)
+    sw = api.SlidingWindowInference(tile_size=S, overlap=0.5, blend_mode="gaussian", verbose=False)
+    m = model(prec, weights)
+    out = sw.predict_with_sliding_window(img, m, MEAN, STD, use_tta=True, tta_mode="basic")
+    pos = G.tile_positions(300, 420, S, sw.stride)
+    preds = [U.predict_with_tta(np.ascontiguousarray(img[y:y + S, x:x + S]), MEAN, STD, params, "basic") for y, x in pos]
+    ref = G.gaussian_reconstruct(preds, pos, img.shape, G.gaussian_window(S))
+    assert np.abs(out - ref).max() <= TOL[prec]
+    sw2 = api.SlidingWindowInference(tile_size=S, overlap=0.75, blend_mode="linear", verbose=False)
+    out2 = sw2.predict_with_sliding_window(img, m, MEAN, STD)
+    pos2 = G.tile_positions(300, 420, S, sw2.stride)
+    preds2 = [U.predict_single(np.ascontiguousarray(img[y:y + S, x:x + S]), MEAN, STD, params) for y, x in pos2]
+    assert np.abs(out2 - G.linear_reconstruct(preds2, pos2, img.shape)).max() <= TOL[prec]

@@ -1,0 +1,101 @@
+"""GPU parity of the post-processing kernels against the vectors the reference's own NumPy code
+produced (tests/golden) — bit-exact — and against the oracle for the loss."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from adipose_unet_b200 import api
+from oracle import geometry as G
+from oracle import unet as U
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return api.default_engine()
+
+
+@pytest.mark.parametrize("mode", ["minimal", "basic", "full"])
+def test_tta_combine_bit_exact_vs_reference(golden, fake_model, mode):
+    img = golden["tta_img"]
+    avg, info = api.TestTimeAugmentation(mode).predict_with_tta(fake_model, img, 127.5, 50.0)
+    np.testing.assert_array_equal(avg, golden[f"tta_{mode}_avg"])
+    assert info["num_augmentations"] == len(G.TTA_OPCODES[mode])
+
+
+@pytest.mark.parametrize("size", [40, 96, 1024])
+def test_tta_combine_odd_sizes(eng, size):
+    rng = np.random.default_rng(size)
+    planes = rng.random((8, size, size), dtype=np.float32)
+    out = eng.tta_combine(planes, G.TTA_OPCODES["full"])
+    ref = G.tta_mean([G.d4_apply(G.D4_INVERSE[op], planes[k]) for k, op in enumerate(G.TTA_OPCODES["full"])])
+    np.testing.assert_array_equal(out, ref)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_blenders_bit_exact_vs_reference(golden, tag):
+    tiles = [t.astype(np.float32) for t in golden[f"blend_{tag}_tiles"]]
+    pos = [tuple(int(v) for v in p) for p in golden[f"blend_{tag}_pos"]]
+    shape = tuple(int(v) for v in golden[f"blend_{tag}_shape"])
+    np.testing.assert_array_equal(api.GaussianBlender(tile_size=64).reconstruct(tiles, pos, shape), golden[f"blend_{tag}_gauss"])
+    np.testing.assert_array_equal(api.LinearBlender().reconstruct(tiles, pos, shape), golden[f"blend_{tag}_linear"])
+
+
+@pytest.mark.parametrize("blend", ["gaussian", "linear"])
+def test_sliding_window_foreign_model_bit_exact(golden, fake_model, blend):
+    sw = api.SlidingWindowInference(tile_size=64, overlap=0.5, blend_mode=blend, verbose=False)
+    out = sw.predict_with_sliding_window(golden["sw_img"], fake_model, 127.5, 50.0, use_tta=True, tta_mode="full")
+    np.testing.assert_array_equal(out, golden[f"sw_{blend}"])
+
+
+def test_blend_edge_cases(eng):
+    # uncovered pixels -> 0 (weight_sum clamp), single tile, empty list
+    win = G.gaussian_window(64)
+    t = np.full((64, 64), 0.75, np.float32)
+    out = api.GaussianBlender(64).reconstruct([t], [(10, 20)], (100, 120))
+    ref = G.gaussian_reconstruct([t], [(10, 20)], (100, 120), win)
+    np.testing.assert_array_equal(out, ref)
+    assert out[0, 0] == 0.0
+    np.testing.assert_array_equal(api.LinearBlender().reconstruct([t], [(10, 20)], (100, 120)),
+                                  G.linear_reconstruct([t], [(10, 20)], (100, 120)))
+    assert api.LinearBlender().reconstruct([], [], (8, 8)).sum() == 0
+
+
+def test_threshold_and_metrics_vs_reference(golden):
+    pred, gt = golden["met_pred"], golden["met_gt"]
+    np.testing.assert_array_equal(api.binarize_prediction(pred, 0.5), golden["met_bin"])
+    keys = [str(k) for k in golden["met_keys"]]
+    cases = {"rand": (pred, gt, 0.5), "thr7": (pred, gt, 0.7),
+             "empty": (np.zeros((16, 16), np.float32), np.zeros((16, 16), np.uint8), 0.5),
+             "nopred": (np.zeros((16, 16), np.float32), np.ones((16, 16), np.uint8), 0.5)}
+    for tag, (p, g, thr) in cases.items():
+        m = api.calculate_pixel_metrics(p, g, thr)
+        np.testing.assert_array_equal(np.array([float(m[k]) for k in keys]), golden[f"met_{tag}"])
+
+
+def test_metrics_large_counts_exact(eng):
+    rng = np.random.default_rng(5)
+    p = rng.random((4096, 4096), dtype=np.float32)
+    g = (rng.random((4096, 4096)) > 0.3).astype(np.uint8)
+    mask, counts = eng.threshold_metrics(p, g, 0.5)
+    ref = G.pixel_metrics(p, g, 0.5)
+    assert counts == (ref["tp"], ref["fp"], ref["fn"], ref["tn"])
+    np.testing.assert_array_equal(mask, G.binarize(p, 0.5))
+    assert sum(counts) == p.size
+
+
+def test_loss_and_grad_vs_oracle(eng):
+    rng = np.random.default_rng(9)
+    y = (rng.random((2, 128, 128)) > 0.6).astype(np.float32)
+    p = rng.random((2, 128, 128)).astype(np.float32)
+    p[0, 0, :4] = [0.0, 1.0, 1e-8, 1 - 1e-8]          # exercise the clip
+    res, g = eng.loss_metrics(p, y, want_grad=True)
+    pt = torch.from_numpy(p).double().requires_grad_(True)
+    yt = torch.from_numpy(y).double()
+    loss = U.combined_loss_standard(yt, pt)
+    loss.backward()
+    assert abs(res["loss"] - float(loss)) <= 1e-6 * max(1.0, abs(float(loss)))
+    assert abs(res["dice_coef"] - float(U.dice_coef(yt, pt.detach()))) <= 1e-6
+    gref = pt.grad.numpy()
+    assert np.abs(g - gref).max() <= 1e-6 * max(1.0, np.abs(gref).max())
