@@ -211,6 +211,9 @@ class Engine:
     def synchronize(self):
         _lib.check(self.lib.adp_synchronize(self.h))
 
+    def stream_ptr(self) -> int:
+        return int(self.lib.adp_stream(self.h) or 0)
+
 
 _default_engine: Optional[Engine] = None
 

@@ -59,7 +59,7 @@ struct ConvTcParams {
   int out_pitch, out_coff, Hout, Wout, oscale;
   int relu;
   uint32_t idesc;
-  int dbg;                       // bit0: swap LBO/SBO (descriptor probe)
+  int dbg;                       // reserved for kernel experiments
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -135,8 +135,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
       const uint32_t sA_u = ptx::smem_u32(sA), sB_u = ptx::smem_u32(sB);
       const uint32_t plane_a = (uint32_t)p.PW * 16u;          // bytes between channel-group planes (A)
       const uint32_t plane_b = (uint32_t)p.N * 16u;           // bytes between channel-group planes (B)
-      const uint32_t a_lbo = (p.dbg & 1) ? 128u : plane_a, a_sbo = (p.dbg & 1) ? plane_a : 128u;
-      const uint32_t b_lbo = (p.dbg & 1) ? 128u : plane_b, b_sbo = (p.dbg & 1) ? plane_b : 128u;
+      // K-major / SWIZZLE_NONE: LBO = distance between the two 16-byte K chunks of one MMA (the
+      // next channel-group plane), SBO = distance between 8-row core matrices (8 pixels x 16 B).
+      const uint32_t a_lbo = plane_a, a_sbo = 128u, b_lbo = plane_b, b_sbo = 128u;
       const int kk_n = p.CG >> 1;                             // MMAs (K=16) per chunk and tap
       int it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {

@@ -711,6 +711,8 @@ int adp_synchronize(adp_engine *e) {
   ADP_CATCH
 }
 
+void *adp_stream(adp_engine *e) { return e ? (void *)e->stream : nullptr; }
+
 int adp_set_weight(adp_engine *e, const char *layer_name, const float *kernel, const int64_t kshape[4], const float *bias,
                    int64_t nbias) {
   ADP_TRY

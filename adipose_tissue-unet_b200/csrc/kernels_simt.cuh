@@ -38,7 +38,7 @@ ADP_DEVINL float first_conv_fetch(const FirstConvSrc &s, int tile, int S, int si
   if (s.slideW) return (float)s.u8[s.slide_origin[tile] + (int64_t)si * s.slideW + sj];
   if (s.ch == 1) return (float)s.u8[((size_t)tile * S + si) * S + sj];
   const uint8_t *q = s.u8 + (((size_t)tile * S + si) * S + sj) * 3;
-  int y = (4899 * (int)q[0] + 9617 * (int)q[1] + 1868 * (int)q[2] + 8192) >> 14;
+  int y = (9798 * (int)q[0] + 19235 * (int)q[1] + 3735 * (int)q[2] + 16384) >> 15;   // OpenCV 4.x RGB2GRAY, 8-bit
   return (float)y;
 }
 

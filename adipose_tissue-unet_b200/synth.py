@@ -56,13 +56,14 @@ def rgb_tile(size: int = 1024, seed: int = SEED) -> np.ndarray:
 
 
 def rgb_to_gray_u8(rgb: np.ndarray) -> np.ndarray:
-    """OpenCV 8-bit RGB->gray: Y=(4899 R + 9617 G + 1868 B + 8192)>>14
-    (what cv2.imread(..., IMREAD_GRAYSCALE) yields for the reference,
-    train_adipose_unet_v3.py:555, full_evaluation_enhanced.py:1383)."""
+    """OpenCV 4.x 8-bit RGB->gray: Y=(9798 R + 19235 G + 3735 B + 16384)>>15, bit-identical to
+    cv2.cvtColor(RGB2GRAY) (checked against the installed 4.13; the reference pins 4.8.0.76 and
+    reads tiles with cv2.imread(..., IMREAD_GRAYSCALE), train_adipose_unet_v3.py:555,
+    full_evaluation_enhanced.py:1383)."""
     r = rgb[..., 0].astype(np.int32)
     g = rgb[..., 1].astype(np.int32)
     b = rgb[..., 2].astype(np.int32)
-    return ((4899 * r + 9617 * g + 1868 * b + 8192) >> 14).astype(np.uint8)
+    return ((9798 * r + 19235 * g + 3735 * b + 16384) >> 15).astype(np.uint8)
 
 
 def slide_block(by: int, bx: int, block: int = 1024, seed: int = SEED) -> np.ndarray:

@@ -71,6 +71,7 @@ int adp_create(int device, int precision, int init_nb, int max_forwards, adp_eng
 int adp_destroy(adp_engine *e);
 int adp_precision(const adp_engine *e);
 int adp_synchronize(adp_engine *e);
+void *adp_stream(adp_engine *e);            /* the engine's cudaStream_t (for event timing by the caller) */
 
 /* ---- weights ---------------------------------------------------------------------------------
  * Replaces net.load_weights / load_legacy_weights (full_evaluation_enhanced.py:1266-1301): the
@@ -93,9 +94,9 @@ int adp_weights_ready(adp_engine *e);       /* 1 if all 22 layers are set, else 
  * ops == NULL or n_ops == 0 means a single identity forward. */
 int adp_predict(adp_engine *e, const float *tiles, int n, int size, float mean, float std,
                 const int *ops, int n_ops, float *out);
-/* same, uint8 input; channels = 1 (gray) or 3 (interleaved RGB, converted with OpenCV's
- * 8-bit formula Y=(4899R+9617G+1868B+8192)>>14, i.e. cv2.imread(..., IMREAD_GRAYSCALE) of
- * the reference, train_adipose_unet_v3.py:555) */
+/* same, uint8 input; channels = 1 (gray) or 3 (interleaved RGB, converted with OpenCV 4.x's
+ * 8-bit fixed-point formula Y=(9798R+19235G+3735B+16384)>>15 == cv2.cvtColor(RGB2GRAY); the
+ * reference reads tiles with cv2.imread(..., IMREAD_GRAYSCALE), train_adipose_unet_v3.py:555) */
 int adp_predict_u8(adp_engine *e, const uint8_t *tiles, int n, int size, int channels, float mean,
                    float std, const int *ops, int n_ops, float *out);
 int adp_tta_ops(int mode, int ops[8]);      /* fills ops, returns their count (1,2,4,8) */

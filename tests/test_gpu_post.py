@@ -91,11 +91,17 @@ def test_loss_and_grad_vs_oracle(eng):
     p = rng.random((2, 128, 128)).astype(np.float32)
     p[0, 0, :4] = [0.0, 1.0, 1e-8, 1 - 1e-8]          # exercise the clip
     res, g = eng.loss_metrics(p, y, want_grad=True)
-    pt = torch.from_numpy(p).double().requires_grad_(True)
-    yt = torch.from_numpy(y).double()
+    # float32 oracle: the clip bounds 1e-7 / 1-1e-7 are float32 quantities in TF as well
+    pt = torch.from_numpy(p).requires_grad_(True)
+    yt = torch.from_numpy(y)
     loss = U.combined_loss_standard(yt, pt)
     loss.backward()
-    assert abs(res["loss"] - float(loss)) <= 1e-6 * max(1.0, abs(float(loss)))
-    assert abs(res["dice_coef"] - float(U.dice_coef(yt, pt.detach()))) <= 1e-6
+    assert abs(res["loss"] - float(loss.detach())) <= 2e-6 * max(1.0, abs(float(loss.detach())))
+    assert abs(res["dice_coef"] - float(U.dice_coef(yt, pt.detach()))) <= 2e-6
     gref = pt.grad.numpy()
-    assert np.abs(g - gref).max() <= 1e-6 * max(1.0, np.abs(gref).max())
+    assert np.abs(g - gref).max() <= 2e-6 * max(1.0, np.abs(gref).max())
+    # away from the clip the float64 oracle agrees to 1e-6 too
+    p2 = np.clip(p, 0.01, 0.99)
+    res2 = eng.loss_metrics(p2, y)
+    l64 = float(U.combined_loss_standard(yt.double(), torch.from_numpy(p2).double()))
+    assert abs(res2["loss"] - l64) <= 1e-6 * max(1.0, abs(l64))
