@@ -227,34 +227,37 @@ void plan_tc(ConvLayer &L) {
       for (int t = 0; t < 9; ++t) { p.tap_box[t] = t / 3; p.tap_row[t] = 0; p.tap_xs[t] = (t % 3) * L.dil; }
     }
   }
-  // channel chunk: largest divisor (in units of 16) that fits the shared-memory budget
-  const int k16 = L.cin_pad / 16;
-  const size_t budget = 200 * 1024;
-  int best = 1;
-  for (int k = k16; k >= 1; --k) {
-    if (k16 % k) continue;
-    size_t a = (size_t)p.nbox * (((size_t)p.BR * (2 * k) * p.PW * 16 + 127) / 128 * 128);
-    a = (a + 1023) / 1024 * 1024;
-    size_t b = ((size_t)16 * k * N * 2 + 127) / 128 * 128;
-    if (2 * a + 4 * b <= budget && a <= 80 * 1024) { best = k; break; }
-  }
-  const int KC = 16 * best;
-  p.CG = KC / 8; p.nchunks = k16 / best;
-  p.a_box_stride = (uint32_t)(((size_t)p.BR * p.CG * p.PW * 16 + 127) / 128 * 128);
-  p.a_stride = (uint32_t)(((size_t)p.nbox * p.a_box_stride + 1023) / 1024 * 1024);
-  p.a_tx_bytes = (uint32_t)((size_t)p.nbox * p.BR * p.CG * p.PW * 16);
-  p.b_bytes = (uint32_t)((size_t)KC * N * 2);
-  p.b_stride = (p.b_bytes + 127) / 128 * 128;
-  p.SB = (int)std::min<size_t>(8, std::max<size_t>(3, (32 * 1024) / p.b_stride));
-  size_t rest = budget - (size_t)p.SB * p.b_stride;
-  p.SA = (int)std::min<size_t>(4, std::max<size_t>(2, rest / p.a_stride));
+  // one pipeline stage = 16 input channels: activation boxes + the weight blocks of all taps
+  p.nchunks = L.cin_pad / 16;
+  p.a_box_stride = (uint32_t)(((size_t)p.BR * 2 * p.PW * 16 + 127) / 128 * 128);
+  p.a_bytes = (uint32_t)(((size_t)p.nbox * p.a_box_stride + 127) / 128 * 128);
+  p.a_tx_bytes = (uint32_t)((size_t)p.nbox * p.BR * 2 * p.PW * 16);
+  p.b_bytes = (uint32_t)((size_t)p.ntaps * N * 32);
+  p.stage_stride = (uint32_t)(((size_t)p.a_bytes + p.b_bytes + 1023) / 1024 * 1024);
+  const size_t budget = 220 * 1024;
+  p.S = (int)std::min<size_t>(8, budget / p.stage_stride);
+  ADP_REQUIRE(p.S >= 2, "conv stage does not fit shared memory twice");
   p.idesc = ptx::make_idesc(128, N, 1);
   p.relu = 1;
-  for (int v = 0; v < p.nvar; ++v) p.var[v].wbase = v * p.nchunks * p.ntaps;
+  for (int v = 0; v < p.nvar; ++v) p.var[v].wbase = v * p.nchunks;
 }
 
 size_t tc_smem_bytes(const ConvTcParams &p) {
-  return (size_t)p.SA * p.a_stride + (size_t)p.SB * p.b_stride + (2 * p.SA + 2 * p.SB + 4) * 8 + 16;
+  return (size_t)p.S * p.stage_stride + (2 * p.S + 4) * 8 + 16;
+}
+
+typedef void (*ConvTcKernel)(const CUtensorMap, const ConvTcParams);
+ConvTcKernel tc_kernel_for(int ntaps, int T) {
+  if (ntaps == 9) {
+    if (T == 4) return conv_tc_kernel<9, 4>;
+    if (T == 2) return conv_tc_kernel<9, 2>;
+    if (T == 1) return conv_tc_kernel<9, 1>;
+  } else if (ntaps == 4) {
+    if (T == 4) return conv_tc_kernel<4, 4>;
+    if (T == 2) return conv_tc_kernel<4, 2>;
+    if (T == 1) return conv_tc_kernel<4, 1>;
+  }
+  throw Error(ADP_EINVAL, "no tcgen05 conv instantiation for this (taps, rows) pair");
 }
 
 // Effective padded fp32 weights wp[9][cin_pad][cout_pad] (concat layers: skip channels land in
@@ -290,14 +293,14 @@ void pack_layer(adp_engine *e, ConvLayer &L) {
   const ConvTcParams &p = L.tc;
   std::vector<float> w32 = padded_weights(L, h, false);   // sum taps in fp32, round once
   auto W = [&](int t, int ci, int co) -> float { return w32[((size_t)t * L.cin_pad + ci) * L.cout_pad + co]; };
-  const int KC = p.CG * 8, N = p.N;
-  const size_t blk = (size_t)KC * N;
+  const int KC = 16, N = p.N;
+  const size_t blk = (size_t)KC * N;      // one (chunk, tap) block: [2 planes][N][8]
   std::vector<__nv_bfloat16> pk((size_t)p.nvar * p.nchunks * p.ntaps * blk);
   for (int v = 0; v < p.nvar; ++v)
     for (int c = 0; c < p.nchunks; ++c)
       for (int t = 0; t < p.ntaps; ++t) {
-        __nv_bfloat16 *dst = pk.data() + ((size_t)p.var[v].wbase + (size_t)c * p.ntaps + t) * blk;
-        for (int g = 0; g < p.CG; ++g)
+        __nv_bfloat16 *dst = pk.data() + (((size_t)p.var[v].wbase + c) * p.ntaps + t) * blk;
+        for (int g = 0; g < 2; ++g)
           for (int n = 0; n < N; ++n)
             for (int j = 0; j < 8; ++j) {
               const int ci = c * KC + g * 8 + j;
@@ -392,7 +395,7 @@ const CUtensorMap &get_tmap(adp_engine *e, const ConvLayer &L, const DevBuf &src
   CUtensorMap m;
   cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)(C / 8), (cuuint64_t)H, (cuuint64_t)e->max_fw};
   cuuint64_t gstr[4] = {(cuuint64_t)pitch * 2, 16, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
-  cuuint32_t box[5] = {8, (cuuint32_t)p.PW, (cuuint32_t)p.CG, (cuuint32_t)p.BR, 1};
+  cuuint32_t box[5] = {8, (cuuint32_t)p.PW, 2, (cuuint32_t)p.BR, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   void *base = (void *)(src.as<__nv_bfloat16>() + coff);
   CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr,
@@ -425,8 +428,9 @@ void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs,
     const int nitems = nb * p.nty * p.ntx * p.nvar;
     const int grid = std::min(nitems, e->num_sms);
     const size_t smem = tc_smem_bytes(p);
-    e->launch("conv3x3_tcgen05", fl, by, [&] {
-      conv_tc_kernel<<<grid, 256, smem, e->stream>>>(tm, p);
+    ConvTcKernel kern = tc_kernel_for(p.ntaps, p.T);
+    e->launch(("conv3x3_tcgen05/" + name).c_str(), fl, by, [&] {
+      kern<<<grid, kTcThreads, smem, e->stream>>>(tm, p);
     });
     return;
   }
@@ -435,14 +439,14 @@ void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs,
   if (e->prec == ADP_PREC_FP32) {
     auto in = view<float>(src, Hs, Ws, spitch, scoff, L.cin_pad);
     auto out = view<float>(dst, Ho, Wo, dpitch, dcoff, L.cout_pad);
-    e->launch("conv3x3_simt_fp32", fl, by, [&] {
+    e->launch(("conv3x3_simt_fp32/" + name).c_str(), fl, by, [&] {
       if (L.up) conv3x3_simt_kernel<float, true><<<grid, block, 0, e->stream>>>(in, out, L.w_simt.as<float>(), L.bias.as<float>(), L.dil, 1);
       else conv3x3_simt_kernel<float, false><<<grid, block, 0, e->stream>>>(in, out, L.w_simt.as<float>(), L.bias.as<float>(), L.dil, 1);
     });
   } else {
     auto in = view<__nv_bfloat16>(src, Hs, Ws, spitch, scoff, L.cin_pad);
     auto out = view<__nv_bfloat16>(dst, Ho, Wo, dpitch, dcoff, L.cout_pad);
-    e->launch("conv3x3_simt_bf16", fl, by, [&] {
+    e->launch(("conv3x3_simt_bf16/" + name).c_str(), fl, by, [&] {
       if (L.up) conv3x3_simt_kernel<__nv_bfloat16, true><<<grid, block, 0, e->stream>>>(in, out, L.w_simt.as<float>(), L.bias.as<float>(), L.dil, 1);
       else conv3x3_simt_kernel<__nv_bfloat16, false><<<grid, block, 0, e->stream>>>(in, out, L.w_simt.as<float>(), L.bias.as<float>(), L.dil, 1);
     });
@@ -682,7 +686,9 @@ int adp_create(int device, int precision, int init_nb, int max_forwards, adp_eng
   ADP_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   ADP_CUDA(cudaEventCreate(&e->ev0));
   ADP_CUDA(cudaEventCreate(&e->ev1));
-  ADP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  for (int nt : {9, 4})
+    for (int T : {4, 2, 1})
+      ADP_CUDA(cudaFuncSetAttribute(tc_kernel_for(nt, T), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (const char *d = getenv("ADP_TC_DEBUG")) e->dbg = atoi(d);
   build_layers(e.get());
   *out = e.release();
