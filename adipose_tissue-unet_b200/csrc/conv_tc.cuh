@@ -11,8 +11,10 @@
 //
 // Operand staging (both operands K-major, SWIZZLE_NONE "interleaved" core matrices).  One pipeline
 // stage = one chunk of 16 input channels (= one MMA K step):
-//   * activations: 5-D TMA boxes bring the rows an item needs (with halo) into shared memory as
-//     channel-group planes  [row][cin/8][pixel][8 x bf16].  Each filter tap is then just a
+//   * activations live in HBM row-planar ([image][row][cin/8][column][8 x bf16], kernels_simt.cuh), so
+//     a 5-D TMA box whose inner extent is 8 pixels x 8 channels = one 128-byte line brings the rows
+//     an item needs (with an 8-pixel-aligned halo) into shared memory as channel-group planes
+//     [row][cin/8][pixel][8 x bf16].  Each filter tap is then just a
 //     different descriptor start address into the same planes (+16 bytes per pixel of horizontal
 //     shift, another row slot per vertical shift), so an input pixel is fetched from L2 once and
 //     reused by all taps.  'same' zero padding, image borders and channel tails come from TMA
@@ -34,11 +36,12 @@
 namespace adp {
 
 struct ConvTcVariant {
-  int y0, x0;        // origin of the activation box relative to the item's (row, col)
+  int y0;            // first row of the activation box relative to the item's first output row
+  int xs_add;        // extra pixel shift of every tap of this variant
   int oy, ox;        // output pixel offset (output = work pixel * oscale + offset)
   int wbase;         // first weight chunk-block of this variant (units of b_bytes)
   int bias_off;      // first bias element
-  int out_coff;      // channel offset added to the output view
+  int out_cg;        // channel-group offset added to the output view
   int pad_;
 };
 
@@ -50,14 +53,14 @@ struct ConvTcParams {
   int ntaps;
   int tap_box[9], tap_row[9], tap_xs[9];   // activation box index, first row slot, pixel shift of each tap
   int nbox, box_dy[3], BR;       // boxes per chunk, their row offsets, rows per box
-  int PW, nchunks;               // plane width (pixels), chunks of 16 input channels
+  int PW, margin8, nchunks;      // plane width (pixels), left halo in 8-pixel groups, chunks of 16 input channels
   int N;                         // GEMM-N (padded couts of one variant), multiple of 16, <= 256
   int S;                         // pipeline depth
   uint32_t a_box_stride, a_bytes, a_tx_bytes, b_bytes, stage_stride;
   const __nv_bfloat16 *wpk;      // packed weight blocks
   const float *bias;
   __nv_bfloat16 *out;
-  int out_pitch, out_coff, Hout, Wout, oscale;
+  int out_cgs, out_cg0, Hout, Wout, oscale;   // output view: channel groups per row of the buffer, first group
   int relu;
   uint32_t idesc;
   int dbg;                       // reserved for kernel experiments
@@ -100,14 +103,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
         const int v = item % p.nvar; int q = item / p.nvar;
         const int tx = q % p.ntx; q /= p.ntx;
         const int ty = q % p.nty; const int n = q / p.nty;
-        const int xs = tx * 128 + p.var[v].x0, ys = ty * T + p.var[v].y0;
+        const int xg = tx * 16 - p.margin8, ys = ty * T + p.var[v].y0;
         const __nv_bfloat16 *w0 = p.wpk + (size_t)p.var[v].wbase * blk_elems;
         for (int c = 0; c < p.nchunks; ++c) {
           uint8_t *sa = smem + (size_t)st * p.stage_stride;
           ptx::mbar_wait(&empty[st], ph ^ 1, 1);
           ptx::mbar_expect_tx(&full[st], p.a_tx_bytes + p.b_bytes);
           for (int b = 0; b < p.nbox; ++b)
-            ptx::tma_load_5d(sa + (size_t)b * p.a_box_stride, &tmap, &full[st], 0, xs, c * 2, ys + p.box_dy[b], n);
+            ptx::tma_load_5d(sa + (size_t)b * p.a_box_stride, &tmap, &full[st], 0, xg, c * 2, ys + p.box_dy[b], n);
           ptx::bulk_load_1d(sa + p.a_bytes, w0 + (size_t)c * blk_elems, p.b_bytes, &full[st]);
           if (++st == p.S) { st = 0; ph ^= 1; }
         }
@@ -139,16 +142,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
         ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3);
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)buf * (uint32_t)T * n_cols;
+        const uint32_t v_off = (uint32_t)p.var[item % p.nvar].xs_add;   // pixels == 16-byte units
         for (int c = 0; c < p.nchunks; ++c) {
           ptx::mbar_wait(&full[st], ph, 4);
           ptx::tc_fence_after();
           const uint32_t s_lo = ((smem0 + (uint32_t)st * p.stage_stride) & 0x3FFFFu) >> 4;
+          const uint32_t sa_lo = s_lo + v_off;
 #pragma unroll
           for (int t = 0; t < NTAPS; ++t) {
             const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo0 | (s_lo + b_off[t]));
 #pragma unroll
             for (int r = 0; r < T; ++r) {
-              const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo0 | (s_lo + a_off[t] + (uint32_t)r * row_step));
+              const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo0 | (sa_lo + a_off[t] + (uint32_t)r * row_step));
               ptx::mma_f16_ss(d0 + (uint32_t)r * n_cols, ad, bd, idesc, (uint32_t)((c | t) != 0));
             }
           }
@@ -176,9 +181,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
       for (int r = 0; r < T; ++r) {
         const int y = ty * T + r;
         const bool live = (y < p.Hin) && (x < p.Win);
-        const size_t opix = ((size_t)n * p.Hout + (size_t)(y * p.oscale + p.var[v].oy)) * p.Wout +
-                            (size_t)(x * p.oscale + p.var[v].ox);
-        __nv_bfloat16 *o = p.out + opix * p.out_pitch + p.out_coff + p.var[v].out_coff;
+        // row-planar output: ((((n*H + y)*cgs + cg)*W + x)*8; consecutive lanes = consecutive pixels
+        const size_t orow = ((size_t)n * p.Hout + (size_t)(y * p.oscale + p.var[v].oy)) * p.out_cgs + p.out_cg0 + p.var[v].out_cg;
+        const size_t plane = (size_t)p.Wout * 8;
+        __nv_bfloat16 *o = p.out + orow * plane + (size_t)(x * p.oscale + p.var[v].ox) * 8;
 #pragma unroll 1
         for (int ch = 0; ch < p.N; ch += 16) {
           float acc[16];
@@ -190,8 +196,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
               float f = acc[i] + __ldg(bias + ch + i);
               h[i] = __float2bfloat16_rn(p.relu ? fmaxf(f, 0.f) : f);
             }
-            *reinterpret_cast<uint4 *>(o + ch) = *reinterpret_cast<uint4 *>(h);
-            *reinterpret_cast<uint4 *>(o + ch + 8) = *reinterpret_cast<uint4 *>(h + 8);
+            *reinterpret_cast<uint4 *>(o + (size_t)(ch >> 3) * plane) = *reinterpret_cast<uint4 *>(h);
+            *reinterpret_cast<uint4 *>(o + (size_t)((ch >> 3) + 1) * plane) = *reinterpret_cast<uint4 *>(h + 8);
           }
         }
       }

@@ -202,29 +202,32 @@ void plan_tc(ConvLayer &L) {
   if (L.dil > 1) T = 1;
   p.T = T;
   if (L.up) {
-    // four output parities, 2x2 taps each (see conv_tc.cuh)
-    p.nvar = 4; p.ntaps = 4; p.nbox = 1; p.BR = T + 1; p.PW = 129; p.oscale = 2;
+    // four output parities, 2x2 taps each (see conv_tc.cuh); the activation box starts 8 pixels left
+    // of the strip (TMA boxes are whole 8-pixel groups), tap (ry,rx) of parity (py,px) reads source
+    // pixel (Y + py - 1 + ry, X + px - 1 + rx)
+    p.nvar = 4; p.ntaps = 4; p.nbox = 1; p.BR = T + 1; p.margin8 = 1; p.PW = 144; p.oscale = 2;
     for (int v = 0; v < 4; ++v) {
       const int py = v >> 1, px = v & 1;
-      p.var[v].y0 = py - 1; p.var[v].x0 = px - 1; p.var[v].oy = py; p.var[v].ox = px;
-      p.var[v].bias_off = 0; p.var[v].out_coff = 0;
+      p.var[v].y0 = py - 1; p.var[v].xs_add = px; p.var[v].oy = py; p.var[v].ox = px;
+      p.var[v].bias_off = 0; p.var[v].out_cg = 0;
     }
-    for (int t = 0; t < 4; ++t) { p.tap_box[t] = 0; p.tap_row[t] = t >> 1; p.tap_xs[t] = t & 1; }
+    for (int t = 0; t < 4; ++t) { p.tap_box[t] = 0; p.tap_row[t] = t >> 1; p.tap_xs[t] = 7 + (t & 1); }
     p.box_dy[0] = 0;
   } else {
     p.nvar = nsplit; p.ntaps = 9; p.oscale = 1;
+    const int margin = (L.dil + 7) / 8 * 8;
+    p.margin8 = margin / 8; p.PW = 128 + 2 * margin;
     for (int v = 0; v < nsplit; ++v) {
-      p.var[v].y0 = -L.dil; p.var[v].x0 = -L.dil; p.var[v].oy = 0; p.var[v].ox = 0;
-      p.var[v].bias_off = v * N; p.var[v].out_coff = v * N;
+      p.var[v].y0 = -L.dil; p.var[v].xs_add = 0; p.var[v].oy = 0; p.var[v].ox = 0;
+      p.var[v].bias_off = v * N; p.var[v].out_cg = v * N / 8;
     }
-    p.PW = 128 + 2 * L.dil;
     if (L.dil == 1) {
       p.nbox = 1; p.BR = T + 2; p.box_dy[0] = 0;
-      for (int t = 0; t < 9; ++t) { p.tap_box[t] = 0; p.tap_row[t] = t / 3; p.tap_xs[t] = t % 3; }
+      for (int t = 0; t < 9; ++t) { p.tap_box[t] = 0; p.tap_row[t] = t / 3; p.tap_xs[t] = margin + (t % 3 - 1); }
     } else {
       p.nbox = 3; p.BR = T;
       for (int b = 0; b < 3; ++b) p.box_dy[b] = b * L.dil;
-      for (int t = 0; t < 9; ++t) { p.tap_box[t] = t / 3; p.tap_row[t] = 0; p.tap_xs[t] = (t % 3) * L.dil; }
+      for (int t = 0; t < 9; ++t) { p.tap_box[t] = t / 3; p.tap_row[t] = 0; p.tap_xs[t] = margin + (t % 3 - 1) * L.dil; }
     }
   }
   // one pipeline stage = 16 input channels: activation boxes + the weight blocks of all taps
@@ -319,7 +322,7 @@ void pack_layer(adp_engine *e, ConvLayer &L) {
                     }
                   }
                 } else {
-                  val = W(t, ci, p.var[v].out_coff + n);
+                  val = W(t, ci, p.var[v].out_cg * 8 + n);
                 }
               }
               dst[((size_t)g * N + n) * 8 + j] = __float2bfloat16_rn(val);
@@ -381,9 +384,10 @@ void ensure_arena(adp_engine *e, int S) {
   e->S = S;
 }
 
+// pitch / coff / C in channels (multiples of 8); the buffer is row-planar (kernels_simt.cuh)
 template <typename T> View<T> view(const DevBuf &b, int H, int W, int pitch, int coff, int C) {
   View<T> v;
-  v.p = b.as<T>(); v.H = H; v.W = W; v.pitch = pitch; v.coff = coff; v.C = C;
+  v.p = b.as<T>(); v.H = H; v.W = W; v.cgs = pitch / 8; v.cg0 = coff / 8; v.C = C;
   return v;
 }
 
@@ -393,11 +397,15 @@ const CUtensorMap &get_tmap(adp_engine *e, const ConvLayer &L, const DevBuf &src
   if (it != e->tmaps.end()) return it->second;
   const ConvTcParams &p = L.tc;
   CUtensorMap m;
-  cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)(C / 8), (cuuint64_t)H, (cuuint64_t)e->max_fw};
-  cuuint64_t gstr[4] = {(cuuint64_t)pitch * 2, 16, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
-  cuuint32_t box[5] = {8, (cuuint32_t)p.PW, 2, (cuuint32_t)p.BR, 1};
+  ADP_REQUIRE(W % 8 == 0, "tcgen05 conv path needs every level's width to be a multiple of 8 (tile size % 64 == 0)");
+  // row-planar source [n][y][cg][x][8]: dim0 = 8 pixels x 8 channels (one 128-byte line), dim1 = 8-pixel
+  // groups along the row, dim2 = channel group, dim3 = row, dim4 = image
+  cuuint64_t gdim[5] = {64, (cuuint64_t)(W / 8), (cuuint64_t)(C / 8), (cuuint64_t)H, (cuuint64_t)e->max_fw};
+  const cuuint64_t cgs = pitch / 8;
+  cuuint64_t gstr[4] = {128, (cuuint64_t)W * 16, cgs * W * 16, (cuuint64_t)H * cgs * W * 16};
+  cuuint32_t box[5] = {64, (cuuint32_t)(p.PW / 8), 2, (cuuint32_t)p.BR, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  void *base = (void *)(src.as<__nv_bfloat16>() + coff);
+  void *base = (void *)(src.as<__nv_bfloat16>() + (size_t)(coff / 8) * W * 8);
   CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -422,7 +430,7 @@ void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs,
     p.nb = nb; p.Hin = Hs; p.Win = Ws;
     p.ntx = cdiv(Ws, 128); p.nty = cdiv(Hs, p.T);
     p.wpk = L.w_tc.as<__nv_bfloat16>(); p.bias = L.bias.as<float>();
-    p.out = dst.as<__nv_bfloat16>(); p.out_pitch = dpitch; p.out_coff = dcoff; p.Hout = Ho; p.Wout = Wo;
+    p.out = dst.as<__nv_bfloat16>(); p.out_cgs = dpitch / 8; p.out_cg0 = dcoff / 8; p.Hout = Ho; p.Wout = Wo;
     p.dbg = e->dbg;
     const CUtensorMap &tm = get_tmap(e, L, src, Hs, Ws, spitch, scoff, L.cin_pad);
     const int nitems = nb * p.nty * p.ntx * p.nvar;
@@ -434,8 +442,8 @@ void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs,
     });
     return;
   }
-  dim3 grid(cdiv(Wo, 16), cdiv(Ho, 16), nb * (L.cout_pad / 16));
-  dim3 block(16, 16);
+  dim3 grid(cdiv(Wo, 32), cdiv(Ho, 8), nb * (L.cout_pad / 16));
+  dim3 block(32, 8);
   if (e->prec == ADP_PREC_FP32) {
     auto in = view<float>(src, Hs, Ws, spitch, scoff, L.cin_pad);
     auto out = view<float>(dst, Ho, Wo, dpitch, dcoff, L.cout_pad);
@@ -457,7 +465,7 @@ template <typename T>
 void run_pool(adp_engine *e, const DevBuf &src, int Hs, int Ws, int spitch, int C, const DevBuf &dst, int nb) {
   auto in = view<T>(src, Hs, Ws, spitch, 0, C);
   auto out = view<T>(dst, Hs / 2, Ws / 2, C, 0, C);
-  const size_t total = (size_t)nb * (Hs / 2) * (Ws / 2) * (C / (16 / sizeof(T)));
+  const size_t total = (size_t)nb * (Hs / 2) * (Ws / 2) * (C / 8);
   const int grid = (int)std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 16);
   e->launch("maxpool2x2", 0, (double)nb * Hs * Ws * C * sizeof(T) * 1.25, [&] {
     maxpool2_kernel<T><<<grid, 256, 0, e->stream>>>(in, out, nb);
@@ -477,7 +485,7 @@ template <typename T> void forward_t(adp_engine *e, const FirstConvSrc &src, con
   const float sd_f = (float)((double)std_ + 1e-10);
   {
     auto out = view<T>(e->a1, S, S, cp[0], 0, cp[0]);
-    dim3 grid(cdiv(S, 16), cdiv(S, 16), nfw), block(16, 16);
+    dim3 grid(cdiv(S, 32), cdiv(S, 8), nfw), block(32, 8);
     const size_t smem = (size_t)10 * cp[0] * 4;
     e->launch("first_conv", 2.0 * nfw * S * S * 9.0 * e->c[0], (double)nfw * S * S * (4 + cp[0] * sizeof(T)), [&] {
       first_conv_kernel<T><<<grid, block, smem, e->stream>>>(s, e->fwt_tile.as<int>(), e->fwt_op.as<int>(), S, mean_f, sd_f,
@@ -863,12 +871,15 @@ int adp_debug_layer(adp_engine *e, const char *name, int idx, float *out, int64_
   const size_t npx = (size_t)t.H * t.H, img = npx * t.pitch * e->esz;
   std::vector<uint8_t> host(img);
   ADP_CUDA(cudaMemcpy(host.data(), (const uint8_t *)t.b->p + (size_t)idx * img, img, cudaMemcpyDeviceToHost));
-  for (size_t px = 0; px < npx; ++px)
-    for (int ch = 0; ch < t.C; ++ch) {
-      const size_t si = px * t.pitch + t.coff + ch;
-      out[px * t.C + ch] = e->esz == 4 ? reinterpret_cast<const float *>(host.data())[si]
-                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(host.data())[si]);
-    }
+  const int W = t.H, cgs = t.pitch / 8;
+  for (int y = 0; y < t.H; ++y)
+    for (int x = 0; x < W; ++x)
+      for (int ch = 0; ch < t.C; ++ch) {
+        const int cc = t.coff + ch;       // row-planar: (((y*cgs + cg)*W + x)*8 + c%8
+        const size_t si = (((size_t)y * cgs + cc / 8) * W + x) * 8 + cc % 8;
+        out[((size_t)y * W + x) * t.C + ch] = e->esz == 4 ? reinterpret_cast<const float *>(host.data())[si]
+                                                          : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(host.data())[si]);
+      }
   ADP_CATCH
 }
 

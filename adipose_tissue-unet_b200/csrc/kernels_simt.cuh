@@ -1,21 +1,31 @@
 // kernels_simt.cuh — CUDA-core kernels of the U-Net path: first conv (Cin=1, fused z-score +
 // dihedral load), generic 3x3 conv (exact-fp32 parity path and bf16 cross-check), max-pool,
-// six-way add, 1x1 softmax head.  All activations are NHWC with the channel count padded to a
-// multiple of 16 (pad channels are exact zeros); `pitch` is the channel pitch of the buffer and
-// `coff` the first channel of the view, so concat buffers are written in place
-// (Concatenate([skip, up]) of train_adipose_unet_v3.py:693,700,707 costs nothing).
+// six-way add, 1x1 softmax head.
+//
+// Activation layout in HBM ("row-planar"): [image][row y][channel group cg][column x][8 channels],
+// channel count padded to a multiple of 16 (pad channels are exact zeros).  A warp that owns 32
+// consecutive pixels of a row reads/writes 512 contiguous bytes per channel group, and a TMA box
+// of 8 pixels x 8 channels is one 128-byte line — the layout is chosen for the tcgen05 conv's
+// operand staging (conv_tc.cuh) and for coalesced epilogues, not for the reference's NHWC.
+// `cgs` is the number of channel groups of the underlying buffer and `cg0` the first group of the
+// view, so concat buffers are written in place (Concatenate([skip, up]) of
+// train_adipose_unet_v3.py:693,700,707 costs nothing).
 #pragma once
 #include "common.cuh"
 
 namespace adp {
 
-template <typename T> struct View {   // NHWC view into an activation buffer
+template <typename T> struct View {
   T *p;
   int H, W;      // spatial size of one image
-  int pitch;     // channels per pixel in the underlying buffer
-  int coff;      // first channel of this view
-  int C;         // channels of the view (padded to 16)
-  __host__ __device__ size_t img_stride() const { return (size_t)H * W * pitch; }
+  int cgs;       // channel groups (of 8) per pixel row in the underlying buffer
+  int cg0;       // first channel group of this view
+  int C;         // channels of the view (multiple of 16)
+  __host__ __device__ size_t img_stride() const { return (size_t)H * cgs * W * 8; }
+  // element offset of (image n, row y, channel group g of the view, column x)
+  __host__ __device__ size_t at(int n, int y, int g, int x) const {
+    return ((((size_t)n * H + y) * cgs + cg0 + g) * W + x) * 8;
+  }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -42,6 +52,30 @@ ADP_DEVINL float first_conv_fetch(const FirstConvSrc &s, int tile, int S, int si
   return (float)y;
 }
 
+template <typename T> ADP_DEVINL void store8(T *o, const float *a) {
+  if constexpr (sizeof(T) == 2) {
+    __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) h[c] = __float2bfloat16_rn(a[c]);
+    *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<uint4 *>(h);
+  } else {
+    *reinterpret_cast<float4 *>(o) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4 *>(o + 4) = make_float4(a[4], a[5], a[6], a[7]);
+  }
+}
+template <typename T> ADP_DEVINL void load8(const T *i, float *a) {
+  if constexpr (sizeof(T) == 2) {
+    __align__(16) __nv_bfloat16 h[8];
+    *reinterpret_cast<uint4 *>(h) = *reinterpret_cast<const uint4 *>(i);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = __bfloat162float(h[c]);
+  } else {
+    float4 lo = *reinterpret_cast<const float4 *>(i), hi = *reinterpret_cast<const float4 *>(i + 4);
+    a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+  }
+}
+
+// block = (32, 8): a warp owns 32 consecutive pixels of one row
 template <typename T>
 __global__ void __launch_bounds__(256)
 first_conv_kernel(FirstConvSrc src, const int *__restrict__ fw_tile, const int *__restrict__ fw_op,
@@ -50,11 +84,12 @@ first_conv_kernel(FirstConvSrc src, const int *__restrict__ fw_tile, const int *
   extern __shared__ float sm[];
   float *ws = sm;                 // 9*C
   float *bs = sm + 9 * out.C;     // C
-  for (int i = threadIdx.x + threadIdx.y * 16; i < 9 * out.C; i += 256) ws[i] = w[i];
-  for (int i = threadIdx.x + threadIdx.y * 16; i < out.C; i += 256) bs[i] = bias[i];
+  const int tid = threadIdx.x + threadIdx.y * 32;
+  for (int i = tid; i < 9 * out.C; i += 256) ws[i] = w[i];
+  for (int i = tid; i < out.C; i += 256) bs[i] = bias[i];
   __syncthreads();
-  const int x = blockIdx.x * 16 + threadIdx.x;
-  const int y = blockIdx.y * 16 + threadIdx.y;
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
   const int f = blockIdx.z;
   if (x >= S || y >= S) return;
   const int tile = fw_tile[f], op = fw_op[f];
@@ -73,26 +108,17 @@ first_conv_kernel(FirstConvSrc src, const int *__restrict__ fw_tile, const int *
       }
       v[ky * 3 + kx] = val;
     }
-  T *o = out.p + (size_t)f * out.img_stride() + ((size_t)y * S + x) * out.pitch + out.coff;
-  for (int c0 = 0; c0 < out.C; c0 += 8) {
+  for (int g = 0; g < out.C / 8; ++g) {
     float a[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) a[c] = bs[c0 + c];
+    for (int c = 0; c < 8; ++c) a[c] = bs[g * 8 + c];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) a[c] = fmaf(v[t], ws[t * out.C + c0 + c], a[c]);
-    if constexpr (sizeof(T) == 2) {
-      __align__(16) __nv_bfloat16 h[8];
+      for (int c = 0; c < 8; ++c) a[c] = fmaf(v[t], ws[t * out.C + g * 8 + c], a[c]);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) h[c] = __float2bfloat16_rn(fmaxf(a[c], 0.f));
-      *reinterpret_cast<uint4 *>(o + c0) = *reinterpret_cast<uint4 *>(h);
-    } else {
-      float4 lo = make_float4(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f), fmaxf(a[2], 0.f), fmaxf(a[3], 0.f));
-      float4 hi = make_float4(fmaxf(a[4], 0.f), fmaxf(a[5], 0.f), fmaxf(a[6], 0.f), fmaxf(a[7], 0.f));
-      *reinterpret_cast<float4 *>(o + c0) = lo;
-      *reinterpret_cast<float4 *>(o + c0 + 4) = hi;
-    }
+    for (int c = 0; c < 8; ++c) a[c] = fmaxf(a[c], 0.f);
+    store8<T>(out.p + out.at(f, y, g, x), a);
   }
 }
 
@@ -100,7 +126,7 @@ first_conv_kernel(FirstConvSrc src, const int *__restrict__ fw_tile, const int *
 // Generic Conv2D(3x3, same, dilation d) + bias + ReLU on CUDA cores (fp32 accumulate).
 // UP: the logical input is UpSampling2D((2,2)) nearest of `in` (out[y][x] = in[y//2][x//2],
 // train_adipose_unet_v3.py:691,698,705), folded into the gather.
-// One thread = one output pixel x 16 output channels.  grid = (W/16, H/16, nb * Cout/16).
+// One thread = one output pixel x 16 output channels.  block (32, 8), grid = (W/32, H/8, nb*Cout/16).
 // w: [9][Cin][Cout] fp32 (padded, zero in pad rows/cols).
 template <typename T, bool UP>
 __global__ void __launch_bounds__(256)
@@ -111,14 +137,13 @@ conv3x3_simt_kernel(View<T> in, View<T> out, const float *__restrict__ w, const 
   const int cgroups = out.C >> 4;
   const int n = blockIdx.z / cgroups;
   const int co0 = (blockIdx.z % cgroups) << 4;
-  const int x = blockIdx.x * 16 + threadIdx.x;
-  const int y = blockIdx.y * 16 + threadIdx.y;
-  const int tid = threadIdx.y * 16 + threadIdx.x;
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
   const bool live = (x < W) && (y < H);
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  const T *ibase = in.p + (size_t)n * in.img_stride() + in.coff;
   for (int c0 = 0; c0 < in.C; c0 += 16) {
     __syncthreads();
     for (int i = tid; i < 9 * 256; i += 256) {
@@ -132,21 +157,9 @@ conv3x3_simt_kernel(View<T> in, View<T> out, const float *__restrict__ w, const 
       const int iy = y + (t / 3 - 1) * dil, ix = x + (t % 3 - 1) * dil;
       if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
       const int sy = UP ? (iy >> 1) : iy, sx = UP ? (ix >> 1) : ix;
-      const T *ip = ibase + ((size_t)sy * in.W + sx) * in.pitch + c0;
       float a[16];
-      if constexpr (sizeof(T) == 2) {
-        __align__(16) __nv_bfloat16 h[16];
-        *reinterpret_cast<uint4 *>(h) = *reinterpret_cast<const uint4 *>(ip);
-        *reinterpret_cast<uint4 *>(h + 8) = *reinterpret_cast<const uint4 *>(ip + 8);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) a[c] = __bfloat162float(h[c]);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4 f = *reinterpret_cast<const float4 *>(ip + 4 * q);
-          a[4 * q] = f.x; a[4 * q + 1] = f.y; a[4 * q + 2] = f.z; a[4 * q + 3] = f.w;
-        }
-      }
+      load8<T>(in.p + in.at(n, sy, c0 >> 3, sx), a);
+      load8<T>(in.p + in.at(n, sy, (c0 >> 3) + 1, sx), a + 8);
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const float4 *wr = reinterpret_cast<const float4 *>(&ws[t][c][0]);
@@ -162,50 +175,38 @@ conv3x3_simt_kernel(View<T> in, View<T> out, const float *__restrict__ w, const 
     }
   }
   if (!live) return;
-  T *o = out.p + (size_t)n * out.img_stride() + ((size_t)y * W + x) * out.pitch + out.coff + co0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     float v = acc[i] + bias[co0 + i];
     acc[i] = relu ? fmaxf(v, 0.f) : v;
   }
-  if constexpr (sizeof(T) == 2) {
-    __align__(16) __nv_bfloat16 h[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) h[i] = __float2bfloat16_rn(acc[i]);
-    *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<uint4 *>(h);
-    *reinterpret_cast<uint4 *>(o + 8) = *reinterpret_cast<uint4 *>(h + 8);
-  } else {
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      *reinterpret_cast<float4 *>(o + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-  }
+  store8<T>(out.p + out.at(n, y, co0 >> 3, x), acc);
+  store8<T>(out.p + out.at(n, y, (co0 >> 3) + 1, x), acc + 8);
 }
 
 // ---------------------------------------------------------------------------------------------
-// MaxPooling2D((2,2), strides=(2,2)) — train_adipose_unet_v3.py:670,674,678.  16-byte vectors.
+// MaxPooling2D((2,2), strides=(2,2)) — train_adipose_unet_v3.py:670,674,678.
+// One thread = one output pixel of one channel group (16-byte vectors for bf16, 2 x 16 for fp32).
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_kernel(View<T> in, View<T> out, int nb) {
-  constexpr int V = 16 / sizeof(T);
-  const int vec_per_px = out.C / V;
-  const size_t total = (size_t)nb * out.H * out.W * vec_per_px;
+  const int G = out.C / 8;
+  const size_t total = (size_t)nb * out.H * G * out.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int v = i % vec_per_px;
-    size_t px = i / vec_per_px;
-    int x = px % out.W;
-    size_t r = px / out.W;
+    int x = i % out.W;
+    size_t r = i / out.W;
+    int g = r % G; r /= G;
     int y = r % out.H;
     int n = r / out.H;
-    const T *ip = in.p + (size_t)n * in.img_stride() + ((size_t)(2 * y) * in.W + 2 * x) * in.pitch + in.coff + v * V;
-    __align__(16) T a[V], b[V], c[V], d[V], m[V];
-    *reinterpret_cast<uint4 *>(a) = *reinterpret_cast<const uint4 *>(ip);
-    *reinterpret_cast<uint4 *>(b) = *reinterpret_cast<const uint4 *>(ip + in.pitch);
-    *reinterpret_cast<uint4 *>(c) = *reinterpret_cast<const uint4 *>(ip + (size_t)in.W * in.pitch);
-    *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(ip + (size_t)in.W * in.pitch + in.pitch);
+    float a[8], b[8], c[8], d[8], m[8];
+    const T *ip = in.p + in.at(n, 2 * y, g, 2 * x);
+    load8<T>(ip, a);
+    load8<T>(ip + 8, b);
+    const T *ip2 = in.p + in.at(n, 2 * y + 1, g, 2 * x);
+    load8<T>(ip2, c);
+    load8<T>(ip2 + 8, d);
 #pragma unroll
-    for (int k = 0; k < V; ++k)
-      m[k] = from_f<T>(fmaxf(fmaxf(to_f(a[k]), to_f(b[k])), fmaxf(to_f(c[k]), to_f(d[k]))));
-    T *op = out.p + (size_t)n * out.img_stride() + ((size_t)y * out.W + x) * out.pitch + out.coff + v * V;
-    *reinterpret_cast<uint4 *>(op) = *reinterpret_cast<uint4 *>(m);
+    for (int k = 0; k < 8; ++k) m[k] = fmaxf(fmaxf(a[k], b[k]), fmaxf(c[k], d[k]));
+    store8<T>(out.p + out.at(n, y, g, x), m);
   }
 }
 
@@ -244,17 +245,18 @@ head_kernel(View<T> in, int nb, const float *__restrict__ wh, const float *__res
   const size_t total = (size_t)nb * in.H * in.W;
   const float b0 = bh[0], b1 = bh[1];
   for (size_t px = blockIdx.x * (size_t)blockDim.x + threadIdx.x; px < total; px += (size_t)gridDim.x * blockDim.x) {
-    const T *ip = in.p + px * in.pitch + in.coff;   // images are contiguous: n*H*W + y*W + x
+    const int x = px % in.W;
+    const size_t r = px / in.W;
+    const int y = r % in.H;
+    const int n = r / in.H;
     float z0 = 0.f, z1 = 0.f;
-    constexpr int V = 16 / sizeof(T);
-    for (int c0 = 0; c0 < in.C; c0 += V) {
-      __align__(16) T a[V];
-      *reinterpret_cast<uint4 *>(a) = *reinterpret_cast<const uint4 *>(ip + c0);
+    for (int g = 0; g < in.C / 8; ++g) {
+      float a[8];
+      load8<T>(in.p + in.at(n, y, g, x), a);
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        float v = to_f(a[k]);
-        z0 = fmaf(v, sm[c0 + k], z0);
-        z1 = fmaf(v, sm[in.C + c0 + k], z1);
+      for (int k = 0; k < 8; ++k) {
+        z0 = fmaf(a[k], sm[g * 8 + k], z0);
+        z1 = fmaf(a[k], sm[in.C + g * 8 + k], z1);
       }
     }
     z0 += b0; z1 += b1;
