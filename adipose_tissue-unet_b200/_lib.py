@@ -40,6 +40,7 @@ SIGNATURES = {
     "adp_precision": (_I, [_P]),
     "adp_synchronize": (_I, [_P]),
     "adp_stream": (_P, [_P]),
+    "adp_set_option": (_I, [_P, C.c_char_p, _I]),
     "adp_set_weight": (_I, [_P, C.c_char_p, _P, C.POINTER(_I64), _P, _I64]),
     "adp_get_weight": (_I, [_P, C.c_char_p, _P, _I64, _P, _I64]),
     "adp_weights_ready": (_I, [_P]),

@@ -211,6 +211,9 @@ class Engine:
     def synchronize(self):
         _lib.check(self.lib.adp_synchronize(self.h))
 
+    def set_option(self, key: str, value: int):
+        _lib.check(self.lib.adp_set_option(self.h, key.encode(), int(value)))
+
     def stream_ptr(self) -> int:
         return int(self.lib.adp_stream(self.h) or 0)
 

@@ -28,8 +28,12 @@
 // on the low-resolution grid each output parity (py,px) is a 2x2-tap conv whose weights are sums
 // of the 3x3 taps that land on the same source pixel — 4/9 of the MMA work and no upsampled tensor.
 //
-// Warp roles (192 threads): w0 producer (TMA + bulk copy), w1 MMA issuer (one elected lane) and
-// TMEM allocator, w2-5 epilogue (tcgen05.ld -> bias -> ReLU -> bf16 -> global).
+// Warp roles (320 threads): w0 producer (TMA + bulk copy), w1 MMA issuer (one elected lane) and
+// TMEM allocator, w2-9 epilogue: two warps per TMEM lane quarter, software-pipelined
+// tcgen05.ld -> bias -> ReLU -> bf16 -> coalesced row-planar stores.  Fused epilogues:
+//   EPI_HEAD  Conv2D(2,1x1,softmax)[...,1] of train_adipose_unet_v3.py:748-750 on the fp32 accumulators
+//             of up1_conv3 (the 44-channel activation never reaches HBM),
+//   EPI_POOL  MaxPooling2D(2x2) (train_adipose_unet_v3.py:670,674) written next to the skip tensor.
 #pragma once
 #include "ptx.cuh"
 
@@ -63,10 +67,60 @@ struct ConvTcParams {
   int out_cgs, out_cg0, Hout, Wout, oscale;   // output view: channel groups per row of the buffer, first group
   int relu;
   uint32_t idesc;
+  int epi_mode;                  // EPI_STORE / EPI_HEAD / EPI_POOL
+  const float *head_w;           // [2][N] fp32 (zero padded), EPI_HEAD
+  const float *head_b;           // [2]
+  float *prob;                   // [nb][Hout][Wout] fp32, EPI_HEAD
+  __nv_bfloat16 *pool_out;       // pooled row-planar tensor [nb][Hout/2][pool_cgs][Wout/2][8], EPI_POOL
+  int pool_cgs, pool_cg0;
   int dbg;                       // reserved for kernel experiments
 };
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;
+constexpr int EPI_STORE = 0, EPI_HEAD = 1, EPI_POOL = 2;
+
+// Software-pipelined walk over 16-column accumulator units u0, u0+step, ... < uend: the TMEM load
+// of the next unit is in flight while `body` works on the current one.
+template <typename F>
+ADP_DEVINL void tmem_pipeline(uint32_t tbase, int u0, int step, int uend, F &&body) {
+  uint32_t ra[16], rb[16];
+  int u = u0;
+  if (u < uend) ptx::tmem_ld16_issue(tbase + (uint32_t)u * 16u, ra);
+  while (u < uend) {
+    ptx::tmem_ld16_wait(ra);
+    const int u2 = u + step;
+    if (u2 < uend) ptx::tmem_ld16_issue(tbase + (uint32_t)u2 * 16u, rb);
+    body(u, ra);
+    if (u2 >= uend) break;
+    ptx::tmem_ld16_wait(rb);
+    const int u3 = u2 + step;
+    if (u3 < uend) ptx::tmem_ld16_issue(tbase + (uint32_t)u3 * 16u, ra);
+    body(u2, rb);
+    u = u3;
+  }
+}
+
+ADP_DEVINL void bias_relu16(const uint32_t (&r)[16], const float *sb, int relu, float (&f)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4 *>(sb + 4 * q);
+    f[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b.x;
+    f[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b.y;
+    f[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b.z;
+    f[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+  }
+}
+ADP_DEVINL void store16_bf16(__nv_bfloat16 *o, size_t plane, const float (&f)[16]) {
+  __align__(16) __nv_bfloat16 h[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) h[i] = __float2bfloat16_rn(f[i]);
+  *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<uint4 *>(h);
+  *reinterpret_cast<uint4 *>(o + plane) = *reinterpret_cast<uint4 *>(h + 8);
+}
 
 template <int NTAPS, int T>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -76,13 +130,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
   uint64_t *full = bars, *empty = full + p.S;
   uint64_t *acc_full = empty + p.S, *acc_empty = acc_full + 2;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  float *sbias = reinterpret_cast<float *>(acc_empty + 4);        // [nvar * N] (<= 704 floats)
+  float *shead = sbias + 704;                                      // [2 * N] + 2, EPI_HEAD only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.nvar * p.N; i += kTcThreads) {
+    const int v = i / p.N;
+    sbias[i] = p.bias[p.var[v].bias_off + (i - v * p.N)];
+  }
+  if (p.epi_mode == EPI_HEAD) {
+    for (int i = threadIdx.x; i < 2 * p.N; i += kTcThreads) shead[i] = p.head_w[i];
+    if (threadIdx.x < 2) shead[2 * p.N + threadIdx.x] = p.head_b[threadIdx.x];
+  }
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.S; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 8); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmap);
   }
@@ -164,40 +228,85 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
       }
     }
   } else {
-    // ---------------- epilogue (warps 2..5; TMEM lane quarter = warp % 4) ----------------
-    const int ew = warp & 3;
+    // ---------------- epilogue (warps 2..9; TMEM lane quarter = warp % 4, two warps per quarter) ----------------
+    const int q4 = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int NU = p.N >> 4;                                  // 16-column units per accumulator row
     int it = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
       const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
       const int v = item % p.nvar; int q = item / p.nvar;
       const int tx = q % p.ntx; q /= p.ntx;
       const int ty = q % p.nty; const int n = q / p.nty;
-      const int x = tx * 128 + ew * 32 + lane;
-      const float *bias = p.bias + p.var[v].bias_off;
+      const int x = tx * 128 + q4 * 32 + lane;
+      const float *sb = sbias + v * p.N;
       ptx::mbar_wait(&acc_full[buf], acc_ph, 6);
       ptx::tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * T * p.N);
-#pragma unroll 1
-      for (int r = 0; r < T; ++r) {
+      const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * T * p.N);
+      const size_t plane = (size_t)p.Wout * 8;
+      const int ox = x * p.oscale + p.var[v].ox;
+      // row-planar output row base of accumulator row r: ((((n*H + y)*cgs + cg)*W)*8
+      auto out_row = [&](int r) -> __nv_bfloat16 * {
         const int y = ty * T + r;
-        const bool live = (y < p.Hin) && (x < p.Win);
-        // row-planar output: ((((n*H + y)*cgs + cg)*W + x)*8; consecutive lanes = consecutive pixels
         const size_t orow = ((size_t)n * p.Hout + (size_t)(y * p.oscale + p.var[v].oy)) * p.out_cgs + p.out_cg0 + p.var[v].out_cg;
-        const size_t plane = (size_t)p.Wout * 8;
-        __nv_bfloat16 *o = p.out + orow * plane + (size_t)(x * p.oscale + p.var[v].ox) * 8;
-#pragma unroll 1
-        for (int ch = 0; ch < p.N; ch += 16) {
-          float acc[16];
-          ptx::tmem_ld16(t0 + (uint32_t)(r * p.N + ch), acc);
-          if (live) {
-            __align__(16) __nv_bfloat16 h[16];
+        return p.out + orow * plane + (size_t)ox * 8;
+      };
+      if (p.epi_mode == EPI_STORE) {
+        tmem_pipeline(t0, half, 2, T * NU, [&](int u, const uint32_t (&r)[16]) {
+          const int row = u / NU, cu = u - row * NU;
+          float f[16];
+          bias_relu16(r, sb + cu * 16, p.relu, f);
+          if ((ty * T + row < p.Hin) && (x < p.Win)) store16_bf16(out_row(row) + (size_t)(2 * cu) * plane, plane, f);
+        });
+      } else if (p.epi_mode == EPI_HEAD) {
+        // rows split between the two warps of a quarter so that one thread sees all channels of its pixel
+        for (int row = half; row < T; row += 2) {
+          float z0 = 0.f, z1 = 0.f;
+          tmem_pipeline(t0, row * NU, 1, row * NU + NU, [&](int u, const uint32_t (&r)[16]) {
+            const int cu = u - row * NU;
+            float f[16];
+            bias_relu16(r, sb + cu * 16, p.relu, f);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float f = acc[i] + __ldg(bias + ch + i);
-              h[i] = __float2bfloat16_rn(p.relu ? fmaxf(f, 0.f) : f);
+              z0 = fmaf(f[i], shead[cu * 16 + i], z0);
+              z1 = fmaf(f[i], shead[p.N + cu * 16 + i], z1);
             }
-            *reinterpret_cast<uint4 *>(o + (size_t)(ch >> 3) * plane) = *reinterpret_cast<uint4 *>(h);
-            *reinterpret_cast<uint4 *>(o + (size_t)((ch >> 3) + 1) * plane) = *reinterpret_cast<uint4 *>(h + 8);
+          });
+          const int y = ty * T + row;
+          if (y < p.Hin && x < p.Win) {
+            z0 += shead[2 * p.N]; z1 += shead[2 * p.N + 1];
+            p.prob[((size_t)n * p.Hout + y) * p.Wout + x] = 1.f / (1.f + expf(z0 - z1));
+          }
+        }
+      } else {
+        // EPI_POOL: unit = (row pair k, 16 channels); both rows are stored, their max is reduced with
+        // the neighbouring column (lane ^ 1) and even lanes write the pooled pixel
+        const int HU = (T / 2) * NU;
+        for (int pu = half; pu < HU; pu += 2) {
+          const int k = pu / NU, cu = pu - k * NU;
+          uint32_t ra[16], rb[16];
+          ptx::tmem_ld16_issue(t0 + (uint32_t)((2 * k) * p.N + cu * 16), ra);
+          ptx::tmem_ld16_issue(t0 + (uint32_t)((2 * k + 1) * p.N + cu * 16), rb);
+          ptx::tmem_ld16_wait(ra);
+          ptx::tmem_ld16_wait(rb);
+          float fa[16], fb[16];
+          bias_relu16(ra, sb + cu * 16, p.relu, fa);
+          bias_relu16(rb, sb + cu * 16, p.relu, fb);
+          const bool live = (ty * T + 2 * k + 1 < p.Hin) && (x < p.Win);
+          if (live) {
+            store16_bf16(out_row(2 * k) + (size_t)(2 * cu) * plane, plane, fa);
+            store16_bf16(out_row(2 * k + 1) + (size_t)(2 * cu) * plane, plane, fb);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float m = fmaxf(fa[i], fb[i]);
+            fa[i] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          }
+          if (live && !(lane & 1)) {
+            const int py = (ty * T + 2 * k) >> 1, px = x >> 1;
+            const size_t pplane = (size_t)(p.Wout >> 1) * 8;
+            const size_t prow = ((size_t)n * (p.Hout >> 1) + py) * p.pool_cgs + p.pool_cg0 + p.var[v].out_cg;
+            store16_bf16(p.pool_out + prow * pplane + (size_t)px * 8 + (size_t)(2 * cu) * pplane, pplane, fa);
           }
         }
       }

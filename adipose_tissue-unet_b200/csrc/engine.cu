@@ -126,6 +126,7 @@ struct adp_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t launches = 0;
   int dbg = 0;
+  bool fuse_head = true, fuse_pool = true;   // tcgen05 path only
 
   template <typename F> void launch(const char *kind, double flops, double bytes, F &&f) {
     if (prof) ADP_CUDA(cudaEventRecord(ev0, stream));
@@ -237,7 +238,7 @@ void plan_tc(ConvLayer &L) {
   p.a_tx_bytes = (uint32_t)((size_t)p.nbox * p.BR * 2 * p.PW * 16);
   p.b_bytes = (uint32_t)((size_t)p.ntaps * N * 32);
   p.stage_stride = (uint32_t)(((size_t)p.a_bytes + p.b_bytes + 1023) / 1024 * 1024);
-  const size_t budget = 220 * 1024;
+  const size_t budget = 216 * 1024;
   p.S = (int)std::min<size_t>(8, budget / p.stage_stride);
   ADP_REQUIRE(p.S >= 2, "conv stage does not fit shared memory twice");
   p.idesc = ptx::make_idesc(128, N, 1);
@@ -246,7 +247,8 @@ void plan_tc(ConvLayer &L) {
 }
 
 size_t tc_smem_bytes(const ConvTcParams &p) {
-  return (size_t)p.S * p.stage_stride + (2 * p.S + 4) * 8 + 16;
+  // stages | mbarriers (2S + 4) + tmem slot | bias (704 floats) | head weights (2*256 + 2 floats)
+  return (size_t)p.S * p.stage_stride + (2 * p.S + 6) * 8 + (704 + 520) * 4;
 }
 
 typedef void (*ConvTcKernel)(const CUtensorMap, const ConvTcParams);
@@ -419,8 +421,13 @@ double conv_flops(const ConvLayer &L, int Hout, int Wout, int nb) {
 }
 
 // one generic 3x3 conv layer: src view (H,W are the SOURCE buffer dims) -> dst view
+struct EpiSpec {
+  int mode = EPI_STORE;
+  const DevBuf *pool_dst = nullptr;   // EPI_POOL: dense pooled tensor (pitch = channels of the layer)
+};
+
 void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs, int Ws, int spitch, int scoff,
-              const DevBuf &dst, int dpitch, int dcoff, int nb) {
+              const DevBuf &dst, int dpitch, int dcoff, int nb, EpiSpec epi = EpiSpec()) {
   ConvLayer &L = layer(e, name);
   const int Ho = L.up ? Hs * 2 : Hs, Wo = L.up ? Ws * 2 : Ws;
   const double fl = conv_flops(L, Ho, Wo, nb);
@@ -432,6 +439,14 @@ void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs,
     p.wpk = L.w_tc.as<__nv_bfloat16>(); p.bias = L.bias.as<float>();
     p.out = dst.as<__nv_bfloat16>(); p.out_cgs = dpitch / 8; p.out_cg0 = dcoff / 8; p.Hout = Ho; p.Wout = Wo;
     p.dbg = e->dbg;
+    p.epi_mode = epi.mode;
+    if (epi.mode == EPI_HEAD) {
+      ADP_REQUIRE(p.T >= 2 && p.nvar == 1 && p.N == e->cp[0], "head fusion needs the 44-channel full-resolution layer");
+      p.head_w = e->w_head.as<float>(); p.head_b = e->b_head.as<float>(); p.prob = e->prob.as<float>();
+    } else if (epi.mode == EPI_POOL) {
+      ADP_REQUIRE(p.T % 2 == 0 && p.oscale == 1 && Ho % 2 == 0 && Wo % 2 == 0, "pool fusion needs an even row block");
+      p.pool_out = epi.pool_dst->as<__nv_bfloat16>(); p.pool_cgs = L.cout_pad / 8; p.pool_cg0 = 0;
+    }
     const CUtensorMap &tm = get_tmap(e, L, src, Hs, Ws, spitch, scoff, L.cin_pad);
     const int nitems = nb * p.nty * p.ntx * p.nvar;
     const int grid = std::min(nitems, e->num_sms);
@@ -492,11 +507,15 @@ template <typename T> void forward_t(adp_engine *e, const FirstConvSrc &src, con
                                                             e->w_first.as<float>(), e->b_first.as<float>(), out);
     });
   }
-  run_conv(e, "down1_conv2", e->a1, S, S, cp[0], 0, e->cat1, 2 * cp[0], 0, nfw);
-  run_pool<T>(e, e->cat1, S, S, 2 * cp[0], cp[0], e->pl1, nfw);
+  const bool tc = e->prec == ADP_PREC_BF16;
+  EpiSpec pool1, pool2, head;
+  if (tc && e->fuse_pool) { pool1.mode = EPI_POOL; pool1.pool_dst = &e->pl1; pool2.mode = EPI_POOL; pool2.pool_dst = &e->pl2; }
+  if (tc && e->fuse_head) head.mode = EPI_HEAD;
+  run_conv(e, "down1_conv2", e->a1, S, S, cp[0], 0, e->cat1, 2 * cp[0], 0, nfw, pool1);
+  if (pool1.mode != EPI_POOL) run_pool<T>(e, e->cat1, S, S, 2 * cp[0], cp[0], e->pl1, nfw);
   run_conv(e, "down2_conv1", e->pl1, S2, S2, cp[0], 0, e->a2, cp[1], 0, nfw);
-  run_conv(e, "down2_conv2", e->a2, S2, S2, cp[1], 0, e->cat2, 2 * cp[1], 0, nfw);
-  run_pool<T>(e, e->cat2, S2, S2, 2 * cp[1], cp[1], e->pl2, nfw);
+  run_conv(e, "down2_conv2", e->a2, S2, S2, cp[1], 0, e->cat2, 2 * cp[1], 0, nfw, pool2);
+  if (pool2.mode != EPI_POOL) run_pool<T>(e, e->cat2, S2, S2, 2 * cp[1], cp[1], e->pl2, nfw);
   run_conv(e, "down3_conv1", e->pl2, S3, S3, cp[1], 0, e->a3, cp[2], 0, nfw);
   run_conv(e, "down3_conv2", e->a3, S3, S3, cp[2], 0, e->cat3, 2 * cp[2], 0, nfw);
   run_pool<T>(e, e->cat3, S3, S3, 2 * cp[2], cp[2], e->pl3, nfw);
@@ -519,8 +538,8 @@ template <typename T> void forward_t(adp_engine *e, const FirstConvSrc &src, con
   run_conv(e, "up2_conv3", e->a2, S2, S2, cp[1], 0, e->b2, cp[1], 0, nfw);
   run_conv(e, "up1_conv1", e->b2, S2, S2, cp[1], 0, e->cat1, 2 * cp[0], cp[0], nfw);
   run_conv(e, "up1_conv2", e->cat1, S, S, 2 * cp[0], 0, e->a1, cp[0], 0, nfw);
-  run_conv(e, "up1_conv3", e->a1, S, S, cp[0], 0, e->b1, cp[0], 0, nfw);
-  {
+  run_conv(e, "up1_conv3", e->a1, S, S, cp[0], 0, e->b1, cp[0], 0, nfw, head);
+  if (head.mode != EPI_HEAD) {
     auto in = view<T>(e->b1, S, S, cp[0], 0, cp[0]);
     const size_t total = (size_t)nfw * S * S;
     const int grid = (int)std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 16);
@@ -726,6 +745,17 @@ int adp_synchronize(adp_engine *e) {
 }
 
 void *adp_stream(adp_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+int adp_set_option(adp_engine *e, const char *key, int value) {
+  ADP_TRY
+  ADP_REQUIRE(e && key, "null argument");
+  std::string k = key;
+  if (k == "fuse_head") e->fuse_head = value != 0;
+  else if (k == "fuse_pool") e->fuse_pool = value != 0;
+  else if (k == "debug") e->dbg = value;
+  else throw Error(ADP_EINVAL, "unknown option " + k);
+  ADP_CATCH
+}
 
 int adp_set_weight(adp_engine *e, const char *layer_name, const float *kernel, const int64_t kshape[4], const float *bias,
                    int64_t nbias) {

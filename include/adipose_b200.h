@@ -72,6 +72,9 @@ int adp_destroy(adp_engine *e);
 int adp_precision(const adp_engine *e);
 int adp_synchronize(adp_engine *e);
 void *adp_stream(adp_engine *e);            /* the engine's cudaStream_t (for event timing by the caller) */
+/* engine switches for tests and experiments: "fuse_head" (softmax head in the last conv's epilogue),
+ * "fuse_pool" (2x2 max-pool in the encoder convs' epilogue) — tcgen05 path only, default 1 */
+int adp_set_option(adp_engine *e, const char *key, int value);
 
 /* ---- weights ---------------------------------------------------------------------------------
  * Replaces net.load_weights / load_legacy_weights (full_evaluation_enhanced.py:1266-1301): the

@@ -55,6 +55,8 @@ def test_per_layer_256(prec, weights, params):
         x = torch.from_numpy((tile - MEAN) / (STD + 1e-10)).float().unsqueeze(0)
         U.forward(x, params, taps=taps)
     m = model(prec, weights)
+    if prec == "bf16":      # un-fused first so that every intermediate tensor exists in HBM
+        m.engine.set_option("fuse_head", 0); m.engine.set_option("fuse_pool", 0)
     out = m.predict_single(tile, MEAN, STD)
     rel_tol = 1e-4 if prec == "fp32" else 3e-2
     worst = {}
@@ -67,6 +69,19 @@ def test_per_layer_256(prec, weights, params):
     assert not bad, f"{prec}: per-layer rel-to-max error over {rel_tol}: {bad} (all: {worst})"
     err = float(np.abs(out - taps["prob"][0].numpy()).max())
     assert err <= TOL[prec], f"{prec}: prob max-abs err {err}"
+    if prec == "bf16":      # fused epilogues (pool in down*_conv2, softmax head in up1_conv3): same answers
+        pools_unfused = {k: m.engine.debug_layer(k, 0) for k in ("pool1", "pool2", "pool3")}
+        m.engine.set_option("fuse_head", 1); m.engine.set_option("fuse_pool", 1)
+        out_f = m.predict_single(tile, MEAN, STD)
+        for k, v in pools_unfused.items():
+            np.testing.assert_array_equal(m.engine.debug_layer(k, 0), v)
+        for name in ("down1_conv2", "down2_conv2"):
+            ref = taps[name][0].permute(1, 2, 0).numpy()
+            got = m.engine.debug_layer(name, 0)
+            assert np.abs(got - ref).max() / np.abs(ref).max() <= rel_tol
+        assert float(np.abs(out_f - taps["prob"][0].numpy()).max()) <= TOL[prec]
+        # the fused head works on un-rounded fp32 activations: at least as close to the oracle
+        assert np.abs(out_f - out).max() <= 5e-3
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])

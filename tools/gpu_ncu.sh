@@ -1,0 +1,13 @@
+#!/bin/bash
+# ncu evidence: (1) launch list with per-launch device time, (2) full capture of the conv kernel instances
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { cat gpurun_out/build.log; exit 1; }
+CMD="python tools/layer_profile.py 1024 8 bf16"
+$CMD > gpurun_out/plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu1.log 2>&1
+echo "launch list rc=$?"
+$CMD > gpurun_out/plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 40 -c 20 -o gpurun_out/prof_conv $CMD > gpurun_out/ncu2.log 2>&1
+echo "full capture rc=$?"
+tail -n 3 gpurun_out/ncu1.log gpurun_out/ncu2.log
+ls -la gpurun_out/
