@@ -112,6 +112,11 @@ struct adp_engine {
   size_t esz = 4;
   DevBuf a1, cat1, b1, pl1, a2, cat2, b2, pl2, a3, cat3, b3, pl3, t[6], ts, prob;
   DevBuf in_stage, out_stage, fwt_tile, fwt_op, fwt_origin;
+  DevBuf in_stage2[2], out_stage2[2];            // double-buffered host<->device staging of run_tiles
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
+  cudaEvent_t ev_out_ready[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
+  DevBuf fin_prob, fin_mask, fin_gt;             // persistent staging of run_finalize
   std::map<std::string, CUtensorMap> tmaps;
   int last_nfw = 0;
 
@@ -487,7 +492,8 @@ void run_pool(adp_engine *e, const DevBuf &src, int Hs, int Ws, int spitch, int 
   });
 }
 
-template <typename T> void forward_t(adp_engine *e, const FirstConvSrc &src, const FwTable &fw, int nfw, float mean, float std_) {
+template <typename T> void forward_t(adp_engine *e, const FirstConvSrc &src, const FwTable &fw, int nfw, float mean, float std_,
+                                     cudaEvent_t input_consumed) {
   const int S = e->S, S2 = S / 2, S3 = S / 4, S4 = S / 8;
   const int *cp = e->cp;
   // forward table -> device (kernel parameter copy; no host buffer lifetime to worry about)
@@ -511,6 +517,7 @@ template <typename T> void forward_t(adp_engine *e, const FirstConvSrc &src, con
   EpiSpec pool1, pool2, head;
   if (tc && e->fuse_pool) { pool1.mode = EPI_POOL; pool1.pool_dst = &e->pl1; pool2.mode = EPI_POOL; pool2.pool_dst = &e->pl2; }
   if (tc && e->fuse_head) head.mode = EPI_HEAD;
+  if (input_consumed) ADP_CUDA(cudaEventRecord(input_consumed, e->stream));
   run_conv(e, "down1_conv2", e->a1, S, S, cp[0], 0, e->cat1, 2 * cp[0], 0, nfw, pool1);
   if (pool1.mode != EPI_POOL) run_pool<T>(e, e->cat1, S, S, 2 * cp[0], cp[0], e->pl1, nfw);
   run_conv(e, "down2_conv1", e->pl1, S2, S2, cp[0], 0, e->a2, cp[1], 0, nfw);
@@ -551,9 +558,10 @@ template <typename T> void forward_t(adp_engine *e, const FirstConvSrc &src, con
   e->last_nfw = nfw;
 }
 
-void forward(adp_engine *e, const FirstConvSrc &src, const FwTable &fw, int nfw, float mean, float std_) {
-  if (e->prec == ADP_PREC_FP32) forward_t<float>(e, src, fw, nfw, mean, std_);
-  else forward_t<__nv_bfloat16>(e, src, fw, nfw, mean, std_);
+void forward(adp_engine *e, const FirstConvSrc &src, const FwTable &fw, int nfw, float mean, float std_,
+             cudaEvent_t input_consumed = nullptr) {
+  if (e->prec == ADP_PREC_FP32) forward_t<float>(e, src, fw, nfw, mean, std_, input_consumed);
+  else forward_t<__nv_bfloat16>(e, src, fw, nfw, mean, std_, input_consumed);
 }
 
 // Runs n tiles through forward + TTA combine.
@@ -579,16 +587,29 @@ void run_tiles(adp_engine *e, int kind, FirstConvSrc src, const void *src_base, 
   const bool src_host = kind != 2 && !is_device_ptr(src_base);
   TtaOps tops; tops.n = n_ops;
   for (int i = 0; i < 8; ++i) tops.inv[i] = d4_inverse(ops[i < n_ops ? i : 0]);
-  for (int t0 = 0; t0 < n; t0 += tpc) {
+  // Host buffers are staged through two device slots on a copy stream, so the H2D of chunk i+1 and
+  // the D2H of chunk i-1 overlap the kernels of chunk i (events order slot reuse).
+  auto h2d = [&](int ci) {       // issue the input copy of chunk ci on the copy stream
+    const int t0 = ci * tpc, nt = std::min(tpc, n - t0), slot = ci & 1;
+    e->in_stage2[slot].ensure((size_t)tpc * src_tile_bytes);
+    if (ci >= 2) ADP_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_in_free[slot], 0));
+    const uint8_t *sp = reinterpret_cast<const uint8_t *>(src_base) + (size_t)t0 * src_tile_bytes;
+    ADP_CUDA(cudaMemcpyAsync(e->in_stage2[slot].p, sp, (size_t)nt * src_tile_bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    ADP_CUDA(cudaEventRecord(e->ev_in_ready[slot], e->copy_stream));
+  };
+  const int nchunks = cdiv(n, tpc);
+  if (src_host) h2d(0);
+  for (int ci = 0; ci < nchunks; ++ci) {
+    const int t0 = ci * tpc;
     const int nt = std::min(tpc, n - t0);
+    const int slot = ci & 1;
     FirstConvSrc s = src;
     if (kind != 2) {
-      const uint8_t *sp = reinterpret_cast<const uint8_t *>(src_base) + (size_t)t0 * src_tile_bytes;
-      const void *dp = sp;
+      const void *dp = reinterpret_cast<const uint8_t *>(src_base) + (size_t)t0 * src_tile_bytes;
       if (src_host) {
-        e->in_stage.ensure((size_t)tpc * src_tile_bytes);
-        ADP_CUDA(cudaMemcpyAsync(e->in_stage.p, sp, (size_t)nt * src_tile_bytes, cudaMemcpyHostToDevice, e->stream));
-        dp = e->in_stage.p;
+        if (ci + 1 < nchunks) h2d(ci + 1);
+        ADP_CUDA(cudaStreamWaitEvent(e->stream, e->ev_in_ready[slot], 0));
+        dp = e->in_stage2[slot].p;
       }
       s.f32 = kind == 0 ? reinterpret_cast<const float *>(dp) : nullptr;
       s.u8 = kind == 1 ? reinterpret_cast<const uint8_t *>(dp) : nullptr;
@@ -599,12 +620,17 @@ void run_tiles(adp_engine *e, int kind, FirstConvSrc src, const void *src_base, 
       fw.origin[t] = origins ? origins[t0 + t] : 0;     // indexed by local tile
       for (int k = 0; k < n_ops; ++k) { fw.tile[t * n_ops + k] = t; fw.op[t * n_ops + k] = ops[k]; }
     }
-    forward(e, s, fw, nt * n_ops, mean, std_);
+    forward(e, s, fw, nt * n_ops, mean, std_, src_host ? e->ev_in_free[slot] : nullptr);
     dim3 grid(cdiv(S, 32), cdiv(S, 32)), block(32, 8);
     float *dout = nullptr;
     if (out) {
-      if (out_host) { e->out_stage.ensure((size_t)tpc * tile_px * 4); dout = e->out_stage.as<float>(); }
-      else dout = out + (size_t)t0 * tile_px;
+      if (out_host) {
+        e->out_stage2[slot].ensure((size_t)tpc * tile_px * 4);
+        dout = e->out_stage2[slot].as<float>();
+        if (ci >= 2) ADP_CUDA(cudaStreamWaitEvent(e->stream, e->ev_out_free[slot], 0));
+      } else {
+        dout = out + (size_t)t0 * tile_px;
+      }
     }
     for (int t = 0; t < nt; ++t) {
       const float *planes = e->prob.as<float>() + (size_t)t * n_ops * tile_px;
@@ -623,11 +649,15 @@ void run_tiles(adp_engine *e, int kind, FirstConvSrc src, const void *src_base, 
         });
       }
     }
-    if (out && out_host)
-      ADP_CUDA(cudaMemcpyAsync(out + (size_t)t0 * tile_px, dout, (size_t)nt * tile_px * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (src_host || out_host) ADP_CUDA(cudaStreamSynchronize(e->stream));   // staging buffers are reused
+    if (out && out_host) {
+      ADP_CUDA(cudaEventRecord(e->ev_out_ready[slot], e->stream));
+      ADP_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_out_ready[slot], 0));
+      ADP_CUDA(cudaMemcpyAsync(out + (size_t)t0 * tile_px, dout, (size_t)nt * tile_px * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+      ADP_CUDA(cudaEventRecord(e->ev_out_free[slot], e->copy_stream));
+    }
   }
   ADP_CUDA(cudaStreamSynchronize(e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->copy_stream));
 }
 
 // device-visible copy of a small/large host or device array
@@ -641,12 +671,11 @@ const void *to_device(adp_engine *e, DevBuf &buf, const void *p, size_t bytes) {
 
 void run_finalize(adp_engine *e, const float *acc, const float *wsum, int linear, size_t n, float thr, float *prob,
                   uint8_t *mask, const uint8_t *gt, int64_t counts[4]) {
-  DevBuf dprob, dmask, dgt;
   const bool prob_host = prob && !is_device_ptr(prob), mask_host = mask && !is_device_ptr(mask);
   float *dp = prob; uint8_t *dm = mask;
-  if (prob_host) { dprob.ensure(n * 4); dp = dprob.as<float>(); }
-  if (mask_host) { dmask.ensure(n); dm = dmask.as<uint8_t>(); }
-  const uint8_t *dg = reinterpret_cast<const uint8_t *>(to_device(e, dgt, gt, n));
+  if (prob_host) { e->fin_prob.ensure(n * 4); dp = e->fin_prob.as<float>(); }
+  if (mask_host) { e->fin_mask.ensure(n); dm = e->fin_mask.as<uint8_t>(); }
+  const uint8_t *dg = reinterpret_cast<const uint8_t *>(to_device(e, e->fin_gt, gt, n));
   e->counts.ensure(32);
   ADP_CUDA(cudaMemsetAsync(e->counts.p, 0, 32, e->stream));
   const int grid = (int)std::min<size_t>(cdiv64(n, 256 * 4), (size_t)e->num_sms * 8);
@@ -713,6 +742,13 @@ int adp_create(int device, int precision, int init_nb, int max_forwards, adp_eng
   ADP_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   ADP_CUDA(cudaEventCreate(&e->ev0));
   ADP_CUDA(cudaEventCreate(&e->ev1));
+  ADP_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    ADP_CUDA(cudaEventCreateWithFlags(&e->ev_in_ready[i], cudaEventDisableTiming));
+    ADP_CUDA(cudaEventCreateWithFlags(&e->ev_in_free[i], cudaEventDisableTiming));
+    ADP_CUDA(cudaEventCreateWithFlags(&e->ev_out_ready[i], cudaEventDisableTiming));
+    ADP_CUDA(cudaEventCreateWithFlags(&e->ev_out_free[i], cudaEventDisableTiming));
+  }
   for (int nt : {9, 4})
     for (int T : {4, 2, 1})
       ADP_CUDA(cudaFuncSetAttribute(tc_kernel_for(nt, T), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -729,6 +765,13 @@ int adp_destroy(adp_engine *e) {
   cudaStreamSynchronize(e->stream);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_in_ready[i]) cudaEventDestroy(e->ev_in_ready[i]);
+    if (e->ev_in_free[i]) cudaEventDestroy(e->ev_in_free[i]);
+    if (e->ev_out_ready[i]) cudaEventDestroy(e->ev_out_ready[i]);
+    if (e->ev_out_free[i]) cudaEventDestroy(e->ev_out_free[i]);
+  }
+  if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   ADP_CATCH

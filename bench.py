@@ -152,11 +152,18 @@ def run_ours(args, rank, world, local_rank):
         _lib.check(lib.adp_threshold_metrics(eng.h, _lib.ptr(prob_d), _lib.ptr(masks_d), npx, 0.5, _lib.ptr(mask_d), counts))
         return tuple(counts)
 
+    e2e_parts = [0.0, 0.0, 0.0]
+
     def step_e2e():
         # public API with HOST buffers: H2D of the tiles and ground truth, D2H of probabilities, masks, counts
+        t0 = time.perf_counter()
         _lib.check(lib.adp_predict(eng.h, _lib.ptr(tiles_pin), BATCH_TILES, TILE, mean, std, ops_arr, len(ops), _lib.ptr(prob_d)))
+        t1 = time.perf_counter()
         _lib.check(lib.adp_threshold_metrics(eng.h, _lib.ptr(prob_d), _lib.ptr(masks_pin), npx, 0.5, _lib.ptr(mask_pin), counts))
+        t2 = time.perf_counter()
         prob_pin.copy_(prob_d)
+        t3 = time.perf_counter()
+        e2e_parts[0] += t1 - t0; e2e_parts[1] += t2 - t1; e2e_parts[2] += t3 - t2
         return tuple(counts)
 
     stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=torch.device("cuda", local_rank))
@@ -196,6 +203,7 @@ def run_ours(args, rank, world, local_rank):
         sampler.stop_flag = True
     # e2e through the public call with host buffers
     step_e2e()
+    e2e_parts[:] = [0.0, 0.0, 0.0]
     e2e_dev, e2e_wall, res2 = timed(step_e2e, args.steps)
     assert res == res2, "resident and e2e paths disagree"
 
@@ -235,7 +243,10 @@ def run_ours(args, rank, world, local_rank):
                 "e2e": {"value": tiles_total / e2e_dev, "unit": UNIT,
                         "h2d_bytes_per_step": int(tiles_pin.numel() * 4 + masks_pin.numel()),
                         "d2h_bytes_per_step": int(prob_pin.numel() * 4 + mask_pin.numel() + 32),
-                        "wall_value": tiles_total / e2e_wall},
+                        "wall_value": tiles_total / e2e_wall,
+                        "ms_per_step_parts": {"predict_h2d": e2e_parts[0] / args.steps * 1e3,
+                                              "threshold_metrics_h2d_d2h": e2e_parts[1] / args.steps * 1e3,
+                                              "prob_d2h": e2e_parts[2] / args.steps * 1e3}},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "roofline": roof,
