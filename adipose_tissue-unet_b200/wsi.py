@@ -1,0 +1,170 @@
+"""Whole-slide sliding-window driver with tile-row strip sharding.
+
+Replaces the loop of SlidingWindowInference.predict_with_sliding_window
+(Segmentation/full_evaluation_enhanced.py:286-329) and reconstruct_slide
+(Segmentation/reconstruct_full_images.py:334-417) for slides that are cut on the fly: the slide
+strip lives in HBM as uint8, tiles are cut by the first conv kernel, predicted (TTA) and
+blend-accumulated on the device; per-tile predictions are never materialised.
+
+Multi-GPU: one process per GPU.  Rank g owns tile rows [g*n/G, (g+1)*n/G) and an accumulator over
+the pixel rows those tiles touch.  Output rows are owned by the rank whose first tile row starts
+them; a rank's partial sums that fall into a later rank's rows are shipped raw (acc, weight) and
+added there before normalisation — no collective on the data path, only this boundary exchange
+and a final gather of disjoint strips.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .api import TTA_OPCODES
+
+
+def tile_positions(h: int, w: int, tile: int, stride: int) -> List[Tuple[int, int]]:
+    """extract_tile_positions — full_evaluation_enhanced.py:237-265."""
+    pos = []
+    y_steps = max(1, math.ceil((h - tile) / stride) + 1)
+    x_steps = max(1, math.ceil((w - tile) / stride) + 1)
+    for yi in range(y_steps):
+        for xi in range(x_steps):
+            y = min(yi * stride, h - tile)
+            x = min(xi * stride, w - tile)
+            if y >= 0 and x >= 0 and y + tile <= h and x + tile <= w:
+                pos.append((y, x))
+    return pos
+
+
+@dataclass
+class Strip:
+    rank: int
+    tiles: List[Tuple[int, int]]     # (y, x) in list (row-major) order
+    acc_y0: int                      # first pixel row of the accumulator
+    acc_rows: int
+    own_lo: int                      # output rows this rank normalises and returns
+    own_hi: int
+
+
+def plan_strips(h: int, w: int, tile: int, stride: int, world: int) -> List[Strip]:
+    pos = tile_positions(h, w, tile, stride)
+    rows = sorted({y for y, _ in pos})
+    n = len(rows)
+    strips = []
+    bounds = [(g * n) // world for g in range(world + 1)]
+    first_y = []
+    for g in range(world):
+        mine = rows[bounds[g]:bounds[g + 1]]
+        first_y.append(mine[0] if mine else None)
+    for g in range(world):
+        mine = rows[bounds[g]:bounds[g + 1]]
+        if not mine:
+            strips.append(Strip(g, [], 0, 0, 0, 0))
+            continue
+        tiles = [(y, x) for (y, x) in pos if mine[0] <= y <= mine[-1]]
+        nxt = next((first_y[k] for k in range(g + 1, world) if first_y[k] is not None), None)
+        own_lo = 0 if all(first_y[k] is None for k in range(g)) else mine[0]
+        own_hi = h if nxt is None else nxt
+        strips.append(Strip(g, tiles, mine[0], mine[-1] + tile - mine[0], own_lo, own_hi))
+    return strips
+
+
+def boundary_transfers(strips: Sequence[Strip]) -> List[Tuple[int, int, int, int]]:
+    """(src_rank, dst_rank, y, rows): raw partial sums of src that fall into rows dst owns."""
+    out = []
+    for s in strips:
+        if not s.tiles:
+            continue
+        lo, hi = s.acc_y0, s.acc_y0 + s.acc_rows
+        for d in strips:
+            if d.rank == s.rank or not d.tiles:
+                continue
+            a, b = max(lo, d.own_lo), min(hi, d.own_hi)
+            if b > a:
+                out.append((s.rank, d.rank, a, b - a))
+    return out
+
+
+def reconstruct_wsi(engine, slide_rows: Callable[[int, int], np.ndarray], h: int, w: int, *, tile: int = 1024,
+                    overlap: float = 0.5, blend_mode: str = "gaussian", window: Optional[np.ndarray] = None,
+                    mean: float = 127.5, std: float = 50.0, tta_mode: Optional[str] = "full", threshold: float = 0.5,
+                    gt_rows: Optional[Callable[[int, int], np.ndarray]] = None, rank: int = 0, world: int = 1,
+                    dist=None, batch_tiles: int = 16, want_prob: bool = True, want_mask: bool = True,
+                    to_device=None):
+    """Run the sliding window on this rank's strip and exchange boundaries.
+
+    slide_rows(y0, rows) -> uint8 [rows, w] gray rows of the slide (host).  to_device(host_u8) must return
+    an object with a device pointer (`data_ptr()`), e.g. ``lambda a: torch.from_numpy(a).cuda()``.
+    Returns dict(prob, mask, counts, own=(lo, hi), tiles, n_tiles_total) for THIS rank's owned rows; use
+    gather_strips() for the full slide on rank 0.
+    """
+    ov = max(0.0, min(overlap, 0.75))
+    stride = int(tile * (1 - ov))
+    strips = plan_strips(h, w, tile, stride, world)
+    me = strips[rank]
+    ops = TTA_OPCODES[tta_mode] if tta_mode else None
+    mode = _lib.BLEND_GAUSSIAN if blend_mode == "gaussian" else _lib.BLEND_LINEAR
+    result = dict(prob=None, mask=None, counts=(0, 0, 0, 0), own=(me.own_lo, me.own_hi), tiles=len(me.tiles),
+                  n_tiles_total=sum(len(s.tiles) for s in strips))
+    if me.tiles:
+        engine.wsi_begin(me.acc_rows, w, me.acc_y0, tile, mode, window if mode == _lib.BLEND_GAUSSIAN else None)
+        strip_host = np.ascontiguousarray(slide_rows(me.acc_y0, me.acc_rows))
+        assert strip_host.dtype == np.uint8 and strip_host.shape == (me.acc_rows, w)
+        strip_dev = to_device(strip_host)
+        for i in range(0, len(me.tiles), batch_tiles):
+            chunk = me.tiles[i:i + batch_tiles]
+            engine.wsi_push_from_slide(strip_dev, me.acc_y0, me.acc_rows, [p[0] for p in chunk], [p[1] for p in chunk],
+                                       float(mean), float(std), ops)
+    # ---- boundary exchange (rank order => deterministic summation order)
+    for (src, dst, y, rows) in boundary_transfers(strips):
+        if src == rank:
+            acc, wt = engine.wsi_export(y, rows, w)
+            _send(dist, np.stack([acc, wt]), dst)
+        elif dst == rank:
+            buf = _recv(dist, (2, rows, w), src)
+            engine.wsi_import_add(y, buf[0], buf[1])
+    if me.tiles:
+        rows = me.own_hi - me.own_lo
+        gt = gt_rows(me.own_lo, rows) if gt_rows is not None else None
+        prob, mask, counts = engine.wsi_finalize(me.own_lo, rows, w, threshold, gt, want_prob, want_mask)
+        engine.wsi_end()
+        result.update(prob=prob, mask=mask, counts=counts)
+    return result
+
+
+def _send(dist, arr: np.ndarray, dst: int):
+    import torch
+    dist.send(torch.from_numpy(np.ascontiguousarray(arr)), dst)
+
+
+def _recv(dist, shape, src: int) -> np.ndarray:
+    import torch
+    t = torch.empty(shape, dtype=torch.float32)
+    dist.recv(t, src)
+    return t.numpy()
+
+
+def gather_strips(result: dict, h: int, w: int, rank: int, world: int, dist=None):
+    """Halo-free host gather: rank 0 concatenates the disjoint owned strips and sums the counts."""
+    if world == 1:
+        return result["prob"], result["mask"], result["counts"]
+    payload = [None] * world
+    dist.all_gather_object(payload, dict(own=result["own"], counts=result["counts"],
+                                         prob=result["prob"], mask=result["mask"]))
+    if rank != 0:
+        return None, None, None
+    prob = np.zeros((h, w), np.float32) if any(p["prob"] is not None for p in payload) else None
+    mask = np.zeros((h, w), np.uint8) if any(p["mask"] is not None for p in payload) else None
+    counts = [0, 0, 0, 0]
+    for p in payload:
+        lo, hi = p["own"]
+        if hi <= lo:
+            continue
+        if prob is not None and p["prob"] is not None:
+            prob[lo:hi] = p["prob"]
+        if mask is not None and p["mask"] is not None:
+            mask[lo:hi] = p["mask"]
+        counts = [a + b for a, b in zip(counts, p["counts"])]
+    return prob, mask, tuple(counts)

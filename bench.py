@@ -126,7 +126,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local_rank))
 
     eng = api.Engine(precision=args.precision, device=local_rank, max_forwards=args.max_forwards)
     eng.set_weights(A.synth.init_weights())
@@ -207,6 +207,41 @@ def run_ours(args, rank, world, local_rank):
     e2e_dev, e2e_wall, res2 = timed(step_e2e, args.steps)
     assert res == res2, "resident and e2e paths disagree"
 
+    # secondary measurement: sliding-window whole-slide reconstruction (configs[2] geometry, smaller slide),
+    # tile-row strips sharded over the ranks, device time = max over ranks
+    wsi_res = None
+    if args.wsi_size > 0:
+        from adipose_unet_b200 import wsi as W
+        from adipose_unet_b200.api import GaussianBlender
+        Hs = Ws = args.wsi_size
+        win = GaussianBlender(TILE).weight_map
+        blocks = {}
+        def slide_rows(y0, rows):
+            out = np.empty((rows, Ws), np.uint8)
+            for by in range(y0 // TILE, (y0 + rows - 1) // TILE + 1):
+                for bx in range(Ws // TILE):
+                    key = (by % 2, bx % 2)
+                    if key not in blocks:
+                        blocks[key] = A.synth.slide_block(*key, TILE)
+                    a, b = max(by * TILE, y0), min((by + 1) * TILE, y0 + rows)
+                    out[a - y0:b - y0, bx * TILE:(bx + 1) * TILE] = blocks[key][a - by * TILE:b - by * TILE]
+            return out
+        def run_wsi():
+            return W.reconstruct_wsi(eng, slide_rows, Hs, Ws, tile=TILE, overlap=0.5, blend_mode="gaussian", window=win,
+                                     mean=mean, std=std, tta_mode="full", rank=rank, world=world, dist=dist,
+                                     to_device=lambda a: torch.from_numpy(a).cuda(), want_prob=False, want_mask=True)
+        barrier()
+        t0 = time.perf_counter()
+        r = run_wsi()
+        torch.cuda.synchronize()
+        dt_w = time.perf_counter() - t0
+        tw = torch.tensor([dt_w], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        wsi_res = {"slide": f"{Hs}x{Ws}", "overlap": 0.5, "blend": "gaussian", "tta": "full(8)", "tiles": r["n_tiles_total"],
+                   "seconds": float(tw[0]), "mpx_per_s": Hs * Ws / 1e6 / float(tw[0]),
+                   "includes": "host strip assembly + H2D of the uint8 strip + all tiles (8 forwards each) + boundary exchange + normalise/threshold + mask D2H; wall clock, max over ranks"}
+
     # per-kernel profile pass (event-bracketed launches, same step), rank 0 only
     roof = None
     prof_rows = []
@@ -257,6 +292,8 @@ def run_ours(args, rank, world, local_rank):
                              "gbps": (r["bytes"] / (r["ms"] * 1e-3) / 1e9 if r["ms"] > 0 and r["bytes"] else None)}
                             for r in sorted(prof_rows, key=lambda r: -r["ms"])],
                 "wall_ms_per_step": wall_s / args.steps * 1e3}
+        if wsi_res is not None:
+            line["wsi"] = wsi_res
         if not args.no_cpu_baseline and world >= 1:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
@@ -294,6 +331,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16_simt"])
     ap.add_argument("--max-forwards", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wsi-size", type=int, default=8192, help="side of the synthetic slide of the secondary WSI run (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,0 +1,92 @@
+"""GPU parity of the whole-slide path: tiles cut on the device from a resident uint8 slide,
+TTA + blend accumulation, strip sharding (ranks emulated one after another on one GPU)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import adipose_unet_b200 as A
+from adipose_unet_b200 import api, wsi
+from oracle import geometry as G
+from oracle import unet as U
+
+MEAN, STD = A.synth.DEFAULT_MEAN, A.synth.DEFAULT_STD
+S = 128
+
+
+class LocalDist:
+    """Message queue standing in for torch.distributed when ranks run sequentially in one process."""
+
+    def __init__(self):
+        self.q = {}
+
+    def send(self, t, dst):
+        self.q.setdefault(dst, []).append(t.clone())
+
+    def recv(self, t, src):
+        t.copy_(self.q[self.me].pop(0))
+
+
+@pytest.fixture(scope="module")
+def setup():
+    w = A.synth.init_weights()
+    slide = A.synth.synthetic_slide(448, 320, block=128)
+    return w, slide, U.to_torch_params(w)
+
+
+def _oracle(slide, params, overlap, blend, tta):
+    stride = G.stride_for(S, overlap)
+    pos = G.tile_positions(slide.shape[0], slide.shape[1], S, stride)
+    preds = []
+    for y, x in pos:
+        t = np.ascontiguousarray(slide[y:y + S, x:x + S]).astype(np.float32)
+        preds.append(U.predict_with_tta(t, MEAN, STD, params, tta) if tta else U.predict_single(t, MEAN, STD, params))
+    if blend == "gaussian":
+        return G.gaussian_reconstruct(preds, pos, slide.shape, G.gaussian_window(S))
+    return G.linear_reconstruct(preds, pos, slide.shape)
+
+
+def _run(engine, slide, overlap, blend, tta, world):
+    h, w = slide.shape
+    gt = (slide > 150).astype(np.uint8)
+    d = LocalDist()
+    probs = np.zeros((h, w), np.float32); masks = np.zeros((h, w), np.uint8); counts = np.zeros(4, np.int64)
+    for rank in range(world):
+        d.me = rank
+        r = wsi.reconstruct_wsi(engine, lambda y0, n: slide[y0:y0 + n], h, w, tile=S, overlap=overlap, blend_mode=blend,
+                                window=G.gaussian_window(S), mean=MEAN, std=STD, tta_mode=tta,
+                                gt_rows=lambda y0, n: gt[y0:y0 + n], rank=rank, world=world, dist=d,
+                                to_device=lambda a: torch.from_numpy(a).cuda(), batch_tiles=5)
+        lo, hi = r["own"]
+        if hi > lo:
+            probs[lo:hi] = r["prob"]; masks[lo:hi] = r["mask"]; counts += np.array(r["counts"])
+    return probs, masks, counts, gt
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_wsi_from_slide_vs_oracle(setup, prec, tol):
+    w, slide, params = setup
+    eng = api.Engine(precision=prec, max_forwards=16)
+    eng.set_weights(w)
+    for overlap, blend, tta in [(0.5, "gaussian", "basic"), (0.75, "linear", None)]:
+        prob, mask, counts, gt = _run(eng, slide, overlap, blend, tta, 1)
+        ref = _oracle(slide, params, overlap, blend, tta)
+        assert np.abs(prob - ref).max() <= tol
+        np.testing.assert_array_equal(mask, (prob > 0.5).astype(np.uint8))
+        m = G.pixel_metrics(prob, gt, 0.5)
+        assert tuple(counts) == (m["tp"], m["fp"], m["fn"], m["tn"])
+
+
+def test_wsi_strips_equal_single_gpu(setup):
+    w, slide, _ = setup
+    eng = api.Engine(precision="bf16", max_forwards=16)
+    eng.set_weights(w)
+    p1, m1, c1, _ = _run(eng, slide, 0.5, "gaussian", "basic", 1)
+    for world in (2, 3, 8):
+        pg, mg, cg, _ = _run(eng, slide, 0.5, "gaussian", "basic", world)
+        assert np.abs(pg - p1).max() <= 1e-6
+        assert abs(int(cg[0]) - int(c1[0])) <= 2 and cg.sum() == slide.size
+    p1, _, _, _ = _run(eng, slide, 0.75, "linear", None, 1)
+    pg, _, _, _ = _run(eng, slide, 0.75, "linear", None, 4)
+    assert np.abs(pg - p1).max() <= 1e-6

@@ -1,0 +1,131 @@
+"""Host-side logic of the multi-GPU whole-slide path on CPU: strip plan,
+boundary transfers and the exchange/gather plumbing over a world_size-2 (and 3) gloo group, with a
+NumPy stand-in for the device accumulator (the oracle's blend statements)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from adipose_unet_b200 import wsi, _lib
+from oracle import geometry as G
+
+
+class FakeEngine:
+    """adp_wsi_* semantics in NumPy (oracle statements), tile 'prediction' = a fixed local function."""
+
+    def wsi_begin(self, rows, W, y0, tile, mode, window):
+        self.acc = np.zeros((rows, W), np.float32); self.wt = np.zeros((rows, W), np.float32)
+        self.y0, self.tile, self.mode, self.window = y0, tile, mode, window
+
+    def wsi_push_from_slide(self, strip, region_y0, region_rows, ys, xs, mean, std, ops):
+        T = self.tile
+        for y, x in zip(ys, xs):
+            t = strip[y - region_y0:y - region_y0 + T, x:x + T].astype(np.float32)
+            p = (1.0 / (1.0 + np.exp(-((t - mean) / std)))).astype(np.float32)
+            a = self.acc[y - self.y0:y - self.y0 + T, x:x + T]; w = self.wt[y - self.y0:y - self.y0 + T, x:x + T]
+            if self.mode == _lib.BLEND_GAUSSIAN:
+                a += p * self.window; w += self.window
+            else:
+                a += p; w += 1.0
+
+    def wsi_export(self, y, rows, W):
+        return self.acc[y - self.y0:y - self.y0 + rows].copy(), self.wt[y - self.y0:y - self.y0 + rows].copy()
+
+    def wsi_import_add(self, y, acc, wt):
+        self.acc[y - self.y0:y - self.y0 + acc.shape[0]] += acc
+        self.wt[y - self.y0:y - self.y0 + acc.shape[0]] += wt
+
+    def wsi_finalize(self, y, rows, W, threshold=0.5, gt=None, want_prob=True, want_mask=True):
+        a = self.acc[y - self.y0:y - self.y0 + rows]; w = self.wt[y - self.y0:y - self.y0 + rows]
+        p = (a / np.maximum(w, 1e-8 if self.mode == _lib.BLEND_GAUSSIAN else 1.0)).astype(np.float32)
+        m = (p > threshold).astype(np.uint8)
+        if gt is None:
+            counts = (0, int(m.sum()), 0, int((1 - m).sum()))
+        else:
+            g = gt > 0
+            counts = (int((m.astype(bool) & g).sum()), int((m.astype(bool) & ~g).sum()),
+                      int((~m.astype(bool) & g).sum()), int((~m.astype(bool) & ~g).sum()))
+        return p, m, counts
+
+    def wsi_end(self):
+        pass
+
+
+H, W, T = 330, 200, 64
+
+
+def _slide():
+    return (np.random.default_rng(3).random((H, W)) * 255).astype(np.uint8)
+
+
+def _run(rank, world, d, overlap, blend):
+    slide = _slide()
+    gt = (slide > 128).astype(np.uint8)
+    res = wsi.reconstruct_wsi(FakeEngine(), lambda y0, r: slide[y0:y0 + r], H, W, tile=T, overlap=overlap,
+                              blend_mode=blend, window=G.gaussian_window(T), tta_mode=None,
+                              gt_rows=lambda y0, r: gt[y0:y0 + r], rank=rank, world=world, dist=d,
+                              to_device=lambda a: a)
+    return wsi.gather_strips(res, H, W, rank, world, d)
+
+
+def _worker(rank, world, port, overlap, blend, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    prob, mask, counts = _run(rank, world, dist, overlap, blend)
+    if rank == 0:
+        q.put((prob, mask, counts))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def test_strip_plan_covers_everything_once():
+    for (h, w, t, ov, world) in [(330, 200, 64, 0.5, 2), (330, 200, 64, 0.75, 3), (32768, 32768, 1024, 0.5, 8),
+                                 (16384, 16384, 1024, 0.75, 8), (1024, 1024, 1024, 0.5, 4), (700, 64, 64, 0.75, 8)]:
+        stride = int(t * (1 - ov))
+        strips = wsi.plan_strips(h, w, t, stride, world)
+        pos = wsi.tile_positions(h, w, t, stride)
+        assert pos == G.tile_positions(h, w, t, stride)
+        assert [p for s in strips for p in s.tiles] == pos                 # every tile once, list order kept
+        owned = [(s.own_lo, s.own_hi) for s in strips if s.tiles]
+        assert owned[0][0] == 0 and owned[-1][1] == h
+        assert all(a[1] == b[0] for a, b in zip(owned, owned[1:]))         # disjoint, contiguous
+        for s in strips:
+            if s.tiles:
+                assert s.acc_y0 <= s.own_lo or s.rank == 0
+                assert s.own_hi <= s.acc_y0 + s.acc_rows or s.own_hi == h
+        for (src, dst, y, rows) in wsi.boundary_transfers(strips):
+            assert src < dst and rows > 0                                  # only downwards: no exchange cycle
+
+
+@pytest.mark.parametrize("world,overlap,blend", [(2, 0.5, "gaussian"), (3, 0.75, "linear"), (2, 0.75, "gaussian")])
+def test_sharded_equals_single_rank_over_gloo(world, overlap, blend):
+    ref_prob, ref_mask, ref_counts = _run(0, 1, None, overlap, blend)
+    # the single-rank result is the oracle's own reconstruction
+    stride = int(T * (1 - overlap)); pos = G.tile_positions(H, W, T, stride)
+    slide = _slide()
+    tiles = [(1.0 / (1.0 + np.exp(-((slide[y:y + T, x:x + T].astype(np.float32) - 127.5) / 50.0)))).astype(np.float32)
+             for y, x in pos]
+    want = G.gaussian_reconstruct(tiles, pos, (H, W), G.gaussian_window(T)) if blend == "gaussian" else \
+        G.linear_reconstruct(tiles, pos, (H, W))
+    np.testing.assert_allclose(ref_prob, want, atol=1e-6)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, overlap, blend, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    prob, mask, counts = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    np.testing.assert_allclose(prob, ref_prob, atol=1e-6)
+    assert (mask != ref_mask).mean() < 1e-4
+    assert sum(counts) == H * W and abs(counts[0] - ref_counts[0]) <= 2
