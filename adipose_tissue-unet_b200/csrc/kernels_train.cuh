@@ -1,0 +1,326 @@
+// kernels_train.cuh — backward pass and optimizer kernels of the training step
+// (Keras train_step via net.fit, train_adipose_unet_v3.py:1316-1324; loss :217-241; Adam :801-806).
+// fp32, row-planar activations (kernels_simt.cuh).  The data-gradient of a conv is the forward
+// SIMT conv kernel run with flipped/transposed weights; this file holds what has no forward twin.
+#pragma once
+#include "kernels_simt.cuh"
+
+namespace adp {
+
+// ---------------------------------------------------------------------------------------------
+// Head backward.  p = softmax(z)[1] = sigmoid(z1 - z0);  dz1 = g*p*(1-p), dz0 = -dz1.
+// G[c] = dz1 * (w1[c] - w0[c]);  dWh[1][c] = sum dz1 * x[c] = -dWh[0][c];  dbh[1] = sum dz1 = -dbh[0].
+// One thread per pixel; block-level reduction, one double atomic per block and channel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(View<T> x, int nb, const float *__restrict__ wh /*[2][C]*/, const float *__restrict__ prob,
+                const float *__restrict__ dldp, View<T> g, double *__restrict__ dwh1 /*[C]*/, double *__restrict__ dbh1) {
+  extern __shared__ float sm[];
+  float *wd = sm;                       // C: w1 - w0
+  float *red = sm + x.C;                // C + 1 partial sums of this block
+  const int C = x.C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { wd[i] = wh[C + i] - wh[i]; }
+  for (int i = threadIdx.x; i <= C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const size_t total = (size_t)nb * x.H * x.W;
+  const size_t px = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  float dz = 0.f;
+  int xx = 0, yy = 0, n = 0;
+  const bool live = px < total;
+  if (live) {
+    xx = px % x.W; size_t r = px / x.W; yy = r % x.H; n = r / x.H;
+    const float p = prob[px];
+    dz = dldp[px] * p * (1.f - p);
+  }
+  for (int gi = 0; gi < C / 8; ++gi) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o[8];
+    if (live) load8<T>(x.p + x.at(n, yy, gi, xx), a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      o[k] = dz * wd[gi * 8 + k];
+      float s = warp_sum(dz * a[k]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&red[gi * 8 + k], s);
+    }
+    if (live) store8<T>(g.p + g.at(n, yy, gi, xx), o);
+  }
+  {
+    float s = warp_sum(dz);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[C], s);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dwh1[i], (double)red[i]);
+  if (threadIdx.x == 0) atomicAdd(dbh1, (double)red[C]);
+}
+
+// G <- G * [X > 0] * scale   (ReLU backward; scale = 1/keep at a Dropout site, where X is the
+// post-dropout tensor so that [X > 0] already carries the dropout mask)
+template <typename T>
+__global__ void __launch_bounds__(256) relu_mask_kernel(View<T> g, View<T> x, int nb, float scale) {
+  const int G = g.C / 8;
+  const size_t total = (size_t)nb * g.H * G * g.W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int xx = i % g.W; size_t r = i / g.W;
+    int gi = r % G; r /= G;
+    int yy = r % g.H; int n = r / g.H;
+    float a[8], b[8];
+    load8<T>(g.p + g.at(n, yy, gi, xx), a);
+    load8<T>(x.p + x.at(n, yy, gi, xx), b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = b[k] > 0.f ? a[k] * scale : 0.f;
+    store8<T>(g.p + g.at(n, yy, gi, xx), a);
+  }
+}
+
+// Dropout forward (train_adipose_unet_v3.py:682,696,703,710): X <- X * m / keep, m ~ Bernoulli(keep)
+// from a counter-based hash (TF's RNG stream cannot be reproduced; parity tests supply masks instead).
+ADP_DEVINL uint32_t hash_u32(uint64_t k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+  return (uint32_t)k;
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_kernel(View<T> x, int nb, float keep, uint64_t seed, const uint8_t *__restrict__ mask_in /*NHWC real channels, or null*/,
+               int creal) {
+  const int G = x.C / 8;
+  const size_t total = (size_t)nb * x.H * G * x.W;
+  const float inv = 1.f / keep;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int xx = i % x.W; size_t r = i / x.W;
+    int gi = r % G; r /= G;
+    int yy = r % x.H; int n = r / x.H;
+    float a[8];
+    T *ptr = x.p + x.at(n, yy, gi, xx);
+    load8<T>(ptr, a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = gi * 8 + k;
+      bool keep_it;
+      if (mask_in) keep_it = c < creal ? mask_in[(((size_t)n * x.H + yy) * x.W + xx) * creal + c] != 0 : false;
+      else keep_it = (hash_u32(seed + i * 8 + k) * (1.0f / 4294967296.0f)) < keep;
+      a[k] = keep_it ? a[k] * inv : 0.f;
+    }
+    store8<T>(ptr, a);
+  }
+}
+
+// MaxPooling2D backward: the gradient of a pooled pixel goes to the FIRST maximum of its 2x2 window
+// in (dy,dx) scan order.  One thread per pooled pixel and channel group; gin is ADDED into (the skip
+// tensor's gradient already holds the decoder branch).
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(View<T> xin, View<T> gout, View<T> gin, int nb) {
+  const int G = gout.C / 8;
+  const size_t total = (size_t)nb * gout.H * G * gout.W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int xx = i % gout.W; size_t r = i / gout.W;
+    int gi = r % G; r /= G;
+    int yy = r % gout.H; int n = r / gout.H;
+    float go[8], v[4][8], gi4[4][8];
+    load8<T>(gout.p + gout.at(n, yy, gi, xx), go);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      load8<T>(xin.p + xin.at(n, 2 * yy + (q >> 1), gi, 2 * xx + (q & 1)), v[q]);
+      load8<T>(gin.p + gin.at(n, 2 * yy + (q >> 1), gi, 2 * xx + (q & 1)), gi4[q]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int best = 0;
+#pragma unroll
+      for (int q = 1; q < 4; ++q) if (v[q][k] > v[best][k]) best = q;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (q == best) gi4[q][k] += go[k];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) store8<T>(gin.p + gin.at(n, 2 * yy + (q >> 1), gi, 2 * xx + (q & 1)), gi4[q]);
+  }
+}
+
+// UpSampling2D backward: glow[y][x] = sum of the 2x2 block of ghigh
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2_bwd_kernel(View<T> ghigh, View<T> glow, int nb) {
+  const int G = glow.C / 8;
+  const size_t total = (size_t)nb * glow.H * G * glow.W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int xx = i % glow.W; size_t r = i / glow.W;
+    int gi = r % G; r /= G;
+    int yy = r % glow.H; int n = r / glow.H;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      load8<T>(ghigh.p + ghigh.at(n, 2 * yy + (q >> 1), gi, 2 * xx + (q & 1)), a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] += a[k];
+    }
+    store8<T>(glow.p + glow.at(n, yy, gi, xx), s);
+  }
+}
+
+// dst (view) <- a (view) + b (view)   — gradient fan-in of the Add / skip connections
+template <typename T>
+__global__ void __launch_bounds__(256) add_views_kernel(View<T> dst, View<T> a, View<T> b, int nb) {
+  const int G = dst.C / 8;
+  const size_t total = (size_t)nb * dst.H * G * dst.W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int xx = i % dst.W; size_t r = i / dst.W;
+    int gi = r % G; r /= G;
+    int yy = r % dst.H; int n = r / dst.H;
+    float u[8], v[8];
+    load8<T>(a.p + a.at(n, yy, gi, xx), u);
+    load8<T>(b.p + b.at(n, yy, gi, xx), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u[k] += v[k];
+    store8<T>(dst.p + dst.at(n, yy, gi, xx), u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight gradient of a 3x3 conv:  dW[t][ci][co] = sum_{n,y,x} Xin[n, y+dy_t, x+dx_t, ci] * dZ[n,y,x,co]
+// (zero outside the image; UP: Xin is the nearest-upsampled view of xin), db[co] = sum dZ.
+// grid = (9 taps, ci tiles x co tiles (64 x 64), pixel splits); block = 256 threads, each a 4x4
+// register tile; partial sums leave through fp32 atomics into dW[9][cin_pad][cout_pad].
+template <typename T, bool UP>
+__global__ void __launch_bounds__(256)
+conv_wgrad_kernel(View<T> xin, View<T> dz, float *__restrict__ dW, float *__restrict__ db, int dil, int nb, int cin_pad,
+                  int cout_pad, int co_tiles) {
+  __shared__ float xs[64][33];
+  __shared__ float zs[64][33];
+  const int t = blockIdx.x;
+  const int ci0 = (blockIdx.y / co_tiles) * 64, co0 = (blockIdx.y % co_tiles) * 64;
+  const int H = dz.H, W = dz.W;
+  const int dy = (t / 3 - 1) * dil, dx = (t % 3 - 1) * dil;
+  const int tid = threadIdx.x;
+  const int tci = tid >> 4, tco = tid & 15;
+  const int lp = tid & 31, lplane = tid >> 5;          // loader role: pixel in chunk, channel group in tile
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum[4] = {0, 0, 0, 0};
+  const int chunks_per_row = (W + 31) / 32;
+  const long long nchunks = (long long)nb * H * chunks_per_row;
+  for (long long ch = blockIdx.z; ch < nchunks; ch += gridDim.z) {
+    const int cx = (int)(ch % chunks_per_row) * 32;
+    long long r = ch / chunks_per_row;
+    const int y = (int)(r % H), n = (int)(r / H);
+    __syncthreads();
+    {
+      const int x = cx + lp;
+      float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const int iy = y + dy, ix = x + dx;
+      const int gci = (ci0 >> 3) + lplane, gco = (co0 >> 3) + lplane;
+      if (x < W && iy >= 0 && iy < H && ix >= 0 && ix < W && gci * 8 < cin_pad)
+        load8<T>(xin.p + xin.at(n, UP ? (iy >> 1) : iy, gci, UP ? (ix >> 1) : ix), a);
+      if (x < W && gco * 8 < cout_pad) load8<T>(dz.p + dz.at(n, y, gco, x), b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { xs[lplane * 8 + k][lp] = a[k]; zs[lplane * 8 + k][lp] = b[k]; }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int p = 0; p < 32; ++p) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = xs[tci * 4 + i][p]; b[i] = zs[tco * 4 + i][p]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      if (tci == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bsum[j] += b[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ci = ci0 + tci * 4 + i;
+    if (ci >= cin_pad) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tco * 4 + j;
+      if (co < cout_pad) atomicAdd(&dW[((size_t)t * cin_pad + ci) * cout_pad + co], acc[i][j]);
+    }
+  }
+  if (db && t == 4 && ci0 == 0 && tci == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tco * 4 + j;
+      if (co < cout_pad) atomicAdd(&db[co], bsum[j]);
+    }
+  }
+}
+
+// First layer (Cin = 1) weight gradient: dW[t][co] = sum x_norm(p + tap) * dZ[p][co], db[co] = sum dZ.
+// xnorm: [nb][S][S] float32 (already normalised).  block = 256 threads = 32 pixels x 8 lanes of work.
+template <typename T>
+__global__ void __launch_bounds__(256)
+first_wgrad_kernel(const float *__restrict__ xnorm, View<T> dz, int nb, float *__restrict__ dW /*[9][C]*/, float *__restrict__ db) {
+  extern __shared__ float sm[];      // [10][C] block partials
+  const int C = dz.C, S = dz.H;
+  for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const size_t total = (size_t)nb * S * S;
+  for (size_t px = blockIdx.x * (size_t)blockDim.x + threadIdx.x; px < total; px += (size_t)gridDim.x * blockDim.x) {
+    const int x = px % S; size_t r = px / S; const int y = r % S; const int n = r / S;
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
+      v[t] = (iy >= 0 && iy < S && ix >= 0 && ix < S) ? xnorm[((size_t)n * S + iy) * S + ix] : 0.f;
+    }
+    for (int gi = 0; gi < C / 8; ++gi) {
+      float g[8];
+      load8<T>(dz.p + dz.at(n, y, gi, x), g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (g[k] == 0.f) continue;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) atomicAdd(&sm[t * C + gi * 8 + k], v[t] * g[k]);
+        atomicAdd(&sm[9 * C + gi * 8 + k], g[k]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) atomicAdd(&dW[i], sm[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&db[i], sm[9 * C + i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Keras 2.13 Adam / AdamW update_step on the flat parameter buffer (epsilon OUTSIDE the bias correction):
+//   [AdamW] theta -= theta * wd * lr
+//   m += (g - m)(1 - b1);  v += (g^2 - v)(1 - b2);  theta -= (m * alpha) / (sqrt(v) + eps),
+//   alpha = lr * sqrt(1 - b2^t) / (1 - b1^t)  (computed on the host in float32 like Keras does)
+// trainable: per-parameter-segment flags are applied by launching only over trainable ranges.
+__global__ void __launch_bounds__(256)
+adam_kernel(float *__restrict__ theta, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, size_t n,
+            float gscale, float alpha, float one_minus_b1, float one_minus_b2, float eps, float wd_lr) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float th = theta[i];
+    const float gi = g[i] * gscale;
+    if (wd_lr != 0.f) th = __fsub_rn(th, __fmul_rn(th, wd_lr));
+    float mi = m[i], vi = v[i];
+    mi = __fadd_rn(mi, __fmul_rn(__fsub_rn(gi, mi), one_minus_b1));
+    vi = __fadd_rn(vi, __fmul_rn(__fsub_rn(__fmul_rn(gi, gi), vi), one_minus_b2));
+    th = __fsub_rn(th, __fdiv_rn(__fmul_rn(mi, alpha), __fadd_rn(__fsqrt_rn(vi), eps)));
+    theta[i] = th; m[i] = mi; v[i] = vi;
+  }
+}
+
+// flat HWIO parameter segment <-> padded [9][cin_pad][cout_pad] kernel layout (concat layers: the second
+// half of the real input channels starts at pad16(skip))
+__global__ void __launch_bounds__(256)
+pad_kernel_weights(const float *__restrict__ flat, float *__restrict__ padded, int taps, int cin, int cout, int cin_pad,
+                   int cout_pad, int skip, int skip_pad, int to_flat, int transpose_flip) {
+  const size_t total = (size_t)taps * cin * cout;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int co = i % cout; size_t r = i / cout;
+    const int ci = r % cin; const int t = r / cin;
+    const int cip = (skip && ci >= skip) ? skip_pad + (ci - skip) : ci;
+    size_t pi;
+    if (transpose_flip) pi = ((size_t)(taps - 1 - t) * cout_pad + co) * cin_pad + cip;   // dgrad weights [t'][co][ci]
+    else pi = ((size_t)t * cin_pad + cip) * cout_pad + co;
+    if (to_flat) const_cast<float *>(flat)[i] = padded[pi];
+    else padded[pi] = flat[i];
+  }
+}
+
+}  // namespace adp

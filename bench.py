@@ -126,7 +126,19 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout at communicator creation: keep stdout = the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local_rank))
+            t = torch.zeros(1, device="cuda")
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     eng = api.Engine(precision=args.precision, device=local_rank, max_forwards=args.max_forwards)
     eng.set_weights(A.synth.init_weights())
