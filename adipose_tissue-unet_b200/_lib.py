@@ -18,6 +18,8 @@ LIB_PATH = os.path.join(_HERE, "libadipose_b200.so")
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16_simt": PREC_BF16_SIMT}
 BLEND_GAUSSIAN, BLEND_LINEAR = 0, 1
+OPT_ADAM, OPT_ADAMW = 0, 1
+OPTIMIZERS = {"adam": OPT_ADAM, "adamw": OPT_ADAMW}
 
 
 class ProfRow(C.Structure):
@@ -60,6 +62,18 @@ SIGNATURES = {
     "adp_wsi_finalize": (_I, [_P, _I, _I, _F, _P, _P, _P, C.POINTER(_I64)]),
     "adp_wsi_end": (_I, [_P]),
     "adp_loss_metrics": (_I, [_P, _P, _P, _I64, _P, C.POINTER(C.c_double)]),
+    "adp_train_begin": (_I, [_P, _I, _I, _F, C.c_uint64]),
+    "adp_train_forward": (_I, [_P, _P, _P, _I, C.POINTER(_P), C.POINTER(C.c_double)]),
+    "adp_train_loss": (_I, [C.POINTER(C.c_double), _I64, C.POINTER(C.c_double)]),
+    "adp_train_backward": (_I, [_P, C.POINTER(C.c_double), _I64, _I]),
+    "adp_train_grad_buffer": (_I, [_P, C.POINTER(_P), C.POINTER(_I64)]),
+    "adp_train_get_grad": (_I, [_P, C.c_char_p, _P, _I64, _P, _I64]),
+    "adp_train_probs": (_I, [_P, _P, _I64]),
+    "adp_train_apply": (_I, [_P, _I, _F, _F, C.c_double, C.c_double, _F, _F, _I]),
+    "adp_train_step": (_I, [_P, _P, _P, _I, _I, _F, _F, _I, C.POINTER(C.c_double)]),
+    "adp_train_iterations": (_I64, [_P]),
+    "adp_train_end": (_I, [_P]),
+    "adp_adam_update": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I, _F, C.c_double, C.c_double, _F, _F]),
     "adp_profile_enable": (_I, [_P, _I]),
     "adp_profile_reset": (_I, [_P]),
     "adp_profile_read": (_I, [_P, C.POINTER(ProfRow), _I]),

@@ -148,6 +148,92 @@ class Engine:
         res = dict(loss=out[0], bce=out[1], dice_loss=out[2], dice_coef=out[3])
         return (res, g) if want_grad else res
 
+    # ---- training step (Keras train_step: train_adipose_unet_v3.py:1316-1324)
+    DROPOUT_SITES = ("dropout_dilate1", "dropout_up3", "dropout_up2", "dropout_up1")
+
+    def train_begin(self, batch: int, size: int, dropout_rate: float = 0.3, seed: int = 865):
+        _lib.check(self.lib.adp_train_begin(self.h, batch, size, dropout_rate, seed))
+        self._train_shape = (batch, size, size)
+
+    def train_forward(self, x, y, dropout_masks: Optional[Dict[str, np.ndarray]] = None) -> np.ndarray:
+        """x, y: (B,S,S) float32 (normalised image, target).  dropout_masks: site name -> (B,h,w,C) 0/1.
+        Returns the six loss sums (float64) of this batch."""
+        if isinstance(x, np.ndarray):
+            x = _f32c(x)
+        if isinstance(y, np.ndarray):
+            y = _f32c(y)
+        sums = (C.c_double * 6)()
+        mptr = None
+        keep = []
+        if dropout_masks is not None:
+            arr = (C.c_void_p * 4)()
+            for i, site in enumerate(self.DROPOUT_SITES):
+                m = np.ascontiguousarray(dropout_masks[site], dtype=np.uint8)
+                keep.append(m)
+                arr[i] = m.ctypes.data
+            mptr = arr
+        _lib.check(self.lib.adp_train_forward(self.h, _lib.ptr(x), _lib.ptr(y), int(x.shape[0]), mptr, sums))
+        return np.array(list(sums), dtype=np.float64)
+
+    def train_loss(self, sums, n_px: int) -> Dict[str, float]:
+        s = (C.c_double * 6)(*[float(v) for v in sums])
+        out = (C.c_double * 4)()
+        _lib.check(self.lib.adp_train_loss(s, int(n_px), out))
+        return dict(loss=out[0], bce=out[1], dice_loss=out[2], dice_coef=out[3])
+
+    def train_backward(self, sums, n_px_global: int = 0, freeze_encoder: bool = False):
+        s = (C.c_double * 6)(*[float(v) for v in sums])
+        _lib.check(self.lib.adp_train_backward(self.h, s, int(n_px_global), 1 if freeze_encoder else 0))
+
+    def train_grad_buffer(self) -> Tuple[int, int]:
+        """(device address, element count) of the flat fp32 gradient — what a data-parallel wrapper all-reduces."""
+        p = C.c_void_p(); n = C.c_int64()
+        _lib.check(self.lib.adp_train_grad_buffer(self.h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def train_grads(self) -> Dict[str, np.ndarray]:
+        out = {}
+        for name, (ks, bs) in weight_shapes(self.init_nb).items():
+            k = np.empty(ks, np.float32); b = np.empty(bs, np.float32)
+            _lib.check(self.lib.adp_train_get_grad(self.h, name.encode(), _lib.ptr(k), k.size, _lib.ptr(b), b.size))
+            out[name + "/kernel"] = k; out[name + "/bias"] = b
+        return out
+
+    def train_probs(self) -> np.ndarray:
+        out = np.empty(self._train_shape, np.float32)
+        _lib.check(self.lib.adp_train_probs(self.h, _lib.ptr(out), out.size))
+        return out
+
+    def train_apply(self, lr: float, optimizer: str = "adam", grad_scale: float = 1.0, beta1: float = 0.9,
+                    beta2: float = 0.999, eps: float = 1e-7, weight_decay: float = 0.01, freeze_encoder: bool = False):
+        _lib.check(self.lib.adp_train_apply(self.h, _lib.OPTIMIZERS[optimizer], lr, grad_scale, beta1, beta2, eps,
+                                            weight_decay, 1 if freeze_encoder else 0))
+
+    def train_step(self, x, y, lr: float, optimizer: str = "adam", weight_decay: float = 0.01,
+                   freeze_encoder: bool = False) -> Dict[str, float]:
+        if isinstance(x, np.ndarray):
+            x = _f32c(x)
+        if isinstance(y, np.ndarray):
+            y = _f32c(y)
+        out = (C.c_double * 4)()
+        _lib.check(self.lib.adp_train_step(self.h, _lib.ptr(x), _lib.ptr(y), int(x.shape[0]), _lib.OPTIMIZERS[optimizer], lr,
+                                           weight_decay, 1 if freeze_encoder else 0, out))
+        return dict(loss=out[0], bce=out[1], dice_loss=out[2], dice_coef=out[3])
+
+    def train_iterations(self) -> int:
+        return int(self.lib.adp_train_iterations(self.h))
+
+    def train_end(self):
+        _lib.check(self.lib.adp_train_end(self.h))
+
+    def adam_update(self, theta, grad, m, v, t: int, lr: float, optimizer: str = "adam", beta1: float = 0.9,
+                    beta2: float = 0.999, eps: float = 1e-7, weight_decay: float = 0.0):
+        """One Keras-2.13 Adam/AdamW update on caller arrays (returns new theta, m, v)."""
+        theta = _f32c(theta).copy(); m = _f32c(m).copy(); v = _f32c(v).copy(); grad = _f32c(grad)
+        _lib.check(self.lib.adp_adam_update(self.h, _lib.ptr(theta), _lib.ptr(grad), _lib.ptr(m), _lib.ptr(v), theta.size, t,
+                                            _lib.OPTIMIZERS[optimizer], lr, beta1, beta2, eps, weight_decay))
+        return theta, m, v
+
     # ---- whole-slide accumulator
     def wsi_begin(self, rows, W, y0, tile, mode, window):
         win = _f32c(window) if window is not None else None

@@ -19,6 +19,7 @@
 #include "conv_tc.cuh"
 #include "kernels_post.cuh"
 #include "kernels_simt.cuh"
+#include "kernels_train.cuh"
 
 using namespace adp;
 
@@ -95,6 +96,18 @@ struct ConvLayer {
   bool tc_ready = false;
 };
 
+// Activation buffers of one forward.  Inference aliases buffers whose lifetimes do not overlap
+// (a1 holds down1_conv1 and later up1_conv2, ...); training keeps every tensor for the backward pass.
+struct Acts {
+  DevBuf *d1a, *cat1, *u1b, *u1c, *pl1;
+  DevBuf *d2a, *cat2, *u2b, *u2c, *pl2;
+  DevBuf *d3a, *cat3, *u3b, *u3c, *pl3;
+  DevBuf *t[6], *ts, *prob;
+  int cap;                       // images the buffers are sized for (outermost TMA dimension)
+};
+
+struct TrainState;
+
 }  // namespace
 
 struct adp_engine {
@@ -119,6 +132,8 @@ struct adp_engine {
   DevBuf fin_prob, fin_mask, fin_gt;             // persistent staging of run_finalize
   std::map<std::string, CUtensorMap> tmaps;
   int last_nfw = 0;
+  Acts acts{};                                   // inference buffer assignment
+  TrainState *tr = nullptr;                      // training arena (adp_train_begin .. adp_train_end)
 
   // whole-slide accumulator
   bool wsi_on = false;
@@ -389,6 +404,12 @@ void ensure_arena(adp_engine *e, int S) {
   e->fwt_tile.ensure(64 * 4); e->fwt_op.ensure(64 * 4); e->fwt_origin.ensure(64 * 8);
   e->tmaps.clear();
   e->S = S;
+  Acts &a = e->acts;
+  a.d1a = &e->a1; a.cat1 = &e->cat1; a.u1b = &e->a1; a.u1c = &e->b1; a.pl1 = &e->pl1;
+  a.d2a = &e->a2; a.cat2 = &e->cat2; a.u2b = &e->a2; a.u2c = &e->b2; a.pl2 = &e->pl2;
+  a.d3a = &e->a3; a.cat3 = &e->cat3; a.u3b = &e->a3; a.u3c = &e->b3; a.pl3 = &e->pl3;
+  for (int i = 0; i < 6; ++i) a.t[i] = &e->t[i];
+  a.ts = &e->ts; a.prob = &e->prob; a.cap = e->max_fw;
 }
 
 // pitch / coff / C in channels (multiples of 8); the buffer is row-planar (kernels_simt.cuh)
@@ -399,15 +420,16 @@ template <typename T> View<T> view(const DevBuf &b, int H, int W, int pitch, int
 }
 
 const CUtensorMap &get_tmap(adp_engine *e, const ConvLayer &L, const DevBuf &src, int H, int W, int pitch, int coff,
-                            int C) {
-  auto it = e->tmaps.find(L.name);
+                            int C, int cap) {
+  const std::string key = L.name + "@" + std::to_string((uintptr_t)src.p) + "/" + std::to_string(coff) + "/" + std::to_string(H);
+  auto it = e->tmaps.find(key);
   if (it != e->tmaps.end()) return it->second;
   const ConvTcParams &p = L.tc;
   CUtensorMap m;
   ADP_REQUIRE(W % 8 == 0, "tcgen05 conv path needs every level's width to be a multiple of 8 (tile size % 64 == 0)");
   // row-planar source [n][y][cg][x][8]: dim0 = 8 pixels x 8 channels (one 128-byte line), dim1 = 8-pixel
   // groups along the row, dim2 = channel group, dim3 = row, dim4 = image
-  cuuint64_t gdim[5] = {64, (cuuint64_t)(W / 8), (cuuint64_t)(C / 8), (cuuint64_t)H, (cuuint64_t)e->max_fw};
+  cuuint64_t gdim[5] = {64, (cuuint64_t)(W / 8), (cuuint64_t)(C / 8), (cuuint64_t)H, (cuuint64_t)cap};
   const cuuint64_t cgs = pitch / 8;
   cuuint64_t gstr[4] = {128, (cuuint64_t)W * 16, cgs * W * 16, (cuuint64_t)H * cgs * W * 16};
   cuuint32_t box[5] = {64, (cuuint32_t)(p.PW / 8), 2, (cuuint32_t)p.BR, 1};
@@ -418,7 +440,7 @@ const CUtensorMap &get_tmap(adp_engine *e, const ConvLayer &L, const DevBuf &src
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     throw Error(ADP_ECUDA, "cuTensorMapEncodeTiled failed for " + L.name + " code " + std::to_string((int)r));
-  return e->tmaps.emplace(L.name, m).first->second;
+  return e->tmaps.emplace(key, m).first->second;
 }
 
 double conv_flops(const ConvLayer &L, int Hout, int Wout, int nb) {
@@ -429,10 +451,11 @@ double conv_flops(const ConvLayer &L, int Hout, int Wout, int nb) {
 struct EpiSpec {
   int mode = EPI_STORE;
   const DevBuf *pool_dst = nullptr;   // EPI_POOL: dense pooled tensor (pitch = channels of the layer)
+  float *prob = nullptr;              // EPI_HEAD: probability planes
 };
 
 void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs, int Ws, int spitch, int scoff,
-              const DevBuf &dst, int dpitch, int dcoff, int nb, EpiSpec epi = EpiSpec()) {
+              const DevBuf &dst, int dpitch, int dcoff, int nb, int cap, EpiSpec epi = EpiSpec()) {
   ConvLayer &L = layer(e, name);
   const int Ho = L.up ? Hs * 2 : Hs, Wo = L.up ? Ws * 2 : Ws;
   const double fl = conv_flops(L, Ho, Wo, nb);
@@ -447,12 +470,12 @@ void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs,
     p.epi_mode = epi.mode;
     if (epi.mode == EPI_HEAD) {
       ADP_REQUIRE(p.T >= 2 && p.nvar == 1 && p.N == e->cp[0], "head fusion needs the 44-channel full-resolution layer");
-      p.head_w = e->w_head.as<float>(); p.head_b = e->b_head.as<float>(); p.prob = e->prob.as<float>();
+      p.head_w = e->w_head.as<float>(); p.head_b = e->b_head.as<float>(); p.prob = epi.prob;
     } else if (epi.mode == EPI_POOL) {
       ADP_REQUIRE(p.T % 2 == 0 && p.oscale == 1 && Ho % 2 == 0 && Wo % 2 == 0, "pool fusion needs an even row block");
       p.pool_out = epi.pool_dst->as<__nv_bfloat16>(); p.pool_cgs = L.cout_pad / 8; p.pool_cg0 = 0;
     }
-    const CUtensorMap &tm = get_tmap(e, L, src, Hs, Ws, spitch, scoff, L.cin_pad);
+    const CUtensorMap &tm = get_tmap(e, L, src, Hs, Ws, spitch, scoff, L.cin_pad, cap);
     const int nitems = nb * p.nty * p.ntx * p.nvar;
     const int grid = std::min(nitems, e->num_sms);
     const size_t smem = tc_smem_bytes(p);
@@ -492,10 +515,28 @@ void run_pool(adp_engine *e, const DevBuf &src, int Hs, int Ws, int spitch, int 
   });
 }
 
-template <typename T> void forward_t(adp_engine *e, const FirstConvSrc &src, const FwTable &fw, int nfw, float mean, float std_,
-                                     cudaEvent_t input_consumed) {
-  const int S = e->S, S2 = S / 2, S3 = S / 4, S4 = S / 8;
-  const int *cp = e->cp;
+// Dropout sites of the training graph (train_adipose_unet_v3.py:682,696,703,710); inference passes null.
+struct DropSpec {
+  float keep = 1.f;
+  uint64_t seed = 0;
+  const uint8_t *mask[4] = {nullptr, nullptr, nullptr, nullptr};   // supplied masks (NHWC, real channels) or null
+};
+
+template <typename T>
+void run_dropout(adp_engine *e, const DevBuf &buf, int H, int C, int creal, int nb, const DropSpec &d, int site) {
+  auto v = view<T>(buf, H, H, C, 0, C);
+  const size_t total = (size_t)nb * H * H * (C / 8);
+  const int grid = (int)std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 16);
+  e->launch("dropout", 0, (double)total * 16 * sizeof(T), [&] {
+    dropout_kernel<T><<<grid, 256, 0, e->stream>>>(v, nb, d.keep, d.seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(site + 1), d.mask[site], creal);
+  });
+}
+
+template <typename T> void forward_t(adp_engine *e, const Acts &A, int S, const FirstConvSrc &src, const FwTable &fw, int nfw,
+                                     float mean, float std_, cudaEvent_t input_consumed, const DropSpec *drop) {
+  const int S2 = S / 2, S3 = S / 4, S4 = S / 8;
+  const int *cp = e->cp, *c = e->c;
+  const int cap = A.cap;
   // forward table -> device (kernel parameter copy; no host buffer lifetime to worry about)
   e->launch("fw_table", 0, 0, [&] {
     fw_table_store<<<1, 64, 0, e->stream>>>(fw, e->fwt_tile.as<int>(), e->fwt_op.as<int>(), e->fwt_origin.as<long long>(), nfw);
@@ -505,7 +546,7 @@ template <typename T> void forward_t(adp_engine *e, const FirstConvSrc &src, con
   const float mean_f = mean;
   const float sd_f = (float)((double)std_ + 1e-10);
   {
-    auto out = view<T>(e->a1, S, S, cp[0], 0, cp[0]);
+    auto out = view<T>(*A.d1a, S, S, cp[0], 0, cp[0]);
     dim3 grid(cdiv(S, 32), cdiv(S, 8), nfw), block(32, 8);
     const size_t smem = (size_t)10 * cp[0] * 4;
     e->launch("first_conv", 2.0 * nfw * S * S * 9.0 * e->c[0], (double)nfw * S * S * (4 + cp[0] * sizeof(T)), [&] {
@@ -514,45 +555,50 @@ template <typename T> void forward_t(adp_engine *e, const FirstConvSrc &src, con
     });
   }
   const bool tc = e->prec == ADP_PREC_BF16;
+  const bool dropping = drop && (drop->keep < 1.f || drop->mask[0]);
   EpiSpec pool1, pool2, head;
-  if (tc && e->fuse_pool) { pool1.mode = EPI_POOL; pool1.pool_dst = &e->pl1; pool2.mode = EPI_POOL; pool2.pool_dst = &e->pl2; }
-  if (tc && e->fuse_head) head.mode = EPI_HEAD;
+  if (tc && e->fuse_pool) { pool1.mode = EPI_POOL; pool1.pool_dst = A.pl1; pool2.mode = EPI_POOL; pool2.pool_dst = A.pl2; }
+  if (tc && e->fuse_head && !drop) { head.mode = EPI_HEAD; head.prob = A.prob->as<float>(); }   // training keeps up1_conv3
   if (input_consumed) ADP_CUDA(cudaEventRecord(input_consumed, e->stream));
-  run_conv(e, "down1_conv2", e->a1, S, S, cp[0], 0, e->cat1, 2 * cp[0], 0, nfw, pool1);
-  if (pool1.mode != EPI_POOL) run_pool<T>(e, e->cat1, S, S, 2 * cp[0], cp[0], e->pl1, nfw);
-  run_conv(e, "down2_conv1", e->pl1, S2, S2, cp[0], 0, e->a2, cp[1], 0, nfw);
-  run_conv(e, "down2_conv2", e->a2, S2, S2, cp[1], 0, e->cat2, 2 * cp[1], 0, nfw, pool2);
-  if (pool2.mode != EPI_POOL) run_pool<T>(e, e->cat2, S2, S2, 2 * cp[1], cp[1], e->pl2, nfw);
-  run_conv(e, "down3_conv1", e->pl2, S3, S3, cp[1], 0, e->a3, cp[2], 0, nfw);
-  run_conv(e, "down3_conv2", e->a3, S3, S3, cp[2], 0, e->cat3, 2 * cp[2], 0, nfw);
-  run_pool<T>(e, e->cat3, S3, S3, 2 * cp[2], cp[2], e->pl3, nfw);
-  run_conv(e, "dilate1", e->pl3, S4, S4, cp[2], 0, e->t[0], cp[3], 0, nfw);
+  run_conv(e, "down1_conv2", *A.d1a, S, S, cp[0], 0, *A.cat1, 2 * cp[0], 0, nfw, cap, pool1);
+  if (pool1.mode != EPI_POOL) run_pool<T>(e, *A.cat1, S, S, 2 * cp[0], cp[0], *A.pl1, nfw);
+  run_conv(e, "down2_conv1", *A.pl1, S2, S2, cp[0], 0, *A.d2a, cp[1], 0, nfw, cap);
+  run_conv(e, "down2_conv2", *A.d2a, S2, S2, cp[1], 0, *A.cat2, 2 * cp[1], 0, nfw, cap, pool2);
+  if (pool2.mode != EPI_POOL) run_pool<T>(e, *A.cat2, S2, S2, 2 * cp[1], cp[1], *A.pl2, nfw);
+  run_conv(e, "down3_conv1", *A.pl2, S3, S3, cp[1], 0, *A.d3a, cp[2], 0, nfw, cap);
+  run_conv(e, "down3_conv2", *A.d3a, S3, S3, cp[2], 0, *A.cat3, 2 * cp[2], 0, nfw, cap);
+  run_pool<T>(e, *A.cat3, S3, S3, 2 * cp[2], cp[2], *A.pl3, nfw);
+  run_conv(e, "dilate1", *A.pl3, S4, S4, cp[2], 0, *A.t[0], cp[3], 0, nfw, cap);
+  if (dropping) run_dropout<T>(e, *A.t[0], S4, cp[3], c[3], nfw, *drop, 0);
   const char *dn[5] = {"dilate2", "dilate3", "dilate4", "dilate5", "dilate6"};
-  for (int i = 0; i < 5; ++i) run_conv(e, dn[i], e->t[i], S4, S4, cp[3], 0, e->t[i + 1], cp[3], 0, nfw);
+  for (int i = 0; i < 5; ++i) run_conv(e, dn[i], *A.t[i], S4, S4, cp[3], 0, *A.t[i + 1], cp[3], 0, nfw, cap);
   {
     const size_t nvec = (size_t)nfw * S4 * S4 * cp[3] * sizeof(T) / 16;
     const int grid = (int)std::min<size_t>(cdiv64(nvec, 256), (size_t)e->num_sms * 16);
     e->launch("add6", 0, (double)nvec * 16 * 7, [&] {
-      add6_kernel<T><<<grid, 256, 0, e->stream>>>(e->t[0].as<T>(), e->t[1].as<T>(), e->t[2].as<T>(), e->t[3].as<T>(),
-                                                 e->t[4].as<T>(), e->t[5].as<T>(), e->ts.as<T>(), nvec);
+      add6_kernel<T><<<grid, 256, 0, e->stream>>>(A.t[0]->as<T>(), A.t[1]->as<T>(), A.t[2]->as<T>(), A.t[3]->as<T>(),
+                                                 A.t[4]->as<T>(), A.t[5]->as<T>(), A.ts->as<T>(), nvec);
     });
   }
-  run_conv(e, "up3_conv1", e->ts, S4, S4, cp[3], 0, e->cat3, 2 * cp[2], cp[2], nfw);
-  run_conv(e, "up3_conv2", e->cat3, S3, S3, 2 * cp[2], 0, e->a3, cp[2], 0, nfw);
-  run_conv(e, "up3_conv3", e->a3, S3, S3, cp[2], 0, e->b3, cp[2], 0, nfw);
-  run_conv(e, "up2_conv1", e->b3, S3, S3, cp[2], 0, e->cat2, 2 * cp[1], cp[1], nfw);
-  run_conv(e, "up2_conv2", e->cat2, S2, S2, 2 * cp[1], 0, e->a2, cp[1], 0, nfw);
-  run_conv(e, "up2_conv3", e->a2, S2, S2, cp[1], 0, e->b2, cp[1], 0, nfw);
-  run_conv(e, "up1_conv1", e->b2, S2, S2, cp[1], 0, e->cat1, 2 * cp[0], cp[0], nfw);
-  run_conv(e, "up1_conv2", e->cat1, S, S, 2 * cp[0], 0, e->a1, cp[0], 0, nfw);
-  run_conv(e, "up1_conv3", e->a1, S, S, cp[0], 0, e->b1, cp[0], 0, nfw, head);
+  run_conv(e, "up3_conv1", *A.ts, S4, S4, cp[3], 0, *A.cat3, 2 * cp[2], cp[2], nfw, cap);
+  run_conv(e, "up3_conv2", *A.cat3, S3, S3, 2 * cp[2], 0, *A.u3b, cp[2], 0, nfw, cap);
+  run_conv(e, "up3_conv3", *A.u3b, S3, S3, cp[2], 0, *A.u3c, cp[2], 0, nfw, cap);
+  if (dropping) run_dropout<T>(e, *A.u3c, S3, cp[2], c[2], nfw, *drop, 1);
+  run_conv(e, "up2_conv1", *A.u3c, S3, S3, cp[2], 0, *A.cat2, 2 * cp[1], cp[1], nfw, cap);
+  run_conv(e, "up2_conv2", *A.cat2, S2, S2, 2 * cp[1], 0, *A.u2b, cp[1], 0, nfw, cap);
+  run_conv(e, "up2_conv3", *A.u2b, S2, S2, cp[1], 0, *A.u2c, cp[1], 0, nfw, cap);
+  if (dropping) run_dropout<T>(e, *A.u2c, S2, cp[1], c[1], nfw, *drop, 2);
+  run_conv(e, "up1_conv1", *A.u2c, S2, S2, cp[1], 0, *A.cat1, 2 * cp[0], cp[0], nfw, cap);
+  run_conv(e, "up1_conv2", *A.cat1, S, S, 2 * cp[0], 0, *A.u1b, cp[0], 0, nfw, cap);
+  run_conv(e, "up1_conv3", *A.u1b, S, S, cp[0], 0, *A.u1c, cp[0], 0, nfw, cap, head);
+  if (dropping) run_dropout<T>(e, *A.u1c, S, cp[0], c[0], nfw, *drop, 3);
   if (head.mode != EPI_HEAD) {
-    auto in = view<T>(e->b1, S, S, cp[0], 0, cp[0]);
+    auto in = view<T>(*A.u1c, S, S, cp[0], 0, cp[0]);
     const size_t total = (size_t)nfw * S * S;
     const int grid = (int)std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 16);
     e->launch("head_softmax", 2.0 * total * e->c[0] * 2, (double)total * (cp[0] * sizeof(T) + 4), [&] {
       head_kernel<T><<<grid, 256, (size_t)2 * cp[0] * 4, e->stream>>>(in, nfw, e->w_head.as<float>(), e->b_head.as<float>(),
-                                                                      e->prob.as<float>());
+                                                                      A.prob->as<float>());
     });
   }
   e->last_nfw = nfw;
@@ -560,8 +606,8 @@ template <typename T> void forward_t(adp_engine *e, const FirstConvSrc &src, con
 
 void forward(adp_engine *e, const FirstConvSrc &src, const FwTable &fw, int nfw, float mean, float std_,
              cudaEvent_t input_consumed = nullptr) {
-  if (e->prec == ADP_PREC_FP32) forward_t<float>(e, src, fw, nfw, mean, std_, input_consumed);
-  else forward_t<__nv_bfloat16>(e, src, fw, nfw, mean, std_, input_consumed);
+  if (e->prec == ADP_PREC_FP32) forward_t<float>(e, e->acts, e->S, src, fw, nfw, mean, std_, input_consumed, nullptr);
+  else forward_t<__nv_bfloat16>(e, e->acts, e->S, src, fw, nfw, mean, std_, input_consumed, nullptr);
 }
 
 // Runs n tiles through forward + TTA combine.
@@ -694,6 +740,8 @@ void run_finalize(adp_engine *e, const float *acc, const float *wsum, int linear
 
 }  // namespace
 
+#include "train_host.cuh"
+
 // ================================================================================================
 // C ABI
 // ================================================================================================
@@ -773,6 +821,7 @@ int adp_destroy(adp_engine *e) {
   }
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   if (e->stream) cudaStreamDestroy(e->stream);
+  delete e->tr;
   delete e;
   ADP_CATCH
 }
@@ -815,6 +864,7 @@ int adp_set_weight(adp_engine *e, const char *layer_name, const float *kernel, c
       throw Error(ADP_EINVAL, "kernel shape mismatch for " + n + ": expected (" + std::to_string(want[0]) + "," + std::to_string(want[1]) +
                                   "," + std::to_string(want[2]) + "," + std::to_string(want[3]) + ")");
   ADP_REQUIRE(nbias == want[3], "bias length mismatch");
+  if (e->tr) throw Error(ADP_ESTATE, "weights cannot be replaced while a training state is open (adp_train_end first)");
   HostWeight &h = e->hw[n];
   const size_t ne = (size_t)(want[0] * want[1] * want[2] * want[3]);
   h.k.assign(kernel, kernel + ne);
@@ -828,6 +878,7 @@ int adp_set_weight(adp_engine *e, const char *layer_name, const float *kernel, c
 int adp_get_weight(adp_engine *e, const char *layer_name, float *kernel, int64_t kernel_elems, float *bias, int64_t nbias) {
   ADP_TRY
   ADP_REQUIRE(e && layer_name, "null argument");
+  if (e->tr) { ADP_CUDA(cudaSetDevice(e->device)); sync_host_weights(e); }
   auto it = e->hw.find(layer_name);
   if (it == e->hw.end() || !it->second.set) throw Error(ADP_ESTATE, std::string("layer not set: ") + layer_name);
   const HostWeight &h = it->second;
@@ -1170,6 +1221,158 @@ int adp_loss_metrics(adp_engine *e, const float *p, const float *y, int64_t n_px
     if (host) ADP_CUDA(cudaMemcpyAsync(dldp, g, n * 4, cudaMemcpyDeviceToHost, e->stream));
     ADP_CUDA(cudaStreamSynchronize(e->stream));
   }
+  ADP_CATCH
+}
+
+int adp_train_begin(adp_engine *e, int batch, int size, float dropout_rate, uint64_t seed) {
+  ADP_TRY
+  ADP_REQUIRE(e, "engine");
+  ADP_CUDA(cudaSetDevice(e->device));
+  if (e->tr) { sync_host_weights(e); delete e->tr; e->tr = nullptr; }
+  e->tmaps.clear();
+  train_alloc(e, batch, size, dropout_rate, seed);
+  ADP_CATCH
+}
+
+int adp_train_forward(adp_engine *e, const float *x, const float *y, int batch, const uint8_t *const *dropout_masks,
+                      double sums[6]) {
+  ADP_TRY
+  ADP_REQUIRE(e && x && y && sums, "null argument");
+  ADP_CUDA(cudaSetDevice(e->device));
+  train_forward(e, x, y, batch, dropout_masks, sums);
+  ADP_CATCH
+}
+
+int adp_train_loss(const double sums[6], int64_t n_px, double out[4]) {
+  if (!sums || !out || n_px <= 0) return ADP_EINVAL;
+  loss_from_sums(sums, (double)n_px, out);
+  return ADP_OK;
+}
+
+int adp_train_backward(adp_engine *e, const double sums[6], int64_t n_px_global, int freeze_encoder) {
+  ADP_TRY
+  ADP_REQUIRE(e && sums, "null argument");
+  ADP_CUDA(cudaSetDevice(e->device));
+  train_backward(e, sums, n_px_global, freeze_encoder != 0);
+  ADP_CATCH
+}
+
+int adp_train_grad_buffer(adp_engine *e, float **dev_ptr, int64_t *count) {
+  ADP_TRY
+  ADP_REQUIRE(e && dev_ptr && count, "null argument");
+  if (!e->tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
+  *dev_ptr = e->tr->grad.as<float>();
+  *count = (int64_t)e->tr->P;
+  ADP_CATCH
+}
+
+int adp_train_get_grad(adp_engine *e, const char *layer_name, float *kernel, int64_t kernel_elems, float *bias, int64_t nbias) {
+  ADP_TRY
+  ADP_REQUIRE(e && layer_name, "null argument");
+  if (!e->tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
+  ADP_CUDA(cudaSetDevice(e->device));
+  size_t off = 0;
+  bool found = false;
+  for (const char *n : kAllNames) {
+    const size_t ke = kernel_elems_of(e, n), be = bias_elems_of(e, n);
+    if (std::string(n) == layer_name) {
+      ADP_CUDA(cudaStreamSynchronize(e->stream));
+      if (kernel) { ADP_REQUIRE(kernel_elems == (int64_t)ke, "kernel_elems"); ADP_CUDA(cudaMemcpy(kernel, e->tr->grad.as<float>() + off, ke * 4, cudaMemcpyDeviceToHost)); }
+      if (bias) { ADP_REQUIRE(nbias == (int64_t)be, "nbias"); ADP_CUDA(cudaMemcpy(bias, e->tr->grad.as<float>() + off + ke, be * 4, cudaMemcpyDeviceToHost)); }
+      found = true;
+      break;
+    }
+    off += ke + be;
+  }
+  if (!found) throw Error(ADP_EINVAL, std::string("unknown layer ") + layer_name);
+  ADP_CATCH
+}
+
+int adp_train_probs(adp_engine *e, float *out, int64_t out_elems) {
+  ADP_TRY
+  ADP_REQUIRE(e && out, "null argument");
+  if (!e->tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const size_t n = (size_t)e->tr->nb * e->tr->S * e->tr->S;
+  ADP_REQUIRE(out_elems == (int64_t)n, "out_elems");
+  ADP_CUDA(cudaMemcpyAsync(out, e->tr->prob.p, n * 4, cudaMemcpyDefault, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  ADP_CATCH
+}
+
+int adp_train_apply(adp_engine *e, int optimizer, float lr, float grad_scale, double beta1, double beta2, float eps,
+                    float weight_decay, int freeze_encoder) {
+  ADP_TRY
+  ADP_REQUIRE(e, "engine");
+  ADP_REQUIRE(optimizer == ADP_OPT_ADAM || optimizer == ADP_OPT_ADAMW, "optimizer");
+  ADP_CUDA(cudaSetDevice(e->device));
+  train_apply(e, optimizer, lr, grad_scale, beta1 > 0 ? beta1 : 0.9, beta2 > 0 ? beta2 : 0.999, eps > 0 ? eps : 1e-7f, weight_decay,
+              freeze_encoder != 0);
+  ADP_CATCH
+}
+
+int adp_train_step(adp_engine *e, const float *x, const float *y, int batch, int optimizer, float lr, float weight_decay,
+                   int freeze_encoder, double out[4]) {
+  ADP_TRY
+  ADP_REQUIRE(e && x && y, "null argument");
+  ADP_REQUIRE(optimizer == ADP_OPT_ADAM || optimizer == ADP_OPT_ADAMW, "optimizer");
+  ADP_CUDA(cudaSetDevice(e->device));
+  double sums[6];
+  train_forward(e, x, y, batch, nullptr, sums);
+  if (out) loss_from_sums(sums, (double)batch * e->tr->S * e->tr->S, out);
+  train_backward(e, sums, 0, freeze_encoder != 0);
+  train_apply(e, optimizer, lr, 1.f, 0.9, 0.999, 1e-7f, weight_decay, freeze_encoder != 0);
+  ADP_CATCH
+}
+
+int64_t adp_train_iterations(adp_engine *e) { return (e && e->tr) ? e->tr->iter : -1; }
+
+int adp_train_end(adp_engine *e) {
+  ADP_TRY
+  ADP_REQUIRE(e, "engine");
+  ADP_CUDA(cudaSetDevice(e->device));
+  if (e->tr) {
+    sync_host_weights(e);
+    delete e->tr;
+    e->tr = nullptr;
+    e->tmaps.clear();
+    e->packed = false;        // rebuild the inference operand images from the (updated) host master copy
+  }
+  ADP_CATCH
+}
+
+int adp_adam_update(adp_engine *e, float *theta, const float *grad, float *m, float *v, int64_t n, int64_t t, int optimizer,
+                    float lr, double beta1, double beta2, float eps, float weight_decay) {
+  ADP_TRY
+  ADP_REQUIRE(e && theta && grad && m && v && n > 0 && t >= 1, "null/empty argument");
+  ADP_CUDA(cudaSetDevice(e->device));
+  DevBuf dth, dg, dm, dv;
+  const size_t nb = (size_t)n * 4;
+  const bool host = !is_device_ptr(theta);
+  float *pth = theta, *pm = m, *pv = v; const float *pg = grad;
+  if (host) {
+    dth.ensure(nb); dg.ensure(nb); dm.ensure(nb); dv.ensure(nb);
+    ADP_CUDA(cudaMemcpyAsync(dth.p, theta, nb, cudaMemcpyHostToDevice, e->stream));
+    ADP_CUDA(cudaMemcpyAsync(dg.p, grad, nb, cudaMemcpyHostToDevice, e->stream));
+    ADP_CUDA(cudaMemcpyAsync(dm.p, m, nb, cudaMemcpyHostToDevice, e->stream));
+    ADP_CUDA(cudaMemcpyAsync(dv.p, v, nb, cudaMemcpyHostToDevice, e->stream));
+    pth = dth.as<float>(); pg = dg.as<float>(); pm = dm.as<float>(); pv = dv.as<float>();
+  }
+  if (beta1 <= 0) beta1 = 0.9;
+  if (beta2 <= 0) beta2 = 0.999;
+  if (eps <= 0) eps = 1e-7f;
+  const float b1p = powf((float)beta1, (float)t), b2p = powf((float)beta2, (float)t);
+  const float alpha = lr * sqrtf(1.f - b2p) / (1.f - b1p);
+  e->launch("adam_update", 0, (double)n * 28, [&] {
+    adam_kernel<<<ew_grid(e, (size_t)n), 256, 0, e->stream>>>(pth, pg, pm, pv, (size_t)n, 1.f, alpha, (float)(1.0 - beta1), (float)(1.0 - beta2), eps,
+                                                              optimizer == ADP_OPT_ADAMW ? weight_decay : 0.f, lr);
+  });
+  if (host) {
+    ADP_CUDA(cudaMemcpyAsync(theta, pth, nb, cudaMemcpyDeviceToHost, e->stream));
+    ADP_CUDA(cudaMemcpyAsync(m, pm, nb, cudaMemcpyDeviceToHost, e->stream));
+    ADP_CUDA(cudaMemcpyAsync(v, pv, nb, cudaMemcpyDeviceToHost, e->stream));
+  }
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
   ADP_CATCH
 }
 

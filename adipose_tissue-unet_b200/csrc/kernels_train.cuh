@@ -292,11 +292,11 @@ first_wgrad_kernel(const float *__restrict__ xnorm, View<T> dz, int nb, float *_
 // trainable: per-parameter-segment flags are applied by launching only over trainable ranges.
 __global__ void __launch_bounds__(256)
 adam_kernel(float *__restrict__ theta, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, size_t n,
-            float gscale, float alpha, float one_minus_b1, float one_minus_b2, float eps, float wd_lr) {
+            float gscale, float alpha, float one_minus_b1, float one_minus_b2, float eps, float wd, float lr) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float th = theta[i];
     const float gi = g[i] * gscale;
-    if (wd_lr != 0.f) th = __fsub_rn(th, __fmul_rn(th, wd_lr));
+    if (wd != 0.f) th = __fsub_rn(th, __fmul_rn(__fmul_rn(th, wd), lr));
     float mi = m[i], vi = v[i];
     mi = __fadd_rn(mi, __fmul_rn(__fsub_rn(gi, mi), one_minus_b1));
     vi = __fadd_rn(vi, __fmul_rn(__fsub_rn(__fmul_rn(gi, gi), vi), one_minus_b2));
@@ -320,6 +320,65 @@ pad_kernel_weights(const float *__restrict__ flat, float *__restrict__ padded, i
     else pi = ((size_t)t * cin_pad + cip) * cout_pad + co;
     if (to_flat) const_cast<float *>(flat)[i] = padded[pi];
     else padded[pi] = flat[i];
+  }
+}
+
+}  // namespace adp
+
+namespace adp {
+
+// head gradient sums (double) -> flat float gradients of output_softmax: kernel (1,1,C,2), bias (2)
+__global__ void head_grad_finish_kernel(const double *__restrict__ acc /*[C+1]*/, int C, int acc_c, float *__restrict__ gk, float *__restrict__ gb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) { const float v = (float)acc[i]; gk[i * 2 + 1] = v; gk[i * 2] = -v; }
+  if (i == 0) { const float v = (float)acc[acc_c]; gb[1] = v; gb[0] = -v; }
+}
+
+// flat output_softmax kernel (C,2) -> [2][Cpad]
+__global__ void head_pack_kernel(const float *__restrict__ flat, int C, int Cpad, float *__restrict__ wh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) { wh[i] = flat[i * 2]; wh[Cpad + i] = flat[i * 2 + 1]; }
+}
+
+__global__ void round_bf16_kernel(float *__restrict__ p, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = __bfloat162float(__float2bfloat16_rn(p[i]));
+}
+
+// Device twin of the host packer of the tcgen05 B operand (engine.cu pack_layer): from padded fp32
+// weights wp[9][cin_pad][cout_pad] to bf16 blocks [variant][chunk][tap][2 planes][N][8].
+// up != 0: variant = output parity, tap = (ry,rx) of the 2x2 source window, value = sum of the 3x3 taps
+// that read the same source pixel (summed in fp32, rounded once).
+__global__ void __launch_bounds__(256)
+pack_tc_kernel(const float *__restrict__ wp, __nv_bfloat16 *__restrict__ dst, int nvar, int nchunks, int ntaps, int N,
+               int cin_pad, int cout_pad, int up) {
+  const size_t blk = (size_t)16 * N;
+  const size_t total = (size_t)nvar * nchunks * ntaps * blk;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = i % 8; size_t r = i / 8;
+    const int n = r % N; r /= N;
+    const int g = r % 2; r /= 2;
+    const int t = r % ntaps; r /= ntaps;
+    const int c = r % nchunks; const int v = r / nchunks;
+    const int ci = c * 16 + g * 8 + j;
+    float val = 0.f;
+    if (ci < cin_pad) {
+      if (up) {
+        const int py = v >> 1, px = v & 1, ry = t >> 1, rx = t & 1;
+        for (int ky = 0; ky < 3; ++ky) {
+          const int sy = (py + ky - 1) >= 0 ? (py + ky - 1) / 2 : -1;
+          if (sy - (py - 1) != ry) continue;
+          for (int kx = 0; kx < 3; ++kx) {
+            const int sx = (px + kx - 1) >= 0 ? (px + kx - 1) / 2 : -1;
+            if (sx - (px - 1) != rx) continue;
+            val += wp[((size_t)(ky * 3 + kx) * cin_pad + ci) * cout_pad + n];
+          }
+        }
+      } else {
+        val = wp[((size_t)t * cin_pad + ci) * cout_pad + v * N + n];
+      }
+    }
+    dst[i] = __float2bfloat16_rn(val);
   }
 }
 

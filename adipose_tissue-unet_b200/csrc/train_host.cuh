@@ -1,0 +1,460 @@
+// train_host.cuh — host orchestration of the training step (included by engine.cu).
+// Reference: Keras train_step via net.fit (train_adipose_unet_v3.py:1316-1324, 1413-1421),
+// combined_loss_standard (:217-241), Adam/AdamW (:801-806), freeze/unfreeze (:760-778).
+//
+// State lives on the device for the whole training run: a flat fp32 parameter vector theta in
+// Keras order (kernel HWIO then bias, layer order of kAllNames == creation order), a flat gradient
+// of the same shape (the buffer a data-parallel wrapper all-reduces), Adam moments m and v, every
+// forward activation (row-planar, the backward pass needs them) and their gradients.  After each
+// optimizer step the operand images the kernels read (padded fp32 / packed bf16 / flipped dgrad
+// weights) are rebuilt on the device from theta.
+#pragma once
+
+namespace {
+
+struct TrainLayer {
+  DevBuf wT;        // dgrad weights [9][cout_pad][cin_pad], taps flipped (fp32; bf16-rounded values off the fp32 path)
+  DevBuf gw, gb;    // padded weight / bias gradients [9][cin_pad][cout_pad], [cout_pad]
+  size_t koff = 0, boff = 0;   // offsets into the flat vectors
+};
+
+struct TrainState {
+  int nb = 0, S = 0;
+  float keep = 1.f;
+  uint64_t seed = 0;
+  int64_t iter = 0;           // optimizer iterations done
+  size_t P = 0;
+  DevBuf theta, grad, m, v;
+  size_t koff_first = 0, boff_first = 0, koff_head = 0, boff_head = 0;
+  std::vector<TrainLayer> tl;
+  DevBuf gw_first, gb_first, g_head;     // [9][cp0], [cp0], double [cp0 + 1]
+  DevBuf zeros, sums;
+  DevBuf x, y, dldp;
+  // activations
+  DevBuf d1a, cat1, u1b, u1c, pl1, d2a, cat2, u2b, u2c, pl2, d3a, cat3, u3b, u3c, pl3, t[6], ts, prob;
+  // gradients (same shapes); the dilate chain ping-pongs between gt[0] and gt[1]
+  DevBuf g_d1a, g_cat1, g_u1b, g_u1c, g_pl1, g_d2a, g_cat2, g_u2b, g_u2c, g_pl2, g_d3a, g_cat3, g_u3b, g_u3c, g_pl3,
+      gt[2], g_ts, g_hi;
+  Acts acts{};
+  bool have_forward = false, have_grads = false;
+  bool host_stale = false;    // theta moved on since the host master copy was written
+  DevBuf mask_stage[4];
+};
+
+size_t kernel_elems_of(adp_engine *e, const std::string &n) {
+  if (n == "down1_conv1") return (size_t)9 * e->c[0];
+  if (n == "output_softmax") return (size_t)2 * e->c[0];
+  const ConvLayer &L = layer(e, n);
+  return (size_t)9 * L.cin * L.cout;
+}
+size_t bias_elems_of(adp_engine *e, const std::string &n) {
+  if (n == "down1_conv1") return e->c[0];
+  if (n == "output_softmax") return 2;
+  return layer(e, n).cout;
+}
+
+int ew_grid(adp_engine *e, size_t n) { return (int)std::max<size_t>(1, std::min<size_t>(cdiv64(n, 256), (size_t)e->num_sms * 16)); }
+
+// theta -> every operand image the kernels read
+void repack_from_theta(adp_engine *e) {
+  TrainState *tr = e->tr;
+  const float *th = tr->theta.as<float>();
+  const bool bf = e->prec != ADP_PREC_FP32;
+  const int cp0 = e->cp[0], c0 = e->c[0];
+  e->launch("repack_weights", 0, (double)tr->P * 4 * 3, [&] {
+    // first conv [9][cp0] and bias (never rounded), head [2][cp0] and bias
+    pad_kernel_weights<<<ew_grid(e, 9 * c0), 256, 0, e->stream>>>(th + tr->koff_first, e->w_first.as<float>(), 9, 1, c0, 1, cp0, 0, 0, 0, 0);
+    head_pack_kernel<<<1, 256, 0, e->stream>>>(th + tr->koff_head, c0, cp0, e->w_head.as<float>());
+  });
+  ADP_CUDA(cudaMemcpyAsync(e->b_first.p, th + tr->boff_first, (size_t)c0 * 4, cudaMemcpyDeviceToDevice, e->stream));
+  ADP_CUDA(cudaMemcpyAsync(e->b_head.p, th + tr->boff_head, 8, cudaMemcpyDeviceToDevice, e->stream));
+  for (size_t i = 0; i < e->layers.size(); ++i) {
+    ConvLayer &L = e->layers[i];
+    TrainLayer &T = tr->tl[i];
+    const size_t ne = (size_t)9 * L.cin * L.cout, np = (size_t)9 * L.cin_pad * L.cout_pad;
+    const int sp = L.skip ? pad16(L.skip) : 0;
+    const int g = ew_grid(e, ne);
+    pad_kernel_weights<<<g, 256, 0, e->stream>>>(th + T.koff, L.w_simt.as<float>(), 9, L.cin, L.cout, L.cin_pad, L.cout_pad, L.skip, sp, 0, 0);
+    pad_kernel_weights<<<g, 256, 0, e->stream>>>(th + T.koff, T.wT.as<float>(), 9, L.cin, L.cout, L.cin_pad, L.cout_pad, L.skip, sp, 0, 1);
+    if (e->prec == ADP_PREC_BF16)   // pack from the unrounded padded copy (parity taps are summed in fp32)
+      pack_tc_kernel<<<ew_grid(e, np * 2), 256, 0, e->stream>>>(L.w_simt.as<float>(), L.w_tc.as<__nv_bfloat16>(), L.tc.nvar, L.tc.nchunks,
+                                                               L.tc.ntaps, L.tc.N, L.cin_pad, L.cout_pad, L.up ? 1 : 0);
+    if (bf) {
+      round_bf16_kernel<<<ew_grid(e, np), 256, 0, e->stream>>>(L.w_simt.as<float>(), np);
+      round_bf16_kernel<<<ew_grid(e, np), 256, 0, e->stream>>>(T.wT.as<float>(), np);
+    }
+    ADP_CUDA(cudaMemcpyAsync(L.bias.p, th + T.boff, (size_t)L.cout * 4, cudaMemcpyDeviceToDevice, e->stream));
+    e->launches += bf ? 5 : 2;
+  }
+  ADP_CUDA(cudaGetLastError());
+}
+
+// device theta -> host master copies (adp_get_weight, adp_train_end)
+void sync_host_weights(adp_engine *e) {
+  TrainState *tr = e->tr;
+  if (!tr || !tr->host_stale) return;
+  std::vector<float> h(tr->P);
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  ADP_CUDA(cudaMemcpy(h.data(), tr->theta.p, tr->P * 4, cudaMemcpyDeviceToHost));
+  size_t off = 0;
+  for (const char *n : kAllNames) {
+    HostWeight &w = e->hw[n];
+    const size_t ke = kernel_elems_of(e, n), be = bias_elems_of(e, n);
+    w.k.assign(h.begin() + off, h.begin() + off + ke); off += ke;
+    w.b.assign(h.begin() + off, h.begin() + off + be); off += be;
+  }
+  tr->host_stale = false;
+}
+
+void train_alloc(adp_engine *e, int nb, int S, float dropout_rate, uint64_t seed) {
+  ADP_REQUIRE(nb >= 1 && nb <= 64, "batch must be 1..64");
+  ADP_REQUIRE(S >= 64 && S % 64 == 0 && S <= 4096, "training tile size must be a multiple of 64");
+  ADP_REQUIRE(dropout_rate >= 0.f && dropout_rate < 1.f, "dropout rate");
+  if (!e->packed) pack_all(e);
+  std::unique_ptr<TrainState> tr(new TrainState());
+  tr->nb = nb; tr->S = S; tr->keep = 1.f - dropout_rate; tr->seed = seed;
+  const size_t es = e->esz, n = nb;
+  const size_t s1 = (size_t)S * S, s2 = s1 / 4, s3 = s1 / 16, s4 = s1 / 64;
+  const int *cp = e->cp;
+  auto A = [&](DevBuf &act, DevBuf &g, size_t elems) { act.ensure(elems * es); g.ensure(elems * es); };
+  A(tr->d1a, tr->g_d1a, n * s1 * cp[0]); A(tr->cat1, tr->g_cat1, n * s1 * 2 * cp[0]);
+  A(tr->u1b, tr->g_u1b, n * s1 * cp[0]); A(tr->u1c, tr->g_u1c, n * s1 * cp[0]); A(tr->pl1, tr->g_pl1, n * s2 * cp[0]);
+  A(tr->d2a, tr->g_d2a, n * s2 * cp[1]); A(tr->cat2, tr->g_cat2, n * s2 * 2 * cp[1]);
+  A(tr->u2b, tr->g_u2b, n * s2 * cp[1]); A(tr->u2c, tr->g_u2c, n * s2 * cp[1]); A(tr->pl2, tr->g_pl2, n * s3 * cp[1]);
+  A(tr->d3a, tr->g_d3a, n * s3 * cp[2]); A(tr->cat3, tr->g_cat3, n * s3 * 2 * cp[2]);
+  A(tr->u3b, tr->g_u3b, n * s3 * cp[2]); A(tr->u3c, tr->g_u3c, n * s3 * cp[2]); A(tr->pl3, tr->g_pl3, n * s4 * cp[2]);
+  for (int i = 0; i < 6; ++i) tr->t[i].ensure(n * s4 * cp[3] * es);
+  tr->ts.ensure(n * s4 * cp[3] * es);
+  tr->gt[0].ensure(n * s4 * cp[3] * es); tr->gt[1].ensure(n * s4 * cp[3] * es); tr->g_ts.ensure(n * s4 * cp[3] * es);
+  // hi-res data gradient of an UpSampling2D-fed conv before its 2x2 reduction: largest is up1_conv1 (S^2 x cp1)
+  tr->g_hi.ensure(n * std::max({s1 * cp[1], s2 * cp[2], s3 * cp[3]}) * es);
+  tr->prob.ensure(n * s1 * 4); tr->x.ensure(n * s1 * 4); tr->y.ensure(n * s1 * 4); tr->dldp.ensure(n * s1 * 4);
+  tr->zeros.ensure(4096); ADP_CUDA(cudaMemset(tr->zeros.p, 0, 4096));
+  tr->sums.ensure(64);
+  e->fwt_tile.ensure(64 * 4); e->fwt_op.ensure(64 * 4); e->fwt_origin.ensure(64 * 8);
+  Acts &a = tr->acts;
+  a.d1a = &tr->d1a; a.cat1 = &tr->cat1; a.u1b = &tr->u1b; a.u1c = &tr->u1c; a.pl1 = &tr->pl1;
+  a.d2a = &tr->d2a; a.cat2 = &tr->cat2; a.u2b = &tr->u2b; a.u2c = &tr->u2c; a.pl2 = &tr->pl2;
+  a.d3a = &tr->d3a; a.cat3 = &tr->cat3; a.u3b = &tr->u3b; a.u3c = &tr->u3c; a.pl3 = &tr->pl3;
+  for (int i = 0; i < 6; ++i) a.t[i] = &tr->t[i];
+  a.ts = &tr->ts; a.prob = &tr->prob; a.cap = nb;
+
+  // flat parameter vector
+  size_t off = 0;
+  tr->tl.resize(e->layers.size());
+  std::vector<float> h;
+  for (const char *nm : kAllNames) {
+    const std::string n2 = nm;
+    const size_t ke = kernel_elems_of(e, n2), be = bias_elems_of(e, n2);
+    if (n2 == "down1_conv1") { tr->koff_first = off; tr->boff_first = off + ke; }
+    else if (n2 == "output_softmax") { tr->koff_head = off; tr->boff_head = off + ke; }
+    else {
+      for (size_t i = 0; i < e->layers.size(); ++i)
+        if (e->layers[i].name == n2) { tr->tl[i].koff = off; tr->tl[i].boff = off + ke; }
+    }
+    const HostWeight &w = e->hw.at(n2);
+    h.insert(h.end(), w.k.begin(), w.k.end());
+    h.insert(h.end(), w.b.begin(), w.b.end());
+    off += ke + be;
+  }
+  tr->P = off;
+  tr->theta.ensure(off * 4); tr->grad.ensure(off * 4); tr->m.ensure(off * 4); tr->v.ensure(off * 4);
+  ADP_CUDA(cudaMemcpy(tr->theta.p, h.data(), off * 4, cudaMemcpyHostToDevice));
+  ADP_CUDA(cudaMemset(tr->grad.p, 0, off * 4));
+  ADP_CUDA(cudaMemset(tr->m.p, 0, off * 4));
+  ADP_CUDA(cudaMemset(tr->v.p, 0, off * 4));
+  for (size_t i = 0; i < e->layers.size(); ++i) {
+    const ConvLayer &L = e->layers[i];
+    const size_t np = (size_t)9 * L.cin_pad * L.cout_pad;
+    tr->tl[i].wT.ensure(np * 4); tr->tl[i].gw.ensure(np * 4); tr->tl[i].gb.ensure((size_t)L.cout_pad * 4);
+    ADP_CUDA(cudaMemset(tr->tl[i].wT.p, 0, np * 4));
+  }
+  tr->gw_first.ensure((size_t)9 * cp[0] * 4); tr->gb_first.ensure((size_t)cp[0] * 4); tr->g_head.ensure((size_t)(cp[0] + 1) * 8);
+  delete e->tr;
+  e->tr = tr.release();
+  repack_from_theta(e);
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+}
+
+// ---- forward -----------------------------------------------------------------------------------
+void train_forward(adp_engine *e, const float *x, const float *y, int n, const uint8_t *const *masks, double sums[6]) {
+  TrainState *tr = e->tr;
+  if (!tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
+  ADP_REQUIRE(n == tr->nb, "batch size differs from adp_train_begin");
+  const int S = tr->S;
+  const size_t npx = (size_t)n * S * S;
+  ADP_CUDA(cudaMemcpyAsync(tr->x.p, x, npx * 4, cudaMemcpyDefault, e->stream));
+  ADP_CUDA(cudaMemcpyAsync(tr->y.p, y, npx * 4, cudaMemcpyDefault, e->stream));
+  DropSpec d;
+  d.keep = tr->keep;
+  d.seed = tr->seed + 0xD1B54A32D192ED03ULL * (uint64_t)(tr->iter + 1);
+  if (masks) {
+    const int Hs[4] = {S / 8, S / 4, S / 2, S};
+    const int cr[4] = {e->c[3], e->c[2], e->c[1], e->c[0]};
+    for (int i = 0; i < 4; ++i) {
+      ADP_REQUIRE(masks[i], "all four dropout masks must be given");
+      const size_t bytes = (size_t)n * Hs[i] * Hs[i] * cr[i];
+      d.mask[i] = reinterpret_cast<const uint8_t *>(to_device(e, tr->mask_stage[i], masks[i], bytes));
+    }
+    if (d.keep >= 1.f) d.keep = 0.7f;      // supplied masks imply the reference's Dropout(0.3)
+    tr->keep = d.keep;
+  }
+  FwTable fw;
+  memset(&fw, 0, sizeof(fw));
+  for (int i = 0; i < n; ++i) { fw.tile[i] = i; fw.op[i] = 0; }
+  FirstConvSrc src{};
+  src.f32 = tr->x.as<float>();
+  const bool dropping = masks || tr->keep < 1.f;
+  DropSpec none;   // keep == 1, no masks: the dropout kernels are skipped but the fused head is still off
+  if (e->prec == ADP_PREC_FP32) forward_t<float>(e, tr->acts, S, src, fw, n, 0.f, 1.f, nullptr, dropping ? &d : &none);
+  else forward_t<__nv_bfloat16>(e, tr->acts, S, src, fw, n, 0.f, 1.f, nullptr, dropping ? &d : &none);
+  ADP_CUDA(cudaMemsetAsync(tr->sums.p, 0, 64, e->stream));
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>(cdiv64(npx, 256 * 4), (size_t)e->num_sms * 8));
+  e->launch("loss_reduce", 0, (double)npx * 8, [&] {
+    loss_reduce_kernel<<<grid, 256, 0, e->stream>>>(tr->prob.as<float>(), tr->y.as<float>(), npx, tr->sums.as<double>());
+  });
+  ADP_CUDA(cudaMemcpyAsync(sums, tr->sums.p, 48, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  tr->have_forward = true; tr->have_grads = false;
+}
+
+void loss_from_sums(const double s[6], double n_px, double out[4]) {
+  const double bce = s[0] / n_px;
+  const double denom = s[2] + s[3] + 1.0;
+  const double dice_loss = 1.0 - (2.0 * s[1] + 1.0) / denom;
+  out[0] = bce + dice_loss; out[1] = bce; out[2] = dice_loss;
+  out[3] = (2.0 * s[4] + 1.0) / (s[2] + s[5] + 1.0);
+}
+
+// ---- backward ----------------------------------------------------------------------------------
+template <typename T> struct Bwd {
+  adp_engine *e;
+  TrainState *tr;
+  int nb;
+
+  View<T> V(const DevBuf &b, int H, int pitch, int coff, int C) { return view<T>(b, H, H, pitch, coff, C); }
+
+  void relu_mask(View<T> g, View<T> x, float scale) {
+    const size_t total = (size_t)nb * g.H * g.W * (g.C / 8);
+    e->launch("relu_mask_bwd", 0, (double)total * 8 * sizeof(T) * 3, [&] {
+      relu_mask_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(g, x, nb, scale);
+    });
+  }
+  void add(View<T> dst, View<T> a, View<T> b) {
+    const size_t total = (size_t)nb * dst.H * dst.W * (dst.C / 8);
+    e->launch("grad_add", 0, (double)total * 8 * sizeof(T) * 3, [&] {
+      add_views_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(dst, a, b, nb);
+    });
+  }
+  void pool_bwd(View<T> xin, View<T> gout, View<T> gin) {
+    const size_t total = (size_t)nb * gout.H * gout.W * (gout.C / 8);
+    e->launch("maxpool2x2_bwd", 0, (double)total * 8 * sizeof(T) * 13, [&] {
+      maxpool2_bwd_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(xin, gout, gin, nb);
+    });
+  }
+
+  // weight + bias gradient of layer li: xin = the conv's input (low-res source for an upsampled conv), dz = dL/d(pre-activation)
+  void wgrad(size_t li, View<T> xin, View<T> dz) {
+    ConvLayer &L = e->layers[li];
+    TrainLayer &TL = tr->tl[li];
+    const size_t np = (size_t)9 * L.cin_pad * L.cout_pad;
+    ADP_CUDA(cudaMemsetAsync(TL.gw.p, 0, np * 4, e->stream));
+    ADP_CUDA(cudaMemsetAsync(TL.gb.p, 0, (size_t)L.cout_pad * 4, e->stream));
+    const int ci_tiles = cdiv(L.cin_pad, 64), co_tiles = cdiv(L.cout_pad, 64);
+    const long long nchunks = (long long)nb * dz.H * cdiv(dz.W, 32);
+    const int splits = (int)std::max<long long>(1, std::min<long long>(nchunks, std::max(8, e->num_sms * 8 / (9 * ci_tiles * co_tiles))));
+    dim3 grid(9, ci_tiles * co_tiles, splits);
+    const double fl = conv_flops(L, dz.H, dz.W, nb);
+    e->launch(("conv_wgrad_simt/" + L.name).c_str(), fl, 0, [&] {
+      if (L.up) conv_wgrad_kernel<T, true><<<grid, 256, 0, e->stream>>>(xin, dz, TL.gw.as<float>(), TL.gb.as<float>(), L.dil, nb, L.cin_pad, L.cout_pad, co_tiles);
+      else conv_wgrad_kernel<T, false><<<grid, 256, 0, e->stream>>>(xin, dz, TL.gw.as<float>(), TL.gb.as<float>(), L.dil, nb, L.cin_pad, L.cout_pad, co_tiles);
+    });
+    const size_t ne = (size_t)9 * L.cin * L.cout;
+    const int sp = L.skip ? pad16(L.skip) : 0;
+    e->launch("grad_unpad", 0, (double)ne * 8, [&] {
+      pad_kernel_weights<<<ew_grid(e, ne), 256, 0, e->stream>>>(tr->grad.as<float>() + TL.koff, TL.gw.as<float>(), 9, L.cin, L.cout, L.cin_pad,
+                                                               L.cout_pad, L.skip, sp, 1, 0);
+    });
+    ADP_CUDA(cudaMemcpyAsync(tr->grad.as<float>() + TL.boff, TL.gb.p, (size_t)L.cout * 4, cudaMemcpyDeviceToDevice, e->stream));
+  }
+
+  // data gradient of layer li: dz (output resolution) -> gin (input resolution)
+  void dgrad(size_t li, View<T> dz, View<T> gin) {
+    ConvLayer &L = e->layers[li];
+    TrainLayer &TL = tr->tl[li];
+    View<T> out = gin;
+    if (L.up) out = V(tr->g_hi, dz.H, L.cin_pad, 0, L.cin_pad);
+    dim3 grid(cdiv(dz.W, 32), cdiv(dz.H, 8), nb * (L.cin_pad / 16)), block(32, 8);
+    const double fl = conv_flops(L, dz.H, dz.W, nb);
+    e->launch(("conv_dgrad_simt/" + L.name).c_str(), fl, 0, [&] {
+      conv3x3_simt_kernel<T, false><<<grid, block, 0, e->stream>>>(dz, out, TL.wT.as<float>(), tr->zeros.as<float>(), L.dil, 0);
+    });
+    if (L.up) {
+      const size_t total = (size_t)nb * gin.H * gin.W * (gin.C / 8);
+      e->launch("upsample2x2_bwd", 0, (double)total * 8 * sizeof(T) * 5, [&] {
+        upsample2_bwd_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(out, gin, nb);
+      });
+    }
+  }
+};
+
+size_t layer_index(adp_engine *e, const char *n) {
+  for (size_t i = 0; i < e->layers.size(); ++i)
+    if (e->layers[i].name == n) return i;
+  throw Error(ADP_EINVAL, std::string("unknown layer ") + n);
+}
+
+template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
+  TrainState *tr = e->tr;
+  Bwd<T> B{e, tr, tr->nb};
+  const int nb = tr->nb, S = tr->S, S2 = S / 2, S3 = S / 4, S4 = S / 8;
+  const int *cp = e->cp;
+  const float inv_keep = 1.f / tr->keep;
+  auto li = [&](const char *n) { return layer_index(e, n); };
+
+  // head: dL/dp -> dL/d(up1_conv3 post-dropout output), head weight gradients
+  {
+    auto x = B.V(tr->u1c, S, cp[0], 0, cp[0]);
+    auto g = B.V(tr->g_u1c, S, cp[0], 0, cp[0]);
+    ADP_CUDA(cudaMemsetAsync(tr->g_head.p, 0, (size_t)(cp[0] + 1) * 8, e->stream));
+    const size_t total = (size_t)nb * S * S;
+    e->launch("head_bwd", 0, (double)total * (8 + 2.0 * cp[0] * sizeof(T)), [&] {
+      head_bwd_kernel<T><<<(int)cdiv64(total, 256), 256, (size_t)(2 * cp[0] + 1) * 4, e->stream>>>(
+          x, nb, e->w_head.as<float>(), tr->prob.as<float>(), tr->dldp.as<float>(), g, tr->g_head.as<double>(), tr->g_head.as<double>() + cp[0]);
+    });
+    e->launch("head_grad_finish", 0, 0, [&] {
+      head_grad_finish_kernel<<<1, 256, 0, e->stream>>>(tr->g_head.as<double>(), e->c[0], cp[0], tr->grad.as<float>() + tr->koff_head,
+                                                       tr->grad.as<float>() + tr->boff_head);
+    });
+    B.relu_mask(g, x, inv_keep);
+  }
+  // decoder level 1
+  B.wgrad(li("up1_conv3"), B.V(tr->u1b, S, cp[0], 0, cp[0]), B.V(tr->g_u1c, S, cp[0], 0, cp[0]));
+  B.dgrad(li("up1_conv3"), B.V(tr->g_u1c, S, cp[0], 0, cp[0]), B.V(tr->g_u1b, S, cp[0], 0, cp[0]));
+  B.relu_mask(B.V(tr->g_u1b, S, cp[0], 0, cp[0]), B.V(tr->u1b, S, cp[0], 0, cp[0]), 1.f);
+  B.wgrad(li("up1_conv2"), B.V(tr->cat1, S, 2 * cp[0], 0, 2 * cp[0]), B.V(tr->g_u1b, S, cp[0], 0, cp[0]));
+  B.dgrad(li("up1_conv2"), B.V(tr->g_u1b, S, cp[0], 0, cp[0]), B.V(tr->g_cat1, S, 2 * cp[0], 0, 2 * cp[0]));
+  B.relu_mask(B.V(tr->g_cat1, S, 2 * cp[0], cp[0], cp[0]), B.V(tr->cat1, S, 2 * cp[0], cp[0], cp[0]), 1.f);
+  B.wgrad(li("up1_conv1"), B.V(tr->u2c, S2, cp[1], 0, cp[1]), B.V(tr->g_cat1, S, 2 * cp[0], cp[0], cp[0]));
+  B.dgrad(li("up1_conv1"), B.V(tr->g_cat1, S, 2 * cp[0], cp[0], cp[0]), B.V(tr->g_u2c, S2, cp[1], 0, cp[1]));
+  B.relu_mask(B.V(tr->g_u2c, S2, cp[1], 0, cp[1]), B.V(tr->u2c, S2, cp[1], 0, cp[1]), inv_keep);
+  // decoder level 2
+  B.wgrad(li("up2_conv3"), B.V(tr->u2b, S2, cp[1], 0, cp[1]), B.V(tr->g_u2c, S2, cp[1], 0, cp[1]));
+  B.dgrad(li("up2_conv3"), B.V(tr->g_u2c, S2, cp[1], 0, cp[1]), B.V(tr->g_u2b, S2, cp[1], 0, cp[1]));
+  B.relu_mask(B.V(tr->g_u2b, S2, cp[1], 0, cp[1]), B.V(tr->u2b, S2, cp[1], 0, cp[1]), 1.f);
+  B.wgrad(li("up2_conv2"), B.V(tr->cat2, S2, 2 * cp[1], 0, 2 * cp[1]), B.V(tr->g_u2b, S2, cp[1], 0, cp[1]));
+  B.dgrad(li("up2_conv2"), B.V(tr->g_u2b, S2, cp[1], 0, cp[1]), B.V(tr->g_cat2, S2, 2 * cp[1], 0, 2 * cp[1]));
+  B.relu_mask(B.V(tr->g_cat2, S2, 2 * cp[1], cp[1], cp[1]), B.V(tr->cat2, S2, 2 * cp[1], cp[1], cp[1]), 1.f);
+  B.wgrad(li("up2_conv1"), B.V(tr->u3c, S3, cp[2], 0, cp[2]), B.V(tr->g_cat2, S2, 2 * cp[1], cp[1], cp[1]));
+  B.dgrad(li("up2_conv1"), B.V(tr->g_cat2, S2, 2 * cp[1], cp[1], cp[1]), B.V(tr->g_u3c, S3, cp[2], 0, cp[2]));
+  B.relu_mask(B.V(tr->g_u3c, S3, cp[2], 0, cp[2]), B.V(tr->u3c, S3, cp[2], 0, cp[2]), inv_keep);
+  // decoder level 3
+  B.wgrad(li("up3_conv3"), B.V(tr->u3b, S3, cp[2], 0, cp[2]), B.V(tr->g_u3c, S3, cp[2], 0, cp[2]));
+  B.dgrad(li("up3_conv3"), B.V(tr->g_u3c, S3, cp[2], 0, cp[2]), B.V(tr->g_u3b, S3, cp[2], 0, cp[2]));
+  B.relu_mask(B.V(tr->g_u3b, S3, cp[2], 0, cp[2]), B.V(tr->u3b, S3, cp[2], 0, cp[2]), 1.f);
+  B.wgrad(li("up3_conv2"), B.V(tr->cat3, S3, 2 * cp[2], 0, 2 * cp[2]), B.V(tr->g_u3b, S3, cp[2], 0, cp[2]));
+  B.dgrad(li("up3_conv2"), B.V(tr->g_u3b, S3, cp[2], 0, cp[2]), B.V(tr->g_cat3, S3, 2 * cp[2], 0, 2 * cp[2]));
+  B.relu_mask(B.V(tr->g_cat3, S3, 2 * cp[2], cp[2], cp[2]), B.V(tr->cat3, S3, 2 * cp[2], cp[2], cp[2]), 1.f);
+  B.wgrad(li("up3_conv1"), B.V(tr->ts, S4, cp[3], 0, cp[3]), B.V(tr->g_cat3, S3, 2 * cp[2], cp[2], cp[2]));
+  B.dgrad(li("up3_conv1"), B.V(tr->g_cat3, S3, 2 * cp[2], cp[2], cp[2]), B.V(tr->g_ts, S4, cp[3], 0, cp[3]));
+  // bottleneck: Add fans the gradient out to the six dilate outputs; the chain adds the downstream conv's data gradient
+  const char *dn[6] = {"dilate1", "dilate2", "dilate3", "dilate4", "dilate5", "dilate6"};
+  auto VT = [&](const DevBuf &b) { return B.V(b, S4, cp[3], 0, cp[3]); };
+  ADP_CUDA(cudaMemcpyAsync(tr->gt[1].p, tr->g_ts.p, (size_t)nb * S4 * S4 * cp[3] * sizeof(T), cudaMemcpyDeviceToDevice, e->stream));
+  int cur = 1;     // gt[cur] = dL/d t[i]
+  for (int i = 5; i >= 1; --i) {
+    B.relu_mask(VT(tr->gt[cur]), VT(tr->t[i]), 1.f);
+    B.wgrad(li(dn[i]), VT(tr->t[i - 1]), VT(tr->gt[cur]));
+    B.dgrad(li(dn[i]), VT(tr->gt[cur]), VT(tr->gt[cur ^ 1]));
+    B.add(VT(tr->gt[cur ^ 1]), VT(tr->gt[cur ^ 1]), VT(tr->g_ts));
+    cur ^= 1;
+  }
+  B.relu_mask(VT(tr->gt[cur]), VT(tr->t[0]), inv_keep);
+  B.wgrad(li("dilate1"), B.V(tr->pl3, S4, cp[2], 0, cp[2]), VT(tr->gt[cur]));
+  if (freeze_encoder) return;     // phase 1: nothing upstream is trainable (train_adipose_unet_v3.py:760-769)
+  B.dgrad(li("dilate1"), VT(tr->gt[cur]), B.V(tr->g_pl3, S4, cp[2], 0, cp[2]));
+  // encoder level 3
+  B.pool_bwd(B.V(tr->cat3, S3, 2 * cp[2], 0, cp[2]), B.V(tr->g_pl3, S4, cp[2], 0, cp[2]), B.V(tr->g_cat3, S3, 2 * cp[2], 0, cp[2]));
+  B.relu_mask(B.V(tr->g_cat3, S3, 2 * cp[2], 0, cp[2]), B.V(tr->cat3, S3, 2 * cp[2], 0, cp[2]), 1.f);
+  B.wgrad(li("down3_conv2"), B.V(tr->d3a, S3, cp[2], 0, cp[2]), B.V(tr->g_cat3, S3, 2 * cp[2], 0, cp[2]));
+  B.dgrad(li("down3_conv2"), B.V(tr->g_cat3, S3, 2 * cp[2], 0, cp[2]), B.V(tr->g_d3a, S3, cp[2], 0, cp[2]));
+  B.relu_mask(B.V(tr->g_d3a, S3, cp[2], 0, cp[2]), B.V(tr->d3a, S3, cp[2], 0, cp[2]), 1.f);
+  B.wgrad(li("down3_conv1"), B.V(tr->pl2, S3, cp[1], 0, cp[1]), B.V(tr->g_d3a, S3, cp[2], 0, cp[2]));
+  B.dgrad(li("down3_conv1"), B.V(tr->g_d3a, S3, cp[2], 0, cp[2]), B.V(tr->g_pl2, S3, cp[1], 0, cp[1]));
+  // encoder level 2
+  B.pool_bwd(B.V(tr->cat2, S2, 2 * cp[1], 0, cp[1]), B.V(tr->g_pl2, S3, cp[1], 0, cp[1]), B.V(tr->g_cat2, S2, 2 * cp[1], 0, cp[1]));
+  B.relu_mask(B.V(tr->g_cat2, S2, 2 * cp[1], 0, cp[1]), B.V(tr->cat2, S2, 2 * cp[1], 0, cp[1]), 1.f);
+  B.wgrad(li("down2_conv2"), B.V(tr->d2a, S2, cp[1], 0, cp[1]), B.V(tr->g_cat2, S2, 2 * cp[1], 0, cp[1]));
+  B.dgrad(li("down2_conv2"), B.V(tr->g_cat2, S2, 2 * cp[1], 0, cp[1]), B.V(tr->g_d2a, S2, cp[1], 0, cp[1]));
+  B.relu_mask(B.V(tr->g_d2a, S2, cp[1], 0, cp[1]), B.V(tr->d2a, S2, cp[1], 0, cp[1]), 1.f);
+  B.wgrad(li("down2_conv1"), B.V(tr->pl1, S2, cp[0], 0, cp[0]), B.V(tr->g_d2a, S2, cp[1], 0, cp[1]));
+  B.dgrad(li("down2_conv1"), B.V(tr->g_d2a, S2, cp[1], 0, cp[1]), B.V(tr->g_pl1, S2, cp[0], 0, cp[0]));
+  // encoder level 1
+  B.pool_bwd(B.V(tr->cat1, S, 2 * cp[0], 0, cp[0]), B.V(tr->g_pl1, S2, cp[0], 0, cp[0]), B.V(tr->g_cat1, S, 2 * cp[0], 0, cp[0]));
+  B.relu_mask(B.V(tr->g_cat1, S, 2 * cp[0], 0, cp[0]), B.V(tr->cat1, S, 2 * cp[0], 0, cp[0]), 1.f);
+  B.wgrad(li("down1_conv2"), B.V(tr->d1a, S, cp[0], 0, cp[0]), B.V(tr->g_cat1, S, 2 * cp[0], 0, cp[0]));
+  B.dgrad(li("down1_conv2"), B.V(tr->g_cat1, S, 2 * cp[0], 0, cp[0]), B.V(tr->g_d1a, S, cp[0], 0, cp[0]));
+  B.relu_mask(B.V(tr->g_d1a, S, cp[0], 0, cp[0]), B.V(tr->d1a, S, cp[0], 0, cp[0]), 1.f);
+  // first conv (Cin = 1): weight gradient only
+  {
+    ADP_CUDA(cudaMemsetAsync(tr->gw_first.p, 0, (size_t)9 * cp[0] * 4, e->stream));
+    ADP_CUDA(cudaMemsetAsync(tr->gb_first.p, 0, (size_t)cp[0] * 4, e->stream));
+    const size_t total = (size_t)nb * S * S;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 4));
+    e->launch("first_conv_wgrad", 2.0 * total * 9 * e->c[0], (double)total * (4 + cp[0] * sizeof(T)), [&] {
+      first_wgrad_kernel<T><<<grid, 256, (size_t)10 * cp[0] * 4, e->stream>>>(tr->x.as<float>(), B.V(tr->g_d1a, S, cp[0], 0, cp[0]), nb,
+                                                                              tr->gw_first.as<float>(), tr->gb_first.as<float>());
+    });
+    e->launch("grad_unpad", 0, 0, [&] {
+      pad_kernel_weights<<<ew_grid(e, 9 * e->c[0]), 256, 0, e->stream>>>(tr->grad.as<float>() + tr->koff_first, tr->gw_first.as<float>(), 9, 1,
+                                                                         e->c[0], 1, cp[0], 0, 0, 1, 0);
+    });
+    ADP_CUDA(cudaMemcpyAsync(tr->grad.as<float>() + tr->boff_first, tr->gb_first.p, (size_t)e->c[0] * 4, cudaMemcpyDeviceToDevice, e->stream));
+  }
+}
+
+void train_backward(adp_engine *e, const double sums[6], int64_t n_px_global, bool freeze_encoder) {
+  TrainState *tr = e->tr;
+  if (!tr || !tr->have_forward) throw Error(ADP_ESTATE, "adp_train_forward must run first");
+  const size_t npx = (size_t)tr->nb * tr->S * tr->S;
+  const double N = n_px_global > 0 ? (double)n_px_global : (double)npx;
+  const double denom = sums[2] + sums[3] + 1.0;
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>(cdiv64(npx, 256 * 4), (size_t)e->num_sms * 8));
+  e->launch("loss_grad", 0, (double)npx * 12, [&] {
+    loss_grad_kernel<<<grid, 256, 0, e->stream>>>(tr->prob.as<float>(), tr->y.as<float>(), npx, (float)(1.0 / N), (float)(2.0 * sums[1] + 1.0),
+                                                  (float)denom, tr->dldp.as<float>());
+  });
+  if (freeze_encoder) {   // frozen tensors report zero gradient
+    const size_t first_trainable = tr->tl[layer_index(e, "dilate1")].koff;
+    ADP_CUDA(cudaMemsetAsync(tr->grad.p, 0, first_trainable * 4, e->stream));
+  }
+  if (e->prec == ADP_PREC_FP32) backward_t<float>(e, freeze_encoder);
+  else backward_t<__nv_bfloat16>(e, freeze_encoder);
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  tr->have_grads = true;
+}
+
+// Keras Adam / AdamW (train_adipose_unet_v3.py:801-806; epsilon outside the bias correction)
+void train_apply(adp_engine *e, int optimizer, float lr, float grad_scale, double beta1, double beta2, float eps, float weight_decay,
+                 bool freeze_encoder) {
+  TrainState *tr = e->tr;
+  if (!tr || !tr->have_grads) throw Error(ADP_ESTATE, "adp_train_backward must run first");
+  const int64_t t = tr->iter + 1;
+  // alpha in float32 like Keras: lr * sqrt(1 - b2^t) / (1 - b1^t)
+  const float b1p = powf((float)beta1, (float)t), b2p = powf((float)beta2, (float)t);
+  const float alpha = lr * sqrtf(1.f - b2p) / (1.f - b1p);
+  const size_t first = freeze_encoder ? tr->tl[layer_index(e, "dilate1")].koff : 0;
+  const size_t n = tr->P - first;
+  const float wd = optimizer == ADP_OPT_ADAMW ? weight_decay : 0.f;
+  e->launch("adam_update", 0, (double)n * 28, [&] {
+    adam_kernel<<<ew_grid(e, n), 256, 0, e->stream>>>(tr->theta.as<float>() + first, tr->grad.as<float>() + first, tr->m.as<float>() + first,
+                                                      tr->v.as<float>() + first, n, grad_scale, alpha, (float)(1.0 - beta1), (float)(1.0 - beta2), eps, wd, lr);
+  });
+  tr->iter = t;
+  tr->host_stale = true;
+  repack_from_theta(e);
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  tr->have_grads = false; tr->have_forward = false;
+}
+
+}  // namespace

@@ -169,6 +169,47 @@ int adp_wsi_end(adp_engine *e);
  * out = {loss, bce_mean, dice_loss, dice_coef}. */
 int adp_loss_metrics(adp_engine *e, const float *p, const float *y, int64_t n_px, float *dldp, double out[4]);
 
+/* ---- training step -----------------------------------------------------------------------------
+ * Replaces Keras train_step as driven by net.fit (train_adipose_unet_v3.py:1316-1324, 1413-1421):
+ * forward with Dropout(0.3) at the four sites (:682,696,703,710), combined_loss_standard (:228-241),
+ * reverse-mode differentiation of the graph, Adam / AdamW update (:801-806).
+ * The engine keeps theta, the flat gradient, the Adam moments and all activations on the device
+ * between adp_train_begin and adp_train_end; adp_get_weight returns the current parameters.
+ * x: batch*size*size float32 already normalised (the reference normalises on the host, :589-595),
+ * y: batch*size*size float32 targets in [0,1].  Host or device pointers.
+ *
+ * A step is forward -> backward -> apply so that a data-parallel caller can (a) sum the six loss
+ * sums over ranks before backward (exact whole-batch Dice) and (b) all-reduce the flat
+ * gradient (adp_train_grad_buffer) before apply.  adp_train_step chains the three for one GPU. */
+#define ADP_OPT_ADAM 0
+#define ADP_OPT_ADAMW 1
+int adp_train_begin(adp_engine *e, int batch, int size, float dropout_rate, uint64_t seed);
+/* dropout_masks: NULL (masks drawn from the engine's counter-based generator when dropout_rate > 0) or four
+ * uint8 0/1 arrays in NHWC with the real channel counts, sites in graph order
+ * {dilate1 (size/8, 8*init_nb), up3 (size/4, 4*init_nb), up2 (size/2, 2*init_nb), up1 (size, init_nb)}.
+ * sums = {sum bce, sum y*pc, sum y, sum pc, sum y*p, sum p} over this batch (pc = clip(p,1e-7,1-1e-7)). */
+int adp_train_forward(adp_engine *e, const float *x, const float *y, int batch, const uint8_t *const *dropout_masks,
+                      double sums[6]);
+/* loss = {loss, bce_mean, dice_loss, dice_coef} from (possibly rank-summed) sums over n_px pixels */
+int adp_train_loss(const double sums[6], int64_t n_px, double out[4]);
+/* sums / n_px_global: the values the loss is defined over (own batch, or summed over data-parallel ranks);
+ * freeze_encoder != 0 = phase 1 of the reference (down*_conv* frozen, :760-769): their gradients are zero */
+int adp_train_backward(adp_engine *e, const double sums[6], int64_t n_px_global, int freeze_encoder);
+/* device pointer + element count of the flat fp32 gradient (Keras order: per layer kernel HWIO, bias) */
+int adp_train_grad_buffer(adp_engine *e, float **dev_ptr, int64_t *count);
+int adp_train_get_grad(adp_engine *e, const char *layer, float *kernel_hwio, int64_t kernel_elems, float *bias, int64_t nbias);
+int adp_train_probs(adp_engine *e, float *out, int64_t out_elems);          /* probabilities of the last forward */
+/* theta <- optimizer(theta, grad_scale * grad); Keras epsilon placement; beta1/beta2/eps <= 0 select 0.9/0.999/1e-7 */
+int adp_train_apply(adp_engine *e, int optimizer, float lr, float grad_scale, double beta1, double beta2, float eps,
+                    float weight_decay, int freeze_encoder);
+int adp_train_step(adp_engine *e, const float *x, const float *y, int batch, int optimizer, float lr, float weight_decay,
+                   int freeze_encoder, double out[4]);
+int64_t adp_train_iterations(adp_engine *e);
+int adp_train_end(adp_engine *e);
+/* one optimizer update on caller-owned arrays (unit-test entry of the update rule): t is 1-based */
+int adp_adam_update(adp_engine *e, float *theta, const float *grad, float *m, float *v, int64_t n, int64_t t, int optimizer,
+                    float lr, double beta1, double beta2, float eps, float weight_decay);
+
 /* ---- profiling ---------------------------------------------------------------------------------
  * When enabled, every kernel launch is bracketed by CUDA events on the engine stream and
  * accumulated per kernel kind.  adp_profile_read returns up to `cap` rows
