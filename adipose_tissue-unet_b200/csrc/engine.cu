@@ -20,6 +20,7 @@
 #include "kernels_post.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_train.cuh"
+#include "wgrad_tc.cuh"
 
 using namespace adp;
 
@@ -147,6 +148,7 @@ struct adp_engine {
   int64_t launches = 0;
   int dbg = 0;
   bool fuse_head = true, fuse_pool = true;   // tcgen05 path only
+  bool wgrad_simt = false, dgrad_simt = false;   // bf16 training: CUDA-core cross-check of the tcgen05 backward kernels
 
   template <typename F> void launch(const char *kind, double flops, double bytes, F &&f) {
     if (prof) ADP_CUDA(cudaEventRecord(ev0, stream));
@@ -419,27 +421,26 @@ template <typename T> View<T> view(const DevBuf &b, int H, int W, int pitch, int
   return v;
 }
 
-const CUtensorMap &get_tmap(adp_engine *e, const ConvLayer &L, const DevBuf &src, int H, int W, int pitch, int coff,
-                            int C, int cap) {
-  const std::string key = L.name + "@" + std::to_string((uintptr_t)src.p) + "/" + std::to_string(coff) + "/" + std::to_string(H);
+// Tensor map over a row-planar view [n][y][cg][x][8] (bf16): dim0 = 8 pixels x 8 channels (one 128-byte line),
+// dim1 = 8-pixel groups along the row, dim2 = channel group, dim3 = row, dim4 = image.  Box = (64, box_px8,
+// box_cg, box_rows, 1); everything outside the view (borders, channel tail) is zero-filled by the TMA unit.
+const CUtensorMap &tmap_for(adp_engine *e, const void *buf, int H, int W, int cgs, int cg0, int C, int cap, int box_px8,
+                            int box_cg, int box_rows) {
+  char key[160];
+  snprintf(key, sizeof(key), "%p/%d/%d/%d/%d/%d/%d/%d/%d/%d", buf, H, W, cgs, cg0, C, cap, box_px8, box_cg, box_rows);
   auto it = e->tmaps.find(key);
   if (it != e->tmaps.end()) return it->second;
-  const ConvTcParams &p = L.tc;
   CUtensorMap m;
   ADP_REQUIRE(W % 8 == 0, "tcgen05 conv path needs every level's width to be a multiple of 8 (tile size % 64 == 0)");
-  // row-planar source [n][y][cg][x][8]: dim0 = 8 pixels x 8 channels (one 128-byte line), dim1 = 8-pixel
-  // groups along the row, dim2 = channel group, dim3 = row, dim4 = image
   cuuint64_t gdim[5] = {64, (cuuint64_t)(W / 8), (cuuint64_t)(C / 8), (cuuint64_t)H, (cuuint64_t)cap};
-  const cuuint64_t cgs = pitch / 8;
-  cuuint64_t gstr[4] = {128, (cuuint64_t)W * 16, cgs * W * 16, (cuuint64_t)H * cgs * W * 16};
-  cuuint32_t box[5] = {64, (cuuint32_t)(p.PW / 8), 2, (cuuint32_t)p.BR, 1};
+  cuuint64_t gstr[4] = {128, (cuuint64_t)W * 16, (cuuint64_t)cgs * W * 16, (cuuint64_t)H * cgs * W * 16};
+  cuuint32_t box[5] = {64, (cuuint32_t)box_px8, (cuuint32_t)box_cg, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  void *base = (void *)(src.as<__nv_bfloat16>() + (size_t)(coff / 8) * W * 8);
+  void *base = (void *)(reinterpret_cast<const __nv_bfloat16 *>(buf) + (size_t)cg0 * W * 8);
   CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    throw Error(ADP_ECUDA, "cuTensorMapEncodeTiled failed for " + L.name + " code " + std::to_string((int)r));
+  if (r != CUDA_SUCCESS) throw Error(ADP_ECUDA, std::string("cuTensorMapEncodeTiled failed, code ") + std::to_string((int)r) + " key " + key);
   return e->tmaps.emplace(key, m).first->second;
 }
 
@@ -454,6 +455,34 @@ struct EpiSpec {
   float *prob = nullptr;              // EPI_HEAD: probability planes
 };
 
+// tcgen05 conv launch shared by the forward layers and their data-gradient twins (train_host.cuh)
+void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label, double fl, double by, const void *src, int Hs,
+                    int Ws, int s_cgs, int s_cg0, void *dst, int d_cgs, int d_cg0, int nb, int cap, const EpiSpec &epi,
+                    const float *bias, int relu) {
+  ConvTcParams p = L.tc;
+  const int Ho = L.up ? Hs * 2 : Hs, Wo = L.up ? Ws * 2 : Ws;
+  p.nb = nb; p.Hin = Hs; p.Win = Ws;
+  p.ntx = cdiv(Ws, 128); p.nty = cdiv(Hs, p.T);
+  p.wpk = L.w_tc.as<__nv_bfloat16>(); p.bias = bias;
+  p.out = reinterpret_cast<__nv_bfloat16 *>(dst); p.out_cgs = d_cgs; p.out_cg0 = d_cg0; p.Hout = Ho; p.Wout = Wo;
+  p.dbg = e->dbg;
+  p.relu = relu;
+  p.epi_mode = epi.mode;
+  if (epi.mode == EPI_HEAD) {
+    ADP_REQUIRE(p.T >= 2 && p.nvar == 1 && p.N == e->cp[0], "head fusion needs the 44-channel full-resolution layer");
+    p.head_w = e->w_head.as<float>(); p.head_b = e->b_head.as<float>(); p.prob = epi.prob;
+  } else if (epi.mode == EPI_POOL) {
+    ADP_REQUIRE(p.T % 2 == 0 && p.oscale == 1 && Ho % 2 == 0 && Wo % 2 == 0, "pool fusion needs an even row block");
+    p.pool_out = epi.pool_dst->as<__nv_bfloat16>(); p.pool_cgs = L.cout_pad / 8; p.pool_cg0 = 0;
+  }
+  const CUtensorMap &tm = tmap_for(e, src, Hs, Ws, s_cgs, s_cg0, L.cin_pad, cap, p.PW / 8, 2, p.BR);
+  const int nitems = nb * p.nty * p.ntx * p.nvar;
+  const int grid = std::min(nitems, e->num_sms);
+  const size_t smem = tc_smem_bytes(p);
+  ConvTcKernel kern = tc_kernel_for(p.ntaps, p.T);
+  e->launch(label.c_str(), fl, by, [&] { kern<<<grid, kTcThreads, smem, e->stream>>>(tm, p); });
+}
+
 void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs, int Ws, int spitch, int scoff,
               const DevBuf &dst, int dpitch, int dcoff, int nb, int cap, EpiSpec epi = EpiSpec()) {
   ConvLayer &L = layer(e, name);
@@ -461,28 +490,8 @@ void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs,
   const double fl = conv_flops(L, Ho, Wo, nb);
   const double by = (double)nb * ((double)Hs * Ws * L.cin_pad + (double)Ho * Wo * L.cout_pad) * e->esz;
   if (e->prec == ADP_PREC_BF16) {
-    ConvTcParams p = L.tc;
-    p.nb = nb; p.Hin = Hs; p.Win = Ws;
-    p.ntx = cdiv(Ws, 128); p.nty = cdiv(Hs, p.T);
-    p.wpk = L.w_tc.as<__nv_bfloat16>(); p.bias = L.bias.as<float>();
-    p.out = dst.as<__nv_bfloat16>(); p.out_cgs = dpitch / 8; p.out_cg0 = dcoff / 8; p.Hout = Ho; p.Wout = Wo;
-    p.dbg = e->dbg;
-    p.epi_mode = epi.mode;
-    if (epi.mode == EPI_HEAD) {
-      ADP_REQUIRE(p.T >= 2 && p.nvar == 1 && p.N == e->cp[0], "head fusion needs the 44-channel full-resolution layer");
-      p.head_w = e->w_head.as<float>(); p.head_b = e->b_head.as<float>(); p.prob = epi.prob;
-    } else if (epi.mode == EPI_POOL) {
-      ADP_REQUIRE(p.T % 2 == 0 && p.oscale == 1 && Ho % 2 == 0 && Wo % 2 == 0, "pool fusion needs an even row block");
-      p.pool_out = epi.pool_dst->as<__nv_bfloat16>(); p.pool_cgs = L.cout_pad / 8; p.pool_cg0 = 0;
-    }
-    const CUtensorMap &tm = get_tmap(e, L, src, Hs, Ws, spitch, scoff, L.cin_pad, cap);
-    const int nitems = nb * p.nty * p.ntx * p.nvar;
-    const int grid = std::min(nitems, e->num_sms);
-    const size_t smem = tc_smem_bytes(p);
-    ConvTcKernel kern = tc_kernel_for(p.ntaps, p.T);
-    e->launch(("conv3x3_tcgen05/" + name).c_str(), fl, by, [&] {
-      kern<<<grid, kTcThreads, smem, e->stream>>>(tm, p);
-    });
+    launch_conv_tc(e, L, "conv3x3_tcgen05/" + name, fl, by, src.p, Hs, Ws, spitch / 8, scoff / 8, dst.p, dpitch / 8, dcoff / 8, nb, cap,
+                   epi, L.bias.as<float>(), 1);
     return;
   }
   dim3 grid(cdiv(Wo, 32), cdiv(Ho, 8), nb * (L.cout_pad / 16));
@@ -800,6 +809,7 @@ int adp_create(int device, int precision, int init_nb, int max_forwards, adp_eng
   for (int nt : {9, 4})
     for (int T : {4, 2, 1})
       ADP_CUDA(cudaFuncSetAttribute(tc_kernel_for(nt, T), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  ADP_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (const char *d = getenv("ADP_TC_DEBUG")) e->dbg = atoi(d);
   build_layers(e.get());
   *out = e.release();
@@ -844,6 +854,8 @@ int adp_set_option(adp_engine *e, const char *key, int value) {
   std::string k = key;
   if (k == "fuse_head") e->fuse_head = value != 0;
   else if (k == "fuse_pool") e->fuse_pool = value != 0;
+  else if (k == "wgrad_simt") e->wgrad_simt = value != 0;
+  else if (k == "dgrad_simt") e->dgrad_simt = value != 0;
   else if (k == "debug") e->dbg = value;
   else throw Error(ADP_EINVAL, "unknown option " + k);
   ADP_CATCH

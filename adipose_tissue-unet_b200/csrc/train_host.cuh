@@ -16,7 +16,29 @@ struct TrainLayer {
   DevBuf wT;        // dgrad weights [9][cout_pad][cin_pad], taps flipped (fp32; bf16-rounded values off the fp32 path)
   DevBuf gw, gb;    // padded weight / bias gradients [9][cin_pad][cout_pad], [cout_pad]
   size_t koff = 0, boff = 0;   // offsets into the flat vectors
+  ConvLayer twin;   // tcgen05 path: the data gradient is the same conv kernel run on dZ with wT (cin <-> cout)
+  WgradTcParams wg{};
 };
+
+// plan of the tcgen05 weight-gradient kernel for one layer (wgrad_tc.cuh)
+void plan_wgrad_tc(adp_engine *e, const ConvLayer &L, WgradTcParams &p) {
+  memset(&p, 0, sizeof(p));
+  p.dil = L.dil; p.cin_pad = L.cin_pad; p.cout_pad = L.cout_pad;
+  p.co_chunk = std::min(48, L.cout_pad);
+  p.n_co_chunk = cdiv(L.cout_pad, p.co_chunk);
+  p.n_ci_blk = cdiv(L.cin_pad, 128);
+  p.cga_box = std::min(16, L.cin_pad / 8);
+  const int margin = (L.dil + 7) / 8 * 8;
+  p.margin8 = margin / 8; p.PW = 128 + 2 * margin;
+  p.a_bytes = (uint32_t)16 * p.PW * 16;                 // always 16 planes: an M = 128 operand spans 16 channel groups
+  p.b_row_bytes = (uint32_t)(p.co_chunk / 8) * 2048;
+  p.stage_stride = (p.a_bytes + 3 * p.b_row_bytes + 1023) / 1024 * 1024;
+  p.S = (int)std::min<size_t>(4, (size_t)(220 * 1024) / p.stage_stride);
+  ADP_REQUIRE(p.S >= 2, "wgrad stage does not fit shared memory twice");
+  const int ncombo = p.n_ci_blk * p.n_co_chunk;
+  p.ctas_per_combo = std::max(1, e->num_sms / ncombo);
+}
+size_t wgrad_smem_bytes(const WgradTcParams &p) { return (size_t)p.S * p.stage_stride + (2 * p.S + 1) * 8 + 16; }
 
 struct TrainState {
   int nb = 0, S = 0;
@@ -76,9 +98,13 @@ void repack_from_theta(adp_engine *e) {
     const int g = ew_grid(e, ne);
     pad_kernel_weights<<<g, 256, 0, e->stream>>>(th + T.koff, L.w_simt.as<float>(), 9, L.cin, L.cout, L.cin_pad, L.cout_pad, L.skip, sp, 0, 0);
     pad_kernel_weights<<<g, 256, 0, e->stream>>>(th + T.koff, T.wT.as<float>(), 9, L.cin, L.cout, L.cin_pad, L.cout_pad, L.skip, sp, 0, 1);
-    if (e->prec == ADP_PREC_BF16)   // pack from the unrounded padded copy (parity taps are summed in fp32)
+    if (e->prec == ADP_PREC_BF16) {  // pack from the unrounded padded copies (parity taps are summed in fp32)
       pack_tc_kernel<<<ew_grid(e, np * 2), 256, 0, e->stream>>>(L.w_simt.as<float>(), L.w_tc.as<__nv_bfloat16>(), L.tc.nvar, L.tc.nchunks,
                                                                L.tc.ntaps, L.tc.N, L.cin_pad, L.cout_pad, L.up ? 1 : 0);
+      const ConvLayer &W = T.twin;
+      pack_tc_kernel<<<ew_grid(e, np * 2), 256, 0, e->stream>>>(T.wT.as<float>(), W.w_tc.as<__nv_bfloat16>(), W.tc.nvar, W.tc.nchunks,
+                                                               W.tc.ntaps, W.tc.N, W.cin_pad, W.cout_pad, 0);
+    }
     if (bf) {
       round_bf16_kernel<<<ew_grid(e, np), 256, 0, e->stream>>>(L.w_simt.as<float>(), np);
       round_bf16_kernel<<<ew_grid(e, np), 256, 0, e->stream>>>(T.wT.as<float>(), np);
@@ -168,6 +194,15 @@ void train_alloc(adp_engine *e, int nb, int S, float dropout_rate, uint64_t seed
     const size_t np = (size_t)9 * L.cin_pad * L.cout_pad;
     tr->tl[i].wT.ensure(np * 4); tr->tl[i].gw.ensure(np * 4); tr->tl[i].gb.ensure((size_t)L.cout_pad * 4);
     ADP_CUDA(cudaMemset(tr->tl[i].wT.p, 0, np * 4));
+    if (e->prec == ADP_PREC_BF16) {
+      ConvLayer &W = tr->tl[i].twin;
+      W.name = "dgrad/" + L.name; W.cin = L.cout; W.cout = L.cin; W.dil = L.dil; W.up = false; W.skip = 0;
+      W.cin_pad = L.cout_pad; W.cout_pad = L.cin_pad;
+      plan_tc(W);
+      W.w_tc.ensure((size_t)W.tc.nvar * W.tc.nchunks * W.tc.ntaps * 16 * W.tc.N * 2);
+      W.tc_ready = true;
+      plan_wgrad_tc(e, L, tr->tl[i].wg);
+    }
   }
   tr->gw_first.ensure((size_t)9 * cp[0] * 4); tr->gb_first.ensure((size_t)cp[0] * 4); tr->g_head.ensure((size_t)(cp[0] + 1) * 8);
   delete e->tr;
@@ -260,15 +295,42 @@ template <typename T> struct Bwd {
     const size_t np = (size_t)9 * L.cin_pad * L.cout_pad;
     ADP_CUDA(cudaMemsetAsync(TL.gw.p, 0, np * 4, e->stream));
     ADP_CUDA(cudaMemsetAsync(TL.gb.p, 0, (size_t)L.cout_pad * 4, e->stream));
+    const double fl = conv_flops(L, dz.H, dz.W, nb);
+    if (e->prec == ADP_PREC_BF16 && !e->wgrad_simt) {
+      if constexpr (sizeof(T) == 2) {
+        View<T> xs = xin;
+        if (L.up) {     // materialise UpSampling2D(x) once: the weight gradient is then a plain 9-tap reduction at high resolution
+          xs = V(tr->g_hi, dz.H, L.cin_pad, 0, L.cin_pad);
+          const size_t total = (size_t)nb * xs.H * xs.W * (xs.C / 8);
+          e->launch("upsample2x2_materialise", 0, (double)total * 16 * 1.25, [&] {
+            upsample2_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(xin, xs, nb);
+          });
+        }
+        WgradTcParams p = TL.wg;
+        p.nb = nb; p.H = dz.H; p.W = dz.W; p.dW = TL.gw.as<float>();
+        const CUtensorMap &tmx = tmap_for(e, xs.p, xs.H, xs.W, xs.cgs, xs.cg0, xs.C, nb, p.PW / 8, p.cga_box, 1);
+        const CUtensorMap &tmz = tmap_for(e, dz.p, dz.H, dz.W, dz.cgs, dz.cg0, dz.C, nb, 16, p.co_chunk / 8, 1);
+        const int grid = p.n_ci_blk * p.n_co_chunk * p.ctas_per_combo;
+        const double by = (double)nb * dz.H * dz.W * (L.cin_pad + L.cout_pad) * 2.0;
+        e->launch(("conv_wgrad_tcgen05/" + L.name).c_str(), fl, by, [&] {
+          wgrad_tc_kernel<<<grid, kWgThreads, wgrad_smem_bytes(p), e->stream>>>(tmx, tmz, p);
+        });
+        const int G = dz.C / 8;
+        const int blocks = G * std::max(1, std::min(e->num_sms * 4 / G, (int)cdiv64((long long)nb * dz.H * cdiv(dz.W, 32), 8)));
+        e->launch("bias_grad", 0, (double)nb * dz.H * dz.W * dz.C * 2.0, [&] {
+          bias_grad_kernel<T><<<blocks, 256, (size_t)dz.C * 4, e->stream>>>(dz, nb, TL.gb.as<float>());
+        });
+      }
+    } else {
     const int ci_tiles = cdiv(L.cin_pad, 64), co_tiles = cdiv(L.cout_pad, 64);
     const long long nchunks = (long long)nb * dz.H * cdiv(dz.W, 32);
     const int splits = (int)std::max<long long>(1, std::min<long long>(nchunks, std::max(8, e->num_sms * 8 / (9 * ci_tiles * co_tiles))));
     dim3 grid(9, ci_tiles * co_tiles, splits);
-    const double fl = conv_flops(L, dz.H, dz.W, nb);
     e->launch(("conv_wgrad_simt/" + L.name).c_str(), fl, 0, [&] {
       if (L.up) conv_wgrad_kernel<T, true><<<grid, 256, 0, e->stream>>>(xin, dz, TL.gw.as<float>(), TL.gb.as<float>(), L.dil, nb, L.cin_pad, L.cout_pad, co_tiles);
       else conv_wgrad_kernel<T, false><<<grid, 256, 0, e->stream>>>(xin, dz, TL.gw.as<float>(), TL.gb.as<float>(), L.dil, nb, L.cin_pad, L.cout_pad, co_tiles);
     });
+    }
     const size_t ne = (size_t)9 * L.cin * L.cout;
     const int sp = L.skip ? pad16(L.skip) : 0;
     e->launch("grad_unpad", 0, (double)ne * 8, [&] {
@@ -286,9 +348,15 @@ template <typename T> struct Bwd {
     if (L.up) out = V(tr->g_hi, dz.H, L.cin_pad, 0, L.cin_pad);
     dim3 grid(cdiv(dz.W, 32), cdiv(dz.H, 8), nb * (L.cin_pad / 16)), block(32, 8);
     const double fl = conv_flops(L, dz.H, dz.W, nb);
-    e->launch(("conv_dgrad_simt/" + L.name).c_str(), fl, 0, [&] {
-      conv3x3_simt_kernel<T, false><<<grid, block, 0, e->stream>>>(dz, out, TL.wT.as<float>(), tr->zeros.as<float>(), L.dil, 0);
-    });
+    if (e->prec == ADP_PREC_BF16 && !e->dgrad_simt) {
+      const double by = (double)nb * dz.H * dz.W * (L.cin_pad + L.cout_pad) * 2.0;
+      launch_conv_tc(e, TL.twin, "conv_dgrad_tcgen05/" + L.name, fl, by, dz.p, dz.H, dz.W, dz.cgs, dz.cg0, out.p, out.cgs, out.cg0, nb, nb,
+                     EpiSpec(), tr->zeros.as<float>(), 0);
+    } else {
+      e->launch(("conv_dgrad_simt/" + L.name).c_str(), fl, 0, [&] {
+        conv3x3_simt_kernel<T, false><<<grid, block, 0, e->stream>>>(dz, out, TL.wT.as<float>(), tr->zeros.as<float>(), L.dil, 0);
+      });
+    }
     if (L.up) {
       const size_t total = (size_t)nb * gin.H * gin.W * (gin.C / 8);
       e->launch("upsample2x2_bwd", 0, (double)total * 8 * sizeof(T) * 5, [&] {

@@ -1,0 +1,215 @@
+// wgrad_tc.cuh — weight gradient of Conv2D(3x3, same, dilation d) as a tcgen05 GEMM whose reduction
+// dimension is the pixel axis (the K11 "wgrad" row of SURVEY.md section 2a; Keras computes it by
+// reverse-mode AD of train_adipose_unet_v3.py:668-709).
+//
+//   dW[ky][kx][ci][co] = sum_{n,y,x} X[n, y+(ky-1)d, x+(kx-1)d, ci] * dZ[n, y, x, co]
+//
+// Per X row y' the three vertical taps pair it with dZ rows y'+d, y', y'-d.  Both tensors are
+// row-planar ([row][channel group][pixel][8 channels]), so in shared memory
+//   * 8 channels x 8 pixels of X form one MN-major / SWIZZLE_NONE core matrix (8 pixel rows of 16 bytes):
+//     A = X^T tile [M = up to 128 input channels] x [K = 16 pixels], SBO = plane stride, LBO = 128 B;
+//     a horizontal tap is a start-address shift of 16 B per pixel;
+//   * the three dZ rows y'-d, y', y'+d of one output-channel chunk lie contiguously as [row][group] planes,
+//     i.e. ONE B operand with N = 3 x chunk columns: a single MMA produces the three vertical taps.
+// So a K step of 16 pixels is 3 MMAs (one per horizontal tap) of shape 128 x (3*chunk) x 16 into three
+// TMEM accumulators (3 x 144 = 432 of the 512 columns for chunk = 48).
+//
+// A CTA owns one (input-channel block, output-channel chunk) pair and a contiguous range of
+// (image, row, 128-pixel strip) units; it accumulates its whole range in TMEM and then adds the
+// 128 x 432 partial sums into the padded fp32 gradient dW[9][cin_pad][cout_pad] with red.global.add.
+//
+// Warp roles (192 threads): w0 TMA producer, w1 MMA issuer + TMEM allocator, w2-5 epilogue.
+#pragma once
+#include "ptx.cuh"
+
+namespace adp {
+
+struct WgradTcParams {
+  int nb, H, W;                  // images, spatial size (X and dZ have the same size)
+  int dil;
+  int cin_pad, cout_pad;
+  int n_ci_blk, n_co_chunk;      // 128-channel blocks of X, chunks of dZ channels
+  int co_chunk;                  // channels per chunk (multiple of 16, 3*co_chunk <= 170)
+  int ctas_per_combo;
+  int cga_box;                   // channel groups per X box = min(16, cin_pad / 8)
+  int PW, margin8;               // X plane width in pixels (128 + 2*margin), halo in 8-pixel groups
+  int S;                         // pipeline depth
+  uint32_t a_bytes, b_row_bytes, stage_stride;
+  float *dW;                     // [9][cin_pad][cout_pad] fp32, accumulated into
+};
+
+constexpr int kWgThreads = 192;
+
+ADP_DEVINL void red_add_f32(float *addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmz, const WgradTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.S * p.stage_stride);
+  uint64_t *full = bars, *empty = full + p.S, *acc_full = empty + p.S;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.S; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tmx);
+    ptx::prefetch_tmap(&tmz);
+  }
+  if (warp == 1) ptx::tmem_alloc_512(tmem_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // this CTA's combo and unit range
+  const int combo = blockIdx.x / p.ctas_per_combo, part = blockIdx.x % p.ctas_per_combo;
+  const int cib = combo / p.n_co_chunk, coc = combo % p.n_co_chunk;
+  const int ntx = (p.W + 127) / 128;
+  const long long nunits = (long long)p.nb * p.H * ntx;
+  const long long u0 = nunits * part / p.ctas_per_combo, u1 = nunits * (part + 1) / p.ctas_per_combo;
+  const int ci0 = cib * 128, co0 = coc * p.co_chunk;
+  // TMA boxes have a fixed shape: channel groups past the end of the tensor arrive as zeros and only cost MMA columns
+  const int ncga = p.cga_box;                                    // channel groups per X box (<= 16)
+  const int nco = p.co_chunk;
+  const int ncgb = nco / 8;
+  const uint32_t plane_a = (uint32_t)p.PW * 16u, plane_b = 128u * 16u;
+  const uint32_t N = 3u * (uint32_t)nco;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int st = 0; uint32_t ph = 0;
+      const uint32_t a_tx = (uint32_t)ncga * plane_a, b_tx = 3u * (uint32_t)ncgb * plane_b;
+      for (long long u = u0; u < u1; ++u) {
+        const int tx = (int)(u % ntx); long long r = u / ntx;
+        const int y = (int)(r % p.H), n = (int)(r / p.H);
+        uint8_t *sa = smem + (size_t)st * p.stage_stride;
+        ptx::mbar_wait(&empty[st], ph ^ 1, 11);
+        ptx::mbar_expect_tx(&full[st], a_tx + b_tx);
+        ptx::tma_load_5d(sa, &tmx, &full[st], 0, tx * 16 - p.margin8, ci0 / 8, y, n);
+        // dZ rows y-d, y, y+d: three single-row boxes stored back to back (= rows of one stacked B operand)
+        for (int s = 0; s < 3; ++s)
+          ptx::tma_load_5d(sa + p.a_bytes + (size_t)s * ncgb * plane_b, &tmz, &full[st], 0, tx * 16, co0 / 8, y + (s - 1) * p.dil, n);
+        if (++st == p.S) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      int st = 0; uint32_t ph = 0;
+      // MN-major, SWIZZLE_NONE: SBO = byte stride between 8-channel groups (planes), LBO = between 8-pixel blocks
+      const uint32_t a_hi = (plane_a >> 4) | (1u << 14), b_hi = (plane_b >> 4) | (1u << 14);
+      const uint32_t lo_lbo = ((128u >> 4) << 16);
+      const uint32_t idesc = ptx::make_idesc(128, (int)N, 1) | (1u << 15) | (1u << 16);
+      const uint32_t smem0 = ptx::smem_u32(smem);
+      uint32_t a_shift[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) a_shift[j] = (uint32_t)(p.margin8 * 8 + (j - 1) * p.dil);   // pixels == 16-byte units
+      bool first = true;
+      for (long long u = u0; u < u1; ++u) {
+        ptx::mbar_wait(&full[st], ph, 12);
+        ptx::tc_fence_after();
+        const uint32_t s_lo = ((smem0 + (uint32_t)st * p.stage_stride) & 0x3FFFFu) >> 4;
+        const uint32_t b_lo = s_lo + (p.a_bytes >> 4);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(lo_lbo | (b_lo + (uint32_t)ks * 16u));
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(lo_lbo | (s_lo + a_shift[j] + (uint32_t)ks * 16u));
+            ptx::mma_f16_ss(tmem_base + (uint32_t)j * N, ad, bd, idesc, (uint32_t)!(first && ks == 0));
+          }
+        }
+        first = false;
+        ptx::mma_commit(&empty[st]);
+        if (++st == p.S) { st = 0; ph ^= 1; }
+      }
+      ptx::mma_commit(acc_full);
+    }
+  } else {
+    // epilogue: TMEM lane = input channel, column = (kx, dZ row slot s, output channel); ky = 2 - s
+    const int q4 = warp & 3;
+    if (u1 > u0) {
+      ptx::mbar_wait(acc_full, 0, 13);
+      ptx::tc_fence_after();
+      const int ci = ci0 + q4 * 32 + lane;
+      const bool live = ci < p.cin_pad;
+      const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16);
+      const int units = (int)(3u * N) >> 4;
+      for (int un = 0; un < units; ++un) {
+        float v[16];
+        ptx::tmem_ld16(t0 + (uint32_t)un * 16u, v);
+        const int col = un * 16;
+        const int j = col / (int)N, rem = col - j * (int)N;
+        const int s = rem / nco, c = rem - s * nco;
+        const int tap = (2 - s) * 3 + j;
+        if (live && co0 + c < p.cout_pad) {
+          float *dst = p.dW + ((size_t)tap * p.cin_pad + ci) * p.cout_pad + co0 + c;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) red_add_f32(dst + i, v[i]);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc_512(tmem_base);
+}
+
+// db[co] = sum over pixels of dZ (bias gradient).  One warp owns 32 consecutive pixels of a row and walks
+// the channel groups; per-block partial sums leave through shared memory and one atomic per channel.
+template <typename T>
+__global__ void __launch_bounds__(256) bias_grad_kernel(View<T> dz, int nb, float *__restrict__ db) {
+  extern __shared__ float sm[];     // [C]
+  const int C = dz.C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int G = C / 8;
+  const int xchunks = (dz.W + 31) / 32;
+  const long long nwork = (long long)nb * dz.H * xchunks * G;
+  const int lane = threadIdx.x & 31;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  // a warp keeps one channel group while it strides over pixel chunks (work index = chunk * G + group, stride nw:
+  // choose nw as a multiple of G so the group of a warp is fixed)
+  const int g = (int)(wid % G);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long w = wid; w < nwork; w += nw) {
+    long long r = w / G;
+    const int xc = (int)(r % xchunks); r /= xchunks;
+    const int y = (int)(r % dz.H), n = (int)(r / dz.H);
+    const int x = xc * 32 + lane;
+    if (x < dz.W) {
+      float a[8];
+      load8<T>(dz.p + dz.at(n, y, g, x), a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += a[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float s = warp_sum(acc[k]);
+    if (lane == 0) atomicAdd(&sm[g * 8 + k], s);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&db[i], sm[i]);
+}
+
+// nearest-neighbour 2x upsampling, materialised (input of the upsampled convs' weight gradient)
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2_kernel(View<T> lo, View<T> hi, int nb) {
+  const int G = hi.C / 8;
+  const size_t total = (size_t)nb * hi.H * G * hi.W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int xx = i % hi.W; size_t r = i / hi.W;
+    int gi = r % G; r /= G;
+    int yy = r % hi.H; int n = r / hi.H;
+    float a[8];
+    load8<T>(lo.p + lo.at(n, yy >> 1, gi, xx >> 1), a);
+    store8<T>(hi.p + hi.at(n, yy, gi, xx), a);
+  }
+}
+
+}  // namespace adp

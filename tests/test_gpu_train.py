@@ -196,3 +196,26 @@ def test_training_reduces_loss(prec, weights):
     assert losses[-1] < losses[0]
     assert all(np.isfinite(losses))
     eng.train_end(); eng.close()
+
+
+@pytest.mark.parametrize("S", [128, 256])
+def test_tc_backward_matches_cuda_core_backward(S, weights):
+    """bf16 path: the tcgen05 data-gradient (conv kernel on dZ with flipped weights) and weight-gradient (pixel-reduction
+    GEMM, MN-major operands) kernels against the CUDA-core kernels on the same bf16 activations."""
+    n = 2
+    x, y = batch(n, S, seed=21)
+    masks = dropout_masks(n, S, seed=8)
+    grads = {}
+    for mode in ("tc", "simt"):
+        eng = api.Engine(precision="bf16", max_forwards=4)
+        eng.set_weights(weights)
+        eng.set_option("wgrad_simt", int(mode == "simt")); eng.set_option("dgrad_simt", int(mode == "simt"))
+        eng.train_begin(n, S, dropout_rate=0.0)
+        sums = eng.train_forward(x, y, masks)
+        eng.train_backward(sums)
+        grads[mode] = eng.train_grads()
+        eng.train_end(); eng.close()
+    worst = {k: l2_err(grads["tc"][k], grads["simt"][k]) for k in grads["tc"]}
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:4]
+    print("S", S, "tcgen05 vs CUDA-core backward, worst L2:", top)
+    assert top[0][1] <= 1e-2, top
