@@ -286,8 +286,8 @@ class Engine:
             self.lib.adp_profile_reset(self.h)
 
     def profile_rows(self) -> List[dict]:
-        rows = (_lib.ProfRow * 64)()
-        n = self.lib.adp_profile_read(self.h, rows, 64)
+        rows = (_lib.ProfRow * 512)()
+        n = self.lib.adp_profile_read(self.h, rows, 512)
         return [dict(name=rows[i].name.decode(), launches=rows[i].launches, ms=rows[i].ms, flops=rows[i].flops,
                      bytes=rows[i].bytes) for i in range(n)]
 

@@ -74,6 +74,11 @@ struct ConvTcParams {
   __nv_bfloat16 *pool_out;       // pooled row-planar tensor [nb][Hout/2][pool_cgs][Wout/2][8], EPI_POOL
   int pool_cgs, pool_cg0;
   int dbg;                       // reserved for kernel experiments
+  // backward use (data-gradient twin, EPI_STORE only): out = (acc + resid) * [mask > 0] * mask_scale, where resid and
+  // mask are tensors with exactly the layout of `out` (gradient fan-in of Add / ReLU' of the producing layer)
+  const __nv_bfloat16 *resid;
+  const __nv_bfloat16 *mask;
+  float mask_scale;
 };
 
 constexpr int kTcThreads = 320;
@@ -113,6 +118,13 @@ ADP_DEVINL void bias_relu16(const uint32_t (&r)[16], const float *sb, int relu, 
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
   }
+}
+ADP_DEVINL void load16_bf16(const __nv_bfloat16 *o, size_t plane, float (&f)[16]) {
+  __align__(16) __nv_bfloat16 h[16];
+  *reinterpret_cast<uint4 *>(h) = *reinterpret_cast<const uint4 *>(o);
+  *reinterpret_cast<uint4 *>(h + 8) = *reinterpret_cast<const uint4 *>(o + plane);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i] = __bfloat162float(h[i]);
 }
 ADP_DEVINL void store16_bf16(__nv_bfloat16 *o, size_t plane, const float (&f)[16]) {
   __align__(16) __nv_bfloat16 h[16];
@@ -256,7 +268,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
           const int row = u / NU, cu = u - row * NU;
           float f[16];
           bias_relu16(r, sb + cu * 16, p.relu, f);
-          if ((ty * T + row < p.Hin) && (x < p.Win)) store16_bf16(out_row(row) + (size_t)(2 * cu) * plane, plane, f);
+          if ((ty * T + row < p.Hin) && (x < p.Win)) {
+            __nv_bfloat16 *o = out_row(row) + (size_t)(2 * cu) * plane;
+            if (p.resid) {
+              float g[16];
+              load16_bf16(p.resid + (o - p.out), plane, g);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] += g[i];
+            }
+            if (p.mask) {
+              float m[16];
+              load16_bf16(p.mask + (o - p.out), plane, m);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = m[i] > 0.f ? f[i] * p.mask_scale : 0.f;
+            }
+            store16_bf16(o, plane, f);
+          }
         });
       } else if (p.epi_mode == EPI_HEAD) {
         // rows split between the two warps of a quarter so that one thread sees all channels of its pixel

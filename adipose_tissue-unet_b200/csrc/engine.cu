@@ -453,6 +453,8 @@ struct EpiSpec {
   int mode = EPI_STORE;
   const DevBuf *pool_dst = nullptr;   // EPI_POOL: dense pooled tensor (pitch = channels of the layer)
   float *prob = nullptr;              // EPI_HEAD: probability planes
+  const void *resid = nullptr, *mask = nullptr;   // backward (EPI_STORE): see ConvTcParams
+  float mask_scale = 1.f;
 };
 
 // tcgen05 conv launch shared by the forward layers and their data-gradient twins (train_host.cuh)
@@ -468,6 +470,9 @@ void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label,
   p.dbg = e->dbg;
   p.relu = relu;
   p.epi_mode = epi.mode;
+  p.resid = reinterpret_cast<const __nv_bfloat16 *>(epi.resid);
+  p.mask = reinterpret_cast<const __nv_bfloat16 *>(epi.mask);
+  p.mask_scale = epi.mask_scale;
   if (epi.mode == EPI_HEAD) {
     ADP_REQUIRE(p.T >= 2 && p.nvar == 1 && p.N == e->cp[0], "head fusion needs the 44-channel full-resolution layer");
     p.head_w = e->w_head.as<float>(); p.head_b = e->b_head.as<float>(); p.prob = epi.prob;

@@ -9,12 +9,14 @@ namespace adp {
 
 // ---------------------------------------------------------------------------------------------
 // Head backward.  p = softmax(z)[1] = sigmoid(z1 - z0);  dz1 = g*p*(1-p), dz0 = -dz1.
-// G[c] = dz1 * (w1[c] - w0[c]);  dWh[1][c] = sum dz1 * x[c] = -dWh[0][c];  dbh[1] = sum dz1 = -dbh[0].
+// G[c] = dz1 * (w1[c] - w0[c]) * [x[c] > 0] * scale  (x = post-dropout output of up1_conv3: the written tensor is already
+// dL/d(pre-activation) of that layer);  dWh[1][c] = sum dz1 * x[c] = -dWh[0][c];  dbh[1] = sum dz1 = -dbh[0].
 // One thread per pixel; block-level reduction, one double atomic per block and channel.
 template <typename T>
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(View<T> x, int nb, const float *__restrict__ wh /*[2][C]*/, const float *__restrict__ prob,
-                const float *__restrict__ dldp, View<T> g, double *__restrict__ dwh1 /*[C]*/, double *__restrict__ dbh1) {
+                const float *__restrict__ dldp, View<T> g, double *__restrict__ dwh1 /*[C]*/, double *__restrict__ dbh1,
+                float scale) {
   extern __shared__ float sm[];
   float *wd = sm;                       // C: w1 - w0
   float *red = sm + x.C;                // C + 1 partial sums of this block
@@ -37,7 +39,7 @@ head_bwd_kernel(View<T> x, int nb, const float *__restrict__ wh /*[2][C]*/, cons
     if (live) load8<T>(x.p + x.at(n, yy, gi, xx), a);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      o[k] = dz * wd[gi * 8 + k];
+      o[k] = a[k] > 0.f ? dz * wd[gi * 8 + k] * scale : 0.f;   // ReLU' (and dropout mask / keep) of up1_conv3 folded in
       float s = warp_sum(dz * a[k]);
       if ((threadIdx.x & 31) == 0) atomicAdd(&red[gi * 8 + k], s);
     }
@@ -105,7 +107,8 @@ dropout_kernel(View<T> x, int nb, float keep, uint64_t seed, const uint8_t *__re
 
 // MaxPooling2D backward: the gradient of a pooled pixel goes to the FIRST maximum of its 2x2 window
 // in (dy,dx) scan order.  One thread per pooled pixel and channel group; gin is ADDED into (the skip
-// tensor's gradient already holds the decoder branch).
+// tensor's gradient already holds the decoder branch, already multiplied by the ReLU mask of the layer that
+// produced xin — so the pooled contribution is masked the same way here).
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(View<T> xin, View<T> gout, View<T> gin, int nb) {
   const int G = gout.C / 8;
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(View<T> xin, View<T> 
 #pragma unroll
       for (int q = 1; q < 4; ++q) if (v[q][k] > v[best][k]) best = q;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) if (q == best) gi4[q][k] += go[k];
+      for (int q = 0; q < 4; ++q) if (q == best && v[q][k] > 0.f) gi4[q][k] += go[k];   // gin holds dL/d(pre-activation): ReLU' of the pooled layer
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) store8<T>(gin.p + gin.at(n, 2 * yy + (q >> 1), gi, 2 * xx + (q & 1)), gi4[q]);
@@ -135,8 +138,9 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(View<T> xin, View<T> 
 }
 
 // UpSampling2D backward: glow[y][x] = sum of the 2x2 block of ghigh
+// x.p != null: the result is also multiplied by [x > 0] * scale (ReLU' / dropout of the layer that produced the low-res tensor)
 template <typename T>
-__global__ void __launch_bounds__(256) upsample2_bwd_kernel(View<T> ghigh, View<T> glow, int nb) {
+__global__ void __launch_bounds__(256) upsample2_bwd_kernel(View<T> ghigh, View<T> glow, int nb, View<T> x, float scale) {
   const int G = glow.C / 8;
   const size_t total = (size_t)nb * glow.H * G * glow.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -149,6 +153,11 @@ __global__ void __launch_bounds__(256) upsample2_bwd_kernel(View<T> ghigh, View<
       load8<T>(ghigh.p + ghigh.at(n, 2 * yy + (q >> 1), gi, 2 * xx + (q & 1)), a);
 #pragma unroll
       for (int k = 0; k < 8; ++k) s[k] += a[k];
+    }
+    if (x.p) {
+      load8<T>(x.p + x.at(n, yy, gi, xx), a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] = a[k] > 0.f ? s[k] * scale : 0.f;
     }
     store8<T>(glow.p + glow.at(n, yy, gi, xx), s);
   }
@@ -250,38 +259,54 @@ conv_wgrad_kernel(View<T> xin, View<T> dz, float *__restrict__ dW, float *__rest
 }
 
 // First layer (Cin = 1) weight gradient: dW[t][co] = sum x_norm(p + tap) * dZ[p][co], db[co] = sum dZ.
-// xnorm: [nb][S][S] float32 (already normalised).  block = 256 threads = 32 pixels x 8 lanes of work.
+// xnorm: [nb][S][S] float32 (already normalised).  A warp owns 32 consecutive pixels of a row and ONE channel
+// group (gridDim.x * 8 warps is a multiple of the group count), keeps its 9x8 + 8 sums in registers over all its
+// pixels and leaves through shuffles + one atomic per sum.
 template <typename T>
 __global__ void __launch_bounds__(256)
 first_wgrad_kernel(const float *__restrict__ xnorm, View<T> dz, int nb, float *__restrict__ dW /*[9][C]*/, float *__restrict__ db) {
-  extern __shared__ float sm[];      // [10][C] block partials
-  const int C = dz.C, S = dz.H;
-  for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  const size_t total = (size_t)nb * S * S;
-  for (size_t px = blockIdx.x * (size_t)blockDim.x + threadIdx.x; px < total; px += (size_t)gridDim.x * blockDim.x) {
-    const int x = px % S; size_t r = px / S; const int y = r % S; const int n = r / S;
-    float v[9];
+  const int C = dz.C, S = dz.H, G = C / 8;
+  const int lane = threadIdx.x & 31;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int g = (int)(wid % G);
+  const int xchunks = (S + 31) / 32;
+  const long long nwork = (long long)nb * S * xchunks * G;
+  float acc[9][8], bs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    bs[k] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t][k] = 0.f;
+  }
+  for (long long w = wid; w < nwork; w += nw) {
+    long long r = w / G;
+    const int xc = (int)(r % xchunks); r /= xchunks;
+    const int y = (int)(r % S), n = (int)(r / S);
+    const int x = xc * 32 + lane;
+    if (x >= S) continue;
+    float d[8];
+    load8<T>(dz.p + dz.at(n, y, g, x), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bs[k] += d[k];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
-      v[t] = (iy >= 0 && iy < S && ix >= 0 && ix < S) ? xnorm[((size_t)n * S + iy) * S + ix] : 0.f;
-    }
-    for (int gi = 0; gi < C / 8; ++gi) {
-      float g[8];
-      load8<T>(dz.p + dz.at(n, y, gi, x), g);
+      const float v = (iy >= 0 && iy < S && ix >= 0 && ix < S) ? xnorm[((size_t)n * S + iy) * S + ix] : 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (g[k] == 0.f) continue;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) atomicAdd(&sm[t * C + gi * 8 + k], v[t] * g[k]);
-        atomicAdd(&sm[9 * C + gi * 8 + k], g[k]);
-      }
+      for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(v, d[k], acc[t][k]);
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) atomicAdd(&dW[i], sm[i]);
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&db[i], sm[9 * C + i]);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float s = warp_sum(bs[k]);
+    if (lane == 0) atomicAdd(&db[g * 8 + k], s);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float a = warp_sum(acc[t][k]);
+      if (lane == 0) atomicAdd(&dW[t * C + g * 8 + k], a);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

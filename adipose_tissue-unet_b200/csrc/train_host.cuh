@@ -26,8 +26,8 @@ void plan_wgrad_tc(adp_engine *e, const ConvLayer &L, WgradTcParams &p) {
   p.dil = L.dil; p.cin_pad = L.cin_pad; p.cout_pad = L.cout_pad;
   p.co_chunk = std::min(48, L.cout_pad);
   p.n_co_chunk = cdiv(L.cout_pad, p.co_chunk);
-  p.n_ci_blk = cdiv(L.cin_pad, 128);
-  p.cga_box = std::min(16, L.cin_pad / 8);
+  p.n_ci_blk = cdiv(L.cin_pad, 120);
+  p.cga_box = std::min(15, L.cin_pad / 8);
   const int margin = (L.dil + 7) / 8 * 8;
   p.margin8 = margin / 8; p.PW = 128 + 2 * margin;
   p.a_bytes = (uint32_t)16 * p.PW * 16;                 // always 16 planes: an M = 128 operand spans 16 channel groups
@@ -307,18 +307,13 @@ template <typename T> struct Bwd {
           });
         }
         WgradTcParams p = TL.wg;
-        p.nb = nb; p.H = dz.H; p.W = dz.W; p.dW = TL.gw.as<float>();
+        p.nb = nb; p.H = dz.H; p.W = dz.W; p.dW = TL.gw.as<float>(); p.db = TL.gb.as<float>();
         const CUtensorMap &tmx = tmap_for(e, xs.p, xs.H, xs.W, xs.cgs, xs.cg0, xs.C, nb, p.PW / 8, p.cga_box, 1);
         const CUtensorMap &tmz = tmap_for(e, dz.p, dz.H, dz.W, dz.cgs, dz.cg0, dz.C, nb, 16, p.co_chunk / 8, 1);
         const int grid = p.n_ci_blk * p.n_co_chunk * p.ctas_per_combo;
         const double by = (double)nb * dz.H * dz.W * (L.cin_pad + L.cout_pad) * 2.0;
         e->launch(("conv_wgrad_tcgen05/" + L.name).c_str(), fl, by, [&] {
           wgrad_tc_kernel<<<grid, kWgThreads, wgrad_smem_bytes(p), e->stream>>>(tmx, tmz, p);
-        });
-        const int G = dz.C / 8;
-        const int blocks = G * std::max(1, std::min(e->num_sms * 4 / G, (int)cdiv64((long long)nb * dz.H * cdiv(dz.W, 32), 8)));
-        e->launch("bias_grad", 0, (double)nb * dz.H * dz.W * dz.C * 2.0, [&] {
-          bias_grad_kernel<T><<<blocks, 256, (size_t)dz.C * 4, e->stream>>>(dz, nb, TL.gb.as<float>());
         });
       }
     } else {
@@ -340,28 +335,44 @@ template <typename T> struct Bwd {
     ADP_CUDA(cudaMemcpyAsync(tr->grad.as<float>() + TL.boff, TL.gb.p, (size_t)L.cout * 4, cudaMemcpyDeviceToDevice, e->stream));
   }
 
-  // data gradient of layer li: dz (output resolution) -> gin (input resolution)
-  void dgrad(size_t li, View<T> dz, View<T> gin) {
+  // data gradient of layer li: dz (output resolution) -> gin (input resolution):
+  //   gin = (conv(dz, flipped W) [2x2-summed for an upsampled conv] + resid) * [mask > 0] * scale
+  // mask = the forward tensor gin is the gradient of (ReLU', and the dropout mask when scale = 1/keep): the written
+  // tensor is dL/d(pre-activation) of the producing layer.  On the tcgen05 path both live in the conv epilogue.
+  void dgrad(size_t li, View<T> dz, View<T> gin, const View<T> *mask = nullptr, float scale = 1.f, const View<T> *resid = nullptr) {
     ConvLayer &L = e->layers[li];
     TrainLayer &TL = tr->tl[li];
     View<T> out = gin;
     if (L.up) out = V(tr->g_hi, dz.H, L.cin_pad, 0, L.cin_pad);
     dim3 grid(cdiv(dz.W, 32), cdiv(dz.H, 8), nb * (L.cin_pad / 16)), block(32, 8);
     const double fl = conv_flops(L, dz.H, dz.W, nb);
+    bool fused = false;
     if (e->prec == ADP_PREC_BF16 && !e->dgrad_simt) {
       const double by = (double)nb * dz.H * dz.W * (L.cin_pad + L.cout_pad) * 2.0;
+      EpiSpec epi;
+      if (!L.up) {
+        ADP_REQUIRE(!mask || (mask->cgs == gin.cgs && mask->cg0 == gin.cg0 && mask->H == gin.H), "mask layout must equal the gradient layout");
+        ADP_REQUIRE(!resid || (resid->cgs == gin.cgs && resid->cg0 == gin.cg0 && resid->H == gin.H), "residual layout must equal the gradient layout");
+        epi.mask = mask ? mask->p : nullptr; epi.mask_scale = scale; epi.resid = resid ? resid->p : nullptr;
+        fused = true;
+      }
       launch_conv_tc(e, TL.twin, "conv_dgrad_tcgen05/" + L.name, fl, by, dz.p, dz.H, dz.W, dz.cgs, dz.cg0, out.p, out.cgs, out.cg0, nb, nb,
-                     EpiSpec(), tr->zeros.as<float>(), 0);
+                     epi, tr->zeros.as<float>(), 0);
     } else {
       e->launch(("conv_dgrad_simt/" + L.name).c_str(), fl, 0, [&] {
         conv3x3_simt_kernel<T, false><<<grid, block, 0, e->stream>>>(dz, out, TL.wT.as<float>(), tr->zeros.as<float>(), L.dil, 0);
       });
     }
     if (L.up) {
+      ADP_REQUIRE(!resid, "no residual on an upsampled conv");
       const size_t total = (size_t)nb * gin.H * gin.W * (gin.C / 8);
-      e->launch("upsample2x2_bwd", 0, (double)total * 8 * sizeof(T) * 5, [&] {
-        upsample2_bwd_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(out, gin, nb);
+      View<T> none{}; none.p = nullptr;
+      e->launch("upsample2x2_bwd", 0, (double)total * 8 * sizeof(T) * (mask ? 6 : 5), [&] {
+        upsample2_bwd_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(out, gin, nb, mask ? *mask : none, scale);
       });
+    } else if (!fused) {
+      if (resid) add(gin, gin, *resid);
+      if (mask) relu_mask(gin, *mask, scale);
     }
   }
 };
@@ -380,7 +391,7 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
   const float inv_keep = 1.f / tr->keep;
   auto li = [&](const char *n) { return layer_index(e, n); };
 
-  // head: dL/dp -> dL/d(up1_conv3 post-dropout output), head weight gradients
+  // head: dL/dp -> dL/d(pre-activation of up1_conv3) (ReLU' and dropout folded in), head weight gradients
   {
     auto x = B.V(tr->u1c, S, cp[0], 0, cp[0]);
     auto g = B.V(tr->g_u1c, S, cp[0], 0, cp[0]);
@@ -388,89 +399,88 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
     const size_t total = (size_t)nb * S * S;
     e->launch("head_bwd", 0, (double)total * (8 + 2.0 * cp[0] * sizeof(T)), [&] {
       head_bwd_kernel<T><<<(int)cdiv64(total, 256), 256, (size_t)(2 * cp[0] + 1) * 4, e->stream>>>(
-          x, nb, e->w_head.as<float>(), tr->prob.as<float>(), tr->dldp.as<float>(), g, tr->g_head.as<double>(), tr->g_head.as<double>() + cp[0]);
+          x, nb, e->w_head.as<float>(), tr->prob.as<float>(), tr->dldp.as<float>(), g, tr->g_head.as<double>(), tr->g_head.as<double>() + cp[0],
+          inv_keep);
     });
     e->launch("head_grad_finish", 0, 0, [&] {
       head_grad_finish_kernel<<<1, 256, 0, e->stream>>>(tr->g_head.as<double>(), e->c[0], cp[0], tr->grad.as<float>() + tr->koff_head,
                                                        tr->grad.as<float>() + tr->boff_head);
     });
-    B.relu_mask(g, x, inv_keep);
   }
-  // decoder level 1
-  B.wgrad(li("up1_conv3"), B.V(tr->u1b, S, cp[0], 0, cp[0]), B.V(tr->g_u1c, S, cp[0], 0, cp[0]));
-  B.dgrad(li("up1_conv3"), B.V(tr->g_u1c, S, cp[0], 0, cp[0]), B.V(tr->g_u1b, S, cp[0], 0, cp[0]));
-  B.relu_mask(B.V(tr->g_u1b, S, cp[0], 0, cp[0]), B.V(tr->u1b, S, cp[0], 0, cp[0]), 1.f);
-  B.wgrad(li("up1_conv2"), B.V(tr->cat1, S, 2 * cp[0], 0, 2 * cp[0]), B.V(tr->g_u1b, S, cp[0], 0, cp[0]));
-  B.dgrad(li("up1_conv2"), B.V(tr->g_u1b, S, cp[0], 0, cp[0]), B.V(tr->g_cat1, S, 2 * cp[0], 0, 2 * cp[0]));
-  B.relu_mask(B.V(tr->g_cat1, S, 2 * cp[0], cp[0], cp[0]), B.V(tr->cat1, S, 2 * cp[0], cp[0], cp[0]), 1.f);
-  B.wgrad(li("up1_conv1"), B.V(tr->u2c, S2, cp[1], 0, cp[1]), B.V(tr->g_cat1, S, 2 * cp[0], cp[0], cp[0]));
-  B.dgrad(li("up1_conv1"), B.V(tr->g_cat1, S, 2 * cp[0], cp[0], cp[0]), B.V(tr->g_u2c, S2, cp[1], 0, cp[1]));
-  B.relu_mask(B.V(tr->g_u2c, S2, cp[1], 0, cp[1]), B.V(tr->u2c, S2, cp[1], 0, cp[1]), inv_keep);
-  // decoder level 2
-  B.wgrad(li("up2_conv3"), B.V(tr->u2b, S2, cp[1], 0, cp[1]), B.V(tr->g_u2c, S2, cp[1], 0, cp[1]));
-  B.dgrad(li("up2_conv3"), B.V(tr->g_u2c, S2, cp[1], 0, cp[1]), B.V(tr->g_u2b, S2, cp[1], 0, cp[1]));
-  B.relu_mask(B.V(tr->g_u2b, S2, cp[1], 0, cp[1]), B.V(tr->u2b, S2, cp[1], 0, cp[1]), 1.f);
-  B.wgrad(li("up2_conv2"), B.V(tr->cat2, S2, 2 * cp[1], 0, 2 * cp[1]), B.V(tr->g_u2b, S2, cp[1], 0, cp[1]));
-  B.dgrad(li("up2_conv2"), B.V(tr->g_u2b, S2, cp[1], 0, cp[1]), B.V(tr->g_cat2, S2, 2 * cp[1], 0, 2 * cp[1]));
-  B.relu_mask(B.V(tr->g_cat2, S2, 2 * cp[1], cp[1], cp[1]), B.V(tr->cat2, S2, 2 * cp[1], cp[1], cp[1]), 1.f);
-  B.wgrad(li("up2_conv1"), B.V(tr->u3c, S3, cp[2], 0, cp[2]), B.V(tr->g_cat2, S2, 2 * cp[1], cp[1], cp[1]));
-  B.dgrad(li("up2_conv1"), B.V(tr->g_cat2, S2, 2 * cp[1], cp[1], cp[1]), B.V(tr->g_u3c, S3, cp[2], 0, cp[2]));
-  B.relu_mask(B.V(tr->g_u3c, S3, cp[2], 0, cp[2]), B.V(tr->u3c, S3, cp[2], 0, cp[2]), inv_keep);
-  // decoder level 3
-  B.wgrad(li("up3_conv3"), B.V(tr->u3b, S3, cp[2], 0, cp[2]), B.V(tr->g_u3c, S3, cp[2], 0, cp[2]));
-  B.dgrad(li("up3_conv3"), B.V(tr->g_u3c, S3, cp[2], 0, cp[2]), B.V(tr->g_u3b, S3, cp[2], 0, cp[2]));
-  B.relu_mask(B.V(tr->g_u3b, S3, cp[2], 0, cp[2]), B.V(tr->u3b, S3, cp[2], 0, cp[2]), 1.f);
-  B.wgrad(li("up3_conv2"), B.V(tr->cat3, S3, 2 * cp[2], 0, 2 * cp[2]), B.V(tr->g_u3b, S3, cp[2], 0, cp[2]));
-  B.dgrad(li("up3_conv2"), B.V(tr->g_u3b, S3, cp[2], 0, cp[2]), B.V(tr->g_cat3, S3, 2 * cp[2], 0, 2 * cp[2]));
-  B.relu_mask(B.V(tr->g_cat3, S3, 2 * cp[2], cp[2], cp[2]), B.V(tr->cat3, S3, 2 * cp[2], cp[2], cp[2]), 1.f);
-  B.wgrad(li("up3_conv1"), B.V(tr->ts, S4, cp[3], 0, cp[3]), B.V(tr->g_cat3, S3, 2 * cp[2], cp[2], cp[2]));
-  B.dgrad(li("up3_conv1"), B.V(tr->g_cat3, S3, 2 * cp[2], cp[2], cp[2]), B.V(tr->g_ts, S4, cp[3], 0, cp[3]));
-  // bottleneck: Add fans the gradient out to the six dilate outputs; the chain adds the downstream conv's data gradient
+  // Every g_* tensor below holds dL/d(pre-activation) of the layer that produced the matching activation.
+  struct Lvl { int H, c; DevBuf *cat, *g_cat, *ub, *g_ub, *uc, *g_uc, *da, *g_da, *pl, *g_pl; const char *c1, *c2, *c3, *d1, *d2; };
+  const Lvl lv[3] = {
+      {S, cp[0], &tr->cat1, &tr->g_cat1, &tr->u1b, &tr->g_u1b, &tr->u1c, &tr->g_u1c, &tr->d1a, &tr->g_d1a, &tr->pl1, &tr->g_pl1,
+       "up1_conv1", "up1_conv2", "up1_conv3", "down1_conv1", "down1_conv2"},
+      {S2, cp[1], &tr->cat2, &tr->g_cat2, &tr->u2b, &tr->g_u2b, &tr->u2c, &tr->g_u2c, &tr->d2a, &tr->g_d2a, &tr->pl2, &tr->g_pl2,
+       "up2_conv1", "up2_conv2", "up2_conv3", "down2_conv1", "down2_conv2"},
+      {S3, cp[2], &tr->cat3, &tr->g_cat3, &tr->u3b, &tr->g_u3b, &tr->u3c, &tr->g_u3c, &tr->d3a, &tr->g_d3a, &tr->pl3, &tr->g_pl3,
+       "up3_conv1", "up3_conv2", "up3_conv3", "down3_conv1", "down3_conv2"}};
+  // decoder, levels 1..3
+  for (int l = 0; l < 3; ++l) {
+    const Lvl &q = lv[l];
+    const int H = q.H, c = q.c;
+    auto ub = B.V(*q.ub, H, c, 0, c), g_ub = B.V(*q.g_ub, H, c, 0, c), g_uc = B.V(*q.g_uc, H, c, 0, c);
+    auto cat = B.V(*q.cat, H, 2 * c, 0, 2 * c), g_cat = B.V(*q.g_cat, H, 2 * c, 0, 2 * c);
+    auto g_cat_up = B.V(*q.g_cat, H, 2 * c, c, c);
+    B.wgrad(li(q.c3), ub, g_uc);
+    B.dgrad(li(q.c3), g_uc, g_ub, &ub, 1.f);
+    B.wgrad(li(q.c2), cat, g_ub);
+    B.dgrad(li(q.c2), g_ub, g_cat, &cat, 1.f);          // both halves: [skip | up]
+    if (l < 2) {       // input of up{l}_conv1 = post-dropout up{l+1}_conv3 at half resolution
+      const Lvl &n = lv[l + 1];
+      auto src = B.V(*n.uc, n.H, n.c, 0, n.c), g_src = B.V(*n.g_uc, n.H, n.c, 0, n.c);
+      B.wgrad(li(q.c1), src, g_cat_up);
+      B.dgrad(li(q.c1), g_cat_up, g_src, &src, inv_keep);
+    } else {           // up3_conv1 reads the Add of the six bottleneck tensors (no activation of its own)
+      auto ts = B.V(tr->ts, S4, cp[3], 0, cp[3]), g_ts = B.V(tr->g_ts, S4, cp[3], 0, cp[3]);
+      B.wgrad(li(q.c1), ts, g_cat_up);
+      B.dgrad(li(q.c1), g_cat_up, g_ts);
+    }
+  }
+  // bottleneck: Add fans g_ts out to the six dilate outputs; the chain adds the downstream conv's data gradient
   const char *dn[6] = {"dilate1", "dilate2", "dilate3", "dilate4", "dilate5", "dilate6"};
   auto VT = [&](const DevBuf &b) { return B.V(b, S4, cp[3], 0, cp[3]); };
   ADP_CUDA(cudaMemcpyAsync(tr->gt[1].p, tr->g_ts.p, (size_t)nb * S4 * S4 * cp[3] * sizeof(T), cudaMemcpyDeviceToDevice, e->stream));
-  int cur = 1;     // gt[cur] = dL/d t[i]
+  B.relu_mask(VT(tr->gt[1]), VT(tr->t[5]), 1.f);
+  int cur = 1;     // gt[cur] = dL/d(pre-activation of dilate{i+1})
   for (int i = 5; i >= 1; --i) {
-    B.relu_mask(VT(tr->gt[cur]), VT(tr->t[i]), 1.f);
     B.wgrad(li(dn[i]), VT(tr->t[i - 1]), VT(tr->gt[cur]));
-    B.dgrad(li(dn[i]), VT(tr->gt[cur]), VT(tr->gt[cur ^ 1]));
-    B.add(VT(tr->gt[cur ^ 1]), VT(tr->gt[cur ^ 1]), VT(tr->g_ts));
+    auto m = VT(tr->t[i - 1]), r = VT(tr->g_ts);
+    B.dgrad(li(dn[i]), VT(tr->gt[cur]), VT(tr->gt[cur ^ 1]), &m, i == 1 ? inv_keep : 1.f, &r);
     cur ^= 1;
   }
-  B.relu_mask(VT(tr->gt[cur]), VT(tr->t[0]), inv_keep);
   B.wgrad(li("dilate1"), B.V(tr->pl3, S4, cp[2], 0, cp[2]), VT(tr->gt[cur]));
   if (freeze_encoder) return;     // phase 1: nothing upstream is trainable (train_adipose_unet_v3.py:760-769)
-  B.dgrad(li("dilate1"), VT(tr->gt[cur]), B.V(tr->g_pl3, S4, cp[2], 0, cp[2]));
-  // encoder level 3
-  B.pool_bwd(B.V(tr->cat3, S3, 2 * cp[2], 0, cp[2]), B.V(tr->g_pl3, S4, cp[2], 0, cp[2]), B.V(tr->g_cat3, S3, 2 * cp[2], 0, cp[2]));
-  B.relu_mask(B.V(tr->g_cat3, S3, 2 * cp[2], 0, cp[2]), B.V(tr->cat3, S3, 2 * cp[2], 0, cp[2]), 1.f);
-  B.wgrad(li("down3_conv2"), B.V(tr->d3a, S3, cp[2], 0, cp[2]), B.V(tr->g_cat3, S3, 2 * cp[2], 0, cp[2]));
-  B.dgrad(li("down3_conv2"), B.V(tr->g_cat3, S3, 2 * cp[2], 0, cp[2]), B.V(tr->g_d3a, S3, cp[2], 0, cp[2]));
-  B.relu_mask(B.V(tr->g_d3a, S3, cp[2], 0, cp[2]), B.V(tr->d3a, S3, cp[2], 0, cp[2]), 1.f);
-  B.wgrad(li("down3_conv1"), B.V(tr->pl2, S3, cp[1], 0, cp[1]), B.V(tr->g_d3a, S3, cp[2], 0, cp[2]));
-  B.dgrad(li("down3_conv1"), B.V(tr->g_d3a, S3, cp[2], 0, cp[2]), B.V(tr->g_pl2, S3, cp[1], 0, cp[1]));
-  // encoder level 2
-  B.pool_bwd(B.V(tr->cat2, S2, 2 * cp[1], 0, cp[1]), B.V(tr->g_pl2, S3, cp[1], 0, cp[1]), B.V(tr->g_cat2, S2, 2 * cp[1], 0, cp[1]));
-  B.relu_mask(B.V(tr->g_cat2, S2, 2 * cp[1], 0, cp[1]), B.V(tr->cat2, S2, 2 * cp[1], 0, cp[1]), 1.f);
-  B.wgrad(li("down2_conv2"), B.V(tr->d2a, S2, cp[1], 0, cp[1]), B.V(tr->g_cat2, S2, 2 * cp[1], 0, cp[1]));
-  B.dgrad(li("down2_conv2"), B.V(tr->g_cat2, S2, 2 * cp[1], 0, cp[1]), B.V(tr->g_d2a, S2, cp[1], 0, cp[1]));
-  B.relu_mask(B.V(tr->g_d2a, S2, cp[1], 0, cp[1]), B.V(tr->d2a, S2, cp[1], 0, cp[1]), 1.f);
-  B.wgrad(li("down2_conv1"), B.V(tr->pl1, S2, cp[0], 0, cp[0]), B.V(tr->g_d2a, S2, cp[1], 0, cp[1]));
-  B.dgrad(li("down2_conv1"), B.V(tr->g_d2a, S2, cp[1], 0, cp[1]), B.V(tr->g_pl1, S2, cp[0], 0, cp[0]));
-  // encoder level 1
-  B.pool_bwd(B.V(tr->cat1, S, 2 * cp[0], 0, cp[0]), B.V(tr->g_pl1, S2, cp[0], 0, cp[0]), B.V(tr->g_cat1, S, 2 * cp[0], 0, cp[0]));
-  B.relu_mask(B.V(tr->g_cat1, S, 2 * cp[0], 0, cp[0]), B.V(tr->cat1, S, 2 * cp[0], 0, cp[0]), 1.f);
-  B.wgrad(li("down1_conv2"), B.V(tr->d1a, S, cp[0], 0, cp[0]), B.V(tr->g_cat1, S, 2 * cp[0], 0, cp[0]));
-  B.dgrad(li("down1_conv2"), B.V(tr->g_cat1, S, 2 * cp[0], 0, cp[0]), B.V(tr->g_d1a, S, cp[0], 0, cp[0]));
-  B.relu_mask(B.V(tr->g_d1a, S, cp[0], 0, cp[0]), B.V(tr->d1a, S, cp[0], 0, cp[0]), 1.f);
+  // encoder, levels 3..1
+  for (int l = 2; l >= 0; --l) {
+    const Lvl &q = lv[l];
+    const int H = q.H, c = q.c;
+    auto g_pl = B.V(*q.g_pl, H / 2, c, 0, c);
+    auto skip = B.V(*q.cat, H, 2 * c, 0, c), g_skip = B.V(*q.g_cat, H, 2 * c, 0, c);
+    auto da = B.V(*q.da, H, c, 0, c), g_da = B.V(*q.g_da, H, c, 0, c);
+    if (l == 2) B.dgrad(li("dilate1"), VT(tr->gt[cur]), g_pl);
+    else {
+      const Lvl &n = lv[l + 1];
+      B.dgrad(li(n.d1), B.V(*n.g_da, n.H, n.c, 0, n.c), g_pl);
+    }
+    B.pool_bwd(skip, g_pl, g_skip);
+    B.wgrad(li(q.d2), da, g_skip);
+    B.dgrad(li(q.d2), g_skip, g_da, &da, 1.f);
+    if (l > 0) {     // down{l}_conv1 reads the pooled output of the level above (down1_conv1: first-layer kernel below)
+      const Lvl &u = lv[l - 1];
+      B.wgrad(li(q.d1), B.V(*u.pl, H, u.c, 0, u.c), g_da);
+    }
+  }
   // first conv (Cin = 1): weight gradient only
   {
     ADP_CUDA(cudaMemsetAsync(tr->gw_first.p, 0, (size_t)9 * cp[0] * 4, e->stream));
     ADP_CUDA(cudaMemsetAsync(tr->gb_first.p, 0, (size_t)cp[0] * 4, e->stream));
     const size_t total = (size_t)nb * S * S;
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 4));
+    const int G0 = cp[0] / 8;
+    const int grid = G0 * std::max(1, std::min(e->num_sms * 4 / G0, (int)cdiv64((long long)nb * S * cdiv(S, 32), 8)));
     e->launch("first_conv_wgrad", 2.0 * total * 9 * e->c[0], (double)total * (4 + cp[0] * sizeof(T)), [&] {
-      first_wgrad_kernel<T><<<grid, 256, (size_t)10 * cp[0] * 4, e->stream>>>(tr->x.as<float>(), B.V(tr->g_d1a, S, cp[0], 0, cp[0]), nb,
+      first_wgrad_kernel<T><<<grid, 256, 0, e->stream>>>(tr->x.as<float>(), B.V(tr->g_d1a, S, cp[0], 0, cp[0]), nb,
                                                                               tr->gw_first.as<float>(), tr->gb_first.as<float>());
     });
     e->launch("grad_unpad", 0, 0, [&] {

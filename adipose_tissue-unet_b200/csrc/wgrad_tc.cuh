@@ -14,6 +14,9 @@
 // So a K step of 16 pixels is 3 MMAs (one per horizontal tap) of shape 128 x (3*chunk) x 16 into three
 // TMEM accumulators (3 x 144 = 432 of the 512 columns for chunk = 48).
 //
+// Bias gradient for free: an X block carries at most 15 channel groups (120 channels); the 16th plane of the A
+// operand is filled once with bf16 ones, so accumulator row 120 of the centre tap is sum_pixels dZ = db.
+//
 // A CTA owns one (input-channel block, output-channel chunk) pair and a contiguous range of
 // (image, row, 128-pixel strip) units; it accumulates its whole range in TMEM and then adds the
 // 128 x 432 partial sums into the padded fp32 gradient dW[9][cin_pad][cout_pad] with red.global.add.
@@ -28,14 +31,15 @@ struct WgradTcParams {
   int nb, H, W;                  // images, spatial size (X and dZ have the same size)
   int dil;
   int cin_pad, cout_pad;
-  int n_ci_blk, n_co_chunk;      // 128-channel blocks of X, chunks of dZ channels
+  int n_ci_blk, n_co_chunk;      // 120-channel blocks of X, chunks of dZ channels
   int co_chunk;                  // channels per chunk (multiple of 16, 3*co_chunk <= 170)
   int ctas_per_combo;
-  int cga_box;                   // channel groups per X box = min(16, cin_pad / 8)
+  int cga_box;                   // channel groups per X box = min(15, cin_pad / 8); plane 15 holds ones
   int PW, margin8;               // X plane width in pixels (128 + 2*margin), halo in 8-pixel groups
   int S;                         // pipeline depth
   uint32_t a_bytes, b_row_bytes, stage_stride;
   float *dW;                     // [9][cin_pad][cout_pad] fp32, accumulated into
+  float *db;                     // [cout_pad] fp32, accumulated into
 };
 
 constexpr int kWgThreads = 192;
@@ -60,6 +64,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
     ptx::prefetch_tmap(&tmz);
   }
   if (warp == 1) ptx::tmem_alloc_512(tmem_ptr);
+  // plane 15 of every stage's A region := bf16 1.0 (never touched by the TMA boxes, which carry <= 15 groups)
+  for (int st = 0; st < p.S; ++st) {
+    uint32_t *ones = reinterpret_cast<uint32_t *>(smem + (size_t)st * p.stage_stride + (size_t)15 * p.PW * 16);
+    for (int i = threadIdx.x; i < p.PW * 4; i += kWgThreads) ones[i] = 0x3F803F80u;
+  }
+  ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -71,7 +81,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
   const int ntx = (p.W + 127) / 128;
   const long long nunits = (long long)p.nb * p.H * ntx;
   const long long u0 = nunits * part / p.ctas_per_combo, u1 = nunits * (part + 1) / p.ctas_per_combo;
-  const int ci0 = cib * 128, co0 = coc * p.co_chunk;
+  const int ci0 = cib * 120, co0 = coc * p.co_chunk;
   // TMA boxes have a fixed shape: channel groups past the end of the tensor arrive as zeros and only cost MMA columns
   const int ncga = p.cga_box;                                    // channel groups per X box (<= 16)
   const int nco = p.co_chunk;
@@ -134,8 +144,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
     if (u1 > u0) {
       ptx::mbar_wait(acc_full, 0, 13);
       ptx::tc_fence_after();
-      const int ci = ci0 + q4 * 32 + lane;
-      const bool live = ci < p.cin_pad;
+      const int row = q4 * 32 + lane;
+      const int ci = ci0 + row;
+      const bool live = row < ncga * 8 && ci < p.cin_pad;
+      const bool bias_row = row == 120 && cib == 0;
       const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16);
       const int units = (int)(3u * N) >> 4;
       for (int un = 0; un < units; ++un) {
@@ -149,6 +161,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
           float *dst = p.dW + ((size_t)tap * p.cin_pad + ci) * p.cout_pad + co0 + c;
 #pragma unroll
           for (int i = 0; i < 16; ++i) red_add_f32(dst + i, v[i]);
+        }
+        if (bias_row && j == 1 && s == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (co0 + c + i < p.cout_pad) red_add_f32(p.db + co0 + c + i, v[i]);
         }
       }
     }
