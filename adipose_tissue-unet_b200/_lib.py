@@ -67,6 +67,8 @@ SIGNATURES = {
     "adp_train_loss": (_I, [C.POINTER(C.c_double), _I64, C.POINTER(C.c_double)]),
     "adp_train_backward": (_I, [_P, C.POINTER(C.c_double), _I64, _I]),
     "adp_train_grad_buffer": (_I, [_P, C.POINTER(_P), C.POINTER(_I64)]),
+    "adp_train_grad_read": (_I, [_P, _P, _I64]),
+    "adp_train_grad_write": (_I, [_P, _P, _I64]),
     "adp_train_get_grad": (_I, [_P, C.c_char_p, _P, _I64, _P, _I64]),
     "adp_train_probs": (_I, [_P, _P, _I64]),
     "adp_train_apply": (_I, [_P, _I, _F, _F, C.c_double, C.c_double, _F, _F, _I]),

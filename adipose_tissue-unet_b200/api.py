@@ -191,6 +191,16 @@ class Engine:
         _lib.check(self.lib.adp_train_grad_buffer(self.h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
 
+    def grad_to_host(self) -> np.ndarray:
+        _, n = self.train_grad_buffer()
+        g = np.empty(n, np.float32)
+        _lib.check(self.lib.adp_train_grad_read(self.h, _lib.ptr(g), n))
+        return g
+
+    def grad_from_host(self, g: np.ndarray):
+        g = _f32c(g).ravel()
+        _lib.check(self.lib.adp_train_grad_write(self.h, _lib.ptr(g), g.size))
+
     def train_grads(self) -> Dict[str, np.ndarray]:
         out = {}
         for name, (ks, bs) in weight_shapes(self.init_nb).items():

@@ -1283,6 +1283,28 @@ int adp_train_grad_buffer(adp_engine *e, float **dev_ptr, int64_t *count) {
   ADP_CATCH
 }
 
+int adp_train_grad_read(adp_engine *e, float *host, int64_t count) {
+  ADP_TRY
+  ADP_REQUIRE(e && host, "null argument");
+  if (!e->tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
+  ADP_REQUIRE(count == (int64_t)e->tr->P, "count != parameter count");
+  ADP_CUDA(cudaSetDevice(e->device));
+  ADP_CUDA(cudaMemcpyAsync(host, e->tr->grad.as<float>(), (size_t)count * 4, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  ADP_CATCH
+}
+
+int adp_train_grad_write(adp_engine *e, const float *host, int64_t count) {
+  ADP_TRY
+  ADP_REQUIRE(e && host, "null argument");
+  if (!e->tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
+  ADP_REQUIRE(count == (int64_t)e->tr->P, "count != parameter count");
+  ADP_CUDA(cudaSetDevice(e->device));
+  ADP_CUDA(cudaMemcpyAsync(e->tr->grad.as<float>(), host, (size_t)count * 4, cudaMemcpyHostToDevice, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  ADP_CATCH
+}
+
 int adp_train_get_grad(adp_engine *e, const char *layer_name, float *kernel, int64_t kernel_elems, float *bias, int64_t nbias) {
   ADP_TRY
   ADP_REQUIRE(e && layer_name, "null argument");

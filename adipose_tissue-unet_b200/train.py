@@ -1,0 +1,150 @@
+"""Data-parallel training step and the reference's learning-rate schedule.
+
+One process per GPU.  A step is the engine's forward -> backward -> apply (include/adipose_b200.h, adp_train_*)
+with two exchanges between ranks:
+
+* six float64 loss sums before backward (``dice_mode="global"``): the reference's Dice term is defined over the
+  WHOLE batch (train_adipose_unet_v3.py:217-225), so the exact data-parallel equivalent of a single-GPU step on the
+  concatenated batch needs sum(y*p), sum(y), sum(p) over all ranks before dL/dp is formed.  ``dice_mode="replica"``
+  skips this exchange and averages per-replica gradients instead (what wrapping the reference in a DP strategy does);
+* one all-reduce (sum) of the flat fp32 gradient buffer (8.5 M parameters, 34 MB) before the optimizer, done by
+  ``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the CPU tests) directly on the engine's device
+  buffer and stream - PyTorch is only the collective plumbing here.
+
+Nothing in this file computes on the CPU: without the CUDA library ``api.Engine`` raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+
+
+class _CudaView:
+    """__cuda_array_interface__ over a raw device pointer so torch can alias the engine's gradient buffer."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class DataParallelTrainer:
+    """Drives one engine per rank.  ``dist`` is ``torch.distributed`` (initialised) or None for a single rank.
+
+    step(x, y, lr) == Keras ``train_step`` on the global batch (train_adipose_unet_v3.py:1316-1324, 1413-1421):
+    returns {loss, bce, dice_loss, dice_coef} of the GLOBAL batch in dice_mode="global".  The three phases
+    (forward_sums / backward / apply) are public so a test can interleave several in-process 'ranks'."""
+
+    def __init__(self, engine, batch: int, size: int, *, dist=None, rank: int = 0, world: int = 1,
+                 dropout_rate: float = 0.3, seed: int = 865, optimizer: str = "adam", weight_decay: float = 0.01,
+                 dice_mode: str = "global", freeze_encoder: bool = False):
+        assert dice_mode in ("global", "replica")
+        self.engine, self.dist, self.rank, self.world = engine, dist, rank, world
+        self.batch, self.size = batch, size
+        self.optimizer, self.weight_decay = optimizer, weight_decay
+        self.dice_mode, self.freeze_encoder = dice_mode, freeze_encoder
+        # per-rank dropout stream: the same seed would drop the same units on every replica
+        engine.train_begin(batch, size, dropout_rate, seed + 7919 * rank)
+        self._grad_t = None
+        self._torch_stream = None
+        self.allreduce_bytes = 4 * engine.train_grad_buffer()[1]
+        if dist is not None and world > 1:
+            self._bind_collective()
+
+    # -- plumbing ---------------------------------------------------------------------------------------------
+    def _bind_collective(self):
+        import torch
+        if self.dist.get_backend() == "nccl":
+            ptr, n = self.engine.train_grad_buffer()
+            dev = getattr(self.engine, "device", 0)
+            self._grad_t = torch.as_tensor(_CudaView(ptr, n), device=f"cuda:{dev}")
+            sp = self.engine.stream_ptr()
+            self._torch_stream = torch.cuda.ExternalStream(sp, device=dev) if sp else None
+
+    def _allreduce_sums(self, sums: np.ndarray) -> np.ndarray:
+        if self.dist is None or self.world == 1:
+            return sums
+        import torch
+        t = torch.tensor(np.asarray(sums, dtype=np.float64), dtype=torch.float64,
+                         device=self._grad_t.device if self._grad_t is not None else "cpu")
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def _allreduce_grad(self):
+        if self.dist is None or self.world == 1:
+            return
+        import torch
+        if self._grad_t is not None:
+            # enqueued behind the backward kernels on the engine's own stream, the optimizer kernel behind it:
+            # no host synchronisation inside the step
+            if self._torch_stream is not None:
+                with torch.cuda.stream(self._torch_stream):
+                    self.dist.all_reduce(self._grad_t)
+            else:                    # engine runs on the legacy default stream
+                self.engine.synchronize()
+                self.dist.all_reduce(self._grad_t)
+                torch.cuda.synchronize(self._grad_t.device)
+            return
+        g = torch.from_numpy(self.engine.grad_to_host())     # host-staged collective (gloo)
+        self.dist.all_reduce(g)
+        self.engine.grad_from_host(g.numpy())
+
+    # -- phases -----------------------------------------------------------------------------------------------
+    @property
+    def n_local(self) -> int:
+        return self.batch * self.size * self.size
+
+    def forward_sums(self, x, y, dropout_masks=None) -> np.ndarray:
+        return self.engine.train_forward(x, y, dropout_masks)
+
+    def backward(self, sums: np.ndarray, global_sums: Optional[np.ndarray] = None) -> Dict[str, float]:
+        """Backward for the loss the mode defines; returns that loss."""
+        if self.dice_mode == "global":
+            gs = sums if global_sums is None else global_sums
+            n = self.n_local * self.world
+        else:
+            gs, n = sums, self.n_local
+        self.engine.train_backward(gs, n, self.freeze_encoder)
+        return self.engine.train_loss(gs, n)
+
+    def apply(self, lr: float):
+        # global: d(global loss)/d(theta) is the SUM of the ranks' contributions; replica: mean of replica gradients
+        scale = 1.0 if self.dice_mode == "global" else 1.0 / self.world
+        self.engine.train_apply(lr, self.optimizer, grad_scale=scale, weight_decay=self.weight_decay,
+                                freeze_encoder=self.freeze_encoder)
+
+    def step(self, x, y, lr: float, dropout_masks=None) -> Dict[str, float]:
+        sums = self.forward_sums(x, y, dropout_masks)
+        gsums = self._allreduce_sums(sums) if self.dice_mode == "global" else None
+        out = self.backward(sums, gsums)
+        self._allreduce_grad()
+        self.apply(lr)
+        return out
+
+    def close(self):
+        self._grad_t = None
+        self.engine.train_end()
+
+
+def emulated_step(trainers, xs, ys, lr: float, dropout_masks=None):
+    """The same data-parallel step with every 'rank' living in this process (several engines on one device):
+    the two exchanges are done on the host.  Test vehicle for the N>1 arithmetic on a single-GPU box."""
+    sums = [t.forward_sums(x, y, None if dropout_masks is None else dropout_masks[i])
+            for i, (t, x, y) in enumerate(zip(trainers, xs, ys))]
+    gs = np.sum(np.stack(sums), axis=0)
+    outs = [t.backward(s, gs) for t, s in zip(trainers, sums)]
+    total = np.sum(np.stack([t.engine.grad_to_host().astype(np.float64) for t in trainers]), axis=0).astype(np.float32)
+    for t in trainers:
+        t.engine.grad_from_host(total)
+        t.apply(lr)
+    return outs
+
+
+# ---- learning-rate schedule -------------------------------------------------------------------------------------
+def cosine_warmup_lr(epoch: int, max_lr: float, min_lr: float, warmup_epochs: int, total_epochs: int) -> float:
+    """CosineAnnealingWithWarmup.on_epoch_begin (train_adipose_unet_v3.py:393-404), same float64 expression order:
+    linear warm-up (max_lr/warmup)*(epoch+1), then min_lr + 0.5*(max_lr-min_lr)*(1+cos(pi*progress))."""
+    if epoch < warmup_epochs:
+        return (max_lr / warmup_epochs) * (epoch + 1)
+    progress = (epoch - warmup_epochs) / (total_epochs - warmup_epochs)
+    return float(min_lr + 0.5 * (max_lr - min_lr) * (1 + np.cos(np.pi * progress)))

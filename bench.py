@@ -273,6 +273,34 @@ def run_ours(args, rank, world, local_rank):
                     "avg_launch_ms": cms / max(cl, 1), "share_of_step": cms / tot,
                     "algorithmic_flops_per_step": cfl}
 
+    # secondary measurement: configs[3], the data-parallel training step (forward with dropout, BCE+Dice, backward,
+    # NCCL all-reduce of the flat fp32 gradient, Keras Adam), batch 8 per GPU, inputs resident in HBM.
+    # Runs last: it updates the engine's parameters.
+    train_res = None
+    if args.train_batch > 0:
+        from adipose_unet_b200 import train as T
+        import adipose_unet_b200.layers as L
+        nb = args.train_batch
+        xt = ((tiles_d[:nb] - mean) / (std + 1e-10)).contiguous()
+        yt = masks_d[:nb].to(torch.float32).contiguous()
+        torch.cuda.synchronize()
+        tr = T.DataParallelTrainer(eng, nb, TILE, dist=dist, rank=rank, world=world, dropout_rate=0.3,
+                                   dice_mode="replica" if args.train_dice == "replica" else "global")
+        for _ in range(2):
+            out = tr.step(xt, yt, 1e-4)
+        l0t = eng.launch_count()
+        tsteps = max(args.steps, 3)
+        tdev, twall, out = timed(lambda: tr.step(xt, yt, 1e-4), tsteps)
+        tl = eng.launch_count() - l0t
+        train_res = {"workload": "configs[3]: U-Net training step, 1024^2 tiles, batch %d/GPU, %s, dropout 0.3, BCE+Dice, Adam" % (nb, args.precision),
+                     "tiles_per_s": nb * world * tsteps / tdev, "ms_per_step": tdev / tsteps * 1e3,
+                     "wall_ms_per_step": twall / tsteps * 1e3, "steps": tsteps,
+                     "tflops_3x_forward": 3 * L.forward_flops(TILE) * nb * world * tsteps / tdev / 1e12,
+                     "loss_last": out["loss"], "dice_mode": tr.dice_mode, "gpu_launches": int(tl),
+                     "collective": ("NCCL all-reduce of %d gradient bytes per step on the engine stream + 48-byte loss-sum all-reduce" % tr.allreduce_bytes)
+                     if world > 1 else "none (1 GPU)"}
+        tr.close()
+
     if rank == 0:
         tiles_total = BATCH_TILES * world * args.steps
         value = tiles_total / dev_s
@@ -306,6 +334,8 @@ def run_ours(args, rank, world, local_rank):
                 "wall_ms_per_step": wall_s / args.steps * 1e3}
         if wsi_res is not None:
             line["wsi"] = wsi_res
+        if train_res is not None:
+            line["train"] = train_res
         if not args.no_cpu_baseline and world >= 1:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
@@ -343,6 +373,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16_simt"])
     ap.add_argument("--max-forwards", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=8, help="tiles per GPU of the secondary training-step run (0 = skip)")
+    ap.add_argument("--train-dice", default="global", choices=["global", "replica"])
     ap.add_argument("--wsi-size", type=int, default=8192, help="side of the synthetic slide of the secondary WSI run (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -197,6 +197,10 @@ int adp_train_loss(const double sums[6], int64_t n_px, double out[4]);
 int adp_train_backward(adp_engine *e, const double sums[6], int64_t n_px_global, int freeze_encoder);
 /* device pointer + element count of the flat fp32 gradient (Keras order: per layer kernel HWIO, bias) */
 int adp_train_grad_buffer(adp_engine *e, float **dev_ptr, int64_t *count);
+/* whole flat gradient to / from host memory (count must equal the parameter count): the staging path of a
+ * data-parallel caller whose collective runs on host buffers (gloo), and of tests that emulate ranks in-process */
+int adp_train_grad_read(adp_engine *e, float *host, int64_t count);
+int adp_train_grad_write(adp_engine *e, const float *host, int64_t count);
 int adp_train_get_grad(adp_engine *e, const char *layer, float *kernel_hwio, int64_t kernel_elems, float *bias, int64_t nbias);
 int adp_train_probs(adp_engine *e, float *out, int64_t out_elems);          /* probabilities of the last forward */
 /* theta <- optimizer(theta, grad_scale * grad); Keras epsilon placement; beta1/beta2/eps <= 0 select 0.9/0.999/1e-7 */
