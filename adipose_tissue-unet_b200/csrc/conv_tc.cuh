@@ -28,6 +28,14 @@
 // on the low-resolution grid each output parity (py,px) is a 2x2-tap conv whose weights are sums
 // of the 3x3 taps that land on the same source pixel — 4/9 of the MMA work and no upsampled tensor.
 //
+// ky-stacked issue (KYS, dilation 1 and N <= 128): with N = 48 or 96 one MMA needs 44 / 56 shared-memory wavefronts
+// (128 B each: 4 KB of A + N*32 B of B) but only N/2 = 24 / 48 tensor cycles, i.e. the operand read port, not the tensor
+// pipe, bounds the layer (ncu: l1tex__data_pipe_tc_wavefronts_mem_shared 65-81 %, tensor pipe 35-70 %).  Input row i of
+// an item contributes to the output rows o = i-2, i-1, i (vertical taps +1, 0, -1) and the accumulators of consecutive
+// output rows are consecutive TMEM column ranges, so ONE MMA with the three vertical taps stacked along N
+// (B = [W(+1) | W(0) | W(-1)], N' = 3N) adds row i into all three at once: T+2 reads of A per horizontal tap instead of
+// 3T.  The first (chunk 0, kx 0) pass is issued unstacked because the accumulate flag is per instruction.
+//
 // Warp roles (320 threads): w0 producer (TMA + bulk copy), w1 MMA issuer (one elected lane) and
 // TMEM allocator, w2-9 epilogue: two warps per TMEM lane quarter, software-pipelined
 // tcgen05.ld -> bias -> ReLU -> bf16 -> coalesced row-planar stores.  Fused epilogues:
@@ -74,12 +82,30 @@ struct ConvTcParams {
   __nv_bfloat16 *pool_out;       // pooled row-planar tensor [nb][Hout/2][pool_cgs][Wout/2][8], EPI_POOL
   int pool_cgs, pool_cg0;
   int dbg;                       // reserved for kernel experiments
+  // ky-stacked issue (template KYS): the vertical taps of one horizontal tap are stacked along GEMM-N in the weight
+  // block ([kx][cin/8][KY*N][8], vertical taps in DESCENDING order), tap_xs[kx] is the pixel shift of horizontal tap kx
+  int kys;
+  uint32_t idesc_stack[3];       // instruction descriptors for N, 2N, 3N
   // backward use (data-gradient twin, EPI_STORE only): out = (acc + resid) * [mask > 0] * mask_scale, where resid and
   // mask are tensors with exactly the layout of `out` (gradient fan-in of Add / ReLU' of the producing layer)
   const __nv_bfloat16 *resid;
   const __nv_bfloat16 *mask;
   float mask_scale;
 };
+
+// index of weight (tap t, row n of variant block) inside a (variant, chunk) weight block of `ntaps` taps, channel-group
+// plane g, lane j: plain layout [t][g][N][8], ky-stacked layout [kx][g][KY*N][8] with vertical taps descending
+__host__ __device__ inline size_t tc_block_index(int kys, int ntaps, int N, int t, int g, int n, int j) {
+  if (!kys) return (((size_t)t * 2 + g) * N + n) * 8 + j;
+  const int KY = ntaps == 9 ? 3 : 2;
+  const int kyi = t / KY, kx = t % KY;
+  return ((((size_t)kx * 2 + g) * KY + (KY - 1 - kyi)) * N + n) * 8 + j;
+}
+
+size_t tc_smem_bytes(const ConvTcParams &p) {
+  // stages | mbarriers (2S + 4) + tmem slot | bias (704 floats) | head weights (2*256 + 2 floats)
+  return (size_t)p.S * p.stage_stride + (2 * p.S + 6) * 8 + (704 + 520) * 4;
+}
 
 constexpr int kTcThreads = 320;
 constexpr int EPI_STORE = 0, EPI_HEAD = 1, EPI_POOL = 2;
@@ -134,7 +160,7 @@ ADP_DEVINL void store16_bf16(__nv_bfloat16 *o, size_t plane, const float (&f)[16
   *reinterpret_cast<uint4 *>(o + plane) = *reinterpret_cast<uint4 *>(h + 8);
 }
 
-template <int NTAPS, int T>
+template <int NTAPS, int T, bool KYS = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -201,6 +227,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
       // descriptor = hi (SBO = 128 B, version 1) : lo (start >> 4 | LBO >> 4 << 16); only the start moves
       const uint32_t desc_hi = (128u >> 4) | (1u << 14);
       const uint32_t a_lo0 = ((plane_a >> 4) << 16), b_lo0 = ((plane_b >> 4) << 16);
+      const uint32_t row_step = (2u * plane_a) >> 4;          // next output row = next row slot
+      const uint32_t smem0 = ptx::smem_u32(smem);
+      const uint32_t n_cols = (uint32_t)p.N;
+      if constexpr (KYS) {
+        constexpr int KY = (NTAPS == 9) ? 3 : 2, KX = KY;
+        const uint32_t plane_bs = (uint32_t)(KY * p.N) * 16u;  // stacked B: KY*N rows per channel-group plane
+        const uint32_t bs_lo0 = ((plane_bs >> 4) << 16);
+        const uint32_t n16 = (uint32_t)p.N;                    // N rows * 16 B, >> 4
+        uint32_t a_xs[KX], b_blk[KX];
+#pragma unroll
+        for (int kx = 0; kx < KX; ++kx) {
+          a_xs[kx] = (uint32_t)p.tap_xs[kx];                   // pixels == 16-byte units
+          b_blk[kx] = (p.a_bytes + (uint32_t)kx * 2u * plane_bs) >> 4;
+        }
+        const uint32_t id1 = p.idesc_stack[0], id2 = p.idesc_stack[1], id3 = p.idesc_stack[2];
+        int it = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+          const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+          ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3);
+          ptx::tc_fence_after();
+          const uint32_t d0 = tmem_base + (uint32_t)buf * (uint32_t)T * n_cols;
+          const uint32_t v_off = (uint32_t)p.var[item % p.nvar].xs_add;
+          for (int c = 0; c < p.nchunks; ++c) {
+            ptx::mbar_wait(&full[st], ph, 4);
+            ptx::tc_fence_after();
+            const uint32_t s_lo = ((smem0 + (uint32_t)st * p.stage_stride) & 0x3FFFFu) >> 4;
+            const uint32_t sa_lo = s_lo + v_off;
+#pragma unroll
+            for (int kx = 0; kx < KX; ++kx) {
+              if (kx == 0 && c == 0) {
+                // first touch of every accumulator row: one MMA per (output row, vertical tap), overwrite on the first
+#pragma unroll
+                for (int o = 0; o < T; ++o)
+#pragma unroll
+                  for (int kyi = 0; kyi < KY; ++kyi) {
+                    const uint64_t ad = ((uint64_t)desc_hi << 32) |
+                                        (uint64_t)(a_lo0 | (sa_lo + a_xs[0] + (uint32_t)(o + kyi) * row_step));
+                    const uint64_t bd = ((uint64_t)desc_hi << 32) |
+                                        (uint64_t)(bs_lo0 | (s_lo + b_blk[0] + (uint32_t)(KY - 1 - kyi) * n16));
+                    ptx::mma_f16_ss(d0 + (uint32_t)o * n_cols, ad, bd, id1, (uint32_t)(kyi != 0));
+                  }
+              } else {
+#pragma unroll
+                for (int i = 0; i < T + KY - 1; ++i) {
+                  const int o_lo = (i - (KY - 1)) > 0 ? (i - (KY - 1)) : 0;
+                  const int o_hi = i < (T - 1) ? i : (T - 1);
+                  const int cnt = o_hi - o_lo + 1;                       // 1..KY stacked vertical taps
+                  const int sl = KY - 1 - i + o_lo;                      // first stacked tap slot
+                  const uint64_t ad = ((uint64_t)desc_hi << 32) |
+                                      (uint64_t)(a_lo0 | (sa_lo + a_xs[kx] + (uint32_t)i * row_step));
+                  const uint64_t bd = ((uint64_t)desc_hi << 32) |
+                                      (uint64_t)(bs_lo0 | (s_lo + b_blk[kx] + (uint32_t)sl * n16));
+                  ptx::mma_f16_ss(d0 + (uint32_t)o_lo * n_cols, ad, bd, cnt == 1 ? id1 : (cnt == 2 ? id2 : id3), 1u);
+                }
+              }
+            }
+            ptx::mma_commit(&empty[st]);
+            if (++st == p.S) { st = 0; ph ^= 1; }
+          }
+          ptx::mma_commit(&acc_full[buf]);
+        }
+      } else {
       uint32_t a_off[NTAPS], b_off[NTAPS];                    // byte offsets within a stage, >> 4
 #pragma unroll
       for (int t = 0; t < NTAPS; ++t) {
@@ -208,10 +296,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
                     (uint32_t)p.tap_xs[t] * 16u) >> 4;
         b_off[t] = (p.a_bytes + (uint32_t)t * 2u * plane_b) >> 4;
       }
-      const uint32_t row_step = (2u * plane_a) >> 4;          // next output row = next row slot
-      const uint32_t smem0 = ptx::smem_u32(smem);
       const uint32_t idesc = p.idesc;
-      const uint32_t n_cols = (uint32_t)p.N;
       int it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
         const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
@@ -237,6 +322,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
           if (++st == p.S) { st = 0; ph ^= 1; }
         }
         ptx::mma_commit(&acc_full[buf]);
+      }
       }
     }
   } else {

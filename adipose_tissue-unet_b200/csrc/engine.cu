@@ -148,6 +148,7 @@ struct adp_engine {
   int64_t launches = 0;
   int dbg = 0;
   bool fuse_head = true, fuse_pool = true;   // tcgen05 path only
+  bool kys = true;                           // ky-stacked MMA issue for the N <= 128 layers
   bool wgrad_simt = false, dgrad_simt = false;   // bf16 training: CUDA-core cross-check of the tcgen05 backward kernels
 
   template <typename F> void launch(const char *kind, double flops, double bytes, F &&f) {
@@ -214,7 +215,7 @@ const char *const kAllNames[22] = {"down1_conv1", "down1_conv2", "down2_conv1", 
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 plan: everything of ConvTcParams that does not depend on the tile size
-void plan_tc(ConvLayer &L) {
+void plan_tc(ConvLayer &L, bool allow_kys = true) {
   ConvTcParams &p = L.tc;
   memset(&p, 0, sizeof(p));
   const int N = (L.cout_pad <= 256) ? L.cout_pad : L.cout_pad / 2;
@@ -266,15 +267,24 @@ void plan_tc(ConvLayer &L) {
   p.idesc = ptx::make_idesc(128, N, 1);
   p.relu = 1;
   for (int v = 0; v < p.nvar; ++v) p.var[v].wbase = v * p.nchunks;
-}
-
-size_t tc_smem_bytes(const ConvTcParams &p) {
-  // stages | mbarriers (2S + 4) + tmem slot | bias (704 floats) | head weights (2*256 + 2 floats)
-  return (size_t)p.S * p.stage_stride + (2 * p.S + 6) * 8 + (704 + 520) * 4;
+  // ky-stacked issue (conv_tc.cuh): dilation 1, at least two vertical taps fit GEMM-N <= 256
+  const int KY = L.up ? 2 : 3;
+  p.kys = (allow_kys && L.dil == 1 && T >= 2 && std::min(KY, T) * N <= 256) ? 1 : 0;
+  if (p.kys) {
+    for (int kx = 0; kx < KY; ++kx) p.tap_xs[kx] = L.up ? 7 + kx : p.margin8 * 8 + kx - 1;
+    for (int k = 0; k < 3; ++k) p.idesc_stack[k] = ((k + 1) * N <= 256) ? ptx::make_idesc(128, (k + 1) * N, 1) : 0u;
+  }
 }
 
 typedef void (*ConvTcKernel)(const CUtensorMap, const ConvTcParams);
-ConvTcKernel tc_kernel_for(int ntaps, int T) {
+ConvTcKernel tc_kernel_for(int ntaps, int T, int kys) {
+  if (kys) {
+    if (ntaps == 9 && T == 4) return conv_tc_kernel<9, 4, true>;
+    if (ntaps == 9 && T == 2) return conv_tc_kernel<9, 2, true>;
+    if (ntaps == 4 && T == 4) return conv_tc_kernel<4, 4, true>;
+    if (ntaps == 4 && T == 2) return conv_tc_kernel<4, 2, true>;
+    throw Error(ADP_EINVAL, "no ky-stacked tcgen05 conv instantiation for this (taps, rows) pair");
+  }
   if (ntaps == 9) {
     if (T == 4) return conv_tc_kernel<9, 4>;
     if (T == 2) return conv_tc_kernel<9, 2>;
@@ -316,7 +326,7 @@ void pack_layer(adp_engine *e, ConvLayer &L) {
   ADP_CUDA(cudaMemcpy(L.bias.p, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
   if (e->prec != ADP_PREC_BF16) return;
 
-  plan_tc(L);
+  plan_tc(L, e->kys);
   const ConvTcParams &p = L.tc;
   std::vector<float> w32 = padded_weights(L, h, false);   // sum taps in fp32, round once
   auto W = [&](int t, int ci, int co) -> float { return w32[((size_t)t * L.cin_pad + ci) * L.cout_pad + co]; };
@@ -326,7 +336,7 @@ void pack_layer(adp_engine *e, ConvLayer &L) {
   for (int v = 0; v < p.nvar; ++v)
     for (int c = 0; c < p.nchunks; ++c)
       for (int t = 0; t < p.ntaps; ++t) {
-        __nv_bfloat16 *dst = pk.data() + (((size_t)p.var[v].wbase + c) * p.ntaps + t) * blk;
+        __nv_bfloat16 *base = pk.data() + ((size_t)p.var[v].wbase + c) * p.ntaps * blk;
         for (int g = 0; g < 2; ++g)
           for (int n = 0; n < N; ++n)
             for (int j = 0; j < 8; ++j) {
@@ -349,7 +359,7 @@ void pack_layer(adp_engine *e, ConvLayer &L) {
                   val = W(t, ci, p.var[v].out_cg * 8 + n);
                 }
               }
-              dst[((size_t)g * N + n) * 8 + j] = __float2bfloat16_rn(val);
+              base[tc_block_index(p.kys, p.ntaps, N, t, g, n, j)] = __float2bfloat16_rn(val);
             }
       }
   L.w_tc.ensure(pk.size() * 2);
@@ -484,7 +494,7 @@ void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label,
   const int nitems = nb * p.nty * p.ntx * p.nvar;
   const int grid = std::min(nitems, e->num_sms);
   const size_t smem = tc_smem_bytes(p);
-  ConvTcKernel kern = tc_kernel_for(p.ntaps, p.T);
+  ConvTcKernel kern = tc_kernel_for(p.ntaps, p.T, p.kys);
   e->launch(label.c_str(), fl, by, [&] { kern<<<grid, kTcThreads, smem, e->stream>>>(tm, p); });
 }
 
@@ -561,8 +571,8 @@ template <typename T> void forward_t(adp_engine *e, const Acts &A, int S, const 
   const float sd_f = (float)((double)std_ + 1e-10);
   {
     auto out = view<T>(*A.d1a, S, S, cp[0], 0, cp[0]);
-    dim3 grid(cdiv(S, 32), cdiv(S, 8), nfw), block(32, 8);
-    const size_t smem = (size_t)10 * cp[0] * 4;
+    dim3 grid(cdiv(S, 32), cdiv(S, 32), nfw), block(32, 8);
+    const size_t smem = ((size_t)10 * cp[0] + 34 * 34) * 4;
     e->launch("first_conv", 2.0 * nfw * S * S * 9.0 * e->c[0], (double)nfw * S * S * (4 + cp[0] * sizeof(T)), [&] {
       first_conv_kernel<T><<<grid, block, smem, e->stream>>>(s, e->fwt_tile.as<int>(), e->fwt_op.as<int>(), S, mean_f, sd_f,
                                                             e->w_first.as<float>(), e->b_first.as<float>(), out);
@@ -813,7 +823,9 @@ int adp_create(int device, int precision, int init_nb, int max_forwards, adp_eng
   }
   for (int nt : {9, 4})
     for (int T : {4, 2, 1})
-      ADP_CUDA(cudaFuncSetAttribute(tc_kernel_for(nt, T), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      for (int kys : {0, 1})
+        if (!kys || T >= 2)
+          ADP_CUDA(cudaFuncSetAttribute(tc_kernel_for(nt, T, kys), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   ADP_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (const char *d = getenv("ADP_TC_DEBUG")) e->dbg = atoi(d);
   build_layers(e.get());
@@ -862,6 +874,7 @@ int adp_set_option(adp_engine *e, const char *key, int value) {
   else if (k == "wgrad_simt") e->wgrad_simt = value != 0;
   else if (k == "dgrad_simt") e->dgrad_simt = value != 0;
   else if (k == "debug") e->dbg = value;
+  else if (k == "kys") { e->kys = value != 0; e->packed = false; }   // ky-stacked MMA issue (conv_tc.cuh); re-plans on next use
   else throw Error(ADP_EINVAL, "unknown option " + k);
   ADP_CATCH
 }

@@ -75,7 +75,11 @@ template <typename T> ADP_DEVINL void load8(const T *i, float *a) {
   }
 }
 
-// block = (32, 8): a warp owns 32 consecutive pixels of one row
+// block = (32, 8), output tile = 32 columns x 32 rows: the normalised (and dihedrally transformed) 34 x 34 input window
+// is staged once in shared memory (one z-score division per input pixel instead of nine), then a warp owns 32
+// consecutive columns of FOUR rows so that every weight read from shared memory feeds four pixels (288 FMA per 18
+// LDS.128) and every store is 512 contiguous bytes per channel group.
+constexpr int kFcRows = 4;
 template <typename T>
 __global__ void __launch_bounds__(256)
 first_conv_kernel(FirstConvSrc src, const int *__restrict__ fw_tile, const int *__restrict__ fw_op,
@@ -84,41 +88,57 @@ first_conv_kernel(FirstConvSrc src, const int *__restrict__ fw_tile, const int *
   extern __shared__ float sm[];
   float *ws = sm;                 // 9*C
   float *bs = sm + 9 * out.C;     // C
+  float *win = bs + out.C;        // 34 x 34 normalised input window ('same' zero padding applies to the normalised image)
   const int tid = threadIdx.x + threadIdx.y * 32;
   for (int i = tid; i < 9 * out.C; i += 256) ws[i] = w[i];
   for (int i = tid; i < out.C; i += 256) bs[i] = bias[i];
-  __syncthreads();
-  const int x = blockIdx.x * 32 + threadIdx.x;
-  const int y = blockIdx.y * 8 + threadIdx.y;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
   const int f = blockIdx.z;
-  if (x >= S || y >= S) return;
   const int tile = fw_tile[f], op = fw_op[f];
-  float v[9];
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      int i = y + ky - 1, j = x + kx - 1;
-      float val = 0.f;    // 'same' zero padding applies to the normalised image
-      if (i >= 0 && i < S && j >= 0 && j < S) {
-        int si, sj;
-        d4_src(op, i, j, S, si, sj);
-        float raw = first_conv_fetch(src, tile, S, si, sj);
-        val = __fdiv_rn(__fsub_rn(raw, mean_f), sd_f);
-      }
-      v[ky * 3 + kx] = val;
+  for (int i = tid; i < 34 * 34; i += 256) {
+    const int wy = i / 34, wx = i - wy * 34;
+    const int yy = y0 + wy - 1, xx = x0 + wx - 1;
+    float val = 0.f;
+    if (yy >= 0 && yy < S && xx >= 0 && xx < S) {
+      int si, sj;
+      d4_src(op, yy, xx, S, si, sj);
+      const float raw = first_conv_fetch(src, tile, S, si, sj);
+      val = __fdiv_rn(__fsub_rn(raw, mean_f), sd_f);
     }
+    win[i] = val;
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x;
+  const int yb = y0 + threadIdx.y * kFcRows;
+  if (x >= S || yb >= S) return;
+  float v[kFcRows + 2][3];
+#pragma unroll
+  for (int r = 0; r < kFcRows + 2; ++r)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) v[r][kx] = win[(threadIdx.y * kFcRows + r) * 34 + threadIdx.x + kx];
   for (int g = 0; g < out.C / 8; ++g) {
-    float a[8];
+    float a[kFcRows][8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) a[c] = bs[g * 8 + c];
+    for (int r = 0; r < kFcRows; ++r)
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
+      for (int c = 0; c < 8; ++c) a[r][c] = bs[g * 8 + c];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) a[c] = fmaf(v[t], ws[t * out.C + g * 8 + c], a[c]);
+    for (int t = 0; t < 9; ++t) {
+      const float4 w0 = *reinterpret_cast<const float4 *>(ws + t * out.C + g * 8);
+      const float4 w1 = *reinterpret_cast<const float4 *>(ws + t * out.C + g * 8 + 4);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-    for (int c = 0; c < 8; ++c) a[c] = fmaxf(a[c], 0.f);
-    store8<T>(out.p + out.at(f, y, g, x), a);
+      for (int r = 0; r < kFcRows; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[r][c] = fmaf(v[r + t / 3][t % 3], wv[c], a[r][c]);
+    }
+#pragma unroll
+    for (int r = 0; r < kFcRows; ++r) {
+      if (yb + r >= S) break;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[r][c] = fmaxf(a[r][c], 0.f);
+      store8<T>(out.p + out.at(f, yb + r, g, x), a[r]);
+    }
   }
 }
 

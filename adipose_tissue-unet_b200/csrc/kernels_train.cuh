@@ -376,7 +376,7 @@ __global__ void round_bf16_kernel(float *__restrict__ p, size_t n) {
 // that read the same source pixel (summed in fp32, rounded once).
 __global__ void __launch_bounds__(256)
 pack_tc_kernel(const float *__restrict__ wp, __nv_bfloat16 *__restrict__ dst, int nvar, int nchunks, int ntaps, int N,
-               int cin_pad, int cout_pad, int up) {
+               int cin_pad, int cout_pad, int up, int kys) {
   const size_t blk = (size_t)16 * N;
   const size_t total = (size_t)nvar * nchunks * ntaps * blk;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -403,7 +403,9 @@ pack_tc_kernel(const float *__restrict__ wp, __nv_bfloat16 *__restrict__ dst, in
         val = wp[((size_t)t * cin_pad + ci) * cout_pad + v * N + n];
       }
     }
-    dst[i] = __float2bfloat16_rn(val);
+    // i enumerates the plain layout; the ky-stacked layout permutes positions inside the (variant, chunk) block
+    const size_t o = kys ? ((size_t)v * nchunks + c) * ntaps * blk + tc_block_index(1, ntaps, N, t, g, n, j) : i;
+    dst[o] = __float2bfloat16_rn(val);
   }
 }
 

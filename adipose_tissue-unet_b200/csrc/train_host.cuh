@@ -100,10 +100,10 @@ void repack_from_theta(adp_engine *e) {
     pad_kernel_weights<<<g, 256, 0, e->stream>>>(th + T.koff, T.wT.as<float>(), 9, L.cin, L.cout, L.cin_pad, L.cout_pad, L.skip, sp, 0, 1);
     if (e->prec == ADP_PREC_BF16) {  // pack from the unrounded padded copies (parity taps are summed in fp32)
       pack_tc_kernel<<<ew_grid(e, np * 2), 256, 0, e->stream>>>(L.w_simt.as<float>(), L.w_tc.as<__nv_bfloat16>(), L.tc.nvar, L.tc.nchunks,
-                                                               L.tc.ntaps, L.tc.N, L.cin_pad, L.cout_pad, L.up ? 1 : 0);
+                                                               L.tc.ntaps, L.tc.N, L.cin_pad, L.cout_pad, L.up ? 1 : 0, L.tc.kys);
       const ConvLayer &W = T.twin;
       pack_tc_kernel<<<ew_grid(e, np * 2), 256, 0, e->stream>>>(T.wT.as<float>(), W.w_tc.as<__nv_bfloat16>(), W.tc.nvar, W.tc.nchunks,
-                                                               W.tc.ntaps, W.tc.N, W.cin_pad, W.cout_pad, 0);
+                                                               W.tc.ntaps, W.tc.N, W.cin_pad, W.cout_pad, 0, W.tc.kys);
     }
     if (bf) {
       round_bf16_kernel<<<ew_grid(e, np), 256, 0, e->stream>>>(L.w_simt.as<float>(), np);
@@ -198,7 +198,7 @@ void train_alloc(adp_engine *e, int nb, int S, float dropout_rate, uint64_t seed
       ConvLayer &W = tr->tl[i].twin;
       W.name = "dgrad/" + L.name; W.cin = L.cout; W.cout = L.cin; W.dil = L.dil; W.up = false; W.skip = 0;
       W.cin_pad = L.cout_pad; W.cout_pad = L.cin_pad;
-      plan_tc(W);
+      plan_tc(W, e->kys);
       W.w_tc.ensure((size_t)W.tc.nvar * W.tc.nchunks * W.tc.ntaps * 16 * W.tc.N * 2);
       W.tc_ready = true;
       plan_wgrad_tc(e, L, tr->tl[i].wg);

@@ -48,18 +48,22 @@ class DataParallelTrainer:
         self._grad_t = None
         self._torch_stream = None
         self.allreduce_bytes = 4 * engine.train_grad_buffer()[1]
+        self.collective_path = "none"
         if dist is not None and world > 1:
             self._bind_collective()
 
     # -- plumbing ---------------------------------------------------------------------------------------------
     def _bind_collective(self):
         import torch
-        if self.dist.get_backend() == "nccl":
+        if "nccl" in str(self.dist.get_backend()):      # "nccl" or a mixed "cpu:gloo,cuda:nccl" group
             ptr, n = self.engine.train_grad_buffer()
             dev = getattr(self.engine, "device", 0)
             self._grad_t = torch.as_tensor(_CudaView(ptr, n), device=f"cuda:{dev}")
             sp = self.engine.stream_ptr()
             self._torch_stream = torch.cuda.ExternalStream(sp, device=dev) if sp else None
+            self.collective_path = "nccl on the engine's device buffer"
+        else:
+            self.collective_path = "host-staged (%s)" % self.dist.get_backend()
 
     def _allreduce_sums(self, sums: np.ndarray) -> np.ndarray:
         if self.dist is None or self.world == 1:

@@ -298,7 +298,7 @@ def run_ours(args, rank, world, local_rank):
                      "tflops_3x_forward": 3 * L.forward_flops(TILE) * nb * world * tsteps / tdev / 1e12,
                      "loss_last": out["loss"], "dice_mode": tr.dice_mode, "gpu_launches": int(tl),
                      "collective": ("NCCL all-reduce of %d gradient bytes per step on the engine stream + 48-byte loss-sum all-reduce" % tr.allreduce_bytes)
-                     if world > 1 else "none (1 GPU)"}
+                     if world > 1 else "none (1 GPU)", "collective_path": tr.collective_path}
         tr.close()
 
     if rank == 0:

@@ -36,7 +36,6 @@ for r in rows:
 print(f"profiled step: {tot:.1f} ms in {sum(r['launches'] for r in rows)} launches")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
     print(f"  {k:28s} {a['ms']:8.2f} ms {100*a['ms']/tot:5.1f}%  n={a['n']:3d}  {a['flops']/max(a['ms'],1e-9)/1e9:8.1f} TFLOP/s {a['bytes']/max(a['ms'],1e-9)/1e6:8.1f} GB/s")
-sys.exit(0)
 print("per layer (conv kernels):")
 for r in sorted(rows, key=lambda r: -r["ms"]):
     if "/" in r["name"]:
