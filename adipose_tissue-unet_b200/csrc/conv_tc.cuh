@@ -81,7 +81,8 @@ struct ConvTcParams {
   float *prob;                   // [nb][Hout][Wout] fp32, EPI_HEAD
   __nv_bfloat16 *pool_out;       // pooled row-planar tensor [nb][Hout/2][pool_cgs][Wout/2][8], EPI_POOL
   int pool_cgs, pool_cg0;
-  int dbg;                       // reserved for kernel experiments
+  int dbg;                       // timing experiments (ADP_TC_DEBUG): see the producer comment and tools/tc_experiments.sh
+  long long *dbg_out;            // dbg & 16: per-CTA role timers (8 x int64 per CTA), tools/tc_timers.sh
   // ky-stacked issue (template KYS): the vertical taps of one horizontal tap are stacked along GEMM-N in the weight
   // block ([kx][cin/8][KY*N][8], vertical taps in DESCENDING order), tap_xs[kx] is the pixel shift of horizontal tap kx
   int kys;
@@ -108,7 +109,7 @@ size_t tc_smem_bytes(const ConvTcParams &p) {
 }
 
 constexpr int kTcThreads = 320;
-constexpr int EPI_STORE = 0, EPI_HEAD = 1, EPI_POOL = 2;
+constexpr int EPI_STORE = 0, EPI_HEAD = 1, EPI_POOL = 2, EPI_BWD = 3;   // EPI_BWD = EPI_STORE with a mask (data-gradient twin)
 
 // Software-pipelined walk over 16-column accumulator units u0, u0+step, ... < uend: the TMEM load
 // of the next unit is in flight while `body` works on the current one.
@@ -160,7 +161,7 @@ ADP_DEVINL void store16_bf16(__nv_bfloat16 *o, size_t plane, const float (&f)[16
   *reinterpret_cast<uint4 *>(o + plane) = *reinterpret_cast<uint4 *>(h + 8);
 }
 
-template <int NTAPS, int T, bool KYS = false>
+template <int NTAPS, int T, bool KYS, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -177,7 +178,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
     const int v = i / p.N;
     sbias[i] = p.bias[p.var[v].bias_off + (i - v * p.N)];
   }
-  if (p.epi_mode == EPI_HEAD) {
+  if constexpr (EPI == EPI_HEAD) {
     for (int i = threadIdx.x; i < 2 * p.N; i += kTcThreads) shead[i] = p.head_w[i];
     if (threadIdx.x < 2) shead[2 * p.N + threadIdx.x] = p.head_b[threadIdx.x];
   }
@@ -200,6 +201,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
     // ---------------- producer: activation boxes (TMA) + weight block (bulk copy) per stage ----------------
     if (ptx::elect_one()) {
       int st = 0; uint32_t ph = 0;
+      long long t_w0 = 0; const long long t_start = clock64();
       const size_t blk_elems = p.b_bytes / 2;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int v = item % p.nvar; int q = item / p.nvar;
@@ -209,14 +211,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
         const __nv_bfloat16 *w0 = p.wpk + (size_t)p.var[v].wbase * blk_elems;
         for (int c = 0; c < p.nchunks; ++c) {
           uint8_t *sa = smem + (size_t)st * p.stage_stride;
-          ptx::mbar_wait(&empty[st], ph ^ 1, 1);
-          ptx::mbar_expect_tx(&full[st], p.a_tx_bytes + p.b_bytes);
-          for (int b = 0; b < p.nbox; ++b)
-            ptx::tma_load_5d(sa + (size_t)b * p.a_box_stride, &tmap, &full[st], 0, xg, c * 2, ys + p.box_dy[b], n);
-          ptx::bulk_load_1d(sa + p.a_bytes, w0 + (size_t)c * blk_elems, p.b_bytes, &full[st]);
+          { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&empty[st], ph ^ 1, 1); if (p.dbg & 16) t_w0 += clock64() - tw; }
+          // p.dbg (ADP_TC_DEBUG, timing experiments only - results are wrong): 2 = weights only for the first item,
+          // 8 = activations only for the first item, 1 = no epilogue stores, 4 = one MMA per stage, 16 = role timers
+          const bool ld_b = !(p.dbg & 2) || item == (int)blockIdx.x, ld_a = !(p.dbg & 8) || item == (int)blockIdx.x;
+          ptx::mbar_expect_tx(&full[st], (ld_a ? p.a_tx_bytes : 0u) + (ld_b ? p.b_bytes : 0u));
+          if (ld_a)
+            for (int b = 0; b < p.nbox; ++b)
+              ptx::tma_load_5d(sa + (size_t)b * p.a_box_stride, &tmap, &full[st], 0, xg, c * 2, ys + p.box_dy[b], n);
+          if (ld_b) ptx::bulk_load_1d(sa + p.a_bytes, w0 + (size_t)c * blk_elems, p.b_bytes, &full[st]);
           if (++st == p.S) { st = 0; ph ^= 1; }
         }
       }
+      if (p.dbg & 16) { p.dbg_out[blockIdx.x * 8 + 0] = t_w0; p.dbg_out[blockIdx.x * 8 + 1] = clock64() - t_start; }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
@@ -230,6 +237,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
       const uint32_t row_step = (2u * plane_a) >> 4;          // next output row = next row slot
       const uint32_t smem0 = ptx::smem_u32(smem);
       const uint32_t n_cols = (uint32_t)p.N;
+      const bool mma_all = !(p.dbg & 4);
+      long long t_m0 = 0, t_m1 = 0, t_m2 = 0; const long long t_mstart = clock64();
       if constexpr (KYS) {
         constexpr int KY = (NTAPS == 9) ? 3 : 2, KX = KY;
         const uint32_t plane_bs = (uint32_t)(KY * p.N) * 16u;  // stacked B: KY*N rows per channel-group plane
@@ -245,12 +254,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
         int it = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
           const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
-          ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3);
+          { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3); if (p.dbg & 16) t_m0 += clock64() - tw; }
           ptx::tc_fence_after();
           const uint32_t d0 = tmem_base + (uint32_t)buf * (uint32_t)T * n_cols;
           const uint32_t v_off = (uint32_t)p.var[item % p.nvar].xs_add;
           for (int c = 0; c < p.nchunks; ++c) {
-            ptx::mbar_wait(&full[st], ph, 4);
+            { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&full[st], ph, 4); if (p.dbg & 16) t_m1 += clock64() - tw; }
             ptx::tc_fence_after();
             const uint32_t s_lo = ((smem0 + (uint32_t)st * p.stage_stride) & 0x3FFFFu) >> 4;
             const uint32_t sa_lo = s_lo + v_off;
@@ -266,7 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
                                         (uint64_t)(a_lo0 | (sa_lo + a_xs[0] + (uint32_t)(o + kyi) * row_step));
                     const uint64_t bd = ((uint64_t)desc_hi << 32) |
                                         (uint64_t)(bs_lo0 | (s_lo + b_blk[0] + (uint32_t)(KY - 1 - kyi) * n16));
-                    ptx::mma_f16_ss(d0 + (uint32_t)o * n_cols, ad, bd, id1, (uint32_t)(kyi != 0));
+                    if (mma_all || (o | kyi) == 0) ptx::mma_f16_ss(d0 + (uint32_t)o * n_cols, ad, bd, id1, (uint32_t)(kyi != 0));
                   }
               } else {
 #pragma unroll
@@ -279,14 +288,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
                                       (uint64_t)(a_lo0 | (sa_lo + a_xs[kx] + (uint32_t)i * row_step));
                   const uint64_t bd = ((uint64_t)desc_hi << 32) |
                                       (uint64_t)(bs_lo0 | (s_lo + b_blk[kx] + (uint32_t)sl * n16));
-                  ptx::mma_f16_ss(d0 + (uint32_t)o_lo * n_cols, ad, bd, cnt == 1 ? id1 : (cnt == 2 ? id2 : id3), 1u);
+                  if (mma_all) ptx::mma_f16_ss(d0 + (uint32_t)o_lo * n_cols, ad, bd, cnt == 1 ? id1 : (cnt == 2 ? id2 : id3), 1u);
                 }
               }
             }
-            ptx::mma_commit(&empty[st]);
+            { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mma_commit(&empty[st]); if (p.dbg & 16) t_m2 += clock64() - tw; }
             if (++st == p.S) { st = 0; ph ^= 1; }
           }
-          ptx::mma_commit(&acc_full[buf]);
+          { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mma_commit(&acc_full[buf]); if (p.dbg & 16) t_m2 += clock64() - tw; }
         }
       } else {
       uint32_t a_off[NTAPS], b_off[NTAPS];                    // byte offsets within a stage, >> 4
@@ -300,12 +309,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
       int it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
         const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
-        ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3);
+        { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3); if (p.dbg & 16) t_m0 += clock64() - tw; }
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)buf * (uint32_t)T * n_cols;
         const uint32_t v_off = (uint32_t)p.var[item % p.nvar].xs_add;   // pixels == 16-byte units
         for (int c = 0; c < p.nchunks; ++c) {
-          ptx::mbar_wait(&full[st], ph, 4);
+          { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&full[st], ph, 4); if (p.dbg & 16) t_m1 += clock64() - tw; }
           ptx::tc_fence_after();
           const uint32_t s_lo = ((smem0 + (uint32_t)st * p.stage_stride) & 0x3FFFFu) >> 4;
           const uint32_t sa_lo = s_lo + v_off;
@@ -315,21 +324,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
 #pragma unroll
             for (int r = 0; r < T; ++r) {
               const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo0 | (sa_lo + a_off[t] + (uint32_t)r * row_step));
-              ptx::mma_f16_ss(d0 + (uint32_t)r * n_cols, ad, bd, idesc, (uint32_t)((c | t) != 0));
+              if (mma_all || (t | r) == 0) ptx::mma_f16_ss(d0 + (uint32_t)r * n_cols, ad, bd, idesc, (uint32_t)((c | t) != 0));
             }
           }
-          ptx::mma_commit(&empty[st]);
+          { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mma_commit(&empty[st]); if (p.dbg & 16) t_m2 += clock64() - tw; }
           if (++st == p.S) { st = 0; ph ^= 1; }
         }
-        ptx::mma_commit(&acc_full[buf]);
+        { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mma_commit(&acc_full[buf]); if (p.dbg & 16) t_m2 += clock64() - tw; }
       }
       }
+      if (p.dbg & 16) { p.dbg_out[blockIdx.x * 8 + 2] = t_m0; p.dbg_out[blockIdx.x * 8 + 3] = t_m1; p.dbg_out[blockIdx.x * 8 + 4] = clock64() - t_mstart; p.dbg_out[blockIdx.x * 8 + 7] = t_m2; }
     }
   } else {
     // ---------------- epilogue (warps 2..9; TMEM lane quarter = warp % 4, two warps per quarter) ----------------
     const int q4 = warp & 3;
     const int half = (warp - 2) >> 2;
     const int NU = p.N >> 4;                                  // 16-column units per accumulator row
+    long long t_e0 = 0; const long long t_estart = clock64();
     int it = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
       const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
@@ -338,8 +349,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
       const int ty = q % p.nty; const int n = q / p.nty;
       const int x = tx * 128 + q4 * 32 + lane;
       const float *sb = sbias + v * p.N;
-      ptx::mbar_wait(&acc_full[buf], acc_ph, 6);
-      ptx::tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * T * p.N);
       const size_t plane = (size_t)p.Wout * 8;
       const int ox = x * p.oscale + p.var[v].ox;
@@ -349,12 +358,91 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
         const size_t orow = ((size_t)n * p.Hout + (size_t)(y * p.oscale + p.var[v].oy)) * p.out_cgs + p.out_cg0 + p.var[v].out_cg;
         return p.out + orow * plane + (size_t)ox * 8;
       };
-      if (p.epi_mode == EPI_STORE) {
+      if constexpr (EPI == EPI_BWD) {
+        // backward twin (data gradient): out = (acc + resid) * [mask > 0] * mask_scale.  The mask words of ALL units this
+        // warp owns are requested before waiting for the accumulator, so their HBM latency overlaps the MMAs of the
+        // item instead of serialising behind every tcgen05.ld (T*NU <= 12 units per quarter for N <= 192: PF = 6 per warp;
+        // wider accumulators finish with unprefetched loads).
+        constexpr int PF = 6;
+        uint4 mk[PF][2];
+        const int UE = T * NU;
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+          const int u = half + 2 * k;
+          mk[k][0] = make_uint4(0, 0, 0, 0); mk[k][1] = mk[k][0];
+          if (u < UE) {
+            const int row = u / NU, cu = u - row * NU;
+            if ((ty * T + row < p.Hin) && (x < p.Win)) {
+              const __nv_bfloat16 *m = p.mask + ((out_row(row) + (size_t)(2 * cu) * plane) - p.out);
+              mk[k][0] = __ldg(reinterpret_cast<const uint4 *>(m));
+              mk[k][1] = __ldg(reinterpret_cast<const uint4 *>(m + plane));
+            }
+          }
+        }
+        { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_full[buf], acc_ph, 6); if (p.dbg & 16) t_e0 += clock64() - tw; }
+        ptx::tc_fence_after();
+        uint32_t acc[2][16];
+        if (half < UE) ptx::tmem_ld16_issue(t0 + (uint32_t)half * 16u, acc[0]);
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+          const int u = half + 2 * k;
+          if (u < UE) {
+            ptx::tmem_ld16_wait(acc[k & 1]);
+            if (u + 2 < UE) ptx::tmem_ld16_issue(t0 + (uint32_t)(u + 2) * 16u, acc[(k + 1) & 1]);
+            const int row = u / NU, cu = u - row * NU;
+            float f[16];
+            bias_relu16(acc[k & 1], sb + cu * 16, p.relu, f);
+            if ((ty * T + row < p.Hin) && (x < p.Win)) {
+              __nv_bfloat16 *o = out_row(row) + (size_t)(2 * cu) * plane;
+              if (p.resid) {
+                float g[16];
+                load16_bf16(p.resid + (o - p.out), plane, g);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] += g[i];
+              }
+              const __nv_bfloat16 *mh0 = reinterpret_cast<const __nv_bfloat16 *>(&mk[k][0]);
+              const __nv_bfloat16 *mh1 = reinterpret_cast<const __nv_bfloat16 *>(&mk[k][1]);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                f[i] = __bfloat162float(mh0[i]) > 0.f ? f[i] * p.mask_scale : 0.f;
+                f[8 + i] = __bfloat162float(mh1[i]) > 0.f ? f[8 + i] * p.mask_scale : 0.f;
+              }
+              store16_bf16(o, plane, f);
+            }
+          }
+        }
+        for (int u = half + 2 * PF; u < UE; u += 2) {
+          const int row = u / NU, cu = u - row * NU;
+          float f[16], m[16];
+          ptx::tmem_ld16(t0 + (uint32_t)u * 16u, f);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] += sb[cu * 16 + i];
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if ((ty * T + row < p.Hin) && (x < p.Win)) {
+            __nv_bfloat16 *o = out_row(row) + (size_t)(2 * cu) * plane;
+            if (p.resid) {
+              load16_bf16(p.resid + (o - p.out), plane, m);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] += m[i];
+            }
+            load16_bf16(p.mask + (o - p.out), plane, m);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = m[i] > 0.f ? f[i] * p.mask_scale : 0.f;
+            store16_bf16(o, plane, f);
+          }
+        }
+      } else {
+      { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_full[buf], acc_ph, 6); if (p.dbg & 16) t_e0 += clock64() - tw; }
+      ptx::tc_fence_after();
+      if constexpr (EPI == EPI_STORE) {
         tmem_pipeline(t0, half, 2, T * NU, [&](int u, const uint32_t (&r)[16]) {
           const int row = u / NU, cu = u - row * NU;
           float f[16];
           bias_relu16(r, sb + cu * 16, p.relu, f);
-          if ((ty * T + row < p.Hin) && (x < p.Win)) {
+          if ((ty * T + row < p.Hin) && (x < p.Win) && !(p.dbg & 1)) {
             __nv_bfloat16 *o = out_row(row) + (size_t)(2 * cu) * plane;
             if (p.resid) {
               float g[16];
@@ -371,7 +459,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
             store16_bf16(o, plane, f);
           }
         });
-      } else if (p.epi_mode == EPI_HEAD) {
+      } else if constexpr (EPI == EPI_HEAD) {
         // rows split between the two warps of a quarter so that one thread sees all channels of its pixel
         for (int row = half; row < T; row += 2) {
           float z0 = 0.f, z1 = 0.f;
@@ -386,7 +474,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
             }
           });
           const int y = ty * T + row;
-          if (y < p.Hin && x < p.Win) {
+          if (y < p.Hin && x < p.Win && !(p.dbg & 1)) {
             z0 += shead[2 * p.N]; z1 += shead[2 * p.N + 1];
             p.prob[((size_t)n * p.Hout + y) * p.Wout + x] = 1.f / (1.f + expf(z0 - z1));
           }
@@ -405,7 +493,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
           float fa[16], fb[16];
           bias_relu16(ra, sb + cu * 16, p.relu, fa);
           bias_relu16(rb, sb + cu * 16, p.relu, fb);
-          const bool live = (ty * T + 2 * k + 1 < p.Hin) && (x < p.Win);
+          const bool live = (ty * T + 2 * k + 1 < p.Hin) && (x < p.Win) && !(p.dbg & 1);
           if (live) {
             store16_bf16(out_row(2 * k) + (size_t)(2 * cu) * plane, plane, fa);
             store16_bf16(out_row(2 * k + 1) + (size_t)(2 * cu) * plane, plane, fb);
@@ -423,10 +511,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
           }
         }
       }
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
     }
+    if ((p.dbg & 16) && warp == 2 && lane == 0) { p.dbg_out[blockIdx.x * 8 + 5] = t_e0; p.dbg_out[blockIdx.x * 8 + 6] = clock64() - t_estart; }
   }
 
   ptx::tc_fence_before();

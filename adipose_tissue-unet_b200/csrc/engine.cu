@@ -277,24 +277,23 @@ void plan_tc(ConvLayer &L, bool allow_kys = true) {
 }
 
 typedef void (*ConvTcKernel)(const CUtensorMap, const ConvTcParams);
-ConvTcKernel tc_kernel_for(int ntaps, int T, int kys) {
-  if (kys) {
-    if (ntaps == 9 && T == 4) return conv_tc_kernel<9, 4, true>;
-    if (ntaps == 9 && T == 2) return conv_tc_kernel<9, 2, true>;
-    if (ntaps == 4 && T == 4) return conv_tc_kernel<4, 4, true>;
-    if (ntaps == 4 && T == 2) return conv_tc_kernel<4, 2, true>;
-    throw Error(ADP_EINVAL, "no ky-stacked tcgen05 conv instantiation for this (taps, rows) pair");
-  }
-  if (ntaps == 9) {
-    if (T == 4) return conv_tc_kernel<9, 4>;
-    if (T == 2) return conv_tc_kernel<9, 2>;
-    if (T == 1) return conv_tc_kernel<9, 1>;
-  } else if (ntaps == 4) {
-    if (T == 4) return conv_tc_kernel<4, 4>;
-    if (T == 2) return conv_tc_kernel<4, 2>;
-    if (T == 1) return conv_tc_kernel<4, 1>;
-  }
-  throw Error(ADP_EINVAL, "no tcgen05 conv instantiation for this (taps, rows) pair");
+// every (taps, rows per item, ky-stacked, epilogue) combination the plans can ask for; nullptr = not instantiated
+ConvTcKernel tc_kernel_lookup(int ntaps, int T, int kys, int epi) {
+#define ADP_TC(NT, TT, KS, EP) if (ntaps == NT && T == TT && kys == KS && epi == EP) return conv_tc_kernel<NT, TT, (KS != 0), EP>;
+#define ADP_TC_ROWS(NT, EP) ADP_TC(NT, 4, 0, EP) ADP_TC(NT, 4, 1, EP) ADP_TC(NT, 2, 0, EP) ADP_TC(NT, 2, 1, EP)
+  ADP_TC_ROWS(9, EPI_STORE) ADP_TC(9, 1, 0, EPI_STORE)
+  ADP_TC_ROWS(4, EPI_STORE) ADP_TC(4, 1, 0, EPI_STORE)
+  ADP_TC_ROWS(9, EPI_HEAD)
+  ADP_TC_ROWS(9, EPI_POOL)
+  ADP_TC_ROWS(9, EPI_BWD) ADP_TC(9, 1, 0, EPI_BWD)
+#undef ADP_TC_ROWS
+#undef ADP_TC
+  return nullptr;
+}
+ConvTcKernel tc_kernel_for(int ntaps, int T, int kys, int epi) {
+  ConvTcKernel k = tc_kernel_lookup(ntaps, T, kys, epi);
+  if (!k) throw Error(ADP_EINVAL, "no tcgen05 conv instantiation for this (taps, rows, stacking, epilogue) combination");
+  return k;
 }
 
 // Effective padded fp32 weights wp[9][cin_pad][cout_pad] (concat layers: skip channels land in
@@ -494,8 +493,20 @@ void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label,
   const int nitems = nb * p.nty * p.ntx * p.nvar;
   const int grid = std::min(nitems, e->num_sms);
   const size_t smem = tc_smem_bytes(p);
-  ConvTcKernel kern = tc_kernel_for(p.ntaps, p.T, p.kys);
+  ConvTcKernel kern = tc_kernel_for(p.ntaps, p.T, p.kys, (epi.mode == EPI_STORE && epi.mask) ? EPI_BWD : epi.mode);
+  if (e->dbg & 16) { e->misc.ensure(148 * 8 * 8 + 4096); p.dbg_out = reinterpret_cast<long long *>(e->misc.as<char>() + 4096); }
   e->launch(label.c_str(), fl, by, [&] { kern<<<grid, kTcThreads, smem, e->stream>>>(tm, p); });
+  if (e->dbg & 16) {
+    // role timers (cycles, averaged over CTAs): where each warp role of the pipeline waits
+    std::vector<long long> h((size_t)grid * 8);
+    ADP_CUDA(cudaStreamSynchronize(e->stream));
+    ADP_CUDA(cudaMemcpy(h.data(), p.dbg_out, h.size() * 8, cudaMemcpyDeviceToHost));
+    double a[8] = {0};
+    for (int b = 0; b < grid; ++b) for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)b * 8 + k] / grid;
+    const double items = (double)nitems / grid;
+    fprintf(stderr, "tc-timers %-34s items/CTA %6.1f chunks %2d | producer wait-empty %5.1f%% of %8.0f | mma wait-acc-empty %5.1f%% wait-full %5.1f%% commit %5.1f%% of %8.0f | epilogue wait-acc-full %5.1f%% of %8.0f | cycles/item %6.0f\n",
+            label.c_str(), items, p.nchunks, 100 * a[0] / a[1], a[1], 100 * a[2] / a[4], 100 * a[3] / a[4], 100 * a[7] / a[4], a[4], 100 * a[5] / a[6], a[6], a[4] / items);
+  }
 }
 
 void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs, int Ws, int spitch, int scoff,
@@ -824,8 +835,9 @@ int adp_create(int device, int precision, int init_nb, int max_forwards, adp_eng
   for (int nt : {9, 4})
     for (int T : {4, 2, 1})
       for (int kys : {0, 1})
-        if (!kys || T >= 2)
-          ADP_CUDA(cudaFuncSetAttribute(tc_kernel_for(nt, T, kys), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        for (int epi : {EPI_STORE, EPI_HEAD, EPI_POOL, EPI_BWD})
+          if (ConvTcKernel k = tc_kernel_lookup(nt, T, kys, epi))
+            ADP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   ADP_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (const char *d = getenv("ADP_TC_DEBUG")) e->dbg = atoi(d);
   build_layers(e.get());
