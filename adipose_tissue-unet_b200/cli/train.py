@@ -1,0 +1,264 @@
+"""Two-phase fine-tuning - drop-in for Segmentation/train_adipose_unet_v3.py (argparse :1455-1630, driver :1080-1450).
+
+What runs on the device: the whole training step (forward with Dropout(0.3), combined_loss_standard = BCE + Dice,
+backward, Keras Adam/AdamW; include/adipose_b200.h adp_train_*), optionally data-parallel over the GPUs of one box
+(`torchrun --nproc-per-node N -m adipose_unet_b200.cli.train ...`: NCCL all-reduce of the gradient, train.py).
+What stays on the host, as in the reference: tile files, shuffling, augmentation, the epoch loop, the cosine/warm-up
+schedule (:393-404), best-checkpoint bookkeeping, EMA of the weights (:407-505) and the log files.
+
+Recipe coverage: the reference's DEFAULT recipe adds deep-supervision heads, OHEM and
+optional label smoothing on top of the standard loss.  Those are not in this engine yet: with those flags left at their
+defaults the run says so and trains the standard single-output model (== `--no-deep-supervision --no-hard-mining`);
+training_settings.log records `use_deep_supervision: False` so the evaluation scripts build the matching graph."""
+from __future__ import annotations
+
+import argparse
+import csv
+import json
+import math
+import os
+import sys
+import time
+from datetime import datetime
+from pathlib import Path
+
+import cv2
+import numpy as np
+
+from . import common as C
+
+TILE = 1024
+
+
+def build_parser():
+    p = argparse.ArgumentParser(description="Train Adipose U-Net (v3 recipe) on the B200 engine")
+    p.add_argument("--data-root", type=str, default=os.path.expanduser("~/Data_for_ML/Meat_Luci_Tulane/_build"))
+    p.add_argument("--pretrained-weights", type=str, default="checkpoints/unet_1024_dilation/weights_loss_val.weights.h5")
+    p.add_argument("--batch-size", type=int, default=2)
+    p.add_argument("--epochs-phase1", type=int, default=75)
+    p.add_argument("--epochs-phase2", type=int, default=150)
+    p.add_argument("--normalization-method", choices=["zscore", "percentile"], default="percentile")
+    p.add_argument("--percentile-low", type=float, default=1.0)
+    p.add_argument("--percentile-high", type=float, default=99.0)
+    p.add_argument("--augmentation-level", choices=["none", "light", "moderate", "heavy", "tta-style"], default="moderate")
+    p.add_argument("--checkpoint-suffix", type=str, default="")
+    for name, default in (("deep-supervision", True), ("hard-mining", True), ("label-smoothing", False), ("cosine-schedule", True)):
+        dest = "use_" + name.replace("-", "_")
+        p.add_argument(f"--use-{name}", dest=dest, action="store_true", default=default)
+        p.add_argument(f"--no-{name}", dest=dest, action="store_false", default=default)
+    p.add_argument("--hard-example-ratio", type=float, default=0.7)
+    p.add_argument("--ema-decay", type=float, default=0.995)
+    p.add_argument("--optimizer", choices=["adam", "adamw"], default="adam")
+    p.add_argument("--label-smooth-epsilon-pos", type=float, default=0.03)
+    p.add_argument("--label-smooth-epsilon-neg", type=float, default=0.07)
+    p.add_argument("--warmup-epochs-phase1", type=int, default=5)
+    p.add_argument("--warmup-epochs-phase2", type=int, default=3)
+    p.add_argument("--ds-weight-main", type=float, default=1.0)
+    p.add_argument("--ds-weight-aux1", type=float, default=0.4)
+    p.add_argument("--ds-weight-aux2", type=float, default=0.3)
+    g = p.add_argument_group("B200 engine (not in the reference)")
+    g.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
+    g.add_argument("--checkpoint-root", type=str, default="checkpoints/segmentation")
+    g.add_argument("--max-steps-per-epoch", type=int, default=0, help="cap for smoke runs (0 = whole epoch)")
+    g.add_argument("--seed", type=int, default=865)
+    return p
+
+
+class TileDataset:
+    """Paired `images/*.jpg` + `masks/*.tif` (train_adipose_unet_v3.py:510-600): gray float32 tile, mask as stored."""
+
+    def __init__(self, images_dir: Path, masks_dir: Path, method: str, mean: float, std: float, p_low: float, p_high: float):
+        masks = {p.stem: p for p in Path(masks_dir).glob("*.tif")}
+        self.pairs = [(p, masks[p.stem]) for p in sorted(Path(images_dir).glob("*.jpg")) if p.stem in masks]
+        self.method, self.mean, self.std, self.p_low, self.p_high = method, mean, std, p_low, p_high
+        print(f"Found {len(self.pairs)} paired tiles in {Path(images_dir).name}")
+
+    def __len__(self):
+        return len(self.pairs)
+
+    def load(self, idx: int):
+        ip, mp = self.pairs[idx]
+        img = cv2.imread(str(ip), cv2.IMREAD_GRAYSCALE).astype(np.float32)
+        mask = cv2.imread(str(mp), cv2.IMREAD_UNCHANGED).astype(np.float32)
+        if mask.ndim == 3:
+            mask = mask[..., 0]
+        return img, mask
+
+    def normalise(self, img: np.ndarray) -> np.ndarray:
+        if self.method == "zscore":
+            return ((img - self.mean) / (self.std + 1e-10)).astype(np.float32)
+        lo, hi = np.percentile(img, (self.p_low, self.p_high))              # src/utils/data.py:413-416
+        return np.clip((img - lo) / max(hi - lo, 1e-3), 0, 1).astype(np.float32)
+
+
+def augment_d4(img, mask, rng):
+    """Dihedral flips / 90-degree rotations (the geometric part of every augmentation level of the reference;
+    its intensity / elastic jitter is host-side image processing outside this engine)."""
+    k = int(rng.randint(0, 4))
+    if k:
+        img, mask = np.rot90(img, k), np.rot90(mask, k)
+    if rng.rand() < 0.5:
+        img, mask = img[:, ::-1], mask[:, ::-1]
+    if rng.rand() < 0.5:
+        img, mask = img[::-1], mask[::-1]
+    return np.ascontiguousarray(img), np.ascontiguousarray(mask)
+
+
+def batches(ds: TileDataset, batch: int, rng, augment: bool, rank: int, world: int, shuffle: bool):
+    idx = np.arange(len(ds))
+    if shuffle:
+        rng.shuffle(idx)
+    per_step = batch * world
+    for i in range(0, len(idx), per_step):
+        chunk = list(idx[i:i + per_step])
+        while len(chunk) < per_step:              # pad the last global batch by repetition (:583-585)
+            chunk.append(chunk[-1])
+        mine = chunk[rank * batch:(rank + 1) * batch]
+        xs, ys = [], []
+        for j in mine:
+            img, mask = ds.load(int(j))
+            if augment:
+                img, mask = augment_d4(img, mask, rng)
+            xs.append(ds.normalise(img)); ys.append(mask.astype(np.float32))
+        yield np.stack(xs), np.stack(ys)
+
+
+def compute_mean_std(paths):
+    vals = np.concatenate([cv2.imread(str(p), cv2.IMREAD_GRAYSCALE).astype(np.float32).reshape(-1) for p in paths])
+    return float(vals.mean()), float(vals.std() + 1e-10)
+
+
+def validate(engine, ds: TileDataset, batch: int):
+    """val_loss / val_dice_coef over the validation tiles (Keras averages per-batch values)."""
+    losses, dices = [], []
+    rng = np.random.RandomState(0)
+    for x, y in batches(ds, batch, rng, False, 0, 1, False):
+        p = engine.predict(x, 0.0, 1.0 - 1e-10)                    # x is already normalised: (x - 0) / (1 - 1e-10 + 1e-10)
+        m = engine.loss_metrics(p, y)
+        losses.append(m["loss"]); dices.append(m["dice_coef"])
+    return float(np.mean(losses)), float(np.mean(dices))
+
+
+def main(argv=None) -> int:
+    from .. import api, train as T
+    from ..weights_io import load_weights_file, save_weights_file
+    from .. import synth
+    args = build_parser().parse_args(argv)
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        torch.cuda.set_device(local)
+        dist_.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_
+    log = print if rank == 0 else (lambda *a, **k: None)
+    log("=" * 80 + "\nTRAIN ADIPOSE U-NET VERSION 3.1 (B200 engine)\n" + "=" * 80)
+    for flag, name in ((args.use_deep_supervision, "deep supervision"), (args.use_hard_mining, "hard example mining"),
+                       (args.use_label_smoothing, "label smoothing")):
+        if flag:
+            log(f"⚠️  {name}: not implemented in this engine yet - training the standard BCE+Dice single-output recipe")
+    data_root = Path(args.data_root)
+    tr_img, tr_msk = data_root / "dataset" / "train" / "images", data_root / "dataset" / "train" / "masks"
+    va_img, va_msk = data_root / "dataset" / "val" / "images", data_root / "dataset" / "val" / "masks"
+    train_paths = sorted(tr_img.glob("*.jpg"))
+    if not train_paths:
+        print(f"❌ No training tiles under {tr_img}")
+        return 1
+    mean, std = compute_mean_std(train_paths)
+    log(f"Global normalization stats: mean={mean:.2f}, std={std:.2f}")
+    train_ds = TileDataset(tr_img, tr_msk, args.normalization_method, mean, std, args.percentile_low, args.percentile_high)
+    val_ds = TileDataset(va_img, va_msk, args.normalization_method, mean, std, args.percentile_low, args.percentile_high)
+    steps_per_epoch = max(1, math.ceil(len(train_ds) / (args.batch_size * world)))
+    if args.max_steps_per_epoch:
+        steps_per_epoch = min(steps_per_epoch, args.max_steps_per_epoch)
+    stamp = datetime.now().strftime("%Y%m%d_%H%M%S")
+    name = "adipose_sybreosin" + (f"_{args.checkpoint_suffix}" if args.checkpoint_suffix else "")
+    ckpt = Path(args.checkpoint_root) / f"{stamp}_{name}_1024_finetune_v3"          # :650-652
+    if rank == 0:
+        ckpt.mkdir(parents=True, exist_ok=True)
+        with open(ckpt / "normalization_stats.json", "w") as f:                      # :1194-1207
+            json.dump({"mean": mean, "std": std, "normalization_method": args.normalization_method, "dataset_path": str(data_root),
+                       "num_training_images": len(train_paths), "build_timestamp": stamp, "version": "3.0"}, f, indent=2)
+        with open(ckpt / "training_settings.log", "w") as f:                         # :984-1053 (sniffed at eval:513-516)
+            f.write("=" * 80 + "\nTRAINING SETTINGS LOG - VERSION 3\n" + "=" * 80 + f"\n\nGenerated: {stamp}\n")
+            f.write("Script: adipose_unet_b200.cli.train\n" + f"Checkpoint Directory: {ckpt}\n\n" + "-" * 60 + "\nCOMMAND LINE ARGUMENTS\n" + "-" * 60 + "\n")
+            settings = dict(vars(args)); settings["use_deep_supervision"] = False; settings["use_hard_mining"] = False
+            settings["use_label_smoothing"] = False
+            for k, v in settings.items():
+                f.write(f"  {k}: {v}\n")
+            f.write("\n" + "-" * 60 + "\nMACHINE READABLE FORMAT (JSON)\n" + "-" * 60 + "\n" + json.dumps(settings, indent=2, default=str) + "\n")
+    engine = api.Engine(precision=args.precision, device=local, max_forwards=max(8, args.batch_size))
+    if args.pretrained_weights and Path(args.pretrained_weights).exists():
+        engine.set_weights(load_weights_file(args.pretrained_weights))
+        log(f"✓ Loaded pretrained weights from {args.pretrained_weights}")
+    else:
+        log("WARNING: No pretrained weights found, training from scratch")
+        engine.set_weights(synth.init_weights(seed=args.seed))
+    rng = np.random.RandomState(args.seed + rank)
+    best_overall = -1.0
+    ema = None
+    for phase, epochs, max_lr, min_lr, warm, freeze, decay in (
+            (1, args.epochs_phase1, 1e-4, 1e-7, args.warmup_epochs_phase1, True, 0.999),
+            (2, args.epochs_phase2, 1e-5, 1e-8, args.warmup_epochs_phase2, False, args.ema_decay)):
+        if epochs <= 0:
+            continue
+        log(f"\n{'=' * 60}\nPHASE {phase}: {'frozen encoder' if freeze else 'fine-tuning all layers'} ({epochs} epochs)\n{'=' * 60}")
+        if phase == 2 and (ckpt / "phase1_best.weights.h5").exists():
+            engine.set_weights(load_weights_file(str(ckpt / "phase1_best.weights.h5")))       # :1336-1339
+        trainer = T.DataParallelTrainer(engine, args.batch_size, TILE, dist=dist, rank=rank, world=world, dropout_rate=0.3,
+                                        seed=args.seed + 1000 * phase, optimizer=args.optimizer, freeze_encoder=freeze)
+        best_phase, since_best = -1.0, 0
+        logf = None
+        if rank == 0:
+            logf = open(ckpt / f"phase{phase}_training.log", "w", newline="")
+            w = csv.writer(logf); w.writerow(["epoch", "dice_coef", "loss", "lr", "val_dice_coef", "val_loss"])
+        for epoch in range(epochs):
+            lr = T.cosine_warmup_lr(epoch, max_lr, min_lr, warm, epochs) if args.use_cosine_schedule else max_lr
+            t0, losses, dices = time.time(), [], []
+            for step, (x, y) in enumerate(batches(train_ds, args.batch_size, rng, args.augmentation_level != "none", rank, world, True)):
+                if step >= steps_per_epoch:
+                    break
+                out = trainer.step(x, y, lr)
+                losses.append(out["loss"]); dices.append(out["dice_coef"])
+                if rank == 0 and decay > 0:
+                    cur = engine.get_weights()
+                    ema = cur if ema is None else {k: decay * ema[k] + (1.0 - decay) * cur[k] for k in cur}      # :407-470
+            vloss, vdice = validate(engine, val_ds, args.batch_size) if len(val_ds) else (float("nan"), float("nan"))
+            log(f"Epoch {epoch + 1}/{epochs} - {time.time() - t0:.0f}s - loss: {np.mean(losses):.4f} - dice_coef: {np.mean(dices):.4f} "
+                f"- val_loss: {vloss:.4f} - val_dice_coef: {vdice:.4f} - lr: {lr:.2e}")
+            if rank == 0:
+                w.writerow([epoch, np.mean(dices), np.mean(losses), lr, vdice, vloss]); logf.flush()
+                score = vdice if np.isfinite(vdice) else float(np.mean(dices))
+                if score > best_phase:
+                    best_phase, since_best = score, 0
+                    save_weights_file(str(ckpt / f"phase{phase}_best.weights.h5"), engine.get_weights())
+                else:
+                    since_best += 1
+                if score > best_overall:
+                    best_overall = score
+                    save_weights_file(str(ckpt / "weights_best_overall.weights.h5"), engine.get_weights())
+                    if ema is not None and phase == 2:
+                        save_weights_file(str(ckpt / "weights_ema.weights.h5"), {k: v.astype(np.float32) for k, v in ema.items()})
+            stop = since_best >= 15                                  # EarlyStopping(patience=15), :1280-1284, 1370-1374
+            if dist is not None:
+                import torch
+                flag = torch.tensor([1 if (rank == 0 and stop) else 0], device=f"cuda:{local}")
+                dist.broadcast(flag, 0)
+                stop = bool(flag.item())
+            if stop:
+                log(f"Early stopping at epoch {epoch + 1}")
+                break
+        if rank == 0:
+            logf.close()
+            save_weights_file(str(ckpt / f"weights_phase{phase}_final.weights.h5"), engine.get_weights())
+        trainer.close()
+    log(f"\n✓ Training complete. Checkpoints in {ckpt}\n  - phase1_best.weights.h5\n  - phase2_best.weights.h5\n"
+        f"  - weights_best_overall.weights.h5\n  - weights_ema.weights.h5")
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -353,11 +353,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
       const size_t plane = (size_t)p.Wout * 8;
       const int ox = x * p.oscale + p.var[v].ox;
       // row-planar output row base of accumulator row r: ((((n*H + y)*cgs + cg)*W)*8
-      auto out_row = [&](int r) -> __nv_bfloat16 * {
-        const int y = ty * T + r;
-        const size_t orow = ((size_t)n * p.Hout + (size_t)(y * p.oscale + p.var[v].oy)) * p.out_cgs + p.out_cg0 + p.var[v].out_cg;
-        return p.out + orow * plane + (size_t)ox * 8;
-      };
+      // (no integer division and no 64-bit multiply chains per unit: row base + row stride, units walked incrementally)
+      const size_t orstride = (size_t)p.oscale * p.out_cgs * plane;
+      __nv_bfloat16 *const obase = p.out + (((size_t)n * p.Hout + (size_t)(ty * T * p.oscale + p.var[v].oy)) * p.out_cgs +
+                                            p.out_cg0 + p.var[v].out_cg) * plane + (size_t)ox * 8;
+      auto out_row = [&](int r) -> __nv_bfloat16 * { return obase + (size_t)r * orstride; };
+      // unit u = row * NU + cu; this warp owns u = half, half + 2, ...
+      auto unit_next = [&](int &row, int &cu) { cu += 2; while (cu >= NU) { cu -= NU; ++row; } };
+      int row0 = 0, cu0 = half;
+      while (cu0 >= NU) { cu0 -= NU; ++row0; }
       if constexpr (EPI == EPI_BWD) {
         // backward twin (data gradient): out = (acc + resid) * [mask > 0] * mask_scale.  The mask words of ALL units this
         // warp owns are requested before waiting for the accumulator, so their HBM latency overlaps the MMAs of the
@@ -366,12 +370,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
         constexpr int PF = 6;
         uint4 mk[PF][2];
         const int UE = T * NU;
+        int prow = row0, pcu = cu0;
 #pragma unroll
         for (int k = 0; k < PF; ++k) {
           const int u = half + 2 * k;
           mk[k][0] = make_uint4(0, 0, 0, 0); mk[k][1] = mk[k][0];
           if (u < UE) {
-            const int row = u / NU, cu = u - row * NU;
+            const int row = prow, cu = pcu;
+            unit_next(prow, pcu);
             if ((ty * T + row < p.Hin) && (x < p.Win)) {
               const __nv_bfloat16 *m = p.mask + ((out_row(row) + (size_t)(2 * cu) * plane) - p.out);
               mk[k][0] = __ldg(reinterpret_cast<const uint4 *>(m));
@@ -383,13 +389,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
         ptx::tc_fence_after();
         uint32_t acc[2][16];
         if (half < UE) ptx::tmem_ld16_issue(t0 + (uint32_t)half * 16u, acc[0]);
+        prow = row0; pcu = cu0;
 #pragma unroll
         for (int k = 0; k < PF; ++k) {
           const int u = half + 2 * k;
           if (u < UE) {
             ptx::tmem_ld16_wait(acc[k & 1]);
             if (u + 2 < UE) ptx::tmem_ld16_issue(t0 + (uint32_t)(u + 2) * 16u, acc[(k + 1) & 1]);
-            const int row = u / NU, cu = u - row * NU;
+            const int row = prow, cu = pcu;
+            unit_next(prow, pcu);
             float f[16];
             bias_relu16(acc[k & 1], sb + cu * 16, p.relu, f);
             if ((ty * T + row < p.Hin) && (x < p.Win)) {
@@ -438,8 +446,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
       { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_full[buf], acc_ph, 6); if (p.dbg & 16) t_e0 += clock64() - tw; }
       ptx::tc_fence_after();
       if constexpr (EPI == EPI_STORE) {
-        tmem_pipeline(t0, half, 2, T * NU, [&](int u, const uint32_t (&r)[16]) {
-          const int row = u / NU, cu = u - row * NU;
+        int srow = row0, scu = cu0;
+        tmem_pipeline(t0, half, 2, T * NU, [&](int, const uint32_t (&r)[16]) {
+          const int row = srow, cu = scu;
+          unit_next(srow, scu);
           float f[16];
           bias_relu16(r, sb + cu * 16, p.relu, f);
           if ((ty * T + row < p.Hin) && (x < p.Win) && !(p.dbg & 1)) {
@@ -483,8 +493,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
         // EPI_POOL: unit = (row pair k, 16 channels); both rows are stored, their max is reduced with
         // the neighbouring column (lane ^ 1) and even lanes write the pooled pixel
         const int HU = (T / 2) * NU;
+        int pk = row0, pc = cu0;
         for (int pu = half; pu < HU; pu += 2) {
-          const int k = pu / NU, cu = pu - k * NU;
+          const int k = pk, cu = pc;
+          unit_next(pk, pc);
           uint32_t ra[16], rb[16];
           ptx::tmem_ld16_issue(t0 + (uint32_t)((2 * k) * p.N + cu * 16), ra);
           ptx::tmem_ld16_issue(t0 + (uint32_t)((2 * k + 1) * p.N + cu * 16), rb);

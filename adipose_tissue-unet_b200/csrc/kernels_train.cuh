@@ -75,9 +75,15 @@ __global__ void __launch_bounds__(256) relu_mask_kernel(View<T> g, View<T> x, in
 
 // Dropout forward (train_adipose_unet_v3.py:682,696,703,710): X <- X * m / keep, m ~ Bernoulli(keep)
 // from a counter-based hash (TF's RNG stream cannot be reproduced; parity tests supply masks instead).
-ADP_DEVINL uint32_t hash_u32(uint64_t k) {
-  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
-  return (uint32_t)k;
+// One 32-bit murmur3-finalizer hash decides TWO channels (16 bits each: P(keep) is keep rounded to 1/65536), so a
+// group of 8 channels costs four short integer hashes and the kernel stays HBM-bound.
+ADP_DEVINL uint32_t hash_u32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+ADP_DEVINL uint32_t dropout_bits(uint64_t seed, size_t group_index, int pair) {
+  const uint64_t idx = (uint64_t)group_index * 4u + (uint64_t)pair;
+  return hash_u32((uint32_t)idx * 0x9E3779B1u ^ hash_u32((uint32_t)(idx >> 32) ^ (uint32_t)(seed >> 32)) ^ (uint32_t)seed);
 }
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -86,6 +92,7 @@ dropout_kernel(View<T> x, int nb, float keep, uint64_t seed, const uint8_t *__re
   const int G = x.C / 8;
   const size_t total = (size_t)nb * x.H * G * x.W;
   const float inv = 1.f / keep;
+  const uint32_t thr = (uint32_t)fminf(keep * 65536.f, 65536.f);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int xx = i % x.W; size_t r = i / x.W;
     int gi = r % G; r /= G;
@@ -93,13 +100,20 @@ dropout_kernel(View<T> x, int nb, float keep, uint64_t seed, const uint8_t *__re
     float a[8];
     T *ptr = x.p + x.at(n, yy, gi, xx);
     load8<T>(ptr, a);
+    if (mask_in) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = gi * 8 + k;
-      bool keep_it;
-      if (mask_in) keep_it = c < creal ? mask_in[(((size_t)n * x.H + yy) * x.W + xx) * creal + c] != 0 : false;
-      else keep_it = (hash_u32(seed + i * 8 + k) * (1.0f / 4294967296.0f)) < keep;
-      a[k] = keep_it ? a[k] * inv : 0.f;
+      for (int k = 0; k < 8; ++k) {
+        const int c = gi * 8 + k;
+        const bool keep_it = c < creal ? mask_in[(((size_t)n * x.H + yy) * x.W + xx) * creal + c] != 0 : false;
+        a[k] = keep_it ? a[k] * inv : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t h = dropout_bits(seed, i, q);
+        a[2 * q] = (h & 0xFFFFu) < thr ? a[2 * q] * inv : 0.f;
+        a[2 * q + 1] = (h >> 16) < thr ? a[2 * q + 1] * inv : 0.f;
+      }
     }
     store8<T>(ptr, a);
   }
@@ -263,15 +277,16 @@ conv_wgrad_kernel(View<T> xin, View<T> dz, float *__restrict__ dW, float *__rest
 // group (gridDim.x * 8 warps is a multiple of the group count), keeps its 9x8 + 8 sums in registers over all its
 // pixels and leaves through shuffles + one atomic per sum.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 first_wgrad_kernel(const float *__restrict__ xnorm, View<T> dz, int nb, float *__restrict__ dW /*[9][C]*/, float *__restrict__ db) {
   const int C = dz.C, S = dz.H, G = C / 8;
   const int lane = threadIdx.x & 31;
-  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int g = (int)(wid % G);
+  const int wid = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int nw = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+  const int g = wid % G;                        // this warp's channel group (gridDim.x * 8 is a multiple of G)
+  const int slot = wid / G, nslots = nw / G;
   const int xchunks = (S + 31) / 32;
-  const long long nwork = (long long)nb * S * xchunks * G;
+  const int nrc = nb * S * xchunks;             // (image, row, 32-pixel chunk) work items of one channel group
   float acc[9][8], bs[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -279,22 +294,36 @@ first_wgrad_kernel(const float *__restrict__ xnorm, View<T> dz, int nb, float *_
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[t][k] = 0.f;
   }
-  for (long long w = wid; w < nwork; w += nw) {
-    long long r = w / G;
-    const int xc = (int)(r % xchunks); r /= xchunks;
-    const int y = (int)(r % S), n = (int)(r / S);
-    const int x = xc * 32 + lane;
-    if (x >= S) continue;
-    float d[8];
-    load8<T>(dz.p + dz.at(n, y, g, x), d);
+  // MLP work items per trip: their 16-byte gradient loads are issued back to back, then each item's nine input taps (L1
+  // hits) are folded in; 128 registers -> two 256-thread blocks per SM
+  constexpr int MLP = 2;
+  for (int rc0 = slot; rc0 < nrc; rc0 += MLP * nslots) {
+    float d[MLP][8];
+    int yy[MLP], nn[MLP], xx[MLP];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) bs[k] += d[k];
+    for (int j = 0; j < MLP; ++j) {
+      const int rc = rc0 + j * nslots;
+      const int xc = rc % xchunks; const int r = rc / xchunks;
+      yy[j] = r % S; nn[j] = r / S; xx[j] = xc * 32 + lane;
+      if (rc < nrc && xx[j] < S) load8<T>(dz.p + dz.at(nn[j], yy[j], g, xx[j]), d[j]);
+      else {
+        xx[j] = -4;                       // every tap out of range
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
-      const float v = (iy >= 0 && iy < S && ix >= 0 && ix < S) ? xnorm[((size_t)n * S + iy) * S + ix] : 0.f;
+        for (int k = 0; k < 8; ++k) d[j][k] = 0.f;
+      }
+    }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(v, d[k], acc[t][k]);
+    for (int j = 0; j < MLP; ++j) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bs[k] += d[j][k];
+      if (xx[j] < 0) continue;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int iy = yy[j] + t / 3 - 1, ix = xx[j] + t % 3 - 1;
+        const float v = (iy >= 0 && iy < S && ix >= 0 && ix < S) ? __ldg(xnorm + ((size_t)nn[j] * S + iy) * S + ix) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(v, d[j][k], acc[t][k]);
+      }
     }
   }
 #pragma unroll

@@ -478,7 +478,7 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
     ADP_CUDA(cudaMemsetAsync(tr->gb_first.p, 0, (size_t)cp[0] * 4, e->stream));
     const size_t total = (size_t)nb * S * S;
     const int G0 = cp[0] / 8;
-    const int grid = G0 * std::max(1, std::min(e->num_sms * 4 / G0, (int)cdiv64((long long)nb * S * cdiv(S, 32), 8)));
+    const int grid = G0 * std::max(1, std::min(e->num_sms * 2 / G0, (int)cdiv64((long long)nb * S * cdiv(S, 32), 8)));
     e->launch("first_conv_wgrad", 2.0 * total * 9 * e->c[0], (double)total * (4 + cp[0] * sizeof(T)), [&] {
       first_wgrad_kernel<T><<<grid, 256, 0, e->stream>>>(tr->x.as<float>(), B.V(tr->g_d1a, S, cp[0], 0, cp[0]), nb,
                                                                               tr->gw_first.as<float>(), tr->gb_first.as<float>());

@@ -1,0 +1,140 @@
+"""Host-side logic of the re-hosted CLIs (SURVEY.md section 8b "CLI surface to re-host"): argparse truth (flag names and
+defaults of the reference's four entry points), tile-filename geometry, output-folder naming, bootstrap CI, the
+learning-rate schedule wiring and the dataset/normalisation helpers.  No device calls."""
+import json
+
+import cv2
+import numpy as np
+import pytest
+
+from adipose_unet_b200.cli import common as C, evaluate, infer, recon, train
+
+
+def _defaults(parser):
+    return {a.dest: a.default for a in parser._actions if a.dest != "help"}
+
+
+def test_infer_flags_match_reference():
+    # segmentation_inference.py:324-350
+    d = _defaults(infer.build_parser())
+    assert d["threshold"] == 0.5 and d["use_tta"] is False and d["tta_mode"] == "basic" and d["overlay_color"] == "cyan"
+    assert d["save_overlays"] is False and d["save_probability"] is False
+    a = infer.build_parser().parse_args(["--images-dir", "i", "--output-dir", "o", "--weights", "w", "--use-tta", "--tta-mode", "full",
+                                         "--overlay-color", "magenta", "--save-probability"])
+    assert a.use_tta and a.tta_mode == "full" and a.overlay_color == "magenta" and a.save_probability
+    with pytest.raises(SystemExit):
+        infer.build_parser().parse_args(["--images-dir", "i"])          # --output-dir / --weights required
+
+
+def test_eval_flags_match_reference():
+    # full_evaluation_enhanced.py:1989-2036
+    d = _defaults(evaluate.build_parser())
+    assert d["n_vis_samples"] == 10 and d["tta_mode"] == "basic" and d["overlap"] == 0.5 and d["blend_mode"] == "gaussian"
+    assert d["refine_kernel"] == 5 and d["n_positive"] == 120 and d["n_negative"] == 30 and d["output"] is None
+    for flag in ("ema", "optimize_threshold", "no_visualizations", "use_tta", "sliding_window", "boundary_refine", "adaptive_threshold",
+                 "save_overlays"):
+        assert d[flag] is False
+
+
+def test_recon_flags_match_reference():
+    # reconstruct_full_images.py:882-929
+    d = _defaults(recon.build_parser())
+    assert d["tile_size"] == 1024 and d["stride"] == 512 and d["threshold"] == 0.5 and d["blend_mode"] == "gaussian"
+    assert d["tta_mode"] == "basic" and d["refine_kernel"] == 5 and d["min_coverage"] == 0.90 and d["max_tiles"] is None
+
+
+def test_train_flags_match_reference():
+    # train_adipose_unet_v3.py:1455-1630
+    d = _defaults(train.build_parser())
+    want = dict(batch_size=2, epochs_phase1=75, epochs_phase2=150, normalization_method="percentile", percentile_low=1.0,
+                percentile_high=99.0, augmentation_level="moderate", checkpoint_suffix="", use_deep_supervision=True,
+                use_hard_mining=True, hard_example_ratio=0.7, ema_decay=0.995, optimizer="adam", use_label_smoothing=False,
+                label_smooth_epsilon_pos=0.03, label_smooth_epsilon_neg=0.07, use_cosine_schedule=True, warmup_epochs_phase1=5,
+                warmup_epochs_phase2=3, ds_weight_main=1.0, ds_weight_aux1=0.4, ds_weight_aux2=0.3)
+    for k, v in want.items():
+        assert d[k] == v, k
+    a = train.build_parser().parse_args(["--no-deep-supervision", "--no-hard-mining", "--no-cosine-schedule", "--optimizer", "adamw"])
+    assert not a.use_deep_supervision and not a.use_hard_mining and not a.use_cosine_schedule and a.optimizer == "adamw"
+
+
+def test_tile_filename_geometry():
+    # reconstruct_full_images.py:121-147, 240-271, 399-400
+    assert recon.parse_tile_filename("6 BEEF Shoulder -1_grid_5x5_r1_c2_r0_c1.jpg") == ("6 BEEF Shoulder -1_grid_5x5_r1_c2", 0, 1)
+    assert recon.parse_tile_filename("slideA_r12_c7.jpg") == ("slideA", 12, 7)
+    with pytest.raises(ValueError):
+        recon.parse_tile_filename("no_position.jpg")
+    assert recon.infer_full_image_dimensions({(0, 0), (3, 5)}, 1024, 512) == (3 * 512 + 1024, 5 * 512 + 1024)
+    assert recon.infer_full_image_dimensions(set(), 1024, 512) == (0, 0)
+    assert evaluate.extract_slide_id("/x/6 BEEF Shoulder -1_grid_5x5_r1_c2_r0_c1.jpg") == "6 BEEF Shoulder -1_grid_5x5_r1_c2"
+    assert evaluate.extract_slide_id("plain.jpg") == "plain"
+
+
+def test_eval_output_folder_name():
+    # full_evaluation_enhanced.py:2055-2090
+    P = evaluate.build_parser()
+    a = P.parse_args(["--weights", "w", "--test-dataset", "d"])
+    assert evaluate.output_folder_name(a, "clean_test", "stain_normalized") == "clean_test_stain"
+    a = P.parse_args(["--weights", "w", "--test-dataset", "d", "--ema", "--use-tta", "--tta-mode", "full", "--sliding-window", "--overlap",
+                      "0.75", "--boundary-refine", "--refine-kernel", "7", "--adaptive-threshold"])
+    assert evaluate.output_folder_name(a, "human_test", "original") == "human_test_original_ema_tta_full_sw_gaussian_o75_refine7_adaptive"
+
+
+def test_bootstrap_ci_matches_reference_procedure():
+    data = np.array([0.8, 0.9, 0.85, np.nan, 0.7])
+    mean, (lo, hi) = evaluate.bootstrap_ci(data, n_bootstrap=2000)
+    valid = data[np.isfinite(data)]
+    rng = np.random.RandomState(42)
+    stats = np.asarray([np.mean(rng.choice(valid, size=len(valid), replace=True)) for _ in range(2000)])
+    assert mean == pytest.approx(valid.mean())
+    assert (lo, hi) == tuple(np.percentile(stats, [2.5, 97.5]))
+    m, (l, h) = evaluate.bootstrap_ci(np.array([np.nan]))
+    assert np.isnan(m) and np.isnan(l) and np.isnan(h)
+
+
+def test_weight_discovery_and_stats(tmp_path):
+    (tmp_path / "phase2_best.weights.h5").write_bytes(b"x")
+    (tmp_path / "weights_ema.weights.h5").write_bytes(b"x")
+    f, d = C.find_weights_file(str(tmp_path))
+    assert f.endswith("phase2_best.weights.h5") and d == tmp_path
+    f, _ = C.find_weights_file(str(tmp_path), use_ema=True)
+    assert f.endswith("weights_ema.weights.h5")
+    (tmp_path / "weights_best_overall.weights.h5").write_bytes(b"x")
+    assert C.find_weights_file(str(tmp_path))[0].endswith("weights_best_overall.weights.h5")
+    (tmp_path / "normalization_stats.json").write_text(json.dumps({"mean": 101.5, "std": 33.25}))
+    assert C.load_normalization_stats(tmp_path) == (101.5, 33.25)
+    assert C.detect_deep_supervision(tmp_path) is False
+    (tmp_path / "training_settings.log").write_text("  use_deep_supervision: True\n")
+    assert C.detect_deep_supervision(tmp_path) is True
+    with pytest.raises(FileNotFoundError):
+        C.find_weights_file(str(tmp_path / "missing"))
+
+
+def test_train_dataset_normalisation_and_batches(tmp_path):
+    rng = np.random.default_rng(0)
+    (tmp_path / "images").mkdir(); (tmp_path / "masks").mkdir()
+    for i in range(5):
+        img = (rng.random((64, 64)) * 255).astype(np.uint8)
+        cv2.imwrite(str(tmp_path / "images" / f"s_r0_c{i}.jpg"), img)
+        cv2.imwrite(str(tmp_path / "masks" / f"s_r0_c{i}.tif"), (img > 128).astype(np.uint8))
+    mean, std = train.compute_mean_std(sorted((tmp_path / "images").glob("*.jpg")))
+    ds = train.TileDataset(tmp_path / "images", tmp_path / "masks", "zscore", mean, std, 1.0, 99.0)
+    assert len(ds) == 5
+    img, mask = ds.load(0)
+    np.testing.assert_allclose(ds.normalise(img), (img - mean) / (std + 1e-10), rtol=1e-6)
+    pct = train.TileDataset(tmp_path / "images", tmp_path / "masks", "percentile", mean, std, 1.0, 99.0).normalise(img)
+    lo, hi = np.percentile(img, (1.0, 99.0))
+    np.testing.assert_allclose(pct, np.clip((img - lo) / max(hi - lo, 1e-3), 0, 1), rtol=1e-6)
+    # two ranks see disjoint halves of every global batch; the last batch is padded by repetition
+    got = [[], []]
+    for r in range(2):
+        for x, y in train.batches(ds, 2, np.random.RandomState(1), False, r, 2, False):
+            assert x.shape == (2, 64, 64) and y.shape == (2, 64, 64) and set(np.unique(y)) <= {0.0, 1.0}
+            got[r].append(x)
+    assert len(got[0]) == len(got[1]) == 2
+    assert not np.array_equal(got[0][0], got[1][0])
+    # dihedral augmentation keeps image and mask aligned
+    a, m = train.augment_d4(img, mask, np.random.RandomState(3))
+    assert sorted(a.ravel()) == sorted(img.ravel()) and a.shape == img.shape
+    thr = (a > 128).astype(np.float32)
+    jpeg_ok = (thr == m).mean()
+    assert jpeg_ok > 0.9            # JPEG noise moves a few pixels across 128; alignment keeps the rest identical
