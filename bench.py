@@ -268,8 +268,18 @@ def run_ours(args, rank, world, local_rank):
         if conv:
             cms = sum(r["ms"] for r in conv); cfl = sum(r["flops"] for r in conv); cl = sum(r["launches"] for r in conv)
             ach = cfl / (cms * 1e-3) / 1e12
+            # DRAM traffic per launch from the committed ncu --set full capture of the same kernels (bytes per forward summed
+            # over the 20 conv launches of a chunk, scaled to this run's forwards per launch); null if the summary is absent
+            traffic, traffic_src = None, None
+            tp_ = os.path.join(ROOT, "profiles", "r1_ncu_conv_traffic.json")
+            if os.path.exists(tp_):
+                tj = json.load(open(tp_))
+                fw_per_launch = N_AUG * BATCH_TILES * len(conv) / max(cl, 1)
+                traffic = tj["dram_bytes_per_forward"] * fw_per_launch / tj["launches"]
+                traffic_src = tj["source"]
             roof = {"kernel": conv[0]["name"].split("/")[0], "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s",
-                    "frac": ach / tf, "traffic": None, "peak_source": how, "launches_per_step": cl,
+                    "frac": ach / tf, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)",
+                    "traffic_source": traffic_src, "peak_source": how, "launches_per_step": cl,
                     "avg_launch_ms": cms / max(cl, 1), "share_of_step": cms / tot,
                     "algorithmic_flops_per_step": cfl}
 
