@@ -25,35 +25,44 @@ __global__ void __launch_bounds__(256)
 tta_blend_kernel(const float *__restrict__ planes, TtaOps ops, int S, int mode, float *__restrict__ out,
                  float *__restrict__ acc, float *__restrict__ wsum, const float *__restrict__ window,
                  int accW, int accRows, int ty, int tx) {
-  __shared__ float tile[32][33];
+  // all (up to 8) source blocks are requested before the single barrier: one HBM round trip per block instead of one
+  // per augmentation
+  __shared__ float tile[8][32][33];
   const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
   const int lx = threadIdx.x, ly = threadIdx.y;     // 32 x 8
-  float sum[4];
-  for (int k = 0; k < ops.n; ++k) {
-    const int op = ops.inv[k];
-    // source block origin: image of the block's (bi,bj) corner region under op
-    int s0i, s0j, s1i, s1j;
-    d4_src(op, bi, bj, S, s0i, s0j);
-    d4_src(op, min(bi + 31, S - 1), min(bj + 31, S - 1), S, s1i, s1j);
-    const int sbi = min(s0i, s1i), sbj = min(s0j, s1j);
-    const float *P = planes + (size_t)k * S * S;
-    __syncthreads();
+  int sbi[8], sbj[8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int i = sbi + ly + 8 * r, j = sbj + lx;
-      tile[ly + 8 * r][lx] = (i < S && j < S) ? P[(size_t)i * S + j] : 0.f;
-    }
-    __syncthreads();
+  for (int k = 0; k < 8; ++k) {
+    if (k < ops.n) {
+      // source block origin: image of the block's (bi,bj) corner region under op
+      int s0i, s0j, s1i, s1j;
+      d4_src(ops.inv[k], bi, bj, S, s0i, s0j);
+      d4_src(ops.inv[k], min(bi + 31, S - 1), min(bj + 31, S - 1), S, s1i, s1j);
+      sbi[k] = min(s0i, s1i); sbj[k] = min(s0j, s1j);
+      const float *P = planes + (size_t)k * S * S;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int i = bi + ly + 8 * r, j = bj + lx;
-      float v = 0.f;
-      if (i < S && j < S) {
-        int si, sj;
-        d4_src(op, i, j, S, si, sj);
-        v = tile[si - sbi][sj - sbj];
+      for (int r = 0; r < 4; ++r) {
+        const int i = sbi[k] + ly + 8 * r, j = sbj[k] + lx;
+        tile[k][ly + 8 * r][lx] = (i < S && j < S) ? P[(size_t)i * S + j] : 0.f;
       }
-      sum[r] = (k == 0) ? v : __fadd_rn(sum[r], v);
+    }
+  }
+  __syncthreads();
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < ops.n) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = bi + ly + 8 * r, j = bj + lx;
+        float v = 0.f;
+        if (i < S && j < S) {
+          int si, sj;
+          d4_src(ops.inv[k], i, j, S, si, sj);
+          v = tile[k][si - sbi[k]][sj - sbj[k]];
+        }
+        sum[r] = (k == 0) ? v : __fadd_rn(sum[r], v);
+      }
     }
   }
   const float nf = (float)ops.n;

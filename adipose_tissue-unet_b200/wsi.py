@@ -92,7 +92,7 @@ def reconstruct_wsi(engine, slide_rows: Callable[[int, int], np.ndarray], h: int
                     mean: float = 127.5, std: float = 50.0, tta_mode: Optional[str] = "full", threshold: float = 0.5,
                     gt_rows: Optional[Callable[[int, int], np.ndarray]] = None, rank: int = 0, world: int = 1,
                     dist=None, batch_tiles: int = 16, want_prob: bool = True, want_mask: bool = True,
-                    to_device=None):
+                    to_device=None, timings: bool = False):
     """Run the sliding window on this rank's strip and exchange boundaries.
 
     slide_rows(y0, rows) -> uint8 [rows, w] gray rows of the slide (host).  to_device(host_u8) must return
@@ -108,15 +108,30 @@ def reconstruct_wsi(engine, slide_rows: Callable[[int, int], np.ndarray], h: int
     mode = _lib.BLEND_GAUSSIAN if blend_mode == "gaussian" else _lib.BLEND_LINEAR
     result = dict(prob=None, mask=None, counts=(0, 0, 0, 0), own=(me.own_lo, me.own_hi), tiles=len(me.tiles),
                   n_tiles_total=sum(len(s.tiles) for s in strips))
+    import time as _t
+    ph = {}
+    t_ = _t.perf_counter()
+
+    def lap(name):
+        nonlocal t_
+        if timings:
+            if hasattr(engine, "synchronize"):
+                engine.synchronize()
+            now = _t.perf_counter(); ph[name] = ph.get(name, 0.0) + now - t_; t_ = now
+
     if me.tiles:
         engine.wsi_begin(me.acc_rows, w, me.acc_y0, tile, mode, window if mode == _lib.BLEND_GAUSSIAN else None)
+        lap("begin")
         strip_host = np.ascontiguousarray(slide_rows(me.acc_y0, me.acc_rows))
         assert strip_host.dtype == np.uint8 and strip_host.shape == (me.acc_rows, w)
+        lap("strip_assembly")
         strip_dev = to_device(strip_host)
+        lap("strip_h2d")
         for i in range(0, len(me.tiles), batch_tiles):
             chunk = me.tiles[i:i + batch_tiles]
             engine.wsi_push_from_slide(strip_dev, me.acc_y0, me.acc_rows, [p[0] for p in chunk], [p[1] for p in chunk],
                                        float(mean), float(std), ops)
+        lap("tiles")
     # ---- boundary exchange (rank order => deterministic summation order)
     for (src, dst, y, rows) in boundary_transfers(strips):
         if src == rank:
@@ -125,12 +140,17 @@ def reconstruct_wsi(engine, slide_rows: Callable[[int, int], np.ndarray], h: int
         elif dst == rank:
             buf = _recv(dist, (2, rows, w), src)
             engine.wsi_import_add(y, buf[0], buf[1])
+    lap("boundary_exchange")
     if me.tiles:
         rows = me.own_hi - me.own_lo
         gt = gt_rows(me.own_lo, rows) if gt_rows is not None else None
+        lap("gt_assembly")
         prob, mask, counts = engine.wsi_finalize(me.own_lo, rows, w, threshold, gt, want_prob, want_mask)
         engine.wsi_end()
+        lap("finalize")
         result.update(prob=prob, mask=mask, counts=counts)
+    if timings:
+        result["timings"] = {k: round(v, 4) for k, v in ph.items()}
     return result
 
 
