@@ -274,9 +274,14 @@ class Engine:
         _lib.check(self.lib.adp_wsi_export(self.h, y, rows, _lib.ptr(acc), _lib.ptr(wt)))
         return acc, wt
 
+    def wsi_export_into(self, y, rows, acc, wt):
+        """Raw accumulator rows into caller buffers (NumPy arrays or device tensors with data_ptr())."""
+        _lib.check(self.lib.adp_wsi_export(self.h, y, rows, _lib.ptr(acc), _lib.ptr(wt)))
+
     def wsi_import_add(self, y, acc, wt):
-        acc = _f32c(acc); wt = _f32c(wt)
-        _lib.check(self.lib.adp_wsi_import_add(self.h, y, acc.shape[0], _lib.ptr(acc), _lib.ptr(wt)))
+        if isinstance(acc, np.ndarray):
+            acc = _f32c(acc); wt = _f32c(wt)
+        _lib.check(self.lib.adp_wsi_import_add(self.h, y, int(acc.shape[0]), _lib.ptr(acc), _lib.ptr(wt)))
 
     def wsi_finalize(self, y, rows, W, threshold=0.5, gt=None, want_prob=True, want_mask=True):
         prob = np.empty((rows, W), np.float32) if want_prob else None

@@ -108,7 +108,7 @@ size_t tc_smem_bytes(const ConvTcParams &p) {
   return (size_t)p.S * p.stage_stride + (2 * p.S + 6) * 8 + (704 + 520) * 4;
 }
 
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 352;   // producer, MMA issuer A, 8 epilogue warps, MMA issuer B
 constexpr int EPI_STORE = 0, EPI_HEAD = 1, EPI_POOL = 2, EPI_BWD = 3;   // EPI_BWD = EPI_STORE with a mask (data-gradient twin)
 
 // Software-pipelined walk over 16-column accumulator units u0, u0+step, ... < uend: the TMEM load
@@ -184,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
   }
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < p.S; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < p.S; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 2); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 8); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmap);
@@ -225,10 +225,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
       }
       if (p.dbg & 16) { p.dbg_out[blockIdx.x * 8 + 0] = t_w0; p.dbg_out[blockIdx.x * 8 + 1] = clock64() - t_start; }
     }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
+  } else if (warp == 1 || warp == 10) {
+    // ---------------- MMA issuers ----------------
+    // Two issuing threads alternate work items (A: even, B: odd).  An item owns its accumulator buffer (it & 1) and its
+    // own run of pipeline stages, so the two instruction streams are independent; while one thread is blocked in a
+    // tcgen05.mma issue slot the other prepares descriptors.  (Measured with tools/tc_timers.sh: one issuing thread was
+    // > 85 % busy on the 1024^2 layers - ~50 cycles of descriptor arithmetic per MMA - while no pipe was saturated.)
     if (ptx::elect_one()) {
+      const int issuer = (warp == 10) ? 1 : 0;
       int st = 0; uint32_t ph = 0;
+      // The other issuer's stages are still OBSERVED: an mbarrier parity wait is only meaningful for a waiter that sees
+      // every phase of the barrier in order, so the skipping thread waits for each stage's 'full' phase and then arrives on
+      // its 'empty' barrier (count 2: the consuming issuer's tcgen05.commit + this arrive) - the producer cannot run a
+      // stage two phases ahead of either issuer.
+      auto skip_item = [&]() {
+        for (int c = 0; c < p.nchunks; ++c) {
+          ptx::mbar_wait(&full[st], ph, 5);
+          ptx::mbar_arrive(&empty[st]);
+          if (++st == p.S) { st = 0; ph ^= 1; }
+        }
+      };
       const uint32_t plane_a = (uint32_t)p.PW * 16u;          // bytes between the two channel-group planes (A)
       const uint32_t plane_b = (uint32_t)p.N * 16u;           // same for B
       // descriptor = hi (SBO = 128 B, version 1) : lo (start >> 4 | LBO >> 4 << 16); only the start moves
@@ -253,6 +269,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
         const uint32_t id1 = p.idesc_stack[0], id2 = p.idesc_stack[1], id3 = p.idesc_stack[2];
         int it = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+          if ((it & 1) != issuer) { skip_item(); continue; }
           const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
           { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3); if (p.dbg & 16) t_m0 += clock64() - tw; }
           ptx::tc_fence_after();
@@ -308,6 +325,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
       const uint32_t idesc = p.idesc;
       int it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        if ((it & 1) != issuer) { skip_item(); continue; }
         const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
         { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3); if (p.dbg & 16) t_m0 += clock64() - tw; }
         ptx::tc_fence_after();
@@ -333,7 +351,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
         { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mma_commit(&acc_full[buf]); if (p.dbg & 16) t_m2 += clock64() - tw; }
       }
       }
-      if (p.dbg & 16) { p.dbg_out[blockIdx.x * 8 + 2] = t_m0; p.dbg_out[blockIdx.x * 8 + 3] = t_m1; p.dbg_out[blockIdx.x * 8 + 4] = clock64() - t_mstart; p.dbg_out[blockIdx.x * 8 + 7] = t_m2; }
+      if ((p.dbg & 16) && issuer == 0) { p.dbg_out[blockIdx.x * 8 + 2] = t_m0; p.dbg_out[blockIdx.x * 8 + 3] = t_m1; p.dbg_out[blockIdx.x * 8 + 4] = clock64() - t_mstart; p.dbg_out[blockIdx.x * 8 + 7] = t_m2; }
     }
   } else {
     // ---------------- epilogue (warps 2..9; TMEM lane quarter = warp % 4, two warps per quarter) ----------------

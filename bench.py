@@ -244,6 +244,7 @@ def run_ours(args, rank, world, local_rank):
             return W.reconstruct_wsi(eng, slide_rows, Hs, Ws, tile=TILE, overlap=0.5, blend_mode="gaussian", window=win,
                                      mean=mean, std=std, tta_mode="full", rank=rank, world=world, dist=dist,
                                      to_device=lambda a: torch.from_numpy(a).cuda(), want_prob=False, want_mask=True)
+        W.warmup_peer_channels(dist, rank, world, local_rank)
         barrier()
         t0 = time.perf_counter()
         r = run_wsi()

@@ -66,6 +66,7 @@ def main():
     # warm-up: one small slide through the same path (allocations, tensor maps)
     W.reconstruct_wsi(eng, lambda y0, r: slide_rows(y0, r)[:, :2048], 2048, 2048, tile=TILE, overlap=0.5, blend_mode=a.blend, window=win,
                       tta_mode=None, rank=0, world=1, to_device=lambda x: torch.from_numpy(x).cuda(), want_prob=False)
+    W.warmup_peer_channels(dist, rank, world, local)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
