@@ -62,10 +62,12 @@ SIGNATURES = {
     "adp_wsi_finalize": (_I, [_P, _I, _I, _F, _P, _P, _P, C.POINTER(_I64)]),
     "adp_wsi_end": (_I, [_P]),
     "adp_loss_metrics": (_I, [_P, _P, _P, _I64, _P, C.POINTER(C.c_double)]),
+    "adp_loss_metrics_ex": (_I, [_P, _P, _P, _I, _I64, _F, _F, _F, _P, C.POINTER(C.c_double)]),
+    "adp_train_set_loss": (_I, [_P, _F, _F, _F]),
     "adp_train_begin": (_I, [_P, _I, _I, _F, C.c_uint64]),
     "adp_train_forward": (_I, [_P, _P, _P, _I, C.POINTER(_P), C.POINTER(C.c_double)]),
-    "adp_train_loss": (_I, [C.POINTER(C.c_double), _I64, C.POINTER(C.c_double)]),
-    "adp_train_backward": (_I, [_P, C.POINTER(C.c_double), _I64, _I]),
+    "adp_train_loss": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "adp_train_backward": (_I, [_P, C.POINTER(C.c_double), _I]),
     "adp_train_grad_buffer": (_I, [_P, C.POINTER(_P), C.POINTER(_I64)]),
     "adp_train_grad_read": (_I, [_P, _P, _I64]),
     "adp_train_grad_write": (_I, [_P, _P, _I64]),

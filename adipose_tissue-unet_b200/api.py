@@ -140,11 +140,16 @@ class Engine:
                                                   _lib.ptr(win), h, w, _lib.ptr(out)))
         return out
 
-    def loss_metrics(self, p, y, want_grad: bool = False):
+    def loss_metrics(self, p, y, want_grad: bool = False, ohem_keep_ratio: float = 1.0, eps_pos: float = 0.0,
+                     eps_neg: float = 0.0):
+        """combined_loss_standard by default; ohem_keep_ratio < 1 / eps_* > 0 select the reference's hard-mining and
+        label-smoothing losses.  p, y: (B, H, W) (or a single image)."""
         p = _f32c(p); y = _f32c(y)
         out = (C.c_double * 4)()
         g = np.empty(p.shape, np.float32) if want_grad else None
-        _lib.check(self.lib.adp_loss_metrics(self.h, _lib.ptr(p), _lib.ptr(y), p.size, _lib.ptr(g), out))
+        batch = p.shape[0] if p.ndim == 3 else 1
+        _lib.check(self.lib.adp_loss_metrics_ex(self.h, _lib.ptr(p), _lib.ptr(y), batch, p.size // batch, ohem_keep_ratio, eps_pos,
+                                                eps_neg, _lib.ptr(g), out))
         res = dict(loss=out[0], bce=out[1], dice_loss=out[2], dice_coef=out[3])
         return (res, g) if want_grad else res
 
@@ -157,12 +162,12 @@ class Engine:
 
     def train_forward(self, x, y, dropout_masks: Optional[Dict[str, np.ndarray]] = None) -> np.ndarray:
         """x, y: (B,S,S) float32 (normalised image, target).  dropout_masks: site name -> (B,h,w,C) 0/1.
-        Returns the six loss sums (float64) of this batch."""
+        Returns the eight loss sums (float64) of this batch (include/adipose_b200.h)."""
         if isinstance(x, np.ndarray):
             x = _f32c(x)
         if isinstance(y, np.ndarray):
             y = _f32c(y)
-        sums = (C.c_double * 6)()
+        sums = (C.c_double * 8)()
         mptr = None
         keep = []
         if dropout_masks is not None:
@@ -175,15 +180,19 @@ class Engine:
         _lib.check(self.lib.adp_train_forward(self.h, _lib.ptr(x), _lib.ptr(y), int(x.shape[0]), mptr, sums))
         return np.array(list(sums), dtype=np.float64)
 
-    def train_loss(self, sums, n_px: int) -> Dict[str, float]:
-        s = (C.c_double * 6)(*[float(v) for v in sums])
+    def train_set_loss(self, ohem_keep_ratio: float = 1.0, eps_pos: float = 0.0, eps_neg: float = 0.0):
+        """Loss recipe of the following steps (train_adipose_unet_v3.py:808-855)."""
+        _lib.check(self.lib.adp_train_set_loss(self.h, ohem_keep_ratio, eps_pos, eps_neg))
+
+    def train_loss(self, sums) -> Dict[str, float]:
+        s = (C.c_double * 8)(*[float(v) for v in sums])
         out = (C.c_double * 4)()
-        _lib.check(self.lib.adp_train_loss(s, int(n_px), out))
+        _lib.check(self.lib.adp_train_loss(s, out))
         return dict(loss=out[0], bce=out[1], dice_loss=out[2], dice_coef=out[3])
 
-    def train_backward(self, sums, n_px_global: int = 0, freeze_encoder: bool = False):
-        s = (C.c_double * 6)(*[float(v) for v in sums])
-        _lib.check(self.lib.adp_train_backward(self.h, s, int(n_px_global), 1 if freeze_encoder else 0))
+    def train_backward(self, sums, freeze_encoder: bool = False):
+        s = (C.c_double * 8)(*[float(v) for v in sums])
+        _lib.check(self.lib.adp_train_backward(self.h, s, 1 if freeze_encoder else 0))
 
     def train_grad_buffer(self) -> Tuple[int, int]:
         """(device address, element count) of the flat fp32 gradient — what a data-parallel wrapper all-reduces."""

@@ -6,10 +6,11 @@ backward, Keras Adam/AdamW; include/adipose_b200.h adp_train_*), optionally data
 What stays on the host, as in the reference: tile files, shuffling, augmentation, the epoch loop, the cosine/warm-up
 schedule (:393-404), best-checkpoint bookkeeping, EMA of the weights (:407-505) and the log files.
 
-Recipe coverage: the reference's DEFAULT recipe adds deep-supervision heads, OHEM and
-optional label smoothing on top of the standard loss.  Those are not in this engine yet: with those flags left at their
-defaults the run says so and trains the standard single-output model (== `--no-deep-supervision --no-hard-mining`);
-training_settings.log records `use_deep_supervision: False` so the evaluation scripts build the matching graph."""
+Recipe coverage: hard-example mining (--use-hard-mining, --hard-example-ratio) and
+asymmetric label smoothing (--use-label-smoothing, --label-smooth-epsilon-*) run on the device (adp_train_set_loss);
+the deep-supervision heads of the reference's DEFAULT recipe are not in this engine yet: with --use-deep-supervision
+left on, the run says so and trains the single-output model; training_settings.log records
+`use_deep_supervision: False` so the evaluation scripts build the matching graph."""
 from __future__ import annotations
 
 import argparse
@@ -154,10 +155,11 @@ def main(argv=None) -> int:
         dist = dist_
     log = print if rank == 0 else (lambda *a, **k: None)
     log("=" * 80 + "\nTRAIN ADIPOSE U-NET VERSION 3.1 (B200 engine)\n" + "=" * 80)
-    for flag, name in ((args.use_deep_supervision, "deep supervision"), (args.use_hard_mining, "hard example mining"),
-                       (args.use_label_smoothing, "label smoothing")):
-        if flag:
-            log(f"⚠️  {name}: not implemented in this engine yet - training the standard BCE+Dice single-output recipe")
+    if args.use_deep_supervision:
+        log("⚠️  deep supervision: auxiliary heads are not implemented in this engine yet - training the single-output model")
+    log("✓ Hard example mining:", f"ENABLED (keep {args.hard_example_ratio})" if args.use_hard_mining else "DISABLED")
+    log("✓ Label smoothing:", f"ENABLED (eps_pos={args.label_smooth_epsilon_pos}, eps_neg={args.label_smooth_epsilon_neg})"
+        if args.use_label_smoothing else "DISABLED")
     data_root = Path(args.data_root)
     tr_img, tr_msk = data_root / "dataset" / "train" / "images", data_root / "dataset" / "train" / "masks"
     va_img, va_msk = data_root / "dataset" / "val" / "images", data_root / "dataset" / "val" / "masks"
@@ -183,8 +185,7 @@ def main(argv=None) -> int:
         with open(ckpt / "training_settings.log", "w") as f:                         # :984-1053 (sniffed at eval:513-516)
             f.write("=" * 80 + "\nTRAINING SETTINGS LOG - VERSION 3\n" + "=" * 80 + f"\n\nGenerated: {stamp}\n")
             f.write("Script: adipose_unet_b200.cli.train\n" + f"Checkpoint Directory: {ckpt}\n\n" + "-" * 60 + "\nCOMMAND LINE ARGUMENTS\n" + "-" * 60 + "\n")
-            settings = dict(vars(args)); settings["use_deep_supervision"] = False; settings["use_hard_mining"] = False
-            settings["use_label_smoothing"] = False
+            settings = dict(vars(args)); settings["use_deep_supervision"] = False
             for k, v in settings.items():
                 f.write(f"  {k}: {v}\n")
             f.write("\n" + "-" * 60 + "\nMACHINE READABLE FORMAT (JSON)\n" + "-" * 60 + "\n" + json.dumps(settings, indent=2, default=str) + "\n")
@@ -195,6 +196,9 @@ def main(argv=None) -> int:
     else:
         log("WARNING: No pretrained weights found, training from scratch")
         engine.set_weights(synth.init_weights(seed=args.seed))
+    engine.train_set_loss(args.hard_example_ratio if args.use_hard_mining else 1.0,
+                          args.label_smooth_epsilon_pos if args.use_label_smoothing else 0.0,
+                          args.label_smooth_epsilon_neg if args.use_label_smoothing else 0.0)
     rng = np.random.RandomState(args.seed + rank)
     best_overall = -1.0
     ema = None

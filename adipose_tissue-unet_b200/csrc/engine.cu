@@ -149,6 +149,7 @@ struct adp_engine {
   int dbg = 0;
   bool fuse_head = true, fuse_pool = true;   // tcgen05 path only
   bool kys = true;                           // ky-stacked MMA issue for the N <= 128 layers
+  LossRecipe loss;                           // adp_train_set_loss: hard-example mining / label smoothing of the training loss
   bool wgrad_simt = false, dgrad_simt = false;   // bf16 training: CUDA-core cross-check of the tcgen05 backward kernels
 
   template <typename F> void launch(const char *kind, double flops, double bytes, F &&f) {
@@ -775,6 +776,104 @@ void run_finalize(adp_engine *e, const float *acc, const float *wsum, int linear
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// Loss recipes (kernels_post.cuh): sums[8] = {S0 selected-BCE sum, S1 sum ys*pc, S2 sum ys, S3 sum pc, S4 sum y*p, S5 sum p,
+// S6 sum y, S7 number of BCE terms in the mean}.  Every entry is additive over data-parallel ranks.
+struct LossState {
+  DevBuf sums, bce, hist, prefix, tau, tie, sum_gt;
+  std::vector<uint32_t> tau_h;
+  std::vector<float> tie_h;
+  bool ohem = false;
+};
+
+void loss_from_sums8(const double s[8], double out[4]) {
+  const double bce = s[0] / s[7];
+  const double dice_loss = 1.0 - (2.0 * s[1] + 1.0) / (s[2] + s[3] + 1.0);
+  out[0] = bce + dice_loss; out[1] = bce; out[2] = dice_loss;
+  out[3] = (2.0 * s[4] + 1.0) / (s[6] + s[5] + 1.0);
+}
+
+// forward part: the eight sums of `batch` images of npi pixels each (p, y device pointers)
+void loss_forward(adp_engine *e, LossState &ls, const LossRecipe &r, const float *p, const float *y, int batch, size_t npi, double s[8]) {
+  const size_t n = (size_t)batch * npi;
+  ls.ohem = r.ohem_keep < 1.f;
+  ls.sums.ensure(64);
+  ADP_CUDA(cudaMemsetAsync(ls.sums.p, 0, 64, e->stream));
+  if (ls.ohem) ls.bce.ensure(n * 4);
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>(cdiv64(n, 256 * 4), (size_t)e->num_sms * 8));
+  e->launch("loss_reduce", 0, (double)n * (ls.ohem ? 12 : 8), [&] {
+    loss_reduce_kernel<<<grid, 256, 0, e->stream>>>(p, y, n, r.ys_scale(), r.eps_neg, ls.ohem ? ls.bce.as<float>() : nullptr,
+                                                   ls.sums.as<double>());
+  });
+  ADP_CUDA(cudaMemcpyAsync(s, ls.sums.p, 56, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  s[7] = (double)n;
+  if (!ls.ohem) return;
+  // top-k per image: k = int(float(npix) * keep_ratio) (train_adipose_unet_v3.py:307-311)
+  const long long k = (long long)((float)npi * r.ohem_keep);
+  ADP_REQUIRE(k >= 1 && k <= (long long)npi, "hard-example ratio selects no pixel");
+  ls.hist.ensure((size_t)batch * 4096 * 4); ls.prefix.ensure((size_t)batch * 4); ls.tau.ensure((size_t)batch * 4);
+  ls.tie.ensure((size_t)batch * 4); ls.sum_gt.ensure((size_t)batch * 8);
+  std::vector<uint32_t> prefix(batch, 0u), hist((size_t)batch * 4096);
+  std::vector<long long> rank(batch, k), n_gt(batch, 0), n_eq(batch, 0);
+  const dim3 hgrid((unsigned)std::max<size_t>(1, std::min<size_t>(cdiv64(npi, 256 * 8), (size_t)e->num_sms * 2)), (unsigned)batch);
+  const int shifts[3] = {20, 8, 0}, bits[3] = {12, 12, 8};
+  for (int d = 0; d < 3; ++d) {
+    ADP_CUDA(cudaMemcpyAsync(ls.prefix.p, prefix.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, e->stream));
+    ADP_CUDA(cudaMemsetAsync(ls.hist.p, 0, (size_t)batch * 4096 * 4, e->stream));
+    e->launch("ohem_select", 0, (double)n * 4, [&] {
+      ohem_hist_kernel<<<hgrid, 256, 0, e->stream>>>(ls.bce.as<float>(), npi, ls.prefix.as<uint32_t>(), shifts[d], bits[d],
+                                                    ls.hist.as<unsigned int>());
+    });
+    ADP_CUDA(cudaMemcpyAsync(hist.data(), ls.hist.p, (size_t)batch * 4096 * 4, cudaMemcpyDeviceToHost, e->stream));
+    ADP_CUDA(cudaStreamSynchronize(e->stream));
+    for (int b = 0; b < batch; ++b) {
+      const uint32_t *h = hist.data() + (size_t)b * 4096;
+      long long need = rank[b];
+      int bin = (1 << bits[d]) - 1;
+      for (; bin > 0; --bin) {
+        if ((long long)h[bin] >= need) break;
+        need -= h[bin]; n_gt[b] += h[bin];
+      }
+      rank[b] = need;                       // rank of tau inside the chosen bin
+      prefix[b] = (prefix[b] << bits[d]) | (uint32_t)bin;
+      if (d == 2) n_eq[b] = h[bin];
+    }
+  }
+  ls.tau_h = prefix;
+  ls.tie_h.resize(batch);
+  for (int b = 0; b < batch; ++b) ls.tie_h[b] = (float)((double)(k - n_gt[b]) / (double)std::max<long long>(n_eq[b], 1));
+  ADP_CUDA(cudaMemcpyAsync(ls.tau.p, ls.tau_h.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, e->stream));
+  ADP_CUDA(cudaMemcpyAsync(ls.tie.p, ls.tie_h.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, e->stream));
+  ADP_CUDA(cudaMemsetAsync(ls.sum_gt.p, 0, (size_t)batch * 8, e->stream));
+  e->launch("ohem_sum", 0, (double)n * 4, [&] {
+    ohem_sum_kernel<<<hgrid, 256, 0, e->stream>>>(ls.bce.as<float>(), npi, ls.tau.as<uint32_t>(), ls.sum_gt.as<double>());
+  });
+  std::vector<double> sg(batch);
+  ADP_CUDA(cudaMemcpyAsync(sg.data(), ls.sum_gt.p, (size_t)batch * 8, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  double sel = 0;
+  for (int b = 0; b < batch; ++b) {
+    float tau; uint32_t tb = ls.tau_h[b]; memcpy(&tau, &tb, 4);
+    sel += sg[b] + (double)(k - n_gt[b]) * (double)tau;
+  }
+  s[0] = sel;
+  s[7] = (double)batch * (double)k;
+}
+
+// backward part: dL/dp for the loss defined by the (possibly rank-summed) sums
+void loss_backward(adp_engine *e, LossState &ls, const LossRecipe &r, const float *p, const float *y, int batch, size_t npi,
+                   const double s[8], float *dldp) {
+  const size_t n = (size_t)batch * npi;
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>(cdiv64(n, 256 * 4), (size_t)e->num_sms * 8));
+  const double denom = s[2] + s[3] + 1.0;
+  e->launch("loss_grad", 0, (double)n * 12, [&] {
+    loss_grad_kernel<<<grid, 256, 0, e->stream>>>(p, y, n, r.ys_scale(), r.eps_neg, (float)(1.0 / s[7]), (float)(2.0 * s[1] + 1.0),
+                                                 (float)denom, ls.ohem ? ls.tau.as<uint32_t>() : nullptr,
+                                                 ls.ohem ? ls.tie.as<float>() : nullptr, npi, dldp);
+  });
+}
+
 #include "train_host.cuh"
 
 // ================================================================================================
@@ -1230,40 +1329,35 @@ int adp_wsi_end(adp_engine *e) {
   ADP_CATCH
 }
 
-int adp_loss_metrics(adp_engine *e, const float *p, const float *y, int64_t n_px, float *dldp, double out[4]) {
+int adp_loss_metrics_ex(adp_engine *e, const float *p, const float *y, int batch, int64_t px_per_image, float ohem_keep_ratio,
+                        float eps_pos, float eps_neg, float *dldp, double out[4]) {
   ADP_TRY
-  ADP_REQUIRE(e && p && y && out && n_px > 0, "null/empty argument");
+  ADP_REQUIRE(e && p && y && out && batch > 0 && px_per_image > 0, "null/empty argument");
+  ADP_REQUIRE(ohem_keep_ratio > 0.f && ohem_keep_ratio <= 1.f && eps_pos >= 0.f && eps_neg >= 0.f && eps_pos + eps_neg < 1.f,
+              "loss recipe out of range");
   ADP_CUDA(cudaSetDevice(e->device));
   DevBuf dp, dy, dg;
-  const size_t n = (size_t)n_px;
+  const size_t n = (size_t)batch * (size_t)px_per_image;
   const float *pp = reinterpret_cast<const float *>(to_device(e, dp, p, n * 4));
   const float *yy = reinterpret_cast<const float *>(to_device(e, dy, y, n * 4));
-  e->misc.ensure(64);
-  ADP_CUDA(cudaMemsetAsync(e->misc.p, 0, 64, e->stream));
-  const int grid = (int)std::min<size_t>(cdiv64(n, 256 * 4), (size_t)e->num_sms * 8);
-  e->launch("loss_reduce", 0, (double)n * 8, [&] {
-    loss_reduce_kernel<<<std::max(grid, 1), 256, 0, e->stream>>>(pp, yy, n, e->misc.as<double>());
-  });
-  double s[6];
-  ADP_CUDA(cudaMemcpyAsync(s, e->misc.p, 48, cudaMemcpyDeviceToHost, e->stream));
-  ADP_CUDA(cudaStreamSynchronize(e->stream));
-  const double bce = s[0] / (double)n;
-  const double denom = s[2] + s[3] + 1.0;
-  const double dice_loss = 1.0 - (2.0 * s[1] + 1.0) / denom;
-  out[0] = bce + dice_loss; out[1] = bce; out[2] = dice_loss;
-  out[3] = (2.0 * s[4] + 1.0) / (s[2] + s[5] + 1.0);
+  LossRecipe r; r.ohem_keep = ohem_keep_ratio; r.eps_pos = eps_pos; r.eps_neg = eps_neg;
+  LossState ls;
+  double s[8];
+  loss_forward(e, ls, r, pp, yy, batch, (size_t)px_per_image, s);
+  loss_from_sums8(s, out);
   if (dldp) {
     const bool host = !is_device_ptr(dldp);
     float *g = dldp;
     if (host) { dg.ensure(n * 4); g = dg.as<float>(); }
-    e->launch("loss_grad", 0, (double)n * 12, [&] {
-      loss_grad_kernel<<<std::max(grid, 1), 256, 0, e->stream>>>(pp, yy, n, (float)(1.0 / (double)n), (float)(2.0 * s[1] + 1.0),
-                                                                (float)denom, g);
-    });
+    loss_backward(e, ls, r, pp, yy, batch, (size_t)px_per_image, s, g);
     if (host) ADP_CUDA(cudaMemcpyAsync(dldp, g, n * 4, cudaMemcpyDeviceToHost, e->stream));
     ADP_CUDA(cudaStreamSynchronize(e->stream));
   }
   ADP_CATCH
+}
+
+int adp_loss_metrics(adp_engine *e, const float *p, const float *y, int64_t n_px, float *dldp, double out[4]) {
+  return adp_loss_metrics_ex(e, p, y, 1, n_px, 1.f, 0.f, 0.f, dldp, out);
 }
 
 int adp_train_begin(adp_engine *e, int batch, int size, float dropout_rate, uint64_t seed) {
@@ -1277,7 +1371,7 @@ int adp_train_begin(adp_engine *e, int batch, int size, float dropout_rate, uint
 }
 
 int adp_train_forward(adp_engine *e, const float *x, const float *y, int batch, const uint8_t *const *dropout_masks,
-                      double sums[6]) {
+                      double sums[8]) {
   ADP_TRY
   ADP_REQUIRE(e && x && y && sums, "null argument");
   ADP_CUDA(cudaSetDevice(e->device));
@@ -1285,17 +1379,26 @@ int adp_train_forward(adp_engine *e, const float *x, const float *y, int batch, 
   ADP_CATCH
 }
 
-int adp_train_loss(const double sums[6], int64_t n_px, double out[4]) {
-  if (!sums || !out || n_px <= 0) return ADP_EINVAL;
-  loss_from_sums(sums, (double)n_px, out);
+int adp_train_loss(const double sums[8], double out[4]) {
+  if (!sums || !out || !(sums[7] > 0)) return ADP_EINVAL;
+  loss_from_sums8(sums, out);
   return ADP_OK;
 }
 
-int adp_train_backward(adp_engine *e, const double sums[6], int64_t n_px_global, int freeze_encoder) {
+int adp_train_set_loss(adp_engine *e, float ohem_keep_ratio, float eps_pos, float eps_neg) {
+  ADP_TRY
+  ADP_REQUIRE(e, "engine");
+  ADP_REQUIRE(ohem_keep_ratio > 0.f && ohem_keep_ratio <= 1.f && eps_pos >= 0.f && eps_neg >= 0.f && eps_pos + eps_neg < 1.f,
+              "loss recipe out of range");
+  e->loss.ohem_keep = ohem_keep_ratio; e->loss.eps_pos = eps_pos; e->loss.eps_neg = eps_neg;
+  ADP_CATCH
+}
+
+int adp_train_backward(adp_engine *e, const double sums[8], int freeze_encoder) {
   ADP_TRY
   ADP_REQUIRE(e && sums, "null argument");
   ADP_CUDA(cudaSetDevice(e->device));
-  train_backward(e, sums, n_px_global, freeze_encoder != 0);
+  train_backward(e, sums, freeze_encoder != 0);
   ADP_CATCH
 }
 
@@ -1381,10 +1484,10 @@ int adp_train_step(adp_engine *e, const float *x, const float *y, int batch, int
   ADP_REQUIRE(e && x && y, "null argument");
   ADP_REQUIRE(optimizer == ADP_OPT_ADAM || optimizer == ADP_OPT_ADAMW, "optimizer");
   ADP_CUDA(cudaSetDevice(e->device));
-  double sums[6];
+  double sums[8];
   train_forward(e, x, y, batch, nullptr, sums);
-  if (out) loss_from_sums(sums, (double)batch * e->tr->S * e->tr->S, out);
-  train_backward(e, sums, 0, freeze_encoder != 0);
+  if (out) loss_from_sums8(sums, out);
+  train_backward(e, sums, freeze_encoder != 0);
   train_apply(e, optimizer, lr, 1.f, 0.9, 0.999, 1e-7f, weight_decay, freeze_encoder != 0);
   ADP_CATCH
 }

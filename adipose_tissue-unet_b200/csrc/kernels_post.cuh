@@ -160,42 +160,112 @@ finalize_kernel(const float *__restrict__ acc, const float *__restrict__ wsum, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// combined_loss_standard (train_adipose_unet_v3.py:217-241) and dice_coef (src/utils/model.py:93-98).
-// Pass 1: five global sums in float64: S_bce = sum bce_i, S_yp = sum y*pc, S_y = sum y, S_pc = sum pc,
-//         S_yp_raw = sum y*p, S_p = sum p  (pc = clip(p, 1e-7, 1-1e-7)).
-// Pass 2 (host forms the scalars): dL/dp_i = dbce_i/N + ddice_i with
-//   dbce_i  = -( y/(pc+eps) - (1-y)/(1-pc+eps) ) * [eps <= p <= 1-eps]
-//   ddice_i = -( 2*y*D - (2I+1) ) / D^2 * [eps <= p <= 1-eps],  I = S_yp, D = S_y + S_pc + 1
-__global__ void __launch_bounds__(256)
-loss_reduce_kernel(const float *__restrict__ p, const float *__restrict__ y, size_t n, double *__restrict__ sums) {
-  double sb = 0, syp = 0, sy = 0, spc = 0, sypr = 0, sp = 0;
+// Loss family of the reference (train_adipose_unet_v3.py:217-363) and dice_coef (src/utils/model.py:93-98):
+//   combined_loss_standard                       bce_mean(y, p) + dice_loss(y, p)
+//   combined_loss_with_label_smoothing           same on ys = y*(1 - eps_pos - eps_neg) + eps_neg          (:244-279)
+//   online_hard_example_mining_loss[_with_smoothing]   mean of the top-k per-image BCE values (k = int(npix*ratio))
+//                                                + dice_loss over all pixels                               (:282-363)
+// Pass 1 (loss_reduce_kernel): float64 sums  S0 = sum bce_i, S1 = sum ys*pc, S2 = sum ys, S3 = sum pc,
+//         S4 = sum y*p, S5 = sum p, S6 = sum y  (pc = clip(p, 1e-7, 1-1e-7); the metric dice_coef uses the raw y);
+//         optionally the per-pixel BCE values are kept for the top-k selection.
+// OHEM:   per image a three-digit radix select (12 + 12 + 8 bits of the non-negative float's bit pattern,
+//         ohem_hist_kernel + a short host scan per digit) finds tau = the k-th largest BCE value; ohem_sum_kernel adds
+//         the values above tau; the k - n_gt entries equal to tau count with weight (k - n_gt)/n_eq each (TensorFlow's
+//         top_k breaks ties arbitrarily; ties carry no gradient where the clip is active).
+// Pass 2 (loss_grad_kernel; the host forms the scalars): dL/dp_i = w_i * dbce_i / N + ddice_i with
+//   dbce_i  = -( ys/(pc+eps) - (1-ys)/(1-pc+eps) ) * [eps <= p <= 1-eps]
+//   ddice_i = -( 2*ys*D - (2I+1) ) / D^2 * [eps <= p <= 1-eps],  I = S1, D = S2 + S3 + 1
+//   N = number of BCE terms in the mean (all pixels, or batch*k), w_i = OHEM selection weight (1 without OHEM)
+struct LossRecipe {
+  float ohem_keep = 1.f;     // 1 = no hard-example mining
+  float eps_pos = 0.f, eps_neg = 0.f;
+  __host__ __device__ float ys_scale() const { return 1.0f - eps_pos - eps_neg; }
+};
+
+ADP_DEVINL float bce_term(float pv, float ys) {
   const float eps = 1e-7f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    float pv = p[i], yv = y[i];
-    float pc = fminf(fmaxf(pv, eps), 1.0f - eps);
-    float bce = -(yv * logf(pc + eps) + (1.0f - yv) * logf(1.0f - pc + eps));
-    sb += bce; syp += (double)yv * pc; sy += yv; spc += pc; sypr += (double)yv * pv; sp += pv;
-  }
-  sb = warp_sum_d(sb); syp = warp_sum_d(syp); sy = warp_sum_d(sy); spc = warp_sum_d(spc);
-  sypr = warp_sum_d(sypr); sp = warp_sum_d(sp);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&sums[0], sb); atomicAdd(&sums[1], syp); atomicAdd(&sums[2], sy);
-    atomicAdd(&sums[3], spc); atomicAdd(&sums[4], sypr); atomicAdd(&sums[5], sp);
-  }
+  const float pc = fminf(fmaxf(pv, eps), 1.0f - eps);
+  return -(ys * logf(pc + eps) + (1.0f - ys) * logf(1.0f - pc + eps));
 }
 
 __global__ void __launch_bounds__(256)
-loss_grad_kernel(const float *__restrict__ p, const float *__restrict__ y, size_t n, float inv_n, float inter2p1,
-                 float denom, float *__restrict__ dldp) {
+loss_reduce_kernel(const float *__restrict__ p, const float *__restrict__ y, size_t n, float ys_a, float ys_b,
+                   float *__restrict__ bce_out /* or null */, double *__restrict__ sums) {
+  double sb = 0, syp = 0, sy = 0, spc = 0, sypr = 0, sp = 0, syr = 0;
+  const float eps = 1e-7f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float pv = p[i], yr = y[i];
+    const float yv = yr * ys_a + ys_b;
+    const float pc = fminf(fmaxf(pv, eps), 1.0f - eps);
+    const float bce = -(yv * logf(pc + eps) + (1.0f - yv) * logf(1.0f - pc + eps));
+    if (bce_out) bce_out[i] = fmaxf(bce, 0.f);          // -0.0 -> +0.0: the bit pattern is the sort key
+    sb += bce; syp += (double)yv * pc; sy += yv; spc += pc; sypr += (double)yr * pv; sp += pv; syr += yr;
+  }
+  sb = warp_sum_d(sb); syp = warp_sum_d(syp); sy = warp_sum_d(sy); spc = warp_sum_d(spc);
+  sypr = warp_sum_d(sypr); sp = warp_sum_d(sp); syr = warp_sum_d(syr);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sums[0], sb); atomicAdd(&sums[1], syp); atomicAdd(&sums[2], sy);
+    atomicAdd(&sums[3], spc); atomicAdd(&sums[4], sypr); atomicAdd(&sums[5], sp); atomicAdd(&sums[6], syr);
+  }
+}
+
+// One radix digit of the per-image top-k select.  Elements whose bits above `shift + nbits` equal prefix[image]
+// are counted by their digit (bits [shift, shift+nbits)).  grid = (blocks per image, images).
+__global__ void __launch_bounds__(256)
+ohem_hist_kernel(const float *__restrict__ bce, size_t npi, const uint32_t *__restrict__ prefix, int shift, int nbits,
+                 unsigned int *__restrict__ hist /*[images][4096]*/) {
+  __shared__ unsigned int h[4096];
+  const int img = blockIdx.y;
+  const int nb = 1 << nbits;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  const int hi_shift = shift + nbits;
+  const uint32_t pre = prefix[img];
+  const float *b = bce + (size_t)img * npi;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npi; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t u = __float_as_uint(b[i]);
+    if (hi_shift >= 32 || (u >> hi_shift) == pre) atomicAdd(&h[(u >> shift) & (uint32_t)(nb - 1)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x)
+    if (h[i]) atomicAdd(&hist[(size_t)img * 4096 + i], h[i]);
+}
+
+// sum of the BCE values strictly above tau (per image, float64)
+__global__ void __launch_bounds__(256)
+ohem_sum_kernel(const float *__restrict__ bce, size_t npi, const uint32_t *__restrict__ tau_bits, double *__restrict__ sum_gt) {
+  const int img = blockIdx.y;
+  const uint32_t t = tau_bits[img];
+  const float *b = bce + (size_t)img * npi;
+  double s = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npi; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = b[i];
+    if (__float_as_uint(v) > t) s += v;
+  }
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sum_gt[img], s);
+}
+
+__global__ void __launch_bounds__(256)
+loss_grad_kernel(const float *__restrict__ p, const float *__restrict__ y, size_t n, float ys_a, float ys_b, float inv_n,
+                 float inter2p1, float denom, const uint32_t *__restrict__ tau_bits /* or null */,
+                 const float *__restrict__ tie_w, size_t npi, float *__restrict__ dldp) {
   const float eps = 1e-7f;
   const float inv_d2 = 1.0f / (denom * denom);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    float pv = p[i], yv = y[i];
+    const float pv = p[i];
+    const float yv = y[i] * ys_a + ys_b;
     float g = 0.f;
     if (pv >= eps && pv <= 1.0f - eps) {
-      float dbce = -(yv / (pv + eps) - (1.0f - yv) / (1.0f - pv + eps));
-      float ddice = -(2.0f * yv * denom - inter2p1) * inv_d2;
-      g = dbce * inv_n + ddice;
+      float w = 1.f;
+      if (tau_bits) {
+        const size_t img = i / npi;
+        const uint32_t u = __float_as_uint(fmaxf(bce_term(pv, yv), 0.f)), t = tau_bits[img];
+        w = u > t ? 1.f : (u == t ? tie_w[img] : 0.f);
+      }
+      const float dbce = -(yv / (pv + eps) - (1.0f - yv) / (1.0f - pv + eps));
+      const float ddice = -(2.0f * yv * denom - inter2p1) * inv_d2;
+      g = w * dbce * inv_n + ddice;
     }
     dldp[i] = g;
   }

@@ -50,7 +50,8 @@ struct TrainState {
   size_t koff_first = 0, boff_first = 0, koff_head = 0, boff_head = 0;
   std::vector<TrainLayer> tl;
   DevBuf gw_first, gb_first, g_head;     // [9][cp0], [cp0], double [cp0 + 1]
-  DevBuf zeros, sums;
+  DevBuf zeros;
+  LossState ls;
   DevBuf x, y, dldp;
   // activations
   DevBuf d1a, cat1, u1b, u1c, pl1, d2a, cat2, u2b, u2c, pl2, d3a, cat3, u3b, u3c, pl3, t[6], ts, prob;
@@ -156,7 +157,6 @@ void train_alloc(adp_engine *e, int nb, int S, float dropout_rate, uint64_t seed
   tr->g_hi.ensure(n * std::max({s1 * cp[1], s2 * cp[2], s3 * cp[3]}) * es);
   tr->prob.ensure(n * s1 * 4); tr->x.ensure(n * s1 * 4); tr->y.ensure(n * s1 * 4); tr->dldp.ensure(n * s1 * 4);
   tr->zeros.ensure(4096); ADP_CUDA(cudaMemset(tr->zeros.p, 0, 4096));
-  tr->sums.ensure(64);
   e->fwt_tile.ensure(64 * 4); e->fwt_op.ensure(64 * 4); e->fwt_origin.ensure(64 * 8);
   Acts &a = tr->acts;
   a.d1a = &tr->d1a; a.cat1 = &tr->cat1; a.u1b = &tr->u1b; a.u1c = &tr->u1c; a.pl1 = &tr->pl1;
@@ -212,7 +212,7 @@ void train_alloc(adp_engine *e, int nb, int S, float dropout_rate, uint64_t seed
 }
 
 // ---- forward -----------------------------------------------------------------------------------
-void train_forward(adp_engine *e, const float *x, const float *y, int n, const uint8_t *const *masks, double sums[6]) {
+void train_forward(adp_engine *e, const float *x, const float *y, int n, const uint8_t *const *masks, double sums[8]) {
   TrainState *tr = e->tr;
   if (!tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
   ADP_REQUIRE(n == tr->nb, "batch size differs from adp_train_begin");
@@ -243,22 +243,8 @@ void train_forward(adp_engine *e, const float *x, const float *y, int n, const u
   DropSpec none;   // keep == 1, no masks: the dropout kernels are skipped but the fused head is still off
   if (e->prec == ADP_PREC_FP32) forward_t<float>(e, tr->acts, S, src, fw, n, 0.f, 1.f, nullptr, dropping ? &d : &none);
   else forward_t<__nv_bfloat16>(e, tr->acts, S, src, fw, n, 0.f, 1.f, nullptr, dropping ? &d : &none);
-  ADP_CUDA(cudaMemsetAsync(tr->sums.p, 0, 64, e->stream));
-  const int grid = (int)std::max<size_t>(1, std::min<size_t>(cdiv64(npx, 256 * 4), (size_t)e->num_sms * 8));
-  e->launch("loss_reduce", 0, (double)npx * 8, [&] {
-    loss_reduce_kernel<<<grid, 256, 0, e->stream>>>(tr->prob.as<float>(), tr->y.as<float>(), npx, tr->sums.as<double>());
-  });
-  ADP_CUDA(cudaMemcpyAsync(sums, tr->sums.p, 48, cudaMemcpyDeviceToHost, e->stream));
-  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  loss_forward(e, tr->ls, e->loss, tr->prob.as<float>(), tr->y.as<float>(), n, (size_t)S * S, sums);
   tr->have_forward = true; tr->have_grads = false;
-}
-
-void loss_from_sums(const double s[6], double n_px, double out[4]) {
-  const double bce = s[0] / n_px;
-  const double denom = s[2] + s[3] + 1.0;
-  const double dice_loss = 1.0 - (2.0 * s[1] + 1.0) / denom;
-  out[0] = bce + dice_loss; out[1] = bce; out[2] = dice_loss;
-  out[3] = (2.0 * s[4] + 1.0) / (s[2] + s[5] + 1.0);
 }
 
 // ---- backward ----------------------------------------------------------------------------------
@@ -491,17 +477,10 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
   }
 }
 
-void train_backward(adp_engine *e, const double sums[6], int64_t n_px_global, bool freeze_encoder) {
+void train_backward(adp_engine *e, const double sums[8], bool freeze_encoder) {
   TrainState *tr = e->tr;
   if (!tr || !tr->have_forward) throw Error(ADP_ESTATE, "adp_train_forward must run first");
-  const size_t npx = (size_t)tr->nb * tr->S * tr->S;
-  const double N = n_px_global > 0 ? (double)n_px_global : (double)npx;
-  const double denom = sums[2] + sums[3] + 1.0;
-  const int grid = (int)std::max<size_t>(1, std::min<size_t>(cdiv64(npx, 256 * 4), (size_t)e->num_sms * 8));
-  e->launch("loss_grad", 0, (double)npx * 12, [&] {
-    loss_grad_kernel<<<grid, 256, 0, e->stream>>>(tr->prob.as<float>(), tr->y.as<float>(), npx, (float)(1.0 / N), (float)(2.0 * sums[1] + 1.0),
-                                                  (float)denom, tr->dldp.as<float>());
-  });
+  loss_backward(e, tr->ls, e->loss, tr->prob.as<float>(), tr->y.as<float>(), tr->nb, (size_t)tr->S * tr->S, sums, tr->dldp.as<float>());
   if (freeze_encoder) {   // frozen tensors report zero gradient
     const size_t first_trainable = tr->tl[layer_index(e, "dilate1")].koff;
     ADP_CUDA(cudaMemsetAsync(tr->grad.p, 0, first_trainable * 4, e->stream));

@@ -3,7 +3,7 @@
 One process per GPU.  A step is the engine's forward -> backward -> apply (include/adipose_b200.h, adp_train_*)
 with two exchanges between ranks:
 
-* six float64 loss sums before backward (``dice_mode="global"``): the reference's Dice term is defined over the
+* eight float64 loss sums before backward (``dice_mode="global"``): the reference's Dice term is defined over the
   WHOLE batch (train_adipose_unet_v3.py:217-225), so the exact data-parallel equivalent of a single-GPU step on the
   concatenated batch needs sum(y*p), sum(y), sum(p) over all ranks before dL/dp is formed.  ``dice_mode="replica"``
   skips this exchange and averages per-replica gradients instead (what wrapping the reference in a DP strategy does);
@@ -102,14 +102,11 @@ class DataParallelTrainer:
         return self.engine.train_forward(x, y, dropout_masks)
 
     def backward(self, sums: np.ndarray, global_sums: Optional[np.ndarray] = None) -> Dict[str, float]:
-        """Backward for the loss the mode defines; returns that loss."""
-        if self.dice_mode == "global":
-            gs = sums if global_sums is None else global_sums
-            n = self.n_local * self.world
-        else:
-            gs, n = sums, self.n_local
-        self.engine.train_backward(gs, n, self.freeze_encoder)
-        return self.engine.train_loss(gs, n)
+        """Backward for the loss the mode defines; returns that loss.  The sums carry their own term count
+        (sums[7]), so hard-example mining and label smoothing need no special casing here."""
+        gs = sums if (self.dice_mode != "global" or global_sums is None) else global_sums
+        self.engine.train_backward(gs, self.freeze_encoder)
+        return self.engine.train_loss(gs)
 
     def apply(self, lr: float):
         # global: d(global loss)/d(theta) is the SUM of the ranks' contributions; replica: mean of replica gradients

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ADP_ABI_VERSION 1
+#define ADP_ABI_VERSION 2
 
 /* error codes */
 #define ADP_OK 0
@@ -162,12 +162,18 @@ int adp_wsi_finalize(adp_engine *e, int y, int rows, float thr, float *prob, uin
                      const uint8_t *gt, int64_t counts[4]);
 int adp_wsi_end(adp_engine *e);
 
-/* ---- loss / training step ----------------------------------------------------------------------
+/* ---- loss ---------------------------------------------------------------------------------------
  * adp_loss_metrics: combined_loss_standard = mean BCE + (1 - global Dice) and dice_coef
  * (train_adipose_unet_v3.py:217-241, src/utils/model.py:93-98) of probabilities p against y,
  * n_px pixels over the whole batch; dldp (may be NULL) receives dL/dp.
- * out = {loss, bce_mean, dice_loss, dice_coef}. */
+ * out = {loss, bce_mean, dice_loss, dice_coef}.
+ * adp_loss_metrics_ex: the reference's other compile_model choices (train_adipose_unet_v3.py:808-855) on `batch`
+ * images of px_per_image pixels: ohem_keep_ratio < 1 = online_hard_example_mining_loss (:282-323, mean of the top
+ * int(px*ratio) per-image BCE values + Dice over all pixels); eps_pos/eps_neg > 0 = asymmetric label smoothing
+ * (:244-279, 326-363: ys = y*(1-eps_pos-eps_neg)+eps_neg in both terms; dice_coef keeps the raw y). */
 int adp_loss_metrics(adp_engine *e, const float *p, const float *y, int64_t n_px, float *dldp, double out[4]);
+int adp_loss_metrics_ex(adp_engine *e, const float *p, const float *y, int batch, int64_t px_per_image, float ohem_keep_ratio,
+                        float eps_pos, float eps_neg, float *dldp, double out[4]);
 
 /* ---- training step -----------------------------------------------------------------------------
  * Replaces Keras train_step as driven by net.fit (train_adipose_unet_v3.py:1316-1324, 1413-1421):
@@ -184,17 +190,20 @@ int adp_loss_metrics(adp_engine *e, const float *p, const float *y, int64_t n_px
 #define ADP_OPT_ADAM 0
 #define ADP_OPT_ADAMW 1
 int adp_train_begin(adp_engine *e, int batch, int size, float dropout_rate, uint64_t seed);
+/* loss recipe of the following steps (default: standard loss = 1, 0, 0); see adp_loss_metrics_ex */
+int adp_train_set_loss(adp_engine *e, float ohem_keep_ratio, float eps_pos, float eps_neg);
 /* dropout_masks: NULL (masks drawn from the engine's counter-based generator when dropout_rate > 0) or four
  * uint8 0/1 arrays in NHWC with the real channel counts, sites in graph order
  * {dilate1 (size/8, 8*init_nb), up3 (size/4, 4*init_nb), up2 (size/2, 2*init_nb), up1 (size, init_nb)}.
- * sums = {sum bce, sum y*pc, sum y, sum pc, sum y*p, sum p} over this batch (pc = clip(p,1e-7,1-1e-7)). */
+ * sums = {sum of the BCE terms in the mean, sum ys*pc, sum ys, sum pc, sum y*p, sum p, sum y, number of BCE terms} over this
+ * batch (pc = clip(p,1e-7,1-1e-7), ys = smoothed target); every entry is additive over data-parallel ranks. */
 int adp_train_forward(adp_engine *e, const float *x, const float *y, int batch, const uint8_t *const *dropout_masks,
-                      double sums[6]);
-/* loss = {loss, bce_mean, dice_loss, dice_coef} from (possibly rank-summed) sums over n_px pixels */
-int adp_train_loss(const double sums[6], int64_t n_px, double out[4]);
-/* sums / n_px_global: the values the loss is defined over (own batch, or summed over data-parallel ranks);
+                      double sums[8]);
+/* loss = {loss, bce_mean, dice_loss, dice_coef} from (possibly rank-summed) sums */
+int adp_train_loss(const double sums[8], double out[4]);
+/* sums: the values the loss is defined over (own batch, or summed over data-parallel ranks);
  * freeze_encoder != 0 = phase 1 of the reference (down*_conv* frozen, :760-769): their gradients are zero */
-int adp_train_backward(adp_engine *e, const double sums[6], int64_t n_px_global, int freeze_encoder);
+int adp_train_backward(adp_engine *e, const double sums[8], int freeze_encoder);
 /* device pointer + element count of the flat fp32 gradient (Keras order: per layer kernel HWIO, bias) */
 int adp_train_grad_buffer(adp_engine *e, float **dev_ptr, int64_t *count);
 /* whole flat gradient to / from host memory (count must equal the parameter count): the staging path of a

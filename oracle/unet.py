@@ -166,6 +166,30 @@ def combined_loss_standard(y, p):
     return bce_mean(y, p) + dice_loss(y, p)
 
 
+def smooth_labels(y, epsilon_pos=0.03, epsilon_neg=0.07):
+    """Asymmetric label smoothing, train_adipose_unet_v3.py:271-274: 1 -> 1-eps_pos-eps_neg, 0 -> eps_neg."""
+    return y * (1.0 - epsilon_pos - epsilon_neg) + epsilon_neg
+
+
+def combined_loss_with_label_smoothing(y, p, epsilon_pos=0.03, epsilon_neg=0.07):
+    """train_adipose_unet_v3.py:244-279."""
+    ys = smooth_labels(y, epsilon_pos, epsilon_neg)
+    return bce_mean(ys, p) + dice_loss(ys, p)
+
+
+def online_hard_example_mining_loss(y, p, keep_ratio=0.7, epsilon_pos=0.0, epsilon_neg=0.0):
+    """train_adipose_unet_v3.py:282-323 (and :326-363 with smoothing): per-pixel BCE (Keras' binary_crossentropy over a
+    trailing axis of length 1 is the per-pixel value), flattened per image, top int(npix*ratio) values per image,
+    mean over all kept values, plus dice_loss over ALL pixels.  y, p: (B, H, W)."""
+    ys = smooth_labels(y, epsilon_pos, epsilon_neg) if (epsilon_pos or epsilon_neg) else y
+    pc = torch.clamp(p, EPS, 1.0 - EPS)
+    bce = -(ys * torch.log(pc + EPS) + (1.0 - ys) * torch.log(1.0 - pc + EPS))
+    flat = bce.reshape(bce.shape[0], -1)
+    k = int(np.float32(flat.shape[1]) * np.float32(keep_ratio))
+    top, _ = torch.topk(flat, k, dim=1, sorted=False)
+    return top.mean() + dice_loss(ys, p)
+
+
 def dice_coef(y, p):
     """src/utils/model.py:93-98 (no clip, smooth=1)."""
     return (2.0 * torch.sum(y * p) + 1.0) / (torch.sum(y) + torch.sum(p) + 1.0)
@@ -173,7 +197,7 @@ def dice_coef(y, p):
 
 # ------------------------------------------------------------------ T2
 def loss_and_grads(x: np.ndarray, y: np.ndarray, weights, dtype=torch.float32,
-                   dropout_masks=None):
+                   dropout_masks=None, loss_fn=None):
     """One forward+backward of combined_loss_standard through the graph.
     x: (B,H,W) normalised float32, y: (B,H,W) {0,1}.  Returns loss, dice_coef,
     prob, dL/dprob and name -> (dW HWIO, db)."""
@@ -185,7 +209,7 @@ def loss_and_grads(x: np.ndarray, y: np.ndarray, weights, dtype=torch.float32,
         dm = {k: torch.from_numpy(v).to(dtype) for k, v in dropout_masks.items()}
     prob = forward(xt, p, dropout_masks=dm)
     prob.retain_grad()
-    loss = combined_loss_standard(yt, prob)
+    loss = (loss_fn or combined_loss_standard)(yt, prob)
     loss.backward()
     grads = {}
     for name, (w, b) in p.items():

@@ -105,3 +105,36 @@ def test_loss_and_grad_vs_oracle(eng):
     res2 = eng.loss_metrics(p2, y)
     l64 = float(U.combined_loss_standard(yt.double(), torch.from_numpy(p2).double()))
     assert abs(res2["loss"] - l64) <= 1e-6 * max(1.0, abs(l64))
+
+
+# ---- loss recipes of compile_model (train_adipose_unet_v3.py:808-855): hard-example mining and label smoothing
+@pytest.mark.parametrize("keep,eps", [(1.0, (0.03, 0.07)), (0.7, (0.0, 0.0)), (0.7, (0.03, 0.07)), (0.5, (0.0, 0.0))])
+def test_loss_recipes_vs_oracle(keep, eps):
+    import torch
+    from oracle import unet as U
+    rng = np.random.default_rng(7)
+    B, S = 3, 96
+    y = (rng.random((B, S, S)) < 0.3).astype(np.float32)
+    # probabilities spanning saturated (clipped), confident and uncertain pixels
+    z = rng.standard_normal((B, S, S)).astype(np.float32) * 4.0
+    p = (1.0 / (1.0 + np.exp(-z))).astype(np.float32)
+    p[0, :4] = 0.0; p[1, :4] = 1.0                                   # exercise the clip and tie handling
+    # float32 like TensorFlow: for saturated pixels clip(p) + 1e-7 and 1 - clip(p) + 1e-7 are float32 roundings
+    # (1 - 1e-7 -> 0.99999988), which a float64 evaluation would not reproduce
+    pt = torch.tensor(p, dtype=torch.float32, requires_grad=True)
+    yt = torch.tensor(y, dtype=torch.float32)
+    if keep < 1.0:
+        loss = U.online_hard_example_mining_loss(yt, pt, keep, eps[0], eps[1])
+    else:
+        loss = U.combined_loss_with_label_smoothing(yt, pt, eps[0], eps[1])
+    loss.backward()
+    eng = api.default_engine()
+    res, g = eng.loss_metrics(p, y, want_grad=True, ohem_keep_ratio=keep, eps_pos=eps[0], eps_neg=eps[1])
+    assert abs(res["loss"] - float(loss)) <= 2e-5 * max(1.0, abs(float(loss)))          # float32 oracle sums vs float64 device sums
+    assert abs(res["dice_coef"] - float(U.dice_coef(yt, pt.detach()))) <= 1e-5            # metric keeps the raw target
+    gref = pt.grad.numpy()
+    # the fp32 kernel and the float64 oracle may rank a handful of near-equal BCE values differently around tau: compare in
+    # the L2 norm and bound the number of pixels whose selection differs
+    l2 = np.linalg.norm((g - gref).ravel()) / np.linalg.norm(gref.ravel())
+    differ = (np.abs(g - gref) > 1e-6 * np.abs(gref).max() + 1e-9).mean()
+    assert l2 <= 2e-3 and differ <= 1e-3, (l2, differ)

@@ -52,8 +52,8 @@ def run_engine(prec, weights, x, y, masks=None, freeze=False):
     eng.set_weights(weights)
     eng.train_begin(x.shape[0], x.shape[1], dropout_rate=0.0)
     sums = eng.train_forward(x, y, masks)
-    loss = eng.train_loss(sums, x.size)
-    eng.train_backward(sums, 0, freeze)
+    loss = eng.train_loss(sums)
+    eng.train_backward(sums, freeze)
     return eng, loss, eng.train_probs(), eng.train_grads()
 
 
@@ -99,6 +99,30 @@ def test_gradients_vs_oracle(prec, with_dropout, weights):
     assert not bad, bad
     eng.train_end()
     eng.close()
+
+
+def test_hard_mining_and_label_smoothing_step_fp32(weights):
+    """The default loss of the reference's training CLI (OHEM keep 0.7) and its label-smoothing variant through the whole
+    step: loss and every gradient against the oracle's autograd of train_adipose_unet_v3.py:282-363."""
+    n, S = 2, 128
+    x, y = batch(n, S, seed=23)
+    for keep, ep, en in ((0.7, 0.0, 0.0), (0.7, 0.03, 0.07)):
+        fn = lambda yt, p: U.online_hard_example_mining_loss(yt, p, keep, ep, en)
+        loss_ref, _, _, _, g_ref = U.loss_and_grads(x, y, weights, loss_fn=fn)
+        eng = api.Engine(precision="fp32", max_forwards=8)
+        eng.set_weights(weights)
+        eng.train_set_loss(keep, ep, en)
+        eng.train_begin(n, S, dropout_rate=0.0)
+        sums = eng.train_forward(x, y)
+        assert sums[7] == n * int(np.float32(S * S) * np.float32(keep))
+        loss = eng.train_loss(sums)
+        eng.train_backward(sums)
+        g = eng.train_grads()
+        assert abs(loss["loss"] - loss_ref) <= 1e-5 * max(1.0, abs(loss_ref))
+        worst = max(l2_err(g[k], g_ref[k]) for k in g)
+        print("ohem", keep, ep, en, "loss", loss["loss"], loss_ref, "worst grad L2", worst)
+        assert worst <= 2e-3
+        eng.train_end(); eng.close()
 
 
 def test_freeze_encoder_fp32(weights):

@@ -43,14 +43,17 @@ class FakeTrainEngine:
         p = torch.sigmoid(float(self.theta[0]) * self.x + float(self.theta[1]))
         pc = torch.clamp(p, U.EPS, 1 - U.EPS)
         bce = -(self.y * torch.log(pc + U.EPS) + (1 - self.y) * torch.log(1 - pc + U.EPS))
-        return np.array([bce.sum(), (self.y * pc).sum(), self.y.sum(), pc.sum(), (self.y * p).sum(), p.sum()], np.float64)
+        return np.array([bce.sum(), (self.y * pc).sum(), self.y.sum(), pc.sum(), (self.y * p).sum(), p.sum(), self.y.sum(),
+                         float(self.y.numel())], np.float64)
 
     @staticmethod
-    def train_loss(s, n):
+    def train_loss(s):
+        n = s[7]
         dl = 1.0 - (2 * s[1] + 1) / (s[2] + s[3] + 1)
-        return dict(loss=s[0] / n + dl, bce=s[0] / n, dice_loss=dl, dice_coef=(2 * s[4] + 1) / (s[2] + s[5] + 1))
+        return dict(loss=s[0] / n + dl, bce=s[0] / n, dice_loss=dl, dice_coef=(2 * s[4] + 1) / (s[6] + s[5] + 1))
 
-    def train_backward(self, gs, n_global, freeze):
+    def train_backward(self, gs, freeze):
+        n_global = gs[7]
         # dL/dp for LOCAL pixels of the loss defined by the (global) sums: bce/n + 1 - (2I+1)/(Y+P+1)
         th = torch.tensor(self.theta.astype(np.float64), requires_grad=True)
         p = torch.sigmoid(th[0] * self.x + th[1])
