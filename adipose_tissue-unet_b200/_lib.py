@@ -64,6 +64,8 @@ SIGNATURES = {
     "adp_loss_metrics": (_I, [_P, _P, _P, _I64, _P, C.POINTER(C.c_double)]),
     "adp_loss_metrics_ex": (_I, [_P, _P, _P, _I, _I64, _F, _F, _F, _P, C.POINTER(C.c_double)]),
     "adp_train_set_loss": (_I, [_P, _F, _F, _F]),
+    "adp_train_set_deep_supervision": (_I, [_P, _I, _F, _F, _F]),
+    "adp_train_outputs": (_I, [_P]),
     "adp_train_begin": (_I, [_P, _I, _I, _F, C.c_uint64]),
     "adp_train_forward": (_I, [_P, _P, _P, _I, C.POINTER(_P), C.POINTER(C.c_double)]),
     "adp_train_loss": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),

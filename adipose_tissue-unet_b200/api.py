@@ -19,7 +19,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from .layers import LAYER_NAMES, weight_shapes
+from .layers import LAYER_NAMES, weight_shapes, AUX_NAMES, aux_weight_shapes
 
 TTA_OPCODES = {"minimal": [0, 4], "basic": [0, 4, 5, 1], "full": [0, 1, 2, 3, 4, 5, 6, 7]}
 
@@ -54,15 +54,21 @@ class Engine:
     # ---- weights
     def set_weights(self, weights: Dict[str, np.ndarray]):
         """weights: '<layer>/kernel' (HWIO float32) and '<layer>/bias' per Keras layer name."""
-        for name in LAYER_NAMES:
+        names = list(LAYER_NAMES) + [n for n in AUX_NAMES if n + "/kernel" in weights]     # aux heads: deep-supervision training only
+        for name in names:
             k = _f32c(weights[name + "/kernel"])
             b = _f32c(weights[name + "/bias"])
             shp = (C.c_int64 * 4)(*k.shape)
             _lib.check(self.lib.adp_set_weight(self.h, name.encode(), _lib.ptr(k), shp, _lib.ptr(b), b.size))
+            if name in AUX_NAMES:
+                self._has_aux = True
 
     def get_weights(self) -> Dict[str, np.ndarray]:
         out = {}
-        for name, (ks, bs) in weight_shapes(self.init_nb).items():
+        shapes = dict(weight_shapes(self.init_nb))
+        if getattr(self, "_has_aux", False):
+            shapes.update(aux_weight_shapes(self.init_nb))
+        for name, (ks, bs) in shapes.items():
             k = np.empty(ks, np.float32)
             b = np.empty(bs, np.float32)
             _lib.check(self.lib.adp_get_weight(self.h, name.encode(), _lib.ptr(k), k.size, _lib.ptr(b), b.size))
@@ -167,7 +173,8 @@ class Engine:
             x = _f32c(x)
         if isinstance(y, np.ndarray):
             y = _f32c(y)
-        sums = (C.c_double * 8)()
+        nout = int(self.lib.adp_train_outputs(self.h))
+        sums = (C.c_double * (8 * nout))()
         mptr = None
         keep = []
         if dropout_masks is not None:
@@ -184,14 +191,30 @@ class Engine:
         """Loss recipe of the following steps (train_adipose_unet_v3.py:808-855)."""
         _lib.check(self.lib.adp_train_set_loss(self.h, ohem_keep_ratio, eps_pos, eps_neg))
 
+    def train_set_deep_supervision(self, on: bool = True, w_main: float = 1.0, w_aux1: float = 0.4, w_aux2: float = 0.3):
+        """aux_out1 / aux_out2 heads with loss weights (train_adipose_unet_v3.py:712-745, 858-872); needs their weights set."""
+        _lib.check(self.lib.adp_train_set_deep_supervision(self.h, 1 if on else 0, w_main, w_aux1, w_aux2))
+        self._ds_weights = (w_main, w_aux1, w_aux2) if on else None
+
     def train_loss(self, sums) -> Dict[str, float]:
-        s = (C.c_double * 8)(*[float(v) for v in sums])
-        out = (C.c_double * 4)()
-        _lib.check(self.lib.adp_train_loss(s, out))
-        return dict(loss=out[0], bce=out[1], dice_loss=out[2], dice_coef=out[3])
+        """{loss, bce, dice_loss, dice_coef}: with deep supervision `loss` is the weighted total of the three outputs and
+        bce / dice_loss / dice_coef are those of main_out (what Keras logs as main_out_*)."""
+        sums = np.asarray(sums, dtype=np.float64)
+        outs = []
+        for o in range(len(sums) // 8):
+            s = (C.c_double * 8)(*[float(v) for v in sums[8 * o:8 * o + 8]])
+            out = (C.c_double * 4)()
+            _lib.check(self.lib.adp_train_loss(s, out))
+            outs.append(dict(loss=out[0], bce=out[1], dice_loss=out[2], dice_coef=out[3]))
+        res = dict(outs[0])
+        dsw = getattr(self, "_ds_weights", None)
+        if len(outs) == 3 and dsw is not None:
+            res["loss"] = dsw[0] * outs[0]["loss"] + dsw[1] * outs[1]["loss"] + dsw[2] * outs[2]["loss"]
+            res["main_out_loss"], res["aux_out1_loss"], res["aux_out2_loss"] = outs[0]["loss"], outs[1]["loss"], outs[2]["loss"]
+        return res
 
     def train_backward(self, sums, freeze_encoder: bool = False):
-        s = (C.c_double * 8)(*[float(v) for v in sums])
+        s = (C.c_double * len(sums))(*[float(v) for v in sums])
         _lib.check(self.lib.adp_train_backward(self.h, s, 1 if freeze_encoder else 0))
 
     def train_grad_buffer(self) -> Tuple[int, int]:
@@ -212,7 +235,10 @@ class Engine:
 
     def train_grads(self) -> Dict[str, np.ndarray]:
         out = {}
-        for name, (ks, bs) in weight_shapes(self.init_nb).items():
+        shapes = dict(weight_shapes(self.init_nb))
+        if int(self.lib.adp_train_outputs(self.h)) == 3:
+            shapes.update(aux_weight_shapes(self.init_nb))
+        for name, (ks, bs) in shapes.items():
             k = np.empty(ks, np.float32); b = np.empty(bs, np.float32)
             _lib.check(self.lib.adp_train_get_grad(self.h, name.encode(), _lib.ptr(k), k.size, _lib.ptr(b), b.size))
             out[name + "/kernel"] = k; out[name + "/bias"] = b

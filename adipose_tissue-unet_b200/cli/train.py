@@ -6,11 +6,11 @@ backward, Keras Adam/AdamW; include/adipose_b200.h adp_train_*), optionally data
 What stays on the host, as in the reference: tile files, shuffling, augmentation, the epoch loop, the cosine/warm-up
 schedule (:393-404), best-checkpoint bookkeeping, EMA of the weights (:407-505) and the log files.
 
-Recipe coverage: hard-example mining (--use-hard-mining, --hard-example-ratio) and
-asymmetric label smoothing (--use-label-smoothing, --label-smooth-epsilon-*) run on the device (adp_train_set_loss);
-the deep-supervision heads of the reference's DEFAULT recipe are not in this engine yet: with --use-deep-supervision
-left on, the run says so and trains the single-output model; training_settings.log records
-`use_deep_supervision: False` so the evaluation scripts build the matching graph."""
+Recipe coverage: deep supervision (--use-deep-supervision, --ds-weight-*: aux_out1 / aux_out2
+heads, adp_train_set_deep_supervision), hard-example mining (--use-hard-mining, --hard-example-ratio) and asymmetric
+label smoothing (--use-label-smoothing, --label-smooth-epsilon-*; adp_train_set_loss) all run on the device, i.e. the
+reference's default recipe.  Still host-side / not reproduced: the intensity and elastic parts of the augmentation
+levels (geometric D4 part only) and ReduceLROnPlateau of --no-cosine-schedule (constant rate instead)."""
 from __future__ import annotations
 
 import argparse
@@ -155,8 +155,8 @@ def main(argv=None) -> int:
         dist = dist_
     log = print if rank == 0 else (lambda *a, **k: None)
     log("=" * 80 + "\nTRAIN ADIPOSE U-NET VERSION 3.1 (B200 engine)\n" + "=" * 80)
-    if args.use_deep_supervision:
-        log("⚠️  deep supervision: auxiliary heads are not implemented in this engine yet - training the single-output model")
+    log("✓ Deep supervision: ", f"ENABLED (weights main={args.ds_weight_main}, aux1={args.ds_weight_aux1}, aux2={args.ds_weight_aux2})"
+        if args.use_deep_supervision else "DISABLED")
     log("✓ Hard example mining:", f"ENABLED (keep {args.hard_example_ratio})" if args.use_hard_mining else "DISABLED")
     log("✓ Label smoothing:", f"ENABLED (eps_pos={args.label_smooth_epsilon_pos}, eps_neg={args.label_smooth_epsilon_neg})"
         if args.use_label_smoothing else "DISABLED")
@@ -185,17 +185,29 @@ def main(argv=None) -> int:
         with open(ckpt / "training_settings.log", "w") as f:                         # :984-1053 (sniffed at eval:513-516)
             f.write("=" * 80 + "\nTRAINING SETTINGS LOG - VERSION 3\n" + "=" * 80 + f"\n\nGenerated: {stamp}\n")
             f.write("Script: adipose_unet_b200.cli.train\n" + f"Checkpoint Directory: {ckpt}\n\n" + "-" * 60 + "\nCOMMAND LINE ARGUMENTS\n" + "-" * 60 + "\n")
-            settings = dict(vars(args)); settings["use_deep_supervision"] = False
+            settings = dict(vars(args))
             for k, v in settings.items():
                 f.write(f"  {k}: {v}\n")
             f.write("\n" + "-" * 60 + "\nMACHINE READABLE FORMAT (JSON)\n" + "-" * 60 + "\n" + json.dumps(settings, indent=2, default=str) + "\n")
     engine = api.Engine(precision=args.precision, device=local, max_forwards=max(8, args.batch_size))
     if args.pretrained_weights and Path(args.pretrained_weights).exists():
-        engine.set_weights(load_weights_file(args.pretrained_weights))
+        w0 = load_weights_file(args.pretrained_weights, keep_aux=True)
         log(f"✓ Loaded pretrained weights from {args.pretrained_weights}")
     else:
         log("WARNING: No pretrained weights found, training from scratch")
-        engine.set_weights(synth.init_weights(seed=args.seed))
+        w0 = synth.init_weights(seed=args.seed)
+    if args.use_deep_supervision and "aux_out1/kernel" not in w0:
+        # fresh heads as Keras creates them: glorot_uniform kernel, zero bias (Conv2D defaults, :715, 722)
+        r0 = np.random.RandomState(args.seed)
+        for nm, cin in (("aux_out1", 176), ("aux_out2", 88)):
+            lim = np.sqrt(6.0 / (cin + 1))
+            w0[nm + "/kernel"] = r0.uniform(-lim, lim, size=(1, 1, cin, 1)).astype(np.float32)
+            w0[nm + "/bias"] = np.zeros(1, np.float32)
+    if not args.use_deep_supervision:
+        w0 = {k: v for k, v in w0.items() if not k.startswith("aux_out")}
+    engine.set_weights(w0)
+    if args.use_deep_supervision:
+        engine.train_set_deep_supervision(True, args.ds_weight_main, args.ds_weight_aux1, args.ds_weight_aux2)
     engine.train_set_loss(args.hard_example_ratio if args.use_hard_mining else 1.0,
                           args.label_smooth_epsilon_pos if args.use_label_smoothing else 0.0,
                           args.label_smooth_epsilon_neg if args.use_label_smoothing else 0.0)
@@ -209,7 +221,7 @@ def main(argv=None) -> int:
             continue
         log(f"\n{'=' * 60}\nPHASE {phase}: {'frozen encoder' if freeze else 'fine-tuning all layers'} ({epochs} epochs)\n{'=' * 60}")
         if phase == 2 and (ckpt / "phase1_best.weights.h5").exists():
-            engine.set_weights(load_weights_file(str(ckpt / "phase1_best.weights.h5")))       # :1336-1339
+            engine.set_weights(load_weights_file(str(ckpt / "phase1_best.weights.h5"), keep_aux=True))       # :1336-1339
         trainer = T.DataParallelTrainer(engine, args.batch_size, TILE, dist=dist, rank=rank, world=world, dropout_rate=0.3,
                                         seed=args.seed + 1000 * phase, optimizer=args.optimizer, freeze_encoder=freeze)
         best_phase, since_best = -1.0, 0

@@ -233,6 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
     // > 85 % busy on the 1024^2 layers - ~50 cycles of descriptor arithmetic per MMA - while no pipe was saturated.)
     if (ptx::elect_one()) {
       const int issuer = (warp == 10) ? 1 : 0;
+      const bool single_issuer = (p.dbg & 32) != 0;       // experiment switch: issuer B only observes
       int st = 0; uint32_t ph = 0;
       // The other issuer's stages are still OBSERVED: an mbarrier parity wait is only meaningful for a waiter that sees
       // every phase of the barrier in order, so the skipping thread waits for each stage's 'full' phase and then arrives on
@@ -269,7 +270,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
         const uint32_t id1 = p.idesc_stack[0], id2 = p.idesc_stack[1], id3 = p.idesc_stack[2];
         int it = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-          if ((it & 1) != issuer) { skip_item(); continue; }
+          if (single_issuer ? issuer != 0 : (it & 1) != issuer) { skip_item(); continue; }
           const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
           { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3); if (p.dbg & 16) t_m0 += clock64() - tw; }
           ptx::tc_fence_after();
@@ -325,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
       const uint32_t idesc = p.idesc;
       int it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-        if ((it & 1) != issuer) { skip_item(); continue; }
+        if (single_issuer ? issuer != 0 : (it & 1) != issuer) { skip_item(); continue; }
         const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
         { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3); if (p.dbg & 16) t_m0 += clock64() - tw; }
         ptx::tc_fence_after();

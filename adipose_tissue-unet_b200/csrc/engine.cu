@@ -150,6 +150,8 @@ struct adp_engine {
   bool fuse_head = true, fuse_pool = true;   // tcgen05 path only
   bool kys = true;                           // ky-stacked MMA issue for the N <= 128 layers
   LossRecipe loss;                           // adp_train_set_loss: hard-example mining / label smoothing of the training loss
+  bool deep_sup = false;                     // adp_train_set_deep_supervision: aux_out1 / aux_out2 heads while training
+  float ds_w[3] = {1.0f, 0.4f, 0.3f};        // loss weights main / aux1 / aux2 (train_adipose_unet_v3.py:858-872)
   bool wgrad_simt = false, dgrad_simt = false;   // bf16 training: CUDA-core cross-check of the tcgen05 backward kernels
 
   template <typename F> void launch(const char *kind, double flops, double bytes, F &&f) {
@@ -209,6 +211,7 @@ ConvLayer &layer(adp_engine *e, const std::string &n) {
   throw Error(ADP_EINVAL, "unknown layer " + n);
 }
 
+const char *const kAuxNames[2] = {"aux_out1", "aux_out2"};   // deep-supervision heads: 1x1 convs on up3 / up2 (:712-725)
 const char *const kAllNames[22] = {"down1_conv1", "down1_conv2", "down2_conv1", "down2_conv2", "down3_conv1",
                                    "down3_conv2", "dilate1", "dilate2", "dilate3", "dilate4", "dilate5", "dilate6",
                                    "up3_conv1", "up3_conv2", "up3_conv3", "up2_conv1", "up2_conv2", "up2_conv3",
@@ -863,14 +866,14 @@ void loss_forward(adp_engine *e, LossState &ls, const LossRecipe &r, const float
 
 // backward part: dL/dp for the loss defined by the (possibly rank-summed) sums
 void loss_backward(adp_engine *e, LossState &ls, const LossRecipe &r, const float *p, const float *y, int batch, size_t npi,
-                   const double s[8], float *dldp) {
+                   const double s[8], float *dldp, float gain = 1.f) {
   const size_t n = (size_t)batch * npi;
   const int grid = (int)std::max<size_t>(1, std::min<size_t>(cdiv64(n, 256 * 4), (size_t)e->num_sms * 8));
   const double denom = s[2] + s[3] + 1.0;
   e->launch("loss_grad", 0, (double)n * 12, [&] {
     loss_grad_kernel<<<grid, 256, 0, e->stream>>>(p, y, n, r.ys_scale(), r.eps_neg, (float)(1.0 / s[7]), (float)(2.0 * s[1] + 1.0),
                                                  (float)denom, ls.ohem ? ls.tau.as<uint32_t>() : nullptr,
-                                                 ls.ohem ? ls.tie.as<float>() : nullptr, npi, dldp);
+                                                 ls.ohem ? ls.tie.as<float>() : nullptr, npi, gain, dldp);
   });
 }
 
@@ -999,6 +1002,8 @@ int adp_set_weight(adp_engine *e, const char *layer_name, const float *kernel, c
   int64_t want[4];
   if (n == "down1_conv1") { want[0] = 3; want[1] = 3; want[2] = 1; want[3] = e->c[0]; }
   else if (n == "output_softmax") { want[0] = 1; want[1] = 1; want[2] = e->c[0]; want[3] = 2; }
+  else if (n == "aux_out1") { want[0] = 1; want[1] = 1; want[2] = e->c[2]; want[3] = 1; }
+  else if (n == "aux_out2") { want[0] = 1; want[1] = 1; want[2] = e->c[1]; want[3] = 1; }
   else { ConvLayer &L = layer(e, n); want[0] = 3; want[1] = 3; want[2] = L.cin; want[3] = L.cout; }
   for (int i = 0; i < 4; ++i)
     if (kshape[i] != want[i])
@@ -1371,7 +1376,7 @@ int adp_train_begin(adp_engine *e, int batch, int size, float dropout_rate, uint
 }
 
 int adp_train_forward(adp_engine *e, const float *x, const float *y, int batch, const uint8_t *const *dropout_masks,
-                      double sums[8]) {
+                      double *sums) {
   ADP_TRY
   ADP_REQUIRE(e && x && y && sums, "null argument");
   ADP_CUDA(cudaSetDevice(e->device));
@@ -1394,7 +1399,21 @@ int adp_train_set_loss(adp_engine *e, float ohem_keep_ratio, float eps_pos, floa
   ADP_CATCH
 }
 
-int adp_train_backward(adp_engine *e, const double sums[8], int freeze_encoder) {
+int adp_train_set_deep_supervision(adp_engine *e, int on, float w_main, float w_aux1, float w_aux2) {
+  ADP_TRY
+  ADP_REQUIRE(e, "engine");
+  if (e->tr) throw Error(ADP_ESTATE, "deep supervision cannot change while a training state is open (adp_train_end first)");
+  if (on)
+    for (const char *n : kAuxNames)
+      if (!e->hw.count(n) || !e->hw[n].set) throw Error(ADP_ESTATE, std::string("weights of layer ") + n + " not set");
+  e->deep_sup = on != 0;
+  e->ds_w[0] = w_main; e->ds_w[1] = w_aux1; e->ds_w[2] = w_aux2;
+  ADP_CATCH
+}
+
+int adp_train_outputs(adp_engine *e) { return e && e->deep_sup ? 3 : 1; }
+
+int adp_train_backward(adp_engine *e, const double *sums, int freeze_encoder) {
   ADP_TRY
   ADP_REQUIRE(e && sums, "null argument");
   ADP_CUDA(cudaSetDevice(e->device));
@@ -1440,9 +1459,9 @@ int adp_train_get_grad(adp_engine *e, const char *layer_name, float *kernel, int
   ADP_CUDA(cudaSetDevice(e->device));
   size_t off = 0;
   bool found = false;
-  for (const char *n : kAllNames) {
+  for (const std::string &n : param_names(e)) {
     const size_t ke = kernel_elems_of(e, n), be = bias_elems_of(e, n);
-    if (std::string(n) == layer_name) {
+    if (n == layer_name) {
       ADP_CUDA(cudaStreamSynchronize(e->stream));
       if (kernel) { ADP_REQUIRE(kernel_elems == (int64_t)ke, "kernel_elems"); ADP_CUDA(cudaMemcpy(kernel, e->tr->grad.as<float>() + off, ke * 4, cudaMemcpyDeviceToHost)); }
       if (bias) { ADP_REQUIRE(nbias == (int64_t)be, "nbias"); ADP_CUDA(cudaMemcpy(bias, e->tr->grad.as<float>() + off + ke, be * 4, cudaMemcpyDeviceToHost)); }
@@ -1484,9 +1503,16 @@ int adp_train_step(adp_engine *e, const float *x, const float *y, int batch, int
   ADP_REQUIRE(e && x && y, "null argument");
   ADP_REQUIRE(optimizer == ADP_OPT_ADAM || optimizer == ADP_OPT_ADAMW, "optimizer");
   ADP_CUDA(cudaSetDevice(e->device));
-  double sums[8];
+  double sums[24];
   train_forward(e, x, y, batch, nullptr, sums);
-  if (out) loss_from_sums8(sums, out);
+  if (out) {
+    loss_from_sums8(sums, out);
+    if (e->deep_sup) {       // Keras total = sum of weighted output losses; bce / dice_loss / dice_coef stay those of main_out
+      double a1[4], a2[4];
+      loss_from_sums8(sums + 8, a1); loss_from_sums8(sums + 16, a2);
+      out[0] = e->ds_w[0] * out[0] + e->ds_w[1] * a1[0] + e->ds_w[2] * a2[0];
+    }
+  }
   train_backward(e, sums, freeze_encoder != 0);
   train_apply(e, optimizer, lr, 1.f, 0.9, 0.999, 1e-7f, weight_decay, freeze_encoder != 0);
   ADP_CATCH

@@ -153,8 +153,9 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(View<T> xin, View<T> 
 
 // UpSampling2D backward: glow[y][x] = sum of the 2x2 block of ghigh
 // x.p != null: the result is also multiplied by [x > 0] * scale (ReLU' / dropout of the layer that produced the low-res tensor)
+// resid.p != null: a second gradient into the same low-res tensor (deep-supervision head) is added before the mask
 template <typename T>
-__global__ void __launch_bounds__(256) upsample2_bwd_kernel(View<T> ghigh, View<T> glow, int nb, View<T> x, float scale) {
+__global__ void __launch_bounds__(256) upsample2_bwd_kernel(View<T> ghigh, View<T> glow, int nb, View<T> x, float scale, View<T> resid) {
   const int G = glow.C / 8;
   const size_t total = (size_t)nb * glow.H * G * glow.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -165,6 +166,11 @@ __global__ void __launch_bounds__(256) upsample2_bwd_kernel(View<T> ghigh, View<
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       load8<T>(ghigh.p + ghigh.at(n, 2 * yy + (q >> 1), gi, 2 * xx + (q & 1)), a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] += a[k];
+    }
+    if (resid.p) {
+      load8<T>(resid.p + resid.at(n, yy, gi, xx), a);
 #pragma unroll
       for (int k = 0; k < 8; ++k) s[k] += a[k];
     }
@@ -436,6 +442,136 @@ pack_tc_kernel(const float *__restrict__ wp, __nv_bfloat16 *__restrict__ dst, in
     const size_t o = kys ? ((size_t)v * nchunks + c) * ntaps * blk + tc_block_index(1, ntaps, N, t, g, n, j) : i;
     dst[o] = __float2bfloat16_rn(val);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deep supervision (train_adipose_unet_v3.py:712-745): aux_out = sigmoid(Conv2D(1, 1x1)(up)) at the decoder level's
+// resolution, tf.image.resize(..., [S, S], 'bilinear') (half-pixel centres, no antialias) to full resolution.
+// Forward: one thread per low-res pixel.  w: [C] (zero in pad channels), a_low: [nb][h][w] fp32.
+template <typename T>
+__global__ void __launch_bounds__(256)
+aux_head_fwd_kernel(View<T> x, int nb, const float *__restrict__ w /*[Creal]*/, const float *__restrict__ b, int creal,
+                    float *__restrict__ a_low) {
+  extern __shared__ float sm[];
+  for (int i = threadIdx.x; i < x.C; i += blockDim.x) sm[i] = i < creal ? w[i] : 0.f;
+  __syncthreads();
+  const size_t total = (size_t)nb * x.H * x.W;
+  for (size_t px = blockIdx.x * (size_t)blockDim.x + threadIdx.x; px < total; px += (size_t)gridDim.x * blockDim.x) {
+    const int xx = px % x.W; size_t r = px / x.W; const int yy = r % x.H, n = r / x.H;
+    float z = b[0];
+    for (int gi = 0; gi < x.C / 8; ++gi) {
+      float a[8];
+      load8<T>(x.p + x.at(n, yy, gi, xx), a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) z = fmaf(a[k], sm[gi * 8 + k], z);
+    }
+    a_low[px] = 1.f / (1.f + expf(-z));
+  }
+}
+
+// source index pair and lerp weight of output index o for scale = in/out (TF2 / half_pixel_centers bilinear)
+ADP_DEVINL void bilinear_src(int o, float scale, int n_in, int &lo, int &hi, float &t) {
+  const float in = ((float)o + 0.5f) * scale - 0.5f;
+  const float fl = floorf(in);
+  lo = max((int)fl, 0);
+  hi = min((int)ceilf(in), n_in - 1);
+  t = in - fl;
+}
+
+__global__ void __launch_bounds__(256)
+bilinear_up_kernel(const float *__restrict__ a_low, int nb, int h, int S, float *__restrict__ a_full) {
+  const float scale = (float)h / (float)S;
+  const size_t total = (size_t)nb * S * S;
+  for (size_t px = blockIdx.x * (size_t)blockDim.x + threadIdx.x; px < total; px += (size_t)gridDim.x * blockDim.x) {
+    const int xx = px % S; size_t r = px / S; const int yy = r % S, n = r / S;
+    int y0, y1, x0, x1; float ty, tx;
+    bilinear_src(yy, scale, h, y0, y1, ty);
+    bilinear_src(xx, scale, h, x0, x1, tx);
+    const float *A = a_low + (size_t)n * h * h;
+    const float top = A[(size_t)y0 * h + x0] + (A[(size_t)y0 * h + x1] - A[(size_t)y0 * h + x0]) * tx;
+    const float bot = A[(size_t)y1 * h + x0] + (A[(size_t)y1 * h + x1] - A[(size_t)y1 * h + x0]) * tx;
+    a_full[px] = top + (bot - top) * ty;
+  }
+}
+
+// Adjoint of bilinear_up_kernel, gather form (deterministic): low-res pixel (jy, jx) collects w * g_full over the
+// full-res pixels whose interpolation reads it; the weights come from the same bilinear_src, so border clamping is
+// handled by construction.  Output is multiplied by `gain` (the loss weight of the auxiliary output).
+__global__ void __launch_bounds__(256)
+bilinear_up_bwd_kernel(const float *__restrict__ g_full, int nb, int h, int S, float gain, float *__restrict__ g_low) {
+  const float scale = (float)h / (float)S;
+  const int f = S / h;                               // integer upsampling factor (4 or 2)
+  const size_t total = (size_t)nb * h * h;
+  for (size_t px = blockIdx.x * (size_t)blockDim.x + threadIdx.x; px < total; px += (size_t)gridDim.x * blockDim.x) {
+    const int jx = px % h; size_t r = px / h; const int jy = r % h, n = r / h;
+    const float *G = g_full + (size_t)n * S * S;
+    float acc = 0.f;
+    const int iy_lo = max(f * (jy - 1), 0), iy_hi = min(f * (jy + 2) - 1, S - 1);
+    const int ix_lo = max(f * (jx - 1), 0), ix_hi = min(f * (jx + 2) - 1, S - 1);
+    for (int iy = iy_lo; iy <= iy_hi; ++iy) {
+      int y0, y1; float ty;
+      bilinear_src(iy, scale, h, y0, y1, ty);
+      const float wy = (y0 == jy ? 1.f - ty : 0.f) + (y1 == jy ? ty : 0.f);
+      if (wy == 0.f) continue;
+      float row = 0.f;
+      for (int ix = ix_lo; ix <= ix_hi; ++ix) {
+        int x0, x1; float tx;
+        bilinear_src(ix, scale, h, x0, x1, tx);
+        const float wx = (x0 == jx ? 1.f - tx : 0.f) + (x1 == jx ? tx : 0.f);
+        if (wx != 0.f) row = fmaf(wx, G[(size_t)iy * S + ix], row);
+      }
+      acc = fmaf(wy, row, acc);
+    }
+    g_low[px] = acc * gain;
+  }
+}
+
+// Backward of the 1x1 sigmoid head: dz = g_low * a * (1 - a); R[c] = dz * w[c] is written in the layout of the tensor's
+// gradient (added by the data-gradient epilogue of the conv that consumes the tensor); dW[c] = sum dz * x[c], db = sum dz
+// (block reduction, one double atomic per block and channel).
+template <typename T>
+__global__ void __launch_bounds__(256)
+aux_head_bwd_kernel(View<T> x, int nb, const float *__restrict__ w, int creal, const float *__restrict__ a_low,
+                    const float *__restrict__ g_low, View<T> resid, double *__restrict__ dwb /*[C + 1]*/) {
+  extern __shared__ float sm[];
+  float *wd = sm;                       // C
+  float *red = sm + x.C;                // C + 1
+  const int C = x.C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) wd[i] = i < creal ? w[i] : 0.f;
+  for (int i = threadIdx.x; i <= C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const size_t total = (size_t)nb * x.H * x.W;
+  const size_t px = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  float dz = 0.f;
+  int xx = 0, yy = 0, n = 0;
+  const bool live = px < total;
+  if (live) {
+    xx = px % x.W; size_t r = px / x.W; yy = r % x.H; n = r / x.H;
+    const float a = a_low[px];
+    dz = g_low[px] * a * (1.f - a);
+  }
+  for (int gi = 0; gi < C / 8; ++gi) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o[8];
+    if (live) load8<T>(x.p + x.at(n, yy, gi, xx), a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      o[k] = dz * wd[gi * 8 + k];
+      const float s = warp_sum(dz * a[k]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&red[gi * 8 + k], s);
+    }
+    if (live) store8<T>(resid.p + resid.at(n, yy, gi, xx), o);
+  }
+  {
+    const float s = warp_sum(dz);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[C], s);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= C; i += blockDim.x) atomicAdd(&dwb[i], (double)red[i]);
+}
+
+__global__ void aux_grad_finish_kernel(const double *__restrict__ dwb, int creal, int C, float *__restrict__ gk, float *__restrict__ gb) {
+  for (int i = threadIdx.x; i < creal; i += blockDim.x) gk[i] = (float)dwb[i];
+  if (threadIdx.x == 0) gb[0] = (float)dwb[C];
 }
 
 }  // namespace adp

@@ -47,7 +47,10 @@ struct TrainState {
   int64_t iter = 0;           // optimizer iterations done
   size_t P = 0;
   DevBuf theta, grad, m, v;
-  size_t koff_first = 0, boff_first = 0, koff_head = 0, boff_head = 0;
+  size_t koff_first = 0, boff_first = 0, koff_head = 0, boff_head = 0, koff_aux[2] = {0, 0}, boff_aux[2] = {0, 0};
+  // deep supervision: low-res sigmoid maps, their bilinear upsamplings, gradient scratch, residual tensors for the dgrad epilogues
+  DevBuf a_low[2], aux_full[2], g_low, resid[2], g_aux;
+  LossState ls_aux[2];
   std::vector<TrainLayer> tl;
   DevBuf gw_first, gb_first, g_head;     // [9][cp0], [cp0], double [cp0 + 1]
   DevBuf zeros;
@@ -64,15 +67,25 @@ struct TrainState {
   DevBuf mask_stage[4];
 };
 
+// parameter tensors in flat-buffer order: the 22 layers of the graph, then the deep-supervision heads when enabled
+std::vector<std::string> param_names(adp_engine *e) {
+  std::vector<std::string> v(kAllNames, kAllNames + 22);
+  if (e->deep_sup) { v.push_back(kAuxNames[0]); v.push_back(kAuxNames[1]); }
+  return v;
+}
+
 size_t kernel_elems_of(adp_engine *e, const std::string &n) {
   if (n == "down1_conv1") return (size_t)9 * e->c[0];
   if (n == "output_softmax") return (size_t)2 * e->c[0];
+  if (n == "aux_out1") return (size_t)e->c[2];
+  if (n == "aux_out2") return (size_t)e->c[1];
   const ConvLayer &L = layer(e, n);
   return (size_t)9 * L.cin * L.cout;
 }
 size_t bias_elems_of(adp_engine *e, const std::string &n) {
   if (n == "down1_conv1") return e->c[0];
   if (n == "output_softmax") return 2;
+  if (n == "aux_out1" || n == "aux_out2") return 1;
   return layer(e, n).cout;
 }
 
@@ -124,7 +137,7 @@ void sync_host_weights(adp_engine *e) {
   ADP_CUDA(cudaStreamSynchronize(e->stream));
   ADP_CUDA(cudaMemcpy(h.data(), tr->theta.p, tr->P * 4, cudaMemcpyDeviceToHost));
   size_t off = 0;
-  for (const char *n : kAllNames) {
+  for (const std::string &n : param_names(e)) {
     HostWeight &w = e->hw[n];
     const size_t ke = kernel_elems_of(e, n), be = bias_elems_of(e, n);
     w.k.assign(h.begin() + off, h.begin() + off + ke); off += ke;
@@ -169,11 +182,12 @@ void train_alloc(adp_engine *e, int nb, int S, float dropout_rate, uint64_t seed
   size_t off = 0;
   tr->tl.resize(e->layers.size());
   std::vector<float> h;
-  for (const char *nm : kAllNames) {
-    const std::string n2 = nm;
+  for (const std::string &n2 : param_names(e)) {
     const size_t ke = kernel_elems_of(e, n2), be = bias_elems_of(e, n2);
     if (n2 == "down1_conv1") { tr->koff_first = off; tr->boff_first = off + ke; }
     else if (n2 == "output_softmax") { tr->koff_head = off; tr->boff_head = off + ke; }
+    else if (n2 == "aux_out1") { tr->koff_aux[0] = off; tr->boff_aux[0] = off + ke; }
+    else if (n2 == "aux_out2") { tr->koff_aux[1] = off; tr->boff_aux[1] = off + ke; }
     else {
       for (size_t i = 0; i < e->layers.size(); ++i)
         if (e->layers[i].name == n2) { tr->tl[i].koff = off; tr->tl[i].boff = off + ke; }
@@ -205,6 +219,13 @@ void train_alloc(adp_engine *e, int nb, int S, float dropout_rate, uint64_t seed
     }
   }
   tr->gw_first.ensure((size_t)9 * cp[0] * 4); tr->gb_first.ensure((size_t)cp[0] * 4); tr->g_head.ensure((size_t)(cp[0] + 1) * 8);
+  if (e->deep_sup) {
+    tr->a_low[0].ensure(n * s3 * 4); tr->a_low[1].ensure(n * s2 * 4);
+    tr->aux_full[0].ensure(n * s1 * 4); tr->aux_full[1].ensure(n * s1 * 4);
+    tr->g_low.ensure(n * s2 * 4);
+    tr->resid[0].ensure(n * s3 * cp[2] * es); tr->resid[1].ensure(n * s2 * cp[1] * es);
+    tr->g_aux.ensure((size_t)(cp[2] + 1) * 8);
+  }
   delete e->tr;
   e->tr = tr.release();
   repack_from_theta(e);
@@ -212,7 +233,7 @@ void train_alloc(adp_engine *e, int nb, int S, float dropout_rate, uint64_t seed
 }
 
 // ---- forward -----------------------------------------------------------------------------------
-void train_forward(adp_engine *e, const float *x, const float *y, int n, const uint8_t *const *masks, double sums[8]) {
+void train_forward(adp_engine *e, const float *x, const float *y, int n, const uint8_t *const *masks, double *sums /* 8 per output */) {
   TrainState *tr = e->tr;
   if (!tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
   ADP_REQUIRE(n == tr->nb, "batch size differs from adp_train_begin");
@@ -244,6 +265,30 @@ void train_forward(adp_engine *e, const float *x, const float *y, int n, const u
   if (e->prec == ADP_PREC_FP32) forward_t<float>(e, tr->acts, S, src, fw, n, 0.f, 1.f, nullptr, dropping ? &d : &none);
   else forward_t<__nv_bfloat16>(e, tr->acts, S, src, fw, n, 0.f, 1.f, nullptr, dropping ? &d : &none);
   loss_forward(e, tr->ls, e->loss, tr->prob.as<float>(), tr->y.as<float>(), n, (size_t)S * S, sums);
+  if (e->deep_sup) {
+    // aux_out1 <- post-dropout up3 (S/4), aux_out2 <- post-dropout up2 (S/2); their losses never use hard mining
+    // (train_adipose_unet_v3.py:812-838: loss_fn_aux is the standard or the label-smoothing loss)
+    LossRecipe ra = e->loss; ra.ohem_keep = 1.f;
+    const int hs[2] = {S / 4, S / 2}, cps[2] = {e->cp[2], e->cp[1]}, crs[2] = {e->c[2], e->c[1]};
+    DevBuf *src[2] = {&tr->u3c, &tr->u2c};
+    for (int a = 0; a < 2; ++a) {
+      const size_t lowpx = (size_t)n * hs[a] * hs[a];
+      const float *th = tr->theta.as<float>();
+      auto launch_fwd = [&](auto tag) {
+        using T = decltype(tag);
+        auto v = view<T>(*src[a], hs[a], hs[a], cps[a], 0, cps[a]);
+        e->launch("aux_head", 2.0 * lowpx * crs[a], (double)lowpx * (cps[a] * sizeof(T) + 4), [&] {
+          aux_head_fwd_kernel<T><<<ew_grid(e, lowpx), 256, (size_t)cps[a] * 4, e->stream>>>(v, n, th + tr->koff_aux[a], th + tr->boff_aux[a], crs[a],
+                                                                                          tr->a_low[a].as<float>());
+        });
+      };
+      if (e->prec == ADP_PREC_FP32) launch_fwd(float()); else launch_fwd(__nv_bfloat16());
+      e->launch("aux_bilinear_up", 0, (double)npx * 4 + (double)lowpx * 4, [&] {
+        bilinear_up_kernel<<<ew_grid(e, npx), 256, 0, e->stream>>>(tr->a_low[a].as<float>(), n, hs[a], S, tr->aux_full[a].as<float>());
+      });
+      loss_forward(e, tr->ls_aux[a], ra, tr->aux_full[a].as<float>(), tr->y.as<float>(), n, (size_t)S * S, sums + 8 * (a + 1));
+    }
+  }
   tr->have_forward = true; tr->have_grads = false;
 }
 
@@ -350,11 +395,10 @@ template <typename T> struct Bwd {
       });
     }
     if (L.up) {
-      ADP_REQUIRE(!resid, "no residual on an upsampled conv");
       const size_t total = (size_t)nb * gin.H * gin.W * (gin.C / 8);
       View<T> none{}; none.p = nullptr;
       e->launch("upsample2x2_bwd", 0, (double)total * 8 * sizeof(T) * (mask ? 6 : 5), [&] {
-        upsample2_bwd_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(out, gin, nb, mask ? *mask : none, scale);
+        upsample2_bwd_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(out, gin, nb, mask ? *mask : none, scale, resid ? *resid : none);
       });
     } else if (!fused) {
       if (resid) add(gin, gin, *resid);
@@ -369,7 +413,7 @@ size_t layer_index(adp_engine *e, const char *n) {
   throw Error(ADP_EINVAL, std::string("unknown layer ") + n);
 }
 
-template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
+template <typename T> void backward_t(adp_engine *e, bool freeze_encoder, const double *tr_sums) {
   TrainState *tr = e->tr;
   Bwd<T> B{e, tr, tr->nb};
   const int nb = tr->nb, S = tr->S, S2 = S / 2, S3 = S / 4, S4 = S / 8;
@@ -402,6 +446,34 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
        "up2_conv1", "up2_conv2", "up2_conv3", "down2_conv1", "down2_conv2"},
       {S3, cp[2], &tr->cat3, &tr->g_cat3, &tr->u3b, &tr->g_u3b, &tr->u3c, &tr->g_u3c, &tr->d3a, &tr->g_d3a, &tr->pl3, &tr->g_pl3,
        "up3_conv1", "up3_conv2", "up3_conv3", "down3_conv1", "down3_conv2"}};
+  // deep supervision: gradients of the two auxiliary outputs -> head weight gradients + residual tensors that the data
+  // gradient into up3 / up2 adds before the ReLU'/dropout mask (both tensors are read post-dropout by their heads)
+  if (e->deep_sup) {
+    LossRecipe ra = e->loss; ra.ohem_keep = 1.f;
+    const int hs[2] = {S3, S2}, cps[2] = {cp[2], cp[1]}, crs[2] = {e->c[2], e->c[1]};
+    DevBuf *src[2] = {&tr->u3c, &tr->u2c};
+    const size_t npx = (size_t)nb * S * S;
+    for (int a = 0; a < 2; ++a) {
+      const size_t lowpx = (size_t)nb * hs[a] * hs[a];
+      loss_backward(e, tr->ls_aux[a], ra, tr->aux_full[a].as<float>(), tr->y.as<float>(), nb, (size_t)S * S, tr_sums + 8 * (a + 1),
+                    tr->dldp.as<float>(), e->ds_w[a + 1]);
+      e->launch("aux_bilinear_up_bwd", 0, (double)npx * 4 + (double)lowpx * 4, [&] {
+        bilinear_up_bwd_kernel<<<ew_grid(e, lowpx), 256, 0, e->stream>>>(tr->dldp.as<float>(), nb, hs[a], S, 1.0f, tr->g_low.as<float>());
+      });
+      ADP_CUDA(cudaMemsetAsync(tr->g_aux.p, 0, (size_t)(cps[a] + 1) * 8, e->stream));
+      auto x = B.V(*src[a], hs[a], cps[a], 0, cps[a]);
+      auto r = B.V(tr->resid[a], hs[a], cps[a], 0, cps[a]);
+      const float *th = tr->theta.as<float>();
+      e->launch("aux_head_bwd", 4.0 * lowpx * crs[a], (double)lowpx * (2.0 * cps[a] * sizeof(T) + 8), [&] {
+        aux_head_bwd_kernel<T><<<(int)cdiv64(lowpx, 256), 256, (size_t)(2 * cps[a] + 1) * 4, e->stream>>>(
+            x, nb, th + tr->koff_aux[a], crs[a], tr->a_low[a].as<float>(), tr->g_low.as<float>(), r, tr->g_aux.as<double>());
+      });
+      e->launch("aux_grad_finish", 0, 0, [&] {
+        aux_grad_finish_kernel<<<1, 256, 0, e->stream>>>(tr->g_aux.as<double>(), crs[a], cps[a], tr->grad.as<float>() + tr->koff_aux[a],
+                                                        tr->grad.as<float>() + tr->boff_aux[a]);
+      });
+    }
+  }
   // decoder, levels 1..3
   for (int l = 0; l < 3; ++l) {
     const Lvl &q = lv[l];
@@ -417,7 +489,8 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
       const Lvl &n = lv[l + 1];
       auto src = B.V(*n.uc, n.H, n.c, 0, n.c), g_src = B.V(*n.g_uc, n.H, n.c, 0, n.c);
       B.wgrad(li(q.c1), src, g_cat_up);
-      B.dgrad(li(q.c1), g_cat_up, g_src, &src, inv_keep);
+      auto aux_r = B.V(tr->resid[1 - l], n.H, n.c, 0, n.c);      // l = 0 feeds up2 (aux_out2), l = 1 feeds up3 (aux_out1)
+      B.dgrad(li(q.c1), g_cat_up, g_src, &src, inv_keep, e->deep_sup ? &aux_r : nullptr);
     } else {           // up3_conv1 reads the Add of the six bottleneck tensors (no activation of its own)
       auto ts = B.V(tr->ts, S4, cp[3], 0, cp[3]), g_ts = B.V(tr->g_ts, S4, cp[3], 0, cp[3]);
       B.wgrad(li(q.c1), ts, g_cat_up);
@@ -477,16 +550,17 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
   }
 }
 
-void train_backward(adp_engine *e, const double sums[8], bool freeze_encoder) {
+void train_backward(adp_engine *e, const double *sums /* 8 per output */, bool freeze_encoder) {
   TrainState *tr = e->tr;
   if (!tr || !tr->have_forward) throw Error(ADP_ESTATE, "adp_train_forward must run first");
-  loss_backward(e, tr->ls, e->loss, tr->prob.as<float>(), tr->y.as<float>(), tr->nb, (size_t)tr->S * tr->S, sums, tr->dldp.as<float>());
+  loss_backward(e, tr->ls, e->loss, tr->prob.as<float>(), tr->y.as<float>(), tr->nb, (size_t)tr->S * tr->S, sums, tr->dldp.as<float>(),
+                e->deep_sup ? e->ds_w[0] : 1.f);
   if (freeze_encoder) {   // frozen tensors report zero gradient
     const size_t first_trainable = tr->tl[layer_index(e, "dilate1")].koff;
     ADP_CUDA(cudaMemsetAsync(tr->grad.p, 0, first_trainable * 4, e->stream));
   }
-  if (e->prec == ADP_PREC_FP32) backward_t<float>(e, freeze_encoder);
-  else backward_t<__nv_bfloat16>(e, freeze_encoder);
+  if (e->prec == ADP_PREC_FP32) backward_t<float>(e, freeze_encoder, sums);
+  else backward_t<__nv_bfloat16>(e, freeze_encoder, sums);
   ADP_CUDA(cudaStreamSynchronize(e->stream));
   tr->have_grads = true;
 }

@@ -45,6 +45,13 @@ def conv_layers(init_nb: int = INIT_NB):
 LAYER_NAMES = [l[0] for l in conv_layers()]
 
 
+AUX_NAMES = ("aux_out1", "aux_out2")      # deep-supervision heads (train_adipose_unet_v3.py:712-725)
+
+
+def aux_weight_shapes(init_nb: int = INIT_NB):
+    return {"aux_out1": ((1, 1, 4 * init_nb, 1), (1,)), "aux_out2": ((1, 1, 2 * init_nb, 1), (1,))}
+
+
 def weight_shapes(init_nb: int = INIT_NB):
     """name -> (kernel_shape HWIO, bias_shape)."""
     return {n: ((k, k, ci, co), (co,)) for n, ci, co, k, _ in conv_layers(init_nb)}

@@ -198,12 +198,21 @@ int adp_train_set_loss(adp_engine *e, float ohem_keep_ratio, float eps_pos, floa
  * sums = {sum of the BCE terms in the mean, sum ys*pc, sum ys, sum pc, sum y*p, sum p, sum y, number of BCE terms} over this
  * batch (pc = clip(p,1e-7,1-1e-7), ys = smoothed target); every entry is additive over data-parallel ranks. */
 int adp_train_forward(adp_engine *e, const float *x, const float *y, int batch, const uint8_t *const *dropout_masks,
-                      double sums[8]);
+                      double *sums /* 8 per output: adp_train_outputs() x 8 */);
 /* loss = {loss, bce_mean, dice_loss, dice_coef} from (possibly rank-summed) sums */
 int adp_train_loss(const double sums[8], double out[4]);
 /* sums: the values the loss is defined over (own batch, or summed over data-parallel ranks);
  * freeze_encoder != 0 = phase 1 of the reference (down*_conv* frozen, :760-769): their gradients are zero */
-int adp_train_backward(adp_engine *e, const double sums[8], int freeze_encoder);
+int adp_train_backward(adp_engine *e, const double *sums /* 8 per output */, int freeze_encoder);
+/* Deep supervision (train_adipose_unet_v3.py:712-745, 808-872): while training, aux_out1 = sigmoid(Conv2D(1,1x1)) on the
+ * post-dropout up3 tensor (size/4) and aux_out2 on up2 (size/2), each bilinearly resized (half-pixel centres) to full
+ * resolution and scored against y with the standard / label-smoothing loss (never hard mining); total loss =
+ * w_main*L(main_out) + w_aux1*L(aux_out1) + w_aux2*L(aux_out2).  Needs the layers "aux_out1" (1,1,4*init_nb,1) and
+ * "aux_out2" (1,1,2*init_nb,1) set with adp_set_weight; they join the flat parameter / gradient buffer after
+ * output_softmax.  Inference ignores them (full_evaluation_enhanced.py:1313-1319 only reads main_out).
+ * adp_train_outputs: 1, or 3 with deep supervision = number of 8-double groups in `sums` (main, aux1, aux2). */
+int adp_train_set_deep_supervision(adp_engine *e, int on, float w_main, float w_aux1, float w_aux2);
+int adp_train_outputs(adp_engine *e);
 /* device pointer + element count of the flat fp32 gradient (Keras order: per layer kernel HWIO, bias) */
 int adp_train_grad_buffer(adp_engine *e, float **dev_ptr, int64_t *count);
 /* whole flat gradient to / from host memory (count must equal the parameter count): the staging path of a

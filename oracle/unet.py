@@ -36,12 +36,14 @@ def _layers(init_nb=44):
 
 
 DILATION = {n: d for n, _, _, _, d in _layers()}
+DILATION.update({"aux_out1": 1, "aux_out2": 1})     # deep-supervision heads, train_adipose_unet_v3.py:715, 722
 
 
 def to_torch_params(weights: Dict[str, np.ndarray], dtype=torch.float32, requires_grad=False):
     """HWIO kernels -> OIHW tensors; name -> (w, b)."""
     p = {}
-    for name, *_ in _layers():
+    names = [n for n, *_ in _layers()] + [n for n in ("aux_out1", "aux_out2") if n + "/kernel" in weights]
+    for name in names:
         k = torch.from_numpy(np.ascontiguousarray(weights[name + "/kernel"])).to(dtype)
         b = torch.from_numpy(np.ascontiguousarray(weights[name + "/bias"])).to(dtype)
         w = k.permute(3, 2, 0, 1).contiguous()
@@ -62,7 +64,7 @@ def _conv(x, p, name, act=True):
 
 
 def forward(x: torch.Tensor, p, dropout_masks: Optional[Dict[str, torch.Tensor]] = None,
-            taps: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+            taps: Optional[Dict[str, torch.Tensor]] = None, deep_supervision: bool = False):
     """Graph of train_adipose_unet_v3.py:664-752.  x: (B,H,W) already normalised.
     Returns (B,H,W) probabilities = softmax(z)[...,1] = sigmoid(z1-z0).
     dropout_masks (training only): name -> 0/1 mask, applied with the inverted
@@ -119,7 +121,16 @@ def forward(x: torch.Tensor, p, dropout_masks: Optional[Dict[str, torch.Tensor]]
 
     z = _conv(u1, p, "output_softmax", act=False)   # (B,2,H,W)
     prob = torch.softmax(z, dim=1)[:, 1]            # channel 1, squeezed (:748-750)
-    return rec("prob", prob)
+    if not deep_supervision:
+        return rec("prob", prob)
+    # deep supervision (:712-745): sigmoid 1x1 heads on the post-dropout up3 / up2 tensors, tf.image.resize(...,
+    # 'bilinear') to the input size = half-pixel centres without antialiasing = F.interpolate(align_corners=False)
+    size = x.shape[-2:]
+    a1 = torch.sigmoid(_conv(u3, p, "aux_out1", act=False))
+    a2 = torch.sigmoid(_conv(u2, p, "aux_out2", act=False))
+    a1 = F.interpolate(a1, size=size, mode="bilinear", align_corners=False)[:, 0]
+    a2 = F.interpolate(a2, size=size, mode="bilinear", align_corners=False)[:, 0]
+    return rec("prob", prob), rec("aux_out1", a1), rec("aux_out2", a2)
 
 
 def predict_single(image: np.ndarray, mean: float, std: float, p, dtype=torch.float32) -> np.ndarray:
@@ -197,7 +208,7 @@ def dice_coef(y, p):
 
 # ------------------------------------------------------------------ T2
 def loss_and_grads(x: np.ndarray, y: np.ndarray, weights, dtype=torch.float32,
-                   dropout_masks=None, loss_fn=None):
+                   dropout_masks=None, loss_fn=None, ds_weights=None, loss_fn_aux=None):
     """One forward+backward of combined_loss_standard through the graph.
     x: (B,H,W) normalised float32, y: (B,H,W) {0,1}.  Returns loss, dice_coef,
     prob, dL/dprob and name -> (dW HWIO, db)."""
@@ -207,9 +218,16 @@ def loss_and_grads(x: np.ndarray, y: np.ndarray, weights, dtype=torch.float32,
     dm = None
     if dropout_masks is not None:
         dm = {k: torch.from_numpy(v).to(dtype) for k, v in dropout_masks.items()}
-    prob = forward(xt, p, dropout_masks=dm)
-    prob.retain_grad()
-    loss = (loss_fn or combined_loss_standard)(yt, prob)
+    if ds_weights is not None:
+        # compile(loss={main, aux1, aux2}, loss_weights=...) (:858-872): total = sum of weighted output losses
+        prob, a1, a2 = forward(xt, p, dropout_masks=dm, deep_supervision=True)
+        prob.retain_grad()
+        fa = loss_fn_aux or combined_loss_standard
+        loss = ds_weights[0] * (loss_fn or combined_loss_standard)(yt, prob) + ds_weights[1] * fa(yt, a1) + ds_weights[2] * fa(yt, a2)
+    else:
+        prob = forward(xt, p, dropout_masks=dm)
+        prob.retain_grad()
+        loss = (loss_fn or combined_loss_standard)(yt, prob)
     loss.backward()
     grads = {}
     for name, (w, b) in p.items():

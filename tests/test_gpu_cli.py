@@ -45,8 +45,9 @@ def workspace(tmp_path_factory):
 def test_train_then_eval_infer_recon(workspace, capsys):
     ws = workspace
     rc = train.main(["--data-root", str(ws / "build"), "--pretrained-weights", str(ws / "none.h5"), "--batch-size", "1",
-                     "--epochs-phase1", "1", "--epochs-phase2", "1", "--normalization-method", "zscore", "--no-deep-supervision",
-                     "--no-hard-mining", "--checkpoint-root", str(ws / "ckpt"), "--max-steps-per-epoch", "2"])
+                     "--epochs-phase1", "1", "--epochs-phase2", "1", "--normalization-method", "zscore",
+                     "--checkpoint-root", str(ws / "ckpt"), "--max-steps-per-epoch", "2"])      # the reference's DEFAULT recipe:
+    # deep supervision + hard-example mining + cosine schedule
     assert rc == 0
     ckpts = list((ws / "ckpt").iterdir())
     assert len(ckpts) == 1 and ckpts[0].name.endswith("_adipose_sybreosin_1024_finetune_v3")
@@ -56,8 +57,11 @@ def test_train_then_eval_infer_recon(workspace, capsys):
         assert (ck / f).exists(), f
     stats = json.loads((ck / "normalization_stats.json").read_text())
     assert set(stats) == {"mean", "std", "normalization_method", "dataset_path", "num_training_images", "build_timestamp", "version"}
-    assert "use_deep_supervision: False" in (ck / "training_settings.log").read_text()
+    assert "use_deep_supervision: True" in (ck / "training_settings.log").read_text()
+    wa = load_weights_file(str(ck / "weights_best_overall.weights.h5"), keep_aux=True)
+    assert wa["aux_out1/kernel"].shape == (1, 1, 176, 1) and wa["aux_out2/kernel"].shape == (1, 1, 88, 1)
     w = load_weights_file(str(ck / "weights_best_overall.weights.h5"))
+    assert "aux_out1/kernel" not in w                       # inference loads the 22 graph layers only
     assert w["down1_conv1/kernel"].shape == (3, 3, 1, 44) and w["output_softmax/kernel"].shape == (1, 1, 44, 2)
     rows = list(csv.DictReader(open(ck / "phase2_training.log")))
     assert len(rows) == 1 and np.isfinite(float(rows[0]["val_dice_coef"]))

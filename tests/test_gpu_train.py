@@ -243,3 +243,50 @@ def test_tc_backward_matches_cuda_core_backward(S, weights):
     top = sorted(worst.items(), key=lambda kv: -kv[1])[:4]
     print("S", S, "tcgen05 vs CUDA-core backward, worst L2:", top)
     assert top[0][1] <= 1e-2, top
+
+
+@pytest.mark.parametrize("prec,recipe", [("fp32", (1.0, 0.0, 0.0)), ("fp32", (0.7, 0.03, 0.07)), ("bf16", (0.7, 0.0, 0.0))])
+def test_deep_supervision_step_vs_oracle(prec, recipe):
+    """The reference's DEFAULT training graph (train_adipose_unet_v3.py:712-745, 808-872): two sigmoid 1x1 heads on up3 / up2,
+    bilinear resize to full size, total = 1.0*L(main) + 0.4*L(aux1) + 0.3*L(aux2) with hard mining only on the main output.
+    Loss, every gradient (including the heads') and the extra gradient flowing into up3 / up2."""
+    n, S = 2, 128
+    w = A.synth.init_weights(deep_supervision=True)
+    x, y = batch(n, S, seed=29)
+    masks = dropout_masks(n, S, seed=6)
+    omasks = {k: np.ascontiguousarray(v.transpose(0, 3, 1, 2)).astype(np.float32) for k, v in masks.items()}
+    keep, ep, en = recipe
+    f_main = (lambda yt, p: U.online_hard_example_mining_loss(yt, p, keep, ep, en)) if keep < 1 else \
+        ((lambda yt, p: U.combined_loss_with_label_smoothing(yt, p, ep, en)) if (ep or en) else None)
+    f_aux = (lambda yt, p: U.combined_loss_with_label_smoothing(yt, p, ep, en)) if (ep or en) else None
+    dsw = (1.0, 0.4, 0.3)
+    loss_ref, dice_ref, prob_ref, _, g_ref = U.loss_and_grads(x, y, w, dropout_masks=omasks, loss_fn=f_main, ds_weights=dsw, loss_fn_aux=f_aux)
+    eng = api.Engine(precision=prec, max_forwards=8)
+    eng.set_weights(w)
+    eng.train_set_loss(keep, ep, en)
+    eng.train_set_deep_supervision(True, *dsw)
+    eng.train_begin(n, S, dropout_rate=0.0)
+    sums = eng.train_forward(x, y, masks)
+    assert len(sums) == 24
+    loss = eng.train_loss(sums)
+    eng.train_backward(sums)
+    g = eng.train_grads()
+    assert set(g) == set(g_ref) and "aux_out1/kernel" in g and g["aux_out2/kernel"].shape == (1, 1, 88, 1)
+    ltol = 1e-5 if prec == "fp32" else 2e-2
+    assert abs(loss["loss"] - loss_ref) <= ltol * max(1.0, abs(loss_ref)), (loss, loss_ref)
+    assert abs(loss["dice_coef"] - dice_ref) <= (1e-5 if prec == "fp32" else 1e-2)
+    worst = {k: l2_err(g[k], g_ref[k]) for k in g}
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:4]
+    print(prec, recipe, "deep supervision: loss", loss["loss"], loss_ref, "aux losses", loss.get("aux_out1_loss"), loss.get("aux_out2_loss"),
+          "worst grad L2", top)
+    assert top[0][1] <= (2e-3 if prec == "fp32" else 1e-1), top
+    # one optimizer step moves the heads as well and the weights read back include them
+    eng.train_apply(1e-3, "adam")
+    w2 = eng.get_weights()
+    assert not np.array_equal(w2["aux_out1/kernel"], w["aux_out1/kernel"]) and w2["aux_out2/bias"].shape == (1,)
+    eng.train_end()
+    # inference with the same engine ignores the heads
+    tile = A.synth.ecm_tile(S, seed=78).astype(np.float32)
+    p = eng.predict(tile[None], A.synth.DEFAULT_MEAN, A.synth.DEFAULT_STD)[0]
+    assert np.isfinite(p).all() and p.shape == (S, S)
+    eng.close()
