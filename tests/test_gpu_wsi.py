@@ -90,3 +90,29 @@ def test_wsi_strips_equal_single_gpu(setup):
     p1, _, _, _ = _run(eng, slide, 0.75, "linear", None, 1)
     pg, _, _, _ = _run(eng, slide, 0.75, "linear", None, 4)
     assert np.abs(pg - p1).max() <= 1e-6
+
+
+def test_nccl_strips_equal_single_gpu():
+    """Real 2-rank run (torchrun, NCCL device-to-device boundary exchange) against the 1-GPU reconstruction of the same
+    synthetic slide (tools/wsi_full.py): confusion counts cover every pixel and agree up to fp32 summation order at the
+    strip boundary."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (strip arithmetic is covered on one GPU by the emulated-strip tests above)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "tools", "wsi_full.py")
+    args = ["--size", "4096", "--overlap", "0.5", "--tta", "basic"]
+    one = subprocess.run([sys.executable, tool] + args, capture_output=True, text=True, timeout=600, cwd=root)
+    two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29561", tool] + args, capture_output=True, text=True, timeout=600, cwd=root)
+    assert one.returncode == 0 and two.returncode == 0, (one.stderr[-1500:], two.stderr[-1500:])
+    r1 = json.loads([l for l in one.stdout.splitlines() if l.startswith("{")][-1])
+    r2 = json.loads([l for l in two.stdout.splitlines() if l.startswith("{")][-1])
+    assert r1["counts_sum_equals_pixels"] and r2["counts_sum_equals_pixels"] and r2["n_gpus"] == 2
+    diff = sum(abs(a - b) for a, b in zip(r1["counts_tp_fp_fn_tn"], r2["counts_tp_fp_fn_tn"]))
+    print("1-GPU vs 2-GPU counts", r1["counts_tp_fp_fn_tn"], r2["counts_tp_fp_fn_tn"])
+    assert diff <= 1e-5 * 4096 * 4096
