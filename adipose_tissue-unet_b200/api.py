@@ -126,6 +126,15 @@ class Engine:
         _lib.check(self.lib.adp_threshold_metrics(self.h, _lib.ptr(prob), _lib.ptr(g), n, threshold, _lib.ptr(mask), counts))
         return mask, tuple(int(c) for c in counts)
 
+    def threshold_sweep(self, prob, gt, thresholds) -> np.ndarray:
+        """(n_thr, 4) int64 {tp, fp, fn, tn} for ascending candidate thresholds in one device pass."""
+        prob = _f32c(prob)
+        g = np.ascontiguousarray((np.asarray(gt) > 0.5).astype(np.uint8))
+        thr = np.ascontiguousarray(thresholds, dtype=np.float32)
+        counts = np.zeros((len(thr), 4), np.int64)
+        _lib.check(self.lib.adp_threshold_sweep(self.h, _lib.ptr(prob), _lib.ptr(g), prob.size, _lib.ptr(thr), len(thr), _lib.ptr(counts)))
+        return counts
+
     def blend(self, mode: int, tiles: Sequence[np.ndarray], positions, output_shape, window: Optional[np.ndarray]):
         h, w = int(output_shape[0]), int(output_shape[1])
         out = np.empty((h, w), np.float32)

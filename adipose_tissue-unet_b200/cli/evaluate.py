@@ -152,12 +152,17 @@ def tile_metrics(engine, pred, gt, thr):
 
 
 def optimize_threshold_slide_level(engine, preds, gts, paths, thresholds):
-    """full_evaluation_enhanced.py:891-940."""
+    """full_evaluation_enhanced.py:891-940 (slide-macro F1 per candidate, first maximum wins).  The confusion counts of ALL
+    candidates of a tile come from one device pass (adp_threshold_sweep) instead of one pass per candidate."""
+    from .. import api
+    thresholds = np.asarray(thresholds, dtype=np.float64)
+    per_tile = [engine.threshold_sweep(p, g, thresholds.astype(np.float32)) for p, g in zip(preds, gts)]
+    slide_of = [extract_slide_id(path) for path in paths]
     best_t, best_f1 = 0.5, -1.0
-    for t in thresholds:
+    for j, t in enumerate(thresholds):
         per_slide = defaultdict(list)
-        for p, g, path in zip(preds, gts, paths):
-            per_slide[extract_slide_id(path)].append(tile_metrics(engine, p, g, float(t))["f1_score"])
+        for counts, sid in zip(per_tile, slide_of):
+            per_slide[sid].append(api.metrics_from_counts(*[int(c) for c in counts[j]])["f1_score"])
         f1 = float(np.mean([np.mean(v) for v in per_slide.values()]))
         print(f"  Threshold {t:.2f}: Slide-Macro F1 = {f1:.4f}")
         if f1 > best_f1:

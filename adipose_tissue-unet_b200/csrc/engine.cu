@@ -1164,6 +1164,39 @@ int adp_threshold_metrics(adp_engine *e, const float *prob, const uint8_t *gt, i
   ADP_CATCH
 }
 
+int adp_threshold_sweep(adp_engine *e, const float *prob, const uint8_t *gt, int64_t n_px, const float *thresholds, int n_thr,
+                        int64_t *counts) {
+  ADP_TRY
+  ADP_REQUIRE(e && prob && gt && thresholds && counts && n_px > 0, "null/empty argument");
+  ADP_REQUIRE(n_thr >= 1 && n_thr <= 64, "1..64 candidate thresholds");
+  for (int i = 1; i < n_thr; ++i) ADP_REQUIRE(thresholds[i] > thresholds[i - 1], "thresholds must be strictly ascending");
+  ADP_CUDA(cudaSetDevice(e->device));
+  DevBuf dp, dg, dt, dh;
+  const size_t n = (size_t)n_px;
+  const float *p = reinterpret_cast<const float *>(to_device(e, dp, prob, n * 4));
+  const uint8_t *g = reinterpret_cast<const uint8_t *>(to_device(e, dg, gt, n));
+  dt.ensure((size_t)n_thr * 4); dh.ensure((size_t)2 * (n_thr + 1) * 8);
+  ADP_CUDA(cudaMemcpyAsync(dt.p, thresholds, (size_t)n_thr * 4, cudaMemcpyHostToDevice, e->stream));
+  ADP_CUDA(cudaMemsetAsync(dh.p, 0, (size_t)2 * (n_thr + 1) * 8, e->stream));
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>(cdiv64(n, 256 * 8), (size_t)e->num_sms * 8));
+  e->launch("threshold_sweep", 0, (double)n * 5, [&] {
+    threshold_sweep_kernel<<<grid, 256, 0, e->stream>>>(p, g, n, dt.as<float>(), n_thr, dh.as<unsigned long long>());
+  });
+  std::vector<unsigned long long> h((size_t)2 * (n_thr + 1));
+  ADP_CUDA(cudaMemcpyAsync(h.data(), dh.p, h.size() * 8, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  // predicted positive at threshold j  <=>  k > j
+  for (int j = 0; j < n_thr; ++j) {
+    unsigned long long tp = 0, fp = 0, fn = 0, tn = 0;
+    for (int k = 0; k <= n_thr; ++k) {
+      const unsigned long long neg = h[k], pos = h[(size_t)(n_thr + 1) + k];
+      if (k > j) { tp += pos; fp += neg; } else { fn += pos; tn += neg; }
+    }
+    counts[4 * j + 0] = (int64_t)tp; counts[4 * j + 1] = (int64_t)fp; counts[4 * j + 2] = (int64_t)fn; counts[4 * j + 3] = (int64_t)tn;
+  }
+  ADP_CATCH
+}
+
 int adp_blend_reconstruct(adp_engine *e, int blend_mode, const float *tiles, int n, int th, int tw, const int32_t *ys,
                           const int32_t *xs, const float *window, int H, int W, float *out) {
   ADP_TRY

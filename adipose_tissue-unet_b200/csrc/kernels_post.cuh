@@ -165,6 +165,36 @@ finalize_kernel(const float *__restrict__ acc, const float *__restrict__ wsum, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// Threshold sweep (optimize_threshold_f1[_slide_level], full_evaluation_enhanced.py:891-980: the reference re-runs
+// calculate_pixel_metrics for every candidate threshold).  One pass: every pixel is binned by k = number of candidate
+// thresholds strictly below its probability (p > thr_j  <=>  j < k for ascending thr) separately for gt = 0 / 1; the host
+// turns the two histograms into TP/FP/FN/TN of every candidate by suffix sums.  hist: [2][nthr + 1] unsigned 64-bit.
+__global__ void __launch_bounds__(256)
+threshold_sweep_kernel(const float *__restrict__ prob, const uint8_t *__restrict__ gt, size_t n, const float *__restrict__ thr,
+                       int nthr, unsigned long long *__restrict__ hist) {
+  __shared__ float st[64];
+  __shared__ unsigned int h[2][65];
+  for (int i = threadIdx.x; i < nthr; i += blockDim.x) st[i] = thr[i];
+  for (int i = threadIdx.x; i < 2 * 65; i += blockDim.x) (&h[0][0])[i] = 0;
+  __syncthreads();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float p = prob[i];
+    int lo = 0, hi = nthr;                 // k = first index with !(p > thr[k])  (thr ascending)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (p > st[mid]) lo = mid + 1; else hi = mid;
+    }
+    atomicAdd(&h[gt[i] != 0 ? 1 : 0][lo], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * 65; i += blockDim.x) {
+    const unsigned int v = (&h[0][0])[i];
+    const int c = i / 65, k = i % 65;
+    if (v && k <= nthr) atomicAdd(&hist[c * (nthr + 1) + k], (unsigned long long)v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Loss family of the reference (train_adipose_unet_v3.py:217-363) and dice_coef (src/utils/model.py:93-98):
 //   combined_loss_standard                       bce_mean(y, p) + dice_loss(y, p)
 //   combined_loss_with_label_smoothing           same on ys = y*(1 - eps_pos - eps_neg) + eps_neg          (:244-279)

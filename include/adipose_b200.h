@@ -122,6 +122,12 @@ int adp_debug_layer(adp_engine *e, const char *name, int idx, float *out, int64_
  * counts = {tp, fp, fn, tn}.  The ratios (+1e-10) are formed by the caller in float64. */
 int adp_threshold_metrics(adp_engine *e, const float *prob, const uint8_t *gt, int64_t n_px, float thr,
                           uint8_t *mask, int64_t counts[4]);
+/* TP/FP/FN/TN at every candidate threshold in ONE pass over (prob, gt): the reference's threshold search
+ * (optimize_threshold_f1_slide_level / optimize_threshold_f1, full_evaluation_enhanced.py:891-980) evaluates
+ * calculate_pixel_metrics once per candidate.  thresholds: n_thr (1..64) strictly ascending floats; gt: uint8, != 0 = positive;
+ * counts: n_thr x {tp, fp, fn, tn}, identical to n_thr calls of adp_threshold_metrics. */
+int adp_threshold_sweep(adp_engine *e, const float *prob, const uint8_t *gt, int64_t n_px, const float *thresholds, int n_thr,
+                        int64_t *counts);
 
 /* ---- blenders ----------------------------------------------------------------------------------
  * Replaces GaussianBlender.reconstruct / LinearBlender.reconstruct

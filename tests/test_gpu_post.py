@@ -138,3 +138,25 @@ def test_loss_recipes_vs_oracle(keep, eps):
     l2 = np.linalg.norm((g - gref).ravel()) / np.linalg.norm(gref.ravel())
     differ = (np.abs(g - gref) > 1e-6 * np.abs(gref).max() + 1e-9).mean()
     assert l2 <= 2e-3 and differ <= 1e-3, (l2, differ)
+
+
+def test_threshold_sweep_equals_per_threshold_counts():
+    """One-pass sweep (adp_threshold_sweep) == calculate_pixel_metrics per candidate threshold (the reference's search loop,
+    full_evaluation_enhanced.py:891-980), including probabilities that sit exactly on a candidate (strict >)."""
+    rng = np.random.default_rng(3)
+    eng = api.default_engine()
+    n = 300_007
+    p = rng.random(n).astype(np.float32)
+    thr = np.arange(0.1, 0.95, 0.05)                                   # the reference's default candidate range
+    t32 = thr.astype(np.float32)
+    p[:len(t32)] = t32                                                 # exactly on the candidates
+    p[len(t32):2 * len(t32)] = np.nextafter(t32, np.float32(1))        # one ulp above
+    gt = (rng.random(n) < 0.3).astype(np.uint8)
+    sweep = eng.threshold_sweep(p, gt, t32)
+    assert sweep.shape == (len(thr), 4)
+    for j, t in enumerate(t32):
+        _, counts = eng.threshold_metrics(p, gt, float(t), want_mask=False)
+        assert tuple(sweep[j]) == counts, (j, t)
+        ref = G.pixel_metrics(p, gt, float(t))
+        assert (ref["tp"], ref["fp"], ref["fn"], ref["tn"]) == counts
+    assert (sweep.sum(axis=1) == n).all()
