@@ -357,7 +357,7 @@ def run_ours(args, rank, world, local_rank):
             line["wsi"] = wsi_res
         if train_res is not None:
             line["train"] = train_res
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N=1 only
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if dist is not None:
