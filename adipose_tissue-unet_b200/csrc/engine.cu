@@ -524,7 +524,7 @@ void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs,
                    epi, L.bias.as<float>(), 1);
     return;
   }
-  dim3 grid(cdiv(Wo, 32), cdiv(Ho, 8), nb * (L.cout_pad / 16));
+  dim3 grid(cdiv(Wo, 32), cdiv(Ho, 16), nb * (L.cout_pad / 16));   // block (32, 8) covers 32 x 16 pixels
   dim3 block(32, 8);
   if (e->prec == ADP_PREC_FP32) {
     auto in = view<float>(src, Hs, Ws, spitch, scoff, L.cin_pad);

@@ -375,7 +375,7 @@ template <typename T> struct Bwd {
     TrainLayer &TL = tr->tl[li];
     View<T> out = gin;
     if (L.up) out = V(tr->g_hi, dz.H, L.cin_pad, 0, L.cin_pad);
-    dim3 grid(cdiv(dz.W, 32), cdiv(dz.H, 8), nb * (L.cin_pad / 16)), block(32, 8);
+    dim3 grid(cdiv(dz.W, 32), cdiv(dz.H, 16), nb * (L.cin_pad / 16)), block(32, 8);
     const double fl = conv_flops(L, dz.H, dz.W, nb);
     bool fused = false;
     if (e->prec == ADP_PREC_BF16 && !e->dgrad_simt) {
