@@ -54,3 +54,24 @@ def test_keras_adam_differs_from_torch_adam_only_by_eps_placement():
     # at t=1: m=(1-b1)g, v=(1-b2)g^2, alpha = lr*sqrt(1-b2)/(1-b1) -> step = lr*g/(|g| + eps/sqrt(1-b2)) approx
     expect = th - 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9) * (0.1 * g) / (np.sqrt(0.001 * g * g) + 1e-7)
     assert np.abs(t1 - expect).max() < 1e-6
+
+
+def test_two_independent_restatements_agree():
+    """oracle/unet.py (torch.nn.functional) against oracle/unet_numpy.py (plain NumPy float64 written from the Keras op
+    semantics): forward incl. all six dilations, both pools/upsamplings/concats, the softmax head and the
+    deep-supervision heads with the half-pixel bilinear resize."""
+    from oracle import unet_numpy as N
+    w = A.synth.init_weights(deep_supervision=True)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((2, 64, 64)).astype(np.float32)
+    with torch.no_grad():
+        pt, a1t, a2t = U.forward(torch.from_numpy(x).to(torch.float64), U.to_torch_params(w, torch.float64), deep_supervision=True)
+    pn, a1n, a2n = N.forward(x, w, deep_supervision=True)
+    assert np.abs(pt.numpy() - pn).max() < 1e-10
+    assert np.abs(a1t.numpy() - a1n).max() < 1e-10
+    assert np.abs(a2t.numpy() - a2n).max() < 1e-10
+    # the dilation-32 layer really sees its neighbours on a larger map (8x8 at 64^2 only ever reads the centre tap)
+    k = rng.standard_normal((3, 3, 3, 2)); b = rng.standard_normal(2); t = rng.standard_normal((1, 70, 70, 3))
+    ref = torch.nn.functional.conv2d(torch.from_numpy(t).permute(0, 3, 1, 2), torch.from_numpy(k).permute(3, 2, 0, 1),
+                                     torch.from_numpy(b), padding=32, dilation=32).permute(0, 2, 3, 1).numpy()
+    assert np.abs(N.conv2d_same(t, k, b, 32, relu=False) - ref).max() < 1e-10
