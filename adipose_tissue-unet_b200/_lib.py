@@ -15,8 +15,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libadipose_b200.so")
 
-PREC_FP32, PREC_BF16, PREC_BF16_SIMT = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16_simt": PREC_BF16_SIMT}
+PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_BF16X3 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16_simt": PREC_BF16_SIMT, "bf16x3": PREC_BF16X3}
 BLEND_GAUSSIAN, BLEND_LINEAR = 0, 1
 OPT_ADAM, OPT_ADAMW = 0, 1
 OPTIMIZERS = {"adam": OPT_ADAM, "adamw": OPT_ADAMW}

@@ -111,7 +111,8 @@ def make_model(weights_file: str, precision: str, device: int = 0, max_forwards:
 
 def add_engine_args(parser):
     g = parser.add_argument_group("B200 engine (not in the reference)")
-    g.add_argument("--precision", choices=["bf16", "fp32"], default="bf16",
-                   help="bf16 = tcgen05 tensor-core path (default); fp32 = exact CUDA-core path")
+    g.add_argument("--precision", choices=["bf16", "bf16x3", "fp32"], default="bf16",
+                   help="bf16 = tcgen05 tensor-core path (default, |dp| <= 1e-2); bf16x3 = hi/lo split on the tensor cores "
+                        "(|dp| <= 1e-4); fp32 = exact CUDA-core path")
     g.add_argument("--device", type=int, default=0)
     g.add_argument("--batch-tiles", type=int, default=16, help="tiles per device batch")

@@ -36,6 +36,8 @@
 // (B = [W(+1) | W(0) | W(-1)], N' = 3N) adds row i into all three at once: T+2 reads of A per horizontal tap instead of
 // 3T.  The first (chunk 0, kx 0) pass is issued unstacked because the accumulate flag is per instruction.
 //
+// bf16x3 precision (p.split): see ConvTcParams - three chunks per 16 input channels, hi/lo stores in the epilogue.
+//
 // Warp roles (320 threads): w0 producer (TMA + bulk copy), w1 MMA issuer (one elected lane) and
 // TMEM allocator, w2-9 epilogue: two warps per TMEM lane quarter, software-pipelined
 // tcgen05.ld -> bias -> ReLU -> bf16 -> coalesced row-planar stores.  Fused epilogues:
@@ -87,6 +89,13 @@ struct ConvTcParams {
   // block ([kx][cin/8][KY*N][8], vertical taps in DESCENDING order), tap_xs[kx] is the pixel shift of horizontal tap kx
   int kys;
   uint32_t idesc_stack[3];       // instruction descriptors for N, 2N, 3N
+  // bf16x3 ("split") precision: every activation / weight value v is carried as hi = bf16(v), lo = bf16(v - hi) (hi groups
+  // first, lo groups `*_lo` channel groups further in the same row-planar row) and a conv is the three bf16 GEMMs
+  // A_hi*W_hi + A_hi*W_lo + A_lo*W_hi accumulated in fp32 (max-abs probability error ~2e-5 vs float64, CPU simulation
+  // and tests/test_gpu_forward.py).  Implemented as THREE pipeline chunks per 16 input channels: nchunks and the packed
+  // weight blocks are tripled by the host ([W_hi, W_lo, W_hi] per chunk); chunk j reads A from group (j/3)*2 (+ in_lo for
+  // j%3 == 2).  The epilogue stores hi and lo.
+  int split, in_lo, out_lo, pool_lo;
   // backward use (data-gradient twin, EPI_STORE only): out = (acc + resid) * [mask > 0] * mask_scale, where resid and
   // mask are tensors with exactly the layout of `out` (gradient fan-in of Add / ReLU' of the producing layer)
   const __nv_bfloat16 *resid;
@@ -161,6 +170,21 @@ ADP_DEVINL void store16_bf16(__nv_bfloat16 *o, size_t plane, const float (&f)[16
   *reinterpret_cast<uint4 *>(o + plane) = *reinterpret_cast<uint4 *>(h + 8);
 }
 
+// hi/lo store of the bf16x3 precision: lo_elems = element distance between a value's hi and lo halves (0 = plain bf16)
+ADP_DEVINL void store16_out(__nv_bfloat16 *o, size_t lo_elems, size_t plane, const float (&f)[16]) {
+  if (lo_elems == 0) { store16_bf16(o, plane, f); return; }
+  __align__(16) __nv_bfloat16 h[16], l[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    h[i] = __float2bfloat16_rn(f[i]);
+    l[i] = __float2bfloat16_rn(f[i] - __bfloat162float(h[i]));
+  }
+  *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<uint4 *>(h);
+  *reinterpret_cast<uint4 *>(o + plane) = *reinterpret_cast<uint4 *>(h + 8);
+  *reinterpret_cast<uint4 *>(o + lo_elems) = *reinterpret_cast<uint4 *>(l);
+  *reinterpret_cast<uint4 *>(o + lo_elems + plane) = *reinterpret_cast<uint4 *>(l + 8);
+}
+
 template <int NTAPS, int T, bool KYS, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
@@ -216,9 +240,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
           // 8 = activations only for the first item, 1 = no epilogue stores, 4 = one MMA per stage, 16 = role timers
           const bool ld_b = !(p.dbg & 2) || item == (int)blockIdx.x, ld_a = !(p.dbg & 8) || item == (int)blockIdx.x;
           ptx::mbar_expect_tx(&full[st], (ld_a ? p.a_tx_bytes : 0u) + (ld_b ? p.b_bytes : 0u));
+          int cgc = c * 2;                                     // first channel group of this chunk
+          if (p.split) { const int cr = c / 3; cgc = cr * 2 + ((c - cr * 3) == 2 ? p.in_lo : 0); }
           if (ld_a)
             for (int b = 0; b < p.nbox; ++b)
-              ptx::tma_load_5d(sa + (size_t)b * p.a_box_stride, &tmap, &full[st], 0, xg, c * 2, ys + p.box_dy[b], n);
+              ptx::tma_load_5d(sa + (size_t)b * p.a_box_stride, &tmap, &full[st], 0, xg, cgc, ys + p.box_dy[b], n);
           if (ld_b) ptx::bulk_load_1d(sa + p.a_bytes, w0 + (size_t)c * blk_elems, p.b_bytes, &full[st]);
           if (++st == p.S) { st = 0; ph ^= 1; }
         }
@@ -485,7 +511,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = m[i] > 0.f ? f[i] * p.mask_scale : 0.f;
             }
-            store16_bf16(o, plane, f);
+            store16_out(o, (size_t)p.out_lo * plane, plane, f);
           }
         });
       } else if constexpr (EPI == EPI_HEAD) {
@@ -526,8 +552,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
           bias_relu16(rb, sb + cu * 16, p.relu, fb);
           const bool live = (ty * T + 2 * k + 1 < p.Hin) && (x < p.Win) && !(p.dbg & 1);
           if (live) {
-            store16_bf16(out_row(2 * k) + (size_t)(2 * cu) * plane, plane, fa);
-            store16_bf16(out_row(2 * k + 1) + (size_t)(2 * cu) * plane, plane, fb);
+            store16_out(out_row(2 * k) + (size_t)(2 * cu) * plane, (size_t)p.out_lo * plane, plane, fa);
+            store16_out(out_row(2 * k + 1) + (size_t)(2 * cu) * plane, (size_t)p.out_lo * plane, plane, fb);
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -538,7 +564,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
             const int py = (ty * T + 2 * k) >> 1, px = x >> 1;
             const size_t pplane = (size_t)(p.Wout >> 1) * 8;
             const size_t prow = ((size_t)n * (p.Hout >> 1) + py) * p.pool_cgs + p.pool_cg0 + p.var[v].out_cg;
-            store16_bf16(p.pool_out + prow * pplane + (size_t)px * 8 + (size_t)(2 * cu) * pplane, pplane, fa);
+            store16_out(p.pool_out + prow * pplane + (size_t)px * 8 + (size_t)(2 * cu) * pplane, (size_t)p.pool_lo * pplane, pplane, fa);
           }
         }
       }

@@ -149,6 +149,9 @@ struct adp_engine {
   int dbg = 0;
   bool fuse_head = true, fuse_pool = true;   // tcgen05 path only
   bool kys = true;                           // ky-stacked MMA issue for the N <= 128 layers
+  bool split = false;                        // ADP_PREC_BF16X3: hi/lo bf16 activations and weights, three GEMM passes (conv_tc.cuh)
+  int prec_public = 0;                       // what adp_precision() reports
+  int mul() const { return split ? 2 : 1; }  // physical channel groups per logical group
   LossRecipe loss;                           // adp_train_set_loss: hard-example mining / label smoothing of the training loss
   bool deep_sup = false;                     // adp_train_set_deep_supervision: aux_out1 / aux_out2 heads while training
   float ds_w[3] = {1.0f, 0.4f, 0.3f};        // loss weights main / aux1 / aux2 (train_adipose_unet_v3.py:858-872)
@@ -219,7 +222,7 @@ const char *const kAllNames[22] = {"down1_conv1", "down1_conv2", "down2_conv1", 
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 plan: everything of ConvTcParams that does not depend on the tile size
-void plan_tc(ConvLayer &L, bool allow_kys = true) {
+void plan_tc(ConvLayer &L, bool allow_kys = true, bool split = false) {
   ConvTcParams &p = L.tc;
   memset(&p, 0, sizeof(p));
   const int N = (L.cout_pad <= 256) ? L.cout_pad : L.cout_pad / 2;
@@ -259,7 +262,8 @@ void plan_tc(ConvLayer &L, bool allow_kys = true) {
     }
   }
   // one pipeline stage = 16 input channels: activation boxes + the weight blocks of all taps
-  p.nchunks = L.cin_pad / 16;
+  p.nchunks = (L.cin_pad / 16) * (split ? 3 : 1);      // bf16x3: chunks (A_hi,W_hi), (A_hi,W_lo), (A_lo,W_hi) per 16 channels
+  p.split = split ? 1 : 0;
   p.a_box_stride = (uint32_t)(((size_t)p.BR * 2 * p.PW * 16 + 127) / 128 * 128);
   p.a_bytes = (uint32_t)(((size_t)p.nbox * p.a_box_stride + 127) / 128 * 128);
   p.a_tx_bytes = (uint32_t)((size_t)p.nbox * p.BR * 2 * p.PW * 16);
@@ -329,7 +333,7 @@ void pack_layer(adp_engine *e, ConvLayer &L) {
   ADP_CUDA(cudaMemcpy(L.bias.p, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
   if (e->prec != ADP_PREC_BF16) return;
 
-  plan_tc(L, e->kys);
+  plan_tc(L, e->kys, e->split);
   const ConvTcParams &p = L.tc;
   std::vector<float> w32 = padded_weights(L, h, false);   // sum taps in fp32, round once
   auto W = [&](int t, int ci, int co) -> float { return w32[((size_t)t * L.cin_pad + ci) * L.cout_pad + co]; };
@@ -343,7 +347,8 @@ void pack_layer(adp_engine *e, ConvLayer &L) {
         for (int g = 0; g < 2; ++g)
           for (int n = 0; n < N; ++n)
             for (int j = 0; j < 8; ++j) {
-              const int ci = c * KC + g * 8 + j;
+              const int creal = p.split ? c / 3 : c, pass = p.split ? c % 3 : 0;
+              const int ci = creal * KC + g * 8 + j;
               float val = 0.f;
               if (ci < L.cin_pad) {
                 if (L.up) {
@@ -362,7 +367,9 @@ void pack_layer(adp_engine *e, ConvLayer &L) {
                   val = W(t, ci, p.var[v].out_cg * 8 + n);
                 }
               }
-              base[tc_block_index(p.kys, p.ntaps, N, t, g, n, j)] = __float2bfloat16_rn(val);
+              __nv_bfloat16 hv = __float2bfloat16_rn(val);
+              if (p.split && pass == 1) hv = __float2bfloat16_rn(val - __bfloat162float(hv));      // W_lo block
+              base[tc_block_index(p.kys, p.ntaps, N, t, g, n, j)] = hv;
             }
       }
   L.w_tc.ensure(pk.size() * 2);
@@ -404,7 +411,7 @@ void pack_all(adp_engine *e) {
 void ensure_arena(adp_engine *e, int S) {
   if (e->S == S) return;
   ADP_REQUIRE(S >= 8 && S % 8 == 0 && S <= 8192, "tile size must be a multiple of 8");
-  const size_t es = e->esz, nf = e->max_fw;
+  const size_t es = e->esz * e->mul(), nf = e->max_fw;      // bf16x3: hi + lo halves
   const size_t s1 = (size_t)S * S, s2 = s1 / 4, s3 = s1 / 16, s4 = s1 / 64;
   const int *cp = e->cp;
   e->a1.ensure(nf * s1 * cp[0] * es);   e->b1.ensure(nf * s1 * cp[0] * es);   e->cat1.ensure(nf * s1 * 2 * cp[0] * es);
@@ -430,7 +437,13 @@ void ensure_arena(adp_engine *e, int S) {
 // pitch / coff / C in channels (multiples of 8); the buffer is row-planar (kernels_simt.cuh)
 template <typename T> View<T> view(const DevBuf &b, int H, int W, int pitch, int coff, int C) {
   View<T> v;
-  v.p = b.as<T>(); v.H = H; v.W = W; v.cgs = pitch / 8; v.cg0 = coff / 8; v.C = C;
+  v.p = b.as<T>(); v.H = H; v.W = W; v.cgs = pitch / 8; v.cg0 = coff / 8; v.C = C; v.lo = 0;
+  return v;
+}
+// bf16x3: the buffer holds hi groups [0, pitch/8) and lo groups [pitch/8, 2*pitch/8) per pixel row
+template <typename T> View<T> view_split(const DevBuf &b, int H, int W, int pitch, int coff, int C) {
+  View<T> v;
+  v.p = b.as<T>(); v.H = H; v.W = W; v.cgs = 2 * pitch / 8; v.cg0 = coff / 8; v.C = C; v.lo = pitch / 8;
   return v;
 }
 
@@ -475,6 +488,13 @@ void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label,
                     int Ws, int s_cgs, int s_cg0, void *dst, int d_cgs, int d_cg0, int nb, int cap, const EpiSpec &epi,
                     const float *bias, int relu) {
   ConvTcParams p = L.tc;
+  // bf16x3: s_cgs / d_cgs arrive as LOGICAL groups per row; the buffers hold 2x that, lo halves start one logical pitch later
+  p.in_lo = 0; p.out_lo = 0; p.pool_lo = 0;
+  if (p.split) {
+    ADP_REQUIRE(!epi.mask && !epi.resid, "bf16x3 precision is inference-only");
+    p.in_lo = s_cgs; p.out_lo = d_cgs;
+    s_cgs *= 2; d_cgs *= 2;
+  }
   const int Ho = L.up ? Hs * 2 : Hs, Wo = L.up ? Ws * 2 : Ws;
   p.nb = nb; p.Hin = Hs; p.Win = Ws;
   p.ntx = cdiv(Ws, 128); p.nty = cdiv(Hs, p.T);
@@ -492,8 +512,11 @@ void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label,
   } else if (epi.mode == EPI_POOL) {
     ADP_REQUIRE(p.T % 2 == 0 && p.oscale == 1 && Ho % 2 == 0 && Wo % 2 == 0, "pool fusion needs an even row block");
     p.pool_out = epi.pool_dst->as<__nv_bfloat16>(); p.pool_cgs = L.cout_pad / 8; p.pool_cg0 = 0;
+    if (p.split) { p.pool_lo = p.pool_cgs; p.pool_cgs *= 2; }
   }
-  const CUtensorMap &tm = tmap_for(e, src, Hs, Ws, s_cgs, s_cg0, L.cin_pad, cap, p.PW / 8, 2, p.BR);
+  // bf16x3: the map spans hi and lo groups of the view (groups in between belong to other tensors of a concat buffer)
+  const int map_C = p.split ? (p.in_lo + L.cin_pad / 8) * 8 : L.cin_pad;
+  const CUtensorMap &tm = tmap_for(e, src, Hs, Ws, s_cgs, s_cg0, map_C, cap, p.PW / 8, 2, p.BR);
   const int nitems = nb * p.nty * p.ntx * p.nvar;
   const int grid = std::min(nitems, e->num_sms);
   const size_t smem = tc_smem_bytes(p);
@@ -545,8 +568,8 @@ void run_conv(adp_engine *e, const std::string &name, const DevBuf &src, int Hs,
 
 template <typename T>
 void run_pool(adp_engine *e, const DevBuf &src, int Hs, int Ws, int spitch, int C, const DevBuf &dst, int nb) {
-  auto in = view<T>(src, Hs, Ws, spitch, 0, C);
-  auto out = view<T>(dst, Hs / 2, Ws / 2, C, 0, C);
+  auto in = e->split ? view_split<T>(src, Hs, Ws, spitch, 0, C) : view<T>(src, Hs, Ws, spitch, 0, C);
+  auto out = e->split ? view_split<T>(dst, Hs / 2, Ws / 2, C, 0, C) : view<T>(dst, Hs / 2, Ws / 2, C, 0, C);
   const size_t total = (size_t)nb * (Hs / 2) * (Ws / 2) * (C / 8);
   const int grid = (int)std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 16);
   e->launch("maxpool2x2", 0, (double)nb * Hs * Ws * C * sizeof(T) * 1.25, [&] {
@@ -585,7 +608,7 @@ template <typename T> void forward_t(adp_engine *e, const Acts &A, int S, const 
   const float mean_f = mean;
   const float sd_f = (float)((double)std_ + 1e-10);
   {
-    auto out = view<T>(*A.d1a, S, S, cp[0], 0, cp[0]);
+    auto out = e->split ? view_split<T>(*A.d1a, S, S, cp[0], 0, cp[0]) : view<T>(*A.d1a, S, S, cp[0], 0, cp[0]);
     dim3 grid(cdiv(S, 32), cdiv(S, 32), nfw), block(32, 8);
     const size_t smem = ((size_t)10 * cp[0] + 34 * 34) * 4;
     e->launch("first_conv", 2.0 * nfw * S * S * 9.0 * e->c[0], (double)nfw * S * S * (4 + cp[0] * sizeof(T)), [&] {
@@ -596,8 +619,8 @@ template <typename T> void forward_t(adp_engine *e, const Acts &A, int S, const 
   const bool tc = e->prec == ADP_PREC_BF16;
   const bool dropping = drop && (drop->keep < 1.f || drop->mask[0]);
   EpiSpec pool1, pool2, head;
-  if (tc && e->fuse_pool) { pool1.mode = EPI_POOL; pool1.pool_dst = A.pl1; pool2.mode = EPI_POOL; pool2.pool_dst = A.pl2; }
-  if (tc && e->fuse_head && !drop) { head.mode = EPI_HEAD; head.prob = A.prob->as<float>(); }   // training keeps up1_conv3
+  if (tc && (e->fuse_pool || e->split)) { pool1.mode = EPI_POOL; pool1.pool_dst = A.pl1; pool2.mode = EPI_POOL; pool2.pool_dst = A.pl2; }
+  if (tc && (e->fuse_head || e->split) && !drop) { head.mode = EPI_HEAD; head.prob = A.prob->as<float>(); }   // training keeps up1_conv3
   if (input_consumed) ADP_CUDA(cudaEventRecord(input_consumed, e->stream));
   run_conv(e, "down1_conv2", *A.d1a, S, S, cp[0], 0, *A.cat1, 2 * cp[0], 0, nfw, cap, pool1);
   if (pool1.mode != EPI_POOL) run_pool<T>(e, *A.cat1, S, S, 2 * cp[0], cp[0], *A.pl1, nfw);
@@ -611,7 +634,17 @@ template <typename T> void forward_t(adp_engine *e, const Acts &A, int S, const 
   if (dropping) run_dropout<T>(e, *A.t[0], S4, cp[3], c[3], nfw, *drop, 0);
   const char *dn[5] = {"dilate2", "dilate3", "dilate4", "dilate5", "dilate6"};
   for (int i = 0; i < 5; ++i) run_conv(e, dn[i], *A.t[i], S4, S4, cp[3], 0, *A.t[i + 1], cp[3], 0, nfw, cap);
-  {
+  if (e->split) {
+    // hi/lo tensors: the six values are recombined in fp32, summed and split again
+    View<T> v[6];
+    for (int i = 0; i < 6; ++i) v[i] = view_split<T>(*A.t[i], S4, S4, cp[3], 0, cp[3]);
+    auto o = view_split<T>(*A.ts, S4, S4, cp[3], 0, cp[3]);
+    const size_t total = (size_t)nfw * S4 * S4 * (cp[3] / 8);
+    e->launch("add6", 0, (double)total * 32 * 7, [&] {
+      add6_split_kernel<T><<<(int)std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 16), 256, 0, e->stream>>>(
+          v[0], v[1], v[2], v[3], v[4], v[5], o, nfw);
+    });
+  } else {
     const size_t nvec = (size_t)nfw * S4 * S4 * cp[3] * sizeof(T) / 16;
     const int grid = (int)std::min<size_t>(cdiv64(nvec, 256), (size_t)e->num_sms * 16);
     e->launch("add6", 0, (double)nvec * 16 * 7, [&] {
@@ -908,7 +941,7 @@ int adp_device_count(void) {
 int adp_create(int device, int precision, int init_nb, int max_forwards, adp_engine **out) {
   ADP_TRY
   ADP_REQUIRE(out, "out is null");
-  ADP_REQUIRE(precision >= 0 && precision <= 2, "precision");
+  ADP_REQUIRE(precision >= 0 && precision <= 3, "precision");
   if (init_nb <= 0) init_nb = 44;
   ADP_REQUIRE(init_nb % 4 == 0 && init_nb <= 64, "init_nb must be a multiple of 4, at most 64");
   int n = 0;
@@ -919,7 +952,10 @@ int adp_create(int device, int precision, int init_nb, int max_forwards, adp_eng
   if (pr.major != 10) throw Error(ADP_ENODEV, std::string("device is sm_") + std::to_string(pr.major * 10 + pr.minor) + ", this library is sm_100a only");
   ADP_CUDA(cudaSetDevice(device));
   std::unique_ptr<adp_engine> e(new adp_engine());
-  e->device = device; e->prec = precision; e->init_nb = init_nb;
+  e->device = device; e->prec_public = precision; e->init_nb = init_nb;
+  e->split = precision == ADP_PREC_BF16X3;
+  e->prec = e->split ? ADP_PREC_BF16 : precision;       // bf16x3 runs the tcgen05 path on hi/lo bf16 tensors
+  precision = e->prec;
   e->max_fw = max_forwards > 0 ? std::min(max_forwards, 64) : 16;
   e->num_sms = pr.multiProcessorCount;
   e->esz = precision == ADP_PREC_FP32 ? 4 : 2;
@@ -967,7 +1003,7 @@ int adp_destroy(adp_engine *e) {
   ADP_CATCH
 }
 
-int adp_precision(const adp_engine *e) { return e ? e->prec : ADP_EINVAL; }
+int adp_precision(const adp_engine *e) { return e ? e->prec_public : ADP_EINVAL; }
 
 int adp_synchronize(adp_engine *e) {
   ADP_TRY
@@ -1138,17 +1174,19 @@ int adp_debug_layer(adp_engine *e, const char *name, int idx, float *out, int64_
   shape_hwc[0] = t.H; shape_hwc[1] = t.H; shape_hwc[2] = t.C;
   if (!out) return ADP_OK;
   ADP_REQUIRE(out_elems == (int64_t)t.H * t.H * t.C, "out_elems");
-  const size_t npx = (size_t)t.H * t.H, img = npx * t.pitch * e->esz;
+  const size_t npx = (size_t)t.H * t.H, img = npx * t.pitch * e->esz * e->mul();
   std::vector<uint8_t> host(img);
   ADP_CUDA(cudaMemcpy(host.data(), (const uint8_t *)t.b->p + (size_t)idx * img, img, cudaMemcpyDeviceToHost));
-  const int W = t.H, cgs = t.pitch / 8;
+  const int W = t.H, cgs = t.pitch / 8 * e->mul(), lo = e->split ? t.pitch / 8 : 0;     // bf16x3: value = hi + lo
   for (int y = 0; y < t.H; ++y)
     for (int x = 0; x < W; ++x)
       for (int ch = 0; ch < t.C; ++ch) {
         const int cc = t.coff + ch;       // row-planar: (((y*cgs + cg)*W + x)*8 + c%8
         const size_t si = (((size_t)y * cgs + cc / 8) * W + x) * 8 + cc % 8;
-        out[((size_t)y * W + x) * t.C + ch] = e->esz == 4 ? reinterpret_cast<const float *>(host.data())[si]
-                                                          : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(host.data())[si]);
+        float v = e->esz == 4 ? reinterpret_cast<const float *>(host.data())[si]
+                              : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(host.data())[si]);
+        if (lo) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(host.data())[si + (size_t)lo * W * 8]);
+        out[((size_t)y * W + x) * t.C + ch] = v;
       }
   ADP_CATCH
 }
@@ -1402,6 +1440,7 @@ int adp_train_begin(adp_engine *e, int batch, int size, float dropout_rate, uint
   ADP_TRY
   ADP_REQUIRE(e, "engine");
   ADP_CUDA(cudaSetDevice(e->device));
+  if (e->split) throw Error(ADP_EINVAL, "the bf16x3 precision is inference-only; train with bf16 or fp32");
   if (e->tr) { sync_host_weights(e); delete e->tr; e->tr = nullptr; }
   e->tmaps.clear();
   train_alloc(e, batch, size, dropout_rate, seed);

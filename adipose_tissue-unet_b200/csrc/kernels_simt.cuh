@@ -21,6 +21,7 @@ template <typename T> struct View {
   int cgs;       // channel groups (of 8) per pixel row in the underlying buffer
   int cg0;       // first channel group of this view
   int C;         // channels of the view (multiple of 16)
+  int lo;        // bf16x3 precision: channel-group distance from a value's hi half to its lo half (0 = plain tensor)
   __host__ __device__ size_t img_stride() const { return (size_t)H * cgs * W * 8; }
   // element offset of (image n, row y, channel group g of the view, column x)
   __host__ __device__ size_t at(int n, int y, int g, int x) const {
@@ -61,6 +62,30 @@ template <typename T> ADP_DEVINL void store8(T *o, const float *a) {
   } else {
     *reinterpret_cast<float4 *>(o) = make_float4(a[0], a[1], a[2], a[3]);
     *reinterpret_cast<float4 *>(o + 4) = make_float4(a[4], a[5], a[6], a[7]);
+  }
+}
+// hi/lo access of the bf16x3 precision: value = hi + lo; a store splits v into hi = bf16(v), lo = bf16(v - hi)
+template <typename T> ADP_DEVINL void load8(const T *i, float *a);
+template <typename T> ADP_DEVINL void load8v(const View<T> &v, int n, int y, int g, int x, float *a) {
+  const T *p = v.p + v.at(n, y, g, x);
+  load8<T>(p, a);
+  if (v.lo) {
+    float l[8];
+    load8<T>(p + (size_t)v.lo * v.W * 8, l);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] += l[c];
+  }
+}
+template <typename T> ADP_DEVINL void store8v(const View<T> &v, int n, int y, int g, int x, const float *a) {
+  T *p = v.p + v.at(n, y, g, x);
+  store8<T>(p, a);
+  if constexpr (sizeof(T) == 2) {
+    if (v.lo) {
+      float l[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) l[c] = a[c] - __bfloat162float(__float2bfloat16_rn(a[c]));
+      store8<T>(p + (size_t)v.lo * v.W * 8, l);
+    }
   }
 }
 template <typename T> ADP_DEVINL void load8(const T *i, float *a) {
@@ -137,7 +162,7 @@ first_conv_kernel(FirstConvSrc src, const int *__restrict__ fw_tile, const int *
       if (yb + r >= S) break;
 #pragma unroll
       for (int c = 0; c < 8; ++c) a[r][c] = fmaxf(a[r][c], 0.f);
-      store8<T>(out.p + out.at(f, yb + r, g, x), a[r]);
+      store8v<T>(out, f, yb + r, g, x, a[r]);
     }
   }
 }
@@ -242,15 +267,13 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(View<T> in, View<T> out, 
     int y = r % out.H;
     int n = r / out.H;
     float a[8], b[8], c[8], d[8], m[8];
-    const T *ip = in.p + in.at(n, 2 * y, g, 2 * x);
-    load8<T>(ip, a);
-    load8<T>(ip + 8, b);
-    const T *ip2 = in.p + in.at(n, 2 * y + 1, g, 2 * x);
-    load8<T>(ip2, c);
-    load8<T>(ip2 + 8, d);
+    load8v<T>(in, n, 2 * y, g, 2 * x, a);
+    load8v<T>(in, n, 2 * y, g, 2 * x + 1, b);
+    load8v<T>(in, n, 2 * y + 1, g, 2 * x, c);
+    load8v<T>(in, n, 2 * y + 1, g, 2 * x + 1, d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) m[k] = fmaxf(fmaxf(a[k], b[k]), fmaxf(c[k], d[k]));
-    store8<T>(out.p + out.at(n, y, g, x), m);
+    store8v<T>(out, n, y, g, x, m);
   }
 }
 
@@ -275,6 +298,37 @@ add6_kernel(const T *a0, const T *a1, const T *a2, const T *a3, const T *a4, con
       o[k] = from_f<T>(s);
     }
     reinterpret_cast<uint4 *>(out)[i] = *reinterpret_cast<uint4 *>(o);
+  }
+}
+
+// Add of six hi/lo tensors (bf16x3 precision): recombine, sum in fp32, split again.  One thread per pixel and channel group.
+template <typename T>
+__global__ void __launch_bounds__(256)
+add6_split_kernel(View<T> a0, View<T> a1, View<T> a2, View<T> a3, View<T> a4, View<T> a5, View<T> out, int nb) {
+  const int G = out.C / 8;
+  const size_t total = (size_t)nb * out.H * G * out.W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = i % out.W; size_t r = i / out.W;
+    const int g = r % G; r /= G;
+    const int y = r % out.H, n = r / out.H;
+    float s[8], t[8];
+    load8v<T>(a0, n, y, g, x, s);
+    load8v<T>(a1, n, y, g, x, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += t[k];
+    load8v<T>(a2, n, y, g, x, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += t[k];
+    load8v<T>(a3, n, y, g, x, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += t[k];
+    load8v<T>(a4, n, y, g, x, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += t[k];
+    load8v<T>(a5, n, y, g, x, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += t[k];
+    store8v<T>(out, n, y, g, x, s);
   }
 }
 

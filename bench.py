@@ -329,7 +329,7 @@ def run_ours(args, rank, world, local_rank):
         import adipose_unet_b200.layers as L
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "dtype": {"bf16": "bf16", "bf16_simt": "bf16", "bf16x3": "bf16x3"}.get(args.precision, "f32"), "data": "synthetic",
                 "config": {"workload": "configs[1]: 16 x 1024^2 ECM tiles per GPU, 8-way TTA (128 U-Net forwards), "
                                        "softmax head, TTA mean, threshold 0.5, TP/FP/FN/TN vs synthetic masks",
                            "tiles_per_step_per_gpu": BATCH_TILES, "tta": "full(8)", "precision": args.precision,
@@ -391,7 +391,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16_simt"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16_simt", "bf16x3"])
     ap.add_argument("--max-forwards", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-batch", type=int, default=8, help="tiles per GPU of the secondary training-step run (0 = skip)")

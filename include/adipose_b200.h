@@ -40,6 +40,9 @@ extern "C" {
 #define ADP_PREC_FP32 0       /* fp32 activations, CUDA-core FFMA convs (exact-fp32 parity path) */
 #define ADP_PREC_BF16 1       /* bf16 activations, tcgen05/TMEM implicit-GEMM convs, fp32 accumulate */
 #define ADP_PREC_BF16_SIMT 2  /* bf16 activations, CUDA-core convs (cross-check of the tcgen05 path) */
+#define ADP_PREC_BF16X3 3     /* fp32-class accuracy on the tensor cores: values carried as hi+lo bf16, a conv is the three
+                                 bf16 GEMMs hi*hi + hi*lo + lo*hi with fp32 accumulation (inference only; max-abs
+                                 probability error ~2e-5 vs float64, the <= 1e-4 "fp32/TF32 path" of BASELINE.json) */
 
 /* blend modes — GaussianBlender / LinearBlender, Segmentation/full_evaluation_enhanced.py:115-204 */
 #define ADP_BLEND_GAUSSIAN 0

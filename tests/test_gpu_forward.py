@@ -13,7 +13,7 @@ from oracle import geometry as G
 from oracle import unet as U
 
 MEAN, STD = A.synth.DEFAULT_MEAN, A.synth.DEFAULT_STD
-TOL = {"fp32": 1e-4, "bf16": 1e-2, "bf16_simt": 1e-2}
+TOL = {"fp32": 1e-4, "bf16": 1e-2, "bf16_simt": 1e-2, "bf16x3": 1e-4}     # bf16x3: the tensor-core path of the 1e-4 row
 LAYER_TAPS = ["down1_conv2", "down2_conv2", "down3_conv2", "dilate1", "dilate2", "dilate3", "dilate4", "dilate5",
               "dilate6", "dilate_add", "up3_conv1", "up3_conv2", "up3_conv3", "up2_conv1", "up2_conv2", "up2_conv3",
               "up1_conv1", "up1_conv2", "up1_conv3"]
@@ -46,7 +46,7 @@ def mask_dice(a, b):
     return (2.0 * (a & b).sum() + 1e-10) / (a.sum() + b.sum() + 1e-10)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16_simt", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16_simt", "bf16", "bf16x3"])
 def test_per_layer_256(prec, weights, params):
     S = 256
     tile = A.synth.ecm_tile(S, seed=21).astype(np.float32)
@@ -58,9 +58,11 @@ def test_per_layer_256(prec, weights, params):
     if prec == "bf16":      # un-fused first so that every intermediate tensor exists in HBM
         m.engine.set_option("fuse_head", 0); m.engine.set_option("fuse_pool", 0)
     out = m.predict_single(tile, MEAN, STD)
-    rel_tol = 1e-4 if prec == "fp32" else 3e-2
+    rel_tol = {"fp32": 1e-4, "bf16x3": 2e-4}.get(prec, 3e-2)
     worst = {}
     for name in LAYER_TAPS:
+        if prec == "bf16x3" and name == "up1_conv3":
+            continue            # always fused with the head on this path: the tensor never reaches HBM
         ref = taps[name][0].permute(1, 2, 0).numpy()
         got = m.engine.debug_layer(name, 0)
         assert got.shape == ref.shape, name
@@ -84,7 +86,7 @@ def test_per_layer_256(prec, weights, params):
         assert np.abs(out_f - out).max() <= 5e-3
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16x3"])
 def test_tta_full_256(prec, weights, params):
     S = 256
     tile = A.synth.ecm_tile(S, seed=22).astype(np.float32)
@@ -93,11 +95,11 @@ def test_tta_full_256(prec, weights, params):
     out, info = m.predict(tile, MEAN, STD, use_tta=True, tta_mode="full")
     assert info["num_augmentations"] == 8
     assert np.abs(out - ref).max() <= TOL[prec]
-    if prec == "fp32":
+    if prec in ("fp32", "bf16x3"):
         assert mask_dice(out, ref) >= 0.999
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16x3"])
 def test_batch_and_modes_128(prec, weights, params):
     S = 128
     tiles = A.synth.ecm_tiles(5, S, seed=30)
@@ -128,18 +130,18 @@ def test_full_size_1024_fp32_and_bf16(weights, params):
     """BASELINE config 1: one 1024^2 ECM tile, batch 1."""
     tile = A.synth.ecm_tile(1024).astype(np.float32)
     ref = U.predict_single(tile, MEAN, STD, params)
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "bf16", "bf16x3"):
         out = model(prec, weights).predict_single(tile, MEAN, STD)
         err = float(np.abs(out - ref).max())
         assert err <= TOL[prec], (prec, err)
         d = mask_dice(out, ref)
         band = float((np.abs(ref - 0.5) < TOL[prec]).mean())
         print(f"1024^2 {prec}: max|dp|={err:.2e} mask-dice={d:.5f} px within tol of 0.5: {band:.4%}")
-        if prec == "fp32":
+        if prec in ("fp32", "bf16x3"):
             assert d >= 0.999
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16x3"])
 def test_sliding_window_native(prec, weights, params):
     S = 128
     img = A.synth.synthetic_slide(300, 420, block=128).astype(np.float32)
