@@ -64,7 +64,7 @@ def _run(engine, slide, overlap, blend, tta, world):
     return probs, masks, counts, gt
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("bf16", 1e-2), ("bf16x3", 1e-4)])
 def test_wsi_from_slide_vs_oracle(setup, prec, tol):
     w, slide, params = setup
     eng = api.Engine(precision=prec, max_forwards=16)
