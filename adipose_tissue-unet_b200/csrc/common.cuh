@@ -43,16 +43,15 @@ template <> ADP_DEVINL __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __f
 
 // Dihedral source index: aug[i][j] = img[src(i,j)]  (op codes in adipose_b200.h)
 ADP_DEVINL void d4_src(int op, int i, int j, int n, int &si, int &sj) {
-  switch (op) {
-    case 0: si = i; sj = j; break;
-    case 1: si = j; sj = n - 1 - i; break;
-    case 2: si = n - 1 - i; sj = n - 1 - j; break;
-    case 3: si = n - 1 - j; sj = i; break;
-    case 4: si = i; sj = n - 1 - j; break;
-    case 5: si = n - 1 - i; sj = j; break;
-    case 6: si = n - 1 - j; sj = n - 1 - i; break;
-    default: si = j; sj = i; break;
-  }
+  // branch-free: 3 bits per op = (transpose, mirror the row index, mirror the column index)
+  //   0: (i, j)         1: (j, n-1-i)     2: (n-1-i, n-1-j)  3: (n-1-j, i)
+  //   4: (i, n-1-j)     5: (n-1-i, j)     6: (n-1-j, n-1-i)  7: (j, i)
+  // (an 8-way switch compiles to ~16 predicated compares per call, which made the TTA kernel instruction-bound)
+  constexpr unsigned kTable = (0u << 0) | (5u << 3) | (6u << 6) | (3u << 9) | (4u << 12) | (2u << 15) | (7u << 18) | (1u << 21);
+  const unsigned b = (kTable >> (3 * (op & 7))) & 7u;
+  const int u = (b & 1u) ? j : i, v = (b & 1u) ? i : j;
+  si = (b & 2u) ? n - 1 - u : u;
+  sj = (b & 4u) ? n - 1 - v : v;
 }
 __host__ __device__ inline int d4_inverse(int op) {
   return op == 1 ? 3 : (op == 3 ? 1 : op);

@@ -799,8 +799,10 @@ void run_finalize(adp_engine *e, const float *acc, const float *wsum, int linear
   const int grid = (int)std::min<size_t>(cdiv64(n, 256 * 4), (size_t)e->num_sms * 8);
   const double by = (double)n * ((wsum ? 8 : 4) + (dp ? 4 : 0) + (dm ? 1 : 0) + (dg ? 1 : 0));
   e->launch("finalize_threshold_metrics", 0, by, [&] {
+    auto al = [](const void *q, size_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
+    const int vec = al(acc, 16) && al(wsum, 16) && al(dp, 16) && al(dm, 4) && al(dg, 4);
     finalize_kernel<<<std::max(grid, 1), 256, 0, e->stream>>>(acc, wsum, linear, n, thr, dp, dm, dg,
-                                                             e->counts.as<unsigned long long>());
+                                                             e->counts.as<unsigned long long>(), vec);
   });
   if (prob_host) ADP_CUDA(cudaMemcpyAsync(prob, dp, n * 4, cudaMemcpyDeviceToHost, e->stream));
   if (mask_host) ADP_CUDA(cudaMemcpyAsync(mask, dm, n, cudaMemcpyDeviceToHost, e->stream));

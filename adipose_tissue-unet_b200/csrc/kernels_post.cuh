@@ -21,53 +21,41 @@ namespace adp {
 // mode 2: linear blend:   acc += avg; wsum(count as float) += 1   (LinearBlender, :196-199)
 struct TtaOps { int n; int inv[8]; };
 
+// (Requesting 4 or 8 augmentations' source blocks per barrier was tried and measured slower: 35-60 us instead of 26 us per
+// 1024^2 tile, so the kernel walks one plane at a time.)
 __global__ void __launch_bounds__(256)
 tta_blend_kernel(const float *__restrict__ planes, TtaOps ops, int S, int mode, float *__restrict__ out,
                  float *__restrict__ acc, float *__restrict__ wsum, const float *__restrict__ window,
                  int accW, int accRows, int ty, int tx) {
-  // the source blocks of four augmentations are requested before each barrier: two HBM round trips per block instead
-  // of eight, at 17 KB of shared memory (eight resident blocks per SM keep the 1024-block grid a single wave)
-  __shared__ float tile[4][32][33];
+  __shared__ float tile[32][33];
   const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
   const int lx = threadIdx.x, ly = threadIdx.y;     // 32 x 8
-  float sum[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < ops.n; k0 += 4) {
-    int sbi[4], sbj[4];
-    if (k0) __syncthreads();
+  float sum[4];
+  for (int k = 0; k < ops.n; ++k) {
+    const int op = ops.inv[k];
+    // source block origin: image of the block's (bi,bj) corner region under op
+    int s0i, s0j, s1i, s1j;
+    d4_src(op, bi, bj, S, s0i, s0j);
+    d4_src(op, min(bi + 31, S - 1), min(bj + 31, S - 1), S, s1i, s1j);
+    const int sbi = min(s0i, s1i), sbj = min(s0j, s1j);
+    const float *P = planes + (size_t)k * S * S;
+    __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int k = k0 + q;
-      if (k < ops.n) {
-        // source block origin: image of the block's (bi,bj) corner region under op
-        int s0i, s0j, s1i, s1j;
-        d4_src(ops.inv[k], bi, bj, S, s0i, s0j);
-        d4_src(ops.inv[k], min(bi + 31, S - 1), min(bj + 31, S - 1), S, s1i, s1j);
-        sbi[q] = min(s0i, s1i); sbj[q] = min(s0j, s1j);
-        const float *P = planes + (size_t)k * S * S;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int i = sbi[q] + ly + 8 * r, j = sbj[q] + lx;
-          tile[q][ly + 8 * r][lx] = (i < S && j < S) ? P[(size_t)i * S + j] : 0.f;
-        }
-      }
+    for (int r = 0; r < 4; ++r) {
+      int i = sbi + ly + 8 * r, j = sbj + lx;
+      tile[ly + 8 * r][lx] = (i < S && j < S) ? P[(size_t)i * S + j] : 0.f;
     }
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int k = k0 + q;
-      if (k < ops.n) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int i = bi + ly + 8 * r, j = bj + lx;
-          float v = 0.f;
-          if (i < S && j < S) {
-            int si, sj;
-            d4_src(ops.inv[k], i, j, S, si, sj);
-            v = tile[q][si - sbi[q]][sj - sbj[q]];
-          }
-          sum[r] = (k == 0) ? v : __fadd_rn(sum[r], v);
-        }
+    for (int r = 0; r < 4; ++r) {
+      int i = bi + ly + 8 * r, j = bj + lx;
+      float v = 0.f;
+      if (i < S && j < S) {
+        int si, sj;
+        d4_src(op, i, j, S, si, sj);
+        v = tile[si - sbi][sj - sbj];
       }
+      sum[r] = (k == 0) ? v : __fadd_rn(sum[r], v);
     }
   }
   const float nf = (float)ops.n;
@@ -134,21 +122,41 @@ add_partial_kernel(float *__restrict__ acc, float *__restrict__ wsum, const floa
 //   raw (acc only, wsum == null): p = acc           (adp_threshold_metrics)
 // mask = p > thr (strict, :716-718); truth = gt > 0.5 -> gt != 0 for uint8 masks (:737).
 // counts[0..3] = tp, fp, fn, tn  (unsigned 64-bit atomics, one per warp after shuffle reduction)
+ADP_DEVINL float finalize_value(float a, float w, bool has_w, int linear) {
+  if (!has_w) return a;
+  if (linear) return (float)((double)a / (double)fmaxf(w, 1.0f));
+  return __fdiv_rn(a, fmaxf(w, 1e-8f));
+}
+
+// vec != 0: every pointer is 16-byte (float) / 4-byte (uint8) aligned - four pixels per thread through 128-bit / 32-bit
+// accesses (the byte-wide scalar form reached 21 % of DRAM peak); the tail (n % 4) and unaligned calls take the scalar path.
 __global__ void __launch_bounds__(256)
 finalize_kernel(const float *__restrict__ acc, const float *__restrict__ wsum, int linear, size_t n, float thr,
                 float *__restrict__ prob, uint8_t *__restrict__ mask, const uint8_t *__restrict__ gt,
-                unsigned long long *__restrict__ counts) {
+                unsigned long long *__restrict__ counts, int vec) {
   unsigned tp = 0, fp = 0, fn = 0, tn = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    float p = acc[i];
-    if (wsum) {
-      if (linear) {
-        float c = fmaxf(wsum[i], 1.0f);
-        p = (float)((double)p / (double)c);
-      } else {
-        p = __fdiv_rn(p, fmaxf(wsum[i], 1e-8f));
-      }
+  const size_t nq = vec ? n / 4 : 0;
+  for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
+    const float4 a4 = reinterpret_cast<const float4 *>(acc)[q];
+    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (wsum) w4 = reinterpret_cast<const float4 *>(wsum)[q];
+    const float a[4] = {a4.x, a4.y, a4.z, a4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+    uchar4 g4 = make_uchar4(0, 0, 0, 0);
+    if (gt) g4 = reinterpret_cast<const uchar4 *>(gt)[q];
+    const unsigned char g[4] = {g4.x, g4.y, g4.z, g4.w};
+    float p[4]; unsigned char m[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      p[k] = finalize_value(a[k], w[k], wsum != nullptr, linear);
+      const bool pb = p[k] > thr, tb = gt ? (g[k] != 0) : false;
+      m[k] = pb ? 1 : 0;
+      tp += (pb && tb); fp += (pb && !tb); fn += (!pb && tb); tn += (!pb && !tb);
     }
+    if (prob) reinterpret_cast<float4 *>(prob)[q] = make_float4(p[0], p[1], p[2], p[3]);
+    if (mask) reinterpret_cast<uchar4 *>(mask)[q] = make_uchar4(m[0], m[1], m[2], m[3]);
+  }
+  for (size_t i = nq * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float p = finalize_value(acc[i], wsum ? wsum[i] : 0.f, wsum != nullptr, linear);
     if (prob) prob[i] = p;
     const bool pb = p > thr;
     if (mask) mask[i] = pb ? 1 : 0;
