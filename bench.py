@@ -322,6 +322,31 @@ def run_ours(args, rank, world, local_rank):
                      if world > 1 else "none (1 GPU)", "collective_path": tr.collective_path}
         tr.close()
 
+    # secondary measurement (rank 0, N=1): the <= 1e-4 tensor-core path (precision "bf16x3", hi/lo-split bf16, three GEMM passes)
+    # on the same batch, and how far the headline bf16 probabilities are from it
+    x3_res = None
+    if rank == 0 and world == 1 and args.precision == "bf16" and not args.no_x3:
+        prob_bf16 = prob_d[:2].clone()
+        eng3 = api.Engine(precision="bf16x3", device=local_rank, max_forwards=args.max_forwards)
+        eng3.set_weights(A.synth.init_weights())
+        stream3 = torch.cuda.ExternalStream(eng3.stream_ptr(), device=torch.device("cuda", local_rank))
+        prob3 = torch.empty_like(prob_d)
+        def step3():
+            _lib.check(lib.adp_predict(eng3.h, _lib.ptr(tiles_d), BATCH_TILES, TILE, mean, std, ops_arr, len(ops), _lib.ptr(prob3)))
+        step3()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream3)
+        for _ in range(2):
+            step3()
+        e1.record(stream3)
+        torch.cuda.synchronize()
+        dt3 = e0.elapsed_time(e1) / 1e3 / 2
+        x3_res = {"precision": "bf16x3", "tiles_per_s": BATCH_TILES / dt3, "ms_per_step": dt3 * 1e3, "steps": 2,
+                  "max_abs_diff_bf16_vs_bf16x3_probabilities": float((prob3[:2] - prob_bf16).abs().max()),
+                  "note": "same 16-tile 8-way-TTA batch, inputs resident; parity of this path vs the oracle: <= 1e-4 (tests/test_gpu_forward.py)"}
+        eng3.close()
+
     if rank == 0:
         tiles_total = BATCH_TILES * world * args.steps
         value = tiles_total / dev_s
@@ -357,6 +382,8 @@ def run_ours(args, rank, world, local_rank):
             line["wsi"] = wsi_res
         if train_res is not None:
             line["train"] = train_res
+        if x3_res is not None:
+            line["bf16x3"] = x3_res
         if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N=1 only
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
@@ -394,6 +421,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16_simt", "bf16x3"])
     ap.add_argument("--max-forwards", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-x3", action="store_true", help="skip the secondary bf16x3 (<= 1e-4 path) measurement")
     ap.add_argument("--train-batch", type=int, default=8, help="tiles per GPU of the secondary training-step run (0 = skip)")
     ap.add_argument("--train-dice", default="global", choices=["global", "replica"])
     ap.add_argument("--wsi-size", type=int, default=8192, help="side of the synthetic slide of the secondary WSI run (0 = skip)")
