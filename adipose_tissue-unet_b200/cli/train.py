@@ -213,7 +213,6 @@ def main(argv=None) -> int:
                           args.label_smooth_epsilon_neg if args.use_label_smoothing else 0.0)
     rng = np.random.RandomState(args.seed + rank)
     best_overall = -1.0
-    ema = None
     for phase, epochs, max_lr, min_lr, warm, freeze, decay in (
             (1, args.epochs_phase1, 1e-4, 1e-7, args.warmup_epochs_phase1, True, 0.999),
             (2, args.epochs_phase2, 1e-5, 1e-8, args.warmup_epochs_phase2, False, args.ema_decay)):
@@ -225,6 +224,9 @@ def main(argv=None) -> int:
         trainer = T.DataParallelTrainer(engine, args.batch_size, TILE, dist=dist, rank=rank, world=world, dropout_rate=0.3,
                                         seed=args.seed + 1000 * phase, optimizer=args.optimizer, freeze_encoder=freeze)
         best_phase, since_best = -1.0, 0
+        # EMACallback (:410-505): one instance per phase (phase 1: decay 0.999, never saved; phase 2: --ema-decay, best snapshot
+        # by the monitored validation Dice), updated at EPOCH end from the current weights, initialised at the first epoch end
+        ema, ema_best, ema_saved = None, -np.inf, False
         logf = None
         if rank == 0:
             logf = open(ckpt / f"phase{phase}_training.log", "w", newline="")
@@ -237,9 +239,6 @@ def main(argv=None) -> int:
                     break
                 out = trainer.step(x, y, lr)
                 losses.append(out["loss"]); dices.append(out["dice_coef"])
-                if rank == 0 and decay > 0:
-                    cur = engine.get_weights()
-                    ema = cur if ema is None else {k: decay * ema[k] + (1.0 - decay) * cur[k] for k in cur}      # :407-470
             vloss, vdice = validate(engine, val_ds, args.batch_size) if len(val_ds) else (float("nan"), float("nan"))
             log(f"Epoch {epoch + 1}/{epochs} - {time.time() - t0:.0f}s - loss: {np.mean(losses):.4f} - dice_coef: {np.mean(dices):.4f} "
                 f"- val_loss: {vloss:.4f} - val_dice_coef: {vdice:.4f} - lr: {lr:.2e}")
@@ -254,8 +253,12 @@ def main(argv=None) -> int:
                 if score > best_overall:
                     best_overall = score
                     save_weights_file(str(ckpt / "weights_best_overall.weights.h5"), engine.get_weights())
-                    if ema is not None and phase == 2:
-                        save_weights_file(str(ckpt / "weights_ema.weights.h5"), {k: v.astype(np.float32) for k, v in ema.items()})
+                cur = engine.get_weights()
+                ema = {k: v.copy() for k, v in cur.items()} if ema is None else \
+                    {k: (decay * ema[k] + (1 - decay) * cur[k]).astype(np.float32) for k in cur}
+                if phase == 2 and np.isfinite(vdice) and vdice > ema_best:          # save_best_only on the monitor
+                    ema_best, ema_saved = vdice, True
+                    save_weights_file(str(ckpt / "weights_ema.weights.h5"), ema)
             stop = since_best >= 15                                  # EarlyStopping(patience=15), :1280-1284, 1370-1374
             if dist is not None:
                 import torch
@@ -268,6 +271,8 @@ def main(argv=None) -> int:
         if rank == 0:
             logf.close()
             save_weights_file(str(ckpt / f"weights_phase{phase}_final.weights.h5"), engine.get_weights())
+            if phase == 2 and ema is not None and not ema_saved:                      # on_train_end fallback (:484-491)
+                save_weights_file(str(ckpt / "weights_ema.weights.h5"), ema)
         trainer.close()
     log(f"\n✓ Training complete. Checkpoints in {ckpt}\n  - phase1_best.weights.h5\n  - phase2_best.weights.h5\n"
         f"  - weights_best_overall.weights.h5\n  - weights_ema.weights.h5")

@@ -52,7 +52,8 @@ def test_train_then_eval_infer_recon(workspace, capsys):
     ckpts = list((ws / "ckpt").iterdir())
     assert len(ckpts) == 1 and ckpts[0].name.endswith("_adipose_sybreosin_1024_finetune_v3")
     ck = ckpts[0]
-    for f in ("phase1_best.weights.h5", "phase2_best.weights.h5", "weights_best_overall.weights.h5", "normalization_stats.json",
+    for f in ("phase1_best.weights.h5", "phase2_best.weights.h5", "weights_best_overall.weights.h5", "weights_ema.weights.h5",
+              "normalization_stats.json",
               "training_settings.log", "phase1_training.log", "phase2_training.log"):
         assert (ck / f).exists(), f
     stats = json.loads((ck / "normalization_stats.json").read_text())
