@@ -274,6 +274,9 @@ def main(argv=None) -> int:
             if phase == 2 and ema is not None and not ema_saved:                      # on_train_end fallback (:484-491)
                 save_weights_file(str(ckpt / "weights_ema.weights.h5"), ema)
         trainer.close()
+    if rank == 0 and (ckpt / "phase2_best.weights.h5").exists():       # best_overall := best phase-2 weights (:1425-1428)
+        save_weights_file(str(ckpt / "weights_best_overall.weights.h5"),
+                          load_weights_file(str(ckpt / "phase2_best.weights.h5"), keep_aux=True))
     log(f"\n✓ Training complete. Checkpoints in {ckpt}\n  - phase1_best.weights.h5\n  - phase2_best.weights.h5\n"
         f"  - weights_best_overall.weights.h5\n  - weights_ema.weights.h5")
     if dist is not None:
