@@ -101,6 +101,12 @@ struct ConvTcParams {
   const __nv_bfloat16 *resid;
   const __nv_bfloat16 *mask;
   float mask_scale;
+  // EPI_BWD, N <= 96: the mask tile of an item (T rows x N/8 channel-group planes x 128 pixels x 16 B) is staged in shared
+  // memory by the producer with one TMA box per item (tensor map `tmask`, 1 or 2 buffers after the pipeline stages) instead
+  // of per-thread global loads: with register prefetch the loads' latency was exposed once per item (ablation: 11.5 k
+  // cycles per item with the loads, 6.3 k without).  mask_bufs = 0 keeps the register-prefetch loads (wide accumulators)
+  int mask_bufs;                 // 0, 1 or 2
+  uint32_t mask_bytes;           // T * N * 256
 };
 
 // index of weight (tap t, row n of variant block) inside a (variant, chunk) weight block of `ntaps` taps, channel-group
@@ -114,7 +120,7 @@ __host__ __device__ inline size_t tc_block_index(int kys, int ntaps, int N, int 
 
 size_t tc_smem_bytes(const ConvTcParams &p) {
   // stages | mbarriers (2S + 4) + tmem slot | bias (704 floats) | head weights (2*256 + 2 floats)
-  return (size_t)p.S * p.stage_stride + (2 * p.S + 6) * 8 + (704 + 520) * 4;
+  return (size_t)p.S * p.stage_stride + (size_t)p.mask_bufs * p.mask_bytes + (2 * p.S + 6 + 4) * 8 + (704 + 520) * 4;
 }
 
 constexpr int kTcThreads = 352;   // producer, MMA issuer A, 8 epilogue warps, MMA issuer B
@@ -187,13 +193,15 @@ ADP_DEVINL void store16_out(__nv_bfloat16 *o, size_t lo_elems, size_t plane, con
 
 template <int NTAPS, int T, bool KYS, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmask, const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.S * p.stage_stride);
+  uint8_t *smask = smem + (size_t)p.S * p.stage_stride;           // EPI_BWD: mask_bufs x mask_bytes
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smask + (size_t)p.mask_bufs * p.mask_bytes);
   uint64_t *full = bars, *empty = full + p.S;
   uint64_t *acc_full = empty + p.S, *acc_empty = acc_full + 2;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 2);
-  float *sbias = reinterpret_cast<float *>(acc_empty + 4);        // [nvar * N] (<= 704 floats)
+  uint64_t *mask_full = acc_empty + 4, *mask_empty = mask_full + 2;
+  float *sbias = reinterpret_cast<float *>(acc_empty + 8);        // [nvar * N] (<= 704 floats)
   float *shead = sbias + 704;                                      // [2 * N] + 2, EPI_HEAD only
 
   const int warp = threadIdx.x >> 5;
@@ -210,8 +218,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.S; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 2); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&mask_full[i], 1); ptx::mbar_init(&mask_empty[i], 8); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmap);
+    if constexpr (EPI == EPI_BWD) ptx::prefetch_tmap(&tmask);
   }
   if (warp == 1) ptx::tmem_alloc_512(tmem_ptr);
   ptx::tc_fence_before();
@@ -226,6 +236,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
     if (ptx::elect_one()) {
       int st = 0; uint32_t ph = 0;
       long long t_w0 = 0; const long long t_start = clock64();
+      int mit = 0;                                            // EPI_BWD: items whose mask tile has been requested
       const size_t blk_elems = p.b_bytes / 2;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int v = item % p.nvar; int q = item / p.nvar;
@@ -233,6 +244,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
         const int ty = q % p.nty; const int n = q / p.nty;
         const int xg = tx * 16 - p.margin8, ys = ty * T + p.var[v].y0;
         const __nv_bfloat16 *w0 = p.wpk + (size_t)p.var[v].wbase * blk_elems;
+        if (EPI == EPI_BWD && p.mask_bufs > 0) {
+          const int mb = mit % p.mask_bufs; const uint32_t mph = (uint32_t)(mit / p.mask_bufs) & 1u;
+          ptx::mbar_wait(&mask_empty[mb], mph ^ 1, 8);
+          ptx::mbar_expect_tx(&mask_full[mb], p.mask_bytes);
+          ptx::tma_load_5d(smask + (size_t)mb * p.mask_bytes, &tmask, &mask_full[mb], 0, tx * 16, p.var[v].out_cg, ty * T, n);
+          ++mit;
+        }
         for (int c = 0; c < p.nchunks; ++c) {
           uint8_t *sa = smem + (size_t)st * p.stage_stride;
           { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&empty[st], ph ^ 1, 1); if (p.dbg & 16) t_w0 += clock64() - tw; }
@@ -408,13 +426,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
       int row0 = 0, cu0 = half;
       while (cu0 >= NU) { cu0 -= NU; ++row0; }
       if constexpr (EPI == EPI_BWD) {
-        // backward twin (data gradient): out = (acc + resid) * [mask > 0] * mask_scale.  The mask words of ALL units this
-        // warp owns are requested before waiting for the accumulator, so their HBM latency overlaps the MMAs of the
-        // item instead of serialising behind every tcgen05.ld (T*NU <= 12 units per quarter for N <= 192: PF = 6 per warp;
-        // wider accumulators finish with unprefetched loads).
+        // backward twin (data gradient): out = (acc + resid) * [mask > 0] * mask_scale
+        const int UE = T * NU;
+        if (p.mask_bufs > 0) {
+        // the mask tile of the item sits in shared memory ([row][channel group][128 pixels][8]), landed there by the
+        // producer's TMA box
+        const int mb = it % p.mask_bufs; const uint32_t mph = (uint32_t)(it / p.mask_bufs) & 1u;
+        { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_full[buf], acc_ph, 6); if (p.dbg & 16) t_e0 += clock64() - tw; }
+        ptx::mbar_wait(&mask_full[mb], mph, 9);
+        ptx::tc_fence_after();
+        const uint8_t *mtile = smask + (size_t)mb * p.mask_bytes + (size_t)(q4 * 32 + lane) * 16;
+        int srow = row0, scu = cu0;
+        tmem_pipeline(t0, half, 2, UE, [&](int, const uint32_t (&r)[16]) {
+          const int row = srow, cu = scu;
+          unit_next(srow, scu);
+          float f[16];
+          bias_relu16(r, sb + cu * 16, p.relu, f);
+          if ((ty * T + row < p.Hin) && (x < p.Win)) {
+            __nv_bfloat16 *o = out_row(row) + (size_t)(2 * cu) * plane;
+            if (p.resid) {
+              float g[16];
+              load16_bf16(p.resid + (o - p.out), plane, g);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] += g[i];
+            }
+            const uint8_t *mp = mtile + (size_t)(row * (p.N >> 3) + 2 * cu) * 2048;      // plane = 128 px * 16 B
+            __align__(16) __nv_bfloat16 mh[16];
+            *reinterpret_cast<uint4 *>(mh) = *reinterpret_cast<const uint4 *>(mp);
+            *reinterpret_cast<uint4 *>(mh + 8) = *reinterpret_cast<const uint4 *>(mp + 2048);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __bfloat162float(mh[i]) > 0.f ? f[i] * p.mask_scale : 0.f;
+            store16_bf16(o, plane, f);
+          }
+        });
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&mask_empty[mb]);
+        } else {
+        // wide accumulators (N > 96: the mask tile and a useful pipeline depth do not fit shared memory together): the
+        // mask words of the first PF units this warp owns are requested from global memory before waiting for the
+        // accumulator, so their latency overlaps the MMAs of the item; later units load unprefetched
         constexpr int PF = 6;
         uint4 mk[PF][2];
-        const int UE = T * NU;
         int prow = row0, pcu = cu0;
 #pragma unroll
         for (int k = 0; k < PF; ++k) {
@@ -486,6 +538,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvTcParams p) {
             for (int i = 0; i < 16; ++i) f[i] = m[i] > 0.f ? f[i] * p.mask_scale : 0.f;
             store16_bf16(o, plane, f);
           }
+        }
         }
       } else {
       { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_full[buf], acc_ph, 6); if (p.dbg & 16) t_e0 += clock64() - tw; }

@@ -284,7 +284,7 @@ void plan_tc(ConvLayer &L, bool allow_kys = true, bool split = false) {
   }
 }
 
-typedef void (*ConvTcKernel)(const CUtensorMap, const ConvTcParams);
+typedef void (*ConvTcKernel)(const CUtensorMap, const CUtensorMap, const ConvTcParams);
 // every (taps, rows per item, ky-stacked, epilogue) combination the plans can ask for; nullptr = not instantiated
 ConvTcKernel tc_kernel_lookup(int ntaps, int T, int kys, int epi) {
 #define ADP_TC(NT, TT, KS, EP) if (ntaps == NT && T == TT && kys == KS && epi == EP) return conv_tc_kernel<NT, TT, (KS != 0), EP>;
@@ -519,10 +519,32 @@ void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label,
   const CUtensorMap &tm = tmap_for(e, src, Hs, Ws, s_cgs, s_cg0, map_C, cap, p.PW / 8, 2, p.BR);
   const int nitems = nb * p.nty * p.ntx * p.nvar;
   const int grid = std::min(nitems, e->num_sms);
+  const int epi_kind = (epi.mode == EPI_STORE && epi.mask) ? EPI_BWD : epi.mode;
+  ConvTcKernel kern = tc_kernel_for(p.ntaps, p.T, p.kys, epi_kind);
+  // data-gradient twin, N <= 96 (T >= 2 rows per item): the mask tile of every item is staged in shared memory next to the
+  // pipeline stages (two buffers when at least two stages still fit, else one).  Wider accumulators keep the
+  // register-prefetch loads (mask_bufs = 0): a 44 KB tile per buffer would leave them two 63 KB stages, measured slower
+  // (up2_conv2 twin 0.74 -> 0.98 ms) while the 48/96-wide twins gain (up1_conv2 1.35 -> 0.85 ms, down1_conv2 0.71 -> 0.43 ms).
+  // ADP_BWD_MASK = 0 (never) / 1 / 2 (buffers where staged) / 3 (stage for every width) overrides for experiments.
+  p.mask_bufs = 0; p.mask_bytes = 0;
+  const CUtensorMap *tmk = &tm;
+  if (epi_kind == EPI_BWD) {
+    static const int mode = getenv("ADP_BWD_MASK") ? atoi(getenv("ADP_BWD_MASK")) : -1;
+    const bool stage = p.oscale == 1 && mode != 0 && (p.N <= 96 || mode == 3);
+    if (stage) {
+      p.mask_bytes = (uint32_t)(p.T * p.N * 256);
+      const size_t budget = 220 * 1024;
+      p.mask_bufs = (2 * (size_t)p.mask_bytes + 2 * (size_t)p.stage_stride <= budget) ? 2 : 1;
+      if (mode == 1 || mode == 2) p.mask_bufs = mode;
+      const size_t left = budget - (size_t)p.mask_bufs * p.mask_bytes;
+      p.S = (int)std::min<size_t>(p.S, left / p.stage_stride);
+      ADP_REQUIRE(p.S >= 2, "data-gradient twin: pipeline stages and the mask tile do not fit shared memory");
+      tmk = &tmap_for(e, epi.mask, Ho, Wo, d_cgs, d_cg0, L.cout_pad, cap, 16, p.N / 8, p.T);
+    }
+  }
   const size_t smem = tc_smem_bytes(p);
-  ConvTcKernel kern = tc_kernel_for(p.ntaps, p.T, p.kys, (epi.mode == EPI_STORE && epi.mask) ? EPI_BWD : epi.mode);
   if (e->dbg & 16) { e->misc.ensure(148 * 8 * 8 + 4096); p.dbg_out = reinterpret_cast<long long *>(e->misc.as<char>() + 4096); }
-  e->launch(label.c_str(), fl, by, [&] { kern<<<grid, kTcThreads, smem, e->stream>>>(tm, p); });
+  e->launch(label.c_str(), fl, by, [&] { kern<<<grid, kTcThreads, smem, e->stream>>>(tm, *tmk, p); });
   if (e->dbg & 16) {
     // role timers (cycles, averaged over CTAs): where each warp role of the pipeline waits
     std::vector<long long> h((size_t)grid * 8);
