@@ -157,6 +157,21 @@ struct adp_engine {
   float ds_w[3] = {1.0f, 0.4f, 0.3f};        // loss weights main / aux1 / aux2 (train_adipose_unet_v3.py:858-872)
   bool wgrad_simt = false, dgrad_simt = false;   // bf16 training: CUDA-core cross-check of the tcgen05 backward kernels
 
+  // Grid of a grid-stride elementwise kernel: exactly one resident wave (blocks per SM from the occupancy calculator x SMs),
+  // or fewer blocks when the work is smaller.  A fixed "SMs x 8 / x 16" grid ran 1.33 .. 5.33 waves for kernels that
+  // hold 3, 5 or 6 blocks per SM, i.e. a last wave at 20-60 % occupancy.
+  std::map<const void *, int> occ_cache;
+  template <typename K> int wave_grid(K kern, size_t blocks_needed, int block = 256, size_t smem = 0) {
+    const void *key = reinterpret_cast<const void *>(kern);
+    auto it = occ_cache.find(key);
+    if (it == occ_cache.end()) {
+      int nb = 0;
+      ADP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, block, smem));
+      it = occ_cache.emplace(key, std::max(nb, 1)).first;
+    }
+    return (int)std::max<size_t>(1, std::min<size_t>(blocks_needed, (size_t)num_sms * it->second));
+  }
+
   template <typename F> void launch(const char *kind, double flops, double bytes, F &&f) {
     if (prof) ADP_CUDA(cudaEventRecord(ev0, stream));
     f();
@@ -470,6 +485,13 @@ const CUtensorMap &tmap_for(adp_engine *e, const void *buf, int H, int W, int cg
   return e->tmaps.emplace(key, m).first->second;
 }
 
+// TTA combine / blend kernel (kernels_post.cuh); ADP_TTA_SERIAL=1 selects the one-plane-per-barrier variant for A/B timing
+typedef void (*TtaKernel)(const float *, TtaOps, int, int, float *, float *, float *, const float *, int, int, int, int);
+TtaKernel tta_kernel() {
+  static const bool serial = getenv("ADP_TTA_SERIAL") && atoi(getenv("ADP_TTA_SERIAL")) != 0;
+  return serial ? tta_blend_serial_kernel : tta_blend_kernel;
+}
+
 double conv_flops(const ConvLayer &L, int Hout, int Wout, int nb) {
   return 2.0 * nb * Hout * Wout * 9.0 * L.cin * L.cout;
 }
@@ -593,7 +615,7 @@ void run_pool(adp_engine *e, const DevBuf &src, int Hs, int Ws, int spitch, int 
   auto in = e->split ? view_split<T>(src, Hs, Ws, spitch, 0, C) : view<T>(src, Hs, Ws, spitch, 0, C);
   auto out = e->split ? view_split<T>(dst, Hs / 2, Ws / 2, C, 0, C) : view<T>(dst, Hs / 2, Ws / 2, C, 0, C);
   const size_t total = (size_t)nb * (Hs / 2) * (Ws / 2) * (C / 8);
-  const int grid = (int)std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 16);
+  const int grid = e->wave_grid(maxpool2_kernel<T>, cdiv64(total, 256));
   e->launch("maxpool2x2", 0, (double)nb * Hs * Ws * C * sizeof(T) * 1.25, [&] {
     maxpool2_kernel<T><<<grid, 256, 0, e->stream>>>(in, out, nb);
   });
@@ -610,7 +632,7 @@ template <typename T>
 void run_dropout(adp_engine *e, const DevBuf &buf, int H, int C, int creal, int nb, const DropSpec &d, int site) {
   auto v = view<T>(buf, H, H, C, 0, C);
   const size_t total = (size_t)nb * H * H * (C / 8);
-  const int grid = (int)std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 16);
+  const int grid = e->wave_grid(dropout_kernel<T>, cdiv64(total, 256));
   e->launch("dropout", 0, (double)total * 16 * sizeof(T), [&] {
     dropout_kernel<T><<<grid, 256, 0, e->stream>>>(v, nb, d.keep, d.seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(site + 1), d.mask[site], creal);
   });
@@ -663,12 +685,12 @@ template <typename T> void forward_t(adp_engine *e, const Acts &A, int S, const 
     auto o = view_split<T>(*A.ts, S4, S4, cp[3], 0, cp[3]);
     const size_t total = (size_t)nfw * S4 * S4 * (cp[3] / 8);
     e->launch("add6", 0, (double)total * 32 * 7, [&] {
-      add6_split_kernel<T><<<(int)std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 16), 256, 0, e->stream>>>(
+      add6_split_kernel<T><<<e->wave_grid(add6_split_kernel<T>, cdiv64(total, 256)), 256, 0, e->stream>>>(
           v[0], v[1], v[2], v[3], v[4], v[5], o, nfw);
     });
   } else {
     const size_t nvec = (size_t)nfw * S4 * S4 * cp[3] * sizeof(T) / 16;
-    const int grid = (int)std::min<size_t>(cdiv64(nvec, 256), (size_t)e->num_sms * 16);
+    const int grid = e->wave_grid(add6_kernel<T>, cdiv64(nvec, 256));
     e->launch("add6", 0, (double)nvec * 16 * 7, [&] {
       add6_kernel<T><<<grid, 256, 0, e->stream>>>(A.t[0]->as<T>(), A.t[1]->as<T>(), A.t[2]->as<T>(), A.t[3]->as<T>(),
                                                  A.t[4]->as<T>(), A.t[5]->as<T>(), A.ts->as<T>(), nvec);
@@ -689,7 +711,7 @@ template <typename T> void forward_t(adp_engine *e, const Acts &A, int S, const 
   if (head.mode != EPI_HEAD) {
     auto in = view<T>(*A.u1c, S, S, cp[0], 0, cp[0]);
     const size_t total = (size_t)nfw * S * S;
-    const int grid = (int)std::min<size_t>(cdiv64(total, 256), (size_t)e->num_sms * 16);
+    const int grid = e->wave_grid(head_kernel<T>, cdiv64(total, 256), 256, (size_t)2 * cp[0] * 4);
     e->launch("head_softmax", 2.0 * total * e->c[0] * 2, (double)total * (cp[0] * sizeof(T) + 4), [&] {
       head_kernel<T><<<grid, 256, (size_t)2 * cp[0] * 4, e->stream>>>(in, nfw, e->w_head.as<float>(), e->b_head.as<float>(),
                                                                       A.prob->as<float>());
@@ -777,13 +799,13 @@ void run_tiles(adp_engine *e, int kind, FirstConvSrc src, const void *src_base, 
       const double by = (double)tile_px * 4 * (n_ops + (out ? 1 : (e->wsi_mode == ADP_BLEND_GAUSSIAN ? 5 : 4)));
       if (out) {
         e->launch("tta_combine", 0, by, [&] {
-          tta_blend_kernel<<<grid, block, 0, e->stream>>>(planes, tops, S, 0, dout + (size_t)t * tile_px, nullptr, nullptr,
+          tta_kernel()<<<grid, block, 0, e->stream>>>(planes, tops, S, 0, dout + (size_t)t * tile_px, nullptr, nullptr,
                                                          nullptr, 0, 0, 0, 0);
         });
       } else {
         const int mode = e->wsi_mode == ADP_BLEND_GAUSSIAN ? 1 : 2;
         e->launch("tta_blend", 0, by, [&] {
-          tta_blend_kernel<<<grid, block, 0, e->stream>>>(planes, tops, S, mode, nullptr, e->wsi_acc.as<float>(),
+          tta_kernel()<<<grid, block, 0, e->stream>>>(planes, tops, S, mode, nullptr, e->wsi_acc.as<float>(),
                                                          e->wsi_wsum.as<float>(), e->wsi_window.as<float>(), e->wsi_W,
                                                          e->wsi_rows, ys[t0 + t] - e->wsi_y0, xs[t0 + t]);
         });
@@ -818,12 +840,12 @@ void run_finalize(adp_engine *e, const float *acc, const float *wsum, int linear
   const uint8_t *dg = reinterpret_cast<const uint8_t *>(to_device(e, e->fin_gt, gt, n));
   e->counts.ensure(32);
   ADP_CUDA(cudaMemsetAsync(e->counts.p, 0, 32, e->stream));
-  const int grid = (int)std::min<size_t>(cdiv64(n, 256 * 4), (size_t)e->num_sms * 8);
+  const int grid = e->wave_grid(finalize_kernel, cdiv64(n, 256 * 4));
   const double by = (double)n * ((wsum ? 8 : 4) + (dp ? 4 : 0) + (dm ? 1 : 0) + (dg ? 1 : 0));
   e->launch("finalize_threshold_metrics", 0, by, [&] {
     auto al = [](const void *q, size_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
     const int vec = al(acc, 16) && al(wsum, 16) && al(dp, 16) && al(dm, 4) && al(dg, 4);
-    finalize_kernel<<<std::max(grid, 1), 256, 0, e->stream>>>(acc, wsum, linear, n, thr, dp, dm, dg,
+    finalize_kernel<<<grid, 256, 0, e->stream>>>(acc, wsum, linear, n, thr, dp, dm, dg,
                                                              e->counts.as<unsigned long long>(), vec);
   });
   if (prob_host) ADP_CUDA(cudaMemcpyAsync(prob, dp, n * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -860,7 +882,7 @@ void loss_forward(adp_engine *e, LossState &ls, const LossRecipe &r, const float
   ls.sums.ensure(64);
   ADP_CUDA(cudaMemsetAsync(ls.sums.p, 0, 64, e->stream));
   if (ls.ohem) ls.bce.ensure(n * 4);
-  const int grid = (int)std::max<size_t>(1, std::min<size_t>(cdiv64(n, 256 * 4), (size_t)e->num_sms * 8));
+  const int grid = e->wave_grid(loss_reduce_kernel, cdiv64(n, 256 * 4));
   e->launch("loss_reduce", 0, (double)n * (ls.ohem ? 12 : 8), [&] {
     loss_reduce_kernel<<<grid, 256, 0, e->stream>>>(p, y, n, r.ys_scale(), r.eps_neg, ls.ohem ? ls.bce.as<float>() : nullptr,
                                                    ls.sums.as<double>());
@@ -925,7 +947,7 @@ void loss_forward(adp_engine *e, LossState &ls, const LossRecipe &r, const float
 void loss_backward(adp_engine *e, LossState &ls, const LossRecipe &r, const float *p, const float *y, int batch, size_t npi,
                    const double s[8], float *dldp, float gain = 1.f) {
   const size_t n = (size_t)batch * npi;
-  const int grid = (int)std::max<size_t>(1, std::min<size_t>(cdiv64(n, 256 * 4), (size_t)e->num_sms * 8));
+  const int grid = e->wave_grid(loss_grad_kernel, cdiv64(n, 256 * 4));
   const double denom = s[2] + s[3] + 1.0;
   e->launch("loss_grad", 0, (double)n * 12, [&] {
     loss_grad_kernel<<<grid, 256, 0, e->stream>>>(p, y, n, r.ys_scale(), r.eps_neg, (float)(1.0 / s[7]), (float)(2.0 * s[1] + 1.0),
@@ -1154,7 +1176,7 @@ int adp_tta_combine(adp_engine *e, const float *planes, int size, const int *ops
   }
   dim3 grid(cdiv(size, 32), cdiv(size, 32)), block(32, 8);
   e->launch("tta_combine", 0, (double)px * 4 * (n_ops + 1), [&] {
-    tta_blend_kernel<<<grid, block, 0, e->stream>>>(pl, tops, size, 0, o, nullptr, nullptr, nullptr, 0, 0, 0, 0);
+    tta_kernel()<<<grid, block, 0, e->stream>>>(pl, tops, size, 0, o, nullptr, nullptr, nullptr, 0, 0, 0, 0);
   });
   if (host) ADP_CUDA(cudaMemcpyAsync(out, o, px * 4, cudaMemcpyDeviceToHost, e->stream));
   ADP_CUDA(cudaStreamSynchronize(e->stream));
@@ -1240,7 +1262,7 @@ int adp_threshold_sweep(adp_engine *e, const float *prob, const uint8_t *gt, int
   dt.ensure((size_t)n_thr * 4); dh.ensure((size_t)2 * (n_thr + 1) * 8);
   ADP_CUDA(cudaMemcpyAsync(dt.p, thresholds, (size_t)n_thr * 4, cudaMemcpyHostToDevice, e->stream));
   ADP_CUDA(cudaMemsetAsync(dh.p, 0, (size_t)2 * (n_thr + 1) * 8, e->stream));
-  const int grid = (int)std::max<size_t>(1, std::min<size_t>(cdiv64(n, 256 * 8), (size_t)e->num_sms * 8));
+  const int grid = e->wave_grid(threshold_sweep_kernel, cdiv64(n, 256 * 8));
   e->launch("threshold_sweep", 0, (double)n * 5, [&] {
     threshold_sweep_kernel<<<grid, 256, 0, e->stream>>>(p, g, n, dt.as<float>(), n_thr, dh.as<unsigned long long>());
   });
@@ -1399,7 +1421,7 @@ int adp_wsi_import_add(adp_engine *e, int y, int rows, const float *acc, const f
   DevBuf da, dw;
   const float *a = reinterpret_cast<const float *>(to_device(e, da, acc, n * 4));
   const float *w = reinterpret_cast<const float *>(to_device(e, dw, weight, n * 4));
-  const int grid = (int)std::min<size_t>(cdiv64(n, 256), (size_t)e->num_sms * 8);
+  const int grid = e->wave_grid(add_partial_kernel, cdiv64(n, 256));
   e->launch("wsi_add_partial", 0, (double)n * 24, [&] {
     add_partial_kernel<<<grid, 256, 0, e->stream>>>(e->wsi_acc.as<float>() + off, e->wsi_wsum.as<float>() + off, a, w, n);
   });

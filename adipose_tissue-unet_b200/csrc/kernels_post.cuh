@@ -21,12 +21,91 @@ namespace adp {
 // mode 2: linear blend:   acc += avg; wsum(count as float) += 1   (LinearBlender, :196-199)
 struct TtaOps { int n; int inv[8]; };
 
-// (Requesting 4 or 8 augmentations' source blocks per barrier was tried and measured slower: 35-60 us instead of 26 us per
-// 1024^2 tile, so the kernel walks one plane at a time.)
+// All source blocks (one 32x32 block per augmentation) are requested before the single barrier: 4 * n loads per thread in
+// flight, issued from a register array so that no shared-memory store sits between two global loads.  ADP_TTA_SERIAL=1
+// selects the one-plane-per-barrier walk (tta_blend_serial_kernel, eight dependent DRAM round trips per block) for A/B runs.
 __global__ void __launch_bounds__(256)
 tta_blend_kernel(const float *__restrict__ planes, TtaOps ops, int S, int mode, float *__restrict__ out,
                  float *__restrict__ acc, float *__restrict__ wsum, const float *__restrict__ window,
                  int accW, int accRows, int ty, int tx) {
+  __shared__ float tile[8][32][33];
+  const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
+  const int lx = threadIdx.x, ly = threadIdx.y;     // 32 x 8
+  const int ei = min(bi + 31, S - 1), ej = min(bj + 31, S - 1);
+  float ld[8][4];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < ops.n) {
+      // source block origin: image of the block's corner region under the inverse op
+      int s0i, s0j, s1i, s1j;
+      d4_src(ops.inv[k], bi, bj, S, s0i, s0j);
+      d4_src(ops.inv[k], ei, ej, S, s1i, s1j);
+      const int sbi = min(s0i, s1i), sbj = min(s0j, s1j);
+      const float *P = planes + (size_t)k * S * S;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = sbi + ly + 8 * r, j = sbj + lx;
+        ld[k][r] = (i < S && j < S) ? __ldg(P + (size_t)i * S + j) : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < ops.n) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) tile[k][ly + 8 * r][lx] = ld[k][r];
+    }
+  __syncthreads();
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < ops.n) {
+      const int op = ops.inv[k];
+      int s0i, s0j, s1i, s1j;
+      d4_src(op, bi, bj, S, s0i, s0j);
+      d4_src(op, ei, ej, S, s1i, s1j);
+      const int sbi = min(s0i, s1i), sbj = min(s0j, s1j);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = bi + ly + 8 * r, j = bj + lx;
+        float v = 0.f;
+        if (i < S && j < S) {
+          int si, sj;
+          d4_src(op, i, j, S, si, sj);
+          v = tile[k][si - sbi][sj - sbj];
+        }
+        sum[r] = (k == 0) ? v : __fadd_rn(sum[r], v);
+      }
+    }
+  }
+  const float nf = (float)ops.n;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    int i = bi + ly + 8 * r, j = bj + lx;
+    if (i >= S || j >= S) continue;
+    float avg = (ops.n == 1) ? sum[r] : __fdiv_rn(sum[r], nf);
+    if (mode == 0) {
+      out[(size_t)i * S + j] = avg;
+    } else {
+      int gy = ty + i, gx = tx + j;
+      if (gy < 0 || gy >= accRows || gx < 0 || gx >= accW) continue;
+      size_t g = (size_t)gy * accW + gx;
+      if (mode == 1) {
+        float w = window[(size_t)i * S + j];
+        acc[g] = __fadd_rn(acc[g], __fmul_rn(avg, w));
+        wsum[g] = __fadd_rn(wsum[g], w);
+      } else {
+        acc[g] = __fadd_rn(acc[g], avg);
+        wsum[g] = __fadd_rn(wsum[g], 1.0f);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+tta_blend_serial_kernel(const float *__restrict__ planes, TtaOps ops, int S, int mode, float *__restrict__ out,
+                        float *__restrict__ acc, float *__restrict__ wsum, const float *__restrict__ window,
+                        int accW, int accRows, int ty, int tx) {
   __shared__ float tile[32][33];
   const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
   const int lx = threadIdx.x, ly = threadIdx.y;     // 32 x 8

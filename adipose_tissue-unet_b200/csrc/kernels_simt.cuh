@@ -100,6 +100,33 @@ template <typename T> ADP_DEVINL void load8(const T *i, float *a) {
   }
 }
 
+// eight channels as loaded (16 bytes of bf16, or two float4): lets a kernel keep several loads in flight without holding
+// their unpacked float copies in registers
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> { uint4 v; };
+template <> struct Raw8<float> { float4 a, b; };
+template <typename T> ADP_DEVINL Raw8<T> load_raw8(const T *p) {
+  Raw8<T> r;
+  if constexpr (sizeof(T) == 2) r.v = *reinterpret_cast<const uint4 *>(p);
+  else { r.a = *reinterpret_cast<const float4 *>(p); r.b = *reinterpret_cast<const float4 *>(p + 4); }
+  return r;
+}
+template <typename T> ADP_DEVINL Raw8<T> zero_raw8() {
+  Raw8<T> r;
+  if constexpr (sizeof(T) == 2) r.v = make_uint4(0u, 0u, 0u, 0u);
+  else { r.a = make_float4(0.f, 0.f, 0.f, 0.f); r.b = r.a; }
+  return r;
+}
+template <typename T> ADP_DEVINL void unpack8(const Raw8<T> &r, float *a) {
+  if constexpr (sizeof(T) == 2) {
+    const uint32_t w[4] = {r.v.x, r.v.y, r.v.z, r.v.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { a[2 * c] = __uint_as_float(w[c] << 16); a[2 * c + 1] = __uint_as_float(w[c] & 0xFFFF0000u); }
+  } else {
+    a[0] = r.a.x; a[1] = r.a.y; a[2] = r.a.z; a[3] = r.a.w; a[4] = r.b.x; a[5] = r.b.y; a[6] = r.b.z; a[7] = r.b.w;
+  }
+}
+
 // block = (32, 8), output tile = 32 columns x 32 rows: the normalised (and dihedrally transformed) 34 x 34 input window
 // is staged once in shared memory (one z-score division per input pixel instead of nine), then a warp owns 32
 // consecutive columns of FOUR rows so that every weight read from shared memory feeds four pixels (288 FMA per 18
@@ -261,11 +288,8 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(View<T> in, View<T> out, 
   const int G = out.C / 8;
   const size_t total = (size_t)nb * out.H * G * out.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int x = i % out.W;
-    size_t r = i / out.W;
-    int g = r % G; r /= G;
-    int y = r % out.H;
-    int n = r / out.H;
+    const RpIndex ri = rp_index(i, out.W, G, out.H);
+    const int x = ri.x, g = ri.g, y = ri.y, n = ri.n;
     float a[8], b[8], c[8], d[8], m[8];
     load8v<T>(in, n, 2 * y, g, 2 * x, a);
     load8v<T>(in, n, 2 * y, g, 2 * x + 1, b);
@@ -308,9 +332,8 @@ add6_split_kernel(View<T> a0, View<T> a1, View<T> a2, View<T> a3, View<T> a4, Vi
   const int G = out.C / 8;
   const size_t total = (size_t)nb * out.H * G * out.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int x = i % out.W; size_t r = i / out.W;
-    const int g = r % G; r /= G;
-    const int y = r % out.H, n = r / out.H;
+    const RpIndex ri = rp_index(i, out.W, G, out.H);
+    const int x = ri.x, g = ri.g, y = ri.y, n = ri.n;
     float s[8], t[8];
     load8v<T>(a0, n, y, g, x, s);
     load8v<T>(a1, n, y, g, x, t);

@@ -11,7 +11,10 @@ namespace adp {
 // Head backward.  p = softmax(z)[1] = sigmoid(z1 - z0);  dz1 = g*p*(1-p), dz0 = -dz1.
 // G[c] = dz1 * (w1[c] - w0[c]) * [x[c] > 0] * scale  (x = post-dropout output of up1_conv3: the written tensor is already
 // dL/d(pre-activation) of that layer);  dWh[1][c] = sum dz1 * x[c] = -dWh[0][c];  dbh[1] = sum dz1 = -dbh[0].
-// One thread per pixel; block-level reduction, one double atomic per block and channel.
+// A warp owns one channel group (gridDim.x * 8 warps is a multiple of the group count) and walks (image, row) lines
+// with its lanes along x: 8 + 1 partial sums stay in registers over all its pixels and leave through shuffles, one
+// shared-memory atomic per warp and one double atomic per block and channel.  (One thread per pixel with 49 warp
+// reductions per pixel reached 3.2 TB/s.)
 template <typename T>
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(View<T> x, int nb, const float *__restrict__ wh /*[2][C]*/, const float *__restrict__ prob,
@@ -20,34 +23,60 @@ head_bwd_kernel(View<T> x, int nb, const float *__restrict__ wh /*[2][C]*/, cons
   extern __shared__ float sm[];
   float *wd = sm;                       // C: w1 - w0
   float *red = sm + x.C;                // C + 1 partial sums of this block
-  const int C = x.C;
+  const int C = x.C, G = C / 8;
   for (int i = threadIdx.x; i < C; i += blockDim.x) { wd[i] = wh[C + i] - wh[i]; }
   for (int i = threadIdx.x; i <= C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
-  const size_t total = (size_t)nb * x.H * x.W;
-  const size_t px = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  float dz = 0.f;
-  int xx = 0, yy = 0, n = 0;
-  const bool live = px < total;
-  if (live) {
-    xx = px % x.W; size_t r = px / x.W; yy = r % x.H; n = r / x.H;
-    const float p = prob[px];
-    dz = dldp[px] * p * (1.f - p);
-  }
-  for (int gi = 0; gi < C / 8; ++gi) {
-    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o[8];
-    if (live) load8<T>(x.p + x.at(n, yy, gi, xx), a);
+  const int lane = threadIdx.x & 31;
+  const int wid = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int nw = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+  const int gi = wid % G;
+  float wv[8], part[8], bsum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      o[k] = a[k] > 0.f ? dz * wd[gi * 8 + k] * scale : 0.f;   // ReLU' (and dropout mask / keep) of up1_conv3 folded in
-      float s = warp_sum(dz * a[k]);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&red[gi * 8 + k], s);
+  for (int k = 0; k < 8; ++k) { wv[k] = wd[gi * 8 + k]; part[k] = 0.f; }
+  const int rows = nb * x.H;
+  for (int r = wid / G; r < rows; r += nw / G) {
+    const int n = r / x.H, yy = r - n * x.H;
+    const size_t pbase = (size_t)r * x.W;
+    // U columns per trip, all their loads issued before the first use (ncu on the one-column loop: 48 % warps active,
+    // stalled on the loads, 59 % of DRAM peak)
+    constexpr int U = 4;
+    for (int xx0 = lane; xx0 < x.W; xx0 += 32 * U) {
+      float pp[U], dd[U];
+      Raw8<T> raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int xx = xx0 + 32 * u;
+        pp[u] = 0.f; dd[u] = 0.f; raw[u] = zero_raw8<T>();
+        if (xx < x.W) {
+          pp[u] = prob[pbase + xx]; dd[u] = dldp[pbase + xx];
+          raw[u] = load_raw8<T>(x.p + x.at(n, yy, gi, xx));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int xx = xx0 + 32 * u;
+        const float dz = dd[u] * pp[u] * (1.f - pp[u]);
+        float a[8], o[8];
+        unpack8<T>(raw[u], a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          o[k] = a[k] > 0.f ? dz * wv[k] * scale : 0.f;   // ReLU' (and dropout mask / keep) of up1_conv3 folded in
+          part[k] = fmaf(dz, a[k], part[k]);
+        }
+        bsum += dz;
+        if (xx < x.W) store8<T>(g.p + g.at(n, yy, gi, xx), o);
+      }
     }
-    if (live) store8<T>(g.p + g.at(n, yy, gi, xx), o);
   }
-  {
-    float s = warp_sum(dz);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&red[C], s);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float s = warp_sum(part[k]);
+    if (lane == 0) atomicAdd(&red[gi * 8 + k], s);
+  }
+  if (gi == 0) {
+    const float s = warp_sum(bsum);
+    if (lane == 0) atomicAdd(&red[C], s);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dwh1[i], (double)red[i]);
@@ -61,9 +90,8 @@ __global__ void __launch_bounds__(256) relu_mask_kernel(View<T> g, View<T> x, in
   const int G = g.C / 8;
   const size_t total = (size_t)nb * g.H * G * g.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int xx = i % g.W; size_t r = i / g.W;
-    int gi = r % G; r /= G;
-    int yy = r % g.H; int n = r / g.H;
+    const RpIndex ri = rp_index(i, g.W, G, g.H);
+    const int xx = ri.x, gi = ri.g, yy = ri.y, n = ri.n;
     float a[8], b[8];
     load8<T>(g.p + g.at(n, yy, gi, xx), a);
     load8<T>(x.p + x.at(n, yy, gi, xx), b);
@@ -81,22 +109,26 @@ ADP_DEVINL uint32_t hash_u32(uint32_t h) {
   h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
   return h;
 }
-ADP_DEVINL uint32_t dropout_bits(uint64_t seed, size_t group_index, int pair) {
+// salt = hash(high half of the element index ^ high half of the seed) ^ low half of the seed: constant over a launch whenever
+// the index fits 32 bits (hoisted out of the element loop - the kernel was issue-bound on two hashes per channel pair)
+ADP_DEVINL uint32_t dropout_salt(uint64_t seed, uint32_t idx_hi) { return hash_u32(idx_hi ^ (uint32_t)(seed >> 32)) ^ (uint32_t)seed; }
+ADP_DEVINL uint32_t dropout_bits(uint64_t seed, size_t group_index, int pair, uint32_t salt0) {
   const uint64_t idx = (uint64_t)group_index * 4u + (uint64_t)pair;
-  return hash_u32((uint32_t)idx * 0x9E3779B1u ^ hash_u32((uint32_t)(idx >> 32) ^ (uint32_t)(seed >> 32)) ^ (uint32_t)seed);
+  const uint32_t hi = (uint32_t)(idx >> 32);
+  return hash_u32((uint32_t)idx * 0x9E3779B1u ^ (hi == 0 ? salt0 : dropout_salt(seed, hi)));
 }
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 dropout_kernel(View<T> x, int nb, float keep, uint64_t seed, const uint8_t *__restrict__ mask_in /*NHWC real channels, or null*/,
                int creal) {
   const int G = x.C / 8;
   const size_t total = (size_t)nb * x.H * G * x.W;
   const float inv = 1.f / keep;
   const uint32_t thr = (uint32_t)fminf(keep * 65536.f, 65536.f);
+  const uint32_t salt0 = dropout_salt(seed, 0u);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int xx = i % x.W; size_t r = i / x.W;
-    int gi = r % G; r /= G;
-    int yy = r % x.H; int n = r / x.H;
+    const RpIndex ri = rp_index(i, x.W, G, x.H);
+    const int xx = ri.x, gi = ri.g, yy = ri.y, n = ri.n;
     float a[8];
     T *ptr = x.p + x.at(n, yy, gi, xx);
     load8<T>(ptr, a);
@@ -110,7 +142,7 @@ dropout_kernel(View<T> x, int nb, float keep, uint64_t seed, const uint8_t *__re
     } else {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint32_t h = dropout_bits(seed, i, q);
+        const uint32_t h = dropout_bits(seed, i, q, salt0);
         a[2 * q] = (h & 0xFFFFu) < thr ? a[2 * q] * inv : 0.f;
         a[2 * q + 1] = (h >> 16) < thr ? a[2 * q + 1] * inv : 0.f;
       }
@@ -123,14 +155,50 @@ dropout_kernel(View<T> x, int nb, float keep, uint64_t seed, const uint8_t *__re
 // in (dy,dx) scan order.  One thread per pooled pixel and channel group; gin is ADDED into (the skip
 // tensor's gradient already holds the decoder branch, already multiplied by the ReLU mask of the layer that
 // produced xin — so the pooled contribution is masked the same way here).
+// bf16: the nine 16-byte vectors stay packed (36 registers instead of 72 floats -> 5 resident blocks per SM instead of 3; ncu on
+// the float-array form: 33 % warps active, stalled on the loads, 50 % of DRAM peak) and channels are unpacked pair by pair.
 template <typename T>
-__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(View<T> xin, View<T> gout, View<T> gin, int nb) {
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) maxpool2_bwd_kernel(View<T> xin, View<T> gout, View<T> gin, int nb) {
   const int G = gout.C / 8;
   const size_t total = (size_t)nb * gout.H * G * gout.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int xx = i % gout.W; size_t r = i / gout.W;
-    int gi = r % G; r /= G;
-    int yy = r % gout.H; int n = r / gout.H;
+    const RpIndex ri = rp_index(i, gout.W, G, gout.H);
+    const int xx = ri.x, gi = ri.g, yy = ri.y, n = ri.n;
+    if constexpr (sizeof(T) == 2) {
+      uint32_t go[4], v[4][4], gw[4][4];
+      *reinterpret_cast<uint4 *>(go) = *reinterpret_cast<const uint4 *>(gout.p + gout.at(n, yy, gi, xx));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        *reinterpret_cast<uint4 *>(v[q]) = *reinterpret_cast<const uint4 *>(xin.p + xin.at(n, 2 * yy + (q >> 1), gi, 2 * xx + (q & 1)));
+        *reinterpret_cast<uint4 *>(gw[q]) = *reinterpret_cast<const uint4 *>(gin.p + gin.at(n, 2 * yy + (q >> 1), gi, 2 * xx + (q & 1)));
+      }
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {               // element 2w + h = low / high half of word w
+          const int sh = 16 * h;
+          float vq[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) vq[q] = __uint_as_float((v[q][w] >> sh) << 16);
+          int best = 0; float vb = vq[0];
+#pragma unroll
+          for (int q = 1; q < 4; ++q) if (vq[q] > vb) { vb = vq[q]; best = q; }
+          if (vb > 0.f) {                           // gin holds dL/d(pre-activation): ReLU' of the pooled layer
+            const float g = __uint_as_float((go[w] >> sh) << 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q == best) {
+                const float nv = __uint_as_float((gw[q][w] >> sh) << 16) + g;
+                const uint32_t nb16 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(nv));
+                gw[q][w] = (gw[q][w] & (0xFFFF0000u >> sh)) | (nb16 << sh);
+              }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4 *>(gin.p + gin.at(n, 2 * yy + (q >> 1), gi, 2 * xx + (q & 1))) = *reinterpret_cast<uint4 *>(gw[q]);
+    } else {
     float go[8], v[4][8], gi4[4][8];
     load8<T>(gout.p + gout.at(n, yy, gi, xx), go);
 #pragma unroll
@@ -148,6 +216,7 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(View<T> xin, View<T> 
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) store8<T>(gin.p + gin.at(n, 2 * yy + (q >> 1), gi, 2 * xx + (q & 1)), gi4[q]);
+    }
   }
 }
 
@@ -159,9 +228,8 @@ __global__ void __launch_bounds__(256) upsample2_bwd_kernel(View<T> ghigh, View<
   const int G = glow.C / 8;
   const size_t total = (size_t)nb * glow.H * G * glow.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int xx = i % glow.W; size_t r = i / glow.W;
-    int gi = r % G; r /= G;
-    int yy = r % glow.H; int n = r / glow.H;
+    const RpIndex ri = rp_index(i, glow.W, G, glow.H);
+    const int xx = ri.x, gi = ri.g, yy = ri.y, n = ri.n;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a[8];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -189,9 +257,8 @@ __global__ void __launch_bounds__(256) add_views_kernel(View<T> dst, View<T> a, 
   const int G = dst.C / 8;
   const size_t total = (size_t)nb * dst.H * G * dst.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int xx = i % dst.W; size_t r = i / dst.W;
-    int gi = r % G; r /= G;
-    int yy = r % dst.H; int n = r / dst.H;
+    const RpIndex ri = rp_index(i, dst.W, G, dst.H);
+    const int xx = ri.x, gi = ri.g, yy = ri.y, n = ri.n;
     float u[8], v[8];
     load8<T>(a.p + a.at(n, yy, gi, xx), u);
     load8<T>(b.p + b.at(n, yy, gi, xx), v);
@@ -300,35 +367,53 @@ first_wgrad_kernel(const float *__restrict__ xnorm, View<T> dz, int nb, float *_
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[t][k] = 0.f;
   }
-  // MLP work items per trip: their 16-byte gradient loads are issued back to back, then each item's nine input taps (L1
-  // hits) are folded in; 128 registers -> two 256-thread blocks per SM
-  constexpr int MLP = 2;
-  for (int rc0 = slot; rc0 < nrc; rc0 += MLP * nslots) {
-    float d[MLP][8];
-    int yy[MLP], nn[MLP], xx[MLP];
+  // A warp walks a CONTIGUOUS range of (image, row, 32-pixel chunk) items, so coordinates advance by increments (no
+  // divisions per item) and consecutive chunks re-use the input rows in L1; interior chunks (warp-uniform test) read their
+  // nine input taps without bounds checks.  ncu on the strided, always-checked form: 227 instructions per item for 80 FMAs,
+  // 45 % issue slots at 25 % occupancy.  The 16-byte gradient load of the item PD steps ahead is issued into the register
+  // slot the current item has just been consumed from, so its HBM latency overlaps the FMAs of PD items.
+  constexpr int PD = 2;
+  const int per = (nrc + nslots - 1) / nslots;
+  const int rc_begin = min(nrc, slot * per), rc_end = min(nrc, rc_begin + per);
+  int cxc = rc_begin % xchunks, cy = (rc_begin / xchunks) % S, cn = (rc_begin / xchunks) / S;    // item being consumed
+  int pxc = cxc, py = cy, pn = cn;                                                                // item being prefetched
+  float d[PD][8];
+  auto fetch = [&](int j, bool live) {
+    const int x = pxc * 32 + lane;
+    if (live && x < S) load8<T>(dz.p + dz.at(pn, py, g, x), d[j]);
+    else {
 #pragma unroll
-    for (int j = 0; j < MLP; ++j) {
-      const int rc = rc0 + j * nslots;
-      const int xc = rc % xchunks; const int r = rc / xchunks;
-      yy[j] = r % S; nn[j] = r / S; xx[j] = xc * 32 + lane;
-      if (rc < nrc && xx[j] < S) load8<T>(dz.p + dz.at(nn[j], yy[j], g, xx[j]), d[j]);
-      else {
-        xx[j] = -4;                       // every tap out of range
-#pragma unroll
-        for (int k = 0; k < 8; ++k) d[j][k] = 0.f;
-      }
+      for (int k = 0; k < 8; ++k) d[j][k] = 0.f;
     }
+    if (++pxc == xchunks) { pxc = 0; if (++py == S) { py = 0; ++pn; } }
+  };
 #pragma unroll
-    for (int j = 0; j < MLP; ++j) {
+  for (int j = 0; j < PD; ++j) fetch(j, rc_begin + j < rc_end);
+  for (int rc = rc_begin; rc < rc_end; rc += PD) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) bs[k] += d[j][k];
-      if (xx[j] < 0) continue;
+    for (int j = 0; j < PD; ++j) {
+      if (rc + j < rc_end) {
+        const int x = cxc * 32 + lane;
+        float v[9];
+        const float *xc0 = xnorm + ((size_t)cn * S + cy) * S + x;
+        if (cy >= 1 && cy < S - 1 && cxc >= 1 && cxc * 32 + 32 < S) {
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int iy = yy[j] + t / 3 - 1, ix = xx[j] + t % 3 - 1;
-        const float v = (iy >= 0 && iy < S && ix >= 0 && ix < S) ? __ldg(xnorm + ((size_t)nn[j] * S + iy) * S + ix) : 0.f;
+          for (int t = 0; t < 9; ++t) v[t] = __ldg(xc0 + (t / 3 - 1) * S + (t % 3 - 1));
+        } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(v, d[j][k], acc[t][k]);
+          for (int t = 0; t < 9; ++t) {
+            const int iy = cy + t / 3 - 1, ix = x + t % 3 - 1;
+            v[t] = (iy >= 0 && iy < S && ix >= 0 && ix < S) ? __ldg(xc0 + (t / 3 - 1) * S + (t % 3 - 1)) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bs[k] += d[j][k];
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(v[t], d[j][k], acc[t][k]);
+        if (++cxc == xchunks) { cxc = 0; if (++cy == S) { cy = 0; ++cn; } }
+        fetch(j, rc + j + PD < rc_end);
       }
     }
   }

@@ -89,7 +89,9 @@ size_t bias_elems_of(adp_engine *e, const std::string &n) {
   return layer(e, n).cout;
 }
 
-int ew_grid(adp_engine *e, size_t n) { return (int)std::max<size_t>(1, std::min<size_t>(cdiv64(n, 256), (size_t)e->num_sms * 16)); }
+// one resident wave of 256-thread blocks for a grid-stride kernel over n items (adp_engine::wave_grid)
+template <typename K> int ew_grid(adp_engine *e, size_t n, K kern, size_t smem = 0) { return e->wave_grid(kern, (size_t)cdiv64((long long)n, 256), 256, smem); }
+int ew_grid(adp_engine *e, size_t n) { return (int)std::max<size_t>(1, std::min<size_t>(cdiv64(n, 256), (size_t)e->num_sms * 8)); }
 
 // theta -> every operand image the kernels read
 void repack_from_theta(adp_engine *e) {
@@ -303,19 +305,19 @@ template <typename T> struct Bwd {
   void relu_mask(View<T> g, View<T> x, float scale) {
     const size_t total = (size_t)nb * g.H * g.W * (g.C / 8);
     e->launch("relu_mask_bwd", 0, (double)total * 8 * sizeof(T) * 3, [&] {
-      relu_mask_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(g, x, nb, scale);
+      relu_mask_kernel<T><<<ew_grid(e, total, relu_mask_kernel<T>), 256, 0, e->stream>>>(g, x, nb, scale);
     });
   }
   void add(View<T> dst, View<T> a, View<T> b) {
     const size_t total = (size_t)nb * dst.H * dst.W * (dst.C / 8);
     e->launch("grad_add", 0, (double)total * 8 * sizeof(T) * 3, [&] {
-      add_views_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(dst, a, b, nb);
+      add_views_kernel<T><<<ew_grid(e, total, add_views_kernel<T>), 256, 0, e->stream>>>(dst, a, b, nb);
     });
   }
   void pool_bwd(View<T> xin, View<T> gout, View<T> gin) {
     const size_t total = (size_t)nb * gout.H * gout.W * (gout.C / 8);
     e->launch("maxpool2x2_bwd", 0, (double)total * 8 * sizeof(T) * 13, [&] {
-      maxpool2_bwd_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(xin, gout, gin, nb);
+      maxpool2_bwd_kernel<T><<<ew_grid(e, total, maxpool2_bwd_kernel<T>), 256, 0, e->stream>>>(xin, gout, gin, nb);
     });
   }
 
@@ -334,7 +336,7 @@ template <typename T> struct Bwd {
           xs = V(tr->g_hi, dz.H, L.cin_pad, 0, L.cin_pad);
           const size_t total = (size_t)nb * xs.H * xs.W * (xs.C / 8);
           e->launch("upsample2x2_materialise", 0, (double)total * 16 * 1.25, [&] {
-            upsample2_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(xin, xs, nb);
+            upsample2_kernel<T><<<ew_grid(e, total / 4, upsample2_kernel<T>), 256, 0, e->stream>>>(xin, xs, nb);
           });
         }
         WgradTcParams p = TL.wg;
@@ -398,7 +400,7 @@ template <typename T> struct Bwd {
       const size_t total = (size_t)nb * gin.H * gin.W * (gin.C / 8);
       View<T> none{}; none.p = nullptr;
       e->launch("upsample2x2_bwd", 0, (double)total * 8 * sizeof(T) * (mask ? 6 : 5), [&] {
-        upsample2_bwd_kernel<T><<<ew_grid(e, total), 256, 0, e->stream>>>(out, gin, nb, mask ? *mask : none, scale, resid ? *resid : none);
+        upsample2_bwd_kernel<T><<<ew_grid(e, total, upsample2_bwd_kernel<T>), 256, 0, e->stream>>>(out, gin, nb, mask ? *mask : none, scale, resid ? *resid : none);
       });
     } else if (!fused) {
       if (resid) add(gin, gin, *resid);
@@ -427,8 +429,12 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder, const 
     auto g = B.V(tr->g_u1c, S, cp[0], 0, cp[0]);
     ADP_CUDA(cudaMemsetAsync(tr->g_head.p, 0, (size_t)(cp[0] + 1) * 8, e->stream));
     const size_t total = (size_t)nb * S * S;
+    // one resident wave, rounded to a multiple of the channel-group count (a warp keeps one group: gridDim.x * 8 % G == 0)
+    const int G0 = cp[0] / 8;
+    const size_t hsm = (size_t)(2 * cp[0] + 1) * 4;
+    const int hgrid = std::max(1, e->wave_grid(head_bwd_kernel<T>, (size_t)cdiv64((long long)nb * S * G0, 8), 256, hsm) / G0) * G0;
     e->launch("head_bwd", 0, (double)total * (8 + 2.0 * cp[0] * sizeof(T)), [&] {
-      head_bwd_kernel<T><<<(int)cdiv64(total, 256), 256, (size_t)(2 * cp[0] + 1) * 4, e->stream>>>(
+      head_bwd_kernel<T><<<hgrid, 256, hsm, e->stream>>>(
           x, nb, e->w_head.as<float>(), tr->prob.as<float>(), tr->dldp.as<float>(), g, tr->g_head.as<double>(), tr->g_head.as<double>() + cp[0],
           inv_keep);
     });
@@ -578,7 +584,7 @@ void train_apply(adp_engine *e, int optimizer, float lr, float grad_scale, doubl
   const size_t n = tr->P - first;
   const float wd = optimizer == ADP_OPT_ADAMW ? weight_decay : 0.f;
   e->launch("adam_update", 0, (double)n * 28, [&] {
-    adam_kernel<<<ew_grid(e, n), 256, 0, e->stream>>>(tr->theta.as<float>() + first, tr->grad.as<float>() + first, tr->m.as<float>() + first,
+    adam_kernel<<<ew_grid(e, n, adam_kernel), 256, 0, e->stream>>>(tr->theta.as<float>() + first, tr->grad.as<float>() + first, tr->m.as<float>() + first,
                                                       tr->v.as<float>() + first, n, grad_scale, alpha, (float)(1.0 - beta1), (float)(1.0 - beta2), eps, wd, lr);
   });
   tr->iter = t;

@@ -10,17 +10,20 @@ def main():
     S = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 16
     prec = sys.argv[3] if len(sys.argv) > 3 else "bf16"
+    ops = list(range(8)) if (len(sys.argv) > 4 and sys.argv[4] == "tta") else None   # n tiles -> n/8 tiles x 8 augmentations
     eng = api.Engine(precision=prec, max_forwards=n)
     eng.set_weights(A.synth.init_weights())
     tiles = A.synth.ecm_tiles(min(n, 2), S)
     tiles = np.concatenate([tiles] * (n // len(tiles)))[:n]
+    if ops:
+        tiles = tiles[: max(1, n // 8)]
     import torch
     td = torch.from_numpy(tiles).cuda()
-    out = torch.empty((n, S, S), dtype=torch.float32, device="cuda")
+    out = torch.empty((len(tiles), S, S), dtype=torch.float32, device="cuda")
     for _ in range(2):
-        eng.predict(td, 127.5, 50.0, None, out)
+        eng.predict(td, 127.5, 50.0, ops, out)
     eng.profile(True)
-    eng.predict(td, 127.5, 50.0, None, out)
+    eng.predict(td, 127.5, 50.0, ops, out)
     rows = eng.profile_rows()
     eng.profile(False)
     tot = sum(r["ms"] for r in rows)
