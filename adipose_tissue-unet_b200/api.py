@@ -479,6 +479,36 @@ class GaussianBlender:
         return eng.blend(_lib.BLEND_GAUSSIAN, tiles, positions, output_shape, self.weight_map)
 
 
+class HannBlender:
+    """EXTENSION (not in the reference, which has only Gaussian and linear blenders): Hann-window blending as named by
+    BASELINE.json.  Weights h[y]*h[x], h[i] = 0.5 - 0.5*cos(2*pi*(i + 0.5)/tile) in float64 -> float32: the half-sample
+    shift keeps all weights positive (no zero weight sum on slide borders) and h[i] + h[i + tile/2] == 1 at 50 % overlap.
+    Same accumulate / normalise statements as GaussianBlender.reconstruct, so it runs on the same device kernels."""
+
+    def __init__(self, tile_size: int = 1024, engine: Optional[Engine] = None):
+        self.tile_size = tile_size
+        self.weight_map = self._create_hann_weight_map()
+        self._engine = engine
+
+    def _create_hann_weight_map(self) -> np.ndarray:
+        i = np.arange(self.tile_size, dtype=np.float64)
+        h = 0.5 - 0.5 * np.cos(2.0 * np.pi * (i + 0.5) / self.tile_size)
+        return np.outer(h, h).astype(np.float32)
+
+    def reconstruct(self, tiles, positions, output_shape) -> np.ndarray:
+        eng = self._engine or default_engine()
+        return eng.blend(_lib.BLEND_GAUSSIAN, tiles, positions, output_shape, self.weight_map)
+
+
+def blend_window(blend_mode: str, tile_size: int = 1024) -> Optional[np.ndarray]:
+    """Host window of a weighted blend mode ('gaussian', or the 'hann' extension); None for 'linear'."""
+    if blend_mode == "gaussian":
+        return GaussianBlender(tile_size).weight_map
+    if blend_mode == "hann":
+        return HannBlender(tile_size).weight_map
+    return None
+
+
 class LinearBlender:
     """full_evaluation_enhanced.LinearBlender (:186-204)."""
 
@@ -502,6 +532,8 @@ class SlidingWindowInference:
             self.blender = GaussianBlender(tile_size)
         elif blend_mode == "linear":
             self.blender = LinearBlender()
+        elif blend_mode == "hann":                      # extension, see HannBlender
+            self.blender = HannBlender(tile_size)
         else:
             self.blender = None
         if verbose:

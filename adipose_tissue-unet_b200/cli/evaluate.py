@@ -80,7 +80,8 @@ def build_parser():
     p.add_argument("--tta-mode", type=str, default="basic", choices=["minimal", "basic", "full"])
     p.add_argument("--sliding-window", action="store_true", default=False)
     p.add_argument("--overlap", type=float, default=0.5)
-    p.add_argument("--blend-mode", type=str, default="gaussian", choices=["gaussian", "linear", "none"])
+    p.add_argument("--blend-mode", type=str, default="gaussian", choices=["gaussian", "linear", "none", "hann"],
+                   help="gaussian / linear / none as in the reference; hann is an extension (api.HannBlender)")
     p.add_argument("--boundary-refine", action="store_true", default=False)
     p.add_argument("--refine-kernel", type=int, default=5)
     p.add_argument("--adaptive-threshold", action="store_true", default=False)

@@ -68,7 +68,8 @@ def build_parser():
     p.add_argument("--tile-size", type=int, default=1024)
     p.add_argument("--stride", type=int, default=512)
     p.add_argument("--threshold", type=float, default=0.5)
-    p.add_argument("--blend-mode", type=str, default="gaussian", choices=["gaussian", "linear"])
+    p.add_argument("--blend-mode", type=str, default="gaussian", choices=["gaussian", "linear", "hann"],
+                   help="gaussian / linear as in the reference; hann is an extension (api.HannBlender)")
     p.add_argument("--use-tta", action="store_true", default=False)
     p.add_argument("--tta-mode", type=str, default="basic", choices=["minimal", "basic", "full"])
     p.add_argument("--boundary-refine", action="store_true", default=False)
@@ -88,8 +89,8 @@ def reconstruct_slide(model, tiles_info, full_shape, tile_size, stride, mean, st
     from .. import api, _lib
     eng = model.engine
     H, W = full_shape
-    mode = _lib.BLEND_GAUSSIAN if blend_mode == "gaussian" else _lib.BLEND_LINEAR
-    window = api.GaussianBlender(tile_size, engine=eng).weight_map if blend_mode == "gaussian" else None
+    mode = _lib.BLEND_GAUSSIAN if blend_mode in ("gaussian", "hann") else _lib.BLEND_LINEAR
+    window = api.blend_window(blend_mode, tile_size)
     ops = api.TTA_OPCODES[tta_mode] if tta_mode else None
     eng.wsi_begin(H, W, 0, tile_size, mode, window)
     positions, gt_tiles, rgb_tiles = [], [], []

@@ -133,7 +133,7 @@ template <typename T> ADP_DEVINL void unpack8(const Raw8<T> &r, float *a) {
 // LDS.128) and every store is 512 contiguous bytes per channel group.
 constexpr int kFcRows = 4;
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 first_conv_kernel(FirstConvSrc src, const int *__restrict__ fw_tile, const int *__restrict__ fw_op,
                   int S, float mean_f, float sd_f, const float *__restrict__ w /*[9][C]*/,
                   const float *__restrict__ bias /*[C]*/, View<T> out) {

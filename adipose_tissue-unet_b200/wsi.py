@@ -105,7 +105,8 @@ def reconstruct_wsi(engine, slide_rows: Callable[[int, int], np.ndarray], h: int
     strips = plan_strips(h, w, tile, stride, world)
     me = strips[rank]
     ops = TTA_OPCODES[tta_mode] if tta_mode else None
-    mode = _lib.BLEND_GAUSSIAN if blend_mode == "gaussian" else _lib.BLEND_LINEAR
+    # 'gaussian' and the 'hann' extension are both window-weighted blends (the window is supplied by the caller)
+    mode = _lib.BLEND_GAUSSIAN if blend_mode in ("gaussian", "hann") else _lib.BLEND_LINEAR
     result = dict(prob=None, mask=None, counts=(0, 0, 0, 0), own=(me.own_lo, me.own_hi), tiles=len(me.tiles),
                   n_tiles_total=sum(len(s.tiles) for s in strips))
     import time as _t

@@ -224,9 +224,9 @@ def run_ours(args, rank, world, local_rank):
     wsi_res = None
     if args.wsi_size > 0:
         from adipose_unet_b200 import wsi as W
-        from adipose_unet_b200.api import GaussianBlender
+        from adipose_unet_b200.api import blend_window
         Hs = Ws = args.wsi_size
-        win = GaussianBlender(TILE).weight_map
+        win = blend_window(args.wsi_blend, TILE)
         blocks = {}
         def slide_rows(y0, rows):
             out = np.empty((rows, Ws), np.uint8)
@@ -241,7 +241,7 @@ def run_ours(args, rank, world, local_rank):
         for key in ((0, 0), (0, 1), (1, 0), (1, 1)):      # synthetic slide content is generated BEFORE the timed region
             blocks[key] = A.synth.slide_block(*key, TILE)
         def run_wsi():
-            return W.reconstruct_wsi(eng, slide_rows, Hs, Ws, tile=TILE, overlap=0.5, blend_mode="gaussian", window=win,
+            return W.reconstruct_wsi(eng, slide_rows, Hs, Ws, tile=TILE, overlap=0.5, blend_mode=args.wsi_blend, window=win,
                                      mean=mean, std=std, tta_mode="full", rank=rank, world=world, dist=dist,
                                      to_device=lambda a: torch.from_numpy(a).cuda(), want_prob=False, want_mask=True)
         W.warmup_peer_channels(dist, rank, world, local_rank)
@@ -253,7 +253,7 @@ def run_ours(args, rank, world, local_rank):
         tw = torch.tensor([dt_w], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        wsi_res = {"slide": f"{Hs}x{Ws}", "overlap": 0.5, "blend": "gaussian", "tta": "full(8)", "tiles": r["n_tiles_total"],
+        wsi_res = {"slide": f"{Hs}x{Ws}", "overlap": 0.5, "blend": args.wsi_blend + (" (extension: the reference has gaussian / linear only)" if args.wsi_blend == "hann" else ""), "tta": "full(8)", "tiles": r["n_tiles_total"],
                    "seconds": float(tw[0]), "mpx_per_s": Hs * Ws / 1e6 / float(tw[0]),
                    "includes": "host strip assembly (memcpy of pre-generated blocks) + H2D of the uint8 strip + all tiles (8 forwards each) + boundary exchange + normalise/threshold + mask D2H; wall clock, max over ranks"}
 
@@ -424,6 +424,8 @@ def main():
     ap.add_argument("--no-x3", action="store_true", help="skip the secondary bf16x3 (<= 1e-4 path) measurement")
     ap.add_argument("--train-batch", type=int, default=8, help="tiles per GPU of the secondary training-step run (0 = skip)")
     ap.add_argument("--train-dice", default="global", choices=["global", "replica"])
+    ap.add_argument("--wsi-blend", default="gaussian", choices=["gaussian", "linear", "hann"],
+                    help="blend window of the WSI run: gaussian / linear are the reference's blenders, hann is the labelled extension")
     ap.add_argument("--wsi-size", type=int, default=8192, help="side of the synthetic slide of the secondary WSI run (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -79,6 +79,29 @@ def gaussian_window(tile: int = 1024, sigma_factor: float = 0.25) -> np.ndarray:
     return w.astype(np.float32)
 
 
+# --------------------------------------------------------------------- G2x (extension, NOT in the reference)
+def hann_window(tile: int = 1024) -> np.ndarray:
+    """Hann blending window named by BASELINE.json's north_star; the reference has only Gaussian and linear
+    blenders, so this is a labelled extension with its own formula:
+
+        h[i] = 0.5 - 0.5 * cos(2*pi*(i + 0.5) / tile),  w[y, x] = h[y] * h[x]   (float64 -> float32)
+
+    The half-sample shift keeps every weight > 0 (np.hanning is 0 at both ends, which would leave the slide border
+    with a zero weight sum) and makes the window symmetric; at 50 % overlap h[i] + h[i + tile/2] == 1, so the weight
+    sum of interior pixels is 1 up to float32 rounding."""
+    i = np.arange(tile, dtype=np.float64)
+    h = 0.5 - 0.5 * np.cos(2.0 * np.pi * (i + 0.5) / tile)
+    return np.outer(h, h).astype(np.float32)
+
+
+def hann_reconstruct(tiles, positions, output_shape, window: np.ndarray = None, return_parts: bool = False):
+    """Weighted blend with the Hann window: same accumulation statement as GaussianBlender.reconstruct
+    (full_evaluation_enhanced.py:149-183), different weights."""
+    if window is None:
+        window = hann_window(tiles[0].shape[0])
+    return gaussian_reconstruct(tiles, positions, output_shape, window, return_parts)
+
+
 # --------------------------------------------------------------------- G3
 def gaussian_reconstruct(tiles, positions, output_shape, window: np.ndarray,
                          return_parts: bool = False):

@@ -49,6 +49,22 @@ def test_sliding_window_foreign_model_bit_exact(golden, fake_model, blend):
     np.testing.assert_array_equal(out, golden[f"sw_{blend}"])
 
 
+def test_hann_blender_extension_vs_oracle(golden, fake_model):
+    """Hann blending (extension): the device blend with the Hann window equals the oracle's statement bit for bit."""
+    np.testing.assert_array_equal(api.HannBlender(64).weight_map, G.hann_window(64))
+    np.testing.assert_array_equal(api.blend_window("hann", 1024), G.hann_window(1024))
+    tiles = [t.astype(np.float32) for t in golden["blend_a_tiles"]]
+    pos = [tuple(int(v) for v in p) for p in golden["blend_a_pos"]]
+    shape = tuple(int(v) for v in golden["blend_a_shape"])
+    np.testing.assert_array_equal(api.HannBlender(tile_size=64).reconstruct(tiles, pos, shape), G.hann_reconstruct(tiles, pos, shape))
+    sw = api.SlidingWindowInference(tile_size=64, overlap=0.5, blend_mode="hann", verbose=False)
+    out = sw.predict_with_sliding_window(golden["sw_img"], fake_model, 127.5, 50.0, use_tta=False)
+    img = golden["sw_img"]
+    positions = G.tile_positions(img.shape[0], img.shape[1], 64, G.stride_for(64, 0.5))
+    preds = [fake_model.predict_single(img[y:y + 64, x:x + 64], 127.5, 50.0) for (y, x) in positions]
+    np.testing.assert_array_equal(out, G.hann_reconstruct(preds, positions, img.shape[:2]))
+
+
 def test_blend_edge_cases(eng):
     # uncovered pixels -> 0 (weight_sum clamp), single tile, empty list
     win = G.gaussian_window(64)

@@ -123,3 +123,23 @@ def test_threshold_and_metrics(golden):
         m2 = G.metrics_from_counts(m["tp"], m["fp"], m["fn"], m["tn"])
         assert m2 == m
     assert G.prob_to_u8(np.array([0.0, 0.5, 0.999, 1.0], np.float32)).tolist() == [0, 127, 254, 255]
+
+
+def test_hann_window_extension_properties():
+    """Hann blending is an extension (the reference has Gaussian / linear only): formula h[i] = 0.5 - 0.5 cos(2 pi (i + 0.5) / T)."""
+    for T in (64, 1024):
+        w = G.hann_window(T)
+        assert w.dtype == np.float32 and w.shape == (T, T)
+        assert w.min() > 0.0                                    # no zero weights: slide borders keep a positive weight sum
+        np.testing.assert_array_equal(w, w[::-1, ::-1])         # symmetric (half-sample shift)
+        np.testing.assert_array_equal(w, w.T)
+        h = 0.5 - 0.5 * np.cos(2 * np.pi * (np.arange(T) + 0.5) / T)
+        np.testing.assert_allclose(h[: T // 2] + h[T // 2:], 1.0, atol=1e-15)   # partition of unity at 50 % overlap
+    # a constant field blends to the same constant everywhere, borders included; interior weight sum == 1
+    T, H, W = 64, 192, 256
+    pos = [(y, x) for y in range(0, H - T + 1, T // 2) for x in range(0, W - T + 1, T // 2)]
+    tiles = [np.full((T, T), 0.625, np.float32) for _ in pos]
+    res, acc, wsum = G.hann_reconstruct(tiles, pos, (H, W), return_parts=True)
+    np.testing.assert_allclose(res, 0.625, rtol=2e-6)
+    np.testing.assert_allclose(wsum[T // 2:H - T // 2, T // 2:W - T // 2], 1.0, rtol=1e-6)
+    assert wsum.min() > 0
