@@ -53,6 +53,7 @@ SIGNATURES = {
     "adp_debug_layer": (_I, [_P, C.c_char_p, _I, _P, _I64, C.POINTER(_I64)]),
     "adp_threshold_metrics": (_I, [_P, _P, _P, _I64, _F, _P, C.POINTER(_I64)]),
     "adp_threshold_sweep": (_I, [_P, _P, _P, _I64, _P, _I, _P]),
+    "adp_boundary_refine": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _F, _P]),
     "adp_blend_reconstruct": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
     "adp_wsi_begin": (_I, [_P, _I, _I, _I, _I, _I, _P]),
     "adp_wsi_push_tiles": (_I, [_P, _P, _I, _P, _P, _F, _F, C.POINTER(_I), _I]),

@@ -135,6 +135,20 @@ class Engine:
         _lib.check(self.lib.adp_threshold_sweep(self.h, _lib.ptr(prob), _lib.ptr(g), prob.size, _lib.ptr(thr), len(thr), _lib.ptr(counts)))
         return counts
 
+    def boundary_refine(self, mask, kernel_size: int = 5, bilateral_d: int = 5, sigma_color: float = 50.0,
+                        sigma_space: float = 50.0, out=None):
+        """BoundaryRefiner.refine on the device.  mask: (H,W) or (n,H,W) float32, host ndarray or CUDA torch tensor."""
+        is_np = isinstance(mask, np.ndarray)
+        if is_np:
+            mask = _f32c(mask)
+        shape = tuple(mask.shape)
+        n, (h, w) = (1, shape) if len(shape) == 2 else (shape[0], shape[1:])
+        if out is None:
+            out = np.empty(shape, np.float32)
+        _lib.check(self.lib.adp_boundary_refine(self.h, _lib.ptr(mask), n, h, w, int(kernel_size), int(bilateral_d),
+                                                float(sigma_color), float(sigma_space), _lib.ptr(out)))
+        return out
+
     def blend(self, mode: int, tiles: Sequence[np.ndarray], positions, output_shape, window: Optional[np.ndarray]):
         h, w = int(output_shape[0]), int(output_shape[1])
         out = np.empty((h, w), np.float32)
@@ -477,6 +491,24 @@ class GaussianBlender:
     def reconstruct(self, tiles, positions, output_shape) -> np.ndarray:
         eng = self._engine or default_engine()
         return eng.blend(_lib.BLEND_GAUSSIAN, tiles, positions, output_shape, self.weight_map)
+
+
+class BoundaryRefiner:
+    """full_evaluation_enhanced.BoundaryRefiner (:332-393): morphological boundary refinement of a [0,1] mask /
+    probability map, on the device (adp_boundary_refine).  `image` is accepted and unused, as in the reference."""
+
+    def __init__(self, kernel_size: int = 5, bilateral_d: int = 5, bilateral_sigma_color: float = 50,
+                 bilateral_sigma_space: float = 50, engine: Optional[Engine] = None):
+        self.kernel_size = kernel_size
+        self.bilateral_d = bilateral_d
+        self.sigma_color = bilateral_sigma_color
+        self.sigma_space = bilateral_sigma_space
+        self._engine = engine
+
+    def refine(self, mask: np.ndarray, image: Optional[np.ndarray] = None) -> np.ndarray:
+        eng = self._engine or default_engine()
+        return eng.boundary_refine(np.asarray(mask, dtype=np.float32), self.kernel_size, self.bilateral_d, self.sigma_color,
+                                   self.sigma_space)
 
 
 class HannBlender:

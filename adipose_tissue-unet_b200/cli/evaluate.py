@@ -4,7 +4,7 @@ Tiles are predicted in device batches (+TTA / sliding window), thresholding and 
 (adp_threshold_metrics) for the fixed threshold and for every candidate of the slide-level F1 search (:891-940); slide
 aggregation and the 10 000-sample bootstrap (:983-1018, RandomState(42)) are host statistics as in the reference.
 Outside this engine's scope and therefore reported as NaN in the results table: ROC/PR AUC (sklearn), Hausdorff95/ASSD
-(scipy EDT) and the matplotlib panels; --boundary-refine is accepted and reported as not applied."""
+(scipy EDT) and the matplotlib panels; --boundary-refine runs BoundaryRefiner.refine on the device (adp_boundary_refine)."""
 from __future__ import annotations
 
 import argparse
@@ -142,6 +142,9 @@ def predict_all(model, pairs, mean, std, args):
             el = time.time() - start
             print(f"  Processed {i + 1}/{len(pairs)} samples | Rate: {(i + 1) / el:.1f}/s")
     flush()
+    if args.boundary_refine:                      # BoundaryRefiner.refine on every prediction (:1574-1576), on the device
+        refiner = api.BoundaryRefiner(kernel_size=args.refine_kernel, engine=model.engine)
+        preds = [refiner.refine(p) for p in preds]
     print(f"✓ Inference completed in {(time.time() - start) / 60:.1f} minutes")
     return preds, gts
 
@@ -197,7 +200,7 @@ def main(argv=None) -> int:
     model = C.make_model(weights_file, args.precision, args.device, max(args.batch_tiles, 8))
     print("✓ Model loaded successfully")
     if args.boundary_refine:
-        print("⚠️  --boundary-refine: CPU post-filter of the reference, not applied by this engine")
+        print(f"✓ Boundary refinement enabled (kernel={args.refine_kernel})")
     print(f"\nRunning inference on {len(pairs)} samples...")
     preds, gts = predict_all(model, pairs, mean, std, args)
     paths = [p for p, _ in pairs]

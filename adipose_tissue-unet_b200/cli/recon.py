@@ -6,8 +6,8 @@ whole-slide accumulator (adp_wsi_*), the normalised probability map, mask and TP
 call.  The ground-truth and RGB mosaics are blends of given tiles (no network) and use adp_blend_reconstruct.
 Outputs keep the reference's names: {slide}/original_image.tif (BGR), prediction_mask.tif (probability*255),
 ground_truth_mask.tif, gt_overlay.png, pred_overlay.png, metrics.txt, metrics/{slide}_metrics.json, metrics/summary.csv,
-reconstruction_log.json.  Boundary refinement (--boundary-refine) is a CPU post-filter of the reference that this
-engine does not re-implement: the flag is accepted and reported as not applied."""
+reconstruction_log.json.  With --boundary-refine every tile prediction passes through BoundaryRefiner.refine on the device
+(adp_boundary_refine) before it is blended, as in reconstruct_full_images.py:378-380."""
 from __future__ import annotations
 
 import argparse
@@ -84,7 +84,8 @@ def build_parser():
     return p
 
 
-def reconstruct_slide(model, tiles_info, full_shape, tile_size, stride, mean, std, blend_mode, tta_mode, threshold, batch_tiles):
+def reconstruct_slide(model, tiles_info, full_shape, tile_size, stride, mean, std, blend_mode, tta_mode, threshold, batch_tiles,
+                      refine_kernel=None):
     """-> (rgb float32 [0,1], probability, ground truth or None, mask, (tp,fp,fn,tn) or None)."""
     from .. import api, _lib
     eng = model.engine
@@ -98,7 +99,11 @@ def reconstruct_slide(model, tiles_info, full_shape, tile_size, stride, mean, st
 
     def flush():
         if batch:
-            eng.wsi_push_tiles(np.stack(batch).astype(np.float32), ys, xs, mean, std, ops)
+            if refine_kernel:          # :372-380: predict (+TTA), BoundaryRefiner.refine per tile, then blend the refined tiles
+                probs = eng.predict(np.stack(batch).astype(np.float32), mean, std, ops)
+                eng.wsi_push_probs(eng.boundary_refine(probs, kernel_size=refine_kernel), ys, xs)
+            else:
+                eng.wsi_push_tiles(np.stack(batch).astype(np.float32), ys, xs, mean, std, ops)
             batch.clear(); ys.clear(); xs.clear()
 
     for row, col, img_path, mask_path in tiles_info:
@@ -142,7 +147,7 @@ def main(argv=None) -> int:
     model = C.make_model(weights_file, args.precision, args.device, max(args.batch_tiles, 8))
     print("✓ Model loaded successfully")
     if args.boundary_refine:
-        print("⚠️  --boundary-refine: CPU post-filter of the reference, not applied by this engine")
+        print(f"✓ Boundary refinement enabled (kernel={args.refine_kernel})")
     slides = group_tiles_by_slide(images_dir, masks_dir)
     print(f"✓ Found {len(slides)} slide(s)")
     tta_mode = args.tta_mode if args.use_tta else None
@@ -169,7 +174,8 @@ def main(argv=None) -> int:
             full_shape = infer_full_image_dimensions(positions, args.tile_size, args.stride)
         print(f"  Reconstructing {full_shape[1]}x{full_shape[0]} with {args.blend_mode} blending...")
         rgb, prob, gt, mask, counts = reconstruct_slide(model, tiles, full_shape, args.tile_size, args.stride, mean, std,
-                                                        args.blend_mode, tta_mode, args.threshold, args.batch_tiles)
+                                                        args.blend_mode, tta_mode, args.threshold, args.batch_tiles,
+                                                        args.refine_kernel if args.boundary_refine else None)
         sdir = output_dir / sid
         sdir.mkdir(parents=True, exist_ok=True)
         rgb8 = (rgb * 255).astype(np.uint8)
@@ -195,7 +201,7 @@ def main(argv=None) -> int:
             res = {"slide_id": sid,
                    "reconstruction": {"tiles_used": len(tiles), "tiles_missing": len(missing), "coverage_ratio": coverage,
                                       "blend_mode": args.blend_mode, "tta_enabled": args.use_tta,
-                                      "tta_mode": args.tta_mode if args.use_tta else None, "boundary_refined": False},
+                                      "tta_mode": args.tta_mode if args.use_tta else None, "boundary_refined": bool(args.boundary_refine)},
                    "dimensions": {"width": full_shape[1], "height": full_shape[0],
                                   "tiles_rows": info["row_range"][1] - info["row_range"][0] + 1,
                                   "tiles_cols": info["col_range"][1] - info["col_range"][0] + 1},
@@ -218,7 +224,7 @@ def main(argv=None) -> int:
         log = {"timestamp": datetime.now().isoformat(),
                "parameters": {"weights": str(args.weights), "data_root": str(args.data_root), "tile_size": args.tile_size, "stride": args.stride,
                               "threshold": args.threshold, "blend_mode": args.blend_mode, "use_tta": args.use_tta,
-                              "tta_mode": args.tta_mode if args.use_tta else None, "boundary_refine": False, "refine_kernel": None},
+                              "tta_mode": args.tta_mode if args.use_tta else None, "boundary_refine": bool(args.boundary_refine), "refine_kernel": args.refine_kernel if args.boundary_refine else None},
                "slides_processed": len(results), "slide_results": results,
                "summary_statistics": {"mean_dice": float(np.mean([r["metrics"]["dice_score"] for r in with_m])) if with_m else None,
                                       "mean_coverage": float(np.mean([r["reconstruction"]["coverage_ratio"] for r in results])),

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "kernels_post.cuh"
+#include "kernels_refine.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_train.cuh"
 #include "wgrad_tc.cuh"
@@ -1278,6 +1279,68 @@ int adp_threshold_sweep(adp_engine *e, const float *prob, const uint8_t *gt, int
     }
     counts[4 * j + 0] = (int64_t)tp; counts[4 * j + 1] = (int64_t)fp; counts[4 * j + 2] = (int64_t)fn; counts[4 * j + 3] = (int64_t)tn;
   }
+  ADP_CATCH
+}
+
+int adp_boundary_refine(adp_engine *e, const float *mask, int n, int H, int W, int kernel_size, int bilateral_d, float sigma_color,
+                        float sigma_space, float *out) {
+  ADP_TRY
+  ADP_REQUIRE(e && mask && out && n > 0 && H > 0 && W > 0, "null/empty argument");
+  ADP_REQUIRE(kernel_size >= 1 && kernel_size <= kRefineMaxK, "kernel_size 1..15");
+  ADP_REQUIRE(bilateral_d >= 1 && bilateral_d <= kRefineMaxD, "bilateral_d 1..9");
+  ADP_REQUIRE(sigma_color > 0.f && sigma_space > 0.f, "sigmas must be positive");
+  ADP_REQUIRE(H >= kRefineMaxD && W >= kRefineMaxD, "image smaller than the bilateral window");
+  ADP_CUDA(cudaSetDevice(e->device));
+  // cv2.getStructuringElement(MORPH_ELLIPSE, (k, k)): row i holds ones in [c - dx, c + dx], dx = round(c * sqrt((r^2 - dy^2) / r^2))
+  RefineSE se; se.n = 0;
+  {
+    const int r = kernel_size / 2, c = kernel_size / 2;
+    const double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+    for (int i = 0; i < kernel_size; ++i) {
+      const int dy = i - r;
+      if (std::abs(dy) > r) continue;
+      const int dx = (int)std::lrint(c * std::sqrt(((double)r * r - (double)dy * dy) * inv_r2));
+      for (int j = std::max(c - dx, 0); j < std::min(c + dx + 1, kernel_size); ++j) { se.dy[se.n] = (signed char)(i - r); se.dx[se.n] = (signed char)(j - c); ++se.n; }
+    }
+  }
+  // cv2.bilateralFilter taps: (i, j) with sqrt(i^2 + j^2) <= radius, row-major; weights rounded to float32 from double exp
+  RefineTaps bt; bt.n = 0;
+  {
+    const int radius = std::max(bilateral_d / 2, 1);
+    const double gs = -0.5 / ((double)sigma_space * sigma_space);
+    for (int i = -radius; i <= radius; ++i)
+      for (int j = -radius; j <= radius; ++j) {
+        const double rr = std::sqrt((double)i * i + (double)j * j);
+        if (rr > radius) continue;
+        bt.dy[bt.n] = (signed char)i; bt.dx[bt.n] = (signed char)j; bt.sw[bt.n] = (float)std::exp(rr * rr * gs); ++bt.n;
+      }
+  }
+  float cw[256];
+  {
+    const double gc = -0.5 / ((double)sigma_color * sigma_color);
+    for (int i = 0; i < 256; ++i) cw[i] = (float)std::exp((double)i * i * gc);
+  }
+  const size_t npx = (size_t)n * H * W;
+  DevBuf din, dout, ua, ub, dcw;
+  const float *m = reinterpret_cast<const float *>(to_device(e, din, mask, npx * 4));
+  const bool out_host = !is_device_ptr(out);
+  float *o = out;
+  if (out_host) { dout.ensure(npx * 4); o = dout.as<float>(); }
+  ua.ensure(npx); ub.ensure(npx); dcw.ensure(256 * 4);
+  ADP_CUDA(cudaMemcpyAsync(dcw.p, cw, 256 * 4, cudaMemcpyHostToDevice, e->stream));
+  uint8_t *A = ua.as<uint8_t>(), *B = ub.as<uint8_t>();
+  const dim3 grid(cdiv(W, 32), cdiv(H, 8), n), block(32, 8);
+  e->launch("refine_quantize", 0, (double)npx * 5, [&] {
+    refine_quantize_kernel<<<e->wave_grid(refine_quantize_kernel, cdiv64(npx, 256)), 256, 0, e->stream>>>(m, A, npx);
+  });
+  e->launch("refine_band_bilateral", 0, (double)npx * 2, [&] { refine_band_kernel<<<grid, block, 0, e->stream>>>(A, B, H, W, se, bt, dcw.as<float>()); });
+  // MORPH_OPEN = dilate(erode), MORPH_CLOSE = erode(dilate)  (:389-390); the last pass also writes refined / 255.0 (:393)
+  e->launch("refine_morph", 0, (double)npx * 2, [&] { refine_morph_kernel<true><<<grid, block, 0, e->stream>>>(B, A, nullptr, H, W, se); });
+  e->launch("refine_morph", 0, (double)npx * 2, [&] { refine_morph_kernel<false><<<grid, block, 0, e->stream>>>(A, B, nullptr, H, W, se); });
+  e->launch("refine_morph", 0, (double)npx * 2, [&] { refine_morph_kernel<false><<<grid, block, 0, e->stream>>>(B, A, nullptr, H, W, se); });
+  e->launch("refine_morph", 0, (double)npx * 6, [&] { refine_morph_kernel<true><<<grid, block, 0, e->stream>>>(A, B, o, H, W, se); });
+  if (out_host) ADP_CUDA(cudaMemcpyAsync(out, o, npx * 4, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
   ADP_CATCH
 }
 

@@ -132,6 +132,15 @@ int adp_threshold_metrics(adp_engine *e, const float *prob, const uint8_t *gt, i
 int adp_threshold_sweep(adp_engine *e, const float *prob, const uint8_t *gt, int64_t n_px, const float *thresholds, int n_thr,
                         int64_t *counts);
 
+/* ---- boundary refinement -------------------------------------------------------
+ * Replaces BoundaryRefiner.refine (full_evaluation_enhanced.py:332-393; callers :1575-1576 and
+ * reconstruct_full_images.py:378-380): mask_u8 = (mask*255).astype(uint8); band = (dilate > 0) xor (erode > 0) with the
+ * kernel_size x kernel_size MORPH_ELLIPSE element; bilateral filter (d, sigma_color, sigma_space) inside the band;
+ * MORPH_OPEN; MORPH_CLOSE; / 255.0.  mask, out: n images of H*W float32 (host or device).  kernel_size 1..15,
+ * bilateral_d 1..9.  The reference's unused `image` argument is not part of the call. */
+int adp_boundary_refine(adp_engine *e, const float *mask, int n, int H, int W, int kernel_size, int bilateral_d, float sigma_color,
+                        float sigma_space, float *out);
+
 /* ---- blenders ----------------------------------------------------------------------------------
  * Replaces GaussianBlender.reconstruct / LinearBlender.reconstruct
  * (full_evaluation_enhanced.py:149-204).  tiles: n tiles of th*tw float32, positions (y,x) in list

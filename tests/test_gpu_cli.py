@@ -106,3 +106,16 @@ def test_train_then_eval_infer_recon(workspace, capsys):
     want = G.gaussian_reconstruct(preds, [(0, 0), (0, 512)], (1024, 1536), G.gaussian_window(T))
     got = cv2.imread(str(sdir / "prediction_mask.tif"), cv2.IMREAD_UNCHANGED)
     assert np.abs(got.astype(np.int32) - (want * 255).astype(np.uint8).astype(np.int32)).max() <= 1
+
+    # the same slide with --boundary-refine (BoundaryRefiner.refine per tile before blending, reconstruct_full_images.py:378-380)
+    # and the Hann blending extension: against the oracle's refine + blend statements
+    from oracle import refine as R
+    rout2 = ws / "recon_refined"
+    rc = recon.main(["--weights", str(ck / "weights_best_overall.weights.h5"), "--data-root", str(val), "--output-dir", str(rout2),
+                     "--stride", "512", "--blend-mode", "hann", "--boundary-refine", "--refine-kernel", "5"])
+    assert rc == 0
+    log = json.loads((rout2 / "reconstruction_log.json").read_text())
+    assert log["parameters"]["boundary_refine"] is True and log["parameters"]["refine_kernel"] == 5
+    want2 = G.hann_reconstruct([R.refine(p) for p in preds], [(0, 0), (0, 512)], (1024, 1536), G.hann_window(T))
+    got2 = cv2.imread(str(rout2 / "slideA" / "prediction_mask.tif"), cv2.IMREAD_UNCHANGED)
+    assert np.abs(got2.astype(np.int32) - (want2 * 255).astype(np.uint8).astype(np.int32)).max() <= 1

@@ -176,3 +176,25 @@ def test_threshold_sweep_equals_per_threshold_counts():
         ref = G.pixel_metrics(p, gt, float(t))
         assert (ref["tp"], ref["fp"], ref["fn"], ref["tn"]) == counts
     assert (sweep.sum(axis=1) == n).all()
+
+
+@pytest.mark.parametrize("k", [3, 5, 9])
+def test_boundary_refine_vs_oracle_and_cv2(eng, k):
+    """adp_boundary_refine (BoundaryRefiner.refine, full_evaluation_enhanced.py:332-393): bit-exact against the restatement of
+    OpenCV's algorithms (oracle/refine.py); against the cv2 of the image within one grey level (its 8-bit bilateral path is
+    not bit-stable across builds) and with mask agreement."""
+    from oracle import refine as R
+    from refine_helpers import _blob_prob, reference_refine_cv2
+    probs = np.stack([_blob_prob(200, 264, 1), (_blob_prob(200, 264, 2) > 0.55).astype(np.float32), np.zeros((200, 264), np.float32)])
+    out = eng.boundary_refine(probs, kernel_size=k)
+    for i in range(len(probs)):
+        np.testing.assert_array_equal(out[i], R.refine(probs[i], kernel_size=k))
+        ref = reference_refine_cv2(probs[i], k=k)
+        assert np.abs(out[i] - ref).max() <= 1.0 / 255.0 + 1e-7
+        assert ((out[i] > 0.5) != (ref > 0.5)).mean() <= 1e-4
+    # device-resident input and output, reference-style object
+    td = torch.from_numpy(probs).cuda()
+    od = torch.empty_like(td)
+    eng.boundary_refine(td, kernel_size=k, out=od)
+    np.testing.assert_array_equal(od.cpu().numpy(), out)
+    np.testing.assert_array_equal(api.BoundaryRefiner(kernel_size=k, engine=eng).refine(probs[0], image=None), out[0])
