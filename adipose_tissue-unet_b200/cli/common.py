@@ -116,3 +116,46 @@ def add_engine_args(parser):
                         "(|dp| <= 1e-4); fp32 = exact CUDA-core path")
     g.add_argument("--device", type=int, default=0)
     g.add_argument("--batch-tiles", type=int, default=16, help="tiles per device batch")
+
+
+def prefetch(gen, depth: int = 2):
+    """tf.data's `dataset.prefetch(...)` of the reference's input pipeline (train_adipose_unet_v3.py:609-623): the generator
+    runs in a background thread `depth` items ahead, so JPEG decode / augmentation of the next batch overlaps the device
+    step of the current one (cv2 and the ctypes calls release the GIL).  Order is preserved; an exception raised by the
+    generator is re-raised in the consumer; abandoning the iterator early stops the producer."""
+    import queue
+    import threading
+    q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
+    stop = threading.Event()
+    _END, _ERR = object(), object()
+
+    def put(item) -> bool:
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def producer():
+        try:
+            for item in gen:
+                if not put(item):
+                    return
+            put(_END)
+        except BaseException as ex:          # noqa: BLE001 - handed to the consumer
+            put((_ERR, ex))
+
+    th = threading.Thread(target=producer, daemon=True)
+    th.start()
+    try:
+        while True:
+            item = q.get()
+            if item is _END:
+                return
+            if isinstance(item, tuple) and len(item) == 2 and item[0] is _ERR:
+                raise item[1]
+            yield item
+    finally:
+        stop.set()

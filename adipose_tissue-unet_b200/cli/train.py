@@ -234,7 +234,8 @@ def main(argv=None) -> int:
         for epoch in range(epochs):
             lr = T.cosine_warmup_lr(epoch, max_lr, min_lr, warm, epochs) if args.use_cosine_schedule else max_lr
             t0, losses, dices = time.time(), [], []
-            for step, (x, y) in enumerate(batches(train_ds, args.batch_size, rng, args.augmentation_level != "none", rank, world, True)):
+            # the next batch is decoded / augmented while the device runs this one (the reference's dataset.prefetch, :620)
+            for step, (x, y) in enumerate(C.prefetch(batches(train_ds, args.batch_size, rng, args.augmentation_level != "none", rank, world, True))):
                 if step >= steps_per_epoch:
                     break
                 out = trainer.step(x, y, lr)

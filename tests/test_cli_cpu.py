@@ -138,3 +138,30 @@ def test_train_dataset_normalisation_and_batches(tmp_path):
     thr = (a > 128).astype(np.float32)
     jpeg_ok = (thr == m).mean()
     assert jpeg_ok > 0.9            # JPEG noise moves a few pixels across 128; alignment keeps the rest identical
+
+
+def test_prefetch_keeps_order_propagates_errors_and_stops():
+    import threading
+    import time
+    from adipose_unet_b200.cli import common as C
+    assert list(C.prefetch(iter(range(50)), depth=3)) == list(range(50))
+    assert list(C.prefetch(iter(()))) == []
+
+    def bad():
+        yield 1
+        raise ValueError("decode failed")
+    it = C.prefetch(bad())
+    assert next(it) == 1
+    with pytest.raises(ValueError, match="decode failed"):
+        next(it)
+
+    produced = []
+    def slow():
+        for i in range(1000):
+            produced.append(i); yield i
+    n0 = threading.active_count()
+    it = C.prefetch(slow(), depth=2)
+    assert next(it) == 0
+    it.close()                                   # consumer leaves early (steps_per_epoch reached): the producer stops
+    time.sleep(0.5)
+    assert len(produced) <= 6 and threading.active_count() <= n0
