@@ -633,9 +633,17 @@ template <typename T>
 void run_dropout(adp_engine *e, const DevBuf &buf, int H, int C, int creal, int nb, const DropSpec &d, int site) {
   auto v = view<T>(buf, H, H, C, 0, C);
   const size_t total = (size_t)nb * H * H * (C / 8);
+  const uint64_t seed = d.seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(site + 1);
+  if (!d.mask[site] && total * 4 <= 0xFFFFFFFFull) {      // dense view (pitch == C, offset 0): item index == element offset / 8
+    const int grid = e->wave_grid(dropout_dense_kernel<T>, cdiv64(total, 256));
+    e->launch("dropout", 0, (double)total * 16 * sizeof(T), [&] {
+      dropout_dense_kernel<T><<<grid, 256, 0, e->stream>>>(v.p, (uint32_t)total, d.keep, seed);
+    });
+    return;
+  }
   const int grid = e->wave_grid(dropout_kernel<T>, cdiv64(total, 256));
   e->launch("dropout", 0, (double)total * 16 * sizeof(T), [&] {
-    dropout_kernel<T><<<grid, 256, 0, e->stream>>>(v, nb, d.keep, d.seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(site + 1), d.mask[site], creal);
+    dropout_kernel<T><<<grid, 256, 0, e->stream>>>(v, nb, d.keep, seed, d.mask[site], creal);
   });
 }
 

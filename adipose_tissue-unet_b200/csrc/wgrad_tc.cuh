@@ -225,10 +225,25 @@ __global__ void __launch_bounds__(256) upsample2_kernel(View<T> lo, View<T> hi, 
     const RpIndex ri = rp_index(i, lo.W, G, lo.H);
     if constexpr (sizeof(T) == 2) {
       const uint4 v = *reinterpret_cast<const uint4 *>(lo.p + lo.at(ri.n, ri.y, ri.g, ri.x));
-      T *o = hi.p + hi.at(ri.n, 2 * ri.y, ri.g, 2 * ri.x);
       const size_t rs = (size_t)hi.cgs * hi.W * 8;           // one output row further
-      reinterpret_cast<uint4 *>(o)[0] = v; reinterpret_cast<uint4 *>(o)[1] = v;
-      reinterpret_cast<uint4 *>(o + rs)[0] = v; reinterpret_cast<uint4 *>(o + rs)[1] = v;
+      if ((lo.W & 31) == 0) {
+        // a warp holds 32 consecutive source pixels of one row = 64 output pixels: lane l stores output pixels l and 32 + l
+        // (values of source lanes l/2 and 16 + l/2), so every store instruction covers 512 contiguous bytes.  (Each thread
+        // storing its own two adjacent 16-byte vectors made every instruction touch 32 half-written sectors: ncu lg_throttle 42.)
+        const int lane = threadIdx.x & 31;
+        uint4 a, b;
+        a.x = __shfl_sync(0xffffffffu, v.x, lane >> 1); a.y = __shfl_sync(0xffffffffu, v.y, lane >> 1);
+        a.z = __shfl_sync(0xffffffffu, v.z, lane >> 1); a.w = __shfl_sync(0xffffffffu, v.w, lane >> 1);
+        b.x = __shfl_sync(0xffffffffu, v.x, 16 + (lane >> 1)); b.y = __shfl_sync(0xffffffffu, v.y, 16 + (lane >> 1));
+        b.z = __shfl_sync(0xffffffffu, v.z, 16 + (lane >> 1)); b.w = __shfl_sync(0xffffffffu, v.w, 16 + (lane >> 1));
+        T *o = hi.p + hi.at(ri.n, 2 * ri.y, ri.g, 2 * (ri.x - lane) + lane);
+        *reinterpret_cast<uint4 *>(o) = a; *reinterpret_cast<uint4 *>(o + 32 * 8) = b;
+        *reinterpret_cast<uint4 *>(o + rs) = a; *reinterpret_cast<uint4 *>(o + rs + 32 * 8) = b;
+      } else {
+        T *o = hi.p + hi.at(ri.n, 2 * ri.y, ri.g, 2 * ri.x);
+        reinterpret_cast<uint4 *>(o)[0] = v; reinterpret_cast<uint4 *>(o)[1] = v;
+        reinterpret_cast<uint4 *>(o + rs)[0] = v; reinterpret_cast<uint4 *>(o + rs)[1] = v;
+      }
     } else {
       float a[8];
       load8<T>(lo.p + lo.at(ri.n, ri.y, ri.g, ri.x), a);
