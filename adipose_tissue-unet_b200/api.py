@@ -644,6 +644,35 @@ def metrics_from_counts(tp: int, fp: int, fn: int, tn: int) -> Dict[str, float]:
             "accuracy": float(accuracy), "tp": int(tp), "fp": int(fp), "fn": int(fn), "tn": int(tn)}
 
 
+def boundary_metrics_from_counts(tp: int, fp: int, fn: int, tn: int) -> Dict[str, float]:
+    """full_evaluation_enhanced.calculate_boundary_metrics (:788-844) from the four confusion counts.
+
+    The reference samples each mask's OWN distance transform on its OWN surface (`pred_dt[pred_surface]`,
+    `true_dt[true_surface]`, :829-830): `pred_dt = distance_transform_edt(~pred_bin)` is 0 on every pixel of `pred_bin`,
+    and a surface is a subset of its mask, so all sampled distances are 0 and both metrics are 0.0 whenever both
+    surfaces are non-empty.  What remains of the function is its case analysis, which the counts decide:
+    both masks empty -> 0.0; exactly one empty -> inf; a surface empty -> inf.  With skimage's binary_erosion
+    (3x3 cross, outside pixels count as foreground) a non-empty mask has an empty surface only when it covers the
+    whole image.  A drop-in follows the code as written, not the metric's name."""
+    pred_any, true_any = (tp + fp) > 0, (tp + fn) > 0
+    if not pred_any and not true_any:
+        return {"hausdorff95": 0.0, "assd": 0.0}
+    if not pred_any or not true_any:
+        return {"hausdorff95": float("inf"), "assd": float("inf")}
+    pred_all, true_all = (fn + tn) == 0, (fp + tn) == 0
+    if pred_all or true_all:
+        return {"hausdorff95": float("inf"), "assd": float("inf")}
+    return {"hausdorff95": 0.0, "assd": 0.0}
+
+
+def calculate_boundary_metrics(pred: np.ndarray, true: np.ndarray, threshold: float = 0.5, spacing=(1.0, 1.0),
+                               engine: Optional[Engine] = None) -> Dict[str, float]:
+    """full_evaluation_enhanced.calculate_boundary_metrics (:788-844): counts on the device, case analysis here
+    (see boundary_metrics_from_counts for why no distance transform is needed to reproduce the reference)."""
+    _, counts = (engine or default_engine()).threshold_metrics(pred, true, threshold, want_mask=False)
+    return boundary_metrics_from_counts(*counts)
+
+
 def calculate_pixel_metrics(pred: np.ndarray, true: np.ndarray, threshold: float = 0.5,
                             engine: Optional[Engine] = None) -> Dict[str, float]:
     """full_evaluation_enhanced.calculate_pixel_metrics (:721-785): counts on the device, ratios here."""

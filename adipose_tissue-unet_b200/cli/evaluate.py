@@ -3,8 +3,10 @@
 Tiles are predicted in device batches (+TTA / sliding window), thresholding and TP/FP/FN/TN run on the device
 (adp_threshold_metrics) for the fixed threshold and for every candidate of the slide-level F1 search (:891-940); slide
 aggregation and the 10 000-sample bootstrap (:983-1018, RandomState(42)) are host statistics as in the reference.
-Outside this engine's scope and therefore reported as NaN in the results table: ROC/PR AUC (sklearn), Hausdorff95/ASSD
-(scipy EDT) and the matplotlib panels; --boundary-refine runs BoundaryRefiner.refine on the device (adp_boundary_refine)."""
+Reported as NaN in the results table: ROC/PR AUC (sklearn statistics outside this engine).  Hausdorff95 / ASSD follow
+the reference's statements as written (api.boundary_metrics_from_counts: the reference samples each mask's own distance
+transform on its own surface, so the values are 0.0 / inf by case).  Not reproduced: the matplotlib panels (DESIGN.md
+section 6).  --boundary-refine runs BoundaryRefiner.refine on the device (adp_boundary_refine)."""
 from __future__ import annotations
 
 import argparse
@@ -216,14 +218,23 @@ def main(argv=None) -> int:
     else:
         thr = 0.5
         print(f"Using fixed threshold: {thr}")
+    from .. import api
     slides = defaultdict(list)
     for p, g, path in zip(preds, gts, paths):
-        slides[extract_slide_id(path)].append(tile_metrics(eng, p, g, thr))
+        m = tile_metrics(eng, p, g, thr)
+        m.update(api.boundary_metrics_from_counts(m["tp"], m["fp"], m["fn"], m["tn"]))   # calculate_boundary_metrics, :788-844
+        slides[extract_slide_id(path)].append(m)
     slide_vals = {k: np.array([np.mean([m[k] for m in tiles]) for tiles in slides.values()]) for k in METRIC_KEYS}
+
+    def finite_mean(tiles, key):                  # slide value = mean of the finite tile values, NaN if none (:1701-1708)
+        v = [m[key] for m in tiles if np.isfinite(m[key])]
+        return float(np.mean(v)) if v else float("nan")
+    for key in ("hausdorff95", "assd"):
+        slide_vals[key] = np.array([finite_mean(tiles, key) for tiles in slides.values()])
     print(f"✓ Calculated slide-level metrics for {len(slides)} slides\n\nCalculating bootstrap confidence intervals (n=10000)...")
-    summary = {k: bootstrap_ci(slide_vals[k]) for k in METRIC_KEYS}
+    summary = {k: bootstrap_ci(slide_vals[k]) for k in list(METRIC_KEYS) + ["hausdorff95", "assd"]}
     nan = (float("nan"), (float("nan"), float("nan")))
-    rows = [summary[k] for k in METRIC_KEYS] + [nan] * 4
+    rows = [summary[k] for k in METRIC_KEYS] + [nan] * 2 + [summary["hausdorff95"], summary["assd"]]
     table = out / f"{name}_comprehensive_results.csv"
     with open(table, "w", newline="") as f:
         w = csv.writer(f)

@@ -229,3 +229,27 @@ def metrics_from_counts(tp: int, fp: int, fn: int, tn: int, both_empty_rule: boo
     return dict(dice_score=float(f1), jaccard_index=float(jaccard), sensitivity=float(sensitivity),
                 specificity=float(specificity), precision=float(precision), f1_score=float(f1),
                 accuracy=float(accuracy), tp=int(tp), fp=int(fp), fn=int(fn), tn=int(tn))
+
+
+# --------------------------------------------------------------------- boundary metrics
+def boundary_metrics_reference(pred: np.ndarray, true: np.ndarray, threshold: float = 0.5) -> dict:
+    """Segmentation/full_evaluation_enhanced.py:788-844 statement by statement, with scipy.ndimage for the distance
+    transform and for skimage.morphology.binary_erosion (skimage is not in this image; its published definition is
+    ndimage.binary_erosion with the 3x3 cross footprint and border_value=True - unpinned).  Note :829-830: each mask's own
+    distance transform is sampled on its own surface."""
+    from scipy import ndimage
+    pred_bin = pred > threshold
+    true_bin = true > 0.5
+    if not pred_bin.any() and not true_bin.any():
+        return {"hausdorff95": 0.0, "assd": 0.0}
+    if not pred_bin.any() or not true_bin.any():
+        return {"hausdorff95": float("inf"), "assd": float("inf")}
+    pred_dt = ndimage.distance_transform_edt(~pred_bin, sampling=(1.0, 1.0))
+    true_dt = ndimage.distance_transform_edt(~true_bin, sampling=(1.0, 1.0))
+    cross = ndimage.generate_binary_structure(2, 1)
+    pred_surface = pred_bin & ~ndimage.binary_erosion(pred_bin, structure=cross, border_value=1)
+    true_surface = true_bin & ~ndimage.binary_erosion(true_bin, structure=cross, border_value=1)
+    if pred_surface.sum() > 0 and true_surface.sum() > 0:
+        allv = np.concatenate([pred_dt[pred_surface], true_dt[true_surface]])
+        return {"hausdorff95": float(np.percentile(allv, 95)), "assd": float(np.mean(allv))}
+    return {"hausdorff95": float("inf"), "assd": float("inf")}

@@ -143,3 +143,21 @@ def test_hann_window_extension_properties():
     np.testing.assert_allclose(res, 0.625, rtol=2e-6)
     np.testing.assert_allclose(wsum[T // 2:H - T // 2, T // 2:W - T // 2], 1.0, rtol=1e-6)
     assert wsum.min() > 0
+
+
+def test_boundary_metrics_case_analysis_matches_reference_statement():
+    """calculate_boundary_metrics as written in the reference (own distance transform on own surface) reduces to a case
+    analysis on the confusion counts: api.boundary_metrics_from_counts against the literal scipy restatement."""
+    from adipose_unet_b200.api import boundary_metrics_from_counts
+    rng = np.random.default_rng(5)
+    h, w = 48, 64
+    blobs = rng.random((h, w))
+    cases = [(np.zeros((h, w)), np.zeros((h, w))), (np.ones((h, w)), np.zeros((h, w))), (np.zeros((h, w)), np.ones((h, w))),
+             (np.ones((h, w)), np.ones((h, w))), (np.ones((h, w)), (blobs > 0.5) * 1.0), ((blobs > 0.3) * 1.0, np.ones((h, w))),
+             (blobs, (rng.random((h, w)) > 0.6) * 1.0), ((blobs > 0.9) * 0.8, (blobs > 0.2) * 1.0)]
+    edge = np.zeros((h, w)); edge[0, :] = 1.0; edge[:, -1] = 1.0            # touches the border only
+    cases.append((edge, edge.T[:h, :w] if edge.T.shape == (h, w) else edge[::-1]))
+    for pred, true in cases:
+        pb, tb = pred > 0.5, true > 0.5
+        counts = (int((pb & tb).sum()), int((pb & ~tb).sum()), int((~pb & tb).sum()), int((~pb & ~tb).sum()))
+        assert boundary_metrics_from_counts(*counts) == G.boundary_metrics_reference(pred.astype(np.float32), true.astype(np.float32))
