@@ -116,3 +116,34 @@ def test_nccl_strips_equal_single_gpu():
     diff = sum(abs(a - b) for a, b in zip(r1["counts_tp_fp_fn_tn"], r2["counts_tp_fp_fn_tn"]))
     print("1-GPU vs 2-GPU counts", r1["counts_tp_fp_fn_tn"], r2["counts_tp_fp_fn_tn"])
     assert diff <= 1e-5 * 4096 * 4096
+
+
+@pytest.mark.parametrize("overlap,tta", [(0.5, "full"), (0.75, "minimal")])
+def test_wsi_full_tile_size_periodicity_property(overlap, tta):
+    """BASELINE-sized tiles (1024^2, the configs[2] / configs[4] geometry) on a slide too large for the CPU oracle: a
+    size-independent property instead.  The slide repeats with period 2048 in x; interior pixels (more than one tile away
+    from the slide border) that are 2048 apart are covered by tiles with identical content, identical relative geometry and
+    identical blend order, so the blended probabilities must be IDENTICAL bit for bit - any slip in tile indexing, TTA
+    un-flip, window addressing or accumulation order breaks it.  Also: mask == (prob > thr), counts add up to H*W."""
+    T = 1024
+    H, W = 3 * T, 6 * T
+    blocks = {(a, b): A.synth.slide_block(a, b, T) for a in (0, 1) for b in (0, 1)}
+    slide = np.empty((H, W), np.uint8)
+    for by in range(H // T):
+        for bx in range(W // T):
+            slide[by * T:(by + 1) * T, bx * T:(bx + 1) * T] = blocks[(by % 2, bx % 2)]
+    gt = (slide > 150).astype(np.uint8)
+    eng = api.Engine(precision="bf16", max_forwards=16)
+    eng.set_weights(A.synth.init_weights())
+    r = wsi.reconstruct_wsi(eng, lambda y0, n: slide[y0:y0 + n], H, W, tile=T, overlap=overlap, blend_mode="gaussian",
+                            window=G.gaussian_window(T), mean=MEAN, std=STD, tta_mode=tta, gt_rows=lambda y0, n: gt[y0:y0 + n],
+                            rank=0, world=1, dist=None, to_device=lambda a: torch.from_numpy(a).cuda())
+    prob, mask, counts = r["prob"], r["mask"], r["counts"]
+    stride = G.stride_for(T, overlap)
+    assert r["n_tiles_total"] == len(G.tile_positions(H, W, T, stride))
+    assert prob.shape == (H, W) and np.isfinite(prob).all() and 0.0 <= prob.min() and prob.max() <= 1.0
+    np.testing.assert_array_equal(prob[T:H - T, T:3 * T], prob[T:H - T, 3 * T:5 * T])
+    np.testing.assert_array_equal(mask, (prob > 0.5).astype(np.uint8))
+    assert int(np.sum(counts)) == H * W
+    m = G.pixel_metrics(prob, gt, 0.5)
+    assert tuple(int(c) for c in counts) == (m["tp"], m["fp"], m["fn"], m["tn"])
