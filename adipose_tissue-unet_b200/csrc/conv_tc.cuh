@@ -38,12 +38,15 @@
 //
 // bf16x3 precision (p.split): see ConvTcParams - three chunks per 16 input channels, hi/lo stores in the epilogue.
 //
-// Warp roles (320 threads): w0 producer (TMA + bulk copy), w1 MMA issuer (one elected lane) and
+// Warp roles (352 threads): w0 producer (TMA + bulk copy), w1 MMA issuer A (one elected lane) and
 // TMEM allocator, w2-9 epilogue: two warps per TMEM lane quarter, software-pipelined
-// tcgen05.ld -> bias -> ReLU -> bf16 -> coalesced row-planar stores.  Fused epilogues:
+// tcgen05.ld -> bias -> ReLU -> bf16 -> coalesced row-planar stores, w10 MMA issuer B (the two issuers
+// alternate work items, see the issuer comment below).  Fused epilogues:
 //   EPI_HEAD  Conv2D(2,1x1,softmax)[...,1] of train_adipose_unet_v3.py:748-750 on the fp32 accumulators
 //             of up1_conv3 (the 44-channel activation never reaches HBM),
-//   EPI_POOL  MaxPooling2D(2x2) (train_adipose_unet_v3.py:670,674) written next to the skip tensor.
+//   EPI_POOL  MaxPooling2D(2x2) (train_adipose_unet_v3.py:670,674) written next to the skip tensor,
+//   EPI_BWD   data-gradient twin of the training step: (acc + residual) * [mask > 0] * scale, the mask tile staged in
+//             shared memory by a TMA box per item for accumulators up to 96 wide (ConvTcParams::mask_bufs).
 #pragma once
 #include "ptx.cuh"
 
@@ -119,7 +122,7 @@ __host__ __device__ inline size_t tc_block_index(int kys, int ntaps, int N, int 
 }
 
 size_t tc_smem_bytes(const ConvTcParams &p) {
-  // stages | mbarriers (2S + 4) + tmem slot | bias (704 floats) | head weights (2*256 + 2 floats)
+  // stages | mask tile buffers (EPI_BWD) | mbarriers (2S + 8) + tmem slot | bias (704 floats) | head weights (2*256 + 2 floats)
   return (size_t)p.S * p.stage_stride + (size_t)p.mask_bufs * p.mask_bytes + (2 * p.S + 6 + 4) * 8 + (704 + 520) * 4;
 }
 
