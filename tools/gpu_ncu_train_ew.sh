@@ -4,7 +4,9 @@
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { cat gpurun_out/build.log; exit 1; }
 CMD="python tools/train_profile.py 1024 8 bf16"
-ncu --set full --clock-control none -k regex:"maxpool2_bwd_kernel|upsample2_kernel|upsample2_bwd_kernel|dropout_kernel|first_wgrad_kernel|head_bwd_kernel|loss_reduce_kernel|first_conv_kernel" -s 85 -c 17 -o gpurun_out/prof_ew $CMD > gpurun_out/ncu_ew.log 2>&1
+# KREGEX / SKIP / COUNT select other kernels (defaults: 17 launches of the sixth step = the profiled one)
+KREGEX=${KREGEX:-"maxpool2_bwd_kernel|upsample2_kernel|upsample2_bwd_kernel|dropout_kernel|dropout_dense_kernel|first_wgrad_kernel|head_bwd_kernel|loss_reduce_kernel|first_conv_kernel"}
+ncu --set full --clock-control none -k regex:"$KREGEX" -s ${SKIP:-85} -c ${COUNT:-17} -o gpurun_out/prof_ew $CMD > gpurun_out/ncu_ew.log 2>&1
 echo "capture rc=$?"
 ncu -i gpurun_out/prof_ew.ncu-rep --page raw --csv > gpurun_out/prof_ew_raw.csv 2>/dev/null
 python - <<'PY'
