@@ -544,7 +544,17 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder, const 
     const size_t total = (size_t)nb * S * S;
     const int G0 = cp[0] / 8;
     const int grid = G0 * std::max(1, std::min(e->num_sms * 2 / G0, (int)cdiv64((long long)nb * S * cdiv(S, 32), 8)));
+    bool on_tensor_cores = false;
+    if constexpr (sizeof(T) == 2) on_tensor_cores = e->prec == ADP_PREC_BF16 && !e->wgrad_simt;
     e->launch("first_conv_wgrad", 2.0 * total * 9 * e->c[0], (double)total * (4 + cp[0] * sizeof(T)), [&] {
+      if constexpr (sizeof(T) == 2) {
+        if (on_tensor_cores) {     // nine taps + ones row as GEMM-M of mma.sync (kernels_train.cuh); one resident wave, a multiple of G0 blocks
+          const int mgrid = std::max(1, e->wave_grid(first_wgrad_mma_kernel, (size_t)cdiv64((long long)nb * S * cdiv(S, 32), 8)) / G0) * G0;
+          first_wgrad_mma_kernel<<<mgrid, 256, 0, e->stream>>>(tr->x.as<float>(), B.V(tr->g_d1a, S, cp[0], 0, cp[0]), nb,
+                                                                tr->gw_first.as<float>(), tr->gb_first.as<float>());
+          return;
+        }
+      }
       first_wgrad_kernel<T><<<grid, 256, 0, e->stream>>>(tr->x.as<float>(), B.V(tr->g_d1a, S, cp[0], 0, cp[0]), nb,
                                                                               tr->gw_first.as<float>(), tr->gb_first.as<float>());
     });
