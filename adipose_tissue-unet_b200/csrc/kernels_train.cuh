@@ -463,16 +463,18 @@ first_wgrad_kernel(const float *__restrict__ xnorm, View<T> dz, int nb, float *_
 // Fragment layout of mma.m16n8k16 (PTX ISA): group = lane / 4, t = lane % 4;
 //   A regs: {row group, cols 2t,2t+1}, {row group + 8, same cols}, {row group, cols 2t+8,2t+9}, {row group + 8, cols 2t+8,2t+9}
 //   B regs: {k = 2t,2t+1; n = group}, {k = 2t+8,2t+9; n = group};  D: {row group, cols 2t,2t+1}, {row group + 8, same cols}.
-// Work split as in first_wgrad_kernel: a warp keeps one channel group and walks a contiguous range of (image, row,
-// 32-pixel chunk) items.
 ADP_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t *>(&v);
 }
-// dZ streams through a per-warp ring of kFwStages x 512-byte shared-memory slots filled with cp.async (16 bytes per lane =
-// one pixel's channel group), kFwStages - 1 chunks ahead: shared memory, not registers, holds the bytes in flight (with
-// the direct 2-byte fragment loads a warp had 512 B outstanding -> 16 KB per SM -> 1.2 TB/s, Little's law).
-constexpr int kFwStages = 8;
+// A warp owns a contiguous range of (image, row, 32-pixel chunk) items for ALL channel groups: the A fragments (input taps)
+// are built once per chunk and feed one MMA per channel group (a warp per channel group re-read the input rows G times
+// through L2: 0.73 ms).  dZ streams through a per-warp ring of kFwStages slots of G x 512 bytes in shared memory, filled
+// with cp.async (16 bytes per lane = one pixel's channel group) kFwStages - 1 chunks ahead: shared memory, not registers,
+// holds the bytes in flight.
+constexpr int kFwStages = 3;
+constexpr int kFwMaxG = 8;                                   // init_nb <= 64 channels
+inline size_t first_wgrad_mma_smem(int G) { return (size_t)8 * kFwStages * G * 512; }
 ADP_DEVINL void cp_async16_zfill(uint32_t dst_smem, const void *src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -480,53 +482,54 @@ __global__ void __launch_bounds__(256)
 first_wgrad_mma_kernel(const float *__restrict__ xnorm, View<__nv_bfloat16> dz, int nb, float *__restrict__ dW /*[9][C]*/,
                        float *__restrict__ db) {
   __shared__ float red[10][64];
-  __shared__ __align__(16) uint8_t zring[8 * kFwStages * 512];
+  extern __shared__ __align__(16) uint8_t zring[];           // [8 warps][kFwStages][G][32 pixels][8 channels] bf16
   const int C = dz.C, S = dz.H, G = C / 8;
   for (int i = threadIdx.x; i < 10 * 64; i += blockDim.x) (&red[0][0])[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, grp = lane >> 2, t4 = lane & 3;
   const int wid = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int nw = (int)(((long long)gridDim.x * blockDim.x) >> 5);
-  const int g = wid % G;                        // gridDim.x * 8 is a multiple of G
-  const int slot = wid / G, nslots = nw / G;
   const int xchunks = (S + 31) / 32;
   const int nrc = nb * S * xchunks;
-  const int per = (nrc + nslots - 1) / nslots;
-  const int rc_begin = min(nrc, slot * per), rc_end = min(nrc, rc_begin + per);
+  const int per = (nrc + nw - 1) / nw;
+  const int rc_begin = min(nrc, wid * per), rc_end = min(nrc, rc_begin + per);
   int cxc = rc_begin % xchunks, cy = (rc_begin / xchunks) % S, cn = (rc_begin / xchunks) / S;    // chunk being consumed
   int pxc = cxc, py = cy, pn = cn;                                                                // chunk being prefetched
-  uint8_t *wz = zring + (size_t)(threadIdx.x >> 5) * kFwStages * 512;
+  const uint32_t stage_bytes = (uint32_t)G * 512u;
+  uint8_t *wz = zring + (size_t)(threadIdx.x >> 5) * kFwStages * stage_bytes;
   const uint32_t wz_u32 = (uint32_t)__cvta_generic_to_shared(wz);
   auto prefetch = [&](int stage, bool live) {
     const int p = pxc * 32 + lane;
     const bool ok = live && p < S;
-    const void *src = ok ? (const void *)(dz.p + dz.at(pn, py, g, p)) : (const void *)dz.p;
-    cp_async16_zfill(wz_u32 + (uint32_t)(stage * 512 + lane * 16), src, ok ? 16u : 0u);      // 0 source bytes = zero fill
+    const __nv_bfloat16 *src = ok ? dz.p + dz.at(pn, py, 0, p) : dz.p;
+    const size_t gstride = (size_t)dz.W * 8;                 // next channel group of the same pixel row
+    for (int gg = 0; gg < G; ++gg)
+      cp_async16_zfill(wz_u32 + (uint32_t)stage * stage_bytes + (uint32_t)(gg * 512 + lane * 16), ok ? (const void *)(src + gg * gstride) : (const void *)dz.p,
+                       ok ? 16u : 0u);                       // 0 source bytes = zero fill
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     if (++pxc == xchunks) { pxc = 0; if (++py == S) { py = 0; ++pn; } }
   };
 #pragma unroll
   for (int j = 0; j < kFwStages - 1; ++j) prefetch(j, rc_begin + j < rc_end);
   const int dy = grp / 3 - 1, dx = grp % 3 - 1;             // tap of A row `grp` (grp = 0..7); row 8 = tap (+1,+1)
-  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+  float c[kFwMaxG][4];
+#pragma unroll
+  for (int gg = 0; gg < kFwMaxG; ++gg) { c[gg][0] = 0.f; c[gg][1] = 0.f; c[gg][2] = 0.f; c[gg][3] = 0.f; }
   int st = 0;                                               // ring slot of the chunk being consumed
   for (int rc = rc_begin; rc < rc_end; ++rc) {
     prefetch(st == 0 ? kFwStages - 1 : st - 1, rc + kFwStages - 1 < rc_end);
     asm volatile("cp.async.wait_group %0;\n" ::"n"(kFwStages - 1) : "memory");
     __syncwarp();
     const float *xrow = xnorm + ((size_t)cn * S + cy) * S;
-    const unsigned short *zs = reinterpret_cast<const unsigned short *>(wz + st * 512) + grp;     // [32 pixels][8 channels]
     const bool interior = cy >= 1 && cy < S - 1 && cxc >= 1 && cxc * 32 + 32 < S;
+    uint32_t a[2][4];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      const int pl = 16 * s + 2 * t4;                        // this lane's pixel pairs (pl, pl+1) and (pl+8, pl+9) within the chunk
-      const int px = cxc * 32 + pl;
+      const int px = cxc * 32 + 16 * s + 2 * t4;             // this lane's pixel pairs (px, px+1) and (px+8, px+9)
       float xa[4], xb[4];                                    // taps `grp` and 8 at those four pixels
-      unsigned short z[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int o = (q & 1) + 8 * (q >> 1), p = px + o;
-        z[q] = zs[(pl + o) * 8];                             // zero-filled beyond the row end
+        const int p = px + (q & 1) + 8 * (q >> 1);
         if (interior) {
           xa[q] = __ldg(xrow + dy * S + p + dx);
           xb[q] = grp == 0 ? __ldg(xrow + S + p + 1) : 0.f;
@@ -536,14 +539,24 @@ first_wgrad_mma_kernel(const float *__restrict__ xnorm, View<__nv_bfloat16> dz, 
           xb[q] = (grp == 0 && p < S && cy + 1 < S && p + 1 < S) ? __ldg(xrow + S + p + 1) : 0.f;
         }
       }
-      const uint32_t a0 = pack_bf16x2(xa[0], xa[1]), a2 = pack_bf16x2(xa[2], xa[3]);
-      uint32_t a1 = 0u, a3 = 0u;
-      if (grp == 0) { a1 = pack_bf16x2(xb[0], xb[1]); a3 = pack_bf16x2(xb[2], xb[3]); }
-      else if (grp == 1) { a1 = 0x3F803F80u; a3 = 0x3F803F80u; }                   // row 9 = ones -> bias gradient
-      const uint32_t b0 = (uint32_t)z[0] | ((uint32_t)z[1] << 16), b1 = (uint32_t)z[2] | ((uint32_t)z[3] << 16);
-      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-                   : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
-                   : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+      a[s][0] = pack_bf16x2(xa[0], xa[1]); a[s][2] = pack_bf16x2(xa[2], xa[3]);
+      a[s][1] = 0u; a[s][3] = 0u;
+      if (grp == 0) { a[s][1] = pack_bf16x2(xb[0], xb[1]); a[s][3] = pack_bf16x2(xb[2], xb[3]); }
+      else if (grp == 1) { a[s][1] = 0x3F803F80u; a[s][3] = 0x3F803F80u; }         // row 9 = ones -> bias gradient
+    }
+    const unsigned short *zs = reinterpret_cast<const unsigned short *>(wz + (size_t)st * stage_bytes) + grp;   // [G][32 pixels][8 channels]
+#pragma unroll
+    for (int gg = 0; gg < kFwMaxG; ++gg) {
+      if (gg < G) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const unsigned short *zp = zs + gg * 256 + (16 * s + 2 * t4) * 8;       // zero-filled beyond the row end
+          const uint32_t b0 = (uint32_t)zp[0] | ((uint32_t)zp[8] << 16), b1 = (uint32_t)zp[64] | ((uint32_t)zp[72] << 16);
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                       : "+f"(c[gg][0]), "+f"(c[gg][1]), "+f"(c[gg][2]), "+f"(c[gg][3])
+                       : "r"(a[s][0]), "r"(a[s][1]), "r"(a[s][2]), "r"(a[s][3]), "r"(b0), "r"(b1));
+        }
+      }
     }
     __syncwarp();                                            // the slot is refilled by the next iteration's prefetch
     if (++st == kFwStages) st = 0;
@@ -551,14 +564,19 @@ first_wgrad_mma_kernel(const float *__restrict__ xnorm, View<__nv_bfloat16> dz, 
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   // D rows: grp -> tap grp (c0, c1), grp + 8 -> tap 8 (grp == 0) or bias (grp == 1) (c2, c3); columns = channels 2*t4, 2*t4 + 1
-  const int ch = g * 8 + 2 * t4;
-  atomicAdd(&red[grp][ch], c0); atomicAdd(&red[grp][ch + 1], c1);
-  if (grp < 2) { atomicAdd(&red[8 + grp][ch], c2); atomicAdd(&red[8 + grp][ch + 1], c3); }
+#pragma unroll
+  for (int gg = 0; gg < kFwMaxG; ++gg) {
+    if (gg < G) {
+      const int ch = gg * 8 + 2 * t4;
+      atomicAdd(&red[grp][ch], c[gg][0]); atomicAdd(&red[grp][ch + 1], c[gg][1]);
+      if (grp < 2) { atomicAdd(&red[8 + grp][ch], c[gg][2]); atomicAdd(&red[8 + grp][ch + 1], c[gg][3]); }
+    }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) {
-    const int r = i / C, c = i - r * C;
-    const float v = red[r][c];
-    if (v != 0.f) atomicAdd(r < 9 ? &dW[r * C + c] : &db[c], v);
+    const int r = i / C, cc = i - r * C;
+    const float v = red[r][cc];
+    if (v != 0.f) atomicAdd(r < 9 ? &dW[r * C + cc] : &db[cc], v);
   }
 }
 

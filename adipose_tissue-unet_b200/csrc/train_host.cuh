@@ -548,9 +548,11 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder, const 
     if constexpr (sizeof(T) == 2) on_tensor_cores = e->prec == ADP_PREC_BF16 && !e->wgrad_simt;
     e->launch("first_conv_wgrad", 2.0 * total * 9 * e->c[0], (double)total * (4 + cp[0] * sizeof(T)), [&] {
       if constexpr (sizeof(T) == 2) {
-        if (on_tensor_cores) {     // nine taps + ones row as GEMM-M of mma.sync (kernels_train.cuh); one resident wave, a multiple of G0 blocks
-          const int mgrid = std::max(1, e->wave_grid(first_wgrad_mma_kernel, (size_t)cdiv64((long long)nb * S * cdiv(S, 32), 8)) / G0) * G0;
-          first_wgrad_mma_kernel<<<mgrid, 256, 0, e->stream>>>(tr->x.as<float>(), B.V(tr->g_d1a, S, cp[0], 0, cp[0]), nb,
+        if (on_tensor_cores) {     // nine taps + ones row as GEMM-M of mma.sync (kernels_train.cuh); one resident wave
+          const size_t msm = first_wgrad_mma_smem(G0);
+          ADP_CUDA(cudaFuncSetAttribute(first_wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_wgrad_mma_smem(kFwMaxG)));
+          const int mgrid = e->wave_grid(first_wgrad_mma_kernel, (size_t)cdiv64((long long)nb * S * cdiv(S, 32), 8), 256, msm);
+          first_wgrad_mma_kernel<<<mgrid, 256, msm, e->stream>>>(tr->x.as<float>(), B.V(tr->g_d1a, S, cp[0], 0, cp[0]), nb,
                                                                 tr->gw_first.as<float>(), tr->gb_first.as<float>());
           return;
         }
