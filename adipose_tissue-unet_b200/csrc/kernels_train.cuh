@@ -455,11 +455,11 @@ first_wgrad_kernel(const float *__restrict__ xnorm, View<T> dz, int nb, float *_
 
 // First-layer weight gradient on the tensor cores (bf16 training path): per 16 pixels ONE mma.sync.m16n8k16
 //   D[16 x 8] += A[16 x 16] * B[16 x 8],   rows of A = the nine input taps (row 9 = ones, so D row 9 is the bias
-//   gradient; rows 10..15 zero), columns of A = 16 consecutive pixels, B = dZ of those pixels for the 8 channels of the
-//   warp's channel group, D rows 0..8 = dW[tap][8 channels] in fp32.
-// 2 MMAs replace the 80 FMAs per lane and 32-pixel chunk of first_wgrad_kernel (which stays the exact-fp32 / CUDA-core
-// cross-check path): ~50 instead of ~165 instructions per chunk and 4 accumulator registers instead of 80, so the kernel
-// runs at full occupancy.  The input pixels enter the MMA rounded to bf16 (dZ already is bf16); accumulation is fp32.
+//   gradient; rows 10..15 zero), columns of A = 16 consecutive pixels, B = dZ of those pixels for the 8 channels of one
+//   channel group, D rows 0..8 = dW[tap][8 channels] in fp32.
+// Two MMAs per channel group replace the 80 FMAs per lane, 32-pixel chunk and channel group of first_wgrad_kernel (which
+// stays the exact-fp32 / CUDA-core cross-check path), with 4 accumulator registers per group instead of 80.  The input
+// pixels enter the MMA rounded to bf16 (dZ already is bf16); accumulation is fp32.
 // Fragment layout of mma.m16n8k16 (PTX ISA): group = lane / 4, t = lane % 4;
 //   A regs: {row group, cols 2t,2t+1}, {row group + 8, same cols}, {row group, cols 2t+8,2t+9}, {row group + 8, cols 2t+8,2t+9}
 //   B regs: {k = 2t,2t+1; n = group}, {k = 2t+8,2t+9; n = group};  D: {row group, cols 2t,2t+1}, {row group + 8, same cols}.
