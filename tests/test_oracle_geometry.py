@@ -161,3 +161,14 @@ def test_boundary_metrics_case_analysis_matches_reference_statement():
         pb, tb = pred > 0.5, true > 0.5
         counts = (int((pb & tb).sum()), int((pb & ~tb).sum()), int((~pb & tb).sum()), int((~pb & ~tb).sum()))
         assert boundary_metrics_from_counts(*counts) == G.boundary_metrics_reference(pred.astype(np.float32), true.astype(np.float32))
+
+
+def test_host_windows_equal_oracle_statements():
+    """The host-side window builders of the product (api.py) against the oracle statements, no GPU needed."""
+    from adipose_unet_b200 import api
+    for T in (64, 1024):
+        np.testing.assert_array_equal(api.blend_window("gaussian", T), G.gaussian_window(T))
+        np.testing.assert_array_equal(api.blend_window("hann", T), G.hann_window(T))
+    assert api.blend_window("linear", 64) is None
+    np.testing.assert_array_equal(api.HannBlender(128).weight_map, G.hann_window(128))
+    np.testing.assert_array_equal(api.GaussianBlender(128, 0.25).weight_map, G.gaussian_window(128, 0.25))
