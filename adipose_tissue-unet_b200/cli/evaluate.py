@@ -3,7 +3,8 @@
 Tiles are predicted in device batches (+TTA / sliding window), thresholding and TP/FP/FN/TN run on the device
 (adp_threshold_metrics) for the fixed threshold and for every candidate of the slide-level F1 search (:891-940); slide
 aggregation and the 10 000-sample bootstrap (:983-1018, RandomState(42)) are host statistics as in the reference.
-Reported as NaN in the results table: ROC/PR AUC (sklearn statistics outside this engine).  Hausdorff95 / ASSD follow
+ROC / PR AUC are the reference's scikit-learn host statistics (calculate_auc_metrics, :847-888; --skip-auc leaves them NaN).
+Hausdorff95 / ASSD follow
 the reference's statements as written (api.boundary_metrics_from_counts: the reference samples each mask's own distance
 transform on its own surface, so the values are 0.0 / inf by case).  Not reproduced: the matplotlib panels (DESIGN.md
 section 6).  --boundary-refine runs BoundaryRefiner.refine on the device (adp_boundary_refine)."""
@@ -91,6 +92,8 @@ def build_parser():
     p.add_argument("--n-positive", type=int, default=120)
     p.add_argument("--n-negative", type=int, default=30)
     C.add_engine_args(p)
+    p.add_argument("--skip-auc", action="store_true", default=False,
+                   help="(not in the reference) skip the scikit-learn ROC/PR AUC host statistics (~0.3 s per 1024^2 tile on the CPU)")
     return p
 
 
@@ -149,6 +152,22 @@ def predict_all(model, pairs, mean, std, args):
         preds = [refiner.refine(p) for p in preds]
     print(f"✓ Inference completed in {(time.time() - start) / 60:.1f} minutes")
     return preds, gts
+
+
+def auc_metrics(pred: np.ndarray, true: np.ndarray):
+    """calculate_auc_metrics (:847-888): pixel-level ROC AUC and average precision with scikit-learn, exactly the reference's
+    host statistics (NaN when only one class is present or when scikit-learn is not installed)."""
+    true_flat = (np.asarray(true) > 0.5).astype(int).ravel()
+    if len(np.unique(true_flat)) < 2:
+        return {"roc_auc": float("nan"), "pr_auc": float("nan")}
+    try:
+        from sklearn.metrics import average_precision_score, roc_auc_score
+        pred_flat = np.asarray(pred).ravel()
+        return {"roc_auc": float(roc_auc_score(true_flat, pred_flat)), "pr_auc": float(average_precision_score(true_flat, pred_flat))}
+    except Exception as e:                      # noqa: BLE001 - the reference warns and reports NaN (:882-888)
+        import warnings
+        warnings.warn(f"Error calculating AUC metrics: {e}")
+        return {"roc_auc": float("nan"), "pr_auc": float("nan")}
 
 
 def tile_metrics(engine, pred, gt, thr):
@@ -223,18 +242,18 @@ def main(argv=None) -> int:
     for p, g, path in zip(preds, gts, paths):
         m = tile_metrics(eng, p, g, thr)
         m.update(api.boundary_metrics_from_counts(m["tp"], m["fp"], m["fn"], m["tn"]))   # calculate_boundary_metrics, :788-844
+        m.update(auc_metrics(p, g) if not args.skip_auc else {"roc_auc": float("nan"), "pr_auc": float("nan")})
         slides[extract_slide_id(path)].append(m)
     slide_vals = {k: np.array([np.mean([m[k] for m in tiles]) for tiles in slides.values()]) for k in METRIC_KEYS}
 
     def finite_mean(tiles, key):                  # slide value = mean of the finite tile values, NaN if none (:1701-1708)
         v = [m[key] for m in tiles if np.isfinite(m[key])]
         return float(np.mean(v)) if v else float("nan")
-    for key in ("hausdorff95", "assd"):
+    for key in ("roc_auc", "pr_auc", "hausdorff95", "assd"):
         slide_vals[key] = np.array([finite_mean(tiles, key) for tiles in slides.values()])
     print(f"✓ Calculated slide-level metrics for {len(slides)} slides\n\nCalculating bootstrap confidence intervals (n=10000)...")
-    summary = {k: bootstrap_ci(slide_vals[k]) for k in list(METRIC_KEYS) + ["hausdorff95", "assd"]}
-    nan = (float("nan"), (float("nan"), float("nan")))
-    rows = [summary[k] for k in METRIC_KEYS] + [nan] * 2 + [summary["hausdorff95"], summary["assd"]]
+    summary = {k: bootstrap_ci(slide_vals[k]) for k in list(METRIC_KEYS) + ["roc_auc", "pr_auc", "hausdorff95", "assd"]}
+    rows = [summary[k] for k in METRIC_KEYS] + [summary["roc_auc"], summary["pr_auc"], summary["hausdorff95"], summary["assd"]]
     table = out / f"{name}_comprehensive_results.csv"
     with open(table, "w", newline="") as f:
         w = csv.writer(f)

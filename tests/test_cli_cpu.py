@@ -165,3 +165,69 @@ def test_prefetch_keeps_order_propagates_errors_and_stops():
     it.close()                                   # consumer leaves early (steps_per_epoch reached): the producer stops
     time.sleep(0.5)
     assert len(produced) <= 6 and threading.active_count() <= n0
+
+
+def test_auc_metrics_follow_reference_rules():
+    rng = np.random.default_rng(0)
+    gt = (rng.random((64, 64)) > 0.7).astype(np.uint8)
+    pred = np.clip(gt * 0.6 + rng.random((64, 64)) * 0.5, 0, 1).astype(np.float32)
+    m = evaluate.auc_metrics(pred, gt)
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    assert m["roc_auc"] == float(roc_auc_score(gt.ravel().astype(int), pred.ravel()))
+    assert m["pr_auc"] == float(average_precision_score(gt.ravel().astype(int), pred.ravel()))
+    one_class = evaluate.auc_metrics(pred, np.zeros_like(gt))           # a single class: NaN (:866-872)
+    assert np.isnan(one_class["roc_auc"]) and np.isnan(one_class["pr_auc"])
+
+
+def test_evaluate_host_pipeline_with_stub_engine(tmp_path, monkeypatch):
+    """The evaluate CLI's HOST logic (pairing, slide aggregation, threshold search bookkeeping, boundary / AUC rows, bootstrap,
+    results table) end to end on the CPU: the device calls are replaced by NumPy stand-ins, so this covers everything
+    around them (the GPU test covers the real engine)."""
+    from adipose_unet_b200 import api
+    rng = np.random.default_rng(3)
+    ds = tmp_path / "set"
+    (ds / "images").mkdir(parents=True); (ds / "masks").mkdir()
+    truth = {}
+    for slide, n in (("slideA", 2), ("slideB", 1)):
+        for c in range(n):
+            stem = f"{slide}_r0_c{c}"
+            img = (rng.random((1024, 1024)) * 255).astype(np.uint8)
+            cv2.imwrite(str(ds / "images" / f"{stem}.png"), img)
+            m = (img > 140).astype(np.uint8) if slide == "slideA" else np.zeros((1024, 1024), np.uint8)
+            cv2.imwrite(str(ds / "masks" / f"{stem}.tif"), m)
+            truth[stem] = m
+    ck = tmp_path / "ckpt"; ck.mkdir()
+    (ck / "weights_best_overall.weights.h5").write_bytes(b"x")
+    (ck / "normalization_stats.json").write_text(json.dumps({"mean": 127.5, "std": 50.0}))
+
+    class StubEngine:
+        def threshold_metrics(self, prob, gt, thr, want_mask=False):
+            pb, tb = np.asarray(prob) > thr, np.asarray(gt) > 0.5
+            return None, (int((pb & tb).sum()), int((pb & ~tb).sum()), int((~pb & tb).sum()), int((~pb & ~tb).sum()))
+
+        def threshold_sweep(self, prob, gt, thresholds):
+            return np.array([self.threshold_metrics(prob, gt, float(t))[1] for t in thresholds], np.int64)
+
+    class StubModel:
+        engine = StubEngine()
+
+        def predict_batch(self, tiles, mean, std, tta_mode=None):
+            return (np.asarray(tiles, np.float32) / 255.0).astype(np.float32)        # "probability" = brightness
+
+    monkeypatch.setattr(C, "make_model", lambda *a, **k: StubModel())
+    monkeypatch.setattr(api, "calculate_pixel_metrics",
+                        lambda pred, true, thr=0.5, engine=None: api.metrics_from_counts(*engine.threshold_metrics(pred, true, thr)[1]))
+    out = tmp_path / "out"
+    rc = evaluate.main(["--weights", str(ck), "--test-dataset", str(ds), "--output", str(out), "--optimize-threshold", "--no-visualizations"])
+    assert rc == 0
+    import csv as _csv
+    rows = {r["Metric"]: r for r in _csv.DictReader(open(out / "set_comprehensive_results.csv"))}
+    assert len(rows) == 11 and all(r["N_Slides"] == "2" and r["N_Tiles"] == "3" for r in rows.values())
+    # slide A is thresholded brightness (separable at 140/255 -> high Dice at the searched threshold); slide B is empty in truth
+    assert 0.4 < float(rows["Dice Score"]["Mean"]) <= 1.0
+    assert float(rows["ROC AUC"]["Mean"]) > 0.99 and float(rows["PR AUC"]["Mean"]) > 0.99     # only slide A has two classes
+    assert float(rows["Hausdorff95"]["Mean"]) == 0.0 and float(rows["ASSD"]["Mean"]) == 0.0   # as the reference computes them
+    rc = evaluate.main(["--weights", str(ck), "--test-dataset", str(ds), "--output", str(out), "--no-visualizations", "--skip-auc"])
+    assert rc == 0
+    rows = {r["Metric"]: r for r in _csv.DictReader(open(out / "set_comprehensive_results.csv"))}
+    assert rows["ROC AUC"]["Mean"] == "nan"
