@@ -513,9 +513,10 @@ class BoundaryRefiner:
 
 class HannBlender:
     """EXTENSION (not in the reference, which has only Gaussian and linear blenders): Hann-window blending as named by
-    BASELINE.json.  Weights h[y]*h[x], h[i] = 0.5 - 0.5*cos(2*pi*(i + 0.5)/tile) in float64 -> float32: the half-sample
-    shift keeps all weights positive (no zero weight sum on slide borders) and h[i] + h[i + tile/2] == 1 at 50 % overlap.
-    Same accumulate / normalise statements as GaussianBlender.reconstruct, so it runs on the same device kernels."""
+    BASELINE.json.  Weights h[y]*h[x], h[i] = max(0.5 - 0.5*cos(2*pi*(i + 0.5)/tile), 1e-3) in float64 -> float32: the
+    half-sample shift keeps the window symmetric and positive, the floor keeps every weight above the 1e-8 clamp of the
+    normalisation (slide corners are covered by a single tile), and h[i] + h[i + tile/2] == 1 at 50 % overlap away from
+    the floored ends.  Same accumulate / normalise statements as GaussianBlender.reconstruct: same device kernels."""
 
     def __init__(self, tile_size: int = 1024, engine: Optional[Engine] = None):
         self.tile_size = tile_size
@@ -524,7 +525,7 @@ class HannBlender:
 
     def _create_hann_weight_map(self) -> np.ndarray:
         i = np.arange(self.tile_size, dtype=np.float64)
-        h = 0.5 - 0.5 * np.cos(2.0 * np.pi * (i + 0.5) / self.tile_size)
+        h = np.maximum(0.5 - 0.5 * np.cos(2.0 * np.pi * (i + 0.5) / self.tile_size), 1e-3)
         return np.outer(h, h).astype(np.float32)
 
     def reconstruct(self, tiles, positions, output_shape) -> np.ndarray:

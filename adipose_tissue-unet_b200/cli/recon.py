@@ -193,7 +193,7 @@ def main(argv=None) -> int:
                 f.write(f"Image Size: {full_shape[1]} x {full_shape[0]} pixels\nTiles Used: {len(tiles)}\nCoverage: {coverage:.1%}\n\n")
                 f.write(f"Reconstruction Settings:\n  Blend Mode: {args.blend_mode}\n")
                 f.write(f"  TTA: {'Yes (' + args.tta_mode + ')' if args.use_tta else 'No'}\n")
-                f.write(f"  Boundary Refinement: No\n  Threshold: {args.threshold}\n\nPerformance Metrics:\n")
+                f.write(f"  Boundary Refinement: {'Yes' if args.boundary_refine else 'No'}\n  Threshold: {args.threshold}\n\nPerformance Metrics:\n")
                 for label, key in (("Dice Score:    ", "dice_score"), ("IoU (Jaccard): ", "jaccard_index"), ("Sensitivity:   ", "sensitivity"),
                                    ("Specificity:   ", "specificity"), ("Precision:     ", "precision"), ("F1-Score:      ", "f1_score")):
                     f.write(f"  {label} {metrics[key]:.4f}\n")

@@ -80,17 +80,22 @@ def gaussian_window(tile: int = 1024, sigma_factor: float = 0.25) -> np.ndarray:
 
 
 # --------------------------------------------------------------------- G2x (extension, NOT in the reference)
+HANN_FLOOR = 1e-3
+
+
 def hann_window(tile: int = 1024) -> np.ndarray:
     """Hann blending window named by BASELINE.json's north_star; the reference has only Gaussian and linear
     blenders, so this is a labelled extension with its own formula:
 
-        h[i] = 0.5 - 0.5 * cos(2*pi*(i + 0.5) / tile),  w[y, x] = h[y] * h[x]   (float64 -> float32)
+        h[i] = max(0.5 - 0.5 * cos(2*pi*(i + 0.5) / tile), 1e-3),  w[y, x] = h[y] * h[x]   (float64 -> float32)
 
-    The half-sample shift keeps every weight > 0 (np.hanning is 0 at both ends, which would leave the slide border
-    with a zero weight sum) and makes the window symmetric; at 50 % overlap h[i] + h[i + tile/2] == 1, so the weight
+    The half-sample shift makes the window symmetric and keeps it positive (np.hanning is 0 at both ends); the floor keeps
+    every weight >= 1e-6, i.e. above the 1e-8 clamp of the blender's normalisation `acc / max(weight_sum, 1e-8)`
+    (full_evaluation_enhanced.py:176-181) - without it the ~60 pixels next to each slide corner, covered by one tile with
+    weight < 1e-8, would be attenuated.  At 50 % overlap h[i] + h[i + tile/2] == 1 away from the floored ends, so the weight
     sum of interior pixels is 1 up to float32 rounding."""
     i = np.arange(tile, dtype=np.float64)
-    h = 0.5 - 0.5 * np.cos(2.0 * np.pi * (i + 0.5) / tile)
+    h = np.maximum(0.5 - 0.5 * np.cos(2.0 * np.pi * (i + 0.5) / tile), HANN_FLOOR)
     return np.outer(h, h).astype(np.float32)
 
 

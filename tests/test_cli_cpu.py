@@ -231,3 +231,77 @@ def test_evaluate_host_pipeline_with_stub_engine(tmp_path, monkeypatch):
     assert rc == 0
     rows = {r["Metric"]: r for r in _csv.DictReader(open(out / "set_comprehensive_results.csv"))}
     assert rows["ROC AUC"]["Mean"] == "nan"
+
+
+def test_recon_host_pipeline_with_stub_engine(tmp_path, monkeypatch):
+    """The recon CLI's HOST logic (tile-name parsing, coverage, inferred slide size, edge clamp, refine-before-blend order,
+    output files and logs) end to end on the CPU with a NumPy stand-in for the engine (oracle statements for blend / refine)."""
+    from oracle import geometry as G
+    from oracle import refine as R
+    T, stride = 1024, 512
+    rng = np.random.default_rng(4)
+    root = tmp_path / "tiles"
+    (root / "images").mkdir(parents=True); (root / "masks").mkdir()
+    base = cv2.GaussianBlur((rng.random((T, T + 2 * stride)) * 255).astype(np.float32), (0, 0), 12)
+    base = ((base - base.min()) / (base.max() - base.min()) * 255).astype(np.uint8)
+    for c in range(3):                                                     # slideA: 1 x 3 tiles at 50 % overlap -> 1024 x 2048
+        tile = base[:, c * stride:c * stride + T]
+        cv2.imwrite(str(root / "images" / f"slideA_r0_c{c}.jpg"), cv2.cvtColor(tile, cv2.COLOR_GRAY2BGR), [cv2.IMWRITE_JPEG_QUALITY, 100])
+        cv2.imwrite(str(root / "masks" / f"slideA_r0_c{c}.tif"), (tile > 128).astype(np.uint8))
+    ck = tmp_path / "ckpt"; ck.mkdir()
+    (ck / "weights_best_overall.weights.h5").write_bytes(b"x")
+    (ck / "normalization_stats.json").write_text(json.dumps({"mean": 127.5, "std": 50.0}))
+
+    def fake_prob(tiles):
+        return (np.asarray(tiles, np.float32) / 255.0).astype(np.float32)
+
+    class StubEngine:
+        def wsi_begin(self, rows, W, y0, tile, mode, window):
+            self.shape, self.mode, self.window, self.tiles, self.pos = (rows, W), mode, window, [], []
+
+        def wsi_push_tiles(self, tiles, ys, xs, mean, std, ops):
+            self.wsi_push_probs(fake_prob(tiles), ys, xs)
+
+        def predict(self, tiles, mean, std, ops=None, out=None):
+            return fake_prob(tiles)
+
+        def boundary_refine(self, mask, kernel_size=5, **kw):
+            return np.stack([R.refine(m, kernel_size=kernel_size) for m in mask])
+
+        def wsi_push_probs(self, probs, ys, xs):
+            self.tiles += list(probs); self.pos += list(zip([int(y) for y in ys], [int(x) for x in xs]))
+
+        def blend(self, mode, tiles, positions, shape, window):
+            tiles = [np.asarray(t, np.float32) for t in tiles]
+            return G.gaussian_reconstruct(tiles, positions, shape, window) if window is not None else G.linear_reconstruct(tiles, positions, shape)
+
+        def wsi_finalize(self, y, rows, W, threshold=0.5, gt=None, want_prob=True, want_mask=True):
+            prob = self.blend(self.mode, self.tiles, self.pos, self.shape, self.window)
+            mask = (prob > threshold).astype(np.uint8)
+            m = G.pixel_metrics(prob, (np.asarray(gt) > 0.5).astype(np.uint8), threshold) if gt is not None else dict(tp=0, fp=0, fn=0, tn=0)
+            return prob, mask, (m["tp"], m["fp"], m["fn"], m["tn"])
+
+        def wsi_end(self):
+            pass
+
+    class StubModel:
+        engine = StubEngine()
+
+    monkeypatch.setattr(C, "make_model", lambda *a, **k: StubModel())
+    out = tmp_path / "out"
+    rc = recon.main(["--weights", str(ck), "--data-root", str(root), "--output-dir", str(out), "--stride", str(stride),
+                     "--blend-mode", "hann", "--boundary-refine", "--refine-kernel", "3"])
+    assert rc == 0
+    sdir = out / "slideA"
+    res = json.loads((out / "metrics" / "slideA_metrics.json").read_text())
+    assert res["dimensions"] == {"width": 2048, "height": 1024, "tiles_rows": 1, "tiles_cols": 3}
+    assert res["reconstruction"]["tiles_used"] == 3 and res["reconstruction"]["boundary_refined"] is True
+    assert "Boundary Refinement: Yes" in (sdir / "metrics.txt").read_text()
+    log = json.loads((out / "reconstruction_log.json").read_text())
+    assert log["parameters"]["blend_mode"] == "hann" and log["parameters"]["refine_kernel"] == 3
+    tiles = [cv2.imread(str(root / "images" / f"slideA_r0_c{c}.jpg"), cv2.IMREAD_GRAYSCALE) for c in range(3)]   # as the CLI reads them
+    want = G.hann_reconstruct([R.refine(fake_prob(t), kernel_size=3) for t in tiles], [(0, 0), (0, 512), (0, 1024)], (1024, 2048))
+    got = cv2.imread(str(sdir / "prediction_mask.tif"), cv2.IMREAD_UNCHANGED)
+    np.testing.assert_array_equal(got, (want * 255).astype(np.uint8))
+    rgb = cv2.imread(str(sdir / "original_image.tif"), cv2.IMREAD_COLOR)
+    assert rgb.shape == (1024, 2048, 3) and np.abs(rgb[:, :, 0].astype(int) - base.astype(int)).max() <= 4      # JPEG q100 + blend (corners included: the Hann floor)
