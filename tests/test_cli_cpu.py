@@ -305,3 +305,43 @@ def test_recon_host_pipeline_with_stub_engine(tmp_path, monkeypatch):
     np.testing.assert_array_equal(got, (want * 255).astype(np.uint8))
     rgb = cv2.imread(str(sdir / "original_image.tif"), cv2.IMREAD_COLOR)
     assert rgb.shape == (1024, 2048, 3) and np.abs(rgb[:, :, 0].astype(int) - base.astype(int)).max() <= 4      # JPEG q100 + blend (corners included: the Hann floor)
+
+
+def test_infer_host_pipeline_with_stub_engine(tmp_path, monkeypatch, capsys):
+    """The infer CLI's HOST logic (file discovery, the non-1024^2 skip with the reference's warning, output names and
+    encodings: masks {0,1}, probabilities trunc(p*255), overlays) end to end on the CPU with a stand-in engine."""
+    rng = np.random.default_rng(6)
+    src = tmp_path / "imgs"; src.mkdir()
+    imgs = {}
+    for name in ("a_r0_c0", "b_r0_c1"):
+        imgs[name] = (rng.random((1024, 1024)) * 255).astype(np.uint8)
+        cv2.imwrite(str(src / f"{name}.png"), imgs[name])
+    cv2.imwrite(str(src / "small.png"), np.zeros((512, 512), np.uint8))
+    ck = tmp_path / "ckpt"; ck.mkdir()
+    (ck / "weights_best_overall.weights.h5").write_bytes(b"x")
+    (ck / "normalization_stats.json").write_text(json.dumps({"mean": 127.5, "std": 50.0}))
+
+    class StubEngine:
+        def threshold_metrics(self, prob, gt, thr, want_mask=True):
+            return (np.asarray(prob) > thr).astype(np.uint8), (0, 0, 0, 0)
+
+    class StubModel:
+        engine = StubEngine()
+
+        def predict_batch(self, tiles, mean, std, tta_mode=None):
+            return (np.asarray(tiles, np.float32) / 255.0).astype(np.float32)
+
+    monkeypatch.setattr(C, "make_model", lambda *a, **k: StubModel())
+    out = tmp_path / "out"
+    rc = infer.main(["--images-dir", str(src), "--output-dir", str(out), "--weights", str(ck), "--threshold", "0.5",
+                     "--save-probability", "--save-overlays", "--overlay-color", "cyan"])
+    assert rc == 0
+    assert "small.png is (512, 512), expected (1024, 1024), skipping" in capsys.readouterr().out
+    assert sorted(f.name for f in (out / "masks").iterdir()) == ["a_r0_c0_mask.tif", "b_r0_c1_mask.tif"]
+    for name, img in imgs.items():
+        p = img.astype(np.float32) / 255.0
+        np.testing.assert_array_equal(cv2.imread(str(out / "masks" / f"{name}_mask.tif"), cv2.IMREAD_UNCHANGED), (p > 0.5).astype(np.uint8))
+        np.testing.assert_array_equal(cv2.imread(str(out / "probabilities" / f"{name}_prob.tif"), cv2.IMREAD_UNCHANGED), (p * 255).astype(np.uint8))
+        ov = cv2.imread(str(out / "overlays" / f"{name}_overlay.png"), cv2.IMREAD_COLOR)
+        assert ov.shape == (1024, 1024, 3)
+    assert infer.main(["--images-dir", str(tmp_path / "missing"), "--output-dir", str(out), "--weights", str(ck)]) == 1
