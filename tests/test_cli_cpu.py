@@ -345,3 +345,92 @@ def test_infer_host_pipeline_with_stub_engine(tmp_path, monkeypatch, capsys):
         ov = cv2.imread(str(out / "overlays" / f"{name}_overlay.png"), cv2.IMREAD_COLOR)
         assert ov.shape == (1024, 1024, 3)
     assert infer.main(["--images-dir", str(tmp_path / "missing"), "--output-dir", str(out), "--weights", str(ck)]) == 1
+
+
+def test_train_host_pipeline_with_stub_engine(tmp_path, monkeypatch):
+    """The train CLI's HOST logic on the CPU with stand-ins for the engine and the trainer: two phases (phase 2 restarts from
+    phase1_best), cosine/warm-up learning rates, CSV logs, best / final / EMA / best-overall checkpoints written and re-read
+    through the HDF5 writer, normalization_stats.json and training_settings.log (sniffed by the evaluation CLI)."""
+    import adipose_unet_b200 as A
+    from adipose_unet_b200 import api, train as T
+    from adipose_unet_b200.weights_io import load_weights_file
+    rng = np.random.default_rng(8)
+    build = tmp_path / "build"
+    for split, n in (("train", 3), ("val", 1)):
+        (build / "dataset" / split / "images").mkdir(parents=True); (build / "dataset" / split / "masks").mkdir(parents=True)
+        for i in range(n):
+            img = (rng.random((1024, 1024)) * 255).astype(np.uint8)
+            cv2.imwrite(str(build / "dataset" / split / "images" / f"s_r0_c{i}.jpg"), img)
+            cv2.imwrite(str(build / "dataset" / split / "masks" / f"s_r0_c{i}.tif"), (img > 128).astype(np.uint8))
+    calls = {"lrs": [], "set_weights": 0, "freeze": []}
+
+    class StubEngine:
+        def __init__(self, **kw):
+            self.w = {}
+
+        def set_weights(self, w):
+            calls["set_weights"] += 1
+            self.w = {k: np.array(v, np.float32) for k, v in w.items()}
+
+        def get_weights(self):
+            return {k: v.copy() for k, v in self.w.items()}
+
+        def train_set_loss(self, *a):
+            calls["loss"] = a
+
+        def train_set_deep_supervision(self, *a):
+            calls["ds"] = a
+
+        def predict(self, x, mean, std, ops=None, out=None):
+            return (1.0 / (1.0 + np.exp(-np.asarray(x, np.float32)))).astype(np.float32)
+
+        def loss_metrics(self, p, y):
+            return {"loss": float(np.mean((p - y) ** 2)), "dice_coef": float(0.5 + 0.01 * len(calls["lrs"]))}    # improves every step
+
+    class StubTrainer:
+        def __init__(self, engine, batch, tile, **kw):
+            self.engine = engine
+            calls["freeze"].append(kw.get("freeze_encoder"))
+
+        def step(self, x, y, lr):
+            assert x.shape == (2, 1024, 1024) and y.shape == (2, 1024, 1024) and x.dtype == np.float32
+            calls["lrs"].append(lr)
+            for k in self.engine.w:                      # "training": nudge every tensor so EMA != current weights
+                self.engine.w[k] = self.engine.w[k] + np.float32(1e-3)
+            return {"loss": 1.0 / len(calls["lrs"]), "dice_coef": 0.1 * len(calls["lrs"])}
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(api, "Engine", StubEngine)
+    monkeypatch.setattr(T, "DataParallelTrainer", StubTrainer)
+    small = A.synth.init_weights()                       # the writer checks the 44-channel shapes: full-size tensors (34 MB per file)
+    root = tmp_path / "ckpts"
+    rc = train.main(["--data-root", str(build), "--pretrained-weights", str(tmp_path / "none.h5"), "--batch-size", "2",
+                     "--epochs-phase1", "2", "--epochs-phase2", "2", "--warmup-epochs-phase1", "1", "--warmup-epochs-phase2", "1",
+                     "--no-deep-supervision", "--no-hard-mining", "--normalization-method", "zscore", "--augmentation-level", "none",
+                     "--checkpoint-root", str(root)])
+    assert rc == 0
+    (ck,) = list(root.iterdir())
+    assert ck.name.endswith("_adipose_sybreosin_1024_finetune_v3")
+    for f in ("phase1_best.weights.h5", "phase2_best.weights.h5", "weights_phase1_final.weights.h5", "weights_phase2_final.weights.h5",
+              "weights_best_overall.weights.h5", "weights_ema.weights.h5", "normalization_stats.json", "training_settings.log",
+              "phase1_training.log", "phase2_training.log"):
+        assert (ck / f).exists(), f
+    assert calls["freeze"] == [True, False]                                   # phase 1 frozen encoder, phase 2 all layers
+    assert "use_deep_supervision: False" in (ck / "training_settings.log").read_text()
+    stats = json.loads((ck / "normalization_stats.json").read_text())
+    assert stats["normalization_method"] == "zscore" and stats["num_training_images"] == 3
+    # 3 training tiles, batch 2 -> 2 steps per epoch (last batch padded); lr per epoch from the cosine/warm-up schedule
+    assert len(calls["lrs"]) == 8
+    want = [T.cosine_warmup_lr(e, 1e-4, 1e-7, 1, 2) for e in range(2)] + [T.cosine_warmup_lr(e, 1e-5, 1e-8, 1, 2) for e in range(2)]
+    assert calls["lrs"][::2] == want and calls["lrs"][1::2] == want
+    import csv as _csv
+    log1 = list(_csv.DictReader(open(ck / "phase1_training.log")))
+    assert [r["epoch"] for r in log1] == ["0", "1"] and set(log1[0]) == {"epoch", "dice_coef", "loss", "lr", "val_dice_coef", "val_loss"}
+    # the checkpoints round-trip through the HDF5 writer; best_overall == phase2_best; the EMA differs from the final weights
+    best2, overall = load_weights_file(str(ck / "phase2_best.weights.h5"), keep_aux=True), load_weights_file(str(ck / "weights_best_overall.weights.h5"), keep_aux=True)
+    assert set(best2) == set(small) and all(np.array_equal(best2[k], overall[k]) for k in best2)
+    ema, final = load_weights_file(str(ck / "weights_ema.weights.h5"), keep_aux=True), load_weights_file(str(ck / "weights_phase2_final.weights.h5"), keep_aux=True)
+    k0 = "down1_conv1/kernel"
+    assert not np.array_equal(ema[k0], final[k0]) and np.allclose(ema[k0], final[k0], atol=1e-2)
