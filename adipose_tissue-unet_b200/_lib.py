@@ -57,14 +57,15 @@ SIGNATURES = {
     "adp_blend_reconstruct": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
     "adp_wsi_begin": (_I, [_P, _I, _I, _I, _I, _I, _P]),
     "adp_wsi_push_tiles": (_I, [_P, _P, _I, _P, _P, _F, _F, C.POINTER(_I), _I]),
-    "adp_wsi_push_from_slide": (_I, [_P, _P, _I, _I, _I, _P, _P, _F, _F, C.POINTER(_I), _I]),
+    "adp_wsi_push_from_slide": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _F, _F, C.POINTER(_I), _I, _I]),
+    "adp_wsi_replay_deferred": (_I, [_P]),
     "adp_wsi_push_probs": (_I, [_P, _P, _I, _P, _P]),
     "adp_wsi_export": (_I, [_P, _I, _I, _P, _P]),
     "adp_wsi_import_add": (_I, [_P, _I, _I, _P, _P]),
     "adp_wsi_finalize": (_I, [_P, _I, _I, _F, _P, _P, _P, C.POINTER(_I64)]),
     "adp_wsi_end": (_I, [_P]),
     "adp_loss_metrics": (_I, [_P, _P, _P, _I64, _P, C.POINTER(C.c_double)]),
-    "adp_loss_metrics_ex": (_I, [_P, _P, _P, _I, _I64, _F, _F, _F, _P, C.POINTER(C.c_double)]),
+    "adp_loss_metrics_ex": (_I, [_P, _P, _P, _I, _I64, _I64, _F, _F, _F, _P, C.POINTER(C.c_double)]),
     "adp_train_set_loss": (_I, [_P, _F, _F, _F]),
     "adp_train_set_deep_supervision": (_I, [_P, _I, _F, _F, _F]),
     "adp_train_outputs": (_I, [_P]),
@@ -72,7 +73,12 @@ SIGNATURES = {
     "adp_train_forward": (_I, [_P, _P, _P, _I, C.POINTER(_P), C.POINTER(C.c_double)]),
     "adp_train_loss": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "adp_train_backward": (_I, [_P, C.POINTER(C.c_double), _I]),
+    "adp_train_sums_buffer": (_I, [_P, C.POINTER(_P), C.POINTER(_I)]),
+    "adp_train_sums_read": (_I, [_P, _P, _I]),
     "adp_train_grad_buffer": (_I, [_P, C.POINTER(_P), C.POINTER(_I64)]),
+    "adp_train_grad_buckets": (_I, [_P, C.POINTER(_I64), C.POINTER(_I64), _I]),
+    "adp_train_bucket_wait": (_I, [_P, _I, _P]),
+    "adp_train_join": (_I, [_P, _P]),
     "adp_train_grad_read": (_I, [_P, _P, _I64]),
     "adp_train_grad_write": (_I, [_P, _P, _I64]),
     "adp_train_get_grad": (_I, [_P, C.c_char_p, _P, _I64, _P, _I64]),

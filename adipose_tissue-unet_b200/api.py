@@ -172,13 +172,15 @@ class Engine:
     def loss_metrics(self, p, y, want_grad: bool = False, ohem_keep_ratio: float = 1.0, eps_pos: float = 0.0,
                      eps_neg: float = 0.0):
         """combined_loss_standard by default; ohem_keep_ratio < 1 / eps_* > 0 select the reference's hard-mining and
-        label-smoothing losses.  p, y: (B, H, W) (or a single image)."""
+        label-smoothing losses.  p, y: (B, H, W) (or a single image); the last axis is the one Keras' binary_crossentropy
+        averages, i.e. hard mining ranks the (B, H) row means (train_adipose_unet_v3.py:301-313)."""
         p = _f32c(p); y = _f32c(y)
         out = (C.c_double * 4)()
         g = np.empty(p.shape, np.float32) if want_grad else None
         batch = p.shape[0] if p.ndim == 3 else 1
-        _lib.check(self.lib.adp_loss_metrics_ex(self.h, _lib.ptr(p), _lib.ptr(y), batch, p.size // batch, ohem_keep_ratio, eps_pos,
-                                                eps_neg, _lib.ptr(g), out))
+        row_len = p.shape[-1] if p.ndim >= 2 else 0
+        _lib.check(self.lib.adp_loss_metrics_ex(self.h, _lib.ptr(p), _lib.ptr(y), batch, p.size // batch, row_len, ohem_keep_ratio,
+                                                eps_pos, eps_neg, _lib.ptr(g), out))
         res = dict(loss=out[0], bce=out[1], dice_loss=out[2], dice_coef=out[3])
         return (res, g) if want_grad else res
 
@@ -189,9 +191,10 @@ class Engine:
         _lib.check(self.lib.adp_train_begin(self.h, batch, size, dropout_rate, seed))
         self._train_shape = (batch, size, size)
 
-    def train_forward(self, x, y, dropout_masks: Optional[Dict[str, np.ndarray]] = None) -> np.ndarray:
+    def train_forward(self, x, y, dropout_masks: Optional[Dict[str, np.ndarray]] = None, want_sums: bool = True):
         """x, y: (B,S,S) float32 (normalised image, target).  dropout_masks: site name -> (B,h,w,C) 0/1.
-        Returns the eight loss sums (float64) of this batch (include/adipose_b200.h)."""
+        Returns the eight loss sums (float64) of this batch (include/adipose_b200.h); want_sums=False leaves them in the
+        device buffer (train_sums_buffer) and returns None without synchronising."""
         if isinstance(x, np.ndarray):
             x = _f32c(x)
         if isinstance(y, np.ndarray):
@@ -207,8 +210,21 @@ class Engine:
                 keep.append(m)
                 arr[i] = m.ctypes.data
             mptr = arr
-        _lib.check(self.lib.adp_train_forward(self.h, _lib.ptr(x), _lib.ptr(y), int(x.shape[0]), mptr, sums))
-        return np.array(list(sums), dtype=np.float64)
+        _lib.check(self.lib.adp_train_forward(self.h, _lib.ptr(x), _lib.ptr(y), int(x.shape[0]), mptr, sums if want_sums else None))
+        return np.array(list(sums), dtype=np.float64) if want_sums else None
+
+    def train_sums_buffer(self) -> Tuple[int, int]:
+        """(device address, count) of the float64 loss sums of the last forward (8 per output)."""
+        p = C.c_void_p(); n = C.c_int()
+        _lib.check(self.lib.adp_train_sums_buffer(self.h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def train_sums_read(self) -> np.ndarray:
+        """Host copy of the device loss sums (synchronises the engine's stream)."""
+        n = 8 * int(self.lib.adp_train_outputs(self.h))
+        out = np.empty(n, np.float64)
+        _lib.check(self.lib.adp_train_sums_read(self.h, _lib.ptr(out), n))
+        return out
 
     def train_set_loss(self, ohem_keep_ratio: float = 1.0, eps_pos: float = 0.0, eps_neg: float = 0.0):
         """Loss recipe of the following steps (train_adipose_unet_v3.py:808-855)."""
@@ -236,8 +252,9 @@ class Engine:
             res["main_out_loss"], res["aux_out1_loss"], res["aux_out2_loss"] = outs[0]["loss"], outs[1]["loss"], outs[2]["loss"]
         return res
 
-    def train_backward(self, sums, freeze_encoder: bool = False):
-        s = (C.c_double * len(sums))(*[float(v) for v in sums])
+    def train_backward(self, sums=None, freeze_encoder: bool = False):
+        """sums: host values the loss is defined over, or None = the device sums buffer as it stands."""
+        s = (C.c_double * len(sums))(*[float(v) for v in sums]) if sums is not None else None
         _lib.check(self.lib.adp_train_backward(self.h, s, 1 if freeze_encoder else 0))
 
     def train_grad_buffer(self) -> Tuple[int, int]:
@@ -245,6 +262,18 @@ class Engine:
         p = C.c_void_p(); n = C.c_int64()
         _lib.check(self.lib.adp_train_grad_buffer(self.h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
+
+    def train_grad_buckets(self) -> List[Tuple[int, int]]:
+        """[lo, hi) element ranges of the flat gradient in the order the backward pass completes them."""
+        lo = (C.c_int64 * 8)(); hi = (C.c_int64 * 8)()
+        n = _lib.check(self.lib.adp_train_grad_buckets(self.h, lo, hi, 8))
+        return [(int(lo[i]), int(hi[i])) for i in range(n)]
+
+    def train_bucket_wait(self, bucket: int, stream_ptr: int):
+        _lib.check(self.lib.adp_train_bucket_wait(self.h, bucket, C.c_void_p(stream_ptr)))
+
+    def train_join(self, stream_ptr: int):
+        _lib.check(self.lib.adp_train_join(self.h, C.c_void_p(stream_ptr)))
 
     def grad_to_host(self) -> np.ndarray:
         _, n = self.train_grad_buffer()
@@ -315,12 +344,18 @@ class Engine:
         _lib.check(self.lib.adp_wsi_push_tiles(self.h, _lib.ptr(tiles), len(ys), _lib.ptr(ys), _lib.ptr(xs), mean, std,
                                                _lib.int_array(ops) if ops else None, len(ops)))
 
-    def wsi_push_from_slide(self, slide_dev, region_y0, region_rows, ys, xs, mean, std, ops):
+    def wsi_push_from_slide(self, slide_dev, region_y0, region_rows, ys, xs, mean, std, ops, channels: int = 1,
+                            defer_below_row: int = 0):
+        """slide_dev: device uint8 region [region_rows, W] (gray) or [region_rows, W, 3] (RGB, channels=3).
+        defer_below_row: see adp_wsi_push_from_slide (exact multi-GPU boundary zone)."""
         ys = np.ascontiguousarray(ys, dtype=np.int32); xs = np.ascontiguousarray(xs, dtype=np.int32)
         ops = list(ops) if ops else []
-        _lib.check(self.lib.adp_wsi_push_from_slide(self.h, _lib.ptr(slide_dev), region_y0, region_rows, len(ys),
+        _lib.check(self.lib.adp_wsi_push_from_slide(self.h, _lib.ptr(slide_dev), int(channels), region_y0, region_rows, len(ys),
                                                     _lib.ptr(ys), _lib.ptr(xs), mean, std,
-                                                    _lib.int_array(ops) if ops else None, len(ops)))
+                                                    _lib.int_array(ops) if ops else None, len(ops), int(defer_below_row)))
+
+    def wsi_replay_deferred(self):
+        _lib.check(self.lib.adp_wsi_replay_deferred(self.h))
 
     def wsi_push_probs(self, probs, ys, xs):
         probs = _f32c(probs)
@@ -345,7 +380,10 @@ class Engine:
         prob = np.empty((rows, W), np.float32) if want_prob else None
         mask = np.empty((rows, W), np.uint8) if want_mask else None
         counts = (C.c_int64 * 4)()
-        g = np.ascontiguousarray((np.asarray(gt) > 0.5).astype(np.uint8)) if gt is not None else None
+        g = None
+        if gt is not None:          # the kernel tests gt != 0, which equals the reference's gt > 0.5 for uint8 masks: no host pass
+            g = np.ascontiguousarray(gt) if getattr(gt, "dtype", None) == np.uint8 else \
+                np.ascontiguousarray((np.asarray(gt) > 0.5).astype(np.uint8))
         _lib.check(self.lib.adp_wsi_finalize(self.h, y, rows, threshold, _lib.ptr(prob), _lib.ptr(mask), _lib.ptr(g), counts))
         return prob, mask, tuple(int(c) for c in counts)
 
@@ -596,12 +634,12 @@ class SlidingWindowInference:
                                     tta_mode: str = "basic") -> np.ndarray:
         tiles, positions = self.extract_tiles(image)
         h, w = image.shape[:2]
-        gaussian = isinstance(self.blender, GaussianBlender)
+        # window-weighted blenders (Gaussian, and the Hann extension) carry a weight_map; linear / none average uniformly
+        win = getattr(self.blender, "weight_map", None)
         if isinstance(model, AdiposeUNet):
             eng = model.engine
             ops = TTA_OPCODES[tta_mode if tta_mode in TTA_OPCODES else "basic"] if use_tta else None
-            eng.wsi_begin(h, w, 0, self.tile_size, _lib.BLEND_GAUSSIAN if gaussian else _lib.BLEND_LINEAR,
-                          self.blender.weight_map if gaussian else None)
+            eng.wsi_begin(h, w, 0, self.tile_size, _lib.BLEND_GAUSSIAN if win is not None else _lib.BLEND_LINEAR, win)
             try:
                 step = 16
                 for i in range(0, len(tiles), step):

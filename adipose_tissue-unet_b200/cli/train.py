@@ -105,10 +105,12 @@ def augment_d4(img, mask, rng):
     return np.ascontiguousarray(img), np.ascontiguousarray(mask)
 
 
-def batches(ds: TileDataset, batch: int, rng, augment: bool, rank: int, world: int, shuffle: bool):
+def batches(ds: TileDataset, batch: int, rng, augment: bool, rank: int, world: int, shuffle: bool, shuffle_rng=None):
+    """rng: this rank's stream (augmentation); shuffle_rng: a stream that is IDENTICAL on every rank (same seed, same
+    number of draws), so that all ranks slice their shards from one permutation and an epoch covers every tile once."""
     idx = np.arange(len(ds))
     if shuffle:
-        rng.shuffle(idx)
+        (shuffle_rng if shuffle_rng is not None else rng).shuffle(idx)
     per_step = batch * world
     for i in range(0, len(idx), per_step):
         chunk = list(idx[i:i + per_step])
@@ -175,6 +177,10 @@ def main(argv=None) -> int:
     if args.max_steps_per_epoch:
         steps_per_epoch = min(steps_per_epoch, args.max_steps_per_epoch)
     stamp = datetime.now().strftime("%Y%m%d_%H%M%S")
+    if dist is not None:          # one checkpoint directory for the whole job: rank 0's clock names it
+        box = [stamp]
+        dist.broadcast_object_list(box, src=0)
+        stamp = box[0]
     name = "adipose_sybreosin" + (f"_{args.checkpoint_suffix}" if args.checkpoint_suffix else "")
     ckpt = Path(args.checkpoint_root) / f"{stamp}_{name}_1024_finetune_v3"          # :650-652
     if rank == 0:
@@ -211,7 +217,8 @@ def main(argv=None) -> int:
     engine.train_set_loss(args.hard_example_ratio if args.use_hard_mining else 1.0,
                           args.label_smooth_epsilon_pos if args.use_label_smoothing else 0.0,
                           args.label_smooth_epsilon_neg if args.use_label_smoothing else 0.0)
-    rng = np.random.RandomState(args.seed + rank)
+    rng = np.random.RandomState(args.seed + rank)          # per-rank: augmentation draws
+    shuffle_rng = np.random.RandomState(args.seed)         # shared: the epoch permutation (identical on every rank)
     best_overall = -1.0
     for phase, epochs, max_lr, min_lr, warm, freeze, decay in (
             (1, args.epochs_phase1, 1e-4, 1e-7, args.warmup_epochs_phase1, True, 0.999),
@@ -219,6 +226,8 @@ def main(argv=None) -> int:
         if epochs <= 0:
             continue
         log(f"\n{'=' * 60}\nPHASE {phase}: {'frozen encoder' if freeze else 'fine-tuning all layers'} ({epochs} epochs)\n{'=' * 60}")
+        if dist is not None:
+            dist.barrier()           # rank 0 has written phase1_best: every replica restarts phase 2 from the same file
         if phase == 2 and (ckpt / "phase1_best.weights.h5").exists():
             engine.set_weights(load_weights_file(str(ckpt / "phase1_best.weights.h5"), keep_aux=True))       # :1336-1339
         trainer = T.DataParallelTrainer(engine, args.batch_size, TILE, dist=dist, rank=rank, world=world, dropout_rate=0.3,
@@ -235,7 +244,7 @@ def main(argv=None) -> int:
             lr = T.cosine_warmup_lr(epoch, max_lr, min_lr, warm, epochs) if args.use_cosine_schedule else max_lr
             t0, losses, dices = time.time(), [], []
             # the next batch is decoded / augmented while the device runs this one (the reference's dataset.prefetch, :620)
-            for step, (x, y) in enumerate(C.prefetch(batches(train_ds, args.batch_size, rng, args.augmentation_level != "none", rank, world, True))):
+            for step, (x, y) in enumerate(C.prefetch(batches(train_ds, args.batch_size, rng, args.augmentation_level != "none", rank, world, True, shuffle_rng))):
                 if step >= steps_per_epoch:
                     break
                 out = trainer.step(x, y, lr)

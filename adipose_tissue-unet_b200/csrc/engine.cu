@@ -141,6 +141,10 @@ struct adp_engine {
   bool wsi_on = false;
   int wsi_rows = 0, wsi_W = 0, wsi_y0 = 0, wsi_tile = 0, wsi_mode = 0;
   DevBuf wsi_acc, wsi_wsum, wsi_window, counts, misc;
+  // deferred boundary zone (adp_wsi_push_from_slide with defer_below_row): TTA-mean probabilities of the tiles that touch
+  // the rows another strip's partial sums must reach FIRST, kept until adp_wsi_replay_deferred
+  struct Deferred { std::unique_ptr<DevBuf> probs; std::vector<int32_t> ys, xs; int below = 0; };
+  std::vector<Deferred> wsi_deferred;
 
   // profiling
   bool prof = false;
@@ -487,7 +491,7 @@ const CUtensorMap &tmap_for(adp_engine *e, const void *buf, int H, int W, int cg
 }
 
 // TTA combine / blend kernel (kernels_post.cuh); ADP_TTA_SERIAL=1 selects the one-plane-per-barrier variant for A/B timing
-typedef void (*TtaKernel)(const float *, TtaOps, int, int, float *, float *, float *, const float *, int, int, int, int);
+typedef void (*TtaKernel)(const float *, TtaOps, int, int, float *, float *, float *, const float *, int, int, int, int, int);
 TtaKernel tta_kernel() {
   static const bool serial = getenv("ADP_TTA_SERIAL") && atoi(getenv("ADP_TTA_SERIAL")) != 0;
   return serial ? tta_blend_serial_kernel : tta_blend_kernel;
@@ -809,14 +813,14 @@ void run_tiles(adp_engine *e, int kind, FirstConvSrc src, const void *src_base, 
       if (out) {
         e->launch("tta_combine", 0, by, [&] {
           tta_kernel()<<<grid, block, 0, e->stream>>>(planes, tops, S, 0, dout + (size_t)t * tile_px, nullptr, nullptr,
-                                                         nullptr, 0, 0, 0, 0);
+                                                         nullptr, 0, 0, 0, 0, 0);
         });
       } else {
         const int mode = e->wsi_mode == ADP_BLEND_GAUSSIAN ? 1 : 2;
         e->launch("tta_blend", 0, by, [&] {
           tta_kernel()<<<grid, block, 0, e->stream>>>(planes, tops, S, mode, nullptr, e->wsi_acc.as<float>(),
                                                          e->wsi_wsum.as<float>(), e->wsi_window.as<float>(), e->wsi_W,
-                                                         e->wsi_rows, ys[t0 + t] - e->wsi_y0, xs[t0 + t]);
+                                                         0, e->wsi_rows, ys[t0 + t] - e->wsi_y0, xs[t0 + t]);
         });
       }
     }
@@ -868,12 +872,11 @@ void run_finalize(adp_engine *e, const float *acc, const float *wsum, int linear
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// Loss recipes (kernels_post.cuh): sums[8] = {S0 selected-BCE sum, S1 sum ys*pc, S2 sum ys, S3 sum pc, S4 sum y*p, S5 sum p,
-// S6 sum y, S7 number of BCE terms in the mean}.  Every entry is additive over data-parallel ranks.
+// Loss recipes (kernels_post.cuh): sums[8] = {S0 sum of the BCE terms in the mean, S1 sum ys*pc, S2 sum ys, S3 sum pc, S4 sum y*p,
+// S5 sum p, S6 sum y, S7 number of BCE terms in the mean}.  Every entry is additive over data-parallel ranks; the eight
+// values are produced and consumed ON THE DEVICE (a host copy is optional), so a training step needs no host round trip.
 struct LossState {
-  DevBuf sums, bce, hist, prefix, tau, tie, sum_gt;
-  std::vector<uint32_t> tau_h;
-  std::vector<float> tie_h;
+  DevBuf own_sums, row_bce, row_w, sel_sum;
   bool ohem = false;
 };
 
@@ -884,84 +887,49 @@ void loss_from_sums8(const double s[8], double out[4]) {
   out[3] = (2.0 * s[4] + 1.0) / (s[6] + s[5] + 1.0);
 }
 
-// forward part: the eight sums of `batch` images of npi pixels each (p, y device pointers)
-void loss_forward(adp_engine *e, LossState &ls, const LossRecipe &r, const float *p, const float *y, int batch, size_t npi, double s[8]) {
+// forward part: the eight sums of `batch` images of npi pixels each (p, y device pointers) into dsums (device, 8 doubles).
+// row_len = length of the trailing axis of the reference's (B, H, W) tensors: hard-example mining ranks per-ROW BCE means
+// (train_adipose_unet_v3.py:301-313, see kernels_post.cuh); without hard mining it only shapes the reduction.
+void loss_forward(adp_engine *e, LossState &ls, const LossRecipe &r, const float *p, const float *y, int batch, size_t npi,
+                  int row_len, double *dsums) {
   const size_t n = (size_t)batch * npi;
   ls.ohem = r.ohem_keep < 1.f;
-  ls.sums.ensure(64);
-  ADP_CUDA(cudaMemsetAsync(ls.sums.p, 0, 64, e->stream));
-  if (ls.ohem) ls.bce.ensure(n * 4);
-  const int grid = e->wave_grid(loss_reduce_kernel, cdiv64(n, 256 * 4));
-  e->launch("loss_reduce", 0, (double)n * (ls.ohem ? 12 : 8), [&] {
-    loss_reduce_kernel<<<grid, 256, 0, e->stream>>>(p, y, n, r.ys_scale(), r.eps_neg, ls.ohem ? ls.bce.as<float>() : nullptr,
-                                                   ls.sums.as<double>());
+  int W = row_len > 0 ? row_len : (int)std::min<size_t>(npi, 1024);
+  int R = 0; long long k = 0;
+  if (ls.ohem) {
+    ADP_REQUIRE(row_len > 0 && npi % (size_t)row_len == 0, "hard-example mining needs the row length of the (B,H,W) tensors");
+    R = (int)(npi / (size_t)row_len);
+    ADP_REQUIRE(R <= kOhemMaxRows, "hard-example mining: more than 8192 rows per image");
+    // k = int(float32(rows) * keep_ratio): tf.cast(tf.cast(num_pixels, tf.float32) * keep_ratio, tf.int32) on the (B, H) tensor
+    k = (long long)((float)R * r.ohem_keep);
+    ADP_REQUIRE(k >= 1 && k <= R, "hard-example ratio selects no row");
+    ls.row_bce.ensure((size_t)batch * R * 4); ls.row_w.ensure((size_t)batch * R * 4); ls.sel_sum.ensure((size_t)batch * 8);
+  }
+  ADP_CUDA(cudaMemsetAsync(dsums, 0, 64, e->stream));
+  const size_t rows = (size_t)cdiv64((long long)n, W);
+  const int grid = e->wave_grid(loss_reduce_kernel, (size_t)cdiv64((long long)rows, 8));
+  e->launch("loss_reduce", 0, (double)n * 8, [&] {
+    loss_reduce_kernel<<<grid, 256, 0, e->stream>>>(p, y, n, W, r.ys_scale(), r.eps_neg, ls.ohem ? ls.row_bce.as<float>() : nullptr, dsums);
   });
-  ADP_CUDA(cudaMemcpyAsync(s, ls.sums.p, 56, cudaMemcpyDeviceToHost, e->stream));
-  ADP_CUDA(cudaStreamSynchronize(e->stream));
-  s[7] = (double)n;
-  if (!ls.ohem) return;
-  // top-k per image: k = int(float(npix) * keep_ratio) (train_adipose_unet_v3.py:307-311)
-  const long long k = (long long)((float)npi * r.ohem_keep);
-  ADP_REQUIRE(k >= 1 && k <= (long long)npi, "hard-example ratio selects no pixel");
-  ls.hist.ensure((size_t)batch * 4096 * 4); ls.prefix.ensure((size_t)batch * 4); ls.tau.ensure((size_t)batch * 4);
-  ls.tie.ensure((size_t)batch * 4); ls.sum_gt.ensure((size_t)batch * 8);
-  std::vector<uint32_t> prefix(batch, 0u), hist((size_t)batch * 4096);
-  std::vector<long long> rank(batch, k), n_gt(batch, 0), n_eq(batch, 0);
-  const dim3 hgrid((unsigned)std::max<size_t>(1, std::min<size_t>(cdiv64(npi, 256 * 8), (size_t)e->num_sms * 2)), (unsigned)batch);
-  const int shifts[3] = {20, 8, 0}, bits[3] = {12, 12, 8};
-  for (int d = 0; d < 3; ++d) {
-    ADP_CUDA(cudaMemcpyAsync(ls.prefix.p, prefix.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, e->stream));
-    ADP_CUDA(cudaMemsetAsync(ls.hist.p, 0, (size_t)batch * 4096 * 4, e->stream));
-    e->launch("ohem_select", 0, (double)n * 4, [&] {
-      ohem_hist_kernel<<<hgrid, 256, 0, e->stream>>>(ls.bce.as<float>(), npi, ls.prefix.as<uint32_t>(), shifts[d], bits[d],
-                                                    ls.hist.as<unsigned int>());
+  if (ls.ohem)
+    e->launch("ohem_select", 0, (double)batch * R * 8, [&] {
+      ohem_select_kernel<<<batch, 1024, (size_t)R * 4, e->stream>>>(ls.row_bce.as<float>(), R, (int)k, 1.0f / (float)W, ls.row_w.as<float>(),
+                                                                    ls.sel_sum.as<double>());
     });
-    ADP_CUDA(cudaMemcpyAsync(hist.data(), ls.hist.p, (size_t)batch * 4096 * 4, cudaMemcpyDeviceToHost, e->stream));
-    ADP_CUDA(cudaStreamSynchronize(e->stream));
-    for (int b = 0; b < batch; ++b) {
-      const uint32_t *h = hist.data() + (size_t)b * 4096;
-      long long need = rank[b];
-      int bin = (1 << bits[d]) - 1;
-      for (; bin > 0; --bin) {
-        if ((long long)h[bin] >= need) break;
-        need -= h[bin]; n_gt[b] += h[bin];
-      }
-      rank[b] = need;                       // rank of tau inside the chosen bin
-      prefix[b] = (prefix[b] << bits[d]) | (uint32_t)bin;
-      if (d == 2) n_eq[b] = h[bin];
-    }
-  }
-  ls.tau_h = prefix;
-  ls.tie_h.resize(batch);
-  for (int b = 0; b < batch; ++b) ls.tie_h[b] = (float)((double)(k - n_gt[b]) / (double)std::max<long long>(n_eq[b], 1));
-  ADP_CUDA(cudaMemcpyAsync(ls.tau.p, ls.tau_h.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, e->stream));
-  ADP_CUDA(cudaMemcpyAsync(ls.tie.p, ls.tie_h.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, e->stream));
-  ADP_CUDA(cudaMemsetAsync(ls.sum_gt.p, 0, (size_t)batch * 8, e->stream));
-  e->launch("ohem_sum", 0, (double)n * 4, [&] {
-    ohem_sum_kernel<<<hgrid, 256, 0, e->stream>>>(ls.bce.as<float>(), npi, ls.tau.as<uint32_t>(), ls.sum_gt.as<double>());
+  e->launch("loss_finish", 0, 0, [&] {
+    loss_finish_kernel<<<1, 32, 0, e->stream>>>(dsums, ls.ohem ? ls.sel_sum.as<double>() : nullptr, batch,
+                                                ls.ohem ? (double)batch * (double)k : (double)n);
   });
-  std::vector<double> sg(batch);
-  ADP_CUDA(cudaMemcpyAsync(sg.data(), ls.sum_gt.p, (size_t)batch * 8, cudaMemcpyDeviceToHost, e->stream));
-  ADP_CUDA(cudaStreamSynchronize(e->stream));
-  double sel = 0;
-  for (int b = 0; b < batch; ++b) {
-    float tau; uint32_t tb = ls.tau_h[b]; memcpy(&tau, &tb, 4);
-    sel += sg[b] + (double)(k - n_gt[b]) * (double)tau;
-  }
-  s[0] = sel;
-  s[7] = (double)batch * (double)k;
 }
 
-// backward part: dL/dp for the loss defined by the (possibly rank-summed) sums
+// backward part: dL/dp for the loss defined by the (possibly rank-summed) device sums
 void loss_backward(adp_engine *e, LossState &ls, const LossRecipe &r, const float *p, const float *y, int batch, size_t npi,
-                   const double s[8], float *dldp, float gain = 1.f) {
+                   int row_len, const double *dsums, float *dldp, float gain = 1.f) {
   const size_t n = (size_t)batch * npi;
   const int grid = e->wave_grid(loss_grad_kernel, cdiv64(n, 256 * 4));
-  const double denom = s[2] + s[3] + 1.0;
   e->launch("loss_grad", 0, (double)n * 12, [&] {
-    loss_grad_kernel<<<grid, 256, 0, e->stream>>>(p, y, n, r.ys_scale(), r.eps_neg, (float)(1.0 / s[7]), (float)(2.0 * s[1] + 1.0),
-                                                 (float)denom, ls.ohem ? ls.tau.as<uint32_t>() : nullptr,
-                                                 ls.ohem ? ls.tie.as<float>() : nullptr, npi, gain, dldp);
+    loss_grad_kernel<<<grid, 256, 0, e->stream>>>(p, y, n, r.ys_scale(), r.eps_neg, dsums, ls.ohem ? ls.row_w.as<float>() : nullptr,
+                                                 row_len > 0 ? row_len : 1, gain, dldp);
   });
 }
 
@@ -1185,7 +1153,7 @@ int adp_tta_combine(adp_engine *e, const float *planes, int size, const int *ops
   }
   dim3 grid(cdiv(size, 32), cdiv(size, 32)), block(32, 8);
   e->launch("tta_combine", 0, (double)px * 4 * (n_ops + 1), [&] {
-    tta_kernel()<<<grid, block, 0, e->stream>>>(pl, tops, size, 0, o, nullptr, nullptr, nullptr, 0, 0, 0, 0);
+    tta_kernel()<<<grid, block, 0, e->stream>>>(pl, tops, size, 0, o, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0);
   });
   if (host) ADP_CUDA(cudaMemcpyAsync(out, o, px * 4, cudaMemcpyDeviceToHost, e->stream));
   ADP_CUDA(cudaStreamSynchronize(e->stream));
@@ -1381,7 +1349,7 @@ int adp_blend_reconstruct(adp_engine *e, int blend_mode, const float *tiles, int
     for (int t = 0; t < nt; ++t)   // stream order == list order: same accumulation order as the NumPy loop
       e->launch("blend_tile", 0, (double)tpx * 4 * (mode == 1 ? 6 : 5), [&] {
         blend_tile_kernel<<<grid, 256, 0, e->stream>>>(dt + (size_t)t * tpx, th, tw, mode, acc.as<float>(), ws.as<float>(), dw,
-                                                      tw, W, H, ys[t0 + t], xs[t0 + t]);
+                                                      tw, W, 0, H, ys[t0 + t], xs[t0 + t]);
       });
     if (th_host) ADP_CUDA(cudaStreamSynchronize(e->stream));
   }
@@ -1419,10 +1387,12 @@ int adp_wsi_push_tiles(adp_engine *e, const float *tiles, int n, const int32_t *
   ADP_CATCH
 }
 
-int adp_wsi_push_from_slide(adp_engine *e, const uint8_t *slide, int region_y0, int region_rows, int n, const int32_t *ys,
-                            const int32_t *xs, float mean, float std_, const int *ops, int n_ops) {
+int adp_wsi_push_from_slide(adp_engine *e, const uint8_t *slide, int channels, int region_y0, int region_rows, int n,
+                            const int32_t *ys, const int32_t *xs, float mean, float std_, const int *ops, int n_ops,
+                            int defer_below_row) {
   ADP_TRY
   ADP_REQUIRE(e && slide && ys && xs && n > 0, "null/empty argument");
+  ADP_REQUIRE(channels == 1 || channels == 3, "channels must be 1 (gray) or 3 (interleaved RGB)");
   if (!e->wsi_on) throw Error(ADP_ESTATE, "adp_wsi_begin not called");
   ADP_REQUIRE(is_device_ptr(slide), "slide region must be device-resident (copy it once, then push tile positions)");
   ADP_CUDA(cudaSetDevice(e->device));
@@ -1434,8 +1404,51 @@ int adp_wsi_push_from_slide(adp_engine *e, const uint8_t *slide, int region_y0, 
     org[i] = (long long)(ys[i] - region_y0) * e->wsi_W + xs[i];
   }
   FirstConvSrc s{};
-  s.u8 = slide; s.ch = 1; s.slideW = e->wsi_W;
-  run_tiles(e, 2, s, nullptr, n, S, mean, std_, ops, n_ops, nullptr, ys, xs, org.data());
+  s.u8 = slide; s.ch = channels; s.slideW = e->wsi_W;
+  const int zone = defer_below_row - e->wsi_y0;          // accumulator rows [0, zone) are deferred
+  if (zone <= 0) {
+    run_tiles(e, 2, s, nullptr, n, S, mean, std_, ops, n_ops, nullptr, ys, xs, org.data());
+    return ADP_OK;
+  }
+  // deferred boundary zone: keep the tiles' probabilities, blend the rows below the zone now, the zone rows on replay
+  ADP_REQUIRE(zone <= e->wsi_rows, "defer_below_row outside the accumulator");
+  const size_t tpx = (size_t)S * S;
+  adp_engine::Deferred d;
+  d.probs.reset(new DevBuf());
+  d.probs->ensure((size_t)n * tpx * 4);
+  d.ys.assign(ys, ys + n); d.xs.assign(xs, xs + n); d.below = zone;
+  run_tiles(e, 2, s, nullptr, n, S, mean, std_, ops, n_ops, d.probs->as<float>(), ys, xs, org.data());
+  const int mode = e->wsi_mode == ADP_BLEND_GAUSSIAN ? 1 : 2;
+  const int grid = (int)std::min<size_t>(cdiv64(tpx, 256), (size_t)e->num_sms * 8);
+  for (int t = 0; t < n; ++t)
+    e->launch("blend_tile", 0, (double)tpx * 4 * (mode == 1 ? 6 : 5), [&] {
+      blend_tile_kernel<<<grid, 256, 0, e->stream>>>(d.probs->as<float>() + (size_t)t * tpx, S, S, mode, e->wsi_acc.as<float>(),
+                                                    e->wsi_wsum.as<float>(), e->wsi_window.as<float>(), S, e->wsi_W, zone, e->wsi_rows,
+                                                    ys[t] - e->wsi_y0, xs[t]);
+    });
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  e->wsi_deferred.push_back(std::move(d));
+  ADP_CATCH
+}
+
+int adp_wsi_replay_deferred(adp_engine *e) {
+  ADP_TRY
+  ADP_REQUIRE(e, "engine");
+  if (!e->wsi_on) throw Error(ADP_ESTATE, "adp_wsi_begin not called");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const int S = e->wsi_tile;
+  const size_t tpx = (size_t)S * S;
+  const int mode = e->wsi_mode == ADP_BLEND_GAUSSIAN ? 1 : 2;
+  const int grid = (int)std::min<size_t>(cdiv64(tpx, 256), (size_t)e->num_sms * 8);
+  for (auto &d : e->wsi_deferred)      // call order == list order: the zone rows see their tiles in row-major order
+    for (size_t t = 0; t < d.ys.size(); ++t)
+      e->launch("blend_tile", 0, (double)tpx * 4 * (mode == 1 ? 6 : 5), [&] {
+        blend_tile_kernel<<<grid, 256, 0, e->stream>>>(d.probs->as<float>() + t * tpx, S, S, mode, e->wsi_acc.as<float>(),
+                                                      e->wsi_wsum.as<float>(), e->wsi_window.as<float>(), S, e->wsi_W, 0, d.below,
+                                                      d.ys[t] - e->wsi_y0, d.xs[t]);
+      });
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  e->wsi_deferred.clear();
   ADP_CATCH
 }
 
@@ -1462,7 +1475,7 @@ int adp_wsi_push_probs(adp_engine *e, const float *probs, int n, const int32_t *
       e->launch("blend_tile", 0, (double)tpx * 4 * (mode == 1 ? 6 : 5), [&] {
         blend_tile_kernel<<<grid, 256, 0, e->stream>>>(dt + (size_t)t * tpx, S, S, mode, e->wsi_acc.as<float>(),
                                                       e->wsi_wsum.as<float>(), e->wsi_window.as<float>(), S, e->wsi_W,
-                                                      e->wsi_rows, ys[t0 + t] - e->wsi_y0, xs[t0 + t]);
+                                                      0, e->wsi_rows, ys[t0 + t] - e->wsi_y0, xs[t0 + t]);
       });
     ADP_CUDA(cudaStreamSynchronize(e->stream));
   }
@@ -1518,16 +1531,18 @@ int adp_wsi_end(adp_engine *e) {
   ADP_REQUIRE(e, "engine");
   ADP_CUDA(cudaSetDevice(e->device));
   e->wsi_acc.release(); e->wsi_wsum.release(); e->wsi_window.release();
+  e->wsi_deferred.clear();
   e->wsi_on = false;
   ADP_CATCH
 }
 
-int adp_loss_metrics_ex(adp_engine *e, const float *p, const float *y, int batch, int64_t px_per_image, float ohem_keep_ratio,
-                        float eps_pos, float eps_neg, float *dldp, double out[4]) {
+int adp_loss_metrics_ex(adp_engine *e, const float *p, const float *y, int batch, int64_t px_per_image, int64_t row_len,
+                        float ohem_keep_ratio, float eps_pos, float eps_neg, float *dldp, double out[4]) {
   ADP_TRY
   ADP_REQUIRE(e && p && y && out && batch > 0 && px_per_image > 0, "null/empty argument");
   ADP_REQUIRE(ohem_keep_ratio > 0.f && ohem_keep_ratio <= 1.f && eps_pos >= 0.f && eps_neg >= 0.f && eps_pos + eps_neg < 1.f,
               "loss recipe out of range");
+  ADP_REQUIRE(row_len >= 0 && row_len <= px_per_image && row_len <= (1 << 30), "row_len");
   ADP_CUDA(cudaSetDevice(e->device));
   DevBuf dp, dy, dg;
   const size_t n = (size_t)batch * (size_t)px_per_image;
@@ -1535,14 +1550,17 @@ int adp_loss_metrics_ex(adp_engine *e, const float *p, const float *y, int batch
   const float *yy = reinterpret_cast<const float *>(to_device(e, dy, y, n * 4));
   LossRecipe r; r.ohem_keep = ohem_keep_ratio; r.eps_pos = eps_pos; r.eps_neg = eps_neg;
   LossState ls;
+  ls.own_sums.ensure(64);
   double s[8];
-  loss_forward(e, ls, r, pp, yy, batch, (size_t)px_per_image, s);
+  loss_forward(e, ls, r, pp, yy, batch, (size_t)px_per_image, (int)row_len, ls.own_sums.as<double>());
+  ADP_CUDA(cudaMemcpyAsync(s, ls.own_sums.p, 64, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
   loss_from_sums8(s, out);
   if (dldp) {
     const bool host = !is_device_ptr(dldp);
     float *g = dldp;
     if (host) { dg.ensure(n * 4); g = dg.as<float>(); }
-    loss_backward(e, ls, r, pp, yy, batch, (size_t)px_per_image, s, g);
+    loss_backward(e, ls, r, pp, yy, batch, (size_t)px_per_image, (int)row_len, ls.own_sums.as<double>(), g);
     if (host) ADP_CUDA(cudaMemcpyAsync(dldp, g, n * 4, cudaMemcpyDeviceToHost, e->stream));
     ADP_CUDA(cudaStreamSynchronize(e->stream));
   }
@@ -1550,7 +1568,7 @@ int adp_loss_metrics_ex(adp_engine *e, const float *p, const float *y, int batch
 }
 
 int adp_loss_metrics(adp_engine *e, const float *p, const float *y, int64_t n_px, float *dldp, double out[4]) {
-  return adp_loss_metrics_ex(e, p, y, 1, n_px, 1.f, 0.f, 0.f, dldp, out);
+  return adp_loss_metrics_ex(e, p, y, 1, n_px, 0, 1.f, 0.f, 0.f, dldp, out);
 }
 
 int adp_train_begin(adp_engine *e, int batch, int size, float dropout_rate, uint64_t seed) {
@@ -1567,7 +1585,7 @@ int adp_train_begin(adp_engine *e, int batch, int size, float dropout_rate, uint
 int adp_train_forward(adp_engine *e, const float *x, const float *y, int batch, const uint8_t *const *dropout_masks,
                       double *sums) {
   ADP_TRY
-  ADP_REQUIRE(e && x && y && sums, "null argument");
+  ADP_REQUIRE(e && x && y, "null argument");
   ADP_CUDA(cudaSetDevice(e->device));
   train_forward(e, x, y, batch, dropout_masks, sums);
   ADP_CATCH
@@ -1604,9 +1622,34 @@ int adp_train_outputs(adp_engine *e) { return e && e->deep_sup ? 3 : 1; }
 
 int adp_train_backward(adp_engine *e, const double *sums, int freeze_encoder) {
   ADP_TRY
-  ADP_REQUIRE(e && sums, "null argument");
+  ADP_REQUIRE(e, "null argument");
   ADP_CUDA(cudaSetDevice(e->device));
   train_backward(e, sums, freeze_encoder != 0);
+  ADP_CATCH
+}
+
+int adp_train_sums_buffer(adp_engine *e, double **dev_ptr, int *count) {
+  ADP_TRY
+  ADP_REQUIRE(e && dev_ptr && count, "null argument");
+  if (!e->tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
+  *dev_ptr = e->tr->dsums.as<double>();
+  *count = e->deep_sup ? 24 : 8;
+  ADP_CATCH
+}
+
+int adp_train_sums_read(adp_engine *e, double *host, int count) {
+  ADP_TRY
+  ADP_REQUIRE(e && host, "null argument");
+  if (!e->tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
+  ADP_REQUIRE(count == (e->deep_sup ? 24 : 8), "count != 8 x outputs");
+  ADP_CUDA(cudaSetDevice(e->device));
+  if (e->tr->sums_mirrored) {       // the values the last backward used: wait for their mirror only, not for the whole step
+    ADP_CUDA(cudaEventSynchronize(e->tr->ev_sums));
+    memcpy(host, e->tr->pinned_sums, (size_t)count * 8);
+  } else {
+    ADP_CUDA(cudaMemcpyAsync(host, e->tr->dsums.p, (size_t)count * 8, cudaMemcpyDeviceToHost, e->stream));
+    ADP_CUDA(cudaStreamSynchronize(e->stream));
+  }
   ADP_CATCH
 }
 
@@ -1616,6 +1659,37 @@ int adp_train_grad_buffer(adp_engine *e, float **dev_ptr, int64_t *count) {
   if (!e->tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
   *dev_ptr = e->tr->grad.as<float>();
   *count = (int64_t)e->tr->P;
+  ADP_CATCH
+}
+
+int adp_train_grad_buckets(adp_engine *e, int64_t *lo, int64_t *hi, int cap) {
+  ADP_TRY
+  ADP_REQUIRE(e, "engine");
+  if (!e->tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
+  const int n = (int)e->tr->buckets.size();
+  if (lo && hi)
+    for (int b = 0; b < n && b < cap; ++b) { lo[b] = (int64_t)e->tr->buckets[b].lo; hi[b] = (int64_t)e->tr->buckets[b].hi; }
+  return n;
+  ADP_CATCH
+}
+
+int adp_train_bucket_wait(adp_engine *e, int bucket, void *stream) {
+  ADP_TRY
+  ADP_REQUIRE(e, "engine");
+  if (!e->tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
+  ADP_REQUIRE(bucket >= 0 && bucket < (int)e->tr->buckets.size(), "bucket index");
+  ADP_CUDA(cudaSetDevice(e->device));
+  ADP_CUDA(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), e->tr->buckets[bucket].ev, 0));
+  ADP_CATCH
+}
+
+int adp_train_join(adp_engine *e, void *stream) {
+  ADP_TRY
+  ADP_REQUIRE(e, "engine");
+  if (!e->tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
+  ADP_CUDA(cudaSetDevice(e->device));
+  ADP_CUDA(cudaEventRecord(e->tr->ev_join, reinterpret_cast<cudaStream_t>(stream)));
+  ADP_CUDA(cudaStreamWaitEvent(e->stream, e->tr->ev_join, 0));
   ADP_CATCH
 }
 
@@ -1702,8 +1776,9 @@ int adp_train_step(adp_engine *e, const float *x, const float *y, int batch, int
       out[0] = e->ds_w[0] * out[0] + e->ds_w[1] * a1[0] + e->ds_w[2] * a2[0];
     }
   }
-  train_backward(e, sums, freeze_encoder != 0);
+  train_backward(e, nullptr, freeze_encoder != 0);
   train_apply(e, optimizer, lr, 1.f, 0.9, 0.999, 1e-7f, weight_decay, freeze_encoder != 0);
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
   ADP_CATCH
 }
 

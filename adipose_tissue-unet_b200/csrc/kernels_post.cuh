@@ -19,6 +19,8 @@ namespace adp {
 // mode 1: Gaussian blend: acc[y+i][x+j] += avg*w[i][j]; wsum[y+i][x+j] += w[i][j]
 //         (GaussianBlender.reconstruct, full_evaluation_enhanced.py:165-173)
 // mode 2: linear blend:   acc += avg; wsum(count as float) += 1   (LinearBlender, :196-199)
+// Only accumulator rows [rlo, rhi) are touched (the whole accumulator normally; a strip that defers its boundary zone
+// blends the rows below the zone first and replays the zone rows after the upper strip's partial sums have arrived).
 struct TtaOps { int n; int inv[8]; };
 
 // All source blocks (one 32x32 block per augmentation) are requested before the single barrier: 4 * n loads per thread in
@@ -27,7 +29,7 @@ struct TtaOps { int n; int inv[8]; };
 __global__ void __launch_bounds__(256)
 tta_blend_kernel(const float *__restrict__ planes, TtaOps ops, int S, int mode, float *__restrict__ out,
                  float *__restrict__ acc, float *__restrict__ wsum, const float *__restrict__ window,
-                 int accW, int accRows, int ty, int tx) {
+                 int accW, int rlo, int rhi, int ty, int tx) {
   __shared__ float tile[8][32][33];
   const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
   const int lx = threadIdx.x, ly = threadIdx.y;     // 32 x 8
@@ -88,7 +90,7 @@ tta_blend_kernel(const float *__restrict__ planes, TtaOps ops, int S, int mode, 
       out[(size_t)i * S + j] = avg;
     } else {
       int gy = ty + i, gx = tx + j;
-      if (gy < 0 || gy >= accRows || gx < 0 || gx >= accW) continue;
+      if (gy < rlo || gy >= rhi || gx < 0 || gx >= accW) continue;
       size_t g = (size_t)gy * accW + gx;
       if (mode == 1) {
         float w = window[(size_t)i * S + j];
@@ -105,7 +107,7 @@ tta_blend_kernel(const float *__restrict__ planes, TtaOps ops, int S, int mode, 
 __global__ void __launch_bounds__(256)
 tta_blend_serial_kernel(const float *__restrict__ planes, TtaOps ops, int S, int mode, float *__restrict__ out,
                         float *__restrict__ acc, float *__restrict__ wsum, const float *__restrict__ window,
-                        int accW, int accRows, int ty, int tx) {
+                        int accW, int rlo, int rhi, int ty, int tx) {
   __shared__ float tile[32][33];
   const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
   const int lx = threadIdx.x, ly = threadIdx.y;     // 32 x 8
@@ -147,7 +149,7 @@ tta_blend_serial_kernel(const float *__restrict__ planes, TtaOps ops, int S, int
       out[(size_t)i * S + j] = avg;
     } else {
       int gy = ty + i, gx = tx + j;
-      if (gy < 0 || gy >= accRows || gx < 0 || gx >= accW) continue;
+      if (gy < rlo || gy >= rhi || gx < 0 || gx >= accW) continue;
       size_t g = (size_t)gy * accW + gx;
       if (mode == 1) {
         float w = window[(size_t)i * S + j];
@@ -165,13 +167,13 @@ tta_blend_serial_kernel(const float *__restrict__ planes, TtaOps ops, int S, int
 // adp_wsi_push_probs).  One thread per tile pixel.
 __global__ void __launch_bounds__(256)
 blend_tile_kernel(const float *__restrict__ tile, int th, int tw, int mode, float *__restrict__ acc,
-                  float *__restrict__ wsum, const float *__restrict__ window, int winW, int accW, int accRows,
+                  float *__restrict__ wsum, const float *__restrict__ window, int winW, int accW, int rlo, int rhi,
                   int ty, int tx) {
   const size_t total = (size_t)th * tw;
   for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
     int i = p / tw, j = p % tw;
     int gy = ty + i, gx = tx + j;
-    if (gy < 0 || gy >= accRows || gx < 0 || gx >= accW) continue;
+    if (gy < rlo || gy >= rhi || gx < 0 || gx >= accW) continue;
     size_t g = (size_t)gy * accW + gx;
     float v = tile[p];
     if (mode == 1) {
@@ -285,106 +287,124 @@ threshold_sweep_kernel(const float *__restrict__ prob, const uint8_t *__restrict
 // Loss family of the reference (train_adipose_unet_v3.py:217-363) and dice_coef (src/utils/model.py:93-98):
 //   combined_loss_standard                       bce_mean(y, p) + dice_loss(y, p)
 //   combined_loss_with_label_smoothing           same on ys = y*(1 - eps_pos - eps_neg) + eps_neg          (:244-279)
-//   online_hard_example_mining_loss[_with_smoothing]   mean of the top-k per-image BCE values (k = int(npix*ratio))
-//                                                + dice_loss over all pixels                               (:282-363)
-// Pass 1 (loss_reduce_kernel): float64 sums  S0 = sum bce_i, S1 = sum ys*pc, S2 = sum ys, S3 = sum pc,
-//         S4 = sum y*p, S5 = sum p, S6 = sum y  (pc = clip(p, 1e-7, 1-1e-7); the metric dice_coef uses the raw y);
-//         optionally the per-pixel BCE values are kept for the top-k selection.
-// OHEM:   per image a three-digit radix select (12 + 12 + 8 bits of the non-negative float's bit pattern,
-//         ohem_hist_kernel + a short host scan per digit) finds tau = the k-th largest BCE value; ohem_sum_kernel adds
-//         the values above tau; the k - n_gt entries equal to tau count with weight (k - n_gt)/n_eq each (TensorFlow's
-//         top_k breaks ties arbitrarily; ties carry no gradient where the clip is active).
-// Pass 2 (loss_grad_kernel; the host forms the scalars): dL/dp_i = w_i * dbce_i / N + ddice_i with
+//   online_hard_example_mining_loss[_with_smoothing]                                                        (:282-363)
+//       tf.keras.losses.binary_crossentropy averages its LAST axis, and the model output / target are (B, H, W)
+//       (:748-750, :611-613), so "per_pixel_bce" is the (B, H) tensor of per-ROW means; flat_loss is (B, H),
+//       k = int(float32(H) * keep_ratio) (716 of 1024 rows at the default 0.7) and hard_bce is the mean of the k largest
+//       row means of every image.  dice_loss runs over all pixels.
+// Pass 1 (loss_reduce_kernel, one warp per image row): float64 sums  S0 = sum bce_i, S1 = sum ys*pc, S2 = sum ys,
+//         S3 = sum pc, S4 = sum y*p, S5 = sum p, S6 = sum y  (pc = clip(p, 1e-7, 1-1e-7); the metric dice_coef uses the raw y);
+//         with hard mining the per-row BCE means are kept (float32, like the tensor TensorFlow ranks).
+// OHEM:   ohem_select_kernel, one block per image: rank of every row mean by counting (ties go to the lower row index, as in
+//         tf.nn.top_k), rows with rank < k are selected: row_w = 1/W (the d(row mean)/d(pixel bce) factor) else 0; the
+//         selected means are summed in a fixed order.
+// Finish: loss_finish_kernel writes S0 (hard mining: sum of the selected row means) and S7 = number of BCE terms in the mean
+//         (all pixels, or batch*k rows), so that the eight sums live on the device, additive over data-parallel ranks.
+// Pass 2 (loss_grad_kernel, scalars read from the device sums): dL/dp_i = w_i * dbce_i / S7 + ddice_i with
 //   dbce_i  = -( ys/(pc+eps) - (1-ys)/(1-pc+eps) ) * [eps <= p <= 1-eps]
 //   ddice_i = -( 2*ys*D - (2I+1) ) / D^2 * [eps <= p <= 1-eps],  I = S1, D = S2 + S3 + 1
-//   N = number of BCE terms in the mean (all pixels, or batch*k), w_i = OHEM selection weight (1 without OHEM)
+//   w_i = row_w[row of i] with hard mining, 1 otherwise
 struct LossRecipe {
   float ohem_keep = 1.f;     // 1 = no hard-example mining
   float eps_pos = 0.f, eps_neg = 0.f;
   __host__ __device__ float ys_scale() const { return 1.0f - eps_pos - eps_neg; }
 };
 
-ADP_DEVINL float bce_term(float pv, float ys) {
-  const float eps = 1e-7f;
-  const float pc = fminf(fmaxf(pv, eps), 1.0f - eps);
-  return -(ys * logf(pc + eps) + (1.0f - ys) * logf(1.0f - pc + eps));
-}
+constexpr int kOhemMaxRows = 8192;      // rows per image the one-block select holds in shared memory
 
+// rows of W pixels (the last one may be short when n % W != 0: flat calls without hard mining); one warp per row
 __global__ void __launch_bounds__(256)
-loss_reduce_kernel(const float *__restrict__ p, const float *__restrict__ y, size_t n, float ys_a, float ys_b,
-                   float *__restrict__ bce_out /* or null */, double *__restrict__ sums) {
+loss_reduce_kernel(const float *__restrict__ p, const float *__restrict__ y, size_t n, int W, float ys_a, float ys_b,
+                   float *__restrict__ row_bce /* or null */, double *__restrict__ sums) {
   double sb = 0, syp = 0, sy = 0, spc = 0, sypr = 0, sp = 0, syr = 0;
   const float eps = 1e-7f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float pv = p[i], yr = y[i];
-    const float yv = yr * ys_a + ys_b;
-    const float pc = fminf(fmaxf(pv, eps), 1.0f - eps);
-    const float bce = -(yv * logf(pc + eps) + (1.0f - yv) * logf(1.0f - pc + eps));
-    if (bce_out) bce_out[i] = fmaxf(bce, 0.f);          // -0.0 -> +0.0: the bit pattern is the sort key
-    sb += bce; syp += (double)yv * pc; sy += yv; spc += pc; sypr += (double)yr * pv; sp += pv; syr += yr;
+  const int lane = threadIdx.x & 31;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const size_t rows = (n + (size_t)W - 1) / (size_t)W;
+  for (size_t r = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
+    const size_t base = r * (size_t)W;
+    const int len = (int)((n - base) < (size_t)W ? (n - base) : (size_t)W);
+    double rb = 0;
+    for (int j = lane; j < len; j += 32) {
+      const float pv = p[base + j], yr = y[base + j];
+      const float yv = yr * ys_a + ys_b;
+      const float pc = fminf(fmaxf(pv, eps), 1.0f - eps);
+      const float bce = -(yv * logf(pc + eps) + (1.0f - yv) * logf(1.0f - pc + eps));
+      rb += bce; syp += (double)yv * pc; sy += yv; spc += pc; sypr += (double)yr * pv; sp += pv; syr += yr;
+    }
+    sb += rb;
+    if (row_bce) {
+      rb = warp_sum_d(rb);
+      if (lane == 0) row_bce[r] = (float)(rb / (double)W);
+    }
   }
   sb = warp_sum_d(sb); syp = warp_sum_d(syp); sy = warp_sum_d(sy); spc = warp_sum_d(spc);
   sypr = warp_sum_d(sypr); sp = warp_sum_d(sp); syr = warp_sum_d(syr);
-  if ((threadIdx.x & 31) == 0) {
+  if (lane == 0) {
     atomicAdd(&sums[0], sb); atomicAdd(&sums[1], syp); atomicAdd(&sums[2], sy);
     atomicAdd(&sums[3], spc); atomicAdd(&sums[4], sypr); atomicAdd(&sums[5], sp); atomicAdd(&sums[6], syr);
   }
 }
 
-// One radix digit of the per-image top-k select.  Elements whose bits above `shift + nbits` equal prefix[image]
-// are counted by their digit (bits [shift, shift+nbits)).  grid = (blocks per image, images).
-__global__ void __launch_bounds__(256)
-ohem_hist_kernel(const float *__restrict__ bce, size_t npi, const uint32_t *__restrict__ prefix, int shift, int nbits,
-                 unsigned int *__restrict__ hist /*[images][4096]*/) {
-  __shared__ unsigned int h[4096];
-  const int img = blockIdx.y;
-  const int nb = 1 << nbits;
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) h[i] = 0;
+// One block (1024 threads) per image: top-k of the R row means by rank counting; dynamic shared memory = R floats.
+__global__ void __launch_bounds__(1024)
+ohem_select_kernel(const float *__restrict__ row_bce, int R, int k, float inv_w, float *__restrict__ row_w,
+                   double *__restrict__ sel_sum) {
+  extern __shared__ float sv[];
+  __shared__ double part[32];
+  const int img = blockIdx.x;
+  const float *b = row_bce + (size_t)img * R;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) sv[i] = b[i];
   __syncthreads();
-  const int hi_shift = shift + nbits;
-  const uint32_t pre = prefix[img];
-  const float *b = bce + (size_t)img * npi;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npi; i += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t u = __float_as_uint(b[i]);
-    if (hi_shift >= 32 || (u >> hi_shift) == pre) atomicAdd(&h[(u >> shift) & (uint32_t)(nb - 1)], 1u);
+  double mine = 0;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    const float v = sv[i];
+    int rank = 0;
+    for (int j = 0; j < R; ++j) {
+      const float u = sv[j];
+      rank += (u > v) || (u == v && j < i);
+    }
+    const bool sel = rank < k;
+    row_w[(size_t)img * R + i] = sel ? inv_w : 0.f;
+    if (sel) mine += (double)v;
   }
+  mine = warp_sum_d(mine);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = mine;
   __syncthreads();
-  for (int i = threadIdx.x; i < nb; i += blockDim.x)
-    if (h[i]) atomicAdd(&hist[(size_t)img * 4096 + i], h[i]);
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w];
+    sel_sum[img] = s;
+  }
 }
 
-// sum of the BCE values strictly above tau (per image, float64)
-__global__ void __launch_bounds__(256)
-ohem_sum_kernel(const float *__restrict__ bce, size_t npi, const uint32_t *__restrict__ tau_bits, double *__restrict__ sum_gt) {
-  const int img = blockIdx.y;
-  const uint32_t t = tau_bits[img];
-  const float *b = bce + (size_t)img * npi;
-  double s = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npi; i += (size_t)gridDim.x * blockDim.x) {
-    const float v = b[i];
-    if (__float_as_uint(v) > t) s += v;
+// sums[7] = number of BCE terms in the mean; with hard mining sums[0] = sum over images of the selected row means
+__global__ void loss_finish_kernel(double *__restrict__ sums, const double *__restrict__ sel_sum /* or null */, int batch,
+                                   double n_terms) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (sel_sum) {
+      double s = 0;
+      for (int b = 0; b < batch; ++b) s += sel_sum[b];
+      sums[0] = s;
+    }
+    sums[7] = n_terms;
   }
-  s = warp_sum_d(s);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&sum_gt[img], s);
 }
 
 __global__ void __launch_bounds__(256)
-loss_grad_kernel(const float *__restrict__ p, const float *__restrict__ y, size_t n, float ys_a, float ys_b, float inv_n,
-                 float inter2p1, float denom, const uint32_t *__restrict__ tau_bits /* or null */,
-                 const float *__restrict__ tie_w, size_t npi, float gain /* loss weight of this output */, float *__restrict__ dldp) {
+loss_grad_kernel(const float *__restrict__ p, const float *__restrict__ y, size_t n, float ys_a, float ys_b,
+                 const double *__restrict__ sums, const float *__restrict__ row_w /* or null */, int W,
+                 float gain /* loss weight of this output */, float *__restrict__ dldp) {
   const float eps = 1e-7f;
+  const double s1 = sums[1], s2 = sums[2], s3 = sums[3], s7 = sums[7];
+  const float inv_n = (float)(1.0 / s7), inter2p1 = (float)(2.0 * s1 + 1.0), denom = (float)(s2 + s3 + 1.0);
   const float inv_d2 = 1.0f / (denom * denom);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float pv = p[i];
     const float yv = y[i] * ys_a + ys_b;
     float g = 0.f;
     if (pv >= eps && pv <= 1.0f - eps) {
-      float w = 1.f;
-      if (tau_bits) {
-        const size_t img = i / npi;
-        const uint32_t u = __float_as_uint(fmaxf(bce_term(pv, yv), 0.f)), t = tau_bits[img];
-        w = u > t ? 1.f : (u == t ? tie_w[img] : 0.f);
-      }
+      const float w = row_w ? row_w[i / (size_t)W] : 1.f;
       const float dbce = -(yv / (pv + eps) - (1.0f - yv) / (1.0f - pv + eps));
       const float ddice = -(2.0f * yv * denom - inter2p1) * inv_d2;
       g = (w * dbce * inv_n + ddice) * gain;

@@ -39,16 +39,16 @@ struct FirstConvSrc {
   const float *f32;     // n_tiles * S * S, or null
   const uint8_t *u8;    // n_tiles * S * S * ch, or null (ch = 1 or 3); or a slide region
   int ch;
-  // slide mode (u8, ch==1): tile t starts at slide_origin[t] = (y*slideW + x) within u8
+  // slide mode (u8, ch = 1 or 3 interleaved): tile t starts at PIXEL slide_origin[t] = y*slideW + x of the region
   const int64_t *slide_origin;
-  int slideW;           // row pitch in bytes of the slide region (0 = packed tiles)
+  int slideW;           // row pitch in pixels of the slide region (0 = packed tiles)
 };
 
 ADP_DEVINL float first_conv_fetch(const FirstConvSrc &s, int tile, int S, int si, int sj) {
   if (s.f32) return s.f32[((size_t)tile * S + si) * S + sj];
-  if (s.slideW) return (float)s.u8[s.slide_origin[tile] + (int64_t)si * s.slideW + sj];
-  if (s.ch == 1) return (float)s.u8[((size_t)tile * S + si) * S + sj];
-  const uint8_t *q = s.u8 + (((size_t)tile * S + si) * S + sj) * 3;
+  const size_t px = s.slideW ? (size_t)(s.slide_origin[tile] + (int64_t)si * s.slideW + sj) : ((size_t)tile * S + si) * S + sj;
+  if (s.ch == 1) return (float)s.u8[px];
+  const uint8_t *q = s.u8 + px * 3;
   int y = (9798 * (int)q[0] + 19235 * (int)q[1] + 3735 * (int)q[2] + 16384) >> 15;   // OpenCV 4.x RGB2GRAY, 8-bit
   return (float)y;
 }

@@ -55,6 +55,21 @@ struct TrainState {
   DevBuf gw_first, gb_first, g_head;     // [9][cp0], [cp0], double [cp0 + 1]
   DevBuf zeros;
   LossState ls;
+  DevBuf dsums;               // 8 doubles per output (main, aux1, aux2): the loss sums, device-resident
+  double *pinned_sums = nullptr;      // host mirror written by an async copy at the start of every backward
+  cudaEvent_t ev_sums = nullptr;      // ... and the event that says it has landed (the loss of a step is read without draining the stream)
+  bool sums_mirrored = false;
+  // gradient buckets for a data-parallel caller: contiguous ranges of the flat gradient in the order the backward pass
+  // completes them, each with an event recorded on the engine's stream when its last weight gradient has been written
+  struct Bucket { size_t lo = 0, hi = 0; cudaEvent_t ev = nullptr; };
+  std::vector<Bucket> buckets;
+  cudaEvent_t ev_join = nullptr;
+  ~TrainState() {
+    if (pinned_sums) cudaFreeHost(pinned_sums);
+    if (ev_sums) cudaEventDestroy(ev_sums);
+    if (ev_join) cudaEventDestroy(ev_join);
+    for (auto &b : buckets) if (b.ev) cudaEventDestroy(b.ev);
+  }
   DevBuf x, y, dldp;
   // activations
   DevBuf d1a, cat1, u1b, u1c, pl1, d2a, cat2, u2b, u2c, pl2, d3a, cat3, u3b, u3c, pl3, t[6], ts, prob;
@@ -172,6 +187,10 @@ void train_alloc(adp_engine *e, int nb, int S, float dropout_rate, uint64_t seed
   tr->g_hi.ensure(n * std::max({s1 * cp[1], s2 * cp[2], s3 * cp[3]}) * es);
   tr->prob.ensure(n * s1 * 4); tr->x.ensure(n * s1 * 4); tr->y.ensure(n * s1 * 4); tr->dldp.ensure(n * s1 * 4);
   tr->zeros.ensure(4096); ADP_CUDA(cudaMemset(tr->zeros.p, 0, 4096));
+  tr->dsums.ensure(24 * 8); ADP_CUDA(cudaMemset(tr->dsums.p, 0, 24 * 8));
+  ADP_CUDA(cudaMallocHost(&tr->pinned_sums, 24 * 8));
+  ADP_CUDA(cudaEventCreateWithFlags(&tr->ev_sums, cudaEventDisableTiming));
+  ADP_CUDA(cudaEventCreateWithFlags(&tr->ev_join, cudaEventDisableTiming));
   e->fwt_tile.ensure(64 * 4); e->fwt_op.ensure(64 * 4); e->fwt_origin.ensure(64 * 8);
   Acts &a = tr->acts;
   a.d1a = &tr->d1a; a.cat1 = &tr->cat1; a.u1b = &tr->u1b; a.u1c = &tr->u1c; a.pl1 = &tr->pl1;
@@ -200,6 +219,17 @@ void train_alloc(adp_engine *e, int nb, int S, float dropout_rate, uint64_t seed
     off += ke + be;
   }
   tr->P = off;
+  {
+    // completion order of the backward pass: decoder + heads, dilate6..4, dilate3..1, encoder
+    auto koff_of = [&](const char *nm) { for (size_t i = 0; i < e->layers.size(); ++i) if (e->layers[i].name == nm) return tr->tl[i].koff; return (size_t)0; };
+    const size_t o_d1 = koff_of("dilate1"), o_d4 = koff_of("dilate4"), o_u3 = koff_of("up3_conv1");
+    const size_t cuts[5] = {off, o_u3, o_d4, o_d1, 0};
+    tr->buckets.resize(4);
+    for (int b = 0; b < 4; ++b) {
+      tr->buckets[b].lo = cuts[b + 1]; tr->buckets[b].hi = cuts[b];
+      ADP_CUDA(cudaEventCreateWithFlags(&tr->buckets[b].ev, cudaEventDisableTiming));
+    }
+  }
   tr->theta.ensure(off * 4); tr->grad.ensure(off * 4); tr->m.ensure(off * 4); tr->v.ensure(off * 4);
   ADP_CUDA(cudaMemcpy(tr->theta.p, h.data(), off * 4, cudaMemcpyHostToDevice));
   ADP_CUDA(cudaMemset(tr->grad.p, 0, off * 4));
@@ -235,7 +265,7 @@ void train_alloc(adp_engine *e, int nb, int S, float dropout_rate, uint64_t seed
 }
 
 // ---- forward -----------------------------------------------------------------------------------
-void train_forward(adp_engine *e, const float *x, const float *y, int n, const uint8_t *const *masks, double *sums /* 8 per output */) {
+void train_forward(adp_engine *e, const float *x, const float *y, int n, const uint8_t *const *masks, double *sums /* 8 per output, or null: stay on the device */) {
   TrainState *tr = e->tr;
   if (!tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
   ADP_REQUIRE(n == tr->nb, "batch size differs from adp_train_begin");
@@ -266,7 +296,8 @@ void train_forward(adp_engine *e, const float *x, const float *y, int n, const u
   DropSpec none;   // keep == 1, no masks: the dropout kernels are skipped but the fused head is still off
   if (e->prec == ADP_PREC_FP32) forward_t<float>(e, tr->acts, S, src, fw, n, 0.f, 1.f, nullptr, dropping ? &d : &none);
   else forward_t<__nv_bfloat16>(e, tr->acts, S, src, fw, n, 0.f, 1.f, nullptr, dropping ? &d : &none);
-  loss_forward(e, tr->ls, e->loss, tr->prob.as<float>(), tr->y.as<float>(), n, (size_t)S * S, sums);
+  double *ds = tr->dsums.as<double>();
+  loss_forward(e, tr->ls, e->loss, tr->prob.as<float>(), tr->y.as<float>(), n, (size_t)S * S, S, ds);
   if (e->deep_sup) {
     // aux_out1 <- post-dropout up3 (S/4), aux_out2 <- post-dropout up2 (S/2); their losses never use hard mining
     // (train_adipose_unet_v3.py:812-838: loss_fn_aux is the standard or the label-smoothing loss)
@@ -288,10 +319,14 @@ void train_forward(adp_engine *e, const float *x, const float *y, int n, const u
       e->launch("aux_bilinear_up", 0, (double)npx * 4 + (double)lowpx * 4, [&] {
         bilinear_up_kernel<<<ew_grid(e, npx), 256, 0, e->stream>>>(tr->a_low[a].as<float>(), n, hs[a], S, tr->aux_full[a].as<float>());
       });
-      loss_forward(e, tr->ls_aux[a], ra, tr->aux_full[a].as<float>(), tr->y.as<float>(), n, (size_t)S * S, sums + 8 * (a + 1));
+      loss_forward(e, tr->ls_aux[a], ra, tr->aux_full[a].as<float>(), tr->y.as<float>(), n, (size_t)S * S, S, ds + 8 * (a + 1));
     }
   }
-  tr->have_forward = true; tr->have_grads = false;
+  if (sums) {
+    ADP_CUDA(cudaMemcpyAsync(sums, ds, (size_t)(e->deep_sup ? 24 : 8) * 8, cudaMemcpyDeviceToHost, e->stream));
+    ADP_CUDA(cudaStreamSynchronize(e->stream));
+  }
+  tr->have_forward = true; tr->have_grads = false; tr->sums_mirrored = false;
 }
 
 // ---- backward ----------------------------------------------------------------------------------
@@ -415,13 +450,14 @@ size_t layer_index(adp_engine *e, const char *n) {
   throw Error(ADP_EINVAL, std::string("unknown layer ") + n);
 }
 
-template <typename T> void backward_t(adp_engine *e, bool freeze_encoder, const double *tr_sums) {
+template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
   TrainState *tr = e->tr;
   Bwd<T> B{e, tr, tr->nb};
   const int nb = tr->nb, S = tr->S, S2 = S / 2, S3 = S / 4, S4 = S / 8;
   const int *cp = e->cp;
   const float inv_keep = 1.f / tr->keep;
   auto li = [&](const char *n) { return layer_index(e, n); };
+  auto bucket_done = [&](int b) { ADP_CUDA(cudaEventRecord(tr->buckets[b].ev, e->stream)); };
 
   // head: dL/dp -> dL/d(pre-activation of up1_conv3) (ReLU' and dropout folded in), head weight gradients
   {
@@ -461,8 +497,8 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder, const 
     const size_t npx = (size_t)nb * S * S;
     for (int a = 0; a < 2; ++a) {
       const size_t lowpx = (size_t)nb * hs[a] * hs[a];
-      loss_backward(e, tr->ls_aux[a], ra, tr->aux_full[a].as<float>(), tr->y.as<float>(), nb, (size_t)S * S, tr_sums + 8 * (a + 1),
-                    tr->dldp.as<float>(), e->ds_w[a + 1]);
+      loss_backward(e, tr->ls_aux[a], ra, tr->aux_full[a].as<float>(), tr->y.as<float>(), nb, (size_t)S * S, S,
+                    tr->dsums.as<double>() + 8 * (a + 1), tr->dldp.as<float>(), e->ds_w[a + 1]);
       e->launch("aux_bilinear_up_bwd", 0, (double)npx * 4 + (double)lowpx * 4, [&] {
         bilinear_up_bwd_kernel<<<ew_grid(e, lowpx), 256, 0, e->stream>>>(tr->dldp.as<float>(), nb, hs[a], S, 1.0f, tr->g_low.as<float>());
       });
@@ -503,6 +539,7 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder, const 
       B.dgrad(li(q.c1), g_cat_up, g_ts);
     }
   }
+  bucket_done(0);
   // bottleneck: Add fans g_ts out to the six dilate outputs; the chain adds the downstream conv's data gradient
   const char *dn[6] = {"dilate1", "dilate2", "dilate3", "dilate4", "dilate5", "dilate6"};
   auto VT = [&](const DevBuf &b) { return B.V(b, S4, cp[3], 0, cp[3]); };
@@ -514,9 +551,11 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder, const 
     auto m = VT(tr->t[i - 1]), r = VT(tr->g_ts);
     B.dgrad(li(dn[i]), VT(tr->gt[cur]), VT(tr->gt[cur ^ 1]), &m, i == 1 ? inv_keep : 1.f, &r);
     cur ^= 1;
+    if (i == 3) bucket_done(1);
   }
   B.wgrad(li("dilate1"), B.V(tr->pl3, S4, cp[2], 0, cp[2]), VT(tr->gt[cur]));
-  if (freeze_encoder) return;     // phase 1: nothing upstream is trainable (train_adipose_unet_v3.py:760-769)
+  bucket_done(2);
+  if (freeze_encoder) { bucket_done(3); return; }     // phase 1: nothing upstream is trainable (train_adipose_unet_v3.py:760-769)
   // encoder, levels 3..1
   for (int l = 2; l >= 0; --l) {
     const Lvl &q = lv[l];
@@ -566,21 +605,26 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder, const 
     });
     ADP_CUDA(cudaMemcpyAsync(tr->grad.as<float>() + tr->boff_first, tr->gb_first.p, (size_t)e->c[0] * 4, cudaMemcpyDeviceToDevice, e->stream));
   }
+  bucket_done(3);
 }
 
-void train_backward(adp_engine *e, const double *sums /* 8 per output */, bool freeze_encoder) {
+void train_backward(adp_engine *e, const double *sums /* 8 per output (host), or null: the device sums as they stand */, bool freeze_encoder) {
   TrainState *tr = e->tr;
   if (!tr || !tr->have_forward) throw Error(ADP_ESTATE, "adp_train_forward must run first");
-  loss_backward(e, tr->ls, e->loss, tr->prob.as<float>(), tr->y.as<float>(), tr->nb, (size_t)tr->S * tr->S, sums, tr->dldp.as<float>(),
-                e->deep_sup ? e->ds_w[0] : 1.f);
+  const size_t sbytes = (size_t)(e->deep_sup ? 24 : 8) * 8;
+  if (sums) ADP_CUDA(cudaMemcpyAsync(tr->dsums.p, sums, sbytes, cudaMemcpyHostToDevice, e->stream));
+  ADP_CUDA(cudaMemcpyAsync(tr->pinned_sums, tr->dsums.p, sbytes, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaEventRecord(tr->ev_sums, e->stream));
+  tr->sums_mirrored = true;
+  loss_backward(e, tr->ls, e->loss, tr->prob.as<float>(), tr->y.as<float>(), tr->nb, (size_t)tr->S * tr->S, tr->S, tr->dsums.as<double>(),
+                tr->dldp.as<float>(), e->deep_sup ? e->ds_w[0] : 1.f);
   if (freeze_encoder) {   // frozen tensors report zero gradient
     const size_t first_trainable = tr->tl[layer_index(e, "dilate1")].koff;
     ADP_CUDA(cudaMemsetAsync(tr->grad.p, 0, first_trainable * 4, e->stream));
   }
-  if (e->prec == ADP_PREC_FP32) backward_t<float>(e, freeze_encoder, sums);
-  else backward_t<__nv_bfloat16>(e, freeze_encoder, sums);
-  ADP_CUDA(cudaStreamSynchronize(e->stream));
-  tr->have_grads = true;
+  if (e->prec == ADP_PREC_FP32) backward_t<float>(e, freeze_encoder);
+  else backward_t<__nv_bfloat16>(e, freeze_encoder);
+  tr->have_grads = true;       // stream-ordered: no host synchronisation inside a step (readers of the gradient synchronise)
 }
 
 // Keras Adam / AdamW (train_adipose_unet_v3.py:801-806; epsilon outside the bias correction)
@@ -602,7 +646,6 @@ void train_apply(adp_engine *e, int optimizer, float lr, float grad_scale, doubl
   tr->iter = t;
   tr->host_stale = true;
   repack_from_theta(e);
-  ADP_CUDA(cudaStreamSynchronize(e->stream));
   tr->have_grads = false; tr->have_forward = false;
 }
 

@@ -6,10 +6,15 @@ with two exchanges between ranks:
 * eight float64 loss sums before backward (``dice_mode="global"``): the reference's Dice term is defined over the
   WHOLE batch (train_adipose_unet_v3.py:217-225), so the exact data-parallel equivalent of a single-GPU step on the
   concatenated batch needs sum(y*p), sum(y), sum(p) over all ranks before dL/dp is formed.  ``dice_mode="replica"``
-  skips this exchange and averages per-replica gradients instead (what wrapping the reference in a DP strategy does);
-* one all-reduce (sum) of the flat fp32 gradient buffer (8.5 M parameters, 34 MB) before the optimizer, done by
+  skips this exchange and averages per-replica gradients instead (what wrapping the reference in a DP strategy does).
+  With NCCL the sums never leave the device: the all-reduce runs in place on the engine's sums buffer and stream;
+* the all-reduce (sum) of the flat fp32 gradient (8.5 M parameters, 34 MB) before the optimizer, done by
   ``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the CPU tests) directly on the engine's device
-  buffer and stream - PyTorch is only the collective plumbing here.
+  buffer - PyTorch is only the collective plumbing here.  With NCCL it is split into the engine's four completion
+  buckets (decoder, dilate6..4, dilate3..1, encoder) and each bucket's all-reduce is enqueued on a side stream behind
+  the event the backward pass records when that bucket's last weight gradient is written, so only the encoder's
+  2.3 MB are exchanged after the last backward kernel.  A step has no host synchronisation; the loss of a step is
+  read from a pinned mirror of the sums that lands at the start of its backward pass.
 
 Nothing in this file computes on the CPU: without the CUDA library ``api.Engine`` raises.
 """
@@ -23,8 +28,8 @@ import numpy as np
 class _CudaView:
     """__cuda_array_interface__ over a raw device pointer so torch can alias the engine's gradient buffer."""
 
-    def __init__(self, ptr: int, count: int):
-        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (ptr, False), "version": 3,
+    def __init__(self, ptr: int, count: int, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3,
                                          "strides": None}
 
 
@@ -46,7 +51,10 @@ class DataParallelTrainer:
         # per-rank dropout stream: the same seed would drop the same units on every replica
         engine.train_begin(batch, size, dropout_rate, seed + 7919 * rank)
         self._grad_t = None
+        self._sums_t = None
         self._torch_stream = None
+        self._side_stream = None
+        self._buckets = []
         self.allreduce_bytes = 4 * engine.train_grad_buffer()[1]
         self.collective_path = "none"
         if dist is not None and world > 1:
@@ -62,6 +70,13 @@ class DataParallelTrainer:
             sp = self.engine.stream_ptr()
             self._torch_stream = torch.cuda.ExternalStream(sp, device=dev) if sp else None
             self.collective_path = "nccl on the engine's device buffer"
+            if self._torch_stream is not None and hasattr(self.engine, "train_sums_buffer"):
+                sptr, sn = self.engine.train_sums_buffer()
+                self._sums_t = torch.as_tensor(_CudaView(sptr, sn, "<f8"), device=f"cuda:{dev}")
+                self._side_stream = torch.cuda.Stream(device=dev)
+                self._buckets = [b for b in self.engine.train_grad_buckets() if b[1] > b[0]]
+                self.collective_path = ("nccl on the engine's device buffers: loss sums in place on the engine stream, gradient in "
+                                        "%d buckets on a side stream behind the backward pass's completion events" % len(self._buckets))
         else:
             self.collective_path = "host-staged (%s)" % self.dist.get_backend()
 
@@ -114,13 +129,41 @@ class DataParallelTrainer:
         self.engine.train_apply(lr, self.optimizer, grad_scale=scale, weight_decay=self.weight_decay,
                                 freeze_encoder=self.freeze_encoder)
 
-    def step(self, x, y, lr: float, dropout_masks=None) -> Dict[str, float]:
-        sums = self.forward_sums(x, y, dropout_masks)
-        gsums = self._allreduce_sums(sums) if self.dice_mode == "global" else None
-        out = self.backward(sums, gsums)
-        self._allreduce_grad()
+    def _device_resident(self) -> bool:
+        """True when a step can stay on the device: one rank, or an NCCL group bound to the engine's buffers."""
+        if not hasattr(self.engine, "train_sums_read"):
+            return False             # stand-in engines of the CPU tests
+        return self.dist is None or self.world == 1 or self._sums_t is not None
+
+    def step(self, x, y, lr: float, dropout_masks=None, want_loss: bool = True) -> Optional[Dict[str, float]]:
+        if not self._device_resident():      # host-staged exchanges (gloo)
+            sums = self.forward_sums(x, y, dropout_masks)
+            gsums = self._allreduce_sums(sums) if self.dice_mode == "global" else None
+            out = self.backward(sums, gsums)
+            self._allreduce_grad()
+            self.apply(lr)
+            return out
+        import torch
+        eng = self.engine
+        eng.train_forward(x, y, dropout_masks, want_sums=False)
+        multi = self.dist is not None and self.world > 1
+        if multi and self.dice_mode == "global":
+            with torch.cuda.stream(self._torch_stream):
+                self.dist.all_reduce(self._sums_t)
+        eng.train_backward(None, self.freeze_encoder)          # enqueued; records the bucket events
+        if multi:
+            side = self._side_stream
+            for b, (lo, hi) in enumerate(eng.train_grad_buckets()):
+                if hi <= lo:
+                    continue
+                eng.train_bucket_wait(b, side.cuda_stream)
+                with torch.cuda.stream(side):
+                    self.dist.all_reduce(self._grad_t[lo:hi])
+            eng.train_join(side.cuda_stream)
         self.apply(lr)
-        return out
+        if not want_loss:
+            return None
+        return eng.train_loss(eng.train_sums_read())
 
     def close(self):
         self._grad_t = None

@@ -8,9 +8,17 @@ blend-accumulated on the device; per-tile predictions are never materialised.
 
 Multi-GPU: one process per GPU.  Rank g owns tile rows [g*n/G, (g+1)*n/G) and an accumulator over
 the pixel rows those tiles touch.  Output rows are owned by the rank whose first tile row starts
-them; a rank's partial sums that fall into a later rank's rows are shipped raw (acc, weight) and
-added there before normalisation — no collective on the data path, only this boundary exchange
-and a final gather of disjoint strips.
+them; a rank's partial sums that fall into the next rank's rows are shipped raw (acc, weight) — no
+collective on the data path, only this boundary exchange and a final gather of disjoint strips.
+
+Masks do not depend on the number of GPUs: float32 addition is order-dependent and the reference adds
+tiles in row-major order (full_evaluation_enhanced.py:165-173), so in the boundary zone (the rows of a
+strip that the strip above also reaches) the upper strip's contributions must come first.  The lower
+strip therefore DEFERS the zone: it keeps the probabilities of its tiles that touch the zone, blends
+only their rows below the zone while the upper strip is still working, receives the upper partial sums
+into the untouched zone rows, and then replays its kept tiles over the zone in the original order
+(adp_wsi_push_from_slide(defer_below_row) / adp_wsi_replay_deferred).  Every pixel sees exactly the
+single-GPU sequence of float32 operations.
 """
 from __future__ import annotations
 
@@ -46,14 +54,15 @@ class Strip:
     acc_rows: int
     own_lo: int                      # output rows this rank normalises and returns
     own_hi: int
+    zone_hi: int = 0                 # rows [own_lo, zone_hi) also receive the upper strip's partial sums (0 = none)
 
 
-def plan_strips(h: int, w: int, tile: int, stride: int, world: int) -> List[Strip]:
+def _plan(h: int, w: int, tile: int, stride: int, world: int, active: int) -> List[Strip]:
     pos = tile_positions(h, w, tile, stride)
     rows = sorted({y for y, _ in pos})
     n = len(rows)
     strips = []
-    bounds = [(g * n) // world for g in range(world + 1)]
+    bounds = [(g * n) // active for g in range(active + 1)] + [n] * (world - active)
     first_y = []
     for g in range(world):
         mine = rows[bounds[g]:bounds[g + 1]]
@@ -69,6 +78,26 @@ def plan_strips(h: int, w: int, tile: int, stride: int, world: int) -> List[Stri
         own_hi = h if nxt is None else nxt
         strips.append(Strip(g, tiles, mine[0], mine[-1] + tile - mine[0], own_lo, own_hi))
     return strips
+
+
+def plan_strips(h: int, w: int, tile: int, stride: int, world: int) -> List[Strip]:
+    """Contiguous tile-row strips.  Ranks are left empty (fewer active strips than `world`) until every boundary zone
+    involves exactly two neighbouring strips - the condition under which the deferred-zone exchange reproduces the
+    single-GPU order of float32 additions (a strip needs at least ceil(tile/stride)-1 tile rows)."""
+    for active in range(max(1, world), 0, -1):
+        strips = _plan(h, w, tile, stride, world, active)
+        live = [s for s in strips if s.tiles]
+        ok = True
+        for i, s in enumerate(live):
+            end = s.acc_y0 + s.acc_rows
+            if i + 1 < len(live) and end > live[i + 1].own_hi:      # reaches past the next strip's rows
+                ok = False
+        if ok:
+            for i in range(1, len(live)):
+                up_end = live[i - 1].acc_y0 + live[i - 1].acc_rows
+                live[i].zone_hi = up_end if up_end > live[i].own_lo else 0
+            return strips
+    raise AssertionError("unreachable: a single strip has no boundary")
 
 
 def boundary_transfers(strips: Sequence[Strip]) -> List[Tuple[int, int, int, int]]:
@@ -95,7 +124,8 @@ def reconstruct_wsi(engine, slide_rows: Callable[[int, int], np.ndarray], h: int
                     to_device=None, timings: bool = False):
     """Run the sliding window on this rank's strip and exchange boundaries.
 
-    slide_rows(y0, rows) -> uint8 [rows, w] gray rows of the slide (host).  to_device(host_u8) must return
+    slide_rows(y0, rows) -> uint8 [rows, w] gray rows of the slide, or [rows, w, 3] RGB rows (converted to gray on the
+    device with OpenCV's 8-bit formula, as cv2.imread(IMREAD_GRAYSCALE) does for the reference), host.  to_device(host_u8) must return
     an object with a device pointer (`data_ptr()`), e.g. ``lambda a: torch.from_numpy(a).cuda()``.
     Returns dict(prob, mask, counts, own=(lo, hi), tiles, n_tiles_total) for THIS rank's owned rows; use
     gather_strips() for the full slide on rank 0.
@@ -124,17 +154,26 @@ def reconstruct_wsi(engine, slide_rows: Callable[[int, int], np.ndarray], h: int
         engine.wsi_begin(me.acc_rows, w, me.acc_y0, tile, mode, window if mode == _lib.BLEND_GAUSSIAN else None)
         lap("begin")
         strip_host = np.ascontiguousarray(slide_rows(me.acc_y0, me.acc_rows))
-        assert strip_host.dtype == np.uint8 and strip_host.shape == (me.acc_rows, w)
+        assert strip_host.dtype == np.uint8 and strip_host.shape in ((me.acc_rows, w), (me.acc_rows, w, 3))
+        channels = 3 if strip_host.ndim == 3 else 1
         lap("strip_assembly")
         strip_dev = to_device(strip_host)
         lap("strip_h2d")
-        for i in range(0, len(me.tiles), batch_tiles):
-            chunk = me.tiles[i:i + batch_tiles]
+        # tiles that touch the boundary zone first (they are the first tile rows of the strip): deferred blend of the zone
+        deferred = [t for t in me.tiles if t[0] < me.zone_hi]
+        rest = me.tiles[len(deferred):]
+        assert deferred == me.tiles[:len(deferred)]
+        if deferred:
+            engine.wsi_push_from_slide(strip_dev, me.acc_y0, me.acc_rows, [p[0] for p in deferred], [p[1] for p in deferred],
+                                       float(mean), float(std), ops, channels=channels, defer_below_row=me.zone_hi)
+        for i in range(0, len(rest), batch_tiles):
+            chunk = rest[i:i + batch_tiles]
             engine.wsi_push_from_slide(strip_dev, me.acc_y0, me.acc_rows, [p[0] for p in chunk], [p[1] for p in chunk],
-                                       float(mean), float(std), ops)
+                                       float(mean), float(std), ops, channels=channels)
         lap("tiles")
-    # ---- boundary exchange: each strip hands its raw (acc, weight) overlap rows to the strip below, which adds them
-    # (only downwards => no cycle; one addend per row => the sum does not depend on arrival order).  With an NCCL
+    # ---- boundary exchange: each strip hands its raw (acc, weight) overlap rows to the strip below, whose zone rows are
+    # still untouched (0 + partial == partial exactly); the strip below then replays its deferred tiles over the zone
+    # (only downwards => no cycle; one source per zone, plan_strips).  With an NCCL
     # group the rows travel device-to-device over NVLink straight out of / into the accumulators' staging tensors;
     # otherwise (gloo, CPU tests) through host buffers.
     transfers = boundary_transfers(strips)
@@ -166,6 +205,9 @@ def reconstruct_wsi(engine, slide_rows: Callable[[int, int], np.ndarray], h: int
                 buf = _recv(dist, (2, rows, w), src)
                 engine.wsi_import_add(y, buf[0], buf[1])
     lap("boundary_exchange")
+    if me.tiles and me.zone_hi > me.own_lo:
+        engine.wsi_replay_deferred()
+        lap("zone_replay")
     if me.tiles:
         rows = me.own_hi - me.own_lo
         gt = gt_rows(me.own_lo, rows) if gt_rows is not None else None

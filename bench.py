@@ -82,6 +82,14 @@ def synthetic_batch(rank: int):
     return tiles, masks
 
 
+def reference_tta_tile(U, G, tile, mask, params, mean, std):
+    """One unit of the workload exactly as the reference runs it (full_evaluation_enhanced.py:577-600, 716-785): eight
+    augment -> predict_single -> de-augment passes, np.mean, threshold 0.5, TP/FP/FN/TN."""
+    prob = U.predict_with_tta(tile, mean, std, params, "full")
+    m = G.pixel_metrics(prob, mask, 0.5)
+    return m["tp"], m["fp"], m["fn"], m["tn"]
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference's CPU algorithm (oracle port) on this box's host cores."""
     if rank != 0:
@@ -89,30 +97,125 @@ def run_reference(args, rank, world):
     import torch
     import adipose_unet_b200 as A
     from oracle import unet as U   # the reference arm is the one other place bench.py may run oracle/
+    from oracle import geometry as G
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     w = A.synth.init_weights()
     params = U.to_torch_params(w)
-    tile = A.synth.ecm_tile(TILE).astype(np.float32)
-    # bounded sample per step: ONE of the 128 forwards of the batch (1 tile, 1 augmentation) + mean
+    tiles, masks = synthetic_batch(0)
+    # bounded sample per step: ONE of the 16 TTA tiles of the batch, complete (8 forwards, de-augmentation, mean, threshold,
+    # confusion counts) - the same work per tile as the GPU arm, so tiles/s compare like for like
+    k = [0]
     def step():
-        return U.predict_single(tile, A.synth.DEFAULT_MEAN, A.synth.DEFAULT_STD, params)
+        i = k[0] % BATCH_TILES; k[0] += 1
+        return reference_tta_tile(U, G, tiles[i], masks[i], params, A.synth.DEFAULT_MEAN, A.synth.DEFAULT_STD)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
-    value = 1.0 / (dt * N_AUG)          # TTA-tile equivalents per second
+    value = 1.0 / dt                    # TTA tiles per second
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: 16 x 1024^2 ECM tiles, 8-way TTA, threshold + Dice/IoU",
                        "note": "PyTorch-CPU restatement of the reference graph (TF 2.13 not installable here)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "1 of the 128 forwards of the batch per step (one 1024^2 tile, identity aug), scaled /8 to TTA-tiles"},
+                             "sample": "one complete TTA tile of the 16-tile batch per step: 8 forwards (batch 1 each, as the reference "
+                                       "loops) + de-augmentation + mean + threshold + TP/FP/FN/TN"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# (name, side, overlap, channels): BASELINE.json configs[2] and configs[4]; ceilings = SURVEY 8(d): all forwards at the measured
+# sustained bf16 peak
+WSI_CASES = [("configs[2]", 32768, 0.5, 3), ("configs[4]", 16384, 0.75, 1)]
+WSI_CASES_SMALL = [("configs[2]-geometry-8192", 8192, 0.5, 3)]
+WSI_CEILING_MPX_PER_GPU = {"configs[2]": 52.5, "configs[4]": 14.0}
+
+
+def run_wsi_case(eng, dist, rank, world, local_rank, barrier, name, size, overlap, channels, blend, reps, mean, std):
+    """One whole-slide reconstruction case.  The synthetic slide and ground truth are generated into pinned host memory
+    BEFORE the clock starts (the slide exists in host RAM, as a decoded WSI would); the timed region is the public driver
+    call: H2D of this rank's strip, every tile (8 forwards each) with TTA mean and blend accumulation, the boundary
+    exchange, normalise / threshold / confusion counts and the mask D2H.  Wall clock, max over ranks."""
+    import torch
+    import adipose_unet_b200 as A
+    from adipose_unet_b200 import wsi as W
+    from adipose_unet_b200.api import blend_window
+    stride = int(TILE * (1 - overlap))
+    me = W.plan_strips(size, size, TILE, stride, world)[rank]
+    win = blend_window(blend, TILE)
+    # 2 x 2 pattern of 1024^2 blocks (hashed seeds), RGB = three independent fields
+    blocks, gts = {}, {}
+    for key in ((0, 0), (0, 1), (1, 0), (1, 1)):
+        if channels == 3:
+            b = np.stack([A.synth.slide_block(key[0], key[1] + 2 * c, TILE) for c in range(3)], axis=-1)
+            gray = A.synth.rgb_to_gray_u8(b)
+        else:
+            b = A.synth.slide_block(*key, TILE)
+            gray = b
+        blocks[key] = b
+        gts[key] = (gray > 160).astype(np.uint8)
+    strip = gt = None
+    if me.tiles:
+        strip = torch.empty((me.acc_rows, size) + ((3,) if channels == 3 else ()), dtype=torch.uint8).pin_memory().numpy()
+        gt = torch.empty((me.own_hi - me.own_lo, size), dtype=torch.uint8).pin_memory().numpy()
+        def fill(dst, y0, src):
+            rows = dst.shape[0]
+            for by in range(y0 // TILE, (y0 + rows - 1) // TILE + 1):
+                a, b_ = max(by * TILE, y0), min((by + 1) * TILE, y0 + rows)
+                for bx in range(size // TILE):
+                    dst[a - y0:b_ - y0, bx * TILE:(bx + 1) * TILE] = src[(by % 2, bx % 2)][a - by * TILE:b_ - by * TILE]
+        fill(strip, me.acc_y0, blocks)
+        fill(gt, me.own_lo, gts)
+
+    def run(h, w_, st, g, m):
+        return W.reconstruct_wsi(eng, (lambda y0, rows: st[y0 - m.acc_y0:y0 - m.acc_y0 + rows]) if st is not None else None, h, w_,
+                                 tile=TILE, overlap=overlap, blend_mode=blend, window=win, mean=mean, std=std, tta_mode="full",
+                                 gt_rows=(lambda y0, rows: g[y0 - m.own_lo:y0 - m.own_lo + rows]) if g is not None else None,
+                                 rank=rank, world=world, dist=dist, to_device=lambda a: torch.from_numpy(a).cuda(),
+                                 want_prob=False, want_mask=True)
+
+    # warm-up: a 2048^2 corner of the same slide through the same code path on every rank alone (allocations, tensor maps)
+    small = np.ascontiguousarray(np.tile(blocks[(0, 0)], (2, 2) + ((1,) if channels == 3 else ())))
+    W.reconstruct_wsi(eng, lambda y0, rows: small[y0:y0 + rows], 2 * TILE, 2 * TILE, tile=TILE, overlap=overlap, blend_mode=blend,
+                      window=win, mean=mean, std=std, tta_mode="full", rank=0, world=1, dist=None,
+                      to_device=lambda a: torch.from_numpy(a).cuda(), want_prob=False, want_mask=True)
+    W.warmup_peer_channels(dist, rank, world, local_rank)
+    secs, counts = [], None
+    for _ in range(reps):
+        barrier()
+        t0 = time.perf_counter()
+        r = run(size, size, strip, gt, me)
+        torch.cuda.synchronize()
+        dt_w = time.perf_counter() - t0
+        tw = torch.tensor([dt_w], dtype=torch.float64, device="cuda")
+        cnt = torch.tensor(list(r["counts"]), dtype=torch.int64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt)
+        secs.append(float(tw[0]))
+        c = [int(v) for v in cnt]
+        assert counts is None or c == counts, "whole-slide counts changed between repetitions"
+        counts = c
+    ntiles = r["n_tiles_total"]
+    mean_s = float(np.mean(secs))
+    out = {"slide": f"{size}x{size}x{channels}", "overlap": overlap, "tta": "full(8)", "tiles": ntiles, "forwards": ntiles * N_AUG,
+           "blend": blend + (" (extension: the reference has gaussian / linear only)" if blend == "hann" else ""),
+           "reps": reps, "seconds": mean_s, "seconds_reps": [round(v, 4) for v in secs],
+           "mpx_per_s": size * size / 1e6 / mean_s, "tiles_per_s": ntiles / mean_s,
+           "counts_tp_fp_fn_tn": counts, "counts_sum_equals_pixels": sum(counts) == size * size,
+           "includes": "H2D of the uint8 strip from pinned host memory + all tiles (8 forwards each, TTA mean, blend) + boundary "
+                       "exchange + normalise/threshold/counts + mask D2H; wall clock, mean of the repetitions, max over ranks; "
+                       "one untimed 2048^2 warm-up call"}
+    if name in WSI_CEILING_MPX_PER_GPU:
+        ceil = WSI_CEILING_MPX_PER_GPU[name] * world
+        out["ceiling_mpx_per_s"] = ceil
+        out["frac_of_ceiling"] = out["mpx_per_s"] / ceil
+        out["ceiling_note"] = "all forwards at the measured sustained bf16 peak (SURVEY 8d), x GPUs"
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
@@ -219,43 +322,15 @@ def run_ours(args, rank, world, local_rank):
     e2e_dev, e2e_wall, res2 = timed(step_e2e, args.steps)
     assert res == res2, "resident and e2e paths disagree"
 
-    # secondary measurement: sliding-window whole-slide reconstruction (configs[2] geometry, smaller slide),
-    # tile-row strips sharded over the ranks, device time = max over ranks
+    # whole-slide sliding-window reconstruction at BASELINE.json's own sizes: configs[2] (32768^2 3-channel pseudocoloured
+    # slide, 50 % overlap) and configs[4] (16384^2 ECM slide, 75 % overlap), 8-way TTA, tile-row strips sharded over the ranks
     wsi_res = None
-    if args.wsi_size > 0:
-        from adipose_unet_b200 import wsi as W
-        from adipose_unet_b200.api import blend_window
-        Hs = Ws = args.wsi_size
-        win = blend_window(args.wsi_blend, TILE)
-        blocks = {}
-        def slide_rows(y0, rows):
-            out = np.empty((rows, Ws), np.uint8)
-            for by in range(y0 // TILE, (y0 + rows - 1) // TILE + 1):
-                for bx in range(Ws // TILE):
-                    key = (by % 2, bx % 2)
-                    if key not in blocks:
-                        blocks[key] = A.synth.slide_block(*key, TILE)
-                    a, b = max(by * TILE, y0), min((by + 1) * TILE, y0 + rows)
-                    out[a - y0:b - y0, bx * TILE:(bx + 1) * TILE] = blocks[key][a - by * TILE:b - by * TILE]
-            return out
-        for key in ((0, 0), (0, 1), (1, 0), (1, 1)):      # synthetic slide content is generated BEFORE the timed region
-            blocks[key] = A.synth.slide_block(*key, TILE)
-        def run_wsi():
-            return W.reconstruct_wsi(eng, slide_rows, Hs, Ws, tile=TILE, overlap=0.5, blend_mode=args.wsi_blend, window=win,
-                                     mean=mean, std=std, tta_mode="full", rank=rank, world=world, dist=dist,
-                                     to_device=lambda a: torch.from_numpy(a).cuda(), want_prob=False, want_mask=True)
-        W.warmup_peer_channels(dist, rank, world, local_rank)
-        barrier()
-        t0 = time.perf_counter()
-        r = run_wsi()
-        torch.cuda.synchronize()
-        dt_w = time.perf_counter() - t0
-        tw = torch.tensor([dt_w], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        wsi_res = {"slide": f"{Hs}x{Ws}", "overlap": 0.5, "blend": args.wsi_blend + (" (extension: the reference has gaussian / linear only)" if args.wsi_blend == "hann" else ""), "tta": "full(8)", "tiles": r["n_tiles_total"],
-                   "seconds": float(tw[0]), "mpx_per_s": Hs * Ws / 1e6 / float(tw[0]),
-                   "includes": "host strip assembly (memcpy of pre-generated blocks) + H2D of the uint8 strip + all tiles (8 forwards each) + boundary exchange + normalise/threshold + mask D2H; wall clock, max over ranks"}
+    if args.wsi != "none":
+        wsi_res = {}
+        cases = WSI_CASES if args.wsi == "full" else WSI_CASES_SMALL
+        for name, size, overlap, channels in cases:
+            wsi_res[name] = run_wsi_case(eng, dist, rank, world, local_rank, barrier, name, size, overlap, channels, args.wsi_blend,
+                                         args.wsi_reps, mean, std)
 
     # per-kernel profile pass (event-bracketed launches, same step), rank 0 only
     roof = None
@@ -318,7 +393,9 @@ def run_ours(args, rank, world, local_rank):
                      "wall_ms_per_step": twall / tsteps * 1e3, "steps": tsteps,
                      "tflops_3x_forward": 3 * L.forward_flops(TILE) * nb * world * tsteps / tdev / 1e12,
                      "loss_last": out["loss"], "dice_mode": tr.dice_mode, "gpu_launches": int(tl),
-                     "collective": ("NCCL all-reduce of %d gradient bytes per step on the engine stream + 48-byte loss-sum all-reduce" % tr.allreduce_bytes)
+                     "collective": ("NCCL all-reduce of %d gradient bytes per step in completion buckets on a side stream, overlapped with "
+                                    "the backward pass + in-place all-reduce of the float64 loss sums on the engine stream; no host "
+                                    "synchronisation inside a step" % tr.allreduce_bytes)
                      if world > 1 else "none (1 GPU)", "collective_path": tr.collective_path}
         tr.close()
 
@@ -397,18 +474,18 @@ def cpu_baseline():
     import torch
     import adipose_unet_b200 as A
     from oracle import unet as U
+    from oracle import geometry as G
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     params = U.to_torch_params(A.synth.init_weights())
-    tile = A.synth.ecm_tile(TILE).astype(np.float32)
-    U.predict_single(tile[:256, :256].copy(), 127.5, 50.0, params)   # warm the thread pool
+    tiles, masks = synthetic_batch(0)
+    U.predict_single(tiles[0], A.synth.DEFAULT_MEAN, A.synth.DEFAULT_STD, params)   # warm the thread pool and the allocator
     t0 = time.perf_counter()
-    reps = 2
-    for _ in range(reps):
-        U.predict_single(tile, A.synth.DEFAULT_MEAN, A.synth.DEFAULT_STD, params)
-    dt = (time.perf_counter() - t0) / reps
-    return {"value": 1.0 / (dt * N_AUG), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{reps} single 1024^2 forwards (1/128 of a step each), {dt:.2f} s per forward, scaled /8 to TTA-tiles",
+    reference_tta_tile(U, G, tiles[1], masks[1], params, A.synth.DEFAULT_MEAN, A.synth.DEFAULT_STD)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"one complete TTA tile (8 forwards + de-augmentation + mean + threshold + counts = 1/16 of a step) after one "
+                      f"warm-up forward: {dt:.2f} s",
             "note": "PyTorch-CPU fp32 restatement of the reference graph; TF 2.13 is not installable in this image"}
 
 
@@ -426,7 +503,9 @@ def main():
     ap.add_argument("--train-dice", default="global", choices=["global", "replica"])
     ap.add_argument("--wsi-blend", default="gaussian", choices=["gaussian", "linear", "hann"],
                     help="blend window of the WSI run: gaussian / linear are the reference's blenders, hann is the labelled extension")
-    ap.add_argument("--wsi-size", type=int, default=8192, help="side of the synthetic slide of the secondary WSI run (0 = skip)")
+    ap.add_argument("--wsi", default="full", choices=["full", "small", "none"],
+                    help="whole-slide runs: full = configs[2] (32768^2 RGB, 50 %) and configs[4] (16384^2, 75 %), small = 8192^2, none")
+    ap.add_argument("--wsi-reps", type=int, default=3, help="timed repetitions of every whole-slide case")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

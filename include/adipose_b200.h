@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ADP_ABI_VERSION 2
+#define ADP_ABI_VERSION 3
 
 /* error codes */
 #define ADP_OK 0
@@ -161,11 +161,20 @@ int adp_wsi_begin(adp_engine *e, int rows, int W, int y0, int tile, int blend_mo
 /* predict n tiles (float32 gray 0..255) and accumulate them at slide positions (ys[i], xs[i]) */
 int adp_wsi_push_tiles(adp_engine *e, const float *tiles, int n, const int32_t *ys, const int32_t *xs,
                        float mean, float std, const int *ops, int n_ops);
-/* same, the tiles are cut on the device from a resident uint8 gray slide region
- * (slide: region_rows x W bytes covering rows [region_y0, ...)) — the sliding-window case */
-int adp_wsi_push_from_slide(adp_engine *e, const uint8_t *slide, int region_y0, int region_rows,
+/* same, the tiles are cut on the device from a resident uint8 slide region (slide: region_rows x W pixels covering rows
+ * [region_y0, ...); channels = 1: gray bytes; channels = 3: interleaved RGB, converted by the first conv kernel with
+ * OpenCV's 8-bit RGB2GRAY formula, i.e. what cv2.imread(..., IMREAD_GRAYSCALE) of reconstruct_full_images.py:364 feeds
+ * the model) - the sliding-window case.
+ * defer_below_row > y0 (multi-GPU strips): slide rows [y0, defer_below_row) of this accumulator also
+ * receive partial sums of the strip above, and float32 addition is order-dependent.  The reference adds tiles in
+ * row-major order (full_evaluation_enhanced.py:165-173), i.e. the upper strip's tiles FIRST.  The call therefore keeps
+ * the TTA-mean probabilities of these tiles on the device, blends only their rows >= defer_below_row now, and
+ * adp_wsi_replay_deferred - called after adp_wsi_import_add has put the upper strip's partial sums into the still
+ * untouched zone rows - blends their rows < defer_below_row in the original order: masks do not depend on the GPU count. */
+int adp_wsi_push_from_slide(adp_engine *e, const uint8_t *slide, int channels, int region_y0, int region_rows,
                             int n, const int32_t *ys, const int32_t *xs, float mean, float std,
-                            const int *ops, int n_ops);
+                            const int *ops, int n_ops, int defer_below_row);
+int adp_wsi_replay_deferred(adp_engine *e);
 /* add already-predicted probability tiles (blend only; used for ground-truth re-blending,
  * reconstruct_full_images.py:404-415) */
 int adp_wsi_push_probs(adp_engine *e, const float *probs, int n, const int32_t *ys, const int32_t *xs);
@@ -186,12 +195,16 @@ int adp_wsi_end(adp_engine *e);
  * n_px pixels over the whole batch; dldp (may be NULL) receives dL/dp.
  * out = {loss, bce_mean, dice_loss, dice_coef}.
  * adp_loss_metrics_ex: the reference's other compile_model choices (train_adipose_unet_v3.py:808-855) on `batch`
- * images of px_per_image pixels: ohem_keep_ratio < 1 = online_hard_example_mining_loss (:282-323, mean of the top
- * int(px*ratio) per-image BCE values + Dice over all pixels); eps_pos/eps_neg > 0 = asymmetric label smoothing
+ * images of px_per_image pixels whose trailing axis has row_len pixels (the W of the reference's (B,H,W) tensors; 0 = flat,
+ * allowed without hard mining): ohem_keep_ratio < 1 = online_hard_example_mining_loss (:282-323).  As written in the
+ * reference, tf.keras.losses.binary_crossentropy averages the LAST axis, so the "per-pixel" BCE it ranks is the (B,H)
+ * tensor of per-row means: the loss is the mean of the top int(float32(H)*ratio) row means of every image (716 of 1024
+ * rows at the default 0.7; ties to the lower row index like tf.nn.top_k) + Dice over all pixels, and a selected row's
+ * pixels each receive 1/(W*B*k) of the BCE gradient.  eps_pos/eps_neg > 0 = asymmetric label smoothing
  * (:244-279, 326-363: ys = y*(1-eps_pos-eps_neg)+eps_neg in both terms; dice_coef keeps the raw y). */
 int adp_loss_metrics(adp_engine *e, const float *p, const float *y, int64_t n_px, float *dldp, double out[4]);
-int adp_loss_metrics_ex(adp_engine *e, const float *p, const float *y, int batch, int64_t px_per_image, float ohem_keep_ratio,
-                        float eps_pos, float eps_neg, float *dldp, double out[4]);
+int adp_loss_metrics_ex(adp_engine *e, const float *p, const float *y, int batch, int64_t px_per_image, int64_t row_len,
+                        float ohem_keep_ratio, float eps_pos, float eps_neg, float *dldp, double out[4]);
 
 /* ---- training step -----------------------------------------------------------------------------
  * Replaces Keras train_step as driven by net.fit (train_adipose_unet_v3.py:1316-1324, 1413-1421):
@@ -214,12 +227,20 @@ int adp_train_set_loss(adp_engine *e, float ohem_keep_ratio, float eps_pos, floa
  * uint8 0/1 arrays in NHWC with the real channel counts, sites in graph order
  * {dilate1 (size/8, 8*init_nb), up3 (size/4, 4*init_nb), up2 (size/2, 2*init_nb), up1 (size, init_nb)}.
  * sums = {sum of the BCE terms in the mean, sum ys*pc, sum ys, sum pc, sum y*p, sum p, sum y, number of BCE terms} over this
- * batch (pc = clip(p,1e-7,1-1e-7), ys = smoothed target); every entry is additive over data-parallel ranks. */
+ * batch (pc = clip(p,1e-7,1-1e-7), ys = smoothed target; with hard mining the BCE terms are the selected per-row means);
+ * every entry is additive over data-parallel ranks.  sums may be NULL: the values then stay in the device buffer
+ * adp_train_sums_buffer() returns (no host synchronisation in the step). */
 int adp_train_forward(adp_engine *e, const float *x, const float *y, int batch, const uint8_t *const *dropout_masks,
-                      double *sums /* 8 per output: adp_train_outputs() x 8 */);
+                      double *sums /* 8 per output: adp_train_outputs() x 8, or NULL */);
+/* device pointer + count (8 x adp_train_outputs()) of the float64 loss sums of the last adp_train_forward: a data-parallel
+ * caller all-reduces them in place on the engine's stream and calls adp_train_backward(e, NULL, ...) */
+int adp_train_sums_buffer(adp_engine *e, double **dev_ptr, int *count);
+/* host copy of that buffer (synchronises the engine's stream); count must equal 8 x adp_train_outputs() */
+int adp_train_sums_read(adp_engine *e, double *host, int count);
 /* loss = {loss, bce_mean, dice_loss, dice_coef} from (possibly rank-summed) sums */
 int adp_train_loss(const double sums[8], double out[4]);
-/* sums: the values the loss is defined over (own batch, or summed over data-parallel ranks);
+/* sums: the values the loss is defined over (own batch, or summed over data-parallel ranks) in host memory, or NULL = the
+ * device sums buffer as it stands; stream-ordered (returns without synchronising the engine's stream);
  * freeze_encoder != 0 = phase 1 of the reference (down*_conv* frozen, :760-769): their gradients are zero */
 int adp_train_backward(adp_engine *e, const double *sums /* 8 per output */, int freeze_encoder);
 /* Deep supervision (train_adipose_unet_v3.py:712-745, 808-872): while training, aux_out1 = sigmoid(Conv2D(1,1x1)) on the
@@ -233,6 +254,14 @@ int adp_train_set_deep_supervision(adp_engine *e, int on, float w_main, float w_
 int adp_train_outputs(adp_engine *e);
 /* device pointer + element count of the flat fp32 gradient (Keras order: per layer kernel HWIO, bias) */
 int adp_train_grad_buffer(adp_engine *e, float **dev_ptr, int64_t *count);
+/* Overlapping the gradient exchange with the backward pass: the flat gradient is completed in adp_train_grad_buckets()
+ * contiguous element ranges [lo, hi) (returned in completion order: decoder + heads, dilate6..4, dilate3..1, encoder); after
+ * adp_train_backward has been enqueued, adp_train_bucket_wait(e, b, s) makes the caller's CUDA stream s wait for bucket b
+ * (cudaStreamWaitEvent on an event the backward pass recorded on the engine's stream), the caller enqueues its collective
+ * on s, and adp_train_join(e, s) makes the engine's stream wait for everything enqueued on s before adp_train_apply. */
+int adp_train_grad_buckets(adp_engine *e, int64_t *lo, int64_t *hi, int cap);
+int adp_train_bucket_wait(adp_engine *e, int bucket, void *stream);
+int adp_train_join(adp_engine *e, void *stream);
 /* whole flat gradient to / from host memory (count must equal the parameter count): the staging path of a
  * data-parallel caller whose collective runs on host buffers (gloo), and of tests that emulate ranks in-process */
 int adp_train_grad_read(adp_engine *e, float *host, int64_t count);

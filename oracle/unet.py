@@ -188,14 +188,23 @@ def combined_loss_with_label_smoothing(y, p, epsilon_pos=0.03, epsilon_neg=0.07)
     return bce_mean(ys, p) + dice_loss(ys, p)
 
 
-def online_hard_example_mining_loss(y, p, keep_ratio=0.7, epsilon_pos=0.0, epsilon_neg=0.0):
-    """train_adipose_unet_v3.py:282-323 (and :326-363 with smoothing): per-pixel BCE (Keras' binary_crossentropy over a
-    trailing axis of length 1 is the per-pixel value), flattened per image, top int(npix*ratio) values per image,
-    mean over all kept values, plus dice_loss over ALL pixels.  y, p: (B, H, W)."""
-    ys = smooth_labels(y, epsilon_pos, epsilon_neg) if (epsilon_pos or epsilon_neg) else y
+def bce_last_axis_mean(y, p):
+    """tf.keras.losses.binary_crossentropy(y_true, y_pred) as a TENSOR (before Keras' loss reduction): the backend's
+    element-wise BCE on clipped probabilities, averaged over the LAST axis only.  For the reference's (B,H,W) output and
+    target (train_adipose_unet_v3.py:748-750, 611-613) the result is (B,H): one mean per image ROW."""
     pc = torch.clamp(p, EPS, 1.0 - EPS)
-    bce = -(ys * torch.log(pc + EPS) + (1.0 - ys) * torch.log(1.0 - pc + EPS))
-    flat = bce.reshape(bce.shape[0], -1)
+    bce = -(y * torch.log(pc + EPS) + (1.0 - y) * torch.log(1.0 - pc + EPS))
+    return bce.mean(dim=-1)
+
+
+def online_hard_example_mining_loss(y, p, keep_ratio=0.7, epsilon_pos=0.0, epsilon_neg=0.0):
+    """train_adipose_unet_v3.py:282-323 (and :326-363 with smoothing), AS WRITTEN: `per_pixel_bce =
+    tf.keras.losses.binary_crossentropy(y_true, y_pred)` (:301) averages the trailing axis, so for y, p of shape (B,H,W) it
+    is the (B,H) tensor of per-row means; `flat_loss = reshape(.., [B,-1])` (:305) stays (B,H); `num_pixels` (:308) is H and
+    k = int(float32(H) * keep_ratio) (:309) = 716 for H = 1024, ratio 0.7; `top_k` (:312) keeps the k largest ROW means of
+    every image and `hard_bce` (:313) is their mean over the whole (B,k) tensor; dice_loss runs over ALL pixels (:316)."""
+    ys = smooth_labels(y, epsilon_pos, epsilon_neg) if (epsilon_pos or epsilon_neg) else y
+    flat = bce_last_axis_mean(ys, p).reshape(p.shape[0], -1)
     k = int(np.float32(flat.shape[1]) * np.float32(keep_ratio))
     top, _ = torch.topk(flat, k, dim=1, sorted=False)
     return top.mean() + dice_loss(ys, p)

@@ -81,3 +81,33 @@ def forward(x: np.ndarray, w: dict, deep_supervision: bool = False):
     a2 = 1.0 / (1.0 + np.exp(-C(u2, "aux_out2", relu=False)[..., 0]))
     H = x.shape[1]
     return prob, resize_bilinear_half_pixel(a1, H), resize_bilinear_half_pixel(a2, H)
+
+
+def ohem_loss_numpy(y: np.ndarray, p: np.ndarray, keep_ratio: float = 0.7, epsilon_pos: float = 0.0, epsilon_neg: float = 0.0):
+    """Second restatement (float64, no torch) of online_hard_example_mining_loss[_with_smoothing]
+    (Segmentation/train_adipose_unet_v3.py:282-363) for y, p of shape (B,H,W), with its gradient dL/dp written out by hand.
+
+    Line by line: binary_crossentropy (:301) = mean over the LAST axis of -[y log(pc+eps) + (1-y) log(1-pc+eps)] with
+    pc = clip(p, eps, 1-eps) -> (B,H); reshape to (B,-1) (:305) -> (B,H); num_pixels = H (:308);
+    k = int(float32(H)*keep_ratio) (:309); top_k per image (:312), ties to the lower index; reduce_mean over (B,k) (:313);
+    plus dice_loss over every pixel (:316, :217-225).  Returns (loss, dL/dp, selected-row mask (B,H))."""
+    eps = 1e-7
+    y = y.astype(np.float64); p = p.astype(np.float64)
+    ys = y * (1.0 - epsilon_pos - epsilon_neg) + epsilon_neg if (epsilon_pos or epsilon_neg) else y
+    B, H, W = p.shape
+    pc = np.clip(p, eps, 1.0 - eps)
+    inside = (p >= eps) & (p <= 1.0 - eps)                       # gradient of clip
+    bce = -(ys * np.log(pc + eps) + (1.0 - ys) * np.log(1.0 - pc + eps))
+    rows = bce.mean(axis=-1)                                     # (B,H)
+    k = int(np.float32(H) * np.float32(keep_ratio))
+    sel = np.zeros((B, H), bool)
+    for b in range(B):
+        order = np.argsort(-rows[b], kind="stable")              # descending, ties keep the lower index first
+        sel[b, order[:k]] = True
+    hard = rows[sel].sum() / (B * k)
+    inter = (ys * pc).sum(); den = ys.sum() + pc.sum() + 1.0
+    loss = hard + 1.0 - (2.0 * inter + 1.0) / den
+    dbce = -(ys / (pc + eps) - (1.0 - ys) / (1.0 - pc + eps))
+    ddice = -(2.0 * ys * den - (2.0 * inter + 1.0)) / den ** 2
+    g = (sel[:, :, None] * dbce / (W * B * k) + ddice) * inside
+    return float(loss), g, sel

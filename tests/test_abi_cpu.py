@@ -33,7 +33,7 @@ def test_header_and_binding_agree(lib):
 
 
 def test_abi_version_and_no_gpu_behaviour(lib):
-    assert lib.adp_abi_version() == 2
+    assert lib.adp_abi_version() == 3
     import ctypes as C
     if lib.adp_device_count() == 0:
         h = C.c_void_p()

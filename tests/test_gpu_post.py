@@ -129,10 +129,10 @@ def test_loss_recipes_vs_oracle(keep, eps):
     import torch
     from oracle import unet as U
     rng = np.random.default_rng(7)
-    B, S = 3, 96
-    y = (rng.random((B, S, S)) < 0.3).astype(np.float32)
+    B, S, SW = 3, 96, 64           # non-square: rows (H = 96) are what hard mining ranks, the row length (W = 64) what it averages
+    y = (rng.random((B, S, SW)) < 0.3).astype(np.float32)
     # probabilities spanning saturated (clipped), confident and uncertain pixels
-    z = rng.standard_normal((B, S, S)).astype(np.float32) * 4.0
+    z = rng.standard_normal((B, S, SW)).astype(np.float32) * 4.0
     p = (1.0 / (1.0 + np.exp(-z))).astype(np.float32)
     p[0, :4] = 0.0; p[1, :4] = 1.0                                   # exercise the clip and tie handling
     # float32 like TensorFlow: for saturated pixels clip(p) + 1e-7 and 1 - clip(p) + 1e-7 are float32 roundings
@@ -149,11 +149,17 @@ def test_loss_recipes_vs_oracle(keep, eps):
     assert abs(res["loss"] - float(loss)) <= 2e-5 * max(1.0, abs(float(loss)))          # float32 oracle sums vs float64 device sums
     assert abs(res["dice_coef"] - float(U.dice_coef(yt, pt.detach()))) <= 1e-5            # metric keeps the raw target
     gref = pt.grad.numpy()
-    # the fp32 kernel and the float64 oracle may rank a handful of near-equal BCE values differently around tau: compare in
-    # the L2 norm and bound the number of pixels whose selection differs
+    # same selected rows as the oracle (row means differ by many ulps here), gradient to float32 rounding
     l2 = np.linalg.norm((g - gref).ravel()) / np.linalg.norm(gref.ravel())
-    differ = (np.abs(g - gref) > 1e-6 * np.abs(gref).max() + 1e-9).mean()
-    assert l2 <= 2e-3 and differ <= 1e-3, (l2, differ)
+    differ = (np.abs(g - gref) > 1e-3 * np.abs(gref) + 1e-7 * np.abs(gref).max()).mean()      # a mis-selected row is off by ~100 %
+    assert l2 <= 1e-5 and differ == 0.0, (l2, differ)
+    if keep < 1.0:
+        # the second (NumPy float64, hand-differentiated) restatement: loss, gradient and the number of selected rows
+        from oracle import unet_numpy as N
+        ln, gn, sel = N.ohem_loss_numpy(y, p, keep, eps[0], eps[1])
+        assert sel.sum() == B * int(np.float32(S) * np.float32(keep))
+        assert abs(res["loss"] - ln) <= 2e-5 * max(1.0, abs(ln))
+        assert np.linalg.norm((g - gn).ravel()) / np.linalg.norm(gn.ravel()) <= 1e-5
 
 
 def test_threshold_sweep_equals_per_threshold_counts():

@@ -102,8 +102,9 @@ def test_gradients_vs_oracle(prec, with_dropout, weights):
 
 
 def test_hard_mining_and_label_smoothing_step_fp32(weights):
-    """The default loss of the reference's training CLI (OHEM keep 0.7) and its label-smoothing variant through the whole
-    step: loss and every gradient against the oracle's autograd of train_adipose_unet_v3.py:282-363."""
+    """The default loss of the reference's training CLI (OHEM keep 0.7: the top int(H*0.7) per-ROW BCE means of every image,
+    train_adipose_unet_v3.py:301-313) and its label-smoothing variant through the whole step: loss and every gradient
+    against the oracle's autograd of train_adipose_unet_v3.py:282-363."""
     n, S = 2, 128
     x, y = batch(n, S, seed=23)
     for keep, ep, en in ((0.7, 0.0, 0.0), (0.7, 0.03, 0.07)):
@@ -114,7 +115,7 @@ def test_hard_mining_and_label_smoothing_step_fp32(weights):
         eng.train_set_loss(keep, ep, en)
         eng.train_begin(n, S, dropout_rate=0.0)
         sums = eng.train_forward(x, y)
-        assert sums[7] == n * int(np.float32(S * S) * np.float32(keep))
+        assert sums[7] == n * int(np.float32(S) * np.float32(keep))        # rows, not pixels: top-k over the (B,H) row means
         loss = eng.train_loss(sums)
         eng.train_backward(sums)
         g = eng.train_grads()

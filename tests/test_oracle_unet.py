@@ -75,3 +75,38 @@ def test_two_independent_restatements_agree():
     ref = torch.nn.functional.conv2d(torch.from_numpy(t).permute(0, 3, 1, 2), torch.from_numpy(k).permute(3, 2, 0, 1),
                                      torch.from_numpy(b), padding=32, dilation=32).permute(0, 2, 3, 1).numpy()
     assert np.abs(N.conv2d_same(t, k, b, 32, relu=False) - ref).max() < 1e-10
+
+
+def test_hard_mining_ranks_row_means_as_the_reference_writes_it():
+    """online_hard_example_mining_loss (train_adipose_unet_v3.py:282-323): binary_crossentropy averages the LAST axis, so
+    the top-k runs over the (B,H) per-row means with k = int(float32(H)*ratio) - 716 of 1024 rows at the CLI default.
+    The torch restatement, the hand-differentiated NumPy restatement and a literal line-by-line evaluation agree."""
+    from oracle import unet_numpy as N
+    assert int(np.float32(1024) * np.float32(0.7)) == 716
+    rng = np.random.default_rng(11)
+    B, H, W = 3, 40, 24
+    y = (rng.random((B, H, W)) < 0.3).astype(np.float32)
+    p = (1.0 / (1.0 + np.exp(-4.0 * rng.standard_normal((B, H, W))))).astype(np.float32)
+    p[0, :2] = 0.0; p[1, :2] = 1.0                                        # clipped rows
+    for keep, ep, en in ((0.7, 0.0, 0.0), (0.5, 0.03, 0.07)):
+        pt = torch.tensor(p, dtype=torch.float64, requires_grad=True)
+        yt = torch.tensor(y, dtype=torch.float64)
+        loss = U.online_hard_example_mining_loss(yt, pt, keep, ep, en)
+        loss.backward()
+        ln, gn, sel = N.ohem_loss_numpy(y, p, keep, ep, en)
+        k = int(np.float32(H) * np.float32(keep))
+        assert sel.sum(axis=1).tolist() == [k] * B
+        assert abs(float(loss) - ln) < 1e-12
+        assert np.abs(pt.grad.numpy() - gn).max() < 1e-12
+        # literal evaluation of the reference's statements with NumPy stand-ins for the TF ops
+        ys = y.astype(np.float64) * (1.0 - ep - en) + en if (ep or en) else y.astype(np.float64)
+        pc = np.clip(p.astype(np.float64), 1e-7, 1 - 1e-7)
+        per_pixel_bce = np.mean(-(ys * np.log(pc + 1e-7) + (1 - ys) * np.log(1 - pc + 1e-7)), axis=-1)   # :301 -> (B,H)
+        flat_loss = per_pixel_bce.reshape(B, -1)                                                          # :305
+        num_pixels = flat_loss.shape[1]                                                                   # :308
+        assert num_pixels == H
+        kk = int(np.float32(num_pixels) * np.float32(keep))                                               # :309
+        top_k_loss = -np.sort(-flat_loss, axis=1)[:, :kk]                                                 # :312
+        hard_bce = top_k_loss.mean()                                                                      # :313
+        dice = 1.0 - (2.0 * (ys * pc).sum() + 1.0) / (ys.sum() + pc.sum() + 1.0)
+        assert abs(hard_bce + dice - ln) < 1e-12
