@@ -83,22 +83,27 @@ def forward(x: np.ndarray, w: dict, deep_supervision: bool = False):
     return prob, resize_bilinear_half_pixel(a1, H), resize_bilinear_half_pixel(a2, H)
 
 
-def ohem_loss_numpy(y: np.ndarray, p: np.ndarray, keep_ratio: float = 0.7, epsilon_pos: float = 0.0, epsilon_neg: float = 0.0):
+def ohem_loss_numpy(y: np.ndarray, p: np.ndarray, keep_ratio: float = 0.7, epsilon_pos: float = 0.0, epsilon_neg: float = 0.0,
+                    dtype=np.float64):
     """Second restatement (float64, no torch) of online_hard_example_mining_loss[_with_smoothing]
     (Segmentation/train_adipose_unet_v3.py:282-363) for y, p of shape (B,H,W), with its gradient dL/dp written out by hand.
 
     Line by line: binary_crossentropy (:301) = mean over the LAST axis of -[y log(pc+eps) + (1-y) log(1-pc+eps)] with
     pc = clip(p, eps, 1-eps) -> (B,H); reshape to (B,-1) (:305) -> (B,H); num_pixels = H (:308);
     k = int(float32(H)*keep_ratio) (:309); top_k per image (:312), ties to the lower index; reduce_mean over (B,k) (:313);
-    plus dice_loss over every pixel (:316, :217-225).  Returns (loss, dL/dp, selected-row mask (B,H))."""
-    eps = 1e-7
-    y = y.astype(np.float64); p = p.astype(np.float64)
-    ys = y * (1.0 - epsilon_pos - epsilon_neg) + epsilon_neg if (epsilon_pos or epsilon_neg) else y
+    plus dice_loss over every pixel (:316, :217-225).  Returns (loss, dL/dp, selected-row mask (B,H)).
+    dtype = np.float32 evaluates the element-wise statements in float32 like TensorFlow (for saturated pixels
+    clip(p) + 1e-7 and 1 - clip(p) + 1e-7 are float32 roundings that float64 does not reproduce); reductions stay float64."""
+    eps = dtype(1e-7)
+    y = y.astype(dtype); p = p.astype(dtype)
+    one = dtype(1.0)
+    ys = y * dtype(1.0 - epsilon_pos - epsilon_neg) + dtype(epsilon_neg) if (epsilon_pos or epsilon_neg) else y
     B, H, W = p.shape
-    pc = np.clip(p, eps, 1.0 - eps)
-    inside = (p >= eps) & (p <= 1.0 - eps)                       # gradient of clip
-    bce = -(ys * np.log(pc + eps) + (1.0 - ys) * np.log(1.0 - pc + eps))
-    rows = bce.mean(axis=-1)                                     # (B,H)
+    pc = np.clip(p, eps, one - eps)
+    inside = (p >= eps) & (p <= one - eps)                       # gradient of clip
+    bce = -(ys * np.log(pc + eps) + (one - ys) * np.log(one - pc + eps))
+    rows = bce.astype(np.float64).mean(axis=-1)                  # (B,H)
+    ys = ys.astype(np.float64); pc = pc.astype(np.float64); eps = 1e-7
     k = int(np.float32(H) * np.float32(keep_ratio))
     sel = np.zeros((B, H), bool)
     for b in range(B):
