@@ -64,6 +64,15 @@ SIGNATURES = {
     "adp_wsi_import_add": (_I, [_P, _I, _I, _P, _P]),
     "adp_wsi_finalize": (_I, [_P, _I, _I, _F, _P, _P, _P, C.POINTER(_I64)]),
     "adp_wsi_end": (_I, [_P]),
+    "adp_jpeg_decode": (_I, [_P, _P, _P, _I, _I, _P, _P, C.POINTER(_P), C.POINTER(_P)]),
+    "adp_wsi_push_tiles_u8": (_I, [_P, _P, _I, _I, _P, _P, _F, _F, C.POINTER(_I), _I]),
+    "adp_wsi_aux_begin": (_I, [_P, _I]),
+    "adp_wsi_push_aux": (_I, [_P, _I, _I, _P, _I, _I, _P, _P]),
+    "adp_wsi_export_u8": (_I, [_P, _I, _I, _I, _I, _I, _P]),
+    "adp_wsi_export_f32": (_I, [_P, _I, _I, _I, _P]),
+    "adp_wsi_finalize_auxgt": (_I, [_P, _I, _I, _I, _F, _P, _P, C.POINTER(_I64)]),
+    "adp_tile_fat_percent": (_I, [_P, _P, _I, _I64, _F, _P]),
+    "adp_tiff_write_lzw": (_I, [C.c_char_p, _P, _I64, _I64, _I, _I, _I]),
     "adp_loss_metrics": (_I, [_P, _P, _P, _I64, _P, C.POINTER(C.c_double)]),
     "adp_loss_metrics_ex": (_I, [_P, _P, _P, _I, _I64, _I64, _F, _F, _F, _P, C.POINTER(C.c_double)]),
     "adp_train_set_loss": (_I, [_P, _F, _F, _F]),

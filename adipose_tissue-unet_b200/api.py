@@ -390,6 +390,79 @@ class Engine:
     def wsi_end(self):
         _lib.check(self.lib.adp_wsi_end(self.h))
 
+    # ---- tile I/O front-end
+    def jpeg_decode(self, blobs: Sequence[bytes], size: int, want_gray: bool = True, want_rgb: bool = False, to_host: bool = True):
+        """nvJPEG decode of JPEG byte strings (size x size tiles).  Returns dict with 'gray' (n,S,S) / 'rgb' (n,S,S,3) uint8 host
+        arrays (to_host) and 'gray_dev' / 'rgb_dev' device addresses (valid until the next decode) for predict / wsi_push_*."""
+        n = len(blobs)
+        bufs = [np.frombuffer(b, dtype=np.uint8) for b in blobs]
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        lens = (C.c_size_t * n)(*[b.size for b in bufs])
+        gray = np.empty((n, size, size), np.uint8) if (want_gray and to_host) else None
+        rgb = np.empty((n, size, size, 3), np.uint8) if (want_rgb and to_host) else None
+        gd, rd = C.c_void_p(), C.c_void_p()
+        _lib.check(self.lib.adp_jpeg_decode(self.h, ptrs, lens, n, size, _lib.ptr(gray), _lib.ptr(rgb),
+                                            C.byref(gd) if want_gray else None, C.byref(rd) if want_rgb else None))
+        return dict(gray=gray, rgb=rgb, gray_dev=gd.value, rgb_dev=rd.value, n=n, size=size)
+
+    def predict_u8_dev(self, dev_ptr: int, n: int, size: int, channels: int, mean: float, std: float,
+                       ops: Optional[Sequence[int]] = None) -> np.ndarray:
+        """adp_predict_u8 on device-resident uint8 tiles (a device address, e.g. the output of jpeg_decode) or a host uint8 array."""
+        ops = list(ops) if ops else []
+        out = np.empty((n, size, size), np.float32)
+        if isinstance(dev_ptr, np.ndarray):
+            dev_ptr = np.ascontiguousarray(dev_ptr, dtype=np.uint8)
+        _lib.check(self.lib.adp_predict_u8(self.h, _lib.ptr(dev_ptr), n, size, channels, mean, std,
+                                           _lib.int_array(ops) if ops else None, len(ops), _lib.ptr(out)))
+        return out
+
+    def wsi_push_tiles_u8(self, tiles, ys, xs, mean, std, ops, channels: int = 1):
+        """tiles: uint8 ndarray (n,S,S[,3]) or a device address (int)."""
+        if isinstance(tiles, np.ndarray):
+            tiles = np.ascontiguousarray(tiles, dtype=np.uint8)
+        ys = np.ascontiguousarray(ys, dtype=np.int32); xs = np.ascontiguousarray(xs, dtype=np.int32)
+        ops = list(ops) if ops else []
+        _lib.check(self.lib.adp_wsi_push_tiles_u8(self.h, _lib.ptr(tiles), int(channels), len(ys), _lib.ptr(ys), _lib.ptr(xs), mean, std,
+                                                  _lib.int_array(ops) if ops else None, len(ops)))
+
+    def wsi_aux_begin(self, n_planes: int):
+        _lib.check(self.lib.adp_wsi_aux_begin(self.h, n_planes))
+
+    def wsi_push_aux(self, plane0: int, tiles, ys, xs, n_planes: int = 1, is_u8: Optional[bool] = None):
+        """Blend tiles into auxiliary planes plane0..plane0+n_planes-1: uint8 (scaled by 1/255) or float32; ndarray
+        (n,S,S[,n_planes]) or a device address (then is_u8 must be given)."""
+        if isinstance(tiles, np.ndarray):
+            is_u8 = tiles.dtype == np.uint8
+            tiles = np.ascontiguousarray(tiles) if is_u8 else _f32c(tiles)
+        ys = np.ascontiguousarray(ys, dtype=np.int32); xs = np.ascontiguousarray(xs, dtype=np.int32)
+        _lib.check(self.lib.adp_wsi_push_aux(self.h, plane0, n_planes, _lib.ptr(tiles), 1 if is_u8 else 0, len(ys), _lib.ptr(ys), _lib.ptr(xs)))
+
+    def wsi_export_u8(self, plane0: int, n_planes: int, y: int, rows: int, W: int, reverse: bool = False) -> np.ndarray:
+        """(normalised plane * 255).astype(uint8); plane0 = -1: the probability plane.  (rows, W) or (rows, W, n_planes)."""
+        out = np.empty((rows, W) if n_planes == 1 else (rows, W, n_planes), np.uint8)
+        _lib.check(self.lib.adp_wsi_export_u8(self.h, plane0, n_planes, 1 if reverse else 0, y, rows, _lib.ptr(out)))
+        return out
+
+    def wsi_export_f32(self, plane: int, y: int, rows: int, W: int) -> np.ndarray:
+        out = np.empty((rows, W), np.float32)
+        _lib.check(self.lib.adp_wsi_export_f32(self.h, plane, y, rows, _lib.ptr(out)))
+        return out
+
+    def wsi_finalize_auxgt(self, gt_plane: int, y: int, rows: int, W: int, threshold: float = 0.5, want_prob=True, want_mask=True):
+        prob = np.empty((rows, W), np.float32) if want_prob else None
+        mask = np.empty((rows, W), np.uint8) if want_mask else None
+        counts = (C.c_int64 * 4)()
+        _lib.check(self.lib.adp_wsi_finalize_auxgt(self.h, gt_plane, y, rows, threshold, _lib.ptr(prob), _lib.ptr(mask), counts))
+        return prob, mask, tuple(int(c) for c in counts)
+
+    def fat_percent(self, probs, threshold: float = 0.5) -> np.ndarray:
+        """calculate_fat_percentage (tile_classification_evaluation.py:211-225) for a batch (n,H,W) or one tile (H,W)."""
+        p = _f32c(probs)
+        n = p.shape[0] if p.ndim == 3 else 1
+        out = np.empty(n, np.float64)
+        _lib.check(self.lib.adp_tile_fat_percent(self.h, _lib.ptr(p), n, p.size // n, threshold, _lib.ptr(out)))
+        return out
+
     # ---- profiling
     def profile(self, on: bool):
         self.lib.adp_profile_enable(self.h, 1 if on else 0)
@@ -717,3 +790,22 @@ def calculate_pixel_metrics(pred: np.ndarray, true: np.ndarray, threshold: float
     """full_evaluation_enhanced.calculate_pixel_metrics (:721-785): counts on the device, ratios here."""
     _, (tp, fp, fn, tn) = (engine or default_engine()).threshold_metrics(pred, true, threshold, want_mask=False)
     return metrics_from_counts(tp, fp, fn, tn)
+
+
+def calculate_fat_percentage(mask: np.ndarray, threshold: float = 0.5, engine: Optional[Engine] = None) -> float:
+    """tile_classification_evaluation.calculate_fat_percentage (:211-225): percentage of pixels above the threshold."""
+    return float((engine or default_engine()).fat_percent(np.asarray(mask, dtype=np.float32), threshold)[0])
+
+
+def classify_tile(fat_percentage: float, classification_threshold: float) -> str:
+    """tile_classification_evaluation.classify_tile (:228-239)."""
+    return "Has Fat" if fat_percentage >= classification_threshold else "No Fat"
+
+
+def write_tiff_lzw(path, array: np.ndarray, threads: int = 0):
+    """tifffile.imwrite(path, array, compression='lzw') for uint8 (H,W) / (H,W,3) arrays: baseline TIFF, strips compressed in
+    parallel by libadipose_b200's host-side writer (no GPU needed)."""
+    a = np.ascontiguousarray(array)
+    if a.dtype != np.uint8 or a.ndim not in (2, 3) or (a.ndim == 3 and a.shape[2] != 3):
+        raise ValueError("write_tiff_lzw: uint8 (H,W) or (H,W,3) arrays only")
+    _lib.check(_lib.load().adp_tiff_write_lzw(str(path).encode(), _lib.ptr(a), a.shape[0], a.shape[1], 1 if a.ndim == 2 else 3, 0, threads))

@@ -82,10 +82,9 @@ def read_mask(path) -> np.ndarray:
 
 
 def write_tiff_u8(path, arr: np.ndarray):
-    """uint8 TIFF, LZW (the reference writes with tifffile; OpenCV's TIFF encoder defaults to LZW)."""
-    ok = cv2.imwrite(str(path), np.ascontiguousarray(arr.astype(np.uint8)))
-    if not ok:
-        raise IOError(f"could not write {path}")
+    """uint8 TIFF, LZW: tifffile.imwrite(path, arr, compression='lzw') of the reference, by the library's parallel strip writer."""
+    from ..api import write_tiff_lzw
+    write_tiff_lzw(path, np.ascontiguousarray(arr.astype(np.uint8)))
 
 
 def overlay(image_rgb_u8: np.ndarray, mask: np.ndarray, color: Tuple[int, int, int]) -> np.ndarray:

@@ -81,52 +81,65 @@ def build_parser():
     p.add_argument("--min-coverage", type=float, default=0.90)
     p.add_argument("--max-tiles", type=int, default=None)
     C.add_engine_args(p)
+    p.add_argument("--decode", choices=["nvjpeg", "cv2"], default="nvjpeg",
+                   help="B200 engine: JPEG tiles are decoded on the device by nvJPEG (default) or on the host by OpenCV "
+                        "(bit-identical to the reference's cv2.imread; nvJPEG's IDCT differs by at most a grey level or two)")
     return p
 
 
+def _load_tiles(eng, paths, tile_size, decode):
+    """Decode a batch of tile files to device-resident uint8 gray + RGB (reconstruct_full_images.py:362-369 reads every tile
+    twice: IMREAD_GRAYSCALE for the model, IMREAD_COLOR for the mosaic).  JPEG files go through nvJPEG on the device
+    (decode == 'nvjpeg'); anything else, or decode == 'cv2', is decoded by OpenCV on the host (bit-identical to the reference's
+    reads) and shipped as uint8.  Returns (gray, rgb): device addresses or uint8 arrays - never float32 tiles."""
+    if decode == "nvjpeg" and all(str(p).lower().endswith((".jpg", ".jpeg")) for p in paths):
+        d = eng.jpeg_decode([Path(p).read_bytes() for p in paths], tile_size, want_gray=True, want_rgb=True, to_host=False)
+        return d["gray_dev"], d["rgb_dev"]
+    gray = np.stack([cv2.imread(str(p), cv2.IMREAD_GRAYSCALE) for p in paths])
+    rgb = np.stack([cv2.cvtColor(cv2.imread(str(p), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB) for p in paths])
+    return gray, rgb
+
+
 def reconstruct_slide(model, tiles_info, full_shape, tile_size, stride, mean, std, blend_mode, tta_mode, threshold, batch_tiles,
-                      refine_kernel=None):
-    """-> (rgb float32 [0,1], probability, ground truth or None, mask, (tp,fp,fn,tn) or None)."""
+                      refine_kernel=None, decode="nvjpeg"):
+    """reconstruct_slide (reconstruct_full_images.py:334-417) with every accumulation on the device: the probability
+    accumulator plus four auxiliary planes sharing its weights - R, G, B of the mosaic (:411-415) and the blended ground truth
+    (:404-409).  Tiles are decoded straight into device memory (nvJPEG) and pushed as uint8; no float32 tile list exists.
+    -> dict(bgr8, prob, prob8, gt8 or None, mask, counts or None)."""
     from .. import api, _lib
     eng = model.engine
     H, W = full_shape
     mode = _lib.BLEND_GAUSSIAN if blend_mode in ("gaussian", "hann") else _lib.BLEND_LINEAR
     window = api.blend_window(blend_mode, tile_size)
     ops = api.TTA_OPCODES[tta_mode] if tta_mode else None
+    has_gt = bool(tiles_info) and all(t[3] is not None for t in tiles_info)
     eng.wsi_begin(H, W, 0, tile_size, mode, window)
-    positions, gt_tiles, rgb_tiles = [], [], []
-    batch, ys, xs = [], [], []
-
-    def flush():
-        if batch:
-            if refine_kernel:          # :372-380: predict (+TTA), BoundaryRefiner.refine per tile, then blend the refined tiles
-                probs = eng.predict(np.stack(batch).astype(np.float32), mean, std, ops)
-                eng.wsi_push_probs(eng.boundary_refine(probs, kernel_size=refine_kernel), ys, xs)
-            else:
-                eng.wsi_push_tiles(np.stack(batch).astype(np.float32), ys, xs, mean, std, ops)
-            batch.clear(); ys.clear(); xs.clear()
-
-    for row, col, img_path, mask_path in tiles_info:
-        bgr = cv2.imread(str(img_path), cv2.IMREAD_COLOR)
-        gray = cv2.imread(str(img_path), cv2.IMREAD_GRAYSCALE)
-        rgb_tiles.append(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB).astype(np.float32) / 255.0)
-        y = min(row * stride, H - tile_size); x = min(col * stride, W - tile_size)      # edge clamp, :399-400
-        positions.append((y, x))
-        batch.append(gray); ys.append(y); xs.append(x)
-        if len(batch) >= batch_tiles:
-            flush()
-        if mask_path is not None:
-            gt_tiles.append(C.read_mask(mask_path))
-    flush()
-    full_gt = None
-    if gt_tiles:
-        full_gt = eng.blend(mode, gt_tiles, positions, (H, W), window)
-    prob, mask, counts = eng.wsi_finalize(0, H, W, threshold, gt=full_gt, want_prob=True, want_mask=True)
+    eng.wsi_aux_begin(4 if has_gt else 3)
+    for i in range(0, len(tiles_info), batch_tiles):
+        chunk = tiles_info[i:i + batch_tiles]
+        # edge clamp, :399-400
+        ys = [min(row * stride, H - tile_size) for row, _, _, _ in chunk]
+        xs = [min(col * stride, W - tile_size) for _, col, _, _ in chunk]
+        gray, rgb = _load_tiles(eng, [t[2] for t in chunk], tile_size, decode)
+        if refine_kernel:          # :372-380: predict (+TTA), BoundaryRefiner.refine per tile, then blend the refined tiles
+            probs = eng.predict_u8_dev(gray, len(chunk), tile_size, 1, mean, std, ops)
+            eng.wsi_push_probs(eng.boundary_refine(probs, kernel_size=refine_kernel), ys, xs)
+        else:
+            eng.wsi_push_tiles_u8(gray, ys, xs, mean, std, ops, channels=1)
+        eng.wsi_push_aux(0, rgb, ys, xs, n_planes=3, is_u8=True)
+        if has_gt:
+            eng.wsi_push_aux(3, np.stack([C.read_mask(t[3]) for t in chunk]), ys, xs, n_planes=1)
+    out = dict(gt8=None, counts=None)
+    if has_gt:      # calculate_pixel_metrics(full_pred, full_gt, threshold), :745-749, on the blended ground truth
+        out["prob"], out["mask"], out["counts"] = eng.wsi_finalize_auxgt(3, 0, H, W, threshold)
+        out["gt8"] = eng.wsi_export_u8(3, 1, 0, H, W)                      # (full_gt * 255).astype(uint8), :745
+        out["gt_mask"] = eng.wsi_export_f32(3, 0, H, W) > 0.5              # the overlay's mask (:423-455)
+    else:
+        out["prob"], out["mask"], _ = eng.wsi_finalize(0, H, W, threshold, gt=None, want_prob=True, want_mask=True)
+    out["prob8"] = eng.wsi_export_u8(-1, 1, 0, H, W)                       # (full_pred * 255).astype(uint8), :733
+    out["bgr8"] = eng.wsi_export_u8(0, 3, 0, H, W, reverse=True)           # (rgb * 255).astype(uint8) -> COLOR_RGB2BGR, :726-727
     eng.wsi_end()
-    rgb = np.zeros((H, W, 3), np.float32)
-    for ch in range(3):
-        rgb[:, :, ch] = eng.blend(mode, [t[:, :, ch] for t in rgb_tiles], positions, (H, W), window)
-    return rgb, prob, full_gt, mask, (counts if full_gt is not None else None)
+    return out
 
 
 def main(argv=None) -> int:
@@ -173,21 +186,22 @@ def main(argv=None) -> int:
         else:
             full_shape = infer_full_image_dimensions(positions, args.tile_size, args.stride)
         print(f"  Reconstructing {full_shape[1]}x{full_shape[0]} with {args.blend_mode} blending...")
-        rgb, prob, gt, mask, counts = reconstruct_slide(model, tiles, full_shape, args.tile_size, args.stride, mean, std,
-                                                        args.blend_mode, tta_mode, args.threshold, args.batch_tiles,
-                                                        args.refine_kernel if args.boundary_refine else None)
+        r = reconstruct_slide(model, tiles, full_shape, args.tile_size, args.stride, mean, std, args.blend_mode, tta_mode,
+                              args.threshold, args.batch_tiles, args.refine_kernel if args.boundary_refine else None, args.decode)
+        prob, mask, counts, has_gt = r["prob"], r["mask"], r["counts"], r["gt8"] is not None
         sdir = output_dir / sid
         sdir.mkdir(parents=True, exist_ok=True)
-        rgb8 = (rgb * 255).astype(np.uint8)
-        cv2.imwrite(str(sdir / "original_image.tif"), cv2.cvtColor(rgb8, cv2.COLOR_RGB2BGR))
-        C.write_tiff_u8(sdir / "prediction_mask.tif", (prob * 255).astype(np.uint8))
+        # tifffile.imwrite(path, original_bgr, compression='lzw') (:724-728): the BGR-ordered samples go into the file as they are
+        api.write_tiff_lzw(sdir / "original_image.tif", r["bgr8"])
+        api.write_tiff_lzw(sdir / "prediction_mask.tif", r["prob8"])
+        rgb8 = r["bgr8"][:, :, ::-1]
         metrics = {}
-        if gt is not None:
-            C.write_tiff_u8(sdir / "ground_truth_mask.tif", (gt * 255).astype(np.uint8))
+        if has_gt:
+            api.write_tiff_lzw(sdir / "ground_truth_mask.tif", r["gt8"])
             metrics = api.metrics_from_counts(*counts)
             print(f"  Dice: {metrics['dice_score']:.4f}\n  IoU: {metrics['jaccard_index']:.4f}")
-            cv2.imwrite(str(sdir / "gt_overlay.png"), cv2.cvtColor(C.overlay(rgb8, gt > 0.5, (255, 255, 0)), cv2.COLOR_RGB2BGR))
-            cv2.imwrite(str(sdir / "pred_overlay.png"), cv2.cvtColor(C.overlay(rgb8, mask, (255, 0, 255)), cv2.COLOR_RGB2BGR))
+            cv2.imwrite(str(sdir / "gt_overlay.png"), cv2.cvtColor(C.overlay(np.ascontiguousarray(rgb8), r["gt_mask"], (255, 255, 0)), cv2.COLOR_RGB2BGR))
+            cv2.imwrite(str(sdir / "pred_overlay.png"), cv2.cvtColor(C.overlay(np.ascontiguousarray(rgb8), mask, (255, 0, 255)), cv2.COLOR_RGB2BGR))
             with open(sdir / "metrics.txt", "w") as f:
                 f.write(f"Full Image Reconstruction Metrics\n{'=' * 60}\n\nSlide: {sid}\n")
                 f.write(f"Image Size: {full_shape[1]} x {full_shape[0]} pixels\nTiles Used: {len(tiles)}\nCoverage: {coverage:.1%}\n\n")
@@ -205,7 +219,7 @@ def main(argv=None) -> int:
                    "dimensions": {"width": full_shape[1], "height": full_shape[0],
                                   "tiles_rows": info["row_range"][1] - info["row_range"][0] + 1,
                                   "tiles_cols": info["col_range"][1] - info["col_range"][0] + 1},
-                   "metrics": metrics if gt is not None else None}
+                   "metrics": metrics if has_gt else None}
             results.append(res)
             with open(output_dir / "metrics" / f"{sid}_metrics.json", "w") as f:
                 json.dump(res, f, indent=2)

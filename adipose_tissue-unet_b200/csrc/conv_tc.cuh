@@ -126,6 +126,17 @@ size_t tc_smem_bytes(const ConvTcParams &p) {
   return (size_t)p.S * p.stage_stride + (size_t)p.mask_bufs * p.mask_bytes + (2 * p.S + 6 + 4) * 8 + (704 + 520) * 4;
 }
 
+// Timing experiments (ADP_TC_DEBUG switches, role timers) are compiled in only by a debug build
+// (`python -m adipose_unet_b200.build --force --debug`, -DADP_TC_DEBUG_BUILD=1): the production kernels carry no p.dbg
+// branches in the MMA-issue and epilogue loops.
+#ifndef ADP_TC_DEBUG_BUILD
+#define ADP_TC_DEBUG_BUILD 0
+#endif
+ADP_DEVINL bool tc_dbg(const ConvTcParams &p, int bits) {
+  if constexpr (ADP_TC_DEBUG_BUILD != 0) return (p.dbg & bits) != 0;
+  else return false;
+}
+
 constexpr int kTcThreads = 352;   // producer, MMA issuer A, 8 epilogue warps, MMA issuer B
 constexpr int EPI_STORE = 0, EPI_HEAD = 1, EPI_POOL = 2, EPI_BWD = 3;   // EPI_BWD = EPI_STORE with a mask (data-gradient twin)
 
@@ -256,10 +267,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }
         for (int c = 0; c < p.nchunks; ++c) {
           uint8_t *sa = smem + (size_t)st * p.stage_stride;
-          { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&empty[st], ph ^ 1, 1); if (p.dbg & 16) t_w0 += clock64() - tw; }
+          { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&empty[st], ph ^ 1, 1); if (tc_dbg(p, 16)) t_w0 += clock64() - tw; }
           // p.dbg (ADP_TC_DEBUG, timing experiments only - results are wrong): 2 = weights only for the first item,
           // 8 = activations only for the first item, 1 = no epilogue stores, 4 = one MMA per stage, 16 = role timers
-          const bool ld_b = !(p.dbg & 2) || item == (int)blockIdx.x, ld_a = !(p.dbg & 8) || item == (int)blockIdx.x;
+          const bool ld_b = !tc_dbg(p, 2) || item == (int)blockIdx.x, ld_a = !tc_dbg(p, 8) || item == (int)blockIdx.x;
           ptx::mbar_expect_tx(&full[st], (ld_a ? p.a_tx_bytes : 0u) + (ld_b ? p.b_bytes : 0u));
           int cgc = c * 2;                                     // first channel group of this chunk
           if (p.split) { const int cr = c / 3; cgc = cr * 2 + ((c - cr * 3) == 2 ? p.in_lo : 0); }
@@ -270,7 +281,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           if (++st == p.S) { st = 0; ph ^= 1; }
         }
       }
-      if (p.dbg & 16) { p.dbg_out[blockIdx.x * 8 + 0] = t_w0; p.dbg_out[blockIdx.x * 8 + 1] = clock64() - t_start; }
+      if (tc_dbg(p, 16)) { p.dbg_out[blockIdx.x * 8 + 0] = t_w0; p.dbg_out[blockIdx.x * 8 + 1] = clock64() - t_start; }
     }
   } else if (warp == 1 || warp == 10) {
     // ---------------- MMA issuers ----------------
@@ -280,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     // > 85 % busy on the 1024^2 layers - ~50 cycles of descriptor arithmetic per MMA - while no pipe was saturated.)
     if (ptx::elect_one()) {
       const int issuer = (warp == 10) ? 1 : 0;
-      const bool single_issuer = (p.dbg & 32) != 0;       // experiment switch: issuer B only observes
+      const bool single_issuer = tc_dbg(p, 32) != 0;       // experiment switch: issuer B only observes
       int st = 0; uint32_t ph = 0;
       // The other issuer's stages are still OBSERVED: an mbarrier parity wait is only meaningful for a waiter that sees
       // every phase of the barrier in order, so the skipping thread waits for each stage's 'full' phase and then arrives on
@@ -301,7 +312,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const uint32_t row_step = (2u * plane_a) >> 4;          // next output row = next row slot
       const uint32_t smem0 = ptx::smem_u32(smem);
       const uint32_t n_cols = (uint32_t)p.N;
-      const bool mma_all = !(p.dbg & 4);
+      const bool mma_all = !tc_dbg(p, 4);
       long long t_m0 = 0, t_m1 = 0, t_m2 = 0; const long long t_mstart = clock64();
       if constexpr (KYS) {
         constexpr int KY = (NTAPS == 9) ? 3 : 2, KX = KY;
@@ -319,12 +330,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
           if (single_issuer ? issuer != 0 : (it & 1) != issuer) { skip_item(); continue; }
           const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
-          { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3); if (p.dbg & 16) t_m0 += clock64() - tw; }
+          { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3); if (tc_dbg(p, 16)) t_m0 += clock64() - tw; }
           ptx::tc_fence_after();
           const uint32_t d0 = tmem_base + (uint32_t)buf * (uint32_t)T * n_cols;
           const uint32_t v_off = (uint32_t)p.var[item % p.nvar].xs_add;
           for (int c = 0; c < p.nchunks; ++c) {
-            { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&full[st], ph, 4); if (p.dbg & 16) t_m1 += clock64() - tw; }
+            { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&full[st], ph, 4); if (tc_dbg(p, 16)) t_m1 += clock64() - tw; }
             ptx::tc_fence_after();
             const uint32_t s_lo = ((smem0 + (uint32_t)st * p.stage_stride) & 0x3FFFFu) >> 4;
             const uint32_t sa_lo = s_lo + v_off;
@@ -357,10 +368,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 }
               }
             }
-            { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mma_commit(&empty[st]); if (p.dbg & 16) t_m2 += clock64() - tw; }
+            { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mma_commit(&empty[st]); if (tc_dbg(p, 16)) t_m2 += clock64() - tw; }
             if (++st == p.S) { st = 0; ph ^= 1; }
           }
-          { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mma_commit(&acc_full[buf]); if (p.dbg & 16) t_m2 += clock64() - tw; }
+          { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mma_commit(&acc_full[buf]); if (tc_dbg(p, 16)) t_m2 += clock64() - tw; }
         }
       } else {
       uint32_t a_off[NTAPS], b_off[NTAPS];                    // byte offsets within a stage, >> 4
@@ -375,12 +386,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
         if (single_issuer ? issuer != 0 : (it & 1) != issuer) { skip_item(); continue; }
         const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
-        { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3); if (p.dbg & 16) t_m0 += clock64() - tw; }
+        { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3); if (tc_dbg(p, 16)) t_m0 += clock64() - tw; }
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)buf * (uint32_t)T * n_cols;
         const uint32_t v_off = (uint32_t)p.var[item % p.nvar].xs_add;   // pixels == 16-byte units
         for (int c = 0; c < p.nchunks; ++c) {
-          { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&full[st], ph, 4); if (p.dbg & 16) t_m1 += clock64() - tw; }
+          { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&full[st], ph, 4); if (tc_dbg(p, 16)) t_m1 += clock64() - tw; }
           ptx::tc_fence_after();
           const uint32_t s_lo = ((smem0 + (uint32_t)st * p.stage_stride) & 0x3FFFFu) >> 4;
           const uint32_t sa_lo = s_lo + v_off;
@@ -393,13 +404,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               if (mma_all || (t | r) == 0) ptx::mma_f16_ss(d0 + (uint32_t)r * n_cols, ad, bd, idesc, (uint32_t)((c | t) != 0));
             }
           }
-          { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mma_commit(&empty[st]); if (p.dbg & 16) t_m2 += clock64() - tw; }
+          { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mma_commit(&empty[st]); if (tc_dbg(p, 16)) t_m2 += clock64() - tw; }
           if (++st == p.S) { st = 0; ph ^= 1; }
         }
-        { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mma_commit(&acc_full[buf]); if (p.dbg & 16) t_m2 += clock64() - tw; }
+        { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mma_commit(&acc_full[buf]); if (tc_dbg(p, 16)) t_m2 += clock64() - tw; }
       }
       }
-      if ((p.dbg & 16) && issuer == 0) { p.dbg_out[blockIdx.x * 8 + 2] = t_m0; p.dbg_out[blockIdx.x * 8 + 3] = t_m1; p.dbg_out[blockIdx.x * 8 + 4] = clock64() - t_mstart; p.dbg_out[blockIdx.x * 8 + 7] = t_m2; }
+      if (tc_dbg(p, 16) && issuer == 0) { p.dbg_out[blockIdx.x * 8 + 2] = t_m0; p.dbg_out[blockIdx.x * 8 + 3] = t_m1; p.dbg_out[blockIdx.x * 8 + 4] = clock64() - t_mstart; p.dbg_out[blockIdx.x * 8 + 7] = t_m2; }
     }
   } else {
     // ---------------- epilogue (warps 2..9; TMEM lane quarter = warp % 4, two warps per quarter) ----------------
@@ -435,7 +446,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         // the mask tile of the item sits in shared memory ([row][channel group][128 pixels][8]), landed there by the
         // producer's TMA box
         const int mb = it % p.mask_bufs; const uint32_t mph = (uint32_t)(it / p.mask_bufs) & 1u;
-        { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_full[buf], acc_ph, 6); if (p.dbg & 16) t_e0 += clock64() - tw; }
+        { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&acc_full[buf], acc_ph, 6); if (tc_dbg(p, 16)) t_e0 += clock64() - tw; }
         ptx::mbar_wait(&mask_full[mb], mph, 9);
         ptx::tc_fence_after();
         const uint8_t *mtile = smask + (size_t)mb * p.mask_bytes + (size_t)(q4 * 32 + lane) * 16;
@@ -485,7 +496,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             }
           }
         }
-        { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_full[buf], acc_ph, 6); if (p.dbg & 16) t_e0 += clock64() - tw; }
+        { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&acc_full[buf], acc_ph, 6); if (tc_dbg(p, 16)) t_e0 += clock64() - tw; }
         ptx::tc_fence_after();
         uint32_t acc[2][16];
         if (half < UE) ptx::tmem_ld16_issue(t0 + (uint32_t)half * 16u, acc[0]);
@@ -544,7 +555,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }
         }
       } else {
-      { const long long tw = (p.dbg & 16) ? clock64() : 0; ptx::mbar_wait(&acc_full[buf], acc_ph, 6); if (p.dbg & 16) t_e0 += clock64() - tw; }
+      { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&acc_full[buf], acc_ph, 6); if (tc_dbg(p, 16)) t_e0 += clock64() - tw; }
       ptx::tc_fence_after();
       if constexpr (EPI == EPI_STORE) {
         int srow = row0, scu = cu0;
@@ -553,7 +564,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           unit_next(srow, scu);
           float f[16];
           bias_relu16(r, sb + cu * 16, p.relu, f);
-          if ((ty * T + row < p.Hin) && (x < p.Win) && !(p.dbg & 1)) {
+          if ((ty * T + row < p.Hin) && (x < p.Win) && !tc_dbg(p, 1)) {
             __nv_bfloat16 *o = out_row(row) + (size_t)(2 * cu) * plane;
             if (p.resid) {
               float g[16];
@@ -585,7 +596,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             }
           });
           const int y = ty * T + row;
-          if (y < p.Hin && x < p.Win && !(p.dbg & 1)) {
+          if (y < p.Hin && x < p.Win && !tc_dbg(p, 1)) {
             z0 += shead[2 * p.N]; z1 += shead[2 * p.N + 1];
             p.prob[((size_t)n * p.Hout + y) * p.Wout + x] = 1.f / (1.f + expf(z0 - z1));
           }
@@ -606,7 +617,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           float fa[16], fb[16];
           bias_relu16(ra, sb + cu * 16, p.relu, fa);
           bias_relu16(rb, sb + cu * 16, p.relu, fb);
-          const bool live = (ty * T + 2 * k + 1 < p.Hin) && (x < p.Win) && !(p.dbg & 1);
+          const bool live = (ty * T + 2 * k + 1 < p.Hin) && (x < p.Win) && !tc_dbg(p, 1);
           if (live) {
             store16_out(out_row(2 * k) + (size_t)(2 * cu) * plane, (size_t)p.out_lo * plane, plane, fa);
             store16_out(out_row(2 * k + 1) + (size_t)(2 * cu) * plane, (size_t)p.out_lo * plane, plane, fb);
@@ -629,7 +640,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
     }
-    if ((p.dbg & 16) && warp == 2 && lane == 0) { p.dbg_out[blockIdx.x * 8 + 5] = t_e0; p.dbg_out[blockIdx.x * 8 + 6] = clock64() - t_estart; }
+    if (tc_dbg(p, 16) && warp == 2 && lane == 0) { p.dbg_out[blockIdx.x * 8 + 5] = t_e0; p.dbg_out[blockIdx.x * 8 + 6] = clock64() - t_estart; }
   }
 
   ptx::tc_fence_before();

@@ -5,6 +5,8 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvjpeg.h>
 
 #include <algorithm>
 #include <cmath>
@@ -17,11 +19,13 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "io_frontend.cuh"
 #include "kernels_post.cuh"
 #include "kernels_refine.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_train.cuh"
 #include "wgrad_tc.cuh"
+#include "tiff_lzw.h"
 
 using namespace adp;
 
@@ -43,6 +47,38 @@ EncodeTiledFn get_encode_tiled() {
     fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+// nvJPEG is resolved at run time (dlopen), like the one driver entry point above: the library loads on machines without
+// it and contains sm_100a code of this repository only.
+struct NvjpegApi {
+  decltype(&nvjpegCreateEx) CreateEx = nullptr;
+  decltype(&nvjpegJpegStateCreate) JpegStateCreate = nullptr;
+  decltype(&nvjpegGetImageInfo) GetImageInfo = nullptr;
+  decltype(&nvjpegDecode) Decode = nullptr;
+  decltype(&nvjpegJpegStateDestroy) JpegStateDestroy = nullptr;
+  decltype(&nvjpegDestroy) Destroy = nullptr;
+};
+const NvjpegApi &nvjpeg_api() {
+  static NvjpegApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *h = nullptr;
+    for (const char *name : {"libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so.12"})
+      if ((h = dlopen(name, RTLD_NOW | RTLD_LOCAL))) break;
+    if (h) {
+      api.CreateEx = reinterpret_cast<decltype(api.CreateEx)>(dlsym(h, "nvjpegCreateEx"));
+      api.JpegStateCreate = reinterpret_cast<decltype(api.JpegStateCreate)>(dlsym(h, "nvjpegJpegStateCreate"));
+      api.GetImageInfo = reinterpret_cast<decltype(api.GetImageInfo)>(dlsym(h, "nvjpegGetImageInfo"));
+      api.Decode = reinterpret_cast<decltype(api.Decode)>(dlsym(h, "nvjpegDecode"));
+      api.JpegStateDestroy = reinterpret_cast<decltype(api.JpegStateDestroy)>(dlsym(h, "nvjpegJpegStateDestroy"));
+      api.Destroy = reinterpret_cast<decltype(api.Destroy)>(dlsym(h, "nvjpegDestroy"));
+    }
+  }
+  if (!api.CreateEx || !api.JpegStateCreate || !api.GetImageInfo || !api.Decode || !api.JpegStateDestroy || !api.Destroy)
+    throw Error(ADP_ESTATE, "nvJPEG (libnvjpeg.so.12) is not available on this machine: decode the tiles on the host (--decode cv2)");
+  return api;
 }
 
 struct DevBuf {
@@ -145,6 +181,11 @@ struct adp_engine {
   // the rows another strip's partial sums must reach FIRST, kept until adp_wsi_replay_deferred
   struct Deferred { std::unique_ptr<DevBuf> probs; std::vector<int32_t> ys, xs; int below = 0; };
   std::vector<Deferred> wsi_deferred;
+  // auxiliary whole-slide planes (RGB mosaic, blended ground truth: io_frontend.cuh) sharing the probability accumulator's weights
+  DevBuf wsi_aux; int wsi_naux = 0;
+  // nvJPEG front-end (adp_jpeg_decode): handle, decoder state and the device-resident decoded tiles
+  nvjpegHandle_t jpeg_h = nullptr; nvjpegJpegState_t jpeg_st = nullptr;
+  DevBuf jpeg_gray, jpeg_rgb, aux_stage;
 
   // profiling
   bool prof = false;
@@ -1000,7 +1041,13 @@ int adp_create(int device, int precision, int init_nb, int max_forwards, adp_eng
           if (ConvTcKernel k = tc_kernel_lookup(nt, T, kys, epi))
             ADP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   ADP_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  if (const char *d = getenv("ADP_TC_DEBUG")) e->dbg = atoi(d);
+  if (const char *d = getenv("ADP_TC_DEBUG")) {
+    e->dbg = atoi(d);
+    if (e->dbg && !ADP_TC_DEBUG_BUILD) {
+      fprintf(stderr, "libadipose_b200: ADP_TC_DEBUG ignored - the timing switches exist only in a debug build (build.py --force --debug)\n");
+      e->dbg = 0;
+    }
+  }
   build_layers(e.get());
   *out = e.release();
   ADP_CATCH
@@ -1019,6 +1066,8 @@ int adp_destroy(adp_engine *e) {
     if (e->ev_out_ready[i]) cudaEventDestroy(e->ev_out_ready[i]);
     if (e->ev_out_free[i]) cudaEventDestroy(e->ev_out_free[i]);
   }
+  if (e->jpeg_st) nvjpeg_api().JpegStateDestroy(e->jpeg_st);
+  if (e->jpeg_h) nvjpeg_api().Destroy(e->jpeg_h);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e->tr;
@@ -1046,7 +1095,7 @@ int adp_set_option(adp_engine *e, const char *key, int value) {
   else if (k == "fuse_pool") e->fuse_pool = value != 0;
   else if (k == "wgrad_simt") e->wgrad_simt = value != 0;
   else if (k == "dgrad_simt") e->dgrad_simt = value != 0;
-  else if (k == "debug") e->dbg = value;
+  else if (k == "debug") e->dbg = ADP_TC_DEBUG_BUILD ? value : 0;
   else if (k == "kys") { e->kys = value != 0; e->packed = false; }   // ky-stacked MMA issue (conv_tc.cuh); re-plans on next use
   else throw Error(ADP_EINVAL, "unknown option " + k);
   ADP_CATCH
@@ -1532,7 +1581,218 @@ int adp_wsi_end(adp_engine *e) {
   ADP_CUDA(cudaSetDevice(e->device));
   e->wsi_acc.release(); e->wsi_wsum.release(); e->wsi_window.release();
   e->wsi_deferred.clear();
+  e->wsi_aux.release(); e->wsi_naux = 0;
   e->wsi_on = false;
+  ADP_CATCH
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile I/O front-end: nvJPEG decode, uint8 tile push, auxiliary planes, fat-%, TIFF-LZW
+#define ADP_NVJPEG(expr)                                                                                     \
+  do {                                                                                                       \
+    nvjpegStatus_t _s = (expr);                                                                              \
+    if (_s != NVJPEG_STATUS_SUCCESS) throw Error(ADP_ECUDA, std::string(#expr) + ": nvjpeg status " + std::to_string((int)_s)); \
+  } while (0)
+
+int adp_jpeg_decode(adp_engine *e, const uint8_t *const *data, const size_t *lengths, int n, int size, uint8_t *gray_host,
+                    uint8_t *rgb_host, uint8_t **gray_dev, uint8_t **rgb_dev) {
+  ADP_TRY
+  ADP_REQUIRE(e && data && lengths && n > 0 && size > 0, "null/empty argument");
+  ADP_CUDA(cudaSetDevice(e->device));
+  if (!e->jpeg_h) {
+    // interpolated chroma upsampling = libjpeg's "fancy upsampling", the default of the cv2.imread the reference decodes with
+    ADP_NVJPEG(nvjpeg_api().CreateEx(NVJPEG_BACKEND_DEFAULT, nullptr, nullptr, NVJPEG_FLAGS_UPSAMPLING_WITH_INTERPOLATION, &e->jpeg_h));
+    ADP_NVJPEG(nvjpeg_api().JpegStateCreate(e->jpeg_h, &e->jpeg_st));
+  }
+  const bool want_gray = gray_host || gray_dev, want_rgb = rgb_host || rgb_dev;
+  const size_t px = (size_t)size * size;
+  if (want_gray) e->jpeg_gray.ensure((size_t)n * px);
+  if (want_rgb) e->jpeg_rgb.ensure((size_t)n * px * 3);
+  for (int i = 0; i < n; ++i) {
+    int ncomp = 0; nvjpegChromaSubsampling_t sub;
+    int ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
+    ADP_NVJPEG(nvjpeg_api().GetImageInfo(e->jpeg_h, data[i], lengths[i], &ncomp, &sub, ws, hs));
+    if (ws[0] != size || hs[0] != size)
+      throw Error(ADP_EINVAL, "JPEG tile " + std::to_string(i) + " is " + std::to_string(ws[0]) + "x" + std::to_string(hs[0]) + ", expected " +
+                                  std::to_string(size) + "x" + std::to_string(size));
+    if (want_gray) {       // the luma plane: what libjpeg hands cv2.imread(..., IMREAD_GRAYSCALE) (out_color_space = JCS_GRAYSCALE)
+      nvjpegImage_t img; memset(&img, 0, sizeof(img));
+      img.channel[0] = e->jpeg_gray.as<unsigned char>() + (size_t)i * px; img.pitch[0] = (size_t)size;
+      ADP_NVJPEG(nvjpeg_api().Decode(e->jpeg_h, e->jpeg_st, data[i], lengths[i], NVJPEG_OUTPUT_Y, &img, e->stream));
+    }
+    if (want_rgb) {
+      nvjpegImage_t img; memset(&img, 0, sizeof(img));
+      img.channel[0] = e->jpeg_rgb.as<unsigned char>() + (size_t)i * px * 3; img.pitch[0] = (size_t)size * 3;
+      ADP_NVJPEG(nvjpeg_api().Decode(e->jpeg_h, e->jpeg_st, data[i], lengths[i], NVJPEG_OUTPUT_RGBI, &img, e->stream));
+    }
+    ++e->launches;
+  }
+  if (gray_host) ADP_CUDA(cudaMemcpyAsync(gray_host, e->jpeg_gray.p, (size_t)n * px, cudaMemcpyDeviceToHost, e->stream));
+  if (rgb_host) ADP_CUDA(cudaMemcpyAsync(rgb_host, e->jpeg_rgb.p, (size_t)n * px * 3, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  if (gray_dev) *gray_dev = e->jpeg_gray.as<uint8_t>();
+  if (rgb_dev) *rgb_dev = e->jpeg_rgb.as<uint8_t>();
+  ADP_CATCH
+}
+
+int adp_wsi_push_tiles_u8(adp_engine *e, const uint8_t *tiles, int channels, int n, const int32_t *ys, const int32_t *xs, float mean,
+                          float std_, const int *ops, int n_ops) {
+  ADP_TRY
+  ADP_REQUIRE(e && tiles && ys && xs && n > 0, "null/empty argument");
+  ADP_REQUIRE(channels == 1 || channels == 3, "channels must be 1 or 3");
+  if (!e->wsi_on) throw Error(ADP_ESTATE, "adp_wsi_begin not called");
+  ADP_CUDA(cudaSetDevice(e->device));
+  FirstConvSrc s{};
+  s.ch = channels;
+  run_tiles(e, 1, s, tiles, n, e->wsi_tile, mean, std_, ops, n_ops, nullptr, ys, xs, nullptr);
+  ADP_CATCH
+}
+
+int adp_wsi_aux_begin(adp_engine *e, int n_planes) {
+  ADP_TRY
+  ADP_REQUIRE(e && n_planes >= 1 && n_planes <= 4, "1..4 auxiliary planes");
+  if (!e->wsi_on) throw Error(ADP_ESTATE, "adp_wsi_begin not called");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const size_t bytes = (size_t)n_planes * e->wsi_rows * e->wsi_W * 4;
+  e->wsi_aux.ensure(bytes);
+  ADP_CUDA(cudaMemsetAsync(e->wsi_aux.p, 0, bytes, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  e->wsi_naux = n_planes;
+  ADP_CATCH
+}
+
+int adp_wsi_push_aux(adp_engine *e, int plane0, int n_planes, const void *tiles, int is_u8, int n, const int32_t *ys, const int32_t *xs) {
+  ADP_TRY
+  ADP_REQUIRE(e && tiles && ys && xs && n > 0, "null/empty argument");
+  if (!e->wsi_on || e->wsi_naux == 0) throw Error(ADP_ESTATE, "adp_wsi_aux_begin not called");
+  ADP_REQUIRE(plane0 >= 0 && (n_planes == 1 || n_planes == 3) && plane0 + n_planes <= e->wsi_naux, "plane range");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const int S = e->wsi_tile;
+  const size_t tpx = (size_t)S * S, tb = tpx * n_planes * (is_u8 ? 1 : 4);
+  const size_t plane_stride = (size_t)e->wsi_rows * e->wsi_W;
+  const int mode = e->wsi_mode == ADP_BLEND_GAUSSIAN ? 1 : 2;
+  const int grid = (int)std::min<size_t>(cdiv64(tpx, 256), (size_t)e->num_sms * 8);
+  const bool host = !is_device_ptr(tiles);
+  const int chunk = 16;
+  for (int t0 = 0; t0 < n; t0 += chunk) {
+    const int nt = std::min(chunk, n - t0);
+    const uint8_t *dt = reinterpret_cast<const uint8_t *>(tiles) + (size_t)t0 * tb;
+    if (host) {
+      e->aux_stage.ensure((size_t)chunk * tb);
+      ADP_CUDA(cudaMemcpyAsync(e->aux_stage.p, dt, (size_t)nt * tb, cudaMemcpyHostToDevice, e->stream));
+      dt = e->aux_stage.as<uint8_t>();
+    }
+    for (int t = 0; t < nt; ++t)     // stream order == list order: the accumulation order of the NumPy loop
+      e->launch("aux_blend", 0, (double)tpx * n_planes * (is_u8 ? 9 : 12), [&] {
+        aux_blend_kernel<<<grid, 256, 0, e->stream>>>(dt + (size_t)t * tb, is_u8, n_planes, S, mode, e->wsi_aux.as<float>() + (size_t)plane0 * plane_stride,
+                                                     plane_stride, e->wsi_window.as<float>(), e->wsi_W, 0, e->wsi_rows, ys[t0 + t] - e->wsi_y0,
+                                                     xs[t0 + t]);
+      });
+    ADP_CUDA(cudaStreamSynchronize(e->stream));
+  }
+  ADP_CATCH
+}
+
+int adp_wsi_export_u8(adp_engine *e, int plane0, int n_planes, int reverse, int y, int rows, uint8_t *out) {
+  ADP_TRY
+  ADP_REQUIRE(e && out, "null argument");
+  if (!e->wsi_on) throw Error(ADP_ESTATE, "adp_wsi_begin not called");
+  ADP_REQUIRE(y >= e->wsi_y0 && rows > 0 && y + rows <= e->wsi_y0 + e->wsi_rows, "row range outside the accumulator");
+  ADP_REQUIRE((plane0 == -1 && n_planes == 1) || (plane0 >= 0 && n_planes >= 1 && plane0 + n_planes <= e->wsi_naux), "plane range");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const size_t off = (size_t)(y - e->wsi_y0) * e->wsi_W, n = (size_t)rows * e->wsi_W;
+  const size_t plane_stride = (size_t)e->wsi_rows * e->wsi_W;
+  const float *planes = plane0 < 0 ? e->wsi_acc.as<float>() + off : e->wsi_aux.as<float>() + (size_t)plane0 * plane_stride + off;
+  const bool host = !is_device_ptr(out);
+  uint8_t *o = out;
+  if (host) { e->fin_mask.ensure(n * n_planes); o = e->fin_mask.as<uint8_t>(); }
+  const int grid = e->wave_grid(aux_export_u8_kernel, cdiv64(n, 256));
+  e->launch("aux_export_u8", 0, (double)n * n_planes * 5 + (double)n * 4, [&] {
+    aux_export_u8_kernel<<<grid, 256, 0, e->stream>>>(planes, plane_stride, e->wsi_wsum.as<float>() + off, e->wsi_mode == ADP_BLEND_LINEAR, n,
+                                                     n_planes, reverse, o);
+  });
+  if (host) ADP_CUDA(cudaMemcpyAsync(out, o, n * n_planes, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  ADP_CATCH
+}
+
+int adp_wsi_export_f32(adp_engine *e, int plane, int y, int rows, float *out) {
+  ADP_TRY
+  ADP_REQUIRE(e && out, "null argument");
+  if (!e->wsi_on) throw Error(ADP_ESTATE, "adp_wsi_begin not called");
+  ADP_REQUIRE(y >= e->wsi_y0 && rows > 0 && y + rows <= e->wsi_y0 + e->wsi_rows, "row range outside the accumulator");
+  ADP_REQUIRE(plane >= 0 && plane < e->wsi_naux, "plane");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const size_t off = (size_t)(y - e->wsi_y0) * e->wsi_W, n = (size_t)rows * e->wsi_W;
+  const size_t plane_stride = (size_t)e->wsi_rows * e->wsi_W;
+  const bool host = !is_device_ptr(out);
+  float *o = out;
+  if (host) { e->fin_prob.ensure(n * 4); o = e->fin_prob.as<float>(); }
+  const int grid = e->wave_grid(aux_export_f32_kernel, cdiv64(n, 256));
+  e->launch("aux_export_f32", 0, (double)n * 12, [&] {
+    aux_export_f32_kernel<<<grid, 256, 0, e->stream>>>(e->wsi_aux.as<float>() + (size_t)plane * plane_stride + off, e->wsi_wsum.as<float>() + off,
+                                                      e->wsi_mode == ADP_BLEND_LINEAR, n, o);
+  });
+  if (host) ADP_CUDA(cudaMemcpyAsync(out, o, n * 4, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  ADP_CATCH
+}
+
+int adp_wsi_finalize_auxgt(adp_engine *e, int gt_plane, int y, int rows, float thr, float *prob, uint8_t *mask, int64_t counts[4]) {
+  ADP_TRY
+  ADP_REQUIRE(e && counts, "null argument");
+  if (!e->wsi_on) throw Error(ADP_ESTATE, "adp_wsi_begin not called");
+  ADP_REQUIRE(y >= e->wsi_y0 && rows > 0 && y + rows <= e->wsi_y0 + e->wsi_rows, "row range outside the accumulator");
+  ADP_REQUIRE(gt_plane >= 0 && gt_plane < e->wsi_naux, "gt_plane");
+  ADP_CUDA(cudaSetDevice(e->device));
+  const size_t off = (size_t)(y - e->wsi_y0) * e->wsi_W, n = (size_t)rows * e->wsi_W;
+  const size_t plane_stride = (size_t)e->wsi_rows * e->wsi_W;
+  const bool prob_host = prob && !is_device_ptr(prob), mask_host = mask && !is_device_ptr(mask);
+  float *dp = prob; uint8_t *dm = mask;
+  if (prob_host) { e->fin_prob.ensure(n * 4); dp = e->fin_prob.as<float>(); }
+  if (mask_host) { e->fin_mask.ensure(n); dm = e->fin_mask.as<uint8_t>(); }
+  e->counts.ensure(32);
+  ADP_CUDA(cudaMemsetAsync(e->counts.p, 0, 32, e->stream));
+  const int grid = e->wave_grid(finalize_auxgt_kernel, cdiv64(n, 256));
+  e->launch("finalize_threshold_metrics", 0, (double)n * 17, [&] {
+    finalize_auxgt_kernel<<<grid, 256, 0, e->stream>>>(e->wsi_acc.as<float>() + off, e->wsi_wsum.as<float>() + off,
+                                                      e->wsi_aux.as<float>() + (size_t)gt_plane * plane_stride + off, e->wsi_mode == ADP_BLEND_LINEAR,
+                                                      n, thr, dp, dm, e->counts.as<unsigned long long>());
+  });
+  if (prob_host) ADP_CUDA(cudaMemcpyAsync(prob, dp, n * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (mask_host) ADP_CUDA(cudaMemcpyAsync(mask, dm, n, cudaMemcpyDeviceToHost, e->stream));
+  unsigned long long hc[4];
+  ADP_CUDA(cudaMemcpyAsync(hc, e->counts.p, 32, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  for (int i = 0; i < 4; ++i) counts[i] = (int64_t)hc[i];
+  ADP_CATCH
+}
+
+int adp_tile_fat_percent(adp_engine *e, const float *probs, int n, int64_t px, float thr, double *pct) {
+  ADP_TRY
+  ADP_REQUIRE(e && probs && pct && n > 0 && px > 0, "null/empty argument");
+  ADP_CUDA(cudaSetDevice(e->device));
+  DevBuf dp, dc;
+  const float *p = reinterpret_cast<const float *>(to_device(e, dp, probs, (size_t)n * px * 4));
+  dc.ensure((size_t)n * 8);
+  ADP_CUDA(cudaMemsetAsync(dc.p, 0, (size_t)n * 8, e->stream));
+  const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv64(px, 256 * 8), (int64_t)e->num_sms * 2)), (unsigned)n);
+  e->launch("tile_fat_count", 0, (double)n * px * 4, [&] {
+    tile_count_kernel<<<grid, 256, 0, e->stream>>>(p, (size_t)px, thr, dc.as<unsigned long long>());
+  });
+  std::vector<unsigned long long> h(n);
+  ADP_CUDA(cudaMemcpyAsync(h.data(), dc.p, (size_t)n * 8, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaStreamSynchronize(e->stream));
+  // (fat_pixels / total_pixels) * 100.0 in float64, tile_classification_evaluation.py:222-225
+  for (int i = 0; i < n; ++i) pct[i] = ((double)h[i] / (double)px) * 100.0;
+  ADP_CATCH
+}
+
+int adp_tiff_write_lzw(const char *path, const uint8_t *data, int64_t H, int64_t W, int channels, int rows_per_strip, int threads) {
+  ADP_TRY
+  std::string msg;
+  const int rc = adp_tiff::write_lzw(path, data, H, W, channels, rows_per_strip, threads, msg);
+  if (rc != 0) throw Error(ADP_EINVAL, msg);
   ADP_CATCH
 }
 

@@ -100,15 +100,9 @@ ADP_DEVINL void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// same, kind::tf32 (fp32 storage, 10-bit mantissa inputs, K = 8 per instruction)
-ADP_DEVINL void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
+// (No kind::tf32 variant: a TF32 path cannot meet the <= 1e-4 probability bound on this 22-layer graph - operand truncation to
+// 10 mantissa bits gives 1.2e-3 (round-to-nearest) .. 3.5e-3 (hardware truncation) max-abs error against the float64 oracle,
+// tools/tf32_error_sim.py -> profiles/r2_tf32_simulation.txt; the <= 1e-4 tensor-core path is bf16x3, 1.7e-5.)
 // all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
 ADP_DEVINL void mma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))

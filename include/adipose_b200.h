@@ -189,6 +189,43 @@ int adp_wsi_finalize(adp_engine *e, int y, int rows, float thr, float *prob, uin
                      const uint8_t *gt, int64_t counts[4]);
 int adp_wsi_end(adp_engine *e);
 
+/* ---- tile I/O front-end --------------------------------------------
+ * adp_jpeg_decode: nvJPEG decode of n JPEG tiles (size x size) on the engine's stream.  gray = the luma plane, i.e. what
+ * cv2.imread(path, IMREAD_GRAYSCALE) returns (libjpeg decodes with out_color_space = JCS_GRAYSCALE; reconstruct_full_images.py:364,
+ * full_evaluation_enhanced.py:1383, segmentation_inference.py:435); rgb = interleaved RGB with interpolated chroma upsampling
+ * (cv2.imread(IMREAD_COLOR) + COLOR_BGR2RGB, reconstruct_full_images.py:367-368).  The decoded tiles stay on the device
+ * (*gray_dev / *rgb_dev, valid until the next decode) for adp_predict_u8 / adp_wsi_push_tiles_u8 / adp_wsi_push_aux; host
+ * copies are optional.  nvJPEG's inverse DCT is not bit-identical to libjpeg-turbo's: tests/test_gpu_io.py measures the
+ * difference (grey levels and resulting mask agreement). */
+int adp_jpeg_decode(adp_engine *e, const uint8_t *const *data, const size_t *lengths, int n, int size, uint8_t *gray_host,
+                    uint8_t *rgb_host, uint8_t **gray_dev, uint8_t **rgb_dev);
+/* adp_wsi_push_tiles for packed uint8 tiles (host or device; channels = 1 gray, 3 interleaved RGB -> OpenCV gray formula) */
+int adp_wsi_push_tiles_u8(adp_engine *e, const uint8_t *tiles, int channels, int n, const int32_t *ys, const int32_t *xs,
+                          float mean, float std, const int *ops, int n_ops);
+/* Auxiliary whole-slide planes next to the probability accumulator, sharing its weight plane (same tiles, positions and
+ * window => same weight sums): the RGB mosaic (three blender.reconstruct calls on the tiles' colour channels as float32
+ * in [0,1], reconstruct_full_images.py:411-415) and the blended ground truth (:404-409) without host-side float32 tile
+ * lists.  adp_wsi_aux_begin after adp_wsi_begin; adp_wsi_push_aux blends n tiles (n_planes = 1 or 3 interleaved samples,
+ * is_u8: bytes scaled by 1/255 in float32, else float32 values; host or device) into planes plane0..; push the same
+ * tiles in the same order as the predictions.
+ * adp_wsi_export_u8: (normalised plane * 255).astype(uint8) of n_planes consecutive planes, interleaved, optionally in
+ * reverse plane order (the reference writes RGB2BGR-converted data, :726-728); plane0 = -1 exports the probability plane
+ * (prediction_mask.tif, :733).  adp_wsi_export_f32: one normalised plane.  adp_wsi_finalize_auxgt: adp_wsi_finalize with
+ * truth = (normalised gt_plane > 0.5), i.e. calculate_pixel_metrics(full_pred, full_gt, thr) (:745-749). */
+int adp_wsi_aux_begin(adp_engine *e, int n_planes);
+int adp_wsi_push_aux(adp_engine *e, int plane0, int n_planes, const void *tiles, int is_u8, int n, const int32_t *ys,
+                     const int32_t *xs);
+int adp_wsi_export_u8(adp_engine *e, int plane0, int n_planes, int reverse, int y, int rows, uint8_t *out);
+int adp_wsi_export_f32(adp_engine *e, int plane, int y, int rows, float *out);
+int adp_wsi_finalize_auxgt(adp_engine *e, int gt_plane, int y, int rows, float thr, float *prob, uint8_t *mask, int64_t counts[4]);
+/* fat-% of n probability tiles of px pixels: 100 * count(p > thr) / px (calculate_fat_percentage,
+ * tile_classification_evaluation.py:211-225), one launch for the batch */
+int adp_tile_fat_percent(adp_engine *e, const float *probs, int n, int64_t px, float thr, double *pct);
+/* Baseline TIFF with LZW compression, strips compressed in parallel on `threads` host threads (0 = all cores); replaces
+ * tifffile.imwrite(path, array, compression='lzw') (reconstruct_full_images.py:724-734, segmentation_inference.py:455-464).
+ * data: H x W x channels uint8 (channels 1 or 3, samples written in the caller's order).  Host only, no engine needed. */
+int adp_tiff_write_lzw(const char *path, const uint8_t *data, int64_t H, int64_t W, int channels, int rows_per_strip, int threads);
+
 /* ---- loss ---------------------------------------------------------------------------------------
  * adp_loss_metrics: combined_loss_standard = mean BCE + (1 - global Dice) and dice_coef
  * (train_adipose_unet_v3.py:217-241, src/utils/model.py:93-98) of probabilities p against y,

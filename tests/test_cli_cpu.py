@@ -262,8 +262,44 @@ def test_recon_host_pipeline_with_stub_engine(tmp_path, monkeypatch):
         def wsi_push_tiles(self, tiles, ys, xs, mean, std, ops):
             self.wsi_push_probs(fake_prob(tiles), ys, xs)
 
+        def wsi_push_tiles_u8(self, tiles, ys, xs, mean, std, ops, channels=1):
+            self.wsi_push_probs(fake_prob(tiles), ys, xs)
+
         def predict(self, tiles, mean, std, ops=None, out=None):
             return fake_prob(tiles)
+
+        def predict_u8_dev(self, tiles, n, size, channels, mean, std, ops=None):
+            return fake_prob(tiles)
+
+        def jpeg_decode(self, blobs, size, want_gray=True, want_rgb=False, to_host=True):
+            # stand-in for nvJPEG: libjpeg through OpenCV ("device" handles are plain arrays here)
+            dec = [np.frombuffer(b, np.uint8) for b in blobs]
+            gray = np.stack([cv2.imdecode(d, cv2.IMREAD_GRAYSCALE) for d in dec])
+            rgb = np.stack([cv2.cvtColor(cv2.imdecode(d, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB) for d in dec])
+            return dict(gray=gray, rgb=rgb, gray_dev=gray, rgb_dev=rgb, n=len(blobs), size=size)
+
+        def wsi_aux_begin(self, n):
+            self.aux = {p: [] for p in range(n)}
+
+        def wsi_push_aux(self, plane0, tiles, ys, xs, n_planes=1, is_u8=None):
+            t = np.asarray(tiles)
+            v = (t.astype(np.float32) / 255.0).astype(np.float32) if t.dtype == np.uint8 else t.astype(np.float32)
+            for c in range(n_planes):
+                self.aux[plane0 + c] += [x[..., c] if n_planes > 1 else x for x in v]
+
+        def _plane(self, p):
+            return self.blend(self.mode, self.tiles if p < 0 else self.aux[p], self.pos, self.shape, self.window)
+
+        def wsi_export_u8(self, plane0, n_planes, y, rows, W, reverse=False):
+            order = range(plane0 + n_planes - 1, plane0 - 1, -1) if reverse else range(plane0, plane0 + n_planes)
+            planes = [(self._plane(p) * 255).astype(np.uint8) for p in order]
+            return planes[0] if n_planes == 1 else np.stack(planes, axis=-1)
+
+        def wsi_export_f32(self, plane, y, rows, W):
+            return self._plane(plane)
+
+        def wsi_finalize_auxgt(self, gt_plane, y, rows, W, threshold=0.5, want_prob=True, want_mask=True):
+            return self.wsi_finalize(y, rows, W, threshold, gt=self._plane(gt_plane))
 
         def boundary_refine(self, mask, kernel_size=5, **kw):
             return np.stack([R.refine(m, kernel_size=kernel_size) for m in mask])
@@ -305,6 +341,10 @@ def test_recon_host_pipeline_with_stub_engine(tmp_path, monkeypatch):
     np.testing.assert_array_equal(got, (want * 255).astype(np.uint8))
     rgb = cv2.imread(str(sdir / "original_image.tif"), cv2.IMREAD_COLOR)
     assert rgb.shape == (1024, 2048, 3) and np.abs(rgb[:, :, 0].astype(int) - base.astype(int)).max() <= 4      # JPEG q100 + blend (corners included: the Hann floor)
+    # ground truth: blended 0/1 masks, (full_gt * 255).astype(uint8) through the library's LZW writer
+    gtf = cv2.imread(str(sdir / "ground_truth_mask.tif"), cv2.IMREAD_UNCHANGED)
+    masks = [(t > 128).astype(np.float32) for t in [base[:, c * stride:c * stride + T] for c in range(3)]]
+    np.testing.assert_array_equal(gtf, (G.hann_reconstruct(masks, [(0, 0), (0, 512), (0, 1024)], (1024, 2048)) * 255).astype(np.uint8))
 
 
 def test_infer_host_pipeline_with_stub_engine(tmp_path, monkeypatch, capsys):

@@ -91,7 +91,7 @@ def test_train_then_eval_infer_recon(workspace, capsys):
     # whole-slide reconstruction of the validation slide (2 tiles, 50 % overlap) against the oracle's blend
     rout = ws / "recon_out"
     rc = recon.main(["--weights", str(ck / "weights_best_overall.weights.h5"), "--data-root", str(val), "--output-dir", str(rout),
-                     "--stride", "512", "--blend-mode", "gaussian"])
+                     "--stride", "512", "--blend-mode", "gaussian", "--decode", "cv2"])      # host libjpeg: the reference's exact tile bytes
     assert rc == 0
     sdir = rout / "slideA"
     for f in ("original_image.tif", "prediction_mask.tif", "ground_truth_mask.tif", "gt_overlay.png", "pred_overlay.png", "metrics.txt"):
@@ -112,10 +112,28 @@ def test_train_then_eval_infer_recon(workspace, capsys):
     from oracle import refine as R
     rout2 = ws / "recon_refined"
     rc = recon.main(["--weights", str(ck / "weights_best_overall.weights.h5"), "--data-root", str(val), "--output-dir", str(rout2),
-                     "--stride", "512", "--blend-mode", "hann", "--boundary-refine", "--refine-kernel", "5"])
+                     "--stride", "512", "--blend-mode", "hann", "--boundary-refine", "--refine-kernel", "5", "--decode", "cv2"])
     assert rc == 0
     log = json.loads((rout2 / "reconstruction_log.json").read_text())
     assert log["parameters"]["boundary_refine"] is True and log["parameters"]["refine_kernel"] == 5
     want2 = G.hann_reconstruct([R.refine(p) for p in preds], [(0, 0), (0, 512)], (1024, 1536), G.hann_window(T))
     got2 = cv2.imread(str(rout2 / "slideA" / "prediction_mask.tif"), cv2.IMREAD_UNCHANGED)
     assert np.abs(got2.astype(np.int32) - (want2 * 255).astype(np.uint8).astype(np.int32)).max() <= 1
+
+
+    # default decode path: nvJPEG on the device.  Its IDCT is not libjpeg-turbo's, so tile bytes may differ by a grey level
+    # (tests/test_gpu_io.py measures it); the reconstructed outputs must stay within 2 levels of the host-decoded run.
+    rout3 = ws / "recon_nvjpeg"
+    rc = recon.main(["--weights", str(ck / "weights_best_overall.weights.h5"), "--data-root", str(val), "--output-dir", str(rout3),
+                     "--stride", "512", "--blend-mode", "gaussian"])
+    assert rc == 0
+    got3 = cv2.imread(str(rout3 / "slideA" / "prediction_mask.tif"), cv2.IMREAD_UNCHANGED)
+    d3 = np.abs(got3.astype(np.int32) - got.astype(np.int32))
+    print("recon nvJPEG vs cv2 decode: prediction_mask.tif max diff", int(d3.max()), "levels, differing px", float((d3 > 0).mean()))
+    assert d3.max() <= 2
+    o1 = cv2.imread(str(sdir / "original_image.tif"), cv2.IMREAD_COLOR).astype(np.int32)
+    o3 = cv2.imread(str(rout3 / "slideA" / "original_image.tif"), cv2.IMREAD_COLOR).astype(np.int32)
+    assert o1.shape == o3.shape == (1024, 1536, 3) and np.abs(o1 - o3).max() <= 3
+    g1 = cv2.imread(str(sdir / "ground_truth_mask.tif"), cv2.IMREAD_UNCHANGED)
+    g3 = cv2.imread(str(rout3 / "slideA" / "ground_truth_mask.tif"), cv2.IMREAD_UNCHANGED)
+    np.testing.assert_array_equal(g1, g3)
