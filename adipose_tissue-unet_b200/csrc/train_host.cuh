@@ -64,7 +64,15 @@ struct TrainState {
   struct Bucket { size_t lo = 0, hi = 0; cudaEvent_t ev = nullptr; };
   std::vector<Bucket> buckets;
   cudaEvent_t ev_join = nullptr;
+  // second stream of the backward pass: HBM-bound elementwise kernels that are off the critical chain (upsample
+  // materialisation, upsample / max-pool backward) run under tensor-bound weight-gradient kernels of the main stream
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fwd = nullptr, ev_mat[3] = {nullptr, nullptr, nullptr}, ev_a = nullptr, ev_b = nullptr;
+  DevBuf up_x[3];             // UpSampling2D(x) of the three upsampled convs' inputs (weight-gradient operands)
+  bool overlap = true;
   ~TrainState() {
+    if (side) cudaStreamDestroy(side);
+    for (cudaEvent_t ev : {ev_fwd, ev_mat[0], ev_mat[1], ev_mat[2], ev_a, ev_b}) if (ev) cudaEventDestroy(ev);
     if (pinned_sums) cudaFreeHost(pinned_sums);
     if (ev_sums) cudaEventDestroy(ev_sums);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -191,6 +199,13 @@ void train_alloc(adp_engine *e, int nb, int S, float dropout_rate, uint64_t seed
   ADP_CUDA(cudaMallocHost(&tr->pinned_sums, 24 * 8));
   ADP_CUDA(cudaEventCreateWithFlags(&tr->ev_sums, cudaEventDisableTiming));
   ADP_CUDA(cudaEventCreateWithFlags(&tr->ev_join, cudaEventDisableTiming));
+  ADP_CUDA(cudaStreamCreateWithFlags(&tr->side, cudaStreamNonBlocking));
+  for (cudaEvent_t *ev : {&tr->ev_fwd, &tr->ev_mat[0], &tr->ev_mat[1], &tr->ev_mat[2], &tr->ev_a, &tr->ev_b})
+    ADP_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+  if (const char *o = getenv("ADP_TRAIN_OVERLAP")) tr->overlap = atoi(o) != 0;
+  if (e->prec == ADP_PREC_BF16) {      // operands of the upsampled convs' weight gradients, one buffer per level (written on the side stream)
+    tr->up_x[0].ensure(n * s1 * cp[1] * es); tr->up_x[1].ensure(n * s2 * cp[2] * es); tr->up_x[2].ensure(n * s3 * cp[3] * es);
+  }
   e->fwt_tile.ensure(64 * 4); e->fwt_op.ensure(64 * 4); e->fwt_origin.ensure(64 * 8);
   Acts &a = tr->acts;
   a.d1a = &tr->d1a; a.cat1 = &tr->cat1; a.u1b = &tr->u1b; a.u1c = &tr->u1c; a.pl1 = &tr->pl1;
@@ -349,10 +364,28 @@ template <typename T> struct Bwd {
       add_views_kernel<T><<<ew_grid(e, total, add_views_kernel<T>), 256, 0, e->stream>>>(dst, a, b, nb);
     });
   }
-  void pool_bwd(View<T> xin, View<T> gout, View<T> gin) {
+  // side != 0: enqueue on the side stream (TrainState::side) - the caller orders it with events
+  cudaStream_t sel(bool side) const { return (side && tr->overlap && !e->prof) ? tr->side : e->stream; }
+  void after(cudaEvent_t ev, bool on_side) {        // make the chosen stream wait for an event recorded on the other one
+    if (tr->overlap && !e->prof) ADP_CUDA(cudaStreamWaitEvent(on_side ? tr->side : e->stream, ev, 0));
+  }
+  void mark(cudaEvent_t ev, bool on_side) {
+    if (tr->overlap && !e->prof) ADP_CUDA(cudaEventRecord(ev, on_side ? tr->side : e->stream));
+  }
+  void pool_bwd(View<T> xin, View<T> gout, View<T> gin, bool side = false) {
     const size_t total = (size_t)nb * gout.H * gout.W * (gout.C / 8);
+    cudaStream_t st = sel(side);
     e->launch("maxpool2x2_bwd", 0, (double)total * 8 * sizeof(T) * 13, [&] {
-      maxpool2_bwd_kernel<T><<<ew_grid(e, total, maxpool2_bwd_kernel<T>), 256, 0, e->stream>>>(xin, gout, gin, nb);
+      maxpool2_bwd_kernel<T><<<ew_grid(e, total, maxpool2_bwd_kernel<T>), 256, 0, st>>>(xin, gout, gin, nb);
+    });
+  }
+  // UpSampling2D(x) written out once per step (operand of the upsampled conv's weight gradient)
+  void materialise(int level, View<T> xin, int cin_pad) {
+    View<T> xs = V(tr->up_x[level], xin.H * 2, cin_pad, 0, cin_pad);
+    const size_t total = (size_t)nb * xs.H * xs.W * (xs.C / 8);
+    cudaStream_t st = sel(true);
+    e->launch("upsample2x2_materialise", 0, (double)total * 16 * 1.25, [&] {
+      upsample2_kernel<T><<<ew_grid(e, total / 4, upsample2_kernel<T>), 256, 0, st>>>(xin, xs, nb);
     });
   }
 
@@ -367,12 +400,11 @@ template <typename T> struct Bwd {
     if (e->prec == ADP_PREC_BF16 && !e->wgrad_simt) {
       if constexpr (sizeof(T) == 2) {
         View<T> xs = xin;
-        if (L.up) {     // materialise UpSampling2D(x) once: the weight gradient is then a plain 9-tap reduction at high resolution
-          xs = V(tr->g_hi, dz.H, L.cin_pad, 0, L.cin_pad);
-          const size_t total = (size_t)nb * xs.H * xs.W * (xs.C / 8);
-          e->launch("upsample2x2_materialise", 0, (double)total * 16 * 1.25, [&] {
-            upsample2_kernel<T><<<ew_grid(e, total / 4, upsample2_kernel<T>), 256, 0, e->stream>>>(xin, xs, nb);
-          });
+        if (L.up) {     // UpSampling2D(x), materialised on the side stream at the start of the backward pass: the weight gradient
+                        // is then a plain 9-tap reduction at high resolution
+          const int level = dz.H == tr->S ? 0 : (dz.H == tr->S / 2 ? 1 : 2);
+          xs = V(tr->up_x[level], dz.H, L.cin_pad, 0, L.cin_pad);
+          after(tr->ev_mat[level], false);
         }
         WgradTcParams p = TL.wg;
         p.nb = nb; p.H = dz.H; p.W = dz.W; p.dW = TL.gw.as<float>(); p.db = TL.gb.as<float>();
@@ -407,7 +439,10 @@ template <typename T> struct Bwd {
   //   gin = (conv(dz, flipped W) [2x2-summed for an upsampled conv] + resid) * [mask > 0] * scale
   // mask = the forward tensor gin is the gradient of (ReLU', and the dropout mask when scale = 1/keep): the written
   // tensor is dL/d(pre-activation) of the producing layer.  On the tcgen05 path both live in the conv epilogue.
-  void dgrad(size_t li, View<T> dz, View<T> gin, const View<T> *mask = nullptr, float scale = 1.f, const View<T> *resid = nullptr) {
+  // up_on_side: the 2x2 reduction of an upsampled conv's data gradient goes to the side stream (the caller overlaps it with
+  // the same layer's weight gradient and waits for ev_b before the reduced gradient is read)
+  void dgrad(size_t li, View<T> dz, View<T> gin, const View<T> *mask = nullptr, float scale = 1.f, const View<T> *resid = nullptr,
+             bool up_on_side = false) {
     ConvLayer &L = e->layers[li];
     TrainLayer &TL = tr->tl[li];
     View<T> out = gin;
@@ -434,9 +469,12 @@ template <typename T> struct Bwd {
     if (L.up) {
       const size_t total = (size_t)nb * gin.H * gin.W * (gin.C / 8);
       View<T> none{}; none.p = nullptr;
+      if (up_on_side) { mark(tr->ev_a, false); after(tr->ev_a, true); }
+      cudaStream_t st = sel(up_on_side);
       e->launch("upsample2x2_bwd", 0, (double)total * 8 * sizeof(T) * (mask ? 6 : 5), [&] {
-        upsample2_bwd_kernel<T><<<ew_grid(e, total, upsample2_bwd_kernel<T>), 256, 0, e->stream>>>(out, gin, nb, mask ? *mask : none, scale, resid ? *resid : none);
+        upsample2_bwd_kernel<T><<<ew_grid(e, total, upsample2_bwd_kernel<T>), 256, 0, st>>>(out, gin, nb, mask ? *mask : none, scale, resid ? *resid : none);
       });
+      if (up_on_side) mark(tr->ev_b, true);
     } else if (!fused) {
       if (resid) add(gin, gin, *resid);
       if (mask) relu_mask(gin, *mask, scale);
@@ -458,6 +496,15 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
   const float inv_keep = 1.f / tr->keep;
   auto li = [&](const char *n) { return layer_index(e, n); };
   auto bucket_done = [&](int b) { ADP_CUDA(cudaEventRecord(tr->buckets[b].ev, e->stream)); };
+  const bool tcw = e->prec == ADP_PREC_BF16 && !e->wgrad_simt && sizeof(T) == 2;
+  if (tcw) {
+    // operands of the three upsampled convs' weight gradients: forward activations only, so they are written on the side
+    // stream while the head / up1 gradients run (ev_fwd orders them behind everything enqueued so far)
+    B.mark(tr->ev_fwd, false); B.after(tr->ev_fwd, true);
+    B.materialise(0, B.V(tr->u2c, S2, cp[1], 0, cp[1]), cp[1]); B.mark(tr->ev_mat[0], true);
+    B.materialise(1, B.V(tr->u3c, S3, cp[2], 0, cp[2]), cp[2]); B.mark(tr->ev_mat[1], true);
+    B.materialise(2, B.V(tr->ts, S4, cp[3], 0, cp[3]), cp[3]); B.mark(tr->ev_mat[2], true);
+  }
 
   // head: dL/dp -> dL/d(pre-activation of up1_conv3) (ReLU' and dropout folded in), head weight gradients
   {
@@ -530,13 +577,16 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
     if (l < 2) {       // input of up{l}_conv1 = post-dropout up{l+1}_conv3 at half resolution
       const Lvl &n = lv[l + 1];
       auto src = B.V(*n.uc, n.H, n.c, 0, n.c), g_src = B.V(*n.g_uc, n.H, n.c, 0, n.c);
-      B.wgrad(li(q.c1), src, g_cat_up);
       auto aux_r = B.V(tr->resid[1 - l], n.H, n.c, 0, n.c);      // l = 0 feeds up2 (aux_out2), l = 1 feeds up3 (aux_out1)
-      B.dgrad(li(q.c1), g_cat_up, g_src, &src, inv_keep, e->deep_sup ? &aux_r : nullptr);
+      // data gradient first: its 2x2 reduction (HBM-bound) runs on the side stream under the weight gradient (tensor-bound)
+      B.dgrad(li(q.c1), g_cat_up, g_src, &src, inv_keep, e->deep_sup ? &aux_r : nullptr, true);
+      B.wgrad(li(q.c1), src, g_cat_up);
+      B.after(tr->ev_b, false);
     } else {           // up3_conv1 reads the Add of the six bottleneck tensors (no activation of its own)
       auto ts = B.V(tr->ts, S4, cp[3], 0, cp[3]), g_ts = B.V(tr->g_ts, S4, cp[3], 0, cp[3]);
+      B.dgrad(li(q.c1), g_cat_up, g_ts, nullptr, 1.f, nullptr, true);
       B.wgrad(li(q.c1), ts, g_cat_up);
-      B.dgrad(li(q.c1), g_cat_up, g_ts);
+      B.after(tr->ev_b, false);
     }
   }
   bucket_done(0);
@@ -553,6 +603,18 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
     cur ^= 1;
     if (i == 3) bucket_done(1);
   }
+  // From here on every max-pool backward (HBM-bound) runs on the side stream under a weight gradient of the main stream:
+  // the data gradient that feeds it is issued first, the weight gradient of the same layer (independent of it) second.
+  auto pool_on_side = [&](int l) {
+    const Lvl &q = lv[l];
+    B.mark(tr->ev_a, false); B.after(tr->ev_a, true);
+    B.pool_bwd(B.V(*q.cat, q.H, 2 * q.c, 0, q.c), B.V(*q.g_pl, q.H / 2, q.c, 0, q.c), B.V(*q.g_cat, q.H, 2 * q.c, 0, q.c), true);
+    B.mark(tr->ev_b, true);
+  };
+  if (!freeze_encoder) {
+    B.dgrad(li("dilate1"), VT(tr->gt[cur]), B.V(*lv[2].g_pl, lv[2].H / 2, lv[2].c, 0, lv[2].c));
+    pool_on_side(2);
+  }
   B.wgrad(li("dilate1"), B.V(tr->pl3, S4, cp[2], 0, cp[2]), VT(tr->gt[cur]));
   bucket_done(2);
   if (freeze_encoder) { bucket_done(3); return; }     // phase 1: nothing upstream is trainable (train_adipose_unet_v3.py:760-769)
@@ -560,19 +622,15 @@ template <typename T> void backward_t(adp_engine *e, bool freeze_encoder) {
   for (int l = 2; l >= 0; --l) {
     const Lvl &q = lv[l];
     const int H = q.H, c = q.c;
-    auto g_pl = B.V(*q.g_pl, H / 2, c, 0, c);
-    auto skip = B.V(*q.cat, H, 2 * c, 0, c), g_skip = B.V(*q.g_cat, H, 2 * c, 0, c);
+    auto g_skip = B.V(*q.g_cat, H, 2 * c, 0, c);
     auto da = B.V(*q.da, H, c, 0, c), g_da = B.V(*q.g_da, H, c, 0, c);
-    if (l == 2) B.dgrad(li("dilate1"), VT(tr->gt[cur]), g_pl);
-    else {
-      const Lvl &n = lv[l + 1];
-      B.dgrad(li(n.d1), B.V(*n.g_da, n.H, n.c, 0, n.c), g_pl);
-    }
-    B.pool_bwd(skip, g_pl, g_skip);
+    B.after(tr->ev_b, false);                          // max-pool backward of this level has written g_skip
     B.wgrad(li(q.d2), da, g_skip);
     B.dgrad(li(q.d2), g_skip, g_da, &da, 1.f);
     if (l > 0) {     // down{l}_conv1 reads the pooled output of the level above (down1_conv1: first-layer kernel below)
       const Lvl &u = lv[l - 1];
+      B.dgrad(li(q.d1), g_da, B.V(*u.g_pl, u.H / 2, u.c, 0, u.c));
+      pool_on_side(l - 1);
       B.wgrad(li(q.d1), B.V(*u.pl, H, u.c, 0, u.c), g_da);
     }
   }
