@@ -85,6 +85,7 @@ SIGNATURES = {
     "adp_train_sums_buffer": (_I, [_P, C.POINTER(_P), C.POINTER(_I)]),
     "adp_train_sums_read": (_I, [_P, _P, _I]),
     "adp_train_grad_buffer": (_I, [_P, C.POINTER(_P), C.POINTER(_I64)]),
+    "adp_train_accuracy_read": (_I, [_P, C.POINTER(C.c_double)]),
     "adp_train_grad_buckets": (_I, [_P, C.POINTER(_I64), C.POINTER(_I64), _I]),
     "adp_train_bucket_wait": (_I, [_P, _I, _P]),
     "adp_train_join": (_I, [_P, _P]),

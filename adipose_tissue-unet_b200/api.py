@@ -263,6 +263,12 @@ class Engine:
         _lib.check(self.lib.adp_train_grad_buffer(self.h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
 
+    def train_accuracy_read(self) -> Tuple[float, float]:
+        """(matching pixels, pixels) of Keras' binary_accuracy for the last backward's batch (needs set_option('train_accuracy', 1))."""
+        out = (C.c_double * 2)()
+        _lib.check(self.lib.adp_train_accuracy_read(self.h, out))
+        return float(out[0]), float(out[1])
+
     def train_grad_buckets(self) -> List[Tuple[int, int]]:
         """[lo, hi) element ranges of the flat gradient in the order the backward pass completes them."""
         lo = (C.c_int64 * 8)(); hi = (C.c_int64 * 8)()

@@ -9,8 +9,10 @@ schedule (:393-404), best-checkpoint bookkeeping, EMA of the weights (:407-505) 
 Recipe coverage: deep supervision (--use-deep-supervision, --ds-weight-*: aux_out1 / aux_out2
 heads, adp_train_set_deep_supervision), hard-example mining (--use-hard-mining, --hard-example-ratio) and asymmetric
 label smoothing (--use-label-smoothing, --label-smooth-epsilon-*; adp_train_set_loss) all run on the device, i.e. the
-reference's default recipe.  Still host-side / not reproduced: the intensity and elastic parts of the augmentation
-levels (geometric D4 part only) and ReduceLROnPlateau of --no-cosine-schedule (constant rate instead)."""
+reference's default recipe.  --no-cosine-schedule runs Keras' ReduceLROnPlateau (factor 0.5, patience 5, :1303-1313) on
+the monitored validation Dice.  phase{1,2}_training.log has CSVLogger's columns for the reference's compile() (epoch + the
+sorted log keys: loss, dice_coef, binary_accuracy and their val_ twins; main_out_/aux_out*_ names with deep supervision).
+Still host-side / not reproduced: the intensity and elastic parts of the augmentation levels (geometric D4 part only)."""
 from __future__ import annotations
 
 import argparse
@@ -131,15 +133,67 @@ def compute_mean_std(paths):
     return float(vals.mean()), float(vals.std() + 1e-10)
 
 
-def validate(engine, ds: TileDataset, batch: int):
-    """val_loss / val_dice_coef over the validation tiles (Keras averages per-batch values)."""
-    losses, dices = [], []
-    rng = np.random.RandomState(0)
-    for x, y in batches(ds, batch, rng, False, 0, 1, False):
-        p = engine.predict(x, 0.0, 1.0 - 1e-10)                    # x is already normalised: (x - 0) / (1 - 1e-10 + 1e-10)
-        m = engine.loss_metrics(p, y)
-        losses.append(m["loss"]); dices.append(m["dice_coef"])
-    return float(np.mean(losses)), float(np.mean(dices))
+def validate(engine, ds: TileDataset, batch: int, deep_supervision: bool = False):
+    """The validation pass of net.fit (train_adipose_unet_v3.py:1316-1324): the training graph with Dropout inactive
+    (engine option train_eval_mode), every output's loss, dice_coef and binary_accuracy of main_out.  Keras semantics:
+    losses and dice_coef are means over the batches, binary_accuracy is matching pixels / pixels over the whole pass."""
+    logs = {}
+    acc = [0.0, 0.0]
+    engine.set_option("train_eval_mode", 1)
+    try:
+        rng = np.random.RandomState(0)
+        for x, y in batches(ds, batch, rng, False, 0, 1, False):
+            m = engine.train_loss(engine.train_forward(x, y))
+            a = engine.train_accuracy_read()
+            acc[0] += a[0]; acc[1] += a[1]
+            for k, v in m.items():
+                logs.setdefault(k, []).append(v)
+    finally:
+        engine.set_option("train_eval_mode", 0)
+    out = {k: float(np.mean(v)) for k, v in logs.items()}
+    out["binary_accuracy"] = acc[0] / max(acc[1], 1.0)
+    return out
+
+
+def keras_logs(train: dict, val: dict, deep_supervision: bool) -> dict:
+    """The `logs` dict Keras hands CSVLogger at epoch end for the reference's compile() (train_adipose_unet_v3.py:858-879):
+    single output: loss, dice_coef, binary_accuracy (+ val_*); deep supervision: loss, {main_out,aux_out1,aux_out2}_loss,
+    main_out_dice_coef, main_out_binary_accuracy (+ val_*).  No learning-rate entry: CSVLogger precedes the schedule callback
+    in the callback list (:1270-1314), so 'lr' is not yet in `logs` when it fixes its columns."""
+    def one(d):
+        if not deep_supervision:
+            return {"loss": d["loss"], "dice_coef": d["dice_coef"], "binary_accuracy": d["binary_accuracy"]}
+        return {"loss": d["loss"], "main_out_loss": d["main_out_loss"], "aux_out1_loss": d["aux_out1_loss"], "aux_out2_loss": d["aux_out2_loss"],
+                "main_out_dice_coef": d["dice_coef"], "main_out_binary_accuracy": d["binary_accuracy"]}
+    logs = one(train)
+    if val:
+        logs.update({"val_" + k: v for k, v in one(val).items()})
+    return logs
+
+
+class ReduceLROnPlateau:
+    """keras.callbacks.ReduceLROnPlateau(monitor, mode='max', factor=0.5, patience=5, min_lr=1e-7) as the reference's
+    --no-cosine-schedule branch configures it (train_adipose_unet_v3.py:1303-1313, 1398-1408); Keras defaults
+    min_delta=1e-4, cooldown=0."""
+
+    def __init__(self, lr: float, factor: float = 0.5, patience: int = 5, min_lr: float = 1e-7, min_delta: float = 1e-4, cooldown: int = 0):
+        self.lr, self.factor, self.patience, self.min_lr, self.min_delta, self.cooldown = lr, factor, patience, min_lr, min_delta, cooldown
+        self.best, self.wait, self.cooldown_counter = -np.inf, 0, 0
+
+    def on_epoch_end(self, current: float) -> float:
+        if self.cooldown_counter > 0:
+            self.cooldown_counter -= 1
+            self.wait = 0
+        if current > self.best + self.min_delta:
+            self.best, self.wait = current, 0
+        elif self.cooldown_counter <= 0:
+            self.wait += 1
+            if self.wait >= self.patience:
+                if self.lr > np.float32(self.min_lr):
+                    self.lr = max(self.lr * self.factor, self.min_lr)
+                    self.cooldown_counter = self.cooldown
+                    self.wait = 0
+        return self.lr
 
 
 def main(argv=None) -> int:
@@ -212,6 +266,7 @@ def main(argv=None) -> int:
     if not args.use_deep_supervision:
         w0 = {k: v for k, v in w0.items() if not k.startswith("aux_out")}
     engine.set_weights(w0)
+    engine.set_option("train_accuracy", 1)            # compile(metrics=[dice_coef, 'binary_accuracy']), :850-853, 877-878
     if args.use_deep_supervision:
         engine.train_set_deep_supervision(True, args.ds_weight_main, args.ds_weight_aux1, args.ds_weight_aux2)
     engine.train_set_loss(args.hard_example_ratio if args.use_hard_mining else 1.0,
@@ -236,25 +291,39 @@ def main(argv=None) -> int:
         # EMACallback (:410-505): one instance per phase (phase 1: decay 0.999, never saved; phase 2: --ema-decay, best snapshot
         # by the monitored validation Dice), updated at EPOCH end from the current weights, initialised at the first epoch end
         ema, ema_best, ema_saved = None, -np.inf, False
-        logf = None
+        logf, w, keys = None, None, None
         if rank == 0:
             logf = open(ckpt / f"phase{phase}_training.log", "w", newline="")
-            w = csv.writer(logf); w.writerow(["epoch", "dice_coef", "loss", "lr", "val_dice_coef", "val_loss"])
+            w = csv.writer(logf)
+        plateau = None if args.use_cosine_schedule else ReduceLROnPlateau(max_lr, min_lr=min_lr)      # legacy mode, :1303-1313
+        ds_on = bool(args.use_deep_supervision)
         for epoch in range(epochs):
-            lr = T.cosine_warmup_lr(epoch, max_lr, min_lr, warm, epochs) if args.use_cosine_schedule else max_lr
-            t0, losses, dices = time.time(), [], []
+            lr = T.cosine_warmup_lr(epoch, max_lr, min_lr, warm, epochs) if args.use_cosine_schedule else plateau.lr
+            t0, steps_logs, acc = time.time(), {}, [0.0, 0.0]
             # the next batch is decoded / augmented while the device runs this one (the reference's dataset.prefetch, :620)
             for step, (x, y) in enumerate(C.prefetch(batches(train_ds, args.batch_size, rng, args.augmentation_level != "none", rank, world, True, shuffle_rng))):
                 if step >= steps_per_epoch:
                     break
                 out = trainer.step(x, y, lr)
-                losses.append(out["loss"]); dices.append(out["dice_coef"])
-            vloss, vdice = validate(engine, val_ds, args.batch_size) if len(val_ds) else (float("nan"), float("nan"))
-            log(f"Epoch {epoch + 1}/{epochs} - {time.time() - t0:.0f}s - loss: {np.mean(losses):.4f} - dice_coef: {np.mean(dices):.4f} "
-                f"- val_loss: {vloss:.4f} - val_dice_coef: {vdice:.4f} - lr: {lr:.2e}")
+                for k, v in out.items():
+                    steps_logs.setdefault(k, []).append(v)
+                a = engine.train_accuracy_read()
+                acc[0] += a[0]; acc[1] += a[1]
+            tlog = {k: float(np.mean(v)) for k, v in steps_logs.items()}
+            tlog["binary_accuracy"] = acc[0] / max(acc[1], 1.0)
+            vlog = validate(engine, val_ds, args.batch_size, ds_on) if len(val_ds) else {}
+            logs = keras_logs(tlog, vlog, ds_on)
+            vloss, vdice = vlog.get("loss", float("nan")), vlog.get("dice_coef", float("nan"))
+            log(f"Epoch {epoch + 1}/{epochs} - {time.time() - t0:.0f}s - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()) + f" - lr: {lr:.2e}")
+            if plateau is not None:
+                # monitor = val_main_out_dice_coef / val_dice_coef (:1268), the training value when there is no validation split
+                plateau.on_epoch_end(vdice if np.isfinite(vdice) else tlog["dice_coef"])
             if rank == 0:
-                w.writerow([epoch, np.mean(dices), np.mean(losses), lr, vdice, vloss]); logf.flush()
-                score = vdice if np.isfinite(vdice) else float(np.mean(dices))
+                if keys is None:                      # CSVLogger: 'epoch' + the sorted keys of the first epoch's logs
+                    keys = sorted(logs)
+                    w.writerow(["epoch"] + keys)
+                w.writerow([epoch] + [logs.get(k, "NA") for k in keys]); logf.flush()
+                score = vdice if np.isfinite(vdice) else tlog["dice_coef"]
                 if score > best_phase:
                     best_phase, since_best = score, 0
                     save_weights_file(str(ckpt / f"phase{phase}_best.weights.h5"), engine.get_weights())

@@ -225,8 +225,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     sbias[i] = p.bias[p.var[v].bias_off + (i - v * p.N)];
   }
   if constexpr (EPI == EPI_HEAD) {
-    for (int i = threadIdx.x; i < 2 * p.N; i += kTcThreads) shead[i] = p.head_w[i];
-    if (threadIdx.x < 2) shead[2 * p.N + threadIdx.x] = p.head_b[threadIdx.x];
+    // softmax(z)[1] = 1 / (1 + exp(z0 - z1)): only the difference of the two 1x1 filters is needed, so the epilogue keeps
+    // w0 - w1 (and b0 - b1) and reads it with 128-bit shared loads - the scalar form issued 2 x N 32-bit loads per pixel row,
+    // 1.7 k shared-memory wavefronts per item that compete with the MMA operand fetch on the same port (ncu: 37 % of the
+    // kernel's shared wavefronts were epilogue loads)
+    for (int i = threadIdx.x; i < p.N; i += kTcThreads) shead[i] = p.head_w[i] - p.head_w[p.N + i];
+    if (threadIdx.x == 0) shead[p.N] = p.head_b[0] - p.head_b[1];
   }
 
   if (warp == 0 && lane == 0) {
@@ -584,22 +588,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       } else if constexpr (EPI == EPI_HEAD) {
         // rows split between the two warps of a quarter so that one thread sees all channels of its pixel
         for (int row = half; row < T; row += 2) {
-          float z0 = 0.f, z1 = 0.f;
+          float zd = 0.f;                                       // z0 - z1
           tmem_pipeline(t0, row * NU, 1, row * NU + NU, [&](int u, const uint32_t (&r)[16]) {
             const int cu = u - row * NU;
             float f[16];
             bias_relu16(r, sb + cu * 16, p.relu, f);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              z0 = fmaf(f[i], shead[cu * 16 + i], z0);
-              z1 = fmaf(f[i], shead[p.N + cu * 16 + i], z1);
+            for (int q = 0; q < 4; ++q) {
+              const float4 w = *reinterpret_cast<const float4 *>(shead + cu * 16 + 4 * q);
+              zd = fmaf(f[4 * q + 0], w.x, zd); zd = fmaf(f[4 * q + 1], w.y, zd);
+              zd = fmaf(f[4 * q + 2], w.z, zd); zd = fmaf(f[4 * q + 3], w.w, zd);
             }
           });
           const int y = ty * T + row;
-          if (y < p.Hin && x < p.Win && !tc_dbg(p, 1)) {
-            z0 += shead[2 * p.N]; z1 += shead[2 * p.N + 1];
-            p.prob[((size_t)n * p.Hout + y) * p.Wout + x] = 1.f / (1.f + expf(z0 - z1));
-          }
+          if (y < p.Hin && x < p.Win && !tc_dbg(p, 1))
+            p.prob[((size_t)n * p.Hout + y) * p.Wout + x] = 1.f / (1.f + expf(zd + shead[p.N]));
         }
       } else {
         // EPI_POOL: unit = (row pair k, 16 channels); both rows are stored, their max is reduced with

@@ -201,6 +201,8 @@ struct adp_engine {
   LossRecipe loss;                           // adp_train_set_loss: hard-example mining / label smoothing of the training loss
   bool deep_sup = false;                     // adp_train_set_deep_supervision: aux_out1 / aux_out2 heads while training
   float ds_w[3] = {1.0f, 0.4f, 0.3f};        // loss weights main / aux1 / aux2 (train_adipose_unet_v3.py:858-872)
+  bool train_eval_mode = false;              // adp_set_option("train_eval_mode"): adp_train_forward without Dropout (validation pass)
+  bool train_accuracy = false;               // adp_set_option("train_accuracy"): count Keras' binary_accuracy in every backward
   bool wgrad_simt = false, dgrad_simt = false;   // bf16 training: CUDA-core cross-check of the tcgen05 backward kernels
 
   // Grid of a grid-stride elementwise kernel: exactly one resident wave (blocks per SM from the occupancy calculator x SMs),
@@ -1095,6 +1097,8 @@ int adp_set_option(adp_engine *e, const char *key, int value) {
   else if (k == "fuse_pool") e->fuse_pool = value != 0;
   else if (k == "wgrad_simt") e->wgrad_simt = value != 0;
   else if (k == "dgrad_simt") e->dgrad_simt = value != 0;
+  else if (k == "train_accuracy") e->train_accuracy = value != 0;
+  else if (k == "train_eval_mode") e->train_eval_mode = value != 0;
   else if (k == "debug") e->dbg = ADP_TC_DEBUG_BUILD ? value : 0;
   else if (k == "kys") { e->kys = value != 0; e->packed = false; }   // ky-stacked MMA issue (conv_tc.cuh); re-plans on next use
   else throw Error(ADP_EINVAL, "unknown option " + k);
@@ -1919,6 +1923,22 @@ int adp_train_grad_buffer(adp_engine *e, float **dev_ptr, int64_t *count) {
   if (!e->tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
   *dev_ptr = e->tr->grad.as<float>();
   *count = (int64_t)e->tr->P;
+  ADP_CATCH
+}
+
+int adp_train_accuracy_read(adp_engine *e, double out[2]) {
+  ADP_TRY
+  ADP_REQUIRE(e && out, "null argument");
+  if (!e->tr) throw Error(ADP_ESTATE, "adp_train_begin not called");
+  if (!e->train_accuracy || !(e->tr->have_forward || e->tr->sums_mirrored)) throw Error(ADP_ESTATE, "set option train_accuracy and run adp_train_forward first");
+  ADP_CUDA(cudaSetDevice(e->device));
+  if (e->tr->sums_mirrored) {        // after a backward: wait for the mirror only
+    ADP_CUDA(cudaEventSynchronize(e->tr->ev_sums));
+    out[0] = e->tr->pinned_sums[24]; out[1] = e->tr->pinned_sums[25];
+  } else {                           // forward only (validation pass)
+    ADP_CUDA(cudaMemcpyAsync(out, e->tr->dsums.as<double>() + 24, 16, cudaMemcpyDeviceToHost, e->stream));
+    ADP_CUDA(cudaStreamSynchronize(e->stream));
+  }
   ADP_CATCH
 }
 

@@ -391,6 +391,17 @@ __global__ void loss_finish_kernel(double *__restrict__ sums, const double *__re
   }
 }
 
+// Keras' 'binary_accuracy' metric of compile_model (train_adipose_unet_v3.py:877-878): mean over all pixels of
+// equal(y_true, cast(y_pred > 0.5)); out[0] += number of matching pixels (float64), out[1] = n is written by the host side.
+__global__ void __launch_bounds__(256)
+binary_accuracy_kernel(const float *__restrict__ p, const float *__restrict__ y, size_t n, double *__restrict__ out) {
+  unsigned c = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    c += (y[i] == (p[i] > 0.5f ? 1.0f : 0.0f));
+  c = warp_sum_u(c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (double)c);
+}
+
 __global__ void __launch_bounds__(256)
 loss_grad_kernel(const float *__restrict__ p, const float *__restrict__ y, size_t n, float ys_a, float ys_b,
                  const double *__restrict__ sums, const float *__restrict__ row_w /* or null */, int W,

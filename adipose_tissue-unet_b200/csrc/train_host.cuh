@@ -68,6 +68,7 @@ struct TrainState {
   // materialisation, upsample / max-pool backward) run under tensor-bound weight-gradient kernels of the main stream
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fwd = nullptr, ev_mat[3] = {nullptr, nullptr, nullptr}, ev_a = nullptr, ev_b = nullptr;
+  DevBuf wg_scratch, wb_scratch;   // per-CTA partial sums of the weight-gradient GEMM (wgrad_tc.cuh), reduced in a fixed order
   DevBuf up_x[3];             // UpSampling2D(x) of the three upsampled convs' inputs (weight-gradient operands)
   bool overlap = true;
   ~TrainState() {
@@ -195,8 +196,8 @@ void train_alloc(adp_engine *e, int nb, int S, float dropout_rate, uint64_t seed
   tr->g_hi.ensure(n * std::max({s1 * cp[1], s2 * cp[2], s3 * cp[3]}) * es);
   tr->prob.ensure(n * s1 * 4); tr->x.ensure(n * s1 * 4); tr->y.ensure(n * s1 * 4); tr->dldp.ensure(n * s1 * 4);
   tr->zeros.ensure(4096); ADP_CUDA(cudaMemset(tr->zeros.p, 0, 4096));
-  tr->dsums.ensure(24 * 8); ADP_CUDA(cudaMemset(tr->dsums.p, 0, 24 * 8));
-  ADP_CUDA(cudaMallocHost(&tr->pinned_sums, 24 * 8));
+  tr->dsums.ensure(32 * 8); ADP_CUDA(cudaMemset(tr->dsums.p, 0, 32 * 8));     // 24 loss sums + {matching pixels, pixels} of binary_accuracy
+  ADP_CUDA(cudaMallocHost(&tr->pinned_sums, 32 * 8));
   ADP_CUDA(cudaEventCreateWithFlags(&tr->ev_sums, cudaEventDisableTiming));
   ADP_CUDA(cudaEventCreateWithFlags(&tr->ev_join, cudaEventDisableTiming));
   ADP_CUDA(cudaStreamCreateWithFlags(&tr->side, cudaStreamNonBlocking));
@@ -307,7 +308,8 @@ void train_forward(adp_engine *e, const float *x, const float *y, int n, const u
   for (int i = 0; i < n; ++i) { fw.tile[i] = i; fw.op[i] = 0; }
   FirstConvSrc src{};
   src.f32 = tr->x.as<float>();
-  const bool dropping = masks || tr->keep < 1.f;
+  // eval mode (adp_set_option "train_eval_mode"): the validation pass of net.fit - same graph and losses, Dropout inactive
+  const bool dropping = (masks || tr->keep < 1.f) && !e->train_eval_mode;
   DropSpec none;   // keep == 1, no masks: the dropout kernels are skipped but the fused head is still off
   if (e->prec == ADP_PREC_FP32) forward_t<float>(e, tr->acts, S, src, fw, n, 0.f, 1.f, nullptr, dropping ? &d : &none);
   else forward_t<__nv_bfloat16>(e, tr->acts, S, src, fw, n, 0.f, 1.f, nullptr, dropping ? &d : &none);
@@ -336,6 +338,13 @@ void train_forward(adp_engine *e, const float *x, const float *y, int n, const u
       });
       loss_forward(e, tr->ls_aux[a], ra, tr->aux_full[a].as<float>(), tr->y.as<float>(), n, (size_t)S * S, S, ds + 8 * (a + 1));
     }
+  }
+  if (e->train_accuracy) {      // Keras' binary_accuracy of main_out on this rank's batch (mirrored to the host with the sums)
+    const double init[2] = {0.0, (double)npx};
+    ADP_CUDA(cudaMemcpyAsync(ds + 24, init, 16, cudaMemcpyHostToDevice, e->stream));
+    e->launch("binary_accuracy", 0, (double)npx * 8, [&] {
+      binary_accuracy_kernel<<<e->wave_grid(binary_accuracy_kernel, cdiv64(npx, 256 * 4)), 256, 0, e->stream>>>(tr->prob.as<float>(), tr->y.as<float>(), npx, ds + 24);
+    });
   }
   if (sums) {
     ADP_CUDA(cudaMemcpyAsync(sums, ds, (size_t)(e->deep_sup ? 24 : 8) * 8, cudaMemcpyDeviceToHost, e->stream));
@@ -394,8 +403,11 @@ template <typename T> struct Bwd {
     ConvLayer &L = e->layers[li];
     TrainLayer &TL = tr->tl[li];
     const size_t np = (size_t)9 * L.cin_pad * L.cout_pad;
-    ADP_CUDA(cudaMemsetAsync(TL.gw.p, 0, np * 4, e->stream));
-    ADP_CUDA(cudaMemsetAsync(TL.gb.p, 0, (size_t)L.cout_pad * 4, e->stream));
+    const bool tc_path = e->prec == ADP_PREC_BF16 && !e->wgrad_simt && sizeof(T) == 2;
+    if (!tc_path) {      // the CUDA-core kernel accumulates into the gradient; the tcgen05 path writes slots and reduces
+      ADP_CUDA(cudaMemsetAsync(TL.gw.p, 0, np * 4, e->stream));
+      ADP_CUDA(cudaMemsetAsync(TL.gb.p, 0, (size_t)L.cout_pad * 4, e->stream));
+    }
     const double fl = conv_flops(L, dz.H, dz.W, nb);
     if (e->prec == ADP_PREC_BF16 && !e->wgrad_simt) {
       if constexpr (sizeof(T) == 2) {
@@ -407,13 +419,20 @@ template <typename T> struct Bwd {
           after(tr->ev_mat[level], false);
         }
         WgradTcParams p = TL.wg;
-        p.nb = nb; p.H = dz.H; p.W = dz.W; p.dW = TL.gw.as<float>(); p.db = TL.gb.as<float>();
+        // deterministic accumulation: every CTA writes the partial sums of its unit range into its own slot, then the slots
+        // are added in a fixed order (wgrad_reduce_kernel) - the gradient is bit-reproducible from run to run
+        tr->wg_scratch.ensure((size_t)p.ctas_per_combo * np * 4); tr->wb_scratch.ensure((size_t)p.ctas_per_combo * L.cout_pad * 4);
+        p.nb = nb; p.H = dz.H; p.W = dz.W; p.dW = tr->wg_scratch.as<float>(); p.db = tr->wb_scratch.as<float>();
         const CUtensorMap &tmx = tmap_for(e, xs.p, xs.H, xs.W, xs.cgs, xs.cg0, xs.C, nb, p.PW / 8, p.cga_box, 1);
         const CUtensorMap &tmz = tmap_for(e, dz.p, dz.H, dz.W, dz.cgs, dz.cg0, dz.C, nb, 16, p.co_chunk / 8, 1);
         const int grid = p.n_ci_blk * p.n_co_chunk * p.ctas_per_combo;
         const double by = (double)nb * dz.H * dz.W * (L.cin_pad + L.cout_pad) * 2.0;
         e->launch(("conv_wgrad_tcgen05/" + L.name).c_str(), fl, by, [&] {
           wgrad_tc_kernel<<<grid, kWgThreads, wgrad_smem_bytes(p), e->stream>>>(tmx, tmz, p);
+        });
+        e->launch("wgrad_reduce", 0, (double)(p.ctas_per_combo + 1) * np * 4, [&] {
+          wgrad_reduce_kernel<<<ew_grid(e, np / 4 + L.cout_pad, wgrad_reduce_kernel), 256, 0, e->stream>>>(
+              tr->wg_scratch.as<float>(), tr->wb_scratch.as<float>(), p.ctas_per_combo, np, L.cout_pad, TL.gw.as<float>(), TL.gb.as<float>());
         });
       }
     } else {
@@ -671,7 +690,7 @@ void train_backward(adp_engine *e, const double *sums /* 8 per output (host), or
   if (!tr || !tr->have_forward) throw Error(ADP_ESTATE, "adp_train_forward must run first");
   const size_t sbytes = (size_t)(e->deep_sup ? 24 : 8) * 8;
   if (sums) ADP_CUDA(cudaMemcpyAsync(tr->dsums.p, sums, sbytes, cudaMemcpyHostToDevice, e->stream));
-  ADP_CUDA(cudaMemcpyAsync(tr->pinned_sums, tr->dsums.p, sbytes, cudaMemcpyDeviceToHost, e->stream));
+  ADP_CUDA(cudaMemcpyAsync(tr->pinned_sums, tr->dsums.p, 32 * 8, cudaMemcpyDeviceToHost, e->stream));
   ADP_CUDA(cudaEventRecord(tr->ev_sums, e->stream));
   tr->sums_mirrored = true;
   loss_backward(e, tr->ls, e->loss, tr->prob.as<float>(), tr->y.as<float>(), tr->nb, (size_t)tr->S * tr->S, tr->S, tr->dsums.as<double>(),

@@ -18,8 +18,10 @@
 // operand is filled once with bf16 ones, so accumulator row 120 of the centre tap is sum_pixels dZ = db.
 //
 // A CTA owns one (input-channel block, output-channel chunk) pair and a contiguous range of
-// (image, row, 128-pixel strip) units; it accumulates its whole range in TMEM and then adds the
-// 128 x 432 partial sums into the padded fp32 gradient dW[9][cin_pad][cout_pad] with red.global.add.
+// (image, row, 128-pixel strip) units; it accumulates its whole range in TMEM and then writes the
+// 128 x 432 partial sums into ITS OWN slot of a scratch buffer [ctas_per_combo][9][cin_pad][cout_pad]; wgrad_reduce_kernel adds
+// the slots in a fixed order.  (The first version added the partials into dW with red.global.add.f32: the order of those
+// float additions changed from run to run, so the gradient was not reproducible.)
 //
 // Warp roles (192 threads): w0 TMA producer, w1 MMA issuer + TMEM allocator, w2-5 epilogue.
 #pragma once
@@ -38,15 +40,12 @@ struct WgradTcParams {
   int PW, margin8;               // X plane width in pixels (128 + 2*margin), halo in 8-pixel groups
   int S;                         // pipeline depth
   uint32_t a_bytes, b_row_bytes, stage_stride;
-  float *dW;                     // [9][cin_pad][cout_pad] fp32, accumulated into
-  float *db;                     // [cout_pad] fp32, accumulated into
+  float *dW;                     // scratch [ctas_per_combo][9][cin_pad][cout_pad] fp32: slot `part` of every combo is written, not accumulated
+  float *db;                     // scratch [ctas_per_combo][cout_pad] fp32
 };
 
 constexpr int kWgThreads = 192;
 
-ADP_DEVINL void red_add_f32(float *addr, float v) {
-  asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(v) : "memory");
-}
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmz, const WgradTcParams p) {
@@ -141,38 +140,67 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
   } else {
     // epilogue: TMEM lane = input channel, column = (kx, dZ row slot s, output channel); ky = 2 - s
     const int q4 = warp & 3;
-    if (u1 > u0) {
+    const bool have = u1 > u0;               // a CTA without units still writes its slot (zeros): the reduction reads every slot
+    if (have) {
       ptx::mbar_wait(acc_full, 0, 13);
       ptx::tc_fence_after();
-      const int row = q4 * 32 + lane;
-      const int ci = ci0 + row;
-      const bool live = row < ncga * 8 && ci < p.cin_pad;
-      const bool bias_row = row == 120 && cib == 0;
-      const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16);
-      const int units = (int)(3u * N) >> 4;
-      for (int un = 0; un < units; ++un) {
-        float v[16];
-        ptx::tmem_ld16(t0 + (uint32_t)un * 16u, v);
-        const int col = un * 16;
-        const int j = col / (int)N, rem = col - j * (int)N;
-        const int s = rem / nco, c = rem - s * nco;
-        const int tap = (2 - s) * 3 + j;
-        if (live && co0 + c < p.cout_pad) {
-          float *dst = p.dW + ((size_t)tap * p.cin_pad + ci) * p.cout_pad + co0 + c;
+    }
+    const int row = q4 * 32 + lane;
+    const int ci = ci0 + row;
+    const bool live = row < ncga * 8 && ci < p.cin_pad;
+    const bool bias_row = row == 120 && cib == 0;
+    const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const int units = (int)(3u * N) >> 4;
+    float *slotW = p.dW + (size_t)part * 9 * p.cin_pad * p.cout_pad;
+    float *slotb = p.db + (size_t)part * p.cout_pad;
+    for (int un = 0; un < units; ++un) {
+      float v[16];
+      if (have) ptx::tmem_ld16(t0 + (uint32_t)un * 16u, v);
+      else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) red_add_f32(dst + i, v[i]);
-        }
-        if (bias_row && j == 1 && s == 1) {
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+      const int col = un * 16;
+      const int j = col / (int)N, rem = col - j * (int)N;
+      const int s = rem / nco, c = rem - s * nco;
+      const int tap = (2 - s) * 3 + j;
+      if (live && co0 + c < p.cout_pad) {
+        float *dst = slotW + ((size_t)tap * p.cin_pad + ci) * p.cout_pad + co0 + c;
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (co0 + c + i < p.cout_pad) red_add_f32(p.db + co0 + c + i, v[i]);
-        }
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      if (bias_row && j == 1 && s == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (co0 + c + i < p.cout_pad) slotb[co0 + c + i] = v[i];
       }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc_512(tmem_base);
+}
+
+// dW[i] = sum over slots (fixed order) of the per-CTA partial sums; same for db.  n = 9 * cin_pad * cout_pad.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float *__restrict__ sW, const float *__restrict__ sb, int slots, size_t n, int nb, float *__restrict__ dW,
+                    float *__restrict__ db) {
+  const size_t n4 = n / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4 + (size_t)nb; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < n4) {
+      float4 a = reinterpret_cast<const float4 *>(sW)[i];
+      for (int s = 1; s < slots; ++s) {
+        const float4 b = reinterpret_cast<const float4 *>(sW + (size_t)s * n)[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      reinterpret_cast<float4 *>(dW)[i] = a;
+    } else {
+      const size_t c = i - n4;
+      float a = sb[c];
+      for (int s = 1; s < slots; ++s) a += sb[(size_t)s * nb + c];
+      db[c] = a;
+    }
+  }
 }
 
 // db[co] = sum over pixels of dZ (bias gradient).  One warp owns 32 consecutive pixels of a row and walks

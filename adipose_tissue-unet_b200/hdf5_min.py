@@ -197,10 +197,19 @@ class Hdf5Reader:
         return name, (arr if shape else arr.reshape(())[()])
 
     # ---- groups
-    def _walk(self, addr: int, path: str, seen: set):
-        if addr in seen or addr == UNDEF:
+    def _walk(self, addr: int, path: str, seen):
+        if addr == UNDEF:
             return
-        seen.add(addr)
+        if not isinstance(seen, dict):       # object address -> first path it was reached by
+            seen = {a: None for a in seen}
+        if addr in seen:
+            # hard link to an object already visited: a dataset is available under this path too (same array), a group
+            # is not descended twice (cycles)
+            first = seen[addr]
+            if first in self.datasets:
+                self.datasets[path] = self.datasets[first]
+            return
+        seen[addr] = path
         msgs = self._messages(addr)
         attrs = {}
         ds = _Dataset()
@@ -480,6 +489,13 @@ class Hdf5Writer:
     def set_attr(self, path: str, name: str, value):
         self._node(path).attrs[name] = value
 
+    def link(self, existing: str, new_path: str):
+        """Hard link: `new_path` names the SAME object as `existing` (one object header, one copy of the data)."""
+        node = self._node(existing, create=False)
+        parts = [p for p in new_path.split("/") if p]
+        parent = self._node("/".join(parts[:-1]))
+        parent.children[parts[-1]] = node
+
     def save(self, path: str):
         out = bytearray(96)      # superblock v0 is 96 bytes with 8-byte offsets
 
@@ -490,11 +506,25 @@ class Hdf5Writer:
             out.extend(b)
             return a
 
-        def header(messages: List[bytes]) -> bytes:
+        def header(messages: List[bytes], refs: int = 1) -> bytes:
             body = b"".join(messages)
-            return struct.pack("<BxHII4x", 1, len(messages), 1, len(body)) + body
+            return struct.pack("<BxHII4x", 1, len(messages), refs, len(body)) + body
+
+        # object reference counts (hard links name one object from several groups)
+        refs: Dict[int, int] = {}
+
+        def count(node: _Node):
+            for c in node.children.values():
+                refs[id(c)] = refs.get(id(c), 0) + 1
+                if refs[id(c)] == 1:
+                    count(c)
+        count(self.root)
+        done = set()
 
         def emit(node: _Node):
+            if id(node) in done:         # reached again through a hard link: already written
+                return
+            done.add(id(node))
             attr_msgs = [_attr_msg(k, v) for k, v in node.attrs.items()]
             if node.data is not None:
                 arr = node.data
@@ -530,7 +560,7 @@ class Hdf5Writer:
                 else:
                     daddr = alloc(arr.astype(arr.dtype.newbyteorder("<")).tobytes()) if arr.size else UNDEF
                     msgs.append(_msg(0x08, struct.pack("<BBQQ", 3, 1, daddr, arr.nbytes)))
-                node.addr = alloc(header(msgs + attr_msgs))
+                node.addr = alloc(header(msgs + attr_msgs, refs.get(id(node), 1)))
                 return
             for c in node.children.values():
                 emit(c)
@@ -566,7 +596,7 @@ class Hdf5Writer:
             tree += struct.pack("<Q", keys[len(snods)])
             tree += b"\x00" * (24 + (2 * INTERNAL_K + 1) * 8 + 2 * INTERNAL_K * 8 - len(tree))
             node.btree = alloc(tree)
-            node.addr = alloc(header([_msg(0x11, struct.pack("<QQ", node.btree, node.heap))] + attr_msgs))
+            node.addr = alloc(header([_msg(0x11, struct.pack("<QQ", node.btree, node.heap))] + attr_msgs, refs.get(id(node), 1)))
 
         emit(self.root)
         while len(out) % 8:
@@ -619,19 +649,81 @@ def write_keras_v3_like_weights(path: str, weights: Dict[str, np.ndarray], layer
     w.save(path)
 
 
+# model.layers of the reference graph in creation order (train_adipose_unet_v3.py:664-750): (Keras class, layer name or None)
+def _reference_layer_classes(deep_supervision: bool) -> List[Tuple[str, Optional[str]]]:
+    L: List[Tuple[str, Optional[str]]] = [("input_layer", None), ("reshape", None)]
+    for lvl in (1, 2, 3):
+        L += [("conv2d", f"down{lvl}_conv1"), ("conv2d", f"down{lvl}_conv2"), ("max_pooling2d", None)]
+    L += [("conv2d", "dilate1"), ("dropout", None)] + [("conv2d", f"dilate{i}") for i in range(2, 7)] + [("add", None)]
+    for lvl in (3, 2, 1):
+        L += [("up_sampling2d", None), ("conv2d", f"up{lvl}_conv1"), ("concatenate", None), ("conv2d", f"up{lvl}_conv2"),
+              ("conv2d", f"up{lvl}_conv3"), ("dropout", None)]
+    L += [("conv2d", "output_softmax")]
+    if deep_supervision:
+        L += [("conv2d", "aux_out1"), ("lambda", None), ("conv2d", "aux_out2"), ("lambda", None), ("lambda", None), ("lambda", None)]
+    L += [("lambda", None), ("lambda", None)]
+    return L
+
+
+def write_keras_weights_hybrid(path: str, weights: Dict[str, np.ndarray], keras_version: str = "2.13.1"):
+    """`*.weights.h5` as written by this repo: ONE file that every loader of the reference accepts.
+
+    * legacy part (root attrs `layer_names` / per-layer `weight_names`, datasets `/<layer>/<layer>/kernel:0`): what
+      `hdf5_format.load_weights_from_hdf5_group[_by_name]` reads (train_adipose_unet_v3.py:881-916,
+      full_evaluation_enhanced.py:1285-1301);
+    * Keras-2.13 saving_lib part (`save_weights` / `ModelCheckpoint` on a `.weights.h5` name, train:918-922, 1271-1278): root
+      `vars`, then per layer of `model.layers` a group `<container>/<snake_case class>[_k]/vars/{0,1}` numbered per class in
+      creation order (kernel = 0, bias = 1; weightless layers get empty `vars` groups).  The container is `layers` in Keras
+      2.13+ and `_layer_checkpoint_dependencies` in 2.12 (Keras' own reader maps one to the other): both are written.
+      With deep supervision the 1x1 heads follow `output_softmax` (conv2d_21), so that the plain inference graph
+      (segmentation_inference.py:150) finds its 22 convolutions under the indices it asks for.
+    The tensors exist once: the saving_lib paths are HDF5 hard links to the legacy datasets (the file is no larger).
+    UNPINNED against a genuine TF-2.13 file (none is shipped with the reference, h5py / TF are not installable here)."""
+    names = []
+    for k in weights:
+        n = k.rsplit("/", 1)[0]
+        if n not in names:
+            names.append(n)
+    w = Hdf5Writer()
+    w.set_attr("/", "layer_names", np.array([n.encode("utf8") for n in names]))
+    w.set_attr("/", "backend", np.bytes_(b"tensorflow"))
+    w.set_attr("/", "keras_version", np.bytes_(keras_version.encode("utf8")))
+    for n in names:
+        w.create_group(f"/{n}")
+        w.set_attr(f"/{n}", "weight_names", np.array([f"{n}/kernel:0".encode(), f"{n}/bias:0".encode()]))
+        w.create_dataset(f"/{n}/{n}/kernel:0", np.asarray(weights[n + "/kernel"], np.float32))
+        w.create_dataset(f"/{n}/{n}/bias:0", np.asarray(weights[n + "/bias"], np.float32))
+    w.create_group("/vars")
+    ds = "aux_out1" in names
+    for container in ("layers", "_layer_checkpoint_dependencies"):
+        counter: Dict[str, int] = {}
+        for cls, lname in _reference_layer_classes(ds):
+            k = counter.get(cls, 0)
+            counter[cls] = k + 1
+            g = f"/{container}/{cls}" + (f"_{k}" if k else "")
+            w.create_group(g + "/vars")
+            if lname is not None:
+                if lname not in names:
+                    raise Hdf5Error(f"weights of layer {lname} missing")
+                w.link(f"/{lname}/{lname}/kernel:0", g + "/vars/0")
+                w.link(f"/{lname}/{lname}/bias:0", g + "/vars/1")
+    w.save(path)
+
+
 _V3_RE = re.compile(r"^(?P<prefix>.*)/(?P<cls>[A-Za-z0-9_]*?)(?:_(?P<idx>\d+))?/vars/(?P<var>\d+)$")
 
 
-def read_keras_weights(path: str, init_nb: int = 44) -> Dict[str, np.ndarray]:
-    """'<layer>/kernel' (HWIO) and '<layer>/bias' for the 22 conv layers (+ aux heads when present)."""
+def read_keras_weights(path: str, init_nb: int = 44, layout: str = "auto") -> Dict[str, np.ndarray]:
+    """'<layer>/kernel' (HWIO) and '<layer>/bias' for the 22 conv layers (+ aux heads when present).
+    layout: 'auto' (by-name datasets first, then saving_lib `vars` groups) or 'vars' (saving_lib groups only)."""
     from .layers import conv_layers
     r = Hdf5Reader(path)
     ds = r.datasets
     layers = conv_layers(init_nb)
     out: Dict[str, np.ndarray] = {}
     # layout 1: by name
-    by_name = True
-    for name, *_ in layers:
+    by_name = layout != "vars"
+    for name, *_ in (layers if by_name else []):
         k = [p for p in ds if p.endswith(f"/{name}/kernel:0") or p.endswith(f"/{name}/kernel")]
         b = [p for p in ds if p.endswith(f"/{name}/bias:0") or p.endswith(f"/{name}/bias")]
         if not k or not b:
@@ -648,10 +740,13 @@ def read_keras_weights(path: str, init_nb: int = 44) -> Dict[str, np.ndarray]:
         return out
     # layout 2: '<prefix>/<class>[_k]/vars/<i>' in creation order, optimizer state ignored
     groups: Dict[Tuple[str, str, int], Dict[int, np.ndarray]] = {}
+    prefixes = sorted({m.group("prefix") for m in (_V3_RE.match(p) for p in ds) if m and "optimizer" not in m.group("prefix")})
     for p, a in ds.items():
         m = _V3_RE.match(p)
         if not m or "optimizer" in m.group("prefix"):
             continue
+        if len(prefixes) > 1 and m.group("prefix") != ("/layers" if "/layers" in prefixes else prefixes[0]):
+            continue        # a hybrid file names the same variables under two containers: read one
         key = (m.group("prefix"), m.group("cls"), int(m.group("idx") or 0))
         groups.setdefault(key, {})[int(m.group("var"))] = a
     convs = [(k, v) for k, v in sorted(groups.items()) if 0 in v and 1 in v and v[0].ndim == 4 and v[1].ndim == 1]

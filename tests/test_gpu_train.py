@@ -291,3 +291,27 @@ def test_deep_supervision_step_vs_oracle(prec, recipe):
     p = eng.predict(tile[None], A.synth.DEFAULT_MEAN, A.synth.DEFAULT_STD)[0]
     assert np.isfinite(p).all() and p.shape == (S, S)
     eng.close()
+
+
+def test_tensor_core_weight_gradients_are_bit_reproducible(weights):
+    """The tcgen05 weight-gradient GEMM writes per-CTA partial sums into slots that are reduced in a fixed order
+    (wgrad_tc.cuh): two backward passes over the same forward give bit-identical gradients for the 20 generic conv layers
+    (round 1 accumulated with red.global.add.f32, whose order - and therefore the low bits - changed from run to run)."""
+    n, S = 2, 256
+    x, y = batch(n, S, seed=41)
+    eng = api.Engine(precision="bf16", max_forwards=8)
+    eng.set_weights(weights)
+    eng.train_begin(n, S, dropout_rate=0.3, seed=3)
+    sums = eng.train_forward(x, y)
+    eng.train_backward(sums)
+    g1 = eng.train_grads()
+    eng.train_backward(sums)
+    g2 = eng.train_grads()
+    generic = [k for k in g1 if not k.startswith(("down1_conv1/", "output_softmax/"))]
+    assert len(generic) == 40
+    for k in generic:
+        assert np.array_equal(g1[k], g2[k]), k
+    for k in ("down1_conv1/kernel", "output_softmax/kernel"):      # float / float64 atomics: equal to rounding, reported
+        print(k, "max run-to-run difference", float(np.abs(g1[k] - g2[k]).max()), "of", float(np.abs(g1[k]).max()))
+        assert np.allclose(g1[k], g2[k], rtol=1e-4, atol=1e-6 * float(np.abs(g1[k]).max()))
+    eng.train_end(); eng.close()

@@ -114,3 +114,37 @@ def test_npz_and_missing_file(tmp_path, weights):
     junk.write_bytes(b"not hdf5" * 100)
     with pytest.raises(H.Hdf5Error):
         W.load_weights_file(str(junk))
+
+
+def test_hybrid_weights_file_serves_every_loader_of_the_reference(tmp_path):
+    """`*.weights.h5` written by this repo: legacy by-name datasets (load_weights_from_hdf5_group[_by_name],
+    full_evaluation_enhanced.py:1285-1301) AND the Keras-2.13 saving_lib groups (`layers/` and the 2.12 container
+    `_layer_checkpoint_dependencies/`, `<class>[_k]/vars/{0,1}` in model.layers order) as hard links to the same tensors."""
+    import os
+    import adipose_unet_b200 as A
+    from adipose_unet_b200 import hdf5_min as H
+    from adipose_unet_b200.weights_io import load_weights_file, save_weights_file
+    for ds in (False, True):
+        w = A.synth.init_weights(deep_supervision=ds)
+        path = str(tmp_path / f"ds{int(ds)}.weights.h5")
+        save_weights_file(path, w)
+        assert os.path.getsize(path) < 1.02 * sum(v.nbytes for v in w.values()) + 200_000       # linked, not copied
+        r = H.Hdf5Reader(path)
+        assert [n.decode() for n in r.attrs["/"]["layer_names"]][:2] == ["down1_conv1", "down1_conv2"]
+        assert "/vars" in r.groups and "/layers/reshape/vars" in r.groups and "/layers/lambda_1/vars" in r.groups
+        for container in ("/layers", "/_layer_checkpoint_dependencies"):
+            np.testing.assert_array_equal(r.datasets[f"{container}/conv2d/vars/0"], w["down1_conv1/kernel"])
+            np.testing.assert_array_equal(r.datasets[f"{container}/conv2d_6/vars/0"], w["dilate1/kernel"])
+            np.testing.assert_array_equal(r.datasets[f"{container}/conv2d_12/vars/1"], w["up3_conv1/bias"])
+            np.testing.assert_array_equal(r.datasets[f"{container}/conv2d_21/vars/0"], w["output_softmax/kernel"])
+            if ds:
+                np.testing.assert_array_equal(r.datasets[f"{container}/conv2d_22/vars/0"], w["aux_out1/kernel"])
+                np.testing.assert_array_equal(r.datasets[f"{container}/conv2d_23/vars/1"], w["aux_out2/bias"])
+        for layout in ("auto", "vars"):
+            got = H.read_keras_weights(path, layout=layout)
+            assert set(got) == set(w) and all(np.array_equal(got[k], w[k]) for k in w)
+        assert set(load_weights_file(path)) == {k for k in w if not k.startswith("aux_out")}
+        assert set(load_weights_file(path, keep_aux=True)) == set(w)
+    # plain `.h5` names keep the legacy layout only
+    save_weights_file(str(tmp_path / "legacy.h5"), A.synth.init_weights())
+    assert not any(g.startswith("/layers") for g in H.Hdf5Reader(str(tmp_path / "legacy.h5")).groups)
