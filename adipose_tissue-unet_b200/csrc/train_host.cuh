@@ -430,10 +430,13 @@ template <typename T> struct Bwd {
         e->launch(("conv_wgrad_tcgen05/" + L.name).c_str(), fl, by, [&] {
           wgrad_tc_kernel<<<grid, kWgThreads, wgrad_smem_bytes(p), e->stream>>>(tmx, tmz, p);
         });
-        e->launch("wgrad_reduce", 0, (double)(p.ctas_per_combo + 1) * np * 4, [&] {
-          wgrad_reduce_kernel<<<ew_grid(e, np / 4 + L.cout_pad, wgrad_reduce_kernel), 256, 0, e->stream>>>(
-              tr->wg_scratch.as<float>(), tr->wb_scratch.as<float>(), p.ctas_per_combo, np, L.cout_pad, TL.gw.as<float>(), TL.gb.as<float>());
+        const size_t nflat = (size_t)9 * L.cin * L.cout + L.cout;
+        e->launch("wgrad_reduce", 0, (double)p.ctas_per_combo * np * 4 + (double)nflat * 4, [&] {
+          wgrad_reduce_kernel<<<ew_grid(e, nflat, wgrad_reduce_kernel), 256, 0, e->stream>>>(
+              tr->wg_scratch.as<float>(), tr->wb_scratch.as<float>(), p.ctas_per_combo, L.cin, L.cout, L.cin_pad, L.cout_pad, L.skip,
+              L.skip ? pad16(L.skip) : 0, tr->grad.as<float>() + TL.koff, tr->grad.as<float>() + TL.boff);
         });
+        return;          // the flat gradient is complete: no padded copy, no un-padding pass
       }
     } else {
     const int ci_tiles = cdiv(L.cin_pad, 64), co_tiles = cdiv(L.cout_pad, 64);

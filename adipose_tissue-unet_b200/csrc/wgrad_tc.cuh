@@ -181,24 +181,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
   if (warp == 1) ptx::tmem_dealloc_512(tmem_base);
 }
 
-// dW[i] = sum over slots (fixed order) of the per-CTA partial sums; same for db.  n = 9 * cin_pad * cout_pad.
+// Fixed-order sum over the slots of the per-CTA partial sums, written straight into the FLAT gradient (Keras order: kernel
+// HWIO with the real channel counts, then bias): flat_k[(t*cin + ci)*cout + co] = sum_s slot_s[(t*cin_pad + cip)*cout_pad + co],
+// cip = ci, or skip_pad + (ci - skip) for the upsampled-path half of a concat-fed layer; flat_b[co] = sum_s slot_b[co].
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float *__restrict__ sW, const float *__restrict__ sb, int slots, size_t n, int nb, float *__restrict__ dW,
-                    float *__restrict__ db) {
-  const size_t n4 = n / 4;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4 + (size_t)nb; i += (size_t)gridDim.x * blockDim.x) {
-    if (i < n4) {
-      float4 a = reinterpret_cast<const float4 *>(sW)[i];
-      for (int s = 1; s < slots; ++s) {
-        const float4 b = reinterpret_cast<const float4 *>(sW + (size_t)s * n)[i];
-        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-      }
-      reinterpret_cast<float4 *>(dW)[i] = a;
+wgrad_reduce_kernel(const float *__restrict__ sW, const float *__restrict__ sb, int slots, int cin, int cout, int cin_pad, int cout_pad,
+                    int skip, int skip_pad, float *__restrict__ flat_k, float *__restrict__ flat_b) {
+  const size_t nk = (size_t)9 * cin * cout, np = (size_t)9 * cin_pad * cout_pad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nk + (size_t)cout; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < nk) {
+      const int co = (int)(i % cout); size_t r = i / cout;
+      const int ci = (int)(r % cin); const int t = (int)(r / cin);
+      const int cip = (skip && ci >= skip) ? skip_pad + (ci - skip) : ci;
+      const size_t pi = ((size_t)t * cin_pad + cip) * cout_pad + co;
+      float a = sW[pi];
+      for (int s = 1; s < slots; ++s) a += sW[(size_t)s * np + pi];
+      flat_k[i] = a;
     } else {
-      const size_t c = i - n4;
+      const size_t c = i - nk;
       float a = sb[c];
-      for (int s = 1; s < slots; ++s) a += sb[(size_t)s * nb + c];
-      db[c] = a;
+      for (int s = 1; s < slots; ++s) a += sb[(size_t)s * cout_pad + c];
+      flat_b[c] = a;
     }
   }
 }
