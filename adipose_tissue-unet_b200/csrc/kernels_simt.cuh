@@ -127,6 +127,14 @@ template <typename T> ADP_DEVINL void unpack8(const Raw8<T> &r, float *a) {
   }
 }
 
+// Packed dual fp32 FMA of sm_100 (SASS FFMA2): two independent IEEE round-to-nearest FMAs per instruction, i.e. the same bits
+// as two fmaf() calls in half the issue slots - a three-register FFMA issues every other cycle per scheduler, which made the
+// first conv issue-bound (ncu: 70 % issue slots at 39 % of DRAM peak).
+ADP_DEVINL void ffma2(float2 &acc, const float2 a, const float2 b) {
+  unsigned long long &d = reinterpret_cast<unsigned long long &>(acc);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(reinterpret_cast<const unsigned long long &>(a)), "l"(reinterpret_cast<const unsigned long long &>(b)));
+}
+
 // block = (32, 8), output tile = 32 columns x 32 rows: the normalised (and dihedrally transformed) 34 x 34 input window
 // is staged once in shared memory (one z-score division per input pixel instead of nine), then a warp owns 32
 // consecutive columns of FOUR rows so that every weight read from shared memory feeds four pixels (288 FMA per 18
@@ -163,33 +171,37 @@ first_conv_kernel(FirstConvSrc src, const int *__restrict__ fw_tile, const int *
   const int x = x0 + threadIdx.x;
   const int yb = y0 + threadIdx.y * kFcRows;
   if (x >= S || yb >= S) return;
-  float v[kFcRows + 2][3];
+  float2 v[kFcRows + 2][3];                      // every window value in both halves of a register pair (FFMA2 operand)
 #pragma unroll
   for (int r = 0; r < kFcRows + 2; ++r)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) v[r][kx] = win[(threadIdx.y * kFcRows + r) * 34 + threadIdx.x + kx];
+    for (int kx = 0; kx < 3; ++kx) {
+      const float q = win[(threadIdx.y * kFcRows + r) * 34 + threadIdx.x + kx];
+      v[r][kx] = make_float2(q, q);
+    }
   for (int g = 0; g < out.C / 8; ++g) {
-    float a[kFcRows][8];
+    float2 a[kFcRows][4];
 #pragma unroll
     for (int r = 0; r < kFcRows; ++r)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) a[r][c] = bs[g * 8 + c];
+      for (int c = 0; c < 4; ++c) a[r][c] = make_float2(bs[g * 8 + 2 * c], bs[g * 8 + 2 * c + 1]);
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const float4 w0 = *reinterpret_cast<const float4 *>(ws + t * out.C + g * 8);
       const float4 w1 = *reinterpret_cast<const float4 *>(ws + t * out.C + g * 8 + 4);
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
       for (int r = 0; r < kFcRows; ++r)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) a[r][c] = fmaf(v[r + t / 3][t % 3], wv[c], a[r][c]);
+        for (int c = 0; c < 4; ++c) ffma2(a[r][c], v[r + t / 3][t % 3], wv[c]);
     }
 #pragma unroll
     for (int r = 0; r < kFcRows; ++r) {
       if (yb + r >= S) break;
+      float o8[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) a[r][c] = fmaxf(a[r][c], 0.f);
-      store8v<T>(out, f, yb + r, g, x, a[r]);
+      for (int c = 0; c < 4; ++c) { o8[2 * c] = fmaxf(a[r][c].x, 0.f); o8[2 * c + 1] = fmaxf(a[r][c].y, 0.f); }
+      store8v<T>(out, f, yb + r, g, x, o8);
     }
   }
 }
@@ -216,11 +228,11 @@ conv3x3_simt_kernel(View<T> in, View<T> out, const float *__restrict__ w, const 
   const int y0 = blockIdx.y * 16 + threadIdx.y;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const bool live[2] = {(x < W) && (y0 < H), (x < W) && (y0 + 8 < H)};
-  float acc[2][16];
+  float2 acc2[2][8];
 #pragma unroll
   for (int r = 0; r < 2; ++r)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[r][i] = 0.f;
+    for (int i = 0; i < 8; ++i) acc2[r][i] = make_float2(0.f, 0.f);
   for (int c0 = 0; c0 < in.C; c0 += 16) {
     __syncthreads();
     for (int i = tid; i < 9 * 256; i += 256) {
@@ -253,20 +265,24 @@ conv3x3_simt_kernel(View<T> in, View<T> out, const float *__restrict__ w, const 
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const float4 *wr = reinterpret_cast<const float4 *>(&ws[t][c][0]);
+        const float2 a2[2] = {make_float2(a[0][c], a[0][c]), make_float2(a[1][c], a[1][c])};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 wv = wr[q];
 #pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            acc[r][4 * q] = fmaf(a[r][c], wv.x, acc[r][4 * q]);
-            acc[r][4 * q + 1] = fmaf(a[r][c], wv.y, acc[r][4 * q + 1]);
-            acc[r][4 * q + 2] = fmaf(a[r][c], wv.z, acc[r][4 * q + 2]);
-            acc[r][4 * q + 3] = fmaf(a[r][c], wv.w, acc[r][4 * q + 3]);
+          for (int r = 0; r < 2; ++r) {          // packed dual FMA (ffma2): the same two IEEE FMAs per accumulator pair
+            ffma2(acc2[r][2 * q], a2[r], make_float2(wv.x, wv.y));
+            ffma2(acc2[r][2 * q + 1], a2[r], make_float2(wv.z, wv.w));
           }
         }
       }
     }
   }
+  float acc[2][16];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[r][2 * i] = acc2[r][i].x; acc[r][2 * i + 1] = acc2[r][i].y; }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     if (!live[r]) continue;

@@ -349,7 +349,7 @@ def run_ours(args, rank, world, local_rank):
             # DRAM traffic per launch from the committed ncu --set full capture of the same kernels (bytes per forward summed
             # over the 20 conv launches of a chunk, scaled to this run's forwards per launch); null if the summary is absent
             traffic, traffic_src = None, None
-            tp_ = os.path.join(ROOT, "profiles", "r1_ncu_conv_traffic.json")
+            tp_ = os.path.join(ROOT, "profiles", "r2_ncu_conv_traffic.json")
             if os.path.exists(tp_):
                 tj = json.load(open(tp_))
                 fw_per_launch = N_AUG * BATCH_TILES * len(conv) / max(cl, 1)
