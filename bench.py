@@ -403,7 +403,7 @@ def run_ours(args, rank, world, local_rank):
     # on the same batch, and how far the headline bf16 probabilities are from it
     x3_res = None
     if rank == 0 and world == 1 and args.precision == "bf16" and not args.no_x3:
-        prob_bf16 = prob_d[:2].clone()
+        prob_bf16 = prob_d.clone()
         eng3 = api.Engine(precision="bf16x3", device=local_rank, max_forwards=args.max_forwards)
         eng3.set_weights(A.synth.init_weights())
         stream3 = torch.cuda.ExternalStream(eng3.stream_ptr(), device=torch.device("cuda", local_rank))
@@ -419,8 +419,14 @@ def run_ours(args, rank, world, local_rank):
         e1.record(stream3)
         torch.cuda.synchronize()
         dt3 = e0.elapsed_time(e1) / 1e3 / 2
+        # mask agreement of the headline bf16 path with the <= 1e-4 path on this batch (BASELINE: Dice >= 0.999; DESIGN.md section 2
+        # explains why random-init weights cannot meet it on ANY <= 1e-2 path: the fraction of pixels that close to 0.5)
+        ma, mb = prob_bf16 > 0.5, prob3 > 0.5
+        dice = float((2.0 * (ma & mb).sum() + 1e-10) / (ma.sum() + mb.sum() + 1e-10))
         x3_res = {"precision": "bf16x3", "tiles_per_s": BATCH_TILES / dt3, "ms_per_step": dt3 * 1e3, "steps": 2,
-                  "max_abs_diff_bf16_vs_bf16x3_probabilities": float((prob3[:2] - prob_bf16).abs().max()),
+                  "max_abs_diff_bf16_vs_bf16x3_probabilities": float((prob3 - prob_bf16).abs().max()),
+                  "mask_dice_bf16_vs_bf16x3": dice, "flipped_pixels": int((ma != mb).sum()),
+                  "fraction_of_pixels_within_1e-2_of_threshold": float(((prob3 - 0.5).abs() <= 1e-2).float().mean()),
                   "note": "same 16-tile 8-way-TTA batch, inputs resident; parity of this path vs the oracle: <= 1e-4 (tests/test_gpu_forward.py)"}
         eng3.close()
 

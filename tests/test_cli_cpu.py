@@ -509,3 +509,36 @@ def test_reduce_lr_on_plateau_and_keras_log_columns():
                           "val_aux_out1_loss", "val_aux_out2_loss", "val_loss", "val_main_out_binary_accuracy", "val_main_out_dice_coef",
                           "val_main_out_loss"]
     assert train.keras_logs(t, {}, False) == {"loss": 1.0, "dice_coef": 0.5, "binary_accuracy": 0.9}
+
+
+def test_sliding_window_hands_the_blend_window_to_the_engine():
+    """SlidingWindowInference with the native model: every window-weighted blender (Gaussian, and the Hann extension) must
+    reach wsi_begin as a weighted blend WITH its window; linear / none as the uniform average (round-1 advisor finding: 'hann'
+    silently ran as linear)."""
+    from adipose_unet_b200 import api, _lib
+    seen = {}
+
+    class StubEngine:
+        def wsi_begin(self, rows, W, y0, tile, mode, window):
+            seen["mode"], seen["window"] = mode, window
+
+        def wsi_push_tiles(self, *a, **k):
+            pass
+
+        def wsi_finalize(self, y, rows, W, **k):
+            return np.zeros((rows, W), np.float32), None, (0, 0, 0, 0)
+
+        def wsi_end(self):
+            pass
+
+    model = api.AdiposeUNet.__new__(api.AdiposeUNet)
+    model.engine = StubEngine()
+    img = np.zeros((96, 160), np.float32)
+    for blend, want_mode, window_of in (("gaussian", _lib.BLEND_GAUSSIAN, lambda: api.GaussianBlender(64).weight_map),
+                                        ("hann", _lib.BLEND_GAUSSIAN, lambda: api.HannBlender(64).weight_map),
+                                        ("linear", _lib.BLEND_LINEAR, lambda: None), ("none", _lib.BLEND_LINEAR, lambda: None)):
+        sw = api.SlidingWindowInference(tile_size=64, overlap=0.5, blend_mode=blend, verbose=False)
+        sw.predict_with_sliding_window(img, model, 127.5, 50.0)
+        assert seen["mode"] == want_mode, blend
+        want = window_of()
+        assert (seen["window"] is None) if want is None else np.array_equal(seen["window"], want), blend
