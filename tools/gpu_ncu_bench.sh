@@ -3,7 +3,7 @@
 # step are what bench.py's roofline.share_of_step must agree with
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { cat gpurun_out/build.log; exit 1; }
-BENCH="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --wsi-size 0 --train-batch 0"
+BENCH="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --wsi none --train-batch 0"
 $BENCH > gpurun_out/plain_bench.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/launches_bench.csv $BENCH > gpurun_out/ncu0.log 2>&1
 echo "bench launch list rc=$?"

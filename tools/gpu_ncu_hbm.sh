@@ -3,7 +3,7 @@
 # bytes and throughput per launch, from the bench command (1024^2 tiles, 16 forwards per launch) with a small WSI run appended
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { cat gpurun_out/build.log; exit 1; }
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --wsi-size 2048 --train-batch 0"
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --wsi small --train-batch 0"
 $CMD > gpurun_out/plain_hbm.log 2>&1 && \
 ncu --set full --clock-control none -k regex:"first_conv_kernel|add6_kernel|maxpool2_kernel|tta_blend_kernel|finalize_kernel" -s 12 -c 40 \
     -o gpurun_out/prof_hbm $CMD > gpurun_out/ncu_hbm.log 2>&1

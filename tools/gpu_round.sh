@@ -11,7 +11,7 @@ python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench.json'))
 print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}); print(d['e2e']); print(d['roofline']['frac'], d.get('cpu_baseline'))
-print({k:d['train'][k] for k in ('tiles_per_s','ms_per_step')}, d['wsi']['mpx_per_s'])
+print({k:d['train'][k] for k in ('tiles_per_s','ms_per_step')}, {k: w['mpx_per_s'] for k, w in d['wsi'].items()})
 for k in d['kernels']:
     if 'conv3x3_tc' not in k['name']: print(k)
 PY
