@@ -48,6 +48,7 @@
 //   EPI_BWD   data-gradient twin of the training step: (acc + residual) * [mask > 0] * scale, the mask tile staged in
 //             shared memory by a TMA box per item for accumulators up to 96 wide (ConvTcParams::mask_bufs).
 #pragma once
+#include "kernels_simt.cuh"
 #include "ptx.cuh"
 
 namespace adp {
@@ -60,6 +61,17 @@ struct ConvTcVariant {
   int bias_off;      // first bias element
   int out_cg;        // channel-group offset added to the output view
   int pad_;
+};
+
+// FC variant (template flag): the A operand of down1_conv2 - the output of the FIRST conv, Reshape + Conv2D(1 -> C, 3x3) + ReLU
+// (train_adipose_unet_v3.py:665-668) - is computed inside the kernel by five "stencil" warps straight into the pipeline stages,
+// in exactly the layout the TMA boxes would have produced.  The 48-channel tensor (100 MB per forward) is then neither written
+// nor read.  The stencil reads the normalised, dihedrally transformed image (float32 [forward][S][S], written by
+// tta_input_kernel: full_evaluation_enhanced.py:1306, :590) through 8 x 136 TMA boxes (tensor map `tmask`) whose out-of-range
+// fill is the conv's zero padding.  Inference only (training needs the tensor for the weight gradient).
+struct FirstConvFuse {
+  alignas(16) float w[9][64];    // [tap][output channel] fp32, zero padded (read through the constant bank, 128-bit uniform loads)
+  alignas(16) float b[64];
 };
 
 struct ConvTcParams {
@@ -110,6 +122,7 @@ struct ConvTcParams {
   // cycles per item with the loads, 6.3 k without).  mask_bufs = 0 keeps the register-prefetch loads (wide accumulators)
   int mask_bufs;                 // 0, 1 or 2
   uint32_t mask_bytes;           // T * N * 256
+  FirstConvFuse fc;              // FC variant only
 };
 
 // index of weight (tap t, row n of variant block) inside a (variant, chunk) weight block of `ntaps` taps, channel-group
@@ -121,10 +134,16 @@ __host__ __device__ inline size_t tc_block_index(int kys, int ntaps, int N, int 
   return ((((size_t)kx * 2 + g) * KY + (KY - 1 - kyi)) * N + n) * 8 + j;
 }
 
-size_t tc_smem_bytes(const ConvTcParams &p) {
+size_t tc_smem_bytes(const ConvTcParams &p) {   // FC variant: + kFcWinBytes
   // stages | mask tile buffers (EPI_BWD) | mbarriers (2S + 8) + tmem slot | bias (704 floats) | head weights (2*256 + 2 floats)
   return (size_t)p.S * p.stage_stride + (size_t)p.mask_bufs * p.mask_bytes + (2 * p.S + 6 + 4) * 8 + (704 + 520) * 4;
 }
+constexpr int kFcWinW = 136, kFcWinRows = 8;                     // input window of one item: 8 rows x 132 columns, loaded as a
+constexpr int kFcWinX0 = 4;                                      // box of 136 that starts 4 columns left of the strip (16-byte aligned)
+constexpr uint32_t kFcWinBoxBytes = kFcWinRows * kFcWinW * 4;
+constexpr size_t kFcWinBytes = 2 * kFcWinBoxBytes + 128 + 10 * 64 * 4;   // double buffered, 128-byte aligned; + weights and bias
+constexpr int kFcMaxChunks = 4;                                  // first conv of at most 64 channels
+constexpr int kFcWarps = 5, kFcThreads = kFcWarps * 32;          // four warps own 32 columns each, the fifth the two halo columns
 
 // Timing experiments (ADP_TC_DEBUG switches, role timers) are compiled in only by a debug build
 // (`python -m adipose_unet_b200.build --force --debug`, -DADP_TC_DEBUG_BUILD=1): the production kernels carry no p.dbg
@@ -138,6 +157,56 @@ ADP_DEVINL bool tc_dbg(const ConvTcParams &p, int bits) {
 }
 
 constexpr int kTcThreads = 352;   // producer, MMA issuer A, 8 epilogue warps, MMA issuer B
+constexpr int kTcThreadsFc = kTcThreads + kFcThreads;   // FC variant: + five stencil warps (w11..15)
+
+// f32 pair -> packed bf16x2 with ReLU (cvt.rn.relu: max(x, 0) then round to nearest even, what fmaxf + __float2bfloat16_rn give)
+ADP_DEVINL uint32_t relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// ---- FC variant: the first conv as an in-kernel producer of the A operand (see FirstConvFuse) ----
+// R consecutive rows x 8 channels (group cg) of the first conv at one column: acc = bias, then the nine taps in order with one
+// IEEE FMA each (the accumulation order of first_conv_kernel: bit-identical values), ReLU, round to bf16, one 16-byte shared
+// store per row into the pipeline stage.  The weights sit in shared memory (one broadcast LDS.128 per four weights = one
+// wavefront: ~450 per item next to the ~4000 of the MMA operand fetch).  Measured alternatives (1024^2, 16 forwards, whole
+// kernel): weights as uniform-register FFMA2 operands from the parameter block, fully unrolled - 1.24 ms, 37 % of the stencil
+// warps' issue slots lost to instruction fetch (24 KB of straight-line code per item); indexed LDC.64 in this loop - 1.46 ms.
+template <int R>
+ADP_DEVINL void fc_rows(const float *__restrict__ ws /*[9][64] then bias[64], shared*/, const float (&v)[R + 2][3], int cg, uint32_t live_rows,
+                        uint8_t *dst, uint32_t row_stride) {
+  float2 a[R][4];
+  {
+    const float4 b0 = *reinterpret_cast<const float4 *>(ws + 9 * 64 + cg * 8), b1 = *reinterpret_cast<const float4 *>(ws + 9 * 64 + cg * 8 + 4);
+    const float2 b[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r][c] = b[c];
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 w0 = *reinterpret_cast<const float4 *>(ws + t * 64 + cg * 8), w1 = *reinterpret_cast<const float4 *>(ws + t * 64 + cg * 8 + 4);
+    const float2 w[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float q = v[r + t / 3][t % 3];
+        ffma2(a[r][c], make_float2(q, q), w[c]);
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);                     // outside the image the operand is zero (what the TMA box fill gives)
+    if ((live_rows >> r) & 1u)
+      o = make_uint4(relu_bf16x2(a[r][0].x, a[r][0].y), relu_bf16x2(a[r][1].x, a[r][1].y), relu_bf16x2(a[r][2].x, a[r][2].y),
+                     relu_bf16x2(a[r][3].x, a[r][3].y));
+    *reinterpret_cast<uint4 *>(dst + (size_t)r * row_stride) = o;
+  }
+}
+
 constexpr int EPI_STORE = 0, EPI_HEAD = 1, EPI_POOL = 2, EPI_BWD = 3;   // EPI_BWD = EPI_STORE with a mask (data-gradient twin)
 
 // Software-pipelined walk over 16-column accumulator units u0, u0+step, ... < uend: the TMEM load
@@ -205,10 +274,11 @@ ADP_DEVINL void store16_out(__nv_bfloat16 *o, size_t lo_elems, size_t plane, con
   *reinterpret_cast<uint4 *>(o + lo_elems + plane) = *reinterpret_cast<uint4 *>(l + 8);
 }
 
-template <int NTAPS, int T, bool KYS, int EPI>
-__global__ void __launch_bounds__(kTcThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmask, const ConvTcParams p) {
+template <int NTAPS, int T, bool KYS, int EPI, bool FC = false>
+__global__ void __launch_bounds__(FC ? kTcThreadsFc : kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmask, const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int kThreads = FC ? kTcThreadsFc : kTcThreads;
   uint8_t *smask = smem + (size_t)p.S * p.stage_stride;           // EPI_BWD: mask_bufs x mask_bytes
   uint64_t *bars = reinterpret_cast<uint64_t *>(smask + (size_t)p.mask_bufs * p.mask_bytes);
   uint64_t *full = bars, *empty = full + p.S;
@@ -217,10 +287,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   uint64_t *mask_full = acc_empty + 4, *mask_empty = mask_full + 2;
   float *sbias = reinterpret_cast<float *>(acc_empty + 8);        // [nvar * N] (<= 704 floats)
   float *shead = sbias + 704;                                      // [2 * N] + 2, EPI_HEAD only
+  // FC only: [2][kFcWinRows][kFcWinW] input windows (TMA destinations); their barriers are the mask tile's (unused by EPI_POOL)
+  // (offset arithmetic on the shared array itself: a pointer that went through an integer loses its address space and
+  // every access through it becomes a generic LD/ST)
+  const size_t fc_off = ((size_t)p.S * p.stage_stride + (size_t)p.mask_bufs * p.mask_bytes + (size_t)(2 * p.S + 10) * 8 + (704 + 520) * 4 + 127) &
+                        ~(size_t)127;
+  float *swin = reinterpret_cast<float *>(smem + fc_off);
+  float *sfw = swin + 2 * kFcWinRows * kFcWinW;                    // FC only: first-conv weights [9][64] + bias [64]
+  if constexpr (FC) {
+    const float *src = &p.fc.w[0][0];                              // w and b are contiguous in the parameter block
+    for (int i = threadIdx.x; i < 10 * 64; i += kThreads) sfw[i] = src[i];
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < p.nvar * p.N; i += kTcThreads) {
+  for (int i = threadIdx.x; i < p.nvar * p.N; i += kThreads) {
     const int v = i / p.N;
     sbias[i] = p.bias[p.var[v].bias_off + (i - v * p.N)];
   }
@@ -229,17 +310,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     // w0 - w1 (and b0 - b1) and reads it with 128-bit shared loads - the scalar form issued 2 x N 32-bit loads per pixel row,
     // 1.7 k shared-memory wavefronts per item that compete with the MMA operand fetch on the same port (ncu: 37 % of the
     // kernel's shared wavefronts were epilogue loads)
-    for (int i = threadIdx.x; i < p.N; i += kTcThreads) shead[i] = p.head_w[i] - p.head_w[p.N + i];
+    for (int i = threadIdx.x; i < p.N; i += kThreads) shead[i] = p.head_w[i] - p.head_w[p.N + i];
     if (threadIdx.x == 0) shead[p.N] = p.head_b[0] - p.head_b[1];
   }
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < p.S; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 2); }
+    // FC: a stage is full when the weight block has landed (producer thread: expect_tx) AND the five stencil warps have written A
+    for (int i = 0; i < p.S; ++i) { ptx::mbar_init(&full[i], FC ? 1 + kFcWarps : 1); ptx::mbar_init(&empty[i], 2); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 8); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&mask_full[i], 1); ptx::mbar_init(&mask_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&mask_full[i], 1); ptx::mbar_init(&mask_empty[i], FC ? kFcWarps : 8); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmap);
-    if constexpr (EPI == EPI_BWD) ptx::prefetch_tmap(&tmask);
+    if constexpr (EPI == EPI_BWD || FC) ptx::prefetch_tmap(&tmask);
   }
   if (warp == 1) ptx::tmem_alloc_512(tmem_ptr);
   ptx::tc_fence_before();
@@ -269,16 +351,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           ptx::tma_load_5d(smask + (size_t)mb * p.mask_bytes, &tmask, &mask_full[mb], 0, tx * 16, p.var[v].out_cg, ty * T, n);
           ++mit;
         }
+        if constexpr (FC) {                                   // input window of the item (rows ty*T - 2 .., columns tx*128 - 4 ..)
+          const int wb = mit & 1; const uint32_t wph = (uint32_t)(mit >> 1) & 1u;
+          ptx::mbar_wait(&mask_empty[wb], wph ^ 1, 13);
+          ptx::mbar_expect_tx(&mask_full[wb], kFcWinBoxBytes);
+          ptx::tma_load_5d(swin + (size_t)wb * (kFcWinRows * kFcWinW), &tmask, &mask_full[wb], tx * 128 - kFcWinX0, ty * T - 2, n, 0, 0);
+          ++mit;
+        }
         for (int c = 0; c < p.nchunks; ++c) {
           uint8_t *sa = smem + (size_t)st * p.stage_stride;
           { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&empty[st], ph ^ 1, 1); if (tc_dbg(p, 16)) t_w0 += clock64() - tw; }
           // p.dbg (ADP_TC_DEBUG, timing experiments only - results are wrong): 2 = weights only for the first item,
           // 8 = activations only for the first item, 1 = no epilogue stores, 4 = one MMA per stage, 16 = role timers
           const bool ld_b = !tc_dbg(p, 2) || item == (int)blockIdx.x, ld_a = !tc_dbg(p, 8) || item == (int)blockIdx.x;
-          ptx::mbar_expect_tx(&full[st], (ld_a ? p.a_tx_bytes : 0u) + (ld_b ? p.b_bytes : 0u));
+          ptx::mbar_expect_tx(&full[st], ((ld_a && !FC) ? p.a_tx_bytes : 0u) + (ld_b ? p.b_bytes : 0u));
           int cgc = c * 2;                                     // first channel group of this chunk
           if (p.split) { const int cr = c / 3; cgc = cr * 2 + ((c - cr * 3) == 2 ? p.in_lo : 0); }
-          if (ld_a)
+          if (ld_a && !FC)
             for (int b = 0; b < p.nbox; ++b)
               ptx::tma_load_5d(sa + (size_t)b * p.a_box_stride, &tmap, &full[st], 0, xg, cgc, ys + p.box_dy[b], n);
           if (ld_b) ptx::bulk_load_1d(sa + p.a_bytes, w0 + (size_t)c * blk_elems, p.b_bytes, &full[st]);
@@ -416,7 +505,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       }
       if (tc_dbg(p, 16) && issuer == 0) { p.dbg_out[blockIdx.x * 8 + 2] = t_m0; p.dbg_out[blockIdx.x * 8 + 3] = t_m1; p.dbg_out[blockIdx.x * 8 + 4] = clock64() - t_mstart; p.dbg_out[blockIdx.x * 8 + 7] = t_m2; }
     }
-  } else {
+  } else if (!FC || warp < 10) {
     // ---------------- epilogue (warps 2..9; TMEM lane quarter = warp % 4, two warps per quarter) ----------------
     const int q4 = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -644,6 +733,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
     }
     if (tc_dbg(p, 16) && warp == 2 && lane == 0) { p.dbg_out[blockIdx.x * 8 + 5] = t_e0; p.dbg_out[blockIdx.x * 8 + 6] = clock64() - t_estart; }
+  } else {
+    // ---------------- FC: stencil warps 11..15 compute the A operand (first conv) into the pipeline stages ----------------
+    // Item = T (= 4) output rows x 128 columns: the A box is 6 rows x 130 columns of the first conv's output (stage row r <->
+    // image row ty*4 - 1 + r, box pixel 7 + j <-> image column tx*128 - 1 + j), which needs an 8 x 132 window of the input:
+    // the producer thread lands it in shared memory with one TMA box per item (two buffers).  Warps 0..3 of the group own 32
+    // columns each - all six rows of a column in one thread, so every window value feeds up to nine FMAs from a register - and
+    // the fifth warp's first 12 lanes the two halo columns (one row each).
+    if constexpr (FC) {
+      const int sw = warp - 11;
+      const uint32_t plane_a = (uint32_t)p.PW * 16u, row_stride = 2u * plane_a;
+      constexpr int R = 6;                                     // rows per thread of the main warps
+      const bool main_warp = sw < 4;
+      const bool act = main_warp || lane < 12;
+      const int j = main_warp ? sw * 32 + lane : 128 + (lane & 1);        // box column 0..129
+      const int r0 = (main_warp || !act) ? 0 : (lane >> 1);               // first box row of this thread
+      int st = 0; uint32_t ph = 0; int it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        int q = item; const int tx = q % p.ntx; q /= p.ntx; const int ty = q % p.nty;
+        const int wbuf = it & 1; const uint32_t wph = (uint32_t)(it >> 1) & 1u;
+        const float *wb = swin + wbuf * (kFcWinRows * kFcWinW) + r0 * kFcWinW + j + (kFcWinX0 - 2);
+        float v[R + 2][3];
+        ptx::mbar_wait(&mask_full[wbuf], wph, 14);
+#pragma unroll
+        for (int r = 0; r < R + 2; ++r)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) v[r][kx] = (main_warp || r < 3) ? wb[r * kFcWinW + kx] : 0.f;
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&mask_empty[wbuf]);    // the values are in registers: the producer may refill the buffer
+        const int X = tx * 128 - 1 + j;
+        uint32_t live = 0;
+        if (X >= 0 && X < p.Win)
+#pragma unroll
+          for (int r = 0; r < R; ++r) { const int Y = ty * T - 1 + r0 + r; live |= (Y >= 0 && Y < p.Hin) ? (1u << r) : 0u; }
+        float v1[3][3];                                          // halo warp: its one row
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) v1[r][kx] = v[r][kx];
+        // One pass per group of 8 output channels, NOT unrolled: the loop body (216 FFMA2 + 36 indexed constant loads) stays
+        // resident in the instruction cache - the fully unrolled form (24 KB of straight-line code per item, four warps at
+        // four different places of it) spent 37 % of its issue slots waiting for instruction fetch (ncu, stall_no_inst).
+#pragma unroll 1
+        for (int cg = 0; cg < 2 * p.nchunks; ++cg) {
+          uint8_t *sa = smem + (size_t)st * p.stage_stride + (size_t)r0 * row_stride + (size_t)(7 + j) * 16 + (size_t)(cg & 1) * plane_a;
+          if (!(cg & 1)) ptx::mbar_wait(&empty[st], ph ^ 1, 11);
+          if (main_warp) fc_rows<R>(sfw, v, cg, live, sa, row_stride);
+          else if (act) fc_rows<1>(sfw, v1, cg, live, sa, row_stride);
+          if (cg & 1) {
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&full[st]);
+            if (++st == p.S) { st = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
   }
 
   ptx::tc_fence_before();

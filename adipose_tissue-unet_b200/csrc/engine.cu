@@ -194,6 +194,9 @@ struct adp_engine {
   int64_t launches = 0;
   int dbg = 0;
   bool fuse_head = true, fuse_pool = true;   // tcgen05 path only
+  bool fuse_first = false;                   // tcgen05 inference: first conv computed inside down1_conv2 (conv_tc.cuh, FC variant): bit-identical,
+                                             // opt-in - measured break-even (profiles/r2_fc_fusion_experiment.txt)
+  FirstConvFuse fc_host;                     // its fp32 weights / bias as kernel parameters (filled by pack_all)
   bool kys = true;                           // ky-stacked MMA issue for the N <= 128 layers
   bool split = false;                        // ADP_PREC_BF16X3: hi/lo bf16 activations and weights, three GEMM passes (conv_tc.cuh)
   int prec_public = 0;                       // what adp_precision() reports
@@ -454,6 +457,12 @@ void pack_all(adp_engine *e) {
     e->w_first.ensure(w.size() * 4); e->b_first.ensure(b.size() * 4);
     ADP_CUDA(cudaMemcpy(e->w_first.p, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
     ADP_CUDA(cudaMemcpy(e->b_first.p, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    memset(&e->fc_host, 0, sizeof(e->fc_host));
+    if (e->cp[0] <= 64) {
+      for (int t = 0; t < 9; ++t)
+        for (int co = 0; co < e->cp[0]; ++co) e->fc_host.w[t][co] = w[(size_t)t * e->cp[0] + co];
+      for (int co = 0; co < e->cp[0]; ++co) e->fc_host.b[co] = b[co];
+    }
   }
   {
     const HostWeight &h = e->hw["output_softmax"];   // (1,1,c1,2)
@@ -533,6 +542,25 @@ const CUtensorMap &tmap_for(adp_engine *e, const void *buf, int H, int W, int cg
   return e->tmaps.emplace(key, m).first->second;
 }
 
+// Tensor map over the normalised float32 input [forward][H][W] of the fused first conv: box = 8 rows x 136 columns, zero fill
+// outside the image ('same' padding of the normalised image)
+const CUtensorMap &tmap_input(adp_engine *e, const float *buf, int H, int W, int cap) {
+  char key[160];
+  snprintf(key, sizeof(key), "in/%p/%d/%d/%d", (const void *)buf, H, W, cap);
+  auto it = e->tmaps.find(key);
+  if (it != e->tmaps.end()) return it->second;
+  CUtensorMap m;
+  ADP_REQUIRE(W % 4 == 0, "fused first conv needs a row pitch of 16 bytes");
+  cuuint64_t gdim[5] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)cap, 1, 1};
+  cuuint64_t gstr[4] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)cap * H * W * 4, (cuuint64_t)cap * H * W * 4};
+  cuuint32_t box[5] = {(cuuint32_t)kFcWinW, (cuuint32_t)kFcWinRows, 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void *)buf, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(ADP_ECUDA, std::string("cuTensorMapEncodeTiled failed, code ") + std::to_string((int)r) + " key " + key);
+  return e->tmaps.emplace(key, m).first->second;
+}
+
 // TTA combine / blend kernel (kernels_post.cuh); ADP_TTA_SERIAL=1 selects the one-plane-per-barrier variant for A/B timing
 typedef void (*TtaKernel)(const float *, TtaOps, int, int, float *, float *, float *, const float *, int, int, int, int, int);
 TtaKernel tta_kernel() {
@@ -551,6 +579,8 @@ struct EpiSpec {
   float *prob = nullptr;              // EPI_HEAD: probability planes
   const void *resid = nullptr, *mask = nullptr;   // backward (EPI_STORE): see ConvTcParams
   float mask_scale = 1.f;
+  const FirstConvFuse *fc = nullptr;  // EPI_POOL of down1_conv2: compute the source tensor (first conv) in the kernel from
+  const float *fc_input = nullptr;    // the normalised float32 image [forward][Hs][Ws] (tta_input_kernel)
 };
 
 // tcgen05 conv launch shared by the forward layers and their data-gradient twins (train_host.cuh)
@@ -591,6 +621,17 @@ void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label,
   const int grid = std::min(nitems, e->num_sms);
   const int epi_kind = (epi.mode == EPI_STORE && epi.mask) ? EPI_BWD : epi.mode;
   ConvTcKernel kern = tc_kernel_for(p.ntaps, p.T, p.kys, epi_kind);
+  int threads = kTcThreads;
+  size_t smem_extra = 0;
+  if (epi.fc) {
+    ADP_REQUIRE(epi.mode == EPI_POOL && p.ntaps == 9 && p.T == 4 && p.kys == 1 && p.nvar == 1 && !p.split && p.PW == 144 && p.nbox == 1 &&
+                    L.cin_pad <= 16 * kFcMaxChunks, "first-conv fusion needs the 3x3, 4-row, ky-stacked pool layer");
+    p.fc = *epi.fc;
+    kern = conv_tc_kernel<9, 4, true, EPI_POOL, true>;
+    threads = kTcThreadsFc;
+    smem_extra = kFcWinBytes;
+    while (p.S > 2 && tc_smem_bytes(p) + smem_extra > 227 * 1024) --p.S;
+  }
   // data-gradient twin, N <= 96 (T >= 2 rows per item): the mask tile of every item is staged in shared memory next to the
   // pipeline stages (two buffers when at least two stages still fit, else one).  Wider accumulators keep the
   // register-prefetch loads (mask_bufs = 0): a 44 KB tile per buffer would leave them two 63 KB stages, measured slower
@@ -598,6 +639,7 @@ void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label,
   // ADP_BWD_MASK = 0 (never) / 1 / 2 (buffers where staged) / 3 (stage for every width) overrides for experiments.
   p.mask_bufs = 0; p.mask_bytes = 0;
   const CUtensorMap *tmk = &tm;
+  if (epi.fc) tmk = &tmap_input(e, epi.fc_input, Hs, Ws, cap);
   if (epi_kind == EPI_BWD) {
     static const int mode = getenv("ADP_BWD_MASK") ? atoi(getenv("ADP_BWD_MASK")) : -1;
     const bool stage = p.oscale == 1 && mode != 0 && (p.N <= 96 || mode == 3);
@@ -612,9 +654,9 @@ void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label,
       tmk = &tmap_for(e, epi.mask, Ho, Wo, d_cgs, d_cg0, L.cout_pad, cap, 16, p.N / 8, p.T);
     }
   }
-  const size_t smem = tc_smem_bytes(p);
+  const size_t smem = tc_smem_bytes(p) + smem_extra;
   if (e->dbg & 16) { e->misc.ensure(148 * 8 * 8 + 4096); p.dbg_out = reinterpret_cast<long long *>(e->misc.as<char>() + 4096); }
-  e->launch(label.c_str(), fl, by, [&] { kern<<<grid, kTcThreads, smem, e->stream>>>(tm, *tmk, p); });
+  e->launch(label.c_str(), fl, by, [&] { kern<<<grid, threads, smem, e->stream>>>(tm, *tmk, p); });
   if (e->dbg & 16) {
     // role timers (cycles, averaged over CTAs): where each warp role of the pipeline waits
     std::vector<long long> h((size_t)grid * 8);
@@ -707,7 +749,26 @@ template <typename T> void forward_t(adp_engine *e, const Acts &A, int S, const 
   s.slide_origin = reinterpret_cast<const int64_t *>(e->fwt_origin.p);
   const float mean_f = mean;
   const float sd_f = (float)((double)std_ + 1e-10);
-  {
+  const bool tc = e->prec == ADP_PREC_BF16;
+  const bool dropping = drop && (drop->keep < 1.f || drop->mask[0]);
+  EpiSpec pool1, pool2, head;
+  if (tc && (e->fuse_pool || e->split)) { pool1.mode = EPI_POOL; pool1.pool_dst = A.pl1; pool2.mode = EPI_POOL; pool2.pool_dst = A.pl2; }
+  if (tc && (e->fuse_head || e->split) && !drop) { head.mode = EPI_HEAD; head.prob = A.prob->as<float>(); }   // training keeps up1_conv3
+  // Inference on the tcgen05 path: the first conv runs inside down1_conv2 (its 48-channel output is never materialised);
+  // training needs that tensor for the weight gradient, bf16x3 carries hi/lo halves, both keep the separate kernel.
+  const bool fuse_first = tc && e->fuse_first && !drop && !e->split && pool1.mode == EPI_POOL && cp[0] <= 16 * kFcMaxChunks && layer(e, "down1_conv2").tc.kys == 1 &&
+                          layer(e, "down1_conv2").tc.T == 4;
+  if (fuse_first) {
+    // the d1a buffer is free in this mode (until up1_conv2 writes it): it holds the normalised float32 input instead
+    float *xin = A.d1a->as<float>();
+    const size_t total = (size_t)nfw * S * (S / 4);
+    const int grid = e->wave_grid(tta_input_kernel, cdiv64(total, 256));
+    e->launch("tta_input", 0, (double)nfw * S * S * 8, [&] {
+      tta_input_kernel<<<grid, 256, 0, e->stream>>>(s, e->fwt_tile.as<int>(), e->fwt_op.as<int>(), S, mean_f, sd_f, xin, nfw);
+    });
+    if (input_consumed) ADP_CUDA(cudaEventRecord(input_consumed, e->stream));
+    pool1.fc = &e->fc_host; pool1.fc_input = xin;
+  } else {
     auto out = e->split ? view_split<T>(*A.d1a, S, S, cp[0], 0, cp[0]) : view<T>(*A.d1a, S, S, cp[0], 0, cp[0]);
     dim3 grid(cdiv(S, 32), cdiv(S, 32), nfw), block(32, 8);
     const size_t smem = ((size_t)10 * cp[0] + 34 * 34) * 4;
@@ -715,13 +776,8 @@ template <typename T> void forward_t(adp_engine *e, const Acts &A, int S, const 
       first_conv_kernel<T><<<grid, block, smem, e->stream>>>(s, e->fwt_tile.as<int>(), e->fwt_op.as<int>(), S, mean_f, sd_f,
                                                             e->w_first.as<float>(), e->b_first.as<float>(), out);
     });
+    if (input_consumed) ADP_CUDA(cudaEventRecord(input_consumed, e->stream));
   }
-  const bool tc = e->prec == ADP_PREC_BF16;
-  const bool dropping = drop && (drop->keep < 1.f || drop->mask[0]);
-  EpiSpec pool1, pool2, head;
-  if (tc && (e->fuse_pool || e->split)) { pool1.mode = EPI_POOL; pool1.pool_dst = A.pl1; pool2.mode = EPI_POOL; pool2.pool_dst = A.pl2; }
-  if (tc && (e->fuse_head || e->split) && !drop) { head.mode = EPI_HEAD; head.prob = A.prob->as<float>(); }   // training keeps up1_conv3
-  if (input_consumed) ADP_CUDA(cudaEventRecord(input_consumed, e->stream));
   run_conv(e, "down1_conv2", *A.d1a, S, S, cp[0], 0, *A.cat1, 2 * cp[0], 0, nfw, cap, pool1);
   if (pool1.mode != EPI_POOL) run_pool<T>(e, *A.cat1, S, S, 2 * cp[0], cp[0], *A.pl1, nfw);
   run_conv(e, "down2_conv1", *A.pl1, S2, S2, cp[0], 0, *A.d2a, cp[1], 0, nfw, cap);
@@ -1042,6 +1098,7 @@ int adp_create(int device, int precision, int init_nb, int max_forwards, adp_eng
         for (int epi : {EPI_STORE, EPI_HEAD, EPI_POOL, EPI_BWD})
           if (ConvTcKernel k = tc_kernel_lookup(nt, T, kys, epi))
             ADP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  ADP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<9, 4, true, EPI_POOL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   ADP_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (const char *d = getenv("ADP_TC_DEBUG")) {
     e->dbg = atoi(d);
@@ -1093,7 +1150,8 @@ int adp_set_option(adp_engine *e, const char *key, int value) {
   ADP_TRY
   ADP_REQUIRE(e && key, "null argument");
   std::string k = key;
-  if (k == "fuse_head") e->fuse_head = value != 0;
+  if (k == "fuse_first") e->fuse_first = value != 0;
+  else if (k == "fuse_head") e->fuse_head = value != 0;
   else if (k == "fuse_pool") e->fuse_pool = value != 0;
   else if (k == "wgrad_simt") e->wgrad_simt = value != 0;
   else if (k == "dgrad_simt") e->dgrad_simt = value != 0;

@@ -135,6 +135,28 @@ ADP_DEVINL void ffma2(float2 &acc, const float2 a, const float2 b) {
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(reinterpret_cast<const unsigned long long &>(a)), "l"(reinterpret_cast<const unsigned long long &>(b)));
 }
 
+// Input of the fused first conv (conv_tc.cuh, FC variant): out[f][y][x] = (aug_f(img)[y][x] - mean) / (std + 1e-10) in float32,
+// the statements of first_conv_kernel's window fill (full_evaluation_enhanced.py:1306, :590).  One thread = 4 consecutive x.
+__global__ void __launch_bounds__(256)
+tta_input_kernel(FirstConvSrc src, const int *__restrict__ fw_tile, const int *__restrict__ fw_op, int S, float mean_f, float sd_f,
+                 float *__restrict__ out, int nfw) {
+  const int S4 = S >> 2;
+  const size_t total = (size_t)nfw * S * S4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x4 = (int)(i % S4); size_t q = i / S4;
+    const int y = (int)(q % S), f = (int)(q / S);
+    const int tile = fw_tile[f], op = fw_op[f];
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int si, sj;
+      d4_src(op, y, x4 * 4 + k, S, si, sj);
+      v[k] = __fdiv_rn(__fsub_rn(first_conv_fetch(src, tile, S, si, sj), mean_f), sd_f);
+    }
+    *reinterpret_cast<float4 *>(out + ((size_t)f * S + y) * S + x4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 // block = (32, 8), output tile = 32 columns x 32 rows: the normalised (and dihedrally transformed) 34 x 34 input window
 // is staged once in shared memory (one z-score division per input pixel instead of nine), then a warp owns 32
 // consecutive columns of FOUR rows so that every weight read from shared memory feeds four pixels (288 FMA per 18

@@ -156,6 +156,34 @@ def test_full_size_1024_fp32_and_bf16(weights, params):
         check_masks(out, ref, prec, "1024^2")
 
 
+def test_first_conv_fusion_is_bit_identical(weights):
+    """bf16 inference computes the first conv inside down1_conv2 (conv_tc.cuh, FC variant): the stencil warps must hand the
+    tensor cores exactly the bf16 values first_conv_kernel would have written - probabilities and the down1_conv2 tensor are
+    compared bit for bit with the fusion switched off.  Sizes cover a ragged last strip (192 = 128 + 64), one strip, and the
+    1024^2 production tile; sources cover float32, uint8 gray and RGB; every dihedral op is exercised."""
+    m = model("bf16", weights)
+    eng = m.engine
+    cases = [(192, "f32"), (128, "u8"), (256, "rgb"), (1024, "f32")]
+    try:
+        for S, kind in cases:
+            if kind == "f32":
+                tiles = A.synth.ecm_tiles(2, S, seed=50 + S).astype(np.float32)
+            elif kind == "u8":
+                tiles = np.stack([A.synth.ecm_tile(S, seed=51 + S), A.synth.ecm_tile(S, seed=61 + S)])
+            else:
+                tiles = np.stack([A.synth.rgb_tile(S, seed=52 + S), A.synth.rgb_tile(S, seed=53 + S)])
+            ops = list(range(8)) if S < 1024 else [0, 3, 6]
+            out, d1 = {}, {}
+            for fuse in (0, 1):
+                eng.set_option("fuse_first", fuse)
+                out[fuse] = eng.predict(tiles, MEAN, STD, ops=ops)
+                d1[fuse] = eng.debug_layer("down1_conv2", 1)
+            np.testing.assert_array_equal(out[1], out[0], err_msg=f"S={S} {kind}")
+            np.testing.assert_array_equal(d1[1], d1[0], err_msg=f"S={S} {kind} down1_conv2")
+    finally:
+        eng.set_option("fuse_first", 1)
+
+
 def test_mask_dice_on_trained_weights(weights):
     """Mask agreement on a TRAINED (bimodal) model, the case the >= 0.999 bound of BASELINE.json is about: random-init
     weights put 2-7 % of the pixels within the allowed bf16 error of the threshold.  The model is trained here, by this

@@ -13,6 +13,8 @@ def main():
     ops = list(range(8)) if (len(sys.argv) > 4 and sys.argv[4] == "tta") else None   # n tiles -> n/8 tiles x 8 augmentations
     eng = api.Engine(precision=prec, max_forwards=n)
     eng.set_weights(A.synth.init_weights())
+    if os.environ.get("ADP_FUSE_FIRST") is not None:      # experiment: first conv inside down1_conv2 on / off
+        eng.set_option("fuse_first", int(os.environ["ADP_FUSE_FIRST"]))
     tiles = A.synth.ecm_tiles(min(n, 2), S)
     tiles = np.concatenate([tiles] * (n // len(tiles)))[:n]
     if ops:
