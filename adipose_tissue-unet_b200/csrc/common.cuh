@@ -41,6 +41,15 @@ template <typename T> ADP_DEVINL T from_f(float v);
 template <> ADP_DEVINL float from_f<float>(float v) { return v; }
 template <> ADP_DEVINL __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// Counter-based dropout hash (kernels_train.cuh: dropout kernels; conv_tc.cuh: fused into the conv epilogue)
+__host__ __device__ inline uint32_t hash_u32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+// salt = hash(high half of the element index ^ high half of the seed) ^ low half of the seed: constant over a launch whenever
+// the index fits 32 bits (hoisted out of the element loop - the kernel was issue-bound on two hashes per channel pair)
+__host__ __device__ inline uint32_t dropout_salt(uint64_t seed, uint32_t idx_hi) { return hash_u32(idx_hi ^ (uint32_t)(seed >> 32)) ^ (uint32_t)seed; }
+
 // Dihedral source index: aug[i][j] = img[src(i,j)]  (op codes in adipose_b200.h)
 ADP_DEVINL void d4_src(int op, int i, int j, int n, int &si, int &sj) {
   // branch-free: 3 bits per op = (transpose, mirror the row index, mirror the column index)

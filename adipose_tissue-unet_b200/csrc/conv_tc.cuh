@@ -122,6 +122,11 @@ struct ConvTcParams {
   // cycles per item with the loads, 6.3 k without).  mask_bufs = 0 keeps the register-prefetch loads (wide accumulators)
   int mask_bufs;                 // 0, 1 or 2
   uint32_t mask_bytes;           // T * N * 256
+  // Dropout fused into the EPI_STORE epilogue (training forward, hash masks): exactly dropout_dense_kernel on the stored
+  // tensor - the value is rounded to bf16, multiplied by 1/keep or zeroed by the hash of its 8-channel group index
+  // (= element offset / 8 of the dense output tensor), and rounded again.  drop_thr = 0: off.
+  uint32_t drop_thr, drop_salt;
+  float drop_inv;
   FirstConvFuse fc;              // FC variant only
 };
 
@@ -257,6 +262,17 @@ ADP_DEVINL void store16_bf16(__nv_bfloat16 *o, size_t plane, const float (&f)[16
   for (int i = 0; i < 16; ++i) h[i] = __float2bfloat16_rn(f[i]);
   *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<uint4 *>(h);
   *reinterpret_cast<uint4 *>(o + plane) = *reinterpret_cast<uint4 *>(h + 8);
+}
+
+// dropout_dense_kernel's arithmetic on 8 channels held in registers (group index g of the dense tensor)
+ADP_DEVINL void dropout8(float *f, uint32_t g, uint32_t thr, float inv, uint32_t salt0) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t h = hash_u32((g * 4u + (uint32_t)q) * 0x9E3779B1u ^ salt0);
+    const float a = __bfloat162float(__float2bfloat16_rn(f[2 * q])), b = __bfloat162float(__float2bfloat16_rn(f[2 * q + 1]));
+    f[2 * q] = (h & 0xFFFFu) < thr ? a * inv : 0.f;
+    f[2 * q + 1] = (h >> 16) < thr ? b * inv : 0.f;
+  }
 }
 
 // hi/lo store of the bf16x3 precision: lo_elems = element distance between a value's hi and lo halves (0 = plain bf16)
@@ -670,6 +686,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               load16_bf16(p.mask + (o - p.out), plane, m);
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = m[i] > 0.f ? f[i] * p.mask_scale : 0.f;
+            }
+            if (p.drop_thr) {
+              const uint32_t g = (uint32_t)((size_t)(o - p.out) >> 3);
+              dropout8(f, g, p.drop_thr, p.drop_inv, p.drop_salt);
+              dropout8(f + 8, g + (uint32_t)(plane >> 3), p.drop_thr, p.drop_inv, p.drop_salt);
             }
             store16_out(o, (size_t)p.out_lo * plane, plane, f);
           }

@@ -194,6 +194,7 @@ struct adp_engine {
   int64_t launches = 0;
   int dbg = 0;
   bool fuse_head = true, fuse_pool = true;   // tcgen05 path only
+  bool fuse_dropout = true;                  // tcgen05 training forward: hash dropout applied in the producing conv's epilogue
   bool fuse_first = false;                   // tcgen05 inference: first conv computed inside down1_conv2 (conv_tc.cuh, FC variant): bit-identical,
                                              // opt-in - measured break-even (profiles/r2_fc_fusion_experiment.txt)
   FirstConvFuse fc_host;                     // its fp32 weights / bias as kernel parameters (filled by pack_all)
@@ -579,6 +580,8 @@ struct EpiSpec {
   float *prob = nullptr;              // EPI_HEAD: probability planes
   const void *resid = nullptr, *mask = nullptr;   // backward (EPI_STORE): see ConvTcParams
   float mask_scale = 1.f;
+  float drop_keep = 1.f;              // EPI_STORE, training forward: hash dropout of the stored tensor fused into the epilogue
+  uint64_t drop_seed = 0;             // (keep < 1: on; the output must be a dense tensor whose pair index fits 32 bits)
   const FirstConvFuse *fc = nullptr;  // EPI_POOL of down1_conv2: compute the source tensor (first conv) in the kernel from
   const float *fc_input = nullptr;    // the normalised float32 image [forward][Hs][Ws] (tta_input_kernel)
 };
@@ -606,6 +609,14 @@ void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label,
   p.resid = reinterpret_cast<const __nv_bfloat16 *>(epi.resid);
   p.mask = reinterpret_cast<const __nv_bfloat16 *>(epi.mask);
   p.mask_scale = epi.mask_scale;
+  p.drop_thr = 0; p.drop_salt = 0; p.drop_inv = 1.f;
+  if (epi.drop_keep < 1.f) {
+    ADP_REQUIRE(epi.mode == EPI_STORE && !epi.mask && !p.split && d_cg0 == 0 && d_cgs * 8 == L.cout_pad &&
+                    (size_t)nb * Ho * Wo * d_cgs * 4 <= 0xFFFFFFFFull, "fused dropout needs a dense bf16 output tensor");
+    p.drop_thr = (uint32_t)fminf(epi.drop_keep * 65536.f, 65536.f);
+    p.drop_inv = 1.f / epi.drop_keep;
+    p.drop_salt = dropout_salt(epi.drop_seed, 0u);
+  }
   if (epi.mode == EPI_HEAD) {
     ADP_REQUIRE(p.T >= 2 && p.nvar == 1 && p.N == e->cp[0], "head fusion needs the 44-channel full-resolution layer");
     p.head_w = e->w_head.as<float>(); p.head_b = e->b_head.as<float>(); p.prob = epi.prob;
@@ -751,6 +762,17 @@ template <typename T> void forward_t(adp_engine *e, const Acts &A, int S, const 
   const float sd_f = (float)((double)std_ + 1e-10);
   const bool tc = e->prec == ADP_PREC_BF16;
   const bool dropping = drop && (drop->keep < 1.f || drop->mask[0]);
+  // training forward on the tcgen05 path: the four Dropout sites run inside the epilogue of the conv that produces the tensor
+  // (same hash, same roundings as dropout_dense_kernel: bit-identical) unless parity tests supply explicit masks
+  auto drop_fused = [&](int site, int H, int C) {
+    return dropping && tc && e->fuse_dropout && !drop->mask[site] && drop->keep < 1.f && (size_t)nfw * H * H * (C / 8) * 4 <= 0xFFFFFFFFull;
+  };
+  auto drop_epi = [&](int site) {
+    EpiSpec ep;
+    ep.drop_keep = drop->keep;
+    ep.drop_seed = drop->seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(site + 1);
+    return ep;
+  };
   EpiSpec pool1, pool2, head;
   if (tc && (e->fuse_pool || e->split)) { pool1.mode = EPI_POOL; pool1.pool_dst = A.pl1; pool2.mode = EPI_POOL; pool2.pool_dst = A.pl2; }
   if (tc && (e->fuse_head || e->split) && !drop) { head.mode = EPI_HEAD; head.prob = A.prob->as<float>(); }   // training keeps up1_conv3
@@ -786,8 +808,11 @@ template <typename T> void forward_t(adp_engine *e, const Acts &A, int S, const 
   run_conv(e, "down3_conv1", *A.pl2, S3, S3, cp[1], 0, *A.d3a, cp[2], 0, nfw, cap);
   run_conv(e, "down3_conv2", *A.d3a, S3, S3, cp[2], 0, *A.cat3, 2 * cp[2], 0, nfw, cap);
   run_pool<T>(e, *A.cat3, S3, S3, 2 * cp[2], cp[2], *A.pl3, nfw);
-  run_conv(e, "dilate1", *A.pl3, S4, S4, cp[2], 0, *A.t[0], cp[3], 0, nfw, cap);
-  if (dropping) run_dropout<T>(e, *A.t[0], S4, cp[3], c[3], nfw, *drop, 0);
+  if (drop_fused(0, S4, cp[3])) run_conv(e, "dilate1", *A.pl3, S4, S4, cp[2], 0, *A.t[0], cp[3], 0, nfw, cap, drop_epi(0));
+  else {
+    run_conv(e, "dilate1", *A.pl3, S4, S4, cp[2], 0, *A.t[0], cp[3], 0, nfw, cap);
+    if (dropping) run_dropout<T>(e, *A.t[0], S4, cp[3], c[3], nfw, *drop, 0);
+  }
   const char *dn[5] = {"dilate2", "dilate3", "dilate4", "dilate5", "dilate6"};
   for (int i = 0; i < 5; ++i) run_conv(e, dn[i], *A.t[i], S4, S4, cp[3], 0, *A.t[i + 1], cp[3], 0, nfw, cap);
   if (e->split) {
@@ -810,16 +835,25 @@ template <typename T> void forward_t(adp_engine *e, const Acts &A, int S, const 
   }
   run_conv(e, "up3_conv1", *A.ts, S4, S4, cp[3], 0, *A.cat3, 2 * cp[2], cp[2], nfw, cap);
   run_conv(e, "up3_conv2", *A.cat3, S3, S3, 2 * cp[2], 0, *A.u3b, cp[2], 0, nfw, cap);
-  run_conv(e, "up3_conv3", *A.u3b, S3, S3, cp[2], 0, *A.u3c, cp[2], 0, nfw, cap);
-  if (dropping) run_dropout<T>(e, *A.u3c, S3, cp[2], c[2], nfw, *drop, 1);
+  if (drop_fused(1, S3, cp[2])) run_conv(e, "up3_conv3", *A.u3b, S3, S3, cp[2], 0, *A.u3c, cp[2], 0, nfw, cap, drop_epi(1));
+  else {
+    run_conv(e, "up3_conv3", *A.u3b, S3, S3, cp[2], 0, *A.u3c, cp[2], 0, nfw, cap);
+    if (dropping) run_dropout<T>(e, *A.u3c, S3, cp[2], c[2], nfw, *drop, 1);
+  }
   run_conv(e, "up2_conv1", *A.u3c, S3, S3, cp[2], 0, *A.cat2, 2 * cp[1], cp[1], nfw, cap);
   run_conv(e, "up2_conv2", *A.cat2, S2, S2, 2 * cp[1], 0, *A.u2b, cp[1], 0, nfw, cap);
-  run_conv(e, "up2_conv3", *A.u2b, S2, S2, cp[1], 0, *A.u2c, cp[1], 0, nfw, cap);
-  if (dropping) run_dropout<T>(e, *A.u2c, S2, cp[1], c[1], nfw, *drop, 2);
+  if (drop_fused(2, S2, cp[1])) run_conv(e, "up2_conv3", *A.u2b, S2, S2, cp[1], 0, *A.u2c, cp[1], 0, nfw, cap, drop_epi(2));
+  else {
+    run_conv(e, "up2_conv3", *A.u2b, S2, S2, cp[1], 0, *A.u2c, cp[1], 0, nfw, cap);
+    if (dropping) run_dropout<T>(e, *A.u2c, S2, cp[1], c[1], nfw, *drop, 2);
+  }
   run_conv(e, "up1_conv1", *A.u2c, S2, S2, cp[1], 0, *A.cat1, 2 * cp[0], cp[0], nfw, cap);
   run_conv(e, "up1_conv2", *A.cat1, S, S, 2 * cp[0], 0, *A.u1b, cp[0], 0, nfw, cap);
-  run_conv(e, "up1_conv3", *A.u1b, S, S, cp[0], 0, *A.u1c, cp[0], 0, nfw, cap, head);
-  if (dropping) run_dropout<T>(e, *A.u1c, S, cp[0], c[0], nfw, *drop, 3);
+  if (drop_fused(3, S, cp[0]) && head.mode != EPI_HEAD) run_conv(e, "up1_conv3", *A.u1b, S, S, cp[0], 0, *A.u1c, cp[0], 0, nfw, cap, drop_epi(3));
+  else {
+    run_conv(e, "up1_conv3", *A.u1b, S, S, cp[0], 0, *A.u1c, cp[0], 0, nfw, cap, head);
+    if (dropping) run_dropout<T>(e, *A.u1c, S, cp[0], c[0], nfw, *drop, 3);
+  }
   if (head.mode != EPI_HEAD) {
     auto in = view<T>(*A.u1c, S, S, cp[0], 0, cp[0]);
     const size_t total = (size_t)nfw * S * S;
@@ -1151,6 +1185,7 @@ int adp_set_option(adp_engine *e, const char *key, int value) {
   ADP_REQUIRE(e && key, "null argument");
   std::string k = key;
   if (k == "fuse_first") e->fuse_first = value != 0;
+  else if (k == "fuse_dropout") e->fuse_dropout = value != 0;
   else if (k == "fuse_head") e->fuse_head = value != 0;
   else if (k == "fuse_pool") e->fuse_pool = value != 0;
   else if (k == "wgrad_simt") e->wgrad_simt = value != 0;

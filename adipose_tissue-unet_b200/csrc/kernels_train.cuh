@@ -105,13 +105,7 @@ __global__ void __launch_bounds__(256) relu_mask_kernel(View<T> g, View<T> x, in
 // from a counter-based hash (TF's RNG stream cannot be reproduced; parity tests supply masks instead).
 // One 32-bit murmur3-finalizer hash decides TWO channels (16 bits each: P(keep) is keep rounded to 1/65536), so a
 // group of 8 channels costs four short integer hashes and the kernel stays HBM-bound.
-ADP_DEVINL uint32_t hash_u32(uint32_t h) {
-  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
-  return h;
-}
-// salt = hash(high half of the element index ^ high half of the seed) ^ low half of the seed: constant over a launch whenever
-// the index fits 32 bits (hoisted out of the element loop - the kernel was issue-bound on two hashes per channel pair)
-ADP_DEVINL uint32_t dropout_salt(uint64_t seed, uint32_t idx_hi) { return hash_u32(idx_hi ^ (uint32_t)(seed >> 32)) ^ (uint32_t)seed; }
+// (hash_u32 / dropout_salt live in common.cuh: the tcgen05 conv epilogue applies the same mask when the dropout is fused)
 ADP_DEVINL uint32_t dropout_bits(uint64_t seed, size_t group_index, int pair, uint32_t salt0) {
   const uint64_t idx = (uint64_t)group_index * 4u + (uint64_t)pair;
   const uint32_t hi = (uint32_t)(idx >> 32);

@@ -315,3 +315,34 @@ def test_tensor_core_weight_gradients_are_bit_reproducible(weights):
         print(k, "max run-to-run difference", float(np.abs(g1[k] - g2[k]).max()), "of", float(np.abs(g1[k]).max()))
         assert np.allclose(g1[k], g2[k], rtol=1e-4, atol=1e-6 * float(np.abs(g1[k]).max()))
     eng.train_end(); eng.close()
+
+
+def test_fused_dropout_is_bit_identical(weights):
+    """bf16 training forward applies the four Dropout sites in the epilogue of the conv that produces the tensor
+    (conv_tc.cuh, dropout8) instead of a separate in-place pass: same counter-based hash of the element's group index, same
+    two bf16 roundings - loss sums, probabilities and all generic gradients must equal the un-fused run bit for bit."""
+    n, S = 2, 256
+    x, y = batch(n, S, seed=43)
+    eng = api.Engine(precision="bf16", max_forwards=8)
+    eng.set_weights(weights)
+    eng.train_begin(n, S, dropout_rate=0.3, seed=11)
+    res = {}
+    for fuse in (0, 1):
+        eng.set_option("fuse_dropout", fuse)
+        sums = eng.train_forward(x, y)
+        probs = eng.train_probs()
+        eng.train_backward(sums)
+        res[fuse] = (np.array(sums, dtype=np.float64), eng.train_grads(), probs)
+    eng.set_option("fuse_dropout", 1)
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    generic = [k for k in res[0][1] if not k.startswith(("down1_conv1/", "output_softmax/"))]
+    for k in generic:
+        assert np.array_equal(res[0][1][k], res[1][1][k]), k
+    assert float(np.abs(res[0][0]).sum()) > 0
+    # the dropout really ran: a keep = 1 forward gives different sums
+    eng.train_end()
+    eng.train_begin(n, S, dropout_rate=0.0)
+    sums_nodrop = np.array(eng.train_forward(x, y), dtype=np.float64)
+    assert not np.array_equal(sums_nodrop, res[1][0])
+    eng.train_end(); eng.close()

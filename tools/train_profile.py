@@ -11,6 +11,8 @@ nb = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 prec = sys.argv[3] if len(sys.argv) > 3 else "bf16"
 eng = api.Engine(precision=prec, max_forwards=8)
 eng.set_weights(A.synth.init_weights())
+if os.environ.get("ADP_FUSE_DROPOUT") is not None:      # experiment: dropout in the conv epilogue on / off
+    eng.set_option("fuse_dropout", int(os.environ["ADP_FUSE_DROPOUT"]))
 eng.train_begin(nb, S, dropout_rate=0.3)
 rng = np.random.default_rng(0)
 x = rng.standard_normal((nb, S, S)).astype(np.float32)
@@ -18,10 +20,11 @@ y = (rng.random((nb, S, S)) < 0.3).astype(np.float32)
 for _ in range(2):
     eng.train_step(x, y, 1e-4)
 t0 = time.time()
-for _ in range(3):
+REPS = 10
+for _ in range(REPS):
     out = eng.train_step(x, y, 1e-4)
 eng.synchronize()
-dt = (time.time() - t0) / 3
+dt = (time.time() - t0) / REPS
 fl = 3 * A.layers.forward_flops(S) * nb
 print(f"train step S={S} nb={nb} {prec}: {dt*1e3:.1f} ms wall (host buffers), {nb/dt:.2f} tiles/s, ~{fl/dt/1e12:.0f} TFLOP/s (3x fwd flops), loss={out['loss']:.4f}")
 eng.profile(True)
