@@ -195,8 +195,9 @@ struct adp_engine {
   int dbg = 0;
   bool fuse_head = true, fuse_pool = true;   // tcgen05 path only
   bool fuse_dropout = true;                  // tcgen05 training forward: hash dropout applied in the producing conv's epilogue
-  bool fuse_first = false;                   // tcgen05 inference: first conv computed inside down1_conv2 (conv_tc.cuh, FC variant): bit-identical,
-                                             // opt-in - measured break-even (profiles/r2_fc_fusion_experiment.txt)
+  bool fuse_first = true;                    // tcgen05 inference: first conv computed inside down1_conv2 (conv_tc.cuh, FC variant): bit-identical;
+                                             // kernel time is break-even un-throttled, but 3.2 GB less HBM traffic per 16 forwards is worth
+                                             // +1.3 % in bench.py under the power cap (profiles/r2_fc_fusion_experiment.txt)
   FirstConvFuse fc_host;                     // its fp32 weights / bias as kernel parameters (filled by pack_all)
   bool kys = true;                           // ky-stacked MMA issue for the N <= 128 layers
   bool split = false;                        // ADP_PREC_BF16X3: hi/lo bf16 activations and weights, three GEMM passes (conv_tc.cuh)
@@ -1134,6 +1135,8 @@ int adp_create(int device, int precision, int init_nb, int max_forwards, adp_eng
             ADP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   ADP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<9, 4, true, EPI_POOL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   ADP_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (const char *f = getenv("ADP_FUSE_FIRST")) e->fuse_first = atoi(f) != 0;        // A/B runs of whole programs (bench.py)
+  if (const char *f = getenv("ADP_FUSE_DROPOUT")) e->fuse_dropout = atoi(f) != 0;
   if (const char *d = getenv("ADP_TC_DEBUG")) {
     e->dbg = atoi(d);
     if (e->dbg && !ADP_TC_DEBUG_BUILD) {
