@@ -173,14 +173,14 @@ ADP_DEVINL uint32_t relu_bf16x2(float lo, float hi) {
 
 // ---- FC variant: the first conv as an in-kernel producer of the A operand (see FirstConvFuse) ----
 // R consecutive rows x 8 channels (group cg) of the first conv at one column: acc = bias, then the nine taps in order with one
-// IEEE FMA each (the accumulation order of first_conv_kernel: bit-identical values), ReLU, round to bf16, one 16-byte shared
-// store per row into the pipeline stage.  The weights sit in shared memory (one broadcast LDS.128 per four weights = one
+// IEEE FMA each (the accumulation order of first_conv_kernel: bit-identical values), ReLU, round to bf16: one packed 16-byte
+// register quad per row, stored into the pipeline stage by the caller once the stage is free.  The weights sit in shared memory (one broadcast LDS.128 per four weights = one
 // wavefront: ~450 per item next to the ~4000 of the MMA operand fetch).  Measured alternatives (1024^2, 16 forwards, whole
 // kernel): weights as uniform-register FFMA2 operands from the parameter block, fully unrolled - 1.24 ms, 37 % of the stencil
 // warps' issue slots lost to instruction fetch (24 KB of straight-line code per item); indexed LDC.64 in this loop - 1.46 ms.
 template <int R>
-ADP_DEVINL void fc_rows(const float *__restrict__ ws /*[9][64] then bias[64], shared*/, const float (&v)[R + 2][3], int cg, uint32_t live_rows,
-                        uint8_t *dst, uint32_t row_stride) {
+ADP_DEVINL void fc_rows(const float *__restrict__ ws /*[9][64] then bias[64], shared*/, const float (*v)[3] /*R + 2 window rows*/, int cg,
+                        uint32_t live_rows, uint4 (&o)[R]) {
   float2 a[R][4];
   {
     const float4 b0 = *reinterpret_cast<const float4 *>(ws + 9 * 64 + cg * 8), b1 = *reinterpret_cast<const float4 *>(ws + 9 * 64 + cg * 8 + 4);
@@ -204,11 +204,10 @@ ADP_DEVINL void fc_rows(const float *__restrict__ ws /*[9][64] then bias[64], sh
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);                     // outside the image the operand is zero (what the TMA box fill gives)
+    o[r] = make_uint4(0u, 0u, 0u, 0u);                        // outside the image the operand is zero (what the TMA box fill gives)
     if ((live_rows >> r) & 1u)
-      o = make_uint4(relu_bf16x2(a[r][0].x, a[r][0].y), relu_bf16x2(a[r][1].x, a[r][1].y), relu_bf16x2(a[r][2].x, a[r][2].y),
-                     relu_bf16x2(a[r][3].x, a[r][3].y));
-    *reinterpret_cast<uint4 *>(dst + (size_t)r * row_stride) = o;
+      o[r] = make_uint4(relu_bf16x2(a[r][0].x, a[r][0].y), relu_bf16x2(a[r][1].x, a[r][1].y), relu_bf16x2(a[r][2].x, a[r][2].y),
+                        relu_bf16x2(a[r][3].x, a[r][3].y));
   }
 }
 
@@ -290,6 +289,13 @@ ADP_DEVINL void store16_out(__nv_bfloat16 *o, size_t lo_elems, size_t plane, con
   *reinterpret_cast<uint4 *>(o + lo_elems + plane) = *reinterpret_cast<uint4 *>(l + 8);
 }
 
+// item -> (variant, image, row block, strip)
+ADP_DEVINL void decode_item(const ConvTcParams &p, int item, int &v, int &n, int &ty, int &tx) {
+  v = item % p.nvar; int q = item / p.nvar;
+  tx = q % p.ntx; q /= p.ntx;
+  ty = q % p.nty; n = q / p.nty;
+}
+
 template <int NTAPS, int T, bool KYS, int EPI, bool FC = false>
 __global__ void __launch_bounds__(FC ? kTcThreadsFc : kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmask, const __grid_constant__ ConvTcParams p) {
@@ -346,7 +352,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   const uint32_t tmem_base = *tmem_ptr;
 
   const int nitems = p.nb * p.nty * p.ntx * p.nvar;
-
+  const int item0 = (int)blockIdx.x, item_end = nitems, item_step = (int)gridDim.x;   // strips of an image row adjacent in time
   if (warp == 0) {
     // ---------------- producer: activation boxes (TMA) + weight block (bulk copy) per stage ----------------
     if (ptx::elect_one()) {
@@ -354,10 +360,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       long long t_w0 = 0; const long long t_start = clock64();
       int mit = 0;                                            // EPI_BWD: items whose mask tile has been requested
       const size_t blk_elems = p.b_bytes / 2;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int v = item % p.nvar; int q = item / p.nvar;
-        const int tx = q % p.ntx; q /= p.ntx;
-        const int ty = q % p.nty; const int n = q / p.nty;
+      for (int item = item0; item < item_end; item += item_step) {
+        int v, n, ty, tx;
+        decode_item(p, item, v, n, ty, tx);
         const int xg = tx * 16 - p.margin8, ys = ty * T + p.var[v].y0;
         const __nv_bfloat16 *w0 = p.wpk + (size_t)p.var[v].wbase * blk_elems;
         if (EPI == EPI_BWD && p.mask_bufs > 0) {
@@ -379,7 +384,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&empty[st], ph ^ 1, 1); if (tc_dbg(p, 16)) t_w0 += clock64() - tw; }
           // p.dbg (ADP_TC_DEBUG, timing experiments only - results are wrong): 2 = weights only for the first item,
           // 8 = activations only for the first item, 1 = no epilogue stores, 4 = one MMA per stage, 16 = role timers
-          const bool ld_b = !tc_dbg(p, 2) || item == (int)blockIdx.x, ld_a = !tc_dbg(p, 8) || item == (int)blockIdx.x;
+          const bool ld_b = !tc_dbg(p, 2) || item == item0, ld_a = !tc_dbg(p, 8) || item == item0;
           ptx::mbar_expect_tx(&full[st], ((ld_a && !FC) ? p.a_tx_bytes : 0u) + (ld_b ? p.b_bytes : 0u));
           int cgc = c * 2;                                     // first channel group of this chunk
           if (p.split) { const int cr = c / 3; cgc = cr * 2 + ((c - cr * 3) == 2 ? p.in_lo : 0); }
@@ -436,7 +441,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }
         const uint32_t id1 = p.idesc_stack[0], id2 = p.idesc_stack[1], id3 = p.idesc_stack[2];
         int it = 0;
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        for (int item = item0; item < item_end; item += item_step, ++it) {
           if (single_issuer ? issuer != 0 : (it & 1) != issuer) { skip_item(); continue; }
           const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
           { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3); if (tc_dbg(p, 16)) t_m0 += clock64() - tw; }
@@ -492,7 +497,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       }
       const uint32_t idesc = p.idesc;
       int it = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+      for (int item = item0; item < item_end; item += item_step, ++it) {
         if (single_issuer ? issuer != 0 : (it & 1) != issuer) { skip_item(); continue; }
         const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
         { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&acc_empty[buf], acc_ph ^ 1, 3); if (tc_dbg(p, 16)) t_m0 += clock64() - tw; }
@@ -528,11 +533,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const int NU = p.N >> 4;                                  // 16-column units per accumulator row
     long long t_e0 = 0; const long long t_estart = clock64();
     int it = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+    for (int item = item0; item < item_end; item += item_step, ++it) {
       const int buf = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
-      const int v = item % p.nvar; int q = item / p.nvar;
-      const int tx = q % p.ntx; q /= p.ntx;
-      const int ty = q % p.nty; const int n = q / p.nty;
+      int v, n, ty, tx;
+      decode_item(p, item, v, n, ty, tx);
       const int x = tx * 128 + q4 * 32 + lane;
       const float *sb = sbias + v * p.N;
       const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * T * p.N);
@@ -759,25 +763,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     // Item = T (= 4) output rows x 128 columns: the A box is 6 rows x 130 columns of the first conv's output (stage row r <->
     // image row ty*4 - 1 + r, box pixel 7 + j <-> image column tx*128 - 1 + j), which needs an 8 x 132 window of the input:
     // the producer thread lands it in shared memory with one TMA box per item (two buffers).  Warps 0..3 of the group own 32
-    // columns each - all six rows of a column in one thread, so every window value feeds up to nine FMAs from a register - and
+    // columns each - all rows of a column in one thread, so every window value feeds up to nine FMAs from a register - and
     // the fifth warp's first 12 lanes the two halo columns (one row each).
     if constexpr (FC) {
       const int sw = warp - 11;
       const uint32_t plane_a = (uint32_t)p.PW * 16u, row_stride = 2u * plane_a;
-      constexpr int R = 6;                                     // rows per thread of the main warps
       const bool main_warp = sw < 4;
       const bool act = main_warp || lane < 12;
       const int j = main_warp ? sw * 32 + lane : 128 + (lane & 1);        // box column 0..129
       const int r0 = (main_warp || !act) ? 0 : (lane >> 1);               // first box row of this thread
       int st = 0; uint32_t ph = 0; int it = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-        int q = item; const int tx = q % p.ntx; q /= p.ntx; const int ty = q % p.nty;
+      for (int item = item0; item < item_end; item += item_step, ++it) {
+        int vv, n, ty, tx;
+        decode_item(p, item, vv, n, ty, tx);
         const int wbuf = it & 1; const uint32_t wph = (uint32_t)(it >> 1) & 1u;
         const float *wb = swin + wbuf * (kFcWinRows * kFcWinW) + r0 * kFcWinW + j + (kFcWinX0 - 2);
-        float v[R + 2][3];
+        float v[8][3];
         ptx::mbar_wait(&mask_full[wbuf], wph, 14);
 #pragma unroll
-        for (int r = 0; r < R + 2; ++r)
+        for (int r = 0; r < 8; ++r)
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) v[r][kx] = (main_warp || r < 3) ? wb[r * kFcWinW + kx] : 0.f;
         __syncwarp();
@@ -786,21 +790,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         uint32_t live = 0;
         if (X >= 0 && X < p.Win)
 #pragma unroll
-          for (int r = 0; r < R; ++r) { const int Y = ty * T - 1 + r0 + r; live |= (Y >= 0 && Y < p.Hin) ? (1u << r) : 0u; }
-        float v1[3][3];                                          // halo warp: its one row
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) v1[r][kx] = v[r][kx];
-        // One pass per group of 8 output channels, NOT unrolled: the loop body (216 FFMA2 + 36 indexed constant loads) stays
-        // resident in the instruction cache - the fully unrolled form (24 KB of straight-line code per item, four warps at
-        // four different places of it) spent 37 % of its issue slots waiting for instruction fetch (ncu, stall_no_inst).
+          for (int r = 0; r < 6; ++r) { const int Y = ty * T - 1 + r0 + r; live |= (Y >= 0 && Y < p.Hin) ? (1u << r) : 0u; }
+        // One pass per group of 8 output channels, NOT unrolled: the loop body stays resident in the instruction cache - the
+        // fully unrolled form (24 KB of straight-line code per item, four warps at four different places of it) spent 37 % of
+        // its issue slots waiting for instruction fetch (ncu, stall_no_inst).  The FMAs of a pass run BEFORE the wait for the
+        // stage, so the tensor pipe's drain of that stage overlaps them.
 #pragma unroll 1
         for (int cg = 0; cg < 2 * p.nchunks; ++cg) {
-          uint8_t *sa = smem + (size_t)st * p.stage_stride + (size_t)r0 * row_stride + (size_t)(7 + j) * 16 + (size_t)(cg & 1) * plane_a;
-          if (!(cg & 1)) ptx::mbar_wait(&empty[st], ph ^ 1, 11);
-          if (main_warp) fc_rows<R>(sfw, v, cg, live, sa, row_stride);
-          else if (act) fc_rows<1>(sfw, v1, cg, live, sa, row_stride);
+          const uint32_t col = (uint32_t)(7 + j) * 16u + (uint32_t)(cg & 1) * plane_a;
+          uint8_t *sa = smem + (size_t)st * p.stage_stride + col;
+          if (main_warp) {
+            uint4 o[6];
+            fc_rows<6>(sfw, v, cg, live, o);
+            if (!(cg & 1)) ptx::mbar_wait(&empty[st], ph ^ 1, 11);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) *reinterpret_cast<uint4 *>(sa + (size_t)r * row_stride) = o[r];
+          } else {
+            uint4 o[1];
+            if (act) fc_rows<1>(sfw, v, cg, live, o);
+            if (!(cg & 1)) ptx::mbar_wait(&empty[st], ph ^ 1, 12);
+            if (act) *reinterpret_cast<uint4 *>(sa + (size_t)r0 * row_stride) = o[0];
+          }
           if (cg & 1) {
             ptx::fence_proxy_async();
             __syncwarp();
