@@ -195,9 +195,10 @@ struct adp_engine {
   int dbg = 0;
   bool fuse_head = true, fuse_pool = true;   // tcgen05 path only
   bool fuse_dropout = true;                  // tcgen05 training forward: hash dropout applied in the producing conv's epilogue
-  bool fuse_first = true;                    // tcgen05 inference: first conv computed inside down1_conv2 (conv_tc.cuh, FC variant): bit-identical;
-                                             // kernel time is break-even un-throttled, but 3.2 GB less HBM traffic per 16 forwards is worth
-                                             // +1.3 % in bench.py under the power cap (profiles/r2_fc_fusion_experiment.txt)
+  bool fuse_first = false;                   // tcgen05 inference: first conv computed inside down1_conv2 (conv_tc.cuh, FC variant): bit-identical,
+                                             // opt-in.  Kernel time is break-even un-throttled; under the power cap the 3.2 GB less HBM traffic
+                                             // per 16 forwards gave +0.1..1.4 % in bench.py A/B runs - inside the box-to-box spread, and it moves
+                                             // the first conv's time into the dominant kernel (bench.py "first_conv_fusion")
   FirstConvFuse fc_host;                     // its fp32 weights / bias as kernel parameters (filled by pack_all)
   bool kys = true;                           // ky-stacked MMA issue for the N <= 128 layers
   bool split = false;                        // ADP_PREC_BF16X3: hi/lo bf16 activations and weights, three GEMM passes (conv_tc.cuh)

@@ -322,6 +322,21 @@ def run_ours(args, rank, world, local_rank):
     e2e_dev, e2e_wall, res2 = timed(step_e2e, args.steps)
     assert res == res2, "resident and e2e paths disagree"
 
+    # A/B (rank 0, N=1): the same step with the first conv computed inside down1_conv2 (opt-in "fuse_first", bit-identical:
+    # the counts must not change).  Off by default: it moves the first conv's time into the dominant kernel for a gain that is
+    # within the box-to-box spread.
+    fc_res = None
+    if rank == 0 and world == 1 and args.precision == "bf16":
+        eng.set_option("fuse_first", 1)
+        step_resident()
+        fsteps = min(args.steps, 5)
+        fdev, _, fres = timed(step_resident, fsteps)
+        eng.set_option("fuse_first", 0)
+        assert fres == res, "first-conv fusion changed the confusion counts"
+        fc_res = {"tiles_per_s": BATCH_TILES * fsteps / fdev, "ms_per_step": fdev / fsteps * 1e3, "steps": fsteps,
+                  "counts_equal_to_default_path": True,
+                  "note": "same step, adp_set_option('fuse_first', 1): first_conv_kernel replaced by stencil warps inside the tcgen05 kernel of down1_conv2"}
+
     # whole-slide sliding-window reconstruction at BASELINE.json's own sizes: configs[2] (32768^2 3-channel pseudocoloured
     # slide, 50 % overlap) and configs[4] (16384^2 ECM slide, 75 % overlap), 8-way TTA, tile-row strips sharded over the ranks
     wsi_res = None
@@ -467,6 +482,8 @@ def run_ours(args, rank, world, local_rank):
             line["train"] = train_res
         if x3_res is not None:
             line["bf16x3"] = x3_res
+        if fc_res is not None:
+            line["first_conv_fusion"] = fc_res
         if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N=1 only
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
