@@ -212,6 +212,7 @@ ADP_DEVINL void fc_rows(const float *__restrict__ ws /*[9][64] then bias[64], sh
 }
 
 constexpr int EPI_STORE = 0, EPI_HEAD = 1, EPI_POOL = 2, EPI_BWD = 3;   // EPI_BWD = EPI_STORE with a mask (data-gradient twin)
+constexpr int EPI_UPSUM = 4;   // data-gradient twin of an upsampled conv: the 2x2 sum of UpSampling2D's backward in the epilogue
 
 // Software-pipelined walk over 16-column accumulator units u0, u0+step, ... < uend: the TMEM load
 // of the next unit is in flight while `body` works on the current one.
@@ -668,6 +669,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }
         }
       } else {
+      // EPI_UPSUM: the low-resolution mask / second-gradient words of the (at most four) units this warp owns are requested
+      // before the wait for the accumulator, so their latency overlaps the item's MMAs (even lanes own a 2x2 block)
+      constexpr int UPF = 4;
+      uint4 um[EPI == EPI_UPSUM ? UPF : 1][2], ur[EPI == EPI_UPSUM ? UPF : 1][2];
+      size_t up_off = 0, up_plane = 0;
+      bool up_live = false;
+      if constexpr (EPI == EPI_UPSUM) {
+        up_live = (ty * T + 1 < p.Hin) && (x < p.Win) && !(lane & 1) && !tc_dbg(p, 1);
+        up_plane = (size_t)(p.Wout >> 1) * 8;
+        up_off = (((size_t)n * (p.Hout >> 1) + ((ty * T) >> 1)) * p.pool_cgs + p.pool_cg0 + p.var[v].out_cg) * up_plane + (size_t)(x >> 1) * 8;
+#pragma unroll
+        for (int k = 0; k < UPF; ++k) {
+          const int cu = half + 2 * k;
+          um[k][0] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u); um[k][1] = um[k][0];      // "mask > 0" when there is no mask
+          ur[k][0] = make_uint4(0u, 0u, 0u, 0u); ur[k][1] = ur[k][0];
+          if (up_live && cu < NU) {
+            const size_t o = up_off + (size_t)(2 * cu) * up_plane;
+            if (p.mask) { um[k][0] = __ldg(reinterpret_cast<const uint4 *>(p.mask + o)); um[k][1] = __ldg(reinterpret_cast<const uint4 *>(p.mask + o + up_plane)); }
+            if (p.resid) { ur[k][0] = __ldg(reinterpret_cast<const uint4 *>(p.resid + o)); ur[k][1] = __ldg(reinterpret_cast<const uint4 *>(p.resid + o + up_plane)); }
+          }
+        }
+      }
       { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&acc_full[buf], acc_ph, 6); if (tc_dbg(p, 16)) t_e0 += clock64() - tw; }
       ptx::tc_fence_after();
       if constexpr (EPI == EPI_STORE) {
@@ -717,6 +740,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           const int y = ty * T + row;
           if (y < p.Hin && x < p.Win && !tc_dbg(p, 1))
             p.prob[((size_t)n * p.Hout + y) * p.Wout + x] = 1.f / (1.f + expf(zd + shead[p.N]));
+        }
+      } else if constexpr (EPI == EPI_UPSUM) {
+        // Data gradient of UpSampling2D + conv (T = 2): the full-resolution gradient is never written.  Each value is rounded to
+        // bf16 as the store would have done, the 2x2 block is summed in upsample2_bwd_kernel's pairwise order (column sums first),
+        // then the second gradient into the low-resolution tensor (deep-supervision head) is added and the ReLU' / dropout mask of
+        // the producing layer applied - the statements of upsample2_bwd_kernel, bit for bit.  pool_out = low-resolution gradient;
+        // resid / mask have its layout.
+        static_assert(EPI != EPI_UPSUM || T == 2, "the 2x2 sum needs one row pair per item");
+#pragma unroll
+        for (int k = 0; k < UPF; ++k) {
+          const int cu = half + 2 * k;
+          if (cu < NU) {
+            uint32_t ra[16], rb[16];
+            ptx::tmem_ld16_issue(t0 + (uint32_t)(cu * 16), ra);
+            ptx::tmem_ld16_issue(t0 + (uint32_t)(p.N + cu * 16), rb);
+            ptx::tmem_ld16_wait(ra);
+            ptx::tmem_ld16_wait(rb);
+            float fa[16], fb[16];
+            bias_relu16(ra, sb + cu * 16, p.relu, fa);
+            bias_relu16(rb, sb + cu * 16, p.relu, fb);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float t = __bfloat162float(__float2bfloat16_rn(fa[i])) + __bfloat162float(__float2bfloat16_rn(fb[i]));
+              fa[i] = t + __shfl_xor_sync(0xffffffffu, t, 1);       // even lane: (this column's two rows) + (the next column's)
+            }
+            if (up_live) {
+              const __nv_bfloat16 *m0 = reinterpret_cast<const __nv_bfloat16 *>(&um[k][0]), *m1 = reinterpret_cast<const __nv_bfloat16 *>(&um[k][1]);
+              const __nv_bfloat16 *r0 = reinterpret_cast<const __nv_bfloat16 *>(&ur[k][0]), *r1 = reinterpret_cast<const __nv_bfloat16 *>(&ur[k][1]);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (p.resid) { fa[i] += __bfloat162float(r0[i]); fa[8 + i] += __bfloat162float(r1[i]); }
+                if (p.mask) {
+                  fa[i] = __bfloat162float(m0[i]) > 0.f ? fa[i] * p.mask_scale : 0.f;
+                  fa[8 + i] = __bfloat162float(m1[i]) > 0.f ? fa[8 + i] * p.mask_scale : 0.f;
+                }
+              }
+              store16_bf16(p.pool_out + up_off + (size_t)(2 * cu) * up_plane, up_plane, fa);
+            }
+          }
         }
       } else {
         // EPI_POOL: unit = (row pair k, 16 channels); both rows are stored, their max is reduced with

@@ -194,6 +194,7 @@ struct adp_engine {
   int64_t launches = 0;
   int dbg = 0;
   bool fuse_head = true, fuse_pool = true;   // tcgen05 path only
+  bool fuse_upsum = true;                    // tcgen05 backward: UpSampling2D's 2x2 gradient sum in the data-gradient twin's epilogue (T = 2 layers)
   bool fuse_dropout = true;                  // tcgen05 training forward: hash dropout applied in the producing conv's epilogue
   bool fuse_first = false;                   // tcgen05 inference: first conv computed inside down1_conv2 (conv_tc.cuh, FC variant): bit-identical,
                                              // opt-in.  Kernel time is break-even un-throttled; under the power cap the 3.2 GB less HBM traffic
@@ -363,6 +364,7 @@ ConvTcKernel tc_kernel_lookup(int ntaps, int T, int kys, int epi) {
   ADP_TC_ROWS(9, EPI_HEAD)
   ADP_TC_ROWS(9, EPI_POOL)
   ADP_TC_ROWS(9, EPI_BWD) ADP_TC(9, 1, 0, EPI_BWD)
+  ADP_TC(9, 2, 0, EPI_UPSUM) ADP_TC(9, 2, 1, EPI_UPSUM)
 #undef ADP_TC_ROWS
 #undef ADP_TC
   return nullptr;
@@ -582,6 +584,8 @@ struct EpiSpec {
   float *prob = nullptr;              // EPI_HEAD: probability planes
   const void *resid = nullptr, *mask = nullptr;   // backward (EPI_STORE): see ConvTcParams
   float mask_scale = 1.f;
+  void *up_dst = nullptr;             // EPI_UPSUM: low-resolution gradient (view: up_cgs groups per row, first group up_cg0);
+  int up_cgs = 0, up_cg0 = 0;         // resid / mask above then have ITS layout
   float drop_keep = 1.f;              // EPI_STORE, training forward: hash dropout of the stored tensor fused into the epilogue
   uint64_t drop_seed = 0;             // (keep < 1: on; the output must be a dense tensor whose pair index fits 32 bits)
   const FirstConvFuse *fc = nullptr;  // EPI_POOL of down1_conv2: compute the source tensor (first conv) in the kernel from
@@ -622,6 +626,9 @@ void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label,
   if (epi.mode == EPI_HEAD) {
     ADP_REQUIRE(p.T >= 2 && p.nvar == 1 && p.N == e->cp[0], "head fusion needs the 44-channel full-resolution layer");
     p.head_w = e->w_head.as<float>(); p.head_b = e->b_head.as<float>(); p.prob = epi.prob;
+  } else if (epi.mode == EPI_UPSUM) {
+    ADP_REQUIRE(p.T == 2 && p.oscale == 1 && Ho % 2 == 0 && Wo % 2 == 0 && !p.split, "2x2-sum epilogue needs a two-row item");
+    p.pool_out = reinterpret_cast<__nv_bfloat16 *>(epi.up_dst); p.pool_cgs = epi.up_cgs; p.pool_cg0 = epi.up_cg0;
   } else if (epi.mode == EPI_POOL) {
     ADP_REQUIRE(p.T % 2 == 0 && p.oscale == 1 && Ho % 2 == 0 && Wo % 2 == 0, "pool fusion needs an even row block");
     p.pool_out = epi.pool_dst->as<__nv_bfloat16>(); p.pool_cgs = L.cout_pad / 8; p.pool_cg0 = 0;
@@ -1131,13 +1138,14 @@ int adp_create(int device, int precision, int init_nb, int max_forwards, adp_eng
   for (int nt : {9, 4})
     for (int T : {4, 2, 1})
       for (int kys : {0, 1})
-        for (int epi : {EPI_STORE, EPI_HEAD, EPI_POOL, EPI_BWD})
+        for (int epi : {EPI_STORE, EPI_HEAD, EPI_POOL, EPI_BWD, EPI_UPSUM})
           if (ConvTcKernel k = tc_kernel_lookup(nt, T, kys, epi))
             ADP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   ADP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<9, 4, true, EPI_POOL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   ADP_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (const char *f = getenv("ADP_FUSE_FIRST")) e->fuse_first = atoi(f) != 0;        // A/B runs of whole programs (bench.py)
   if (const char *f = getenv("ADP_FUSE_DROPOUT")) e->fuse_dropout = atoi(f) != 0;
+  if (const char *f = getenv("ADP_FUSE_UPSUM")) e->fuse_upsum = atoi(f) != 0;
   if (const char *d = getenv("ADP_TC_DEBUG")) {
     e->dbg = atoi(d);
     if (e->dbg && !ADP_TC_DEBUG_BUILD) {
@@ -1190,6 +1198,7 @@ int adp_set_option(adp_engine *e, const char *key, int value) {
   std::string k = key;
   if (k == "fuse_first") e->fuse_first = value != 0;
   else if (k == "fuse_dropout") e->fuse_dropout = value != 0;
+  else if (k == "fuse_upsum") e->fuse_upsum = value != 0;
   else if (k == "fuse_head") e->fuse_head = value != 0;
   else if (k == "fuse_pool") e->fuse_pool = value != 0;
   else if (k == "wgrad_simt") e->wgrad_simt = value != 0;

@@ -248,13 +248,17 @@ __global__ void __launch_bounds__(256) upsample2_bwd_kernel(View<T> ghigh, View<
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const RpIndex ri = rp_index(i, glow.W, G, glow.H);
     const int xx = ri.x, gi = ri.g, yy = ri.y, n = ri.n;
-    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a[8];
+    // pairwise: (column 2x: row 2y + row 2y+1) + (column 2x+1: the same) - the order the fused epilogue of the data-gradient twin
+    // (conv_tc.cuh, EPI_UPSUM) can form with one shuffle per value
+    float s[8], a[8], b[8];
+    load8<T>(ghigh.p + ghigh.at(n, 2 * yy, gi, 2 * xx), a);
+    load8<T>(ghigh.p + ghigh.at(n, 2 * yy + 1, gi, 2 * xx), b);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      load8<T>(ghigh.p + ghigh.at(n, 2 * yy + (q >> 1), gi, 2 * xx + (q & 1)), a);
+    for (int k = 0; k < 8; ++k) s[k] = a[k] + b[k];
+    load8<T>(ghigh.p + ghigh.at(n, 2 * yy, gi, 2 * xx + 1), a);
+    load8<T>(ghigh.p + ghigh.at(n, 2 * yy + 1, gi, 2 * xx + 1), b);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s[k] += a[k];
-    }
+    for (int k = 0; k < 8; ++k) s[k] += a[k] + b[k];
     if (resid.p) {
       load8<T>(resid.p + resid.at(n, yy, gi, xx), a);
 #pragma unroll

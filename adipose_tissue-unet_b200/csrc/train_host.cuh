@@ -475,6 +475,17 @@ template <typename T> struct Bwd {
     if (e->prec == ADP_PREC_BF16 && !e->dgrad_simt) {
       const double by = (double)nb * dz.H * dz.W * (L.cin_pad + L.cout_pad) * 2.0;
       EpiSpec epi;
+      if (L.up && e->fuse_upsum && TL.twin.tc.T == 2 && (!mask || (mask->cgs == gin.cgs && mask->cg0 == gin.cg0 && mask->H == gin.H)) &&
+          (!resid || (resid->cgs == gin.cgs && resid->cg0 == gin.cg0 && resid->H == gin.H))) {
+        // UpSampling2D's backward (2x2 sum, second gradient, ReLU'/dropout mask) in the twin's epilogue: the full-resolution
+        // gradient never reaches HBM and upsample2_bwd_kernel is not launched
+        epi.mode = EPI_UPSUM;
+        epi.up_dst = gin.p; epi.up_cgs = gin.cgs; epi.up_cg0 = gin.cg0;
+        epi.mask = mask ? mask->p : nullptr; epi.mask_scale = scale; epi.resid = resid ? resid->p : nullptr;
+        launch_conv_tc(e, TL.twin, "conv_dgrad_tcgen05/" + L.name, fl, (double)nb * dz.H * dz.W * (L.cin_pad / 4 + L.cout_pad) * 2.0, dz.p, dz.H, dz.W,
+                       dz.cgs, dz.cg0, out.p, out.cgs, out.cg0, nb, nb, epi, tr->zeros.as<float>(), 0);
+        return;
+      }
       if (!L.up) {
         ADP_REQUIRE(!mask || (mask->cgs == gin.cgs && mask->cg0 == gin.cg0 && mask->H == gin.H), "mask layout must equal the gradient layout");
         ADP_REQUIRE(!resid || (resid->cgs == gin.cgs && resid->cg0 == gin.cg0 && resid->H == gin.H), "residual layout must equal the gradient layout");

@@ -346,3 +346,32 @@ def test_fused_dropout_is_bit_identical(weights):
     sums_nodrop = np.array(eng.train_forward(x, y), dtype=np.float64)
     assert not np.array_equal(sums_nodrop, res[1][0])
     eng.train_end(); eng.close()
+
+
+@pytest.mark.parametrize("deep_sup", [False, True])
+def test_fused_upsample_backward_is_bit_identical(deep_sup, weights):
+    """bf16 backward: the data-gradient twin of up1_conv1 (two-row items) sums UpSampling2D's 2x2 gradient block in its epilogue
+    (conv_tc.cuh EPI_UPSUM) - values rounded to bf16 as the full-resolution store would have, summed in upsample2_bwd_kernel's
+    order, second gradient (deep-supervision head) and ReLU'/dropout mask applied after: every gradient equals the un-fused
+    backward bit for bit."""
+    n, S = 2, 256
+    x, y = batch(n, S, seed=47)
+    w = A.synth.init_weights(deep_supervision=True) if deep_sup else weights
+    eng = api.Engine(precision="bf16", max_forwards=8)
+    eng.set_weights(w)
+    if deep_sup:
+        eng.train_set_deep_supervision(True)
+    eng.train_begin(n, S, dropout_rate=0.3, seed=5)
+    sums = eng.train_forward(x, y)
+    g = {}
+    for fuse in (0, 1):
+        eng.set_option("fuse_upsum", fuse)
+        eng.train_backward(sums)
+        g[fuse] = eng.train_grads()
+    eng.set_option("fuse_upsum", 1)
+    generic = [k for k in g[0] if not k.startswith(("down1_conv1/", "output_softmax/", "aux_out"))]
+    assert len(generic) >= 40
+    for k in generic:
+        assert np.array_equal(g[0][k], g[1][k]), k
+    assert float(np.abs(g[1]["up2_conv3/kernel"]).max()) > 0
+    eng.train_end(); eng.close()
