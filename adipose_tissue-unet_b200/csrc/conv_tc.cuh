@@ -46,7 +46,12 @@
 //             of up1_conv3 (the 44-channel activation never reaches HBM),
 //   EPI_POOL  MaxPooling2D(2x2) (train_adipose_unet_v3.py:670,674) written next to the skip tensor,
 //   EPI_BWD   data-gradient twin of the training step: (acc + residual) * [mask > 0] * scale, the mask tile staged in
-//             shared memory by a TMA box per item for accumulators up to 96 wide (ConvTcParams::mask_bufs).
+//             shared memory by a TMA box per item for accumulators up to 96 wide (ConvTcParams::mask_bufs),
+//   EPI_UPSUM data-gradient twin of an upsampled conv with two-row items: UpSampling2D's backward (2x2 sum, second gradient,
+//             ReLU'/dropout mask) in the epilogue, the full-resolution gradient is never written,
+//   dropout   (EPI_STORE, training forward) the Dropout that follows the layer, by the counter-based hash of kernels_train.cuh.
+// FC variant (template flag, 512 threads, opt-in): five more warps compute the FIRST conv of the network into the pipeline stages
+// of down1_conv2 (struct FirstConvFuse).  All fused forms are bit-identical to the separate kernels they replace.
 #pragma once
 #include "kernels_simt.cuh"
 #include "ptx.cuh"

@@ -75,8 +75,14 @@ int adp_destroy(adp_engine *e);
 int adp_precision(const adp_engine *e);
 int adp_synchronize(adp_engine *e);
 void *adp_stream(adp_engine *e);            /* the engine's cudaStream_t (for event timing by the caller) */
-/* engine switches for tests and experiments: "fuse_head" (softmax head in the last conv's epilogue),
- * "fuse_pool" (2x2 max-pool in the encoder convs' epilogue) — tcgen05 path only, default 1 */
+/* engine switches for tests and experiments (tcgen05 path only; every fused form is bit-identical to its separate kernels,
+ * tests/test_gpu_forward.py, tests/test_gpu_train.py):
+ *   "fuse_head"    softmax head in the last conv's epilogue (inference)                                    default 1
+ *   "fuse_pool"    2x2 max-pool in the encoder convs' epilogue                                             default 1
+ *   "fuse_dropout" the four Dropout sites in the producing conv's epilogue (training forward)              default 1
+ *   "fuse_upsum"   UpSampling2D's backward in the epilogue of up1_conv1's data-gradient conv               default 1
+ *   "fuse_first"   first conv computed inside down1_conv2 (inference; measured break-even)  default 0
+ * (also "train_accuracy", "train_eval_mode" below) */
 int adp_set_option(adp_engine *e, const char *key, int value);
 
 /* ---- weights ---------------------------------------------------------------------------------
