@@ -327,15 +327,18 @@ def run_ours(args, rank, world, local_rank):
     # within the box-to-box spread.
     fc_res = None
     if rank == 0 and world == 1 and args.precision == "bf16":
-        eng.set_option("fuse_first", 1)
-        step_resident()
-        fsteps = min(args.steps, 5)
-        fdev, _, fres = timed(step_resident, fsteps)
-        eng.set_option("fuse_first", 0)
-        assert fres == res, "first-conv fusion changed the confusion counts"
-        fc_res = {"tiles_per_s": BATCH_TILES * fsteps / fdev, "ms_per_step": fdev / fsteps * 1e3, "steps": fsteps,
-                  "counts_equal_to_default_path": True,
-                  "note": "same step, adp_set_option('fuse_first', 1): first_conv_kernel replaced by stencil warps inside the tcgen05 kernel of down1_conv2"}
+        try:
+            eng.set_option("fuse_first", 1)
+            step_resident()
+            fsteps = min(args.steps, 5)
+            fdev, _, fres = timed(step_resident, fsteps)
+            fc_res = {"tiles_per_s": BATCH_TILES * fsteps / fdev, "ms_per_step": fdev / fsteps * 1e3, "steps": fsteps,
+                      "counts_equal_to_default_path": bool(fres == res),
+                      "note": "same step, adp_set_option('fuse_first', 1): first_conv_kernel replaced by stencil warps inside the tcgen05 kernel of down1_conv2"}
+        except Exception as ex:          # a side measurement must not take the bench line down
+            fc_res = {"error": str(ex)[:200]}
+        finally:
+            eng.set_option("fuse_first", 0)
 
     # whole-slide sliding-window reconstruction at BASELINE.json's own sizes: configs[2] (32768^2 3-channel pseudocoloured
     # slide, 50 % overlap) and configs[4] (16384^2 ECM slide, 75 % overlap), 8-way TTA, tile-row strips sharded over the ranks
