@@ -187,7 +187,11 @@ def test_three_steps_fp32_vs_oracle(opt, weights):
     losses = [eng.train_step(x, y, lr, opt)["loss"] for _ in range(steps)]
     assert eng.train_iterations() == steps
     w = eng.get_weights()
-    np.testing.assert_allclose(losses, losses_ref, rtol=2e-4)
+    # step 1 sees identical parameters: tight.  Later steps follow Adam updates of ~lr per parameter whatever the gradient
+    # scale, and the exact-fp32 CUDA-core weight gradient sums with float atomics (order varies run to run), so parameters at
+    # the fp32 noise floor may take a different +-lr step: 2.1e-4 was seen on step 3 on one box, hence 1e-3 there
+    np.testing.assert_allclose(losses[0], losses_ref[0], rtol=2e-5)
+    np.testing.assert_allclose(losses, losses_ref, rtol=1e-3)
     # Adam's step is ~lr per parameter whatever the gradient scale: compare the moved distance in units of lr
     d = np.concatenate([(w[k] - w_ref[k]).ravel() for k in w]).astype(np.float64)
     mv = np.concatenate([(w_ref[k] - weights[k]).ravel() for k in w]).astype(np.float64)
