@@ -132,6 +132,13 @@ struct ConvTcParams {
   // (= element offset / 8 of the dense output tensor), and rounded again.  drop_thr = 0: off.
   uint32_t drop_thr, drop_salt;
   float drop_inv;
+  // Resident weights (bres = 1; launch_conv_tc turns it on when the packed weight blocks of ALL chunks and variants fit next to
+  // >= 4 activation-only stages): the persistent CTA copies them into shared memory once (nvar * nchunks bulk copies on their own
+  // mbarrier) and a pipeline stage then carries activations only.  Per work item of a 48-channel layer this takes the weight
+  // refill (108 of ~1330 shared-memory wavefront-cycles per chunk, the port that binds these layers - DESIGN 4.1) and 13.8 KB of
+  // L2 reads per chunk off the loop.  Same MMAs on the same operand bytes: results are bit-identical.
+  int bres;
+  uint32_t bres_off, bres_bytes; // byte offset of the resident blocks in dynamic shared memory (128-byte aligned), their total size
   FirstConvFuse fc;              // FC variant only
 };
 
@@ -146,7 +153,12 @@ __host__ __device__ inline size_t tc_block_index(int kys, int ntaps, int N, int 
 
 size_t tc_smem_bytes(const ConvTcParams &p) {   // FC variant: + kFcWinBytes
   // stages | mask tile buffers (EPI_BWD) | mbarriers (2S + 8) + tmem slot | bias (704 floats) | head weights (2*256 + 2 floats)
-  return (size_t)p.S * p.stage_stride + (size_t)p.mask_bufs * p.mask_bytes + (2 * p.S + 6 + 4) * 8 + (704 + 520) * 4;
+  const size_t base = (size_t)p.S * p.stage_stride + (size_t)p.mask_bufs * p.mask_bytes + (2 * p.S + 6 + 4) * 8 + (704 + 520) * 4;
+  return p.bres ? (size_t)p.bres_off + p.bres_bytes : base;
+}
+// where the resident weight blocks start for the current S / mask_bufs (host: call after those are final)
+inline uint32_t tc_bres_offset(const ConvTcParams &p) {
+  return (uint32_t)(((size_t)p.S * p.stage_stride + (size_t)p.mask_bufs * p.mask_bytes + (2 * p.S + 6 + 4) * 8 + (704 + 520) * 4 + 127) & ~(size_t)127);
 }
 constexpr int kFcWinW = 136, kFcWinRows = 8;                     // input window of one item: 8 rows x 132 columns, loaded as a
 constexpr int kFcWinX0 = 4;                                      // box of 136 that starts 4 columns left of the strip (16-byte aligned)
@@ -313,6 +325,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   uint64_t *acc_full = empty + p.S, *acc_empty = acc_full + 2;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 2);
   uint64_t *mask_full = acc_empty + 4, *mask_empty = mask_full + 2;
+  uint64_t *b_full = acc_empty + 3;                               // resident weights have landed (bres)
   float *sbias = reinterpret_cast<float *>(acc_empty + 8);        // [nvar * N] (<= 704 floats)
   float *shead = sbias + 704;                                      // [2 * N] + 2, EPI_HEAD only
   // FC only: [2][kFcWinRows][kFcWinW] input windows (TMA destinations); their barriers are the mask tile's (unused by EPI_POOL)
@@ -347,6 +360,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     for (int i = 0; i < p.S; ++i) { ptx::mbar_init(&full[i], FC ? 1 + kFcWarps : 1); ptx::mbar_init(&empty[i], 2); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 8); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&mask_full[i], 1); ptx::mbar_init(&mask_empty[i], FC ? kFcWarps : 8); }
+    ptx::mbar_init(b_full, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tmap);
     if constexpr (EPI == EPI_BWD || FC) ptx::prefetch_tmap(&tmask);
@@ -366,6 +380,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       long long t_w0 = 0; const long long t_start = clock64();
       int mit = 0;                                            // EPI_BWD: items whose mask tile has been requested
       const size_t blk_elems = p.b_bytes / 2;
+      if (p.bres && item0 < item_end) {                       // all weight blocks once: [variant][chunk] in wbase order
+        const int nblk = p.nvar * p.nchunks;
+        ptx::mbar_expect_tx(b_full, p.bres_bytes);
+        for (int b = 0; b < nblk; ++b)
+          ptx::bulk_load_1d(smem + p.bres_off + (size_t)b * p.b_bytes, p.wpk + (size_t)b * blk_elems, p.b_bytes, b_full);
+      }
       for (int item = item0; item < item_end; item += item_step) {
         int v, n, ty, tx;
         decode_item(p, item, v, n, ty, tx);
@@ -390,7 +410,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&empty[st], ph ^ 1, 1); if (tc_dbg(p, 16)) t_w0 += clock64() - tw; }
           // p.dbg (ADP_TC_DEBUG, timing experiments only - results are wrong): 2 = weights only for the first item,
           // 8 = activations only for the first item, 1 = no epilogue stores, 4 = one MMA per stage, 16 = role timers
-          const bool ld_b = !tc_dbg(p, 2) || item == item0, ld_a = !tc_dbg(p, 8) || item == item0;
+          const bool ld_b = (!tc_dbg(p, 2) || item == item0) && !p.bres, ld_a = !tc_dbg(p, 8) || item == item0;
           ptx::mbar_expect_tx(&full[st], ((ld_a && !FC) ? p.a_tx_bytes : 0u) + (ld_b ? p.b_bytes : 0u));
           int cgc = c * 2;                                     // first channel group of this chunk
           if (p.split) { const int cr = c / 3; cgc = cr * 2 + ((c - cr * 3) == 2 ? p.in_lo : 0); }
@@ -434,6 +454,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const uint32_t n_cols = (uint32_t)p.N;
       const bool mma_all = !tc_dbg(p, 4);
       long long t_m0 = 0, t_m1 = 0, t_m2 = 0; const long long t_mstart = clock64();
+      // first byte (>> 4) of the weight block of (variant, chunk): inside the stage, or in the resident region
+      const uint32_t bres_lo = ((smem0 + p.bres_off) & 0x3FFFFu) >> 4, blk16 = p.b_bytes >> 4, a16 = p.a_bytes >> 4;
+      if (p.bres && item0 < item_end) ptx::mbar_wait(b_full, 0, 15);
       if constexpr (KYS) {
         constexpr int KY = (NTAPS == 9) ? 3 : 2, KX = KY;
         const uint32_t plane_bs = (uint32_t)(KY * p.N) * 16u;  // stacked B: KY*N rows per channel-group plane
@@ -443,7 +466,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 #pragma unroll
         for (int kx = 0; kx < KX; ++kx) {
           a_xs[kx] = (uint32_t)p.tap_xs[kx];                   // pixels == 16-byte units
-          b_blk[kx] = (p.a_bytes + (uint32_t)kx * 2u * plane_bs) >> 4;
+          b_blk[kx] = ((uint32_t)kx * 2u * plane_bs) >> 4;
         }
         const uint32_t id1 = p.idesc_stack[0], id2 = p.idesc_stack[1], id3 = p.idesc_stack[2];
         int it = 0;
@@ -454,11 +477,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           ptx::tc_fence_after();
           const uint32_t d0 = tmem_base + (uint32_t)buf * (uint32_t)T * n_cols;
           const uint32_t v_off = (uint32_t)p.var[item % p.nvar].xs_add;
+          const uint32_t wb0 = bres_lo + (uint32_t)p.var[item % p.nvar].wbase * blk16;
           for (int c = 0; c < p.nchunks; ++c) {
             { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&full[st], ph, 4); if (tc_dbg(p, 16)) t_m1 += clock64() - tw; }
             ptx::tc_fence_after();
             const uint32_t s_lo = ((smem0 + (uint32_t)st * p.stage_stride) & 0x3FFFFu) >> 4;
             const uint32_t sa_lo = s_lo + v_off;
+            const uint32_t sb_lo = p.bres ? wb0 + (uint32_t)c * blk16 : s_lo + a16;
 #pragma unroll
             for (int kx = 0; kx < KX; ++kx) {
               if (kx == 0 && c == 0) {
@@ -470,7 +495,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                     const uint64_t ad = ((uint64_t)desc_hi << 32) |
                                         (uint64_t)(a_lo0 | (sa_lo + a_xs[0] + (uint32_t)(o + kyi) * row_step));
                     const uint64_t bd = ((uint64_t)desc_hi << 32) |
-                                        (uint64_t)(bs_lo0 | (s_lo + b_blk[0] + (uint32_t)(KY - 1 - kyi) * n16));
+                                        (uint64_t)(bs_lo0 | (sb_lo + b_blk[0] + (uint32_t)(KY - 1 - kyi) * n16));
                     if (mma_all || (o | kyi) == 0) ptx::mma_f16_ss(d0 + (uint32_t)o * n_cols, ad, bd, id1, (uint32_t)(kyi != 0));
                   }
               } else {
@@ -483,7 +508,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                   const uint64_t ad = ((uint64_t)desc_hi << 32) |
                                       (uint64_t)(a_lo0 | (sa_lo + a_xs[kx] + (uint32_t)i * row_step));
                   const uint64_t bd = ((uint64_t)desc_hi << 32) |
-                                      (uint64_t)(bs_lo0 | (s_lo + b_blk[kx] + (uint32_t)sl * n16));
+                                      (uint64_t)(bs_lo0 | (sb_lo + b_blk[kx] + (uint32_t)sl * n16));
                   if (mma_all) ptx::mma_f16_ss(d0 + (uint32_t)o_lo * n_cols, ad, bd, cnt == 1 ? id1 : (cnt == 2 ? id2 : id3), 1u);
                 }
               }
@@ -499,7 +524,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       for (int t = 0; t < NTAPS; ++t) {
         a_off[t] = ((uint32_t)p.tap_box[t] * p.a_box_stride + (uint32_t)(p.tap_row[t] * 2) * plane_a +
                     (uint32_t)p.tap_xs[t] * 16u) >> 4;
-        b_off[t] = (p.a_bytes + (uint32_t)t * 2u * plane_b) >> 4;
+        b_off[t] = ((uint32_t)t * 2u * plane_b) >> 4;
       }
       const uint32_t idesc = p.idesc;
       int it = 0;
@@ -510,14 +535,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)buf * (uint32_t)T * n_cols;
         const uint32_t v_off = (uint32_t)p.var[item % p.nvar].xs_add;   // pixels == 16-byte units
+        const uint32_t wb0 = bres_lo + (uint32_t)p.var[item % p.nvar].wbase * blk16;
         for (int c = 0; c < p.nchunks; ++c) {
           { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&full[st], ph, 4); if (tc_dbg(p, 16)) t_m1 += clock64() - tw; }
           ptx::tc_fence_after();
           const uint32_t s_lo = ((smem0 + (uint32_t)st * p.stage_stride) & 0x3FFFFu) >> 4;
           const uint32_t sa_lo = s_lo + v_off;
+          const uint32_t sb_lo = p.bres ? wb0 + (uint32_t)c * blk16 : s_lo + a16;
 #pragma unroll
           for (int t = 0; t < NTAPS; ++t) {
-            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo0 | (s_lo + b_off[t]));
+            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo0 | (sb_lo + b_off[t]));
 #pragma unroll
             for (int r = 0; r < T; ++r) {
               const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo0 | (sa_lo + a_off[t] + (uint32_t)r * row_step));

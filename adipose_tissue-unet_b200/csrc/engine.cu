@@ -200,6 +200,8 @@ struct adp_engine {
                                              // opt-in.  Kernel time is break-even un-throttled; under the power cap the 3.2 GB less HBM traffic
                                              // per 16 forwards gave +0.1..1.4 % in bench.py A/B runs - inside the box-to-box spread, and it moves
                                              // the first conv's time into the dominant kernel (bench.py "first_conv_fusion")
+  bool resident_weights = true;              // tcgen05 convs whose packed weights fit next to >= 4 activation stages keep them in shared
+                                             // memory for the life of the persistent CTA (ConvTcParams::bres); bit-identical
   FirstConvFuse fc_host;                     // its fp32 weights / bias as kernel parameters (filled by pack_all)
   bool kys = true;                           // ky-stacked MMA issue for the N <= 128 layers
   bool split = false;                        // ADP_PREC_BF16X3: hi/lo bf16 activations and weights, three GEMM passes (conv_tc.cuh)
@@ -674,7 +676,23 @@ void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label,
       tmk = &tmap_for(e, epi.mask, Ho, Wo, d_cgs, d_cg0, L.cout_pad, cap, 16, p.N / 8, p.T);
     }
   }
+  // resident weights: all (variant, chunk) blocks once per CTA instead of once per item and chunk, stages carry activations only
+  p.bres = 0; p.bres_off = 0; p.bres_bytes = 0;
+  if (e->resident_weights && !epi.fc) {
+    const size_t wb = (size_t)p.nvar * p.nchunks * p.b_bytes;
+    const uint32_t a_stride = (uint32_t)(((size_t)p.a_bytes + 1023) / 1024 * 1024);
+    const size_t fixed = (size_t)p.mask_bufs * p.mask_bytes + (2 * 8 + 10) * 8 + (704 + 520) * 4 + 256;
+    const size_t total = 226 * 1024;
+    static const int min_stages = getenv("ADP_BRES_MIN_STAGES") ? atoi(getenv("ADP_BRES_MIN_STAGES")) : 4;
+    if (wb + fixed + (size_t)min_stages * a_stride <= total && wb < (1u << 20)) {
+      p.bres = 1; p.bres_bytes = (uint32_t)wb;
+      p.stage_stride = a_stride;
+      p.S = (int)std::min<size_t>(8, (total - wb - fixed) / a_stride);
+      p.bres_off = tc_bres_offset(p);
+    }
+  }
   const size_t smem = tc_smem_bytes(p) + smem_extra;
+  ADP_REQUIRE(smem <= 227 * 1024, "tcgen05 conv: shared-memory plan exceeds 227 KB");
   if (e->dbg & 16) { e->misc.ensure(148 * 8 * 8 + 4096); p.dbg_out = reinterpret_cast<long long *>(e->misc.as<char>() + 4096); }
   e->launch(label.c_str(), fl, by, [&] { kern<<<grid, threads, smem, e->stream>>>(tm, *tmk, p); });
   if (e->dbg & 16) {
@@ -1146,6 +1164,7 @@ int adp_create(int device, int precision, int init_nb, int max_forwards, adp_eng
   if (const char *f = getenv("ADP_FUSE_FIRST")) e->fuse_first = atoi(f) != 0;        // A/B runs of whole programs (bench.py)
   if (const char *f = getenv("ADP_FUSE_DROPOUT")) e->fuse_dropout = atoi(f) != 0;
   if (const char *f = getenv("ADP_FUSE_UPSUM")) e->fuse_upsum = atoi(f) != 0;
+  if (const char *f = getenv("ADP_RESIDENT_WEIGHTS")) e->resident_weights = atoi(f) != 0;
   if (const char *d = getenv("ADP_TC_DEBUG")) {
     e->dbg = atoi(d);
     if (e->dbg && !ADP_TC_DEBUG_BUILD) {
@@ -1199,6 +1218,7 @@ int adp_set_option(adp_engine *e, const char *key, int value) {
   if (k == "fuse_first") e->fuse_first = value != 0;
   else if (k == "fuse_dropout") e->fuse_dropout = value != 0;
   else if (k == "fuse_upsum") e->fuse_upsum = value != 0;
+  else if (k == "resident_weights") e->resident_weights = value != 0;
   else if (k == "fuse_head") e->fuse_head = value != 0;
   else if (k == "fuse_pool") e->fuse_pool = value != 0;
   else if (k == "wgrad_simt") e->wgrad_simt = value != 0;

@@ -82,6 +82,7 @@ void *adp_stream(adp_engine *e);            /* the engine's cudaStream_t (for ev
  *   "fuse_dropout" the four Dropout sites in the producing conv's epilogue (training forward)              default 1
  *   "fuse_upsum"   UpSampling2D's backward in the epilogue of up1_conv1's data-gradient conv               default 1
  *   "fuse_first"   first conv computed inside down1_conv2 (inference; measured break-even)  default 0
+ *   "resident_weights" packed weights of the narrow layers stay in shared memory for the life of a CTA     default 1
  * (also "train_accuracy", "train_eval_mode" below) */
 int adp_set_option(adp_engine *e, const char *key, int value);
 
