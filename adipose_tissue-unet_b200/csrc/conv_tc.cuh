@@ -137,6 +137,8 @@ struct ConvTcParams {
   // mbarrier) and a pipeline stage then carries activations only.  Per work item of a 48-channel layer this takes the weight
   // refill (108 of ~1330 shared-memory wavefront-cycles per chunk, the port that binds these layers - DESIGN 4.1) and 13.8 KB of
   // L2 reads per chunk off the loop.  Same MMAs on the same operand bytes: results are bit-identical.
+  // bres = 2: the grid is a multiple of nvar, so a CTA (items blockIdx.x + k * gridDim.x, variant = item % nvar) only ever sees
+  // variant blockIdx.x % nvar and keeps that variant's blocks alone (the four parity variants of an upsampled conv).
   int bres;
   uint32_t bres_off, bres_bytes; // byte offset of the resident blocks in dynamic shared memory (128-byte aligned), their total size
   FirstConvFuse fc;              // FC variant only
@@ -380,11 +382,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       long long t_w0 = 0; const long long t_start = clock64();
       int mit = 0;                                            // EPI_BWD: items whose mask tile has been requested
       const size_t blk_elems = p.b_bytes / 2;
-      if (p.bres && item0 < item_end) {                       // all weight blocks once: [variant][chunk] in wbase order
-        const int nblk = p.nvar * p.nchunks;
+      if (p.bres && item0 < item_end) {                       // weight blocks once: [variant][chunk] in wbase order, or this CTA's variant
+        const int nblk = (p.bres == 2 ? 1 : p.nvar) * p.nchunks;
+        const __nv_bfloat16 *wsrc = p.wpk + (p.bres == 2 ? (size_t)p.var[item0 % p.nvar].wbase * blk_elems : 0);
         ptx::mbar_expect_tx(b_full, p.bres_bytes);
         for (int b = 0; b < nblk; ++b)
-          ptx::bulk_load_1d(smem + p.bres_off + (size_t)b * p.b_bytes, p.wpk + (size_t)b * blk_elems, p.b_bytes, b_full);
+          ptx::bulk_load_1d(smem + p.bres_off + (size_t)b * p.b_bytes, wsrc + (size_t)b * blk_elems, p.b_bytes, b_full);
       }
       for (int item = item0; item < item_end; item += item_step) {
         int v, n, ty, tx;
@@ -477,7 +480,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           ptx::tc_fence_after();
           const uint32_t d0 = tmem_base + (uint32_t)buf * (uint32_t)T * n_cols;
           const uint32_t v_off = (uint32_t)p.var[item % p.nvar].xs_add;
-          const uint32_t wb0 = bres_lo + (uint32_t)p.var[item % p.nvar].wbase * blk16;
+          const uint32_t wb0 = bres_lo + (p.bres == 2 ? 0u : (uint32_t)p.var[item % p.nvar].wbase * blk16);
           for (int c = 0; c < p.nchunks; ++c) {
             { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&full[st], ph, 4); if (tc_dbg(p, 16)) t_m1 += clock64() - tw; }
             ptx::tc_fence_after();
@@ -535,7 +538,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)buf * (uint32_t)T * n_cols;
         const uint32_t v_off = (uint32_t)p.var[item % p.nvar].xs_add;   // pixels == 16-byte units
-        const uint32_t wb0 = bres_lo + (uint32_t)p.var[item % p.nvar].wbase * blk16;
+        const uint32_t wb0 = bres_lo + (p.bres == 2 ? 0u : (uint32_t)p.var[item % p.nvar].wbase * blk16);
         for (int c = 0; c < p.nchunks; ++c) {
           { const long long tw = tc_dbg(p, 16) ? clock64() : 0; ptx::mbar_wait(&full[st], ph, 4); if (tc_dbg(p, 16)) t_m1 += clock64() - tw; }
           ptx::tc_fence_after();

@@ -679,13 +679,14 @@ void launch_conv_tc(adp_engine *e, const ConvLayer &L, const std::string &label,
   // resident weights: all (variant, chunk) blocks once per CTA instead of once per item and chunk, stages carry activations only
   p.bres = 0; p.bres_off = 0; p.bres_bytes = 0;
   if (e->resident_weights && !epi.fc) {
-    const size_t wb = (size_t)p.nvar * p.nchunks * p.b_bytes;
+    const bool own_variant = p.nvar > 1 && grid % p.nvar == 0;      // a CTA then only meets variant blockIdx.x % nvar
+    const size_t wb = (size_t)(own_variant ? 1 : p.nvar) * p.nchunks * p.b_bytes;
     const uint32_t a_stride = (uint32_t)(((size_t)p.a_bytes + 1023) / 1024 * 1024);
     const size_t fixed = (size_t)p.mask_bufs * p.mask_bytes + (2 * 8 + 10) * 8 + (704 + 520) * 4 + 256;
     const size_t total = 226 * 1024;
     static const int min_stages = getenv("ADP_BRES_MIN_STAGES") ? atoi(getenv("ADP_BRES_MIN_STAGES")) : 4;
     if (wb + fixed + (size_t)min_stages * a_stride <= total && wb < (1u << 20)) {
-      p.bres = 1; p.bres_bytes = (uint32_t)wb;
+      p.bres = own_variant ? 2 : 1; p.bres_bytes = (uint32_t)wb;
       p.stage_stride = a_stride;
       p.S = (int)std::min<size_t>(8, (total - wb - fixed) / a_stride);
       p.bres_off = tc_bres_offset(p);
