@@ -22,6 +22,8 @@
 //   * weights: pre-packed on the host in exactly the shared-memory image of the B operand
 //     ([tap][cin/8][N][8 x bf16] per (variant, chunk)), streamed with one 1-D bulk copy per stage.
 // A stage therefore feeds NTAPS x T MMAs between two mbarrier round trips.
+//   * resident weights (ConvTcParams::bres): where the blocks of all chunks (of the one variant a CTA meets) fit next to >= 4
+//     activation-only stages, they are copied once per CTA and the stages carry activations only.
 //
 // "Variants" make one launch cover (a) the two 176-wide halves of a 352-channel output and
 // (b) the four output parities of UpSampling2D(2x2) + conv3x3 (train_adipose_unet_v3.py:691-692):
