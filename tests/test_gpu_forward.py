@@ -119,6 +119,32 @@ def test_tta_full_256(prec, weights, params):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16x3"])
+def test_known_answer_probe_network(prec):
+    """The CUDA graph against a HAND-DERIVED answer, not against a restatement (tests/known_answer.py): sparse weights turn the
+    network into shifts (dilation 1, 2, 4, 16), 8 x 8 max-pool, x8 nearest upsampling, the six-way Add, the skip-first
+    Concatenate and sigmoid(z1 - z0); with 8-way TTA the same answer goes through the dihedral ops of the reference's own
+    NumPy code (oracle/geometry.py, pinned by the golden vectors)."""
+    import known_answer as KA
+    S = 256
+    img = A.synth.ecm_tile(S, seed=21).astype(np.float32)
+    want = KA.expected_probability(img, MEAN, STD)
+    m = api.AdiposeUNet(precision=prec, max_forwards=8)
+    m.build_model()
+    m.set_weights(KA.probe_weights())
+    tol = {"fp32": 5e-6, "bf16x3": 5e-5, "bf16": 1e-2}[prec]
+    got = m.predict_single(img, MEAN, STD)
+    err = float(np.abs(got - want).max())
+    print(f"known answer {prec}: max|p - hand-derived| = {err:.2e}")
+    assert err <= tol, (prec, err)
+    preds = [deaug(KA.expected_probability(np.ascontiguousarray(aug(img)), MEAN, STD).astype(np.float32))
+             for aug, deaug in G.TTA_MODES["full"]]
+    want_tta = G.tta_mean(preds)
+    got_tta, _ = m.predict(img, MEAN, STD, use_tta=True, tta_mode="full")
+    assert float(np.abs(got_tta - want_tta).max()) <= tol, prec
+    assert float(np.abs(want_tta - want.astype(np.float32)).max()) > 0.05      # the probe is not dihedrally symmetric
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "bf16x3"])
 def test_batch_and_modes_128(prec, weights, params):
     S = 128
     tiles = A.synth.ecm_tiles(5, S, seed=30)
