@@ -460,7 +460,8 @@ def run_ours(args, rank, world, local_rank):
                                        "softmax head, TTA mean, threshold 0.5, TP/FP/FN/TN vs synthetic masks",
                            "tiles_per_step_per_gpu": BATCH_TILES, "tta": "full(8)", "precision": args.precision,
                            "weights": "random init seed 865 (Glorot x sqrt2)", "parallelism": f"tile-sharded x{world}, no collective",
-                           "l2": "activation working set per step ~13 GB >> 126 MB L2 (no flush needed)",
+                           "forwards_per_launch": args.max_forwards,
+                           "l2": f"activation working set per launch chunk ~{0.84 * args.max_forwards:.0f} GB >> 126 MB L2 (no flush needed)",
                            "wsi_mpx_per_s_equiv_no_overlap": value * TILE * TILE / 1e6},
                 "e2e": {"value": tiles_total / e2e_dev, "unit": UNIT,
                         "h2d_bytes_per_step": int(tiles_pin.numel() * 4 + masks_pin.numel()),
@@ -522,7 +523,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16_simt", "bf16x3"])
-    ap.add_argument("--max-forwards", type=int, default=16)
+    ap.add_argument("--max-forwards", type=int, default=32,
+                    help="U-Net forwards per kernel launch (activation arena = 0.88 GB x this); 32 measured +0.6 %% over 16 "
+                         "(profiles/r2_max_forwards_ab.txt)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-x3", action="store_true", help="skip the secondary bf16x3 (<= 1e-4 path) measurement")
     ap.add_argument("--train-batch", type=int, default=8, help="tiles per GPU of the secondary training-step run (0 = skip)")
@@ -530,7 +533,7 @@ def main():
     ap.add_argument("--wsi-blend", default="gaussian", choices=["gaussian", "linear", "hann"],
                     help="blend window of the WSI run: gaussian / linear are the reference's blenders, hann is the labelled extension")
     ap.add_argument("--wsi", default="full", choices=["full", "small", "none"],
-                    help="whole-slide runs: full = configs[2] (32768^2 RGB, 50 %) and configs[4] (16384^2, 75 %), small = 8192^2, none")
+                    help="whole-slide runs: full = configs[2] (32768^2 RGB, 50 %%) and configs[4] (16384^2, 75 %%), small = 8192^2, none")
     ap.add_argument("--wsi-reps", type=int, default=3, help="timed repetitions of every whole-slide case")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
