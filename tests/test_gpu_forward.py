@@ -207,7 +207,7 @@ def test_first_conv_fusion_is_bit_identical(weights):
             np.testing.assert_array_equal(out[1], out[0], err_msg=f"S={S} {kind}")
             np.testing.assert_array_equal(d1[1], d1[0], err_msg=f"S={S} {kind} down1_conv2")
     finally:
-        eng.set_option("fuse_first", 1)
+        eng.set_option("fuse_first", 0)          # back to the default path (the one bench.py's headline times)
 
 
 def test_mask_dice_on_trained_weights(weights):
