@@ -2,6 +2,7 @@
 symbol include/adipose_b200.h declares; no compute call is made (no GPU here)."""
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -82,3 +83,11 @@ def test_host_geometry_matches_oracle():
     m = api.metrics_from_counts(10, 3, 2, 85)
     assert m == G.metrics_from_counts(10, 3, 2, 85)
     assert api.metrics_from_counts(0, 0, 0, 7) == G.metrics_from_counts(0, 0, 0, 7)
+
+
+def test_bench_help_renders():
+    """argparse formats help strings with %: an unescaped per-cent sign makes `bench.py --help` raise."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert "--max-forwards" in r.stdout and "--impl" in r.stdout
