@@ -47,3 +47,19 @@ def test_single_tap_conv_is_a_shift_in_the_cross_correlation_direction():
                 got_t = torch.nn.functional.conv2d(torch.from_numpy(x)[None, None], torch.from_numpy(k).permute(3, 2, 0, 1),
                                                    padding=d, dilation=d)[0, 0].numpy()
                 assert np.array_equal(got_np, want) and np.array_equal(got_t, want), (d, ky, kx)
+
+
+def test_bilinear_resize_half_pixel_known_values():
+    """tf.image.resize(..., 'bilinear') of the deep-supervision heads (train_adipose_unet_v3.py:716-726) samples at half-pixel
+    centres without antialiasing: doubling [0, 1] gives [0, 0.25, 0.75, 1] (edge clamp), doubling [0, 4, 8] gives
+    [0, 1, 3, 5, 7, 8] - written down by hand, checked on both restatements."""
+    a = np.array([[0.0, 1.0], [0.0, 1.0]])
+    want = np.tile(np.array([0.0, 0.25, 0.75, 1.0]), (4, 1))
+    got_np = UN.resize_bilinear_half_pixel(a[None], 4)[0]
+    got_t = torch.nn.functional.interpolate(torch.from_numpy(a)[None, None], size=(4, 4), mode="bilinear", align_corners=False)[0, 0].numpy()
+    assert np.allclose(got_np, want, atol=1e-12) and np.allclose(got_t, want, atol=1e-12)
+    b = np.tile(np.array([0.0, 4.0, 8.0]), (3, 1))
+    want_b = np.tile(np.array([0.0, 1.0, 3.0, 5.0, 7.0, 8.0]), (6, 1))
+    assert np.allclose(UN.resize_bilinear_half_pixel(b[None], 6)[0], want_b, atol=1e-12)
+    got_tb = torch.nn.functional.interpolate(torch.from_numpy(b)[None, None], size=(6, 6), mode="bilinear", align_corners=False)[0, 0].numpy()
+    assert np.allclose(got_tb, want_b, atol=1e-12)
